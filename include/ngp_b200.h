@@ -1,0 +1,295 @@
+/* ngp_b200.h — C-ABI of libngp_b200.so, the B200-native (sm_100a) drop-in for instant-ngp's NeRF hot path.
+ *
+ * Two nested boundaries:
+ *
+ *   B1  op level    — replaces what tiny-cuda-nn's `tcnn::cpp::Module` vtable offers
+ *                     (dependencies/tiny-cuda-nn/include/tiny-cuda-nn/cpp_api.h:92-125) plus the NeRF kernels
+ *                     Testbed launches directly (src/testbed_nerf.cu).  All pointers are DEVICE pointers owned
+ *                     by the caller, matrices are sample-contiguous ("column major [dims x n]", cpp_api.cu:82-83),
+ *                     every call is asynchronous on the given stream.
+ *   B2  app level   — a `Testbed` handle mirroring the subset of `pyngp.Testbed` (src/python_api.cu:439-853) that
+ *                     the NeRF path touches: create_empty_nerf_dataset / set_image / set_camera_*, reload_network_*,
+ *                     train, render, density grid, snapshot of params.
+ *
+ * Conventions
+ *   - plain C types only; `stream` is a cudaStream_t passed as void*.
+ *   - every function returns 0 on success, non-zero on failure; ngp_last_error() returns the message
+ *     (the reference throws std::runtime_error: tiny-cuda-nn/common_host.h:71-111).
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails with an error.
+ */
+#ifndef NGP_B200_H
+#define NGP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NGP_MAX_LEVELS 32u
+#define NGP_BATCH_GRANULARITY 256u /* tiny-cuda-nn common.h:246 BATCH_SIZE_GRANULARITY */
+#define NGP_NERF_GRIDSIZE 128u     /* nerf_device.cuh:25 */
+#define NGP_NERF_CASCADES 8u       /* nerf_device.cuh:30 */
+#define NGP_NERF_STEPS 1024u       /* nerf_device.cuh:29 */
+#define NGP_LOSS_SCALE 128.0f      /* neural-graphics-primitives/common.h LOSS_SCALE() */
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Descriptors (plain data, filled by ngp_*_desc_init)
+ * ------------------------------------------------------------------------------------------------------------- */
+
+/* Multiresolution hash grid — mirrors GridEncodingTemplated's constructor arithmetic
+ * (tiny-cuda-nn/encodings/grid.h:673-737) and grid_scale/grid_resolution (common_device.h:886-895). */
+typedef struct ngp_grid_desc {
+	uint32_t n_levels;
+	uint32_t n_features_per_level; /* 2 or 4 */
+	uint32_t log2_hashmap_size;
+	uint32_t base_resolution;
+	float per_level_scale;
+	uint32_t n_params;                     /* = offsets[n_levels] * n_features_per_level */
+	uint32_t offsets[NGP_MAX_LEVELS + 1];  /* in grid entries, as ParamsOffsetTable */
+	uint32_t resolutions[NGP_MAX_LEVELS];
+	float scales[NGP_MAX_LEVELS];
+} ngp_grid_desc;
+
+/* NerfNetwork (include/neural-graphics-primitives/nerf_network.h:81-101):
+ *   pos[3] -HashGrid-> 32 -[64 x n_hidden_density, ReLU]-> 16 (row 0 = raw density)
+ *   [density out(16) | SH4(dir)(16)] -[64 x n_hidden_rgb, ReLU]-> 16 (rows 0..2 = raw rgb)
+ * Flat parameter order: density MLP | rgb MLP | hash grid (nerf_network.h:357-372); weights row-major [out x in]. */
+typedef struct ngp_nerf_desc {
+	ngp_grid_desc grid;
+	uint32_t n_hidden_density; /* configs/nerf/base.json: 1 */
+	uint32_t n_hidden_rgb;     /* configs/nerf/base.json: 2 */
+	uint32_t density_mlp_offset;
+	uint32_t rgb_mlp_offset;
+	uint32_t grid_offset;
+	uint32_t n_mlp_params;     /* = grid_offset: "matrix params" for the optimizer (adam.h:150-155) */
+	uint32_t n_params;
+} ngp_nerf_desc;
+
+typedef enum ngp_activation { NGP_ACT_NONE = 0, NGP_ACT_RELU = 1, NGP_ACT_LOGISTIC = 2, NGP_ACT_EXPONENTIAL = 3 } ngp_activation;
+typedef enum ngp_loss_type { NGP_LOSS_L2 = 0, NGP_LOSS_L1 = 1, NGP_LOSS_MAPE = 2, NGP_LOSS_SMAPE = 3, NGP_LOSS_HUBER = 4, NGP_LOSS_LOGL1 = 5, NGP_LOSS_RELATIVE_L2 = 6 } ngp_loss_type;
+typedef enum ngp_lens_mode { NGP_LENS_PERSPECTIVE = 0, NGP_LENS_OPENCV = 1 } ngp_lens_mode;
+typedef enum ngp_image_type { NGP_IMAGE_NONE = 0, NGP_IMAGE_BYTE = 1, NGP_IMAGE_HALF = 2, NGP_IMAGE_FLOAT = 3 } ngp_image_type;
+typedef enum ngp_color_space { NGP_COLOR_LINEAR = 0, NGP_COLOR_SRGB = 1 } ngp_color_space;
+
+/* One training view: TrainingImageMetadata + TrainingXForm.start (nerf_device.cuh:45-60, common.h:189-194).
+ * xform is the 4x3 camera-to-world matrix in ngp convention, column major: [right | up | forward | origin]. */
+typedef struct ngp_train_view {
+	const void* pixels; /* device pointer, RGBA, layout per image_type */
+	uint32_t image_type;
+	int32_t width, height;
+	float focal_x, focal_y;
+	float principal_x, principal_y; /* in [0,1] */
+	uint32_t lens_mode;
+	float lens_params[4]; /* k1 k2 p1 p2 */
+	float xform[12];
+} ngp_train_view;
+
+/* Exponential-stepping constants, evaluated once on the host with ngp_detmath.h so the device march and the oracle
+ * see the same values (nerf_device.cuh:379-421 recomputes them per call). */
+typedef struct ngp_march_consts {
+	float cone_angle;
+	float log1p_c, a, b, at, bt; /* valid when cone_angle > 1e-5 */
+} ngp_march_consts;
+
+typedef struct ngp_nerf_train_cfg {
+	float aabb_min[3], aabb_max[3];
+	uint32_t max_cascade; /* testbed_nerf.cu:2433-2436 */
+	ngp_march_consts march;
+	uint32_t snap_to_pixel_centers;
+	uint32_t random_bg_color;
+	uint32_t linear_colors;
+	uint32_t color_space;
+	float background_color[3];
+	uint32_t loss_type;
+	uint32_t rgb_activation;     /* default Logistic (testbed.h) */
+	uint32_t density_activation; /* default Exponential */
+	float near_distance;
+	float loss_scale;
+} ngp_nerf_train_cfg;
+
+/* Counters written by the training sample generator / loss kernel (NerfCounters, testbed.h). */
+typedef struct ngp_nerf_counters {
+	uint32_t n_rays;              /* rays that produced >= 1 sample */
+	uint32_t n_samples;           /* before compaction */
+	uint32_t n_samples_compacted; /* after compaction, not clamped */
+	uint32_t pad;
+} ngp_nerf_counters;
+
+typedef struct ngp_adam_cfg {
+	float learning_rate, beta1, beta2, epsilon, l2_reg; /* l2_reg on matrix params only (adam.h:91-95) */
+	float loss_scale;
+	float ema_decay;    /* ema.h */
+	uint32_t ema_step;  /* 1-based optimizer step, for EMA debiasing */
+	uint32_t optimize_matrix_params, optimize_non_matrix_params;
+} ngp_adam_cfg;
+
+const char* ngp_last_error(void);
+int ngp_version(void);
+int ngp_device_count(void);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * B1 — descriptors and parameter initialisation (host only)
+ * ------------------------------------------------------------------------------------------------------------- */
+
+/* per_level_scale <= 0: derive as Testbed::reset_network does (src/testbed.cu:4241-4255) from desired_resolution
+ * (2048) * aabb_scale. */
+int ngp_grid_desc_init(ngp_grid_desc* g, uint32_t n_levels, uint32_t n_features_per_level, uint32_t log2_hashmap_size,
+	uint32_t base_resolution, float per_level_scale, uint32_t aabb_scale);
+int ngp_nerf_desc_init(ngp_nerf_desc* d, const ngp_grid_desc* g, uint32_t n_hidden_density, uint32_t n_hidden_rgb);
+/* cone_angle_constant = aabb_scale <= 1 ? 0 : 1/256 (testbed_nerf.cu:2440). */
+int ngp_march_consts_init(ngp_march_consts* m, float cone_angle);
+/* Trainer::initialize_params (trainer.h:69-87): Xavier-uniform MLPs from a host pcg32, hash grid U(-1e-4, 1e-4) with the
+ * GPU fill pattern of random.h:40-67.  Writes fp32 master params (host pointer). */
+int ngp_nerf_init_params_host(const ngp_nerf_desc* d, uint64_t seed, float* params_fp32_host);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * B1 — network ops (device pointers)
+ * ------------------------------------------------------------------------------------------------------------- */
+
+/* ≙ NerfNetwork::inference_mixed_precision (nerf_network.h:105-139) fused into one kernel.
+ * coords: n x 7 floats (NerfCoordinate: pos.xyz, dt, dir.xyz; nerf_device.cuh:176-202), params: fp16 flat buffer,
+ * out: n x out_stride halves, columns 0..2 raw rgb, 3 raw density (out_stride = 16 reproduces padded_output_width). */
+int ngp_nerf_inference(const ngp_nerf_desc* d, void* stream, uint32_t n, const float* coords, const void* params_fp16,
+	void* out_fp16, uint32_t out_stride);
+
+/* ≙ NerfNetwork::density (nerf_network.h:270-280): hash grid + density MLP only. positions: n x pos_stride floats
+ * (NerfPosition, pos_stride >= 3), out: n halves (raw density). */
+int ngp_nerf_density(const ngp_nerf_desc* d, void* stream, uint32_t n, const float* positions, uint32_t pos_stride,
+	const void* params_fp16, void* out_fp16);
+
+/* ≙ Trainer::training_step with external dL/dy (trainer.h:254-357 → NerfNetwork::forward_impl/backward_impl):
+ * forward + backward over n samples (n % 128 == 0), accumulating dL/dparams into grads_fp16 (same flat layout as
+ * params; fp16 like the reference's grad_t for F >= 2, grid.h:660-671).  The caller zeroes grads (ngp_optimizer_step
+ * does it as it consumes them).  dL_dout: n x 4 halves (d rgb raw x3, d density raw), already loss-scaled.
+ * out_fp16 (optional, may be NULL): n x 4 halves forward output. */
+int ngp_nerf_forward_backward(const ngp_nerf_desc* d, void* stream, uint32_t n, const float* coords, const void* params_fp16,
+	const void* dL_dout_fp16, void* grads_fp16, void* out_fp16);
+
+/* Hash-grid encoding alone (tests, image/SDF style use): out n x (L*F) halves, sample-contiguous. ≙ kernel_grid (grid.h:48-212). */
+int ngp_grid_encode(const ngp_grid_desc* g, void* stream, uint32_t n, const float* positions, uint32_t pos_stride,
+	const void* grid_fp16, void* out_fp16);
+
+/* ≙ Ema{ExponentialDecay{Adam}}::step (adam.h:48-127, ema.h:44-77): one fused pass; reads and ZEROES grads_fp16. */
+int ngp_optimizer_step(const ngp_nerf_desc* d, void* stream, const ngp_adam_cfg* cfg, float* params_fp32, void* params_fp16,
+	void* params_ema_fp16, void* grads_fp16, float* first_moments, float* second_moments, uint32_t* param_steps);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * B1 — NeRF ray march / compaction / accumulation (device pointers)
+ * ------------------------------------------------------------------------------------------------------------- */
+
+/* ≙ generate_training_samples_nerf (testbed_nerf.cu:691-849).  rng_state/rng_inc: the Testbed pcg32 by value.
+ * Outputs: ray_indices[n_rays], rays (6 floats o,d per ray), numsteps[2*n_rays] (count, base), coords[max_samples x 7].
+ * counters must be zeroed by the caller.  Slot order is deterministic here (warp-ordered reservation), unlike the
+ * reference's per-thread atomics; compare as a map ray_id -> (count). */
+int ngp_nerf_generate_training_samples(void* stream, uint32_t n_rays, uint32_t n_rays_total, uint64_t rng_state, uint64_t rng_inc,
+	const ngp_nerf_train_cfg* cfg, const ngp_train_view* views_dev, uint32_t n_views, const uint8_t* density_grid_bitfield,
+	uint32_t max_samples, ngp_nerf_counters* counters_dev, uint32_t* ray_indices, float* rays, uint32_t* numsteps, float* coords);
+
+/* ≙ compute_loss_kernel_train_nerf (testbed_nerf.cu:852-1180): composite, loss, compaction, dL/doutput.
+ * network_output: n_samples x 4 halves. Writes coords_compacted [max_compacted x 7], dloss [max_compacted x 4 halves],
+ * loss_per_ray[n_rays] (may be NULL). */
+int ngp_nerf_compute_loss(void* stream, uint32_t n_rays, uint32_t n_rays_total, uint64_t rng_state, uint64_t rng_inc,
+	const ngp_nerf_train_cfg* cfg, const ngp_train_view* views_dev, uint32_t n_views, const void* network_output_fp16,
+	uint32_t max_compacted, ngp_nerf_counters* counters_dev, const uint32_t* ray_indices, const float* rays, uint32_t* numsteps,
+	const float* coords, float* coords_compacted, void* dloss_fp16, float* loss_per_ray, const float* mean_density_dev);
+
+/* ≙ fill_rollover_and_rescale + fill_rollover (common_device.h:1114-1135, testbed_nerf.cu:3298-3306). */
+int ngp_nerf_fill_rollover(void* stream, uint32_t target_batch, const ngp_nerf_counters* counters_dev, float* coords_compacted,
+	void* dloss_fp16);
+
+/* ≙ update_density_grid_nerf + update_density_grid_mean_and_bitfield (testbed_nerf.cu:2476-2633).
+ * density_grid: 128^3 * (max_cascade+1) floats, bitfield: 128^3 * 8 / 8 bytes, mean: 1 float, scratch sized by
+ * ngp_nerf_density_grid_scratch_bytes().  step 0 additionally requires the views (mark_untrained_density_grid). */
+size_t ngp_nerf_density_grid_scratch_bytes(uint32_t max_cascade);
+int ngp_nerf_update_density_grid(const ngp_nerf_desc* d, void* stream, const ngp_nerf_train_cfg* cfg, const void* params_fp16,
+	uint64_t* grid_rng_state_inout, uint64_t grid_rng_inc, uint32_t training_step, uint32_t ema_step, float decay,
+	const ngp_train_view* views_dev, uint32_t n_views, float* density_grid, uint8_t* bitfield, float* mean_density, void* scratch);
+/* threshold + 7-level max-pool only (after loading a grid). */
+int ngp_nerf_update_bitfield(void* stream, uint32_t max_cascade, const float* density_grid, uint8_t* bitfield, float* mean_density);
+
+/* ≙ render_nerf (testbed_nerf.cu:1894-2150), Shade mode, pinhole or OpenCV camera, one sample per pixel.
+ * camera: 4x3 column-major camera-to-world (ngp convention); rows [y0, y1) are rendered (tile sharding).
+ * rgba: H x W x 4 floats (linear, premultiplied), depth: H x W floats; both full-frame pointers. */
+typedef struct ngp_render_cfg {
+	int32_t width, height;
+	float focal_x, focal_y;   /* pixels */
+	float screen_x, screen_y; /* principal point in [0,1] */
+	float camera[12];
+	float aabb_min[3], aabb_max[3];         /* training aabb */
+	float render_aabb_min[3], render_aabb_max[3];
+	uint32_t max_cascade;
+	ngp_march_consts march;
+	uint32_t rgb_activation, density_activation;
+	float min_transmittance;  /* 0.01 */
+	uint32_t spp_index;       /* sample index; pixel centres are snapped (snap_to_pixel_centers = true) */
+	float near_distance;
+} ngp_render_cfg;
+size_t ngp_nerf_render_scratch_bytes(int32_t width, int32_t rows);
+int ngp_nerf_render(const ngp_nerf_desc* d, void* stream, const ngp_render_cfg* cfg, int32_t y0, int32_t y1, const void* params_fp16,
+	const uint8_t* density_grid_bitfield, float* rgba, float* depth, void* scratch, uint32_t* n_steps_total_dev);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * B2 — Testbed handle (≙ pyngp.Testbed, src/python_api.cu:439-853; Testbed::train src/testbed.cu:4561-4647)
+ * ------------------------------------------------------------------------------------------------------------- */
+typedef struct ngp_testbed ngp_testbed;
+
+ngp_testbed* ngp_testbed_create(int device, void* stream);
+void ngp_testbed_destroy(ngp_testbed* t);
+/* python_api.cu:444 create_empty_nerf_dataset(n_images, aabb_scale, is_hdr) */
+int ngp_testbed_create_empty_nerf_dataset(ngp_testbed* t, uint32_t n_images, uint32_t aabb_scale);
+/* python_api.cu:809-853 nerf.training.set_image / set_camera_extrinsics / set_camera_intrinsics.
+ * rgba_host: w*h*4 float32, straight alpha, linear colour; stored premultiplied fp16 like the loader
+ * (common_device.cuh:698-735). convert_to_ngp applies nerf_matrix_to_ngp (nerf_loader.h:97-116). */
+int ngp_testbed_set_image(ngp_testbed* t, uint32_t idx, const float* rgba_host, int32_t w, int32_t h);
+int ngp_testbed_set_camera_extrinsics(ngp_testbed* t, uint32_t idx, const float* cam_to_world_3x4_rowmajor, int convert_to_ngp);
+int ngp_testbed_set_camera_intrinsics(ngp_testbed* t, uint32_t idx, float fx, float fy, float cx, float cy, float k1, float k2,
+	float p1, float p2);
+/* reload_network_from_json / _from_file (python_api.cu:543-550): the tiny-cuda-nn style config
+ * (configs/nerf/base.json); unsupported otypes are rejected. */
+int ngp_testbed_reload_network_from_json(ngp_testbed* t, const char* json_text);
+int ngp_testbed_reload_network_from_file(ngp_testbed* t, const char* path);
+int ngp_testbed_set_seed(ngp_testbed* t, uint64_t seed);
+int ngp_testbed_set_option(ngp_testbed* t, const char* name, double value); /* nerf.training.* knobs by name */
+double ngp_testbed_get_option(ngp_testbed* t, const char* name);
+/* Testbed::train(batch_size): density-grid prep on the reference's schedule, one training step, optimizer step. */
+int ngp_testbed_train(ngp_testbed* t, uint32_t batch_size);
+/* Split form for data-parallel training: grads of this rank's ray shard, then (after the caller's all-reduce over
+ * ngp_testbed_grads()) the optimizer step.  rank/world partition the global ray batch. */
+int ngp_testbed_set_dp(ngp_testbed* t, uint32_t rank, uint32_t world);
+int ngp_testbed_train_compute_grads(ngp_testbed* t, uint32_t batch_size);
+int ngp_testbed_train_apply_grads(ngp_testbed* t);
+void* ngp_testbed_grads(ngp_testbed* t);          /* device fp16 [n_params] */
+void* ngp_testbed_params(ngp_testbed* t);         /* device fp16 [n_params] (training params) */
+void* ngp_testbed_params_inference(ngp_testbed* t);/* device fp16 EMA params */
+float* ngp_testbed_params_fp32(ngp_testbed* t);
+uint32_t* ngp_testbed_dp_counters(ngp_testbed* t); /* device u32[4]: rays, samples, compacted, pad — summed across ranks by the caller */
+uint32_t ngp_testbed_n_params(ngp_testbed* t);
+uint32_t ngp_testbed_training_step(ngp_testbed* t);
+float ngp_testbed_loss(ngp_testbed* t);
+int ngp_testbed_get_counters(ngp_testbed* t, uint32_t* rays_per_batch, uint32_t* measured_batch_size,
+	uint32_t* measured_batch_size_before_compaction);
+int ngp_testbed_get_desc(ngp_testbed* t, ngp_nerf_desc* out);
+/* params exchange (host pointers), the payload of Trainer::serialize (trainer.h:442-455). */
+int ngp_testbed_set_params_fp32(ngp_testbed* t, const float* params_host, uint32_t n);
+int ngp_testbed_get_params_fp16(ngp_testbed* t, void* params_host_fp16, uint32_t n, int inference_params);
+int ngp_testbed_get_density_grid(ngp_testbed* t, float* grid_host, uint32_t n, uint8_t* bitfield_host, uint32_t n_bitfield_bytes);
+int ngp_testbed_set_density_grid(ngp_testbed* t, const float* grid_host, uint32_t n);
+/* render(width, height, spp=1, linear=true) into host buffers: rgba H*W*4 floats, depth H*W floats (may be NULL).
+ * camera_3x4: ngp-convention camera-to-world, row major [3][4]. rows [y0,y1) only (pass 0,height for all). */
+int ngp_testbed_render(ngp_testbed* t, int32_t width, int32_t height, const float* camera_3x4_rowmajor, float focal_x, float focal_y,
+	float cx, float cy, int32_t y0, int32_t y1, float* rgba_host, float* depth_host, uint32_t* n_steps_total);
+/* device-resident variant: rgba_dev / depth_dev are device buffers of the full frame. */
+int ngp_testbed_render_device(ngp_testbed* t, int32_t width, int32_t height, const float* camera_3x4_rowmajor, float focal_x,
+	float focal_y, float cx, float cy, int32_t y0, int32_t y1, float* rgba_dev, float* depth_dev);
+int ngp_testbed_save_snapshot(ngp_testbed* t, const char* path);
+int ngp_testbed_load_snapshot(ngp_testbed* t, const char* path);
+int ngp_testbed_sync(ngp_testbed* t);
+/* number of kernel launches issued by this library since load (bench.py's gpu_launches). */
+uint64_t ngp_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NGP_B200_H */

@@ -1,0 +1,153 @@
+// json_mini.h — a small recursive-descent JSON reader for network configs (configs/nerf/base.json style).
+// The reference parses these with nlohmann::json and tolerates comments (src/testbed.cu:304); so does this.
+#pragma once
+
+#include <cctype>
+#include <cstdlib>
+#include <map>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace ngpb {
+
+struct Json {
+	enum Type { Null, Bool, Number, String, Array, Object } type = Null;
+	bool b = false;
+	double num = 0.0;
+	std::string str;
+	std::vector<Json> arr;
+	std::map<std::string, Json> obj;
+
+	bool contains(const std::string& k) const { return type == Object && obj.count(k) > 0; }
+	const Json& at(const std::string& k) const {
+		auto it = obj.find(k);
+		if (type != Object || it == obj.end()) throw std::runtime_error("json: missing key '" + k + "'");
+		return it->second;
+	}
+	double value(const std::string& k, double def) const { return contains(k) && obj.at(k).type == Number ? obj.at(k).num : def; }
+	std::string value(const std::string& k, const std::string& def) const { return contains(k) && obj.at(k).type == String ? obj.at(k).str : def; }
+	const Json& sub(const std::string& k) const {
+		static const Json empty{};
+		return contains(k) ? obj.at(k) : empty;
+	}
+};
+
+class JsonParser {
+public:
+	explicit JsonParser(const std::string& text) : s(text) {}
+	Json parse() {
+		Json v = value();
+		skip();
+		if (p != s.size()) fail("trailing characters");
+		return v;
+	}
+
+private:
+	const std::string& s;
+	size_t p = 0;
+	[[noreturn]] void fail(const std::string& m) { throw std::runtime_error("json parse error at byte " + std::to_string(p) + ": " + m); }
+	void skip() {
+		for (;;) {
+			while (p < s.size() && std::isspace((unsigned char)s[p])) ++p;
+			if (p + 1 < s.size() && s[p] == '/' && s[p + 1] == '/') {
+				while (p < s.size() && s[p] != '\n') ++p;
+			} else if (p + 1 < s.size() && s[p] == '/' && s[p + 1] == '*') {
+				p += 2;
+				while (p + 1 < s.size() && !(s[p] == '*' && s[p + 1] == '/')) ++p;
+				p += 2;
+			} else {
+				break;
+			}
+		}
+	}
+	Json value() {
+		skip();
+		if (p >= s.size()) fail("unexpected end");
+		const char c = s[p];
+		if (c == '{') return object();
+		if (c == '[') return array();
+		if (c == '"') {
+			Json j;
+			j.type = Json::String;
+			j.str = string();
+			return j;
+		}
+		if (s.compare(p, 4, "true") == 0) { p += 4; Json j; j.type = Json::Bool; j.b = true; return j; }
+		if (s.compare(p, 5, "false") == 0) { p += 5; Json j; j.type = Json::Bool; j.b = false; return j; }
+		if (s.compare(p, 4, "null") == 0) { p += 4; return Json{}; }
+		char* end = nullptr;
+		const double d = std::strtod(s.c_str() + p, &end);
+		if (end == s.c_str() + p) fail("unexpected token");
+		p = (size_t)(end - s.c_str());
+		Json j;
+		j.type = Json::Number;
+		j.num = d;
+		return j;
+	}
+	std::string string() {
+		++p;
+		std::string out;
+		while (p < s.size() && s[p] != '"') {
+			if (s[p] == '\\' && p + 1 < s.size()) {
+				++p;
+				switch (s[p]) {
+					case 'n': out += '\n'; break;
+					case 't': out += '\t'; break;
+					case 'r': out += '\r'; break;
+					default: out += s[p]; break;
+				}
+			} else {
+				out += s[p];
+			}
+			++p;
+		}
+		if (p >= s.size()) fail("unterminated string");
+		++p;
+		return out;
+	}
+	Json array() {
+		Json j;
+		j.type = Json::Array;
+		++p;
+		skip();
+		if (p < s.size() && s[p] == ']') { ++p; return j; }
+		for (;;) {
+			j.arr.push_back(value());
+			skip();
+			if (p < s.size() && s[p] == ',') { ++p; continue; }
+			if (p < s.size() && s[p] == ']') { ++p; break; }
+			fail("expected , or ]");
+		}
+		return j;
+	}
+	Json object() {
+		Json j;
+		j.type = Json::Object;
+		++p;
+		skip();
+		if (p < s.size() && s[p] == '}') { ++p; return j; }
+		for (;;) {
+			skip();
+			if (p >= s.size() || s[p] != '"') fail("expected key");
+			const std::string k = string();
+			skip();
+			if (p >= s.size() || s[p] != ':') fail("expected :");
+			++p;
+			j.obj[k] = value();
+			skip();
+			if (p < s.size() && s[p] == ',') { ++p; continue; }
+			if (p < s.size() && s[p] == '}') { ++p; break; }
+			fail("expected , or }");
+		}
+		return j;
+	}
+};
+
+inline std::string to_lower(std::string v) {
+	for (auto& c : v) c = (char)std::tolower((unsigned char)c);
+	return v;
+}
+
+}  // namespace ngpb

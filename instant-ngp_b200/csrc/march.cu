@@ -1,0 +1,607 @@
+// march.cu — NeRF training-ray generation, occupancy-grid marching, compositing/loss/compaction and density-grid maintenance.
+// Compiled with -fmad=false (see march.cuh).  Restates src/testbed_nerf.cu kernels, cited per kernel.
+#include "march.cuh"
+
+namespace ngpb {
+
+// ------------------------------------------------------------------------------------------------------------------
+// image access (common_device.cuh:776-872)
+// ------------------------------------------------------------------------------------------------------------------
+struct Rgba {
+	float r, g, b, a;
+};
+__device__ inline Rgba read_rgba_px(int px, int py, int w, const void* pixels, uint32_t type) {
+	const size_t idx = (size_t)px + (size_t)py * (size_t)w;
+	switch (type) {
+		case NGP_IMAGE_BYTE: {
+			const uint32_t val = reinterpret_cast<const uint32_t*>(pixels)[idx];
+			if (val == 0x00FF00FFu) return Rgba{-1.0f, -1.0f, -1.0f, -1.0f};
+			const float a = (float)((val >> 24) & 0xFFu) * (1.0f / 255.0f);
+			Rgba o;
+			o.r = srgb_to_linear((float)(val & 0xFFu) * (1.0f / 255.0f)) * a;
+			o.g = srgb_to_linear((float)((val >> 8) & 0xFFu) * (1.0f / 255.0f)) * a;
+			o.b = srgb_to_linear((float)((val >> 16) & 0xFFu) * (1.0f / 255.0f)) * a;
+			o.a = a;
+			return o;
+		}
+		case NGP_IMAGE_HALF: {
+			const uint2 v = reinterpret_cast<const uint2*>(pixels)[idx];
+			const __half2 lo = *reinterpret_cast<const __half2*>(&v.x), hi = *reinterpret_cast<const __half2*>(&v.y);
+			return Rgba{__low2float(lo), __high2float(lo), __low2float(hi), __high2float(hi)};
+		}
+		case NGP_IMAGE_FLOAT: {
+			const float4 v = reinterpret_cast<const float4*>(pixels)[idx];
+			return Rgba{v.x, v.y, v.z, v.w};
+		}
+		default: return Rgba{5.0f, 0.0f, 0.0f, 1.0f};
+	}
+}
+__device__ inline Rgba read_rgba_uv(float u, float v, int w, int h, const void* pixels, uint32_t type) {
+	const int px = imin(imax((int)(u * (float)w), 0), w - 1);
+	const int py = imin(imax((int)(v * (float)h), 0), h - 1);
+	return read_rgba_px(px, py, w, pixels, type);
+}
+
+// nerf_device.cuh:578-599 (uniform branch): neighbouring rays of a batch look at the same image
+__host__ __device__ inline uint32_t image_idx(uint32_t base_idx, uint32_t n_rays, uint32_t n_images) {
+	return ((base_idx * n_images) / n_rays) % n_images;  // uint32 arithmetic, as the reference
+}
+
+// nerf_device.cuh:553-576 (no error-map CDF)
+__device__ inline void random_image_pos_training(Pcg32& rng, int w, int h, bool snap, float& u, float& v) {
+	u = rng.next_float();
+	v = rng.next_float();
+	if (snap) {
+		u = ((float)imin(imax((int)(u * (float)w), 0), w - 1) + 0.5f) / (float)w;
+		v = ((float)imin(imax((int)(v * (float)h), 0), h - 1) + 0.5f) / (float)h;
+	}
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// generate_training_samples_nerf (testbed_nerf.cu:691-849)
+// One thread per ray.  Slots are reserved once per warp (prefix sum + one atomic) instead of two atomics per ray.
+// ray ids are GLOBAL: ray_id = ray_offset + local index, so that W ranks reproduce the single-GPU batch.
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_generate_training_samples(
+	const uint32_t n_rays_local, const uint32_t ray_offset, const uint32_t n_rays_global, Pcg32 rng_in, const ngp_nerf_train_cfg cfg,
+	const ngp_train_view* __restrict__ views, const uint32_t n_views, const uint8_t* __restrict__ bitfield, const uint32_t max_samples,
+	ngp_nerf_counters* __restrict__ counters, uint32_t* __restrict__ ray_indices_out, float* __restrict__ rays_out,
+	uint32_t* __restrict__ numsteps_out, float* __restrict__ coords_out
+) {
+	const uint32_t li = blockIdx.x * blockDim.x + threadIdx.x;
+	const uint32_t lane = threadIdx.x & 31u;
+	const bool in_range = li < n_rays_local;
+	const uint32_t i = ray_offset + li;
+
+	const Aabb aabb{V3{cfg.aabb_min[0], cfg.aabb_min[1], cfg.aabb_min[2]}, V3{cfg.aabb_max[0], cfg.aabb_max[1], cfg.aabb_max[2]}};
+	uint32_t numsteps = 0;
+	V3 ro{0, 0, 0}, rd{0, 0, 0}, rdn{0, 0, 1}, idir{0, 0, 0};
+	float startt = 0.0f;
+
+	if (in_range) {
+		const uint32_t img = image_idx(i, n_rays_global, n_views);
+		const ngp_train_view vw = views[img];
+		Pcg32 rng = rng_in;
+		rng.advance((uint64_t)i * N_MAX_RANDOM_SAMPLES_PER_RAY);
+		float u, v;
+		random_image_pos_training(rng, vw.width, vw.height, cfg.snap_to_pixel_centers != 0, u, v);
+		const bool masked = read_rgba_uv(u, v, vw.width, vw.height, vw.pixels, vw.image_type).r < 0.0f;
+		if (!masked) {
+			(void)rng.next_float();  // motion-blur time (testbed_nerf.cu:740) — consumed, unused without rolling shutter
+			uv_to_ray(u, v, vw.width, vw.height, vw.focal_x, vw.focal_y, vw.principal_x, vw.principal_y, vw.lens_mode, vw.lens_params, vw.xform, ro, rd);
+			rdn = normalize3(rd);
+			float tmin, tmax;
+			aabb_ray_intersect(aabb, ro, rdn, tmin, tmax);
+			tmin = fmaxf(tmin, 0.0f);
+			startt = advance_n_steps(tmin, cfg.march, rng.next_float());
+			idir = V3{1.0f / rdn.x, 1.0f / rdn.y, 1.0f / rdn.z};
+
+			// pass 1: count the occupied steps
+			uint32_t j = 0;
+			float t = startt;
+			V3 pos;
+			while (aabb.contains(pos = ro + t * rdn) && j < NGP_NERF_STEPS) {
+				const float dt = calc_dt(t, cfg.march);
+				const uint32_t mip = mip_from_dt(dt, pos, cfg.max_cascade);
+				if (density_grid_occupied_at(pos, bitfield, mip)) {
+					++j;
+					t += dt;
+				} else {
+					t = advance_to_next_voxel(t, cfg.march, pos, rdn, idir, mip);
+				}
+			}
+			numsteps = j;
+		}
+	}
+
+	// ---- warp-level reservation of sample slots and ray slots
+	uint32_t incl = numsteps;
+#pragma unroll
+	for (uint32_t o = 1; o < 32; o <<= 1) {
+		const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+		if (lane >= o) incl += t;
+	}
+	const uint32_t warp_total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+	uint32_t warp_base = 0;
+	if (lane == 0 && warp_total > 0) warp_base = atomicAdd(&counters->n_samples, warp_total);
+	warp_base = __shfl_sync(0xFFFFFFFFu, warp_base, 0);
+	const uint32_t base = warp_base + incl - numsteps;
+	const bool keep = numsteps > 0 && (base + numsteps <= max_samples);
+	const uint32_t keep_mask = __ballot_sync(0xFFFFFFFFu, keep);
+	uint32_t ray_base = 0;
+	if (lane == 0 && keep_mask) ray_base = atomicAdd(&counters->n_rays, __popc(keep_mask));
+	ray_base = __shfl_sync(0xFFFFFFFFu, ray_base, 0);
+	if (!keep) return;
+	const uint32_t ray_idx = ray_base + __popc(keep_mask & ((1u << lane) - 1u));
+
+	ray_indices_out[ray_idx] = i;
+	float* r = rays_out + (size_t)ray_idx * 6;
+	r[0] = ro.x; r[1] = ro.y; r[2] = ro.z; r[3] = rd.x; r[4] = rd.y; r[5] = rd.z;
+	numsteps_out[ray_idx * 2 + 0] = numsteps;
+	numsteps_out[ray_idx * 2 + 1] = base;
+
+	// pass 2: write the coordinates
+	const V3 wdir = warp_direction(rdn);
+	float* co = coords_out + (size_t)base * 7;
+	float t = startt;
+	uint32_t j = 0;
+	V3 pos;
+	while (aabb.contains(pos = ro + t * rdn) && j < numsteps) {
+		const float dt = calc_dt(t, cfg.march);
+		const uint32_t mip = mip_from_dt(dt, pos, cfg.max_cascade);
+		if (density_grid_occupied_at(pos, bitfield, mip)) {
+			const V3 wp = warp_position(pos, aabb);
+			float* c = co + (size_t)j * 7;
+			c[0] = wp.x; c[1] = wp.y; c[2] = wp.z; c[3] = warp_dt(dt); c[4] = wdir.x; c[5] = wdir.y; c[6] = wdir.z;
+			++j;
+			t += dt;
+		} else {
+			t = advance_to_next_voxel(t, cfg.march, pos, rdn, idir, mip);
+		}
+	}
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// losses (nerf_device.cuh:75-143, 601-616)
+// ------------------------------------------------------------------------------------------------------------------
+__device__ inline void loss_and_gradient1(float target, float pred, uint32_t type, float& loss, float& grad) {
+	const float d = pred - target;
+	switch (type) {
+		case NGP_LOSS_RELATIVE_L2: { const float den = pred * pred + 1e-2f; loss = d * d / den; grad = 2.0f * d / den; break; }
+		case NGP_LOSS_L1: loss = fabsf(d); grad = copysignf(1.0f, d); break;
+		case NGP_LOSS_MAPE: { const float den = fabsf(pred) + 1e-2f; loss = fabsf(d) / den; grad = copysignf(1.0f / den, d); break; }
+		case NGP_LOSS_SMAPE: { const float den = 0.5f * (fabsf(pred) + fabsf(target)) + 1e-2f; loss = fabsf(d) / den; grad = copysignf(1.0f / den, d); break; }
+		case NGP_LOSS_HUBER: {
+			const float alpha = 0.1f;
+			const float ad = fabsf(d);
+			const float sq = 0.5f / alpha * d * d;
+			loss = (ad > alpha ? (ad - 0.5f * alpha) : sq) / 5.0f;
+			grad = (ad > alpha ? (d > 0.0f ? 1.0f : -1.0f) : (d / alpha)) / 5.0f;
+			break;
+		}
+		case NGP_LOSS_LOGL1: { const float div = fabsf(d) + 1.0f; loss = ngp_logf(div); grad = copysignf(1.0f / div, d); break; }
+		default: loss = d * d; grad = 2.0f * d; break;
+	}
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// compute_loss_kernel_train_nerf (testbed_nerf.cu:852-1180), Nerf train mode, no envmap / depth / exposure / error map.
+// network_output: 4 halves per sample (rgb raw x3, density raw).
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_compute_loss(
+	const uint32_t n_rays_global, Pcg32 rng_in, const ngp_nerf_train_cfg cfg, const ngp_train_view* __restrict__ views, const uint32_t n_views,
+	const __half* __restrict__ network_output, const uint32_t max_compacted, ngp_nerf_counters* __restrict__ counters,
+	const uint32_t* __restrict__ ray_indices_in, const float* __restrict__ rays_in, uint32_t* __restrict__ numsteps_in,
+	const float* __restrict__ coords_in, float* __restrict__ coords_out, __half* __restrict__ dloss_out, float* __restrict__ loss_output,
+	const float* __restrict__ mean_density_ptr
+) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	const uint32_t lane = threadIdx.x & 31u;
+	const uint32_t n_rays_kept = counters->n_rays;
+	const bool active = i < n_rays_kept;
+	const Aabb aabb{V3{cfg.aabb_min[0], cfg.aabb_min[1], cfg.aabb_min[2]}, V3{cfg.aabb_max[0], cfg.aabb_max[1], cfg.aabb_max[2]}};
+
+	uint32_t numsteps = 0, base = 0, compacted_numsteps = 0;
+	float T = 1.0f;
+	V3 rgb_ray{0, 0, 0};
+	V3 ray_o{0, 0, 0};
+	const float EPSILON = 1e-4f;
+	if (active) {
+		numsteps = numsteps_in[i * 2 + 0];
+		base = numsteps_in[i * 2 + 1];
+		ray_o = V3{rays_in[(size_t)i * 6 + 0], rays_in[(size_t)i * 6 + 1], rays_in[(size_t)i * 6 + 2]};
+		const __half* no = network_output + (size_t)base * 4;
+		const float* ci = coords_in + (size_t)base * 7;
+		for (; compacted_numsteps < numsteps; ++compacted_numsteps) {
+			if (T < EPSILON) break;
+			const uint2 raw = *reinterpret_cast<const uint2*>(no + (size_t)compacted_numsteps * 4);
+			const __half2 h01 = *reinterpret_cast<const __half2*>(&raw.x), h23 = *reinterpret_cast<const __half2*>(&raw.y);
+			const V3 rgb = V3{network_to_rgb(__low2float(h01), cfg.rgb_activation), network_to_rgb(__high2float(h01), cfg.rgb_activation),
+				network_to_rgb(__low2float(h23), cfg.rgb_activation)};
+			const float dt = unwarp_dt(ci[(size_t)compacted_numsteps * 7 + 3]);
+			const float density = network_to_density(__high2float(h23), cfg.density_activation);
+			const float alpha = 1.0f - ngp_expf(-density * dt);
+			const float weight = alpha * T;
+			rgb_ray = rgb_ray + weight * rgb;
+			T *= (1.0f - alpha);
+		}
+	}
+
+	// Same draws as the generator (testbed_nerf.cu:951-967)
+	V3 lg_grad{0, 0, 0};
+	float mean_loss = 0.0f;
+	V3 bg{cfg.background_color[0], cfg.background_color[1], cfg.background_color[2]};
+	if (active) {
+		const uint32_t ray_idx = ray_indices_in[i];
+		Pcg32 rng = rng_in;
+		rng.advance((uint64_t)ray_idx * N_MAX_RANDOM_SAMPLES_PER_RAY);
+		const uint32_t img = image_idx(ray_idx, n_rays_global, n_views);
+		const ngp_train_view vw = views[img];
+		float u, v;
+		random_image_pos_training(rng, vw.width, vw.height, cfg.snap_to_pixel_centers != 0, u, v);
+		rng.advance(1);  // motion-blur time
+		if (cfg.random_bg_color) {
+			bg.x = rng.next_float();
+			bg.y = rng.next_float();
+			bg.z = rng.next_float();
+		}
+		bg = V3{srgb_to_linear(bg.x), srgb_to_linear(bg.y), srgb_to_linear(bg.z)};
+		const Rgba tex = read_rgba_uv(u, v, vw.width, vw.height, vw.pixels, vw.image_type);
+		V3 target;
+		if (cfg.linear_colors || cfg.color_space == NGP_COLOR_LINEAR) {
+			target = V3{tex.r + (1.0f - tex.a) * bg.x, tex.g + (1.0f - tex.a) * bg.y, tex.b + (1.0f - tex.a) * bg.z};
+			if (!cfg.linear_colors) {
+				target = V3{linear_to_srgb(target.x), linear_to_srgb(target.y), linear_to_srgb(target.z)};
+				bg = V3{linear_to_srgb(bg.x), linear_to_srgb(bg.y), linear_to_srgb(bg.z)};
+			}
+		} else {
+			bg = V3{linear_to_srgb(bg.x), linear_to_srgb(bg.y), linear_to_srgb(bg.z)};
+			if (tex.a > 0.0f) {
+				target = V3{linear_to_srgb(tex.r / tex.a) * tex.a + (1.0f - tex.a) * bg.x, linear_to_srgb(tex.g / tex.a) * tex.a + (1.0f - tex.a) * bg.y,
+					linear_to_srgb(tex.b / tex.a) * tex.a + (1.0f - tex.a) * bg.z};
+			} else {
+				target = bg;
+			}
+		}
+		if (compacted_numsteps == numsteps) rgb_ray = rgb_ray + T * bg;
+
+		float lx, ly, lz;
+		loss_and_gradient1(target.x, rgb_ray.x, cfg.loss_type, lx, lg_grad.x);
+		loss_and_gradient1(target.y, rgb_ray.y, cfg.loss_type, ly, lg_grad.y);
+		loss_and_gradient1(target.z, rgb_ray.z, cfg.loss_type, lz, lg_grad.z);
+		mean_loss = ((lx + ly) + lz) / 3.0f;
+	}
+
+	// ---- compaction: reserve [compacted_base, +compacted_numsteps) once per warp (testbed_nerf.cu:1010-1016)
+	uint32_t incl = compacted_numsteps;
+#pragma unroll
+	for (uint32_t o = 1; o < 32; o <<= 1) {
+		const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+		if (lane >= o) incl += t;
+	}
+	const uint32_t warp_total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+	uint32_t warp_base = 0;
+	if (lane == 0 && warp_total > 0) warp_base = atomicAdd(&counters->n_samples_compacted, warp_total);
+	warp_base = __shfl_sync(0xFFFFFFFFu, warp_base, 0);
+	if (!active) return;
+	const uint32_t compacted_base = warp_base + incl - compacted_numsteps;
+	const uint32_t cb_clamped = compacted_base < max_compacted ? compacted_base : max_compacted;
+	const uint32_t room = max_compacted - cb_clamped;
+	compacted_numsteps = room < compacted_numsteps ? room : compacted_numsteps;
+	numsteps_in[i * 2 + 0] = compacted_numsteps;
+	numsteps_in[i * 2 + 1] = compacted_base;
+	if (compacted_numsteps == 0) return;
+
+	if (loss_output) loss_output[i] = mean_loss / (float)n_rays_global;
+
+	const float loss_scale = cfg.loss_scale / (float)n_rays_global;
+	const float output_l2_reg = cfg.rgb_activation == NGP_ACT_EXPONENTIAL ? 1e-4f : 0.0f;
+	const float output_l1_reg_density = *mean_density_ptr < min_optical_thickness() ? 1e-4f : 0.0f;
+
+	const __half* no = network_output + (size_t)base * 4;
+	const float* ci = coords_in + (size_t)base * 7;
+	float* co = coords_out + (size_t)compacted_base * 7;
+	__half* dl = dloss_out + (size_t)compacted_base * 4;
+	V3 rgb_ray2{0, 0, 0};
+	T = 1.0f;
+	for (uint32_t j = 0; j < compacted_numsteps; ++j) {
+		float c[7];
+#pragma unroll
+		for (int k = 0; k < 7; ++k) {
+			c[k] = ci[(size_t)j * 7 + k];
+			co[(size_t)j * 7 + k] = c[k];
+		}
+		const V3 pos = unwarp_position(V3{c[0], c[1], c[2]}, aabb);
+		const V3 dp = pos - ray_o;
+		const float depth = length3(dp);
+		const float dt = unwarp_dt(c[3]);
+		const uint2 raw = *reinterpret_cast<const uint2*>(no + (size_t)j * 4);
+		const __half2 h01 = *reinterpret_cast<const __half2*>(&raw.x), h23 = *reinterpret_cast<const __half2*>(&raw.y);
+		const float o0 = __low2float(h01), o1 = __high2float(h01), o2 = __low2float(h23), o3 = __high2float(h23);
+		const V3 rgb = V3{network_to_rgb(o0, cfg.rgb_activation), network_to_rgb(o1, cfg.rgb_activation), network_to_rgb(o2, cfg.rgb_activation)};
+		const float density = network_to_density(o3, cfg.density_activation);
+		const float alpha = 1.0f - ngp_expf(-density * dt);
+		const float weight = alpha * T;
+		rgb_ray2 = rgb_ray2 + weight * rgb;
+		T *= (1.0f - alpha);
+
+		const V3 suffix = rgb_ray - rgb_ray2;
+		const V3 dloss_by_drgb = weight * lg_grad;
+		const float d0 = loss_scale * (dloss_by_drgb.x * network_to_rgb_derivative(o0, cfg.rgb_activation) + fmaxf(0.0f, output_l2_reg * o0));
+		const float d1 = loss_scale * (dloss_by_drgb.y * network_to_rgb_derivative(o1, cfg.rgb_activation) + fmaxf(0.0f, output_l2_reg * o1));
+		const float d2 = loss_scale * (dloss_by_drgb.z * network_to_rgb_derivative(o2, cfg.rgb_activation) + fmaxf(0.0f, output_l2_reg * o2));
+		const float density_derivative = network_to_density_derivative(o3, cfg.density_activation);
+		const V3 tr = T * rgb - suffix;
+		const float dloss_by_dmlp = density_derivative * (dt * dot3(lg_grad, tr));
+		const float d3 = loss_scale * dloss_by_dmlp + (o3 < 0.0f ? -output_l1_reg_density : 0.0f) + (o3 > -10.0f && depth < cfg.near_distance ? 1e-4f : 0.0f);
+		const __half2 w01 = __floats2half2_rn(d0, d1), w23 = __floats2half2_rn(d2, d3);
+		uint2 outv;
+		outv.x = *reinterpret_cast<const uint32_t*>(&w01);
+		outv.y = *reinterpret_cast<const uint32_t*>(&w23);
+		*reinterpret_cast<uint2*>(dl + (size_t)j * 4) = outv;
+	}
+}
+
+// fill_rollover_and_rescale<half>(dloss, stride 4) + fill_rollover<float>(coords, stride 7)
+// (common_device.h:1114-1135 as called at testbed_nerf.cu:3298-3303)
+__global__ void k_fill_rollover(const uint32_t n_elements, const ngp_nerf_counters* __restrict__ counters, float* __restrict__ coords, __half* __restrict__ dloss) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;  // one thread per padded sample
+	const uint32_t n_input = counters->n_samples_compacted < n_elements ? counters->n_samples_compacted : n_elements;
+	if (i < n_input || i >= n_elements || n_input == 0) return;
+	const uint32_t src = i % n_input;
+#pragma unroll
+	for (int k = 0; k < 7; ++k) coords[(size_t)i * 7 + k] = coords[(size_t)src * 7 + k];
+#pragma unroll
+	for (int k = 0; k < 4; ++k) {
+		const float v = __half2float(dloss[(size_t)src * 4 + k]);
+		dloss[(size_t)i * 4 + k] = __float2half_rn(v * (float)n_input / (float)n_elements);
+	}
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// density grid maintenance (testbed_nerf.cu:87-162, 216-284, 316-396, 2476-2633)
+// ------------------------------------------------------------------------------------------------------------------
+__device__ inline V3 pos_to_uv_dir(const float* xform, V3 pos, const ngp_train_view& vw, float& u, float& v) {
+	// pos_to_uv (common_device.cuh:527-577) for perspective/OpenCV lenses, parallax 0
+	const V3 origin = xform_col(xform, 3);
+	V3 dir = pos - origin;
+	// inverse(mat3(camera)) * dir  — general 3x3 inverse via adjugate
+	const float a = xform[0], b = xform[3], c = xform[6], d = xform[1], e = xform[4], f = xform[7], g = xform[2], h = xform[5], k = xform[8];
+	const float A = e * k - f * h, B = -(d * k - f * g), C = d * h - e * g;
+	const float det = a * A + b * B + c * C;
+	const float inv00 = A / det, inv01 = -(b * k - c * h) / det, inv02 = (b * f - c * e) / det;
+	const float inv10 = B / det, inv11 = (a * k - c * g) / det, inv12 = -(a * f - c * d) / det;
+	const float inv20 = C / det, inv21 = -(a * h - b * g) / det, inv22 = (a * e - b * d) / det;
+	V3 l{(inv00 * dir.x + inv01 * dir.y) + inv02 * dir.z, (inv10 * dir.x + inv11 * dir.y) + inv12 * dir.z, (inv20 * dir.x + inv21 * dir.y) + inv22 * dir.z};
+	l = V3{l.x / l.z, l.y / l.z, 1.0f};
+	float du = 0.0f, dv = 0.0f;
+	if (vw.lens_mode == NGP_LENS_OPENCV) opencv_lens_distortion_delta(vw.lens_params, l.x, l.y, &du, &dv);
+	l.x += du;
+	l.y += dv;
+	u = l.x * vw.focal_x / (float)vw.width + vw.principal_x;
+	v = l.y * vw.focal_y / (float)vw.height + vw.principal_y;
+	return dir;
+}
+
+__global__ void k_mark_untrained_density_grid(const uint32_t n_elements, float* __restrict__ grid_out, const uint32_t n_views,
+	const ngp_train_view* __restrict__ views, const bool clear_visible_voxels) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n_elements) return;
+	const uint32_t level = i / GRID_N_CELLS, pos_idx = i % GRID_N_CELLS;
+	const uint32_t x = morton_compact3(pos_idx >> 0), y = morton_compact3(pos_idx >> 1), z = morton_compact3(pos_idx >> 2);
+	const float voxel_size = scalbnf(1.0f / 128.0f, (int)level);
+	const float s = scalbnf(1.0f, (int)level);
+	const V3 pos{((float)x / 128.0f - 0.5f) * s + 0.5f, ((float)y / 128.0f - 0.5f) * s + 0.5f, ((float)z / 128.0f - 0.5f) * s + 0.5f};
+	uint32_t count = 0;
+	for (uint32_t j = 0; j < n_views && count < 1; ++j) {
+		const ngp_train_view vw = views[j];
+		const V3 cam_o = xform_col(vw.xform, 3), cam_fwd = xform_col(vw.xform, 2);
+		for (uint32_t k = 0; k < 8; ++k) {
+			const V3 corner{pos.x + ((k & 1u) ? voxel_size : 0.0f), pos.y + ((k & 2u) ? voxel_size : 0.0f), pos.z + ((k & 4u) ? voxel_size : 0.0f)};
+			const V3 dir = normalize3(corner - cam_o);
+			if (dot3(dir, cam_fwd) < 1e-4f) continue;
+			float u, v;
+			pos_to_uv_dir(vw.xform, corner, vw, u, v);
+			V3 ro, rd;
+			uv_to_ray(u, v, vw.width, vw.height, vw.focal_x, vw.focal_y, vw.principal_x, vw.principal_y, vw.lens_mode, vw.lens_params, vw.xform, ro, rd);
+			const V3 diff = normalize3(rd) - dir;
+			if (length3(diff) < 1e-3f && u > 0.0f && v > 0.0f && u < 1.0f && v < 1.0f) {
+				++count;
+				break;
+			}
+		}
+	}
+	if (clear_visible_voxels || (grid_out[i] < 0.0f) != (count < 1)) grid_out[i] = (count >= 1) ? 0.0f : -1.0f;
+}
+
+__global__ void k_generate_grid_samples(const uint32_t n_elements, Pcg32 rng, const uint32_t step, const Aabb aabb, const float* __restrict__ grid_in,
+	float* __restrict__ out_pos /* 4 floats per sample: xyz + dt */, uint32_t* __restrict__ indices, const uint32_t n_cascades, const float thresh) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n_elements) return;
+	rng.advance((uint64_t)i * 4);
+	const uint32_t level = (uint32_t)(rng.next_float() * (float)n_cascades) % n_cascades;
+	uint32_t idx = 0;
+	for (uint32_t j = 0; j < 10; ++j) {
+		idx = ((i + step * n_elements) * 56924617u + j * 19349663u + 96925573u) % GRID_N_CELLS;
+		idx += level * GRID_N_CELLS;
+		if (grid_in[idx] > thresh) break;
+	}
+	const uint32_t pos_idx = idx % GRID_N_CELLS;
+	const uint32_t x = morton_compact3(pos_idx >> 0), y = morton_compact3(pos_idx >> 1), z = morton_compact3(pos_idx >> 2);
+	const float rx = rng.next_float(), ry = rng.next_float(), rz = rng.next_float();
+	const float s = scalbnf(1.0f, (int)level);
+	const V3 pos{(((float)x + rx) / 128.0f - 0.5f) * s + 0.5f, (((float)y + ry) / 128.0f - 0.5f) * s + 0.5f, (((float)z + rz) / 128.0f - 0.5f) * s + 0.5f};
+	const V3 wp = warp_position(pos, aabb);
+	out_pos[(size_t)i * 4 + 0] = wp.x;
+	out_pos[(size_t)i * 4 + 1] = wp.y;
+	out_pos[(size_t)i * 4 + 2] = wp.z;
+	out_pos[(size_t)i * 4 + 3] = warp_dt(min_cone_stepsize());
+	indices[i] = idx;
+}
+
+__global__ void k_splat_grid_samples(const uint32_t n_elements, const uint32_t* __restrict__ indices, const __half* __restrict__ density_raw,
+	float* __restrict__ grid_out, const uint32_t density_activation) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n_elements) return;
+	const float mlp = network_to_density(__half2float(density_raw[i]), density_activation);
+	const float optical_thickness = mlp * min_cone_stepsize();
+	atomicMax(reinterpret_cast<uint32_t*>(grid_out) + indices[i], __float_as_uint(optical_thickness));
+}
+
+__global__ void k_ema_grid_samples(const uint32_t n_elements, const float decay, float* __restrict__ grid_out, const float* __restrict__ grid_in) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n_elements) return;
+	const float importance = grid_in[i];
+	const float prev = grid_out[i];
+	grid_out[i] = (prev < 0.0f) ? prev : fmaxf(prev * decay, importance);
+}
+
+// mean of max(v, 0) over the first cascade, in a fixed order so the CPU oracle can reproduce it:
+// 1024 partial sums (strided) followed by a sequential sum of the partials.
+__global__ void k_density_mean_partial(const float* __restrict__ grid, float* __restrict__ partial /*1024*/) {
+	const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;  // 1024 threads
+	float s = 0.0f;
+	for (uint32_t i = t; i < GRID_N_CELLS; i += 1024) s += fmaxf(grid[i], 0.0f) / (float)GRID_N_CELLS;
+	partial[t] = s;
+}
+__global__ void k_density_mean_final(const float* __restrict__ partial, float* __restrict__ mean) {
+	float s = 0.0f;
+	for (uint32_t i = 0; i < 1024; ++i) s += partial[i];
+	*mean = s;
+}
+
+__global__ void k_grid_to_bitfield(const uint32_t n_elements, const uint32_t n_nonzero, const float* __restrict__ grid, uint8_t* __restrict__ bitfield,
+	const float* __restrict__ mean_density) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n_elements) return;
+	if (i >= n_nonzero) {
+		bitfield[i] = 0;
+		return;
+	}
+	const float thresh = fminf(min_optical_thickness(), *mean_density);
+	uint8_t bits = 0;
+#pragma unroll
+	for (uint8_t j = 0; j < 8; ++j) bits |= grid[(size_t)i * 8 + j] > thresh ? ((uint8_t)1 << j) : 0;
+	bitfield[i] = bits;
+}
+
+__global__ void k_bitfield_max_pool(const uint32_t n_elements, const uint8_t* __restrict__ prev_level, uint8_t* __restrict__ next_level) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n_elements) return;
+	uint8_t bits = 0;
+#pragma unroll
+	for (uint8_t j = 0; j < 8; ++j) bits |= prev_level[(size_t)i * 8 + j] > 0 ? ((uint8_t)1 << j) : 0;
+	const uint32_t x = morton_compact3(i >> 0) + 128 / 8, y = morton_compact3(i >> 1) + 128 / 8, z = morton_compact3(i >> 2) + 128 / 8;
+	next_level[morton3d(x, y, z)] |= bits;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// host launchers
+// ------------------------------------------------------------------------------------------------------------------
+void nerf_density(const ngp_nerf_desc& d, cudaStream_t stream, uint32_t n, const float* positions, uint32_t pos_stride, const __half* params, __half* out);
+
+static Aabb cfg_aabb(const ngp_nerf_train_cfg& cfg) {
+	return Aabb{V3{cfg.aabb_min[0], cfg.aabb_min[1], cfg.aabb_min[2]}, V3{cfg.aabb_max[0], cfg.aabb_max[1], cfg.aabb_max[2]}};
+}
+
+void generate_training_samples(cudaStream_t stream, uint32_t n_rays_local, uint32_t ray_offset, uint32_t n_rays_global, uint64_t rng_state,
+	uint64_t rng_inc, const ngp_nerf_train_cfg& cfg, const ngp_train_view* views, uint32_t n_views, const uint8_t* bitfield, uint32_t max_samples,
+	ngp_nerf_counters* counters, uint32_t* ray_indices, float* rays, uint32_t* numsteps, float* coords) {
+	if (n_rays_local == 0) return;
+	NGPB_CHECK(n_views > 0, "generate_training_samples: no training views");
+	k_generate_training_samples<<<div_round_up(n_rays_local, 128), 128, 0, stream>>>(n_rays_local, ray_offset, n_rays_global,
+		Pcg32(rng_state, rng_inc, true), cfg, views, n_views, bitfield, max_samples, counters, ray_indices, rays, numsteps, coords);
+	NGPB_LAUNCHED();
+	NGPB_CUDA_CHECK(cudaGetLastError());
+}
+
+void compute_loss(cudaStream_t stream, uint32_t n_rays_local, uint32_t n_rays_global, uint64_t rng_state, uint64_t rng_inc,
+	const ngp_nerf_train_cfg& cfg, const ngp_train_view* views, uint32_t n_views, const __half* network_output, uint32_t max_compacted,
+	ngp_nerf_counters* counters, const uint32_t* ray_indices, const float* rays, uint32_t* numsteps, const float* coords, float* coords_compacted,
+	__half* dloss, float* loss_per_ray, const float* mean_density) {
+	if (n_rays_local == 0) return;
+	k_compute_loss<<<div_round_up(n_rays_local, 128), 128, 0, stream>>>(n_rays_global, Pcg32(rng_state, rng_inc, true), cfg, views, n_views,
+		network_output, max_compacted, counters, ray_indices, rays, numsteps, coords, coords_compacted, dloss, loss_per_ray, mean_density);
+	NGPB_LAUNCHED();
+	NGPB_CUDA_CHECK(cudaGetLastError());
+}
+
+void fill_rollover(cudaStream_t stream, uint32_t target_batch, const ngp_nerf_counters* counters, float* coords_compacted, __half* dloss) {
+	k_fill_rollover<<<div_round_up(target_batch, 256), 256, 0, stream>>>(target_batch, counters, coords_compacted, dloss);
+	NGPB_LAUNCHED();
+	NGPB_CUDA_CHECK(cudaGetLastError());
+}
+
+void update_bitfield(cudaStream_t stream, uint32_t max_cascade, const float* density_grid, uint8_t* bitfield, float* mean_density, float* partial1024) {
+	k_density_mean_partial<<<4, 256, 0, stream>>>(density_grid, partial1024);
+	k_density_mean_final<<<1, 1, 0, stream>>>(partial1024, mean_density);
+	const uint32_t n_bytes = GRID_N_CELLS / 8 * NGP_NERF_CASCADES;
+	k_grid_to_bitfield<<<div_round_up(n_bytes, 256), 256, 0, stream>>>(n_bytes, GRID_N_CELLS / 8 * (max_cascade + 1), density_grid, bitfield, mean_density);
+	NGPB_LAUNCHED(); NGPB_LAUNCHED(); NGPB_LAUNCHED();
+	for (uint32_t level = 1; level < NGP_NERF_CASCADES; ++level) {
+		k_bitfield_max_pool<<<div_round_up(GRID_N_CELLS / 64, 256), 256, 0, stream>>>(GRID_N_CELLS / 64, bitfield + (size_t)(level - 1) * GRID_N_CELLS / 8,
+			bitfield + (size_t)level * GRID_N_CELLS / 8);
+		NGPB_LAUNCHED();
+	}
+	NGPB_CUDA_CHECK(cudaGetLastError());
+}
+
+// scratch layout: positions [n_total x 4 f32] | indices [n_total u32] | density_tmp [n_elements f32] | mlp_out [n_total f16] | partial [1024 f32]
+size_t density_grid_scratch_bytes(uint32_t max_cascade) {
+	const size_t n_elements = (size_t)GRID_N_CELLS * (max_cascade + 1);
+	const size_t n_total = n_elements;  // worst case: the first 256 steps sample every cell once
+	return n_total * 16 + n_total * 4 + n_elements * 4 + next_multiple((uint32_t)(n_total * 2), 16) + 1024 * 4 + 256;
+}
+
+void update_density_grid(const ngp_nerf_desc& d, cudaStream_t stream, const ngp_nerf_train_cfg& cfg, const __half* params, uint64_t* grid_rng_state,
+	uint64_t grid_rng_inc, uint32_t training_step, uint32_t ema_step, float decay, const ngp_train_view* views, uint32_t n_views, float* density_grid,
+	uint8_t* bitfield, float* mean_density, void* scratch) {
+	const uint32_t n_cascades = cfg.max_cascade + 1;
+	const uint32_t n_elements = GRID_N_CELLS * n_cascades;
+	uint32_t n_uniform, n_nonuniform;
+	if (training_step < 256) {
+		n_uniform = GRID_N_CELLS * n_cascades;
+		n_nonuniform = 0;
+	} else {
+		n_uniform = GRID_N_CELLS / 4 * n_cascades;
+		n_nonuniform = GRID_N_CELLS / 4 * n_cascades;
+	}
+	const uint32_t n_total = n_uniform + n_nonuniform;
+	uint8_t* p = reinterpret_cast<uint8_t*>(scratch);
+	float* positions = reinterpret_cast<float*>(p);
+	p += (size_t)n_elements * 16;
+	uint32_t* indices = reinterpret_cast<uint32_t*>(p);
+	p += (size_t)n_elements * 4;
+	float* density_tmp = reinterpret_cast<float*>(p);
+	p += (size_t)n_elements * 4;
+	__half* mlp_out = reinterpret_cast<__half*>(p);
+	p += next_multiple(n_elements * 2, 16);
+	float* partial = reinterpret_cast<float*>(p);
+
+	if (training_step == 0) {
+		k_mark_untrained_density_grid<<<div_round_up(n_elements, 128), 128, 0, stream>>>(n_elements, density_grid, n_views, views, true);
+		NGPB_LAUNCHED();
+	}
+	NGPB_CUDA_CHECK(cudaMemsetAsync(density_tmp, 0, sizeof(float) * n_elements, stream));
+	const Aabb aabb = cfg_aabb(cfg);
+	Pcg32 rng(*grid_rng_state, grid_rng_inc, true);
+	k_generate_grid_samples<<<div_round_up(n_uniform, 128), 128, 0, stream>>>(n_uniform, rng, ema_step, aabb, density_grid, positions, indices, n_cascades, -0.01f);
+	NGPB_LAUNCHED();
+	rng.advance();
+	if (n_nonuniform > 0) {
+		k_generate_grid_samples<<<div_round_up(n_nonuniform, 128), 128, 0, stream>>>(n_nonuniform, rng, ema_step, aabb, density_grid,
+			positions + (size_t)n_uniform * 4, indices + n_uniform, n_cascades, min_optical_thickness());
+		NGPB_LAUNCHED();
+	}
+	rng.advance();
+	*grid_rng_state = rng.state;
+
+	nerf_density(d, stream, n_total, positions, 4, params, mlp_out);
+	k_splat_grid_samples<<<div_round_up(n_total, 256), 256, 0, stream>>>(n_total, indices, mlp_out, density_tmp, cfg.density_activation);
+	k_ema_grid_samples<<<div_round_up(n_elements, 256), 256, 0, stream>>>(n_elements, decay, density_grid, density_tmp);
+	NGPB_LAUNCHED(); NGPB_LAUNCHED();
+	NGPB_CUDA_CHECK(cudaGetLastError());
+	update_bitfield(stream, cfg.max_cascade, density_grid, bitfield, mean_density, partial);
+}
+
+}  // namespace ngpb

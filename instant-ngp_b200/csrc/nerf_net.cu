@@ -1,0 +1,630 @@
+// nerf_net.cu — fused NeRF network kernels for sm_100a and their C-ABI entry points.
+//
+//   k_nerf_forward   hash-grid gather + density MLP + SH + rgb MLP in one kernel; activations never leave the SM.
+//                    ≙ NerfNetwork::inference_mixed_precision_impl (nerf_network.h:105-139) = kernel_grid + transpose +
+//                    kernel_mlp_fused x2 + kernel_sh + extract_density in the reference.
+//   k_nerf_density   hash-grid gather + density MLP (≙ NerfNetwork::density, nerf_network.h:270-280).
+//   k_grid_encode    the encoding alone (≙ kernel_grid, grid.h:48-212), sample-contiguous output.
+//
+// One CTA = 128 threads = one 128-sample tile = one UMMA M=128 accumulator; thread t owns sample t and TMEM lane t.
+// All MLP weights stay resident in shared memory in the chunk-major operand layout for the kernel's lifetime.
+#include "nerf_net.cuh"
+
+#include <vector>
+
+namespace ngpb {
+
+template <uint32_t F, bool DENSITY_ONLY>
+__global__ void __launch_bounds__(TILE, 4) k_nerf_forward(
+	const __grid_constant__ NetDev net, const uint32_t n_max, const uint32_t* __restrict__ n_dev, const float* __restrict__ in,
+	const uint32_t in_stride, const uint32_t dir_offset, const __half* __restrict__ params, __half* __restrict__ out, const uint32_t out_stride
+) {
+	extern __shared__ __align__(128) uint8_t smem[];
+	// optional device-side element count (the sample generator's counter): no host round trip to size the launch
+	uint32_t n = n_max;
+	if (n_dev) {
+		const uint32_t nd = *n_dev;
+		n = nd < n_max ? nd : n_max;
+	}
+	if (blockIdx.x * TILE >= n) return;
+	const FwdSmem L = fwd_smem_layout(net.n_hidden_density, net.n_hidden_rgb);
+	const uint32_t tid = threadIdx.x;
+	uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L.bar_off);
+	uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L.bar_off + 8);
+
+	// ---- one-time setup: weights -> smem, TMEM allocation, barrier
+	{
+		const uint32_t wd_off = 0, wr_off = mlp_n_params(net.n_hidden_density) * 2u;
+		for (uint32_t l = 0; l < mlp_n_layers(net.n_hidden_density); ++l) {
+			stage_weights(params + net.density_off + mlp_layer_off(net.n_hidden_density, l), mlp_layer_out(net.n_hidden_density, l),
+				mlp_layer_in(net.n_hidden_density, l), smem + wd_off + mlp_layer_off(net.n_hidden_density, l) * 2u, tid, TILE);
+		}
+		if (!DENSITY_ONLY) {
+			for (uint32_t l = 0; l < mlp_n_layers(net.n_hidden_rgb); ++l) {
+				stage_weights(params + net.rgb_off + mlp_layer_off(net.n_hidden_rgb, l), mlp_layer_out(net.n_hidden_rgb, l),
+					mlp_layer_in(net.n_hidden_rgb, l), smem + wr_off + mlp_layer_off(net.n_hidden_rgb, l) * 2u, tid, TILE);
+			}
+		}
+	}
+	if (tid < 32) umma::tmem_alloc<64>(tmem_slot);
+	if (tid == 0) {
+		umma::mbar_init(bar, 1);
+		umma::mbar_fence_init();
+	}
+	umma::fence_before_sync();
+	__syncthreads();
+	umma::fence_after_sync();
+	const uint32_t tmem_base = *tmem_slot;
+	uint32_t phase = 0;
+
+	const __half* grid = params + net.grid_off;
+	const uint32_t n_tiles = (n + TILE - 1) / TILE;
+	for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+		const uint32_t i = tile * TILE + tid;
+		const bool valid = i < n;
+		const float* c = in + (size_t)(valid ? i : 0) * in_stride;
+		const float x = c[0], y = c[1], z = c[2];
+
+		// ---- encoding -> A0
+		{
+			__half2 enc[16];
+			grid_gather<F>(net, grid, x, y, z, enc);
+#pragma unroll
+			for (uint32_t kc = 0; kc < 4; ++kc) {
+				const __half2 h[4] = {enc[kc * 4 + 0], enc[kc * 4 + 1], enc[kc * 4 + 2], enc[kc * 4 + 3]};
+				store_chunk(smem + L.a0_off, tid, kc, h);
+			}
+		}
+		if (!DENSITY_ONLY) {
+			__half2 sh[8];
+			sh4_encode(c[dir_offset + 0], c[dir_offset + 1], c[dir_offset + 2], sh);
+			const __half2 h0[4] = {sh[0], sh[1], sh[2], sh[3]};
+			const __half2 h1[4] = {sh[4], sh[5], sh[6], sh[7]};
+			store_chunk(smem + L.a2_off, tid, 2, h0);
+			store_chunk(smem + L.a2_off, tid, 3, h1);
+		}
+
+		// ---- density MLP
+		__half2 dens[8];
+		run_mlp_fwd(smem, L.a0_off, L.h_off, 0, net.n_hidden_density, tmem_base, bar, phase, tid, dens);
+
+		if (DENSITY_ONLY) {
+			if (valid) out[(size_t)i * out_stride] = __low2half(dens[0]);
+		} else {
+			const __half2 h0[4] = {dens[0], dens[1], dens[2], dens[3]};
+			const __half2 h1[4] = {dens[4], dens[5], dens[6], dens[7]};
+			store_chunk(smem + L.a2_off, tid, 0, h0);
+			store_chunk(smem + L.a2_off, tid, 1, h1);
+			__half2 rgb[8];
+			run_mlp_fwd(smem, L.a2_off, L.h_off, mlp_n_params(net.n_hidden_density) * 2u, net.n_hidden_rgb, tmem_base, bar, phase, tid, rgb);
+			if (valid) {
+				// (rgb raw x3, density raw) — columns 0..3 of the reference's padded 16-wide output row
+				uint2 o;
+				o.x = *reinterpret_cast<const uint32_t*>(&rgb[0]);
+				const __half2 t = __halves2half2(__low2half(rgb[1]), __low2half(dens[0]));
+				o.y = *reinterpret_cast<const uint32_t*>(&t);
+				*reinterpret_cast<uint2*>(out + (size_t)i * out_stride) = o;
+			}
+		}
+	}
+
+	umma::fence_before_sync();
+	__syncthreads();
+	if (tid < 32) umma::tmem_dealloc<64>(tmem_base);
+}
+
+template <uint32_t F>
+__global__ void __launch_bounds__(256) k_grid_encode(
+	const __grid_constant__ NetDev net, const uint32_t n, const float* __restrict__ pos, const uint32_t pos_stride,
+	const __half* __restrict__ grid, __half* __restrict__ out
+) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const float* c = pos + (size_t)i * pos_stride;
+	__half2 enc[16];
+	grid_gather<F>(net, grid, c[0], c[1], c[2], enc);
+	uint4* o = reinterpret_cast<uint4*>(out + (size_t)i * ENC_WIDTH);
+#pragma unroll
+	for (uint32_t k = 0; k < 4; ++k) {
+		uint4 v;
+		v.x = *reinterpret_cast<const uint32_t*>(&enc[k * 4 + 0]);
+		v.y = *reinterpret_cast<const uint32_t*>(&enc[k * 4 + 1]);
+		v.z = *reinterpret_cast<const uint32_t*>(&enc[k * 4 + 2]);
+		v.w = *reinterpret_cast<const uint32_t*>(&enc[k * 4 + 3]);
+		o[k] = v;
+	}
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// k_nerf_train — forward + backward of the whole NeRF network for one 128-sample tile per CTA iteration.
+//   ≙ Trainer::training_step(external dL/dy) → NerfNetwork::forward_impl + backward_impl (nerf_network.h:145-268):
+//     kernel_grid, kernel_mlp_fused (x2, writing activations to HBM), kernel_sh, extract_rgb, kernel_mlp_fused_backward (x2),
+//     5 CUTLASS split-K weight-gradient GEMMs, add_density_gradient, transpose, kernel_grid_backward in the reference.
+//   Here: activations live in shared memory for the tile's lifetime, every contraction (forward, data gradient, weight
+//   gradient) is a tcgen05.mma with fp32 accumulation in TMEM, weight gradients accumulate in TMEM across all tiles of
+//   the CTA and leave the SM once, hash-grid gradients go out as fp16x2 reductions exactly like grid.h:252-255.
+// ----------------------------------------------------------------------------------------------------------------
+struct TrainSmem {
+	uint32_t w_bytes;
+	uint32_t a0_off;               // [128 x 32] encoding
+	uint32_t hd_off;               // n_hidden_density x [128 x 64]
+	uint32_t a2_off;               // [128 x 32]
+	uint32_t hr_off;               // n_hidden_rgb x [128 x 64]
+	uint32_t g64_off;              // [128 x 64] dL/d(hidden pre-activation), reused layer by layer
+	uint32_t g16_off;              // [128 x 16] dL/d(output layer output)
+	uint32_t bar_off;
+	uint32_t total;
+};
+__host__ __device__ inline TrainSmem train_smem_layout(uint32_t nhd, uint32_t nhr) {
+	TrainSmem s;
+	s.w_bytes = (mlp_n_params(nhd) + mlp_n_params(nhr)) * 2u;
+	s.a0_off = s.w_bytes;
+	s.hd_off = s.a0_off + TILE * ENC_WIDTH * 2u;
+	s.a2_off = s.hd_off + nhd * TILE * MLP_WIDTH * 2u;
+	s.hr_off = s.a2_off + TILE * ENC_WIDTH * 2u;
+	s.g64_off = s.hr_off + nhr * TILE * MLP_WIDTH * 2u;
+	s.g16_off = s.g64_off + TILE * MLP_WIDTH * 2u;
+	s.bar_off = s.g16_off + TILE * MLP_OUT * 2u;
+	s.total = s.bar_off + 16u;
+	return s;
+}
+
+// TMEM column map of the training kernel: [0,64) working accumulator, then one weight-gradient accumulator per layer.
+// Hidden layers hold dW [64(out) x K(in)] (K columns); 16-wide output layers hold dW^T [64(in) x 16(out)] (16 columns).
+__host__ __device__ inline uint32_t wgrad_cols(uint32_t n_hidden, uint32_t l) { return l == n_hidden ? MLP_OUT : mlp_layer_in(n_hidden, l); }
+__host__ __device__ inline uint32_t wgrad_col_base(uint32_t nhd, uint32_t nhr, bool rgb, uint32_t l) {
+	uint32_t c = 64;
+	if (rgb) {
+		for (uint32_t i = 0; i <= nhd; ++i) c += wgrad_cols(nhd, i);
+		for (uint32_t i = 0; i < l; ++i) c += wgrad_cols(nhr, i);
+	} else {
+		for (uint32_t i = 0; i < l; ++i) c += wgrad_cols(nhd, i);
+	}
+	return c;
+}
+__host__ __device__ inline uint32_t train_tmem_cols(uint32_t nhd, uint32_t nhr) { return wgrad_col_base(nhd, nhr, true, nhr + 1); }
+
+// forward of one MLP keeping every hidden activation: layer l writes hidden buffer l.
+__device__ __forceinline__ void run_mlp_fwd_keep(
+	uint8_t* smem, uint32_t in_off, uint32_t hid_off, uint32_t w_off, uint32_t n_hidden, uint32_t tmem_base, uint64_t* bar, uint32_t& phase,
+	uint32_t tid, __half2 (&out)[8]
+) {
+	const uint32_t smem_base = umma::smem_u32(smem);
+	const uint32_t lane_taddr = tmem_base + ((tid & ~31u) << 16);
+	for (uint32_t l = 0; l <= n_hidden; ++l) {
+		const uint32_t K = mlp_layer_in(n_hidden, l), N = mlp_layer_out(n_hidden, l);
+		const uint32_t a_off = (l == 0) ? in_off : hid_off + (l - 1) * TILE * MLP_WIDTH * 2u;
+		umma::fence_smem_to_async();
+		umma::fence_before_sync();
+		__syncthreads();
+		if (tid == 0) {
+			umma::fence_after_sync();
+			issue_layer_fwd(smem_base + a_off, K, smem_base + w_off + mlp_layer_off(n_hidden, l) * 2u, N, tmem_base, bar);
+		}
+		umma::mbar_wait(bar, phase);
+		phase ^= 1u;
+		umma::fence_after_sync();
+		if (l < n_hidden) {
+			tmem_row_to_smem64<true>(lane_taddr, smem + hid_off + l * TILE * MLP_WIDTH * 2u, tid);
+		} else {
+			tmem_row_to_regs16(lane_taddr, out);
+		}
+	}
+}
+
+// backward of one MLP.  On entry g16 holds dL/d(output) [128 x 16].  For every layer, weight gradient and data
+// gradient are issued back to back and waited for together.  Returns this thread's row of dL/d(mlp input) (32 fp32).
+__device__ __forceinline__ void run_mlp_bwd(
+	uint8_t* smem, uint32_t in_off, uint32_t hid_off, uint32_t g64_off, uint32_t g16_off, uint32_t w_off, uint32_t n_hidden, uint32_t tmem_base,
+	uint32_t wg_col0, uint32_t wg_accumulate, uint64_t* bar, uint32_t& phase, uint32_t tid, float (&dx)[32]
+) {
+	const uint32_t smem_base = umma::smem_u32(smem);
+	const uint32_t lane_taddr = tmem_base + ((tid & ~31u) << 16);
+	// column base of each layer's weight-gradient accumulator
+	uint32_t wg_col[MAX_HIDDEN + 1];
+	{
+		uint32_t c = wg_col0;
+		for (uint32_t l = 0; l <= n_hidden; ++l) {
+			wg_col[l] = c;
+			c += wgrad_cols(n_hidden, l);
+		}
+	}
+	for (int32_t l = (int32_t)n_hidden; l >= 0; --l) {
+		const uint32_t K = mlp_layer_in(n_hidden, l), N = mlp_layer_out(n_hidden, l);
+		const uint32_t x_off = (l == 0) ? in_off : hid_off + (l - 1) * TILE * MLP_WIDTH * 2u;
+		const uint32_t dy_off = ((uint32_t)l == n_hidden) ? g16_off : g64_off;
+		umma::fence_smem_to_async();
+		umma::fence_before_sync();
+		__syncthreads();
+		if (tid == 0) {
+			umma::fence_after_sync();
+			if ((uint32_t)l == n_hidden) {
+				issue_wgrad(smem_base + x_off, MLP_WIDTH, smem_base + dy_off, MLP_OUT, tmem_base + wg_col[l], wg_accumulate);  // dW^T [in x out]
+			} else {
+				issue_wgrad(smem_base + dy_off, MLP_WIDTH, smem_base + x_off, K, tmem_base + wg_col[l], wg_accumulate);  // dW [out x in]
+			}
+			issue_layer_dgrad(smem_base + dy_off, N, smem_base + w_off + mlp_layer_off(n_hidden, l) * 2u, K, tmem_base, bar);
+		}
+		umma::mbar_wait(bar, phase);
+		phase ^= 1u;
+		umma::fence_after_sync();
+		if (l > 0) {
+			// dL/d(hidden l-1 pre-activation) = dX * (hidden_{l-1} > 0)  -> g64
+			uint32_t v0[16], v1[16], v2[16], v3[16];
+			umma::tmem_ld16(lane_taddr + 0, v0);
+			umma::tmem_ld16(lane_taddr + 16, v1);
+			umma::tmem_ld16(lane_taddr + 32, v2);
+			umma::tmem_ld16(lane_taddr + 48, v3);
+			umma::tmem_ld_wait();
+			const uint8_t* act = smem + x_off;
+			uint8_t* g = smem + g64_off;
+			auto emit = [&](const uint32_t(&v)[16], uint32_t kc0) {
+#pragma unroll
+				for (uint32_t c = 0; c < 2; ++c) {
+					const uint4 a = *reinterpret_cast<const uint4*>(act + (kc0 + c) * (TILE * 16u) + tid * 16u);
+					const __half2 ah[4] = {*reinterpret_cast<const __half2*>(&a.x), *reinterpret_cast<const __half2*>(&a.y),
+						*reinterpret_cast<const __half2*>(&a.z), *reinterpret_cast<const __half2*>(&a.w)};
+					__half2 h[4];
+#pragma unroll
+					for (uint32_t j = 0; j < 4; ++j) {
+						const __half2 t = __floats2half2_rn(__uint_as_float(v[c * 8 + 2 * j]), __uint_as_float(v[c * 8 + 2 * j + 1]));
+						const __half2 m = __hgt2(ah[j], __float2half2_rn(0.0f));  // 1.0 where act > 0
+						h[j] = __hmul2(t, m);
+					}
+					store_chunk(g, tid, kc0 + c, h);
+				}
+			};
+			emit(v0, 0);
+			emit(v1, 2);
+			emit(v2, 4);
+			emit(v3, 6);
+		} else {
+			uint32_t v0[16], v1[16];
+			umma::tmem_ld16(lane_taddr + 0, v0);
+			umma::tmem_ld16(lane_taddr + 16, v1);
+			umma::tmem_ld_wait();
+#pragma unroll
+			for (uint32_t j = 0; j < 16; ++j) {
+				dx[j] = __uint_as_float(v0[j]);
+				dx[16 + j] = __uint_as_float(v1[j]);
+			}
+		}
+	}
+}
+
+// scatter dL/d(encoding) of one sample into the fp16 gradient table (≙ kernel_grid_backward, grid.h:214-320).
+template <uint32_t F>
+__device__ __forceinline__ void grid_scatter(const NetDev& net, __half* __restrict__ grid_grad, float x, float y, float z, const __half2 (&g)[16]) {
+	constexpr uint32_t H2_PER_LEVEL = F / 2;
+	const uint32_t n_levels = ENC_WIDTH / F;
+#pragma unroll 2
+	for (uint32_t l = 0; l < n_levels; ++l) {
+		const LevelMeta lv = net.levels[l];
+		const float px = fmaf(lv.scale, x, 0.5f), py = fmaf(lv.scale, y, 0.5f), pz = fmaf(lv.scale, z, 0.5f);
+		const float fx = floorf(px), fy = floorf(py), fz = floorf(pz);
+		const uint32_t gx = (uint32_t)(int)fx, gy = (uint32_t)(int)fy, gz = (uint32_t)(int)fz;
+		const float wx1 = px - fx, wy1 = py - fy, wz1 = pz - fz;
+		const float wx0 = 1.0f - wx1, wy0 = 1.0f - wy1, wz0 = 1.0f - wz1;
+		__half2* lgrad = reinterpret_cast<__half2*>(grid_grad + (size_t)lv.offset * F);
+#pragma unroll
+		for (uint32_t c = 0; c < 8; ++c) {
+			const uint32_t cx = gx + (c & 1u), cy = gy + ((c >> 1) & 1u), cz = gz + ((c >> 2) & 1u);
+			const uint32_t idx = grid_index_3d(cx, cy, cz, lv.resolution, lv.size, lv.dense != 0);
+			const float w = ((c & 1u) ? wx1 : wx0) * ((c & 2u) ? wy1 : wy0) * ((c & 4u) ? wz1 : wz0);
+			const __half2 wh = __float2half2_rn(w);
+#pragma unroll
+			for (uint32_t h = 0; h < H2_PER_LEVEL; ++h) {
+				atomicAdd(lgrad + (size_t)idx * H2_PER_LEVEL + h, __hmul2(wh, g[l * H2_PER_LEVEL + h]));
+			}
+		}
+	}
+}
+
+template <uint32_t F, uint32_t TMEM_COLS>
+__global__ void __launch_bounds__(TILE, 2) k_nerf_train(
+	const __grid_constant__ NetDev net, const uint32_t n, const float* __restrict__ coords, const __half* __restrict__ params,
+	const __half* __restrict__ dL_dout, __half* __restrict__ grads, float* __restrict__ mlp_grads_f32, __half* __restrict__ out
+) {
+	extern __shared__ __align__(128) uint8_t smem[];
+	const uint32_t nhd = net.n_hidden_density, nhr = net.n_hidden_rgb;
+	const TrainSmem L = train_smem_layout(nhd, nhr);
+	const uint32_t tid = threadIdx.x;
+	uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L.bar_off);
+	uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L.bar_off + 8);
+	const uint32_t wr_off = mlp_n_params(nhd) * 2u;
+
+	for (uint32_t l = 0; l <= nhd; ++l)
+		stage_weights(params + net.density_off + mlp_layer_off(nhd, l), mlp_layer_out(nhd, l), mlp_layer_in(nhd, l), smem + mlp_layer_off(nhd, l) * 2u, tid, TILE);
+	for (uint32_t l = 0; l <= nhr; ++l)
+		stage_weights(params + net.rgb_off + mlp_layer_off(nhr, l), mlp_layer_out(nhr, l), mlp_layer_in(nhr, l), smem + wr_off + mlp_layer_off(nhr, l) * 2u, tid, TILE);
+	if (tid < 32) umma::tmem_alloc<TMEM_COLS>(tmem_slot);
+	if (tid == 0) {
+		umma::mbar_init(bar, 1);
+		umma::mbar_fence_init();
+	}
+	umma::fence_before_sync();
+	__syncthreads();
+	umma::fence_after_sync();
+	const uint32_t tmem_base = *tmem_slot;
+	uint32_t phase = 0;
+
+	const __half* grid = params + net.grid_off;
+	__half* grid_grad = grads + net.grid_off;
+	const uint32_t n_tiles = n / TILE;
+	uint32_t iter = 0;
+	for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++iter) {
+		const uint32_t i = tile * TILE + tid;
+		const float* c = coords + (size_t)i * 7;
+		const float x = c[0], y = c[1], z = c[2];
+		{
+			__half2 enc[16];
+			grid_gather<F>(net, grid, x, y, z, enc);
+#pragma unroll
+			for (uint32_t kc = 0; kc < 4; ++kc) {
+				const __half2 h[4] = {enc[kc * 4 + 0], enc[kc * 4 + 1], enc[kc * 4 + 2], enc[kc * 4 + 3]};
+				store_chunk(smem + L.a0_off, tid, kc, h);
+			}
+			__half2 sh[8];
+			sh4_encode(c[4], c[5], c[6], sh);
+			const __half2 h0[4] = {sh[0], sh[1], sh[2], sh[3]};
+			const __half2 h1[4] = {sh[4], sh[5], sh[6], sh[7]};
+			store_chunk(smem + L.a2_off, tid, 2, h0);
+			store_chunk(smem + L.a2_off, tid, 3, h1);
+		}
+		// ---------------- forward
+		__half2 dens[8], rgb[8];
+		run_mlp_fwd_keep(smem, L.a0_off, L.hd_off, 0, nhd, tmem_base, bar, phase, tid, dens);
+		{
+			const __half2 h0[4] = {dens[0], dens[1], dens[2], dens[3]};
+			const __half2 h1[4] = {dens[4], dens[5], dens[6], dens[7]};
+			store_chunk(smem + L.a2_off, tid, 0, h0);
+			store_chunk(smem + L.a2_off, tid, 1, h1);
+		}
+		run_mlp_fwd_keep(smem, L.a2_off, L.hr_off, wr_off, nhr, tmem_base, bar, phase, tid, rgb);
+		if (out) {
+			uint2 o;
+			o.x = *reinterpret_cast<const uint32_t*>(&rgb[0]);
+			const __half2 t = __halves2half2(__low2half(rgb[1]), __low2half(dens[0]));
+			o.y = *reinterpret_cast<const uint32_t*>(&t);
+			*reinterpret_cast<uint2*>(out + (size_t)i * 4) = o;
+		}
+
+		// ---------------- backward
+		const uint2 dl = __ldg(reinterpret_cast<const uint2*>(dL_dout + (size_t)i * 4));
+		const __half2 dl01 = *reinterpret_cast<const __half2*>(&dl.x);  // d rgb0, d rgb1
+		const __half2 dl23 = *reinterpret_cast<const __half2*>(&dl.y);  // d rgb2, d density
+		{
+			const __half2 zero = __float2half2_rn(0.0f);
+			const __half2 h0[4] = {dl01, __halves2half2(__low2half(dl23), __float2half_rn(0.0f)), zero, zero};
+			const __half2 h1[4] = {zero, zero, zero, zero};
+			store_chunk(smem + L.g16_off, tid, 0, h0);
+			store_chunk(smem + L.g16_off, tid, 1, h1);
+		}
+		float dx[32];
+		run_mlp_bwd(smem, L.a2_off, L.hr_off, L.g64_off, L.g16_off, wr_off, nhr, tmem_base, wgrad_col_base(nhd, nhr, true, 0), iter > 0 ? 1u : 0u, bar,
+			phase, tid, dx);
+		{
+			// dL/d(density-net output) = first 16 columns of dL/d(rgb-net input); the density gradient joins column 0 in fp16
+			// (add_density_gradient, nerf_network.h:62-74).
+			__half2 h[8];
+#pragma unroll
+			for (uint32_t j = 0; j < 8; ++j) h[j] = __floats2half2_rn(dx[2 * j], dx[2 * j + 1]);
+			h[0] = __halves2half2(__hadd(__low2half(h[0]), __high2half(dl23)), __high2half(h[0]));
+			const __half2 h0[4] = {h[0], h[1], h[2], h[3]};
+			const __half2 h1[4] = {h[4], h[5], h[6], h[7]};
+			store_chunk(smem + L.g16_off, tid, 0, h0);
+			store_chunk(smem + L.g16_off, tid, 1, h1);
+		}
+		run_mlp_bwd(smem, L.a0_off, L.hd_off, L.g64_off, L.g16_off, 0, nhd, tmem_base, wgrad_col_base(nhd, nhr, false, 0), iter > 0 ? 1u : 0u, bar, phase,
+			tid, dx);
+		{
+			__half2 g[16];
+#pragma unroll
+			for (uint32_t j = 0; j < 16; ++j) g[j] = __floats2half2_rn(dx[2 * j], dx[2 * j + 1]);
+			grid_scatter<F>(net, grid_grad, x, y, z, g);
+		}
+	}
+
+	// ---------------- flush the weight-gradient accumulators (M = 64 accumulator layout: row m sits in TMEM lane
+	// (m % 16) + 32 * (m / 16), i.e. the low 16 lanes of each warp's 32-lane window)
+	umma::fence_before_sync();
+	__syncthreads();
+	umma::fence_after_sync();
+	if (iter > 0) {
+		const uint32_t warp = tid >> 5, lane = tid & 31u;
+		const uint32_t row = warp * 16u + lane;  // valid for lane < 16
+		const uint32_t lane_taddr = tmem_base + ((tid & ~31u) << 16);
+		for (uint32_t net_i = 0; net_i < 2; ++net_i) {
+			const uint32_t nh = net_i ? nhr : nhd;
+			const uint32_t goff = net_i ? net.rgb_off : net.density_off;
+			for (uint32_t l = 0; l <= nh; ++l) {
+				const uint32_t cols = wgrad_cols(nh, l);
+				const uint32_t cbase = wgrad_col_base(nhd, nhr, net_i != 0, l);
+				const uint32_t K = mlp_layer_in(nh, l);
+				float* dst = mlp_grads_f32 + goff + mlp_layer_off(nh, l);
+				for (uint32_t c0 = 0; c0 < cols; c0 += 16) {
+					uint32_t v[16];
+					umma::tmem_ld16(lane_taddr + cbase + c0, v);
+					umma::tmem_ld_wait();
+					if (lane < 16) {
+#pragma unroll
+						for (uint32_t j = 0; j < 16; ++j) {
+							const uint32_t col = c0 + j;
+							// hidden layer: accumulator = dW[out=row][in=col]; output layer: accumulator = dW^T[in=row][out=col]
+							const uint32_t idx = (l == nh) ? (col * MLP_WIDTH + row) : (row * K + col);
+							atomicAdd(dst + idx, __uint_as_float(v[j]));
+						}
+					}
+				}
+			}
+		}
+	}
+	umma::fence_before_sync();
+	__syncthreads();
+	if (tid < 32) umma::tmem_dealloc<TMEM_COLS>(tmem_base);
+}
+
+__global__ void k_mlp_grads_finalize(const uint32_t n, float* __restrict__ src, __half* __restrict__ dst) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	dst[i] = __float2half_rn(src[i]);
+	src[i] = 0.0f;
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// host side
+// ----------------------------------------------------------------------------------------------------------------
+NetDev make_netdev(const ngp_nerf_desc& d) {
+	NetDev n{};
+	const ngp_grid_desc& g = d.grid;
+	NGPB_CHECK(g.n_features_per_level == 2 || g.n_features_per_level == 4, "HashGrid: n_features_per_level must be 2 or 4 in this build");
+	NGPB_CHECK(g.n_levels * g.n_features_per_level == ENC_WIDTH, "HashGrid: n_levels * n_features_per_level must be 32");
+	NGPB_CHECK(g.n_levels <= MAX_DEV_LEVELS, "HashGrid: too many levels");
+	NGPB_CHECK(d.n_hidden_density >= 1 && d.n_hidden_density <= MAX_HIDDEN, "density network: 1..4 hidden layers supported");
+	NGPB_CHECK(d.n_hidden_rgb >= 1 && d.n_hidden_rgb <= MAX_HIDDEN, "rgb network: 1..4 hidden layers supported");
+	n.n_levels = g.n_levels;
+	n.n_features = g.n_features_per_level;
+	for (uint32_t l = 0; l < g.n_levels; ++l) {
+		LevelMeta& m = n.levels[l];
+		m.offset = g.offsets[l];
+		m.size = g.offsets[l + 1] - g.offsets[l];
+		m.resolution = g.resolutions[l];
+		m.scale = g.scales[l];
+		m.dense = level_is_dense_3d(m.resolution, m.size) ? 1u : 0u;
+	}
+	n.n_hidden_density = d.n_hidden_density;
+	n.n_hidden_rgb = d.n_hidden_rgb;
+	n.density_off = d.density_mlp_offset;
+	n.rgb_off = d.rgb_mlp_offset;
+	n.grid_off = d.grid_offset;
+	n.n_mlp_params = d.n_mlp_params;
+	return n;
+}
+
+int device_sm_count() {
+	static int sms = 0;
+	if (!sms) {
+		int dev = 0;
+		NGPB_CUDA_CHECK(cudaGetDevice(&dev));
+		NGPB_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+	}
+	return sms;
+}
+
+template <uint32_t F, bool DENSITY_ONLY>
+static void launch_forward(const NetDev& net, cudaStream_t stream, uint32_t n, const uint32_t* n_dev, const float* in, uint32_t in_stride,
+	uint32_t dir_offset, const __half* params, __half* out, uint32_t out_stride) {
+	if (n == 0) return;
+	const FwdSmem L = fwd_smem_layout(net.n_hidden_density, net.n_hidden_rgb);
+	auto kern = k_nerf_forward<F, DENSITY_ONLY>;
+	static bool attr_set = false;
+	if (!attr_set) {
+		NGPB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+		attr_set = true;
+	}
+	NGPB_CHECK(L.total <= 100 * 1024, "MLP too large for the forward kernel's shared memory budget");
+	const uint32_t n_tiles = div_round_up(n, TILE);
+	const uint32_t max_ctas = (uint32_t)device_sm_count() * 4u;
+	const uint32_t grid = n_tiles < max_ctas ? n_tiles : max_ctas;
+	kern<<<grid, TILE, L.total, stream>>>(net, n, n_dev, in, in_stride, dir_offset, params, out, out_stride);
+	NGPB_LAUNCHED();
+	NGPB_CUDA_CHECK(cudaGetLastError());
+}
+
+void nerf_inference(const ngp_nerf_desc& d, cudaStream_t stream, uint32_t n, const float* coords, const __half* params, __half* out,
+	uint32_t out_stride) {
+	NGPB_CHECK(out_stride >= 4 && (out_stride % 4) == 0, "ngp_nerf_inference: out_stride must be a multiple of 4 (>= 4)");
+	const NetDev net = make_netdev(d);
+	if (net.n_features == 2) {
+		launch_forward<2, false>(net, stream, n, nullptr, coords, 7, 4, params, out, out_stride);
+	} else {
+		launch_forward<4, false>(net, stream, n, nullptr, coords, 7, 4, params, out, out_stride);
+	}
+}
+
+// inference over min(*n_dev, n_max) samples, 4 halves per output row
+void nerf_inference_counted(const ngp_nerf_desc& d, cudaStream_t stream, uint32_t n_max, const uint32_t* n_dev, const float* coords,
+	const __half* params, __half* out) {
+	const NetDev net = make_netdev(d);
+	if (net.n_features == 2) {
+		launch_forward<2, false>(net, stream, n_max, n_dev, coords, 7, 4, params, out, 4);
+	} else {
+		launch_forward<4, false>(net, stream, n_max, n_dev, coords, 7, 4, params, out, 4);
+	}
+}
+
+void nerf_density(const ngp_nerf_desc& d, cudaStream_t stream, uint32_t n, const float* positions, uint32_t pos_stride, const __half* params,
+	__half* out) {
+	NGPB_CHECK(pos_stride >= 3, "ngp_nerf_density: pos_stride must be >= 3");
+	const NetDev net = make_netdev(d);
+	if (net.n_features == 2) {
+		launch_forward<2, true>(net, stream, n, nullptr, positions, pos_stride, 0, params, out, 1);
+	} else {
+		launch_forward<4, true>(net, stream, n, nullptr, positions, pos_stride, 0, params, out, 1);
+	}
+}
+
+void grid_encode(const ngp_grid_desc& g, cudaStream_t stream, uint32_t n, const float* positions, uint32_t pos_stride, const __half* grid,
+	__half* out) {
+	if (n == 0) return;
+	ngp_nerf_desc d{};
+	d.grid = g;
+	d.n_hidden_density = 1;
+	d.n_hidden_rgb = 1;
+	const NetDev net = make_netdev(d);
+	const uint32_t blocks = div_round_up(n, 256);
+	if (net.n_features == 2) {
+		k_grid_encode<2><<<blocks, 256, 0, stream>>>(net, n, positions, pos_stride, grid, out);
+	} else {
+		k_grid_encode<4><<<blocks, 256, 0, stream>>>(net, n, positions, pos_stride, grid, out);
+	}
+	NGPB_LAUNCHED();
+	NGPB_CUDA_CHECK(cudaGetLastError());
+}
+
+
+template <uint32_t F, uint32_t TMEM_COLS>
+static void launch_train(const NetDev& net, cudaStream_t stream, uint32_t n, const float* coords, const __half* params, const __half* dL_dout,
+	__half* grads, float* mlp_grads_f32, __half* out) {
+	const TrainSmem L = train_smem_layout(net.n_hidden_density, net.n_hidden_rgb);
+	auto kern = k_nerf_train<F, TMEM_COLS>;
+	static bool attr_set = false;
+	if (!attr_set) {
+		NGPB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+		attr_set = true;
+	}
+	NGPB_CHECK(L.total <= 227 * 1024, "MLP too deep for the training kernel's shared memory budget");
+	const uint32_t n_tiles = n / TILE;
+	// resident CTAs per SM: limited by shared memory and by TMEM columns
+	uint32_t per_sm = (227u * 1024u) / (L.total + 1024u);
+	if (per_sm > 512u / TMEM_COLS) per_sm = 512u / TMEM_COLS;
+	if (per_sm > 2) per_sm = 2;
+	if (per_sm < 1) per_sm = 1;
+	const uint32_t max_ctas = (uint32_t)device_sm_count() * per_sm;
+	const uint32_t grid = n_tiles < max_ctas ? n_tiles : max_ctas;
+	kern<<<grid, TILE, L.total, stream>>>(net, n, coords, params, dL_dout, grads, mlp_grads_f32, out);
+	NGPB_LAUNCHED();
+	NGPB_CUDA_CHECK(cudaGetLastError());
+}
+
+// mlp_grads_f32: device scratch of n_mlp_params floats, all zero on entry (left zeroed on exit).
+void nerf_forward_backward(const ngp_nerf_desc& d, cudaStream_t stream, uint32_t n, const float* coords, const __half* params,
+	const __half* dL_dout, __half* grads, float* mlp_grads_f32, __half* out) {
+	NGPB_CHECK(n % TILE == 0, "ngp_nerf_forward_backward: batch size must be a multiple of 128");
+	if (n == 0) return;
+	const NetDev net = make_netdev(d);
+	const uint32_t cols = train_tmem_cols(net.n_hidden_density, net.n_hidden_rgb);
+	NGPB_CHECK(cols <= 512, "MLP too deep for the training kernel's TMEM budget");
+	if (net.n_features == 2) {
+		if (cols <= 256) launch_train<2, 256>(net, stream, n, coords, params, dL_dout, grads, mlp_grads_f32, out);
+		else launch_train<2, 512>(net, stream, n, coords, params, dL_dout, grads, mlp_grads_f32, out);
+	} else {
+		if (cols <= 256) launch_train<4, 256>(net, stream, n, coords, params, dL_dout, grads, mlp_grads_f32, out);
+		else launch_train<4, 512>(net, stream, n, coords, params, dL_dout, grads, mlp_grads_f32, out);
+	}
+	k_mlp_grads_finalize<<<div_round_up(d.n_mlp_params, 256), 256, 0, stream>>>(d.n_mlp_params, mlp_grads_f32, grads);
+	NGPB_LAUNCHED();
+	NGPB_CUDA_CHECK(cudaGetLastError());
+}
+
+}  // namespace ngpb

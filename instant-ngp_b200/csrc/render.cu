@@ -1,0 +1,300 @@
+// render.cu — NeRF rendering as ONE persistent kernel: ray generation, occupancy-grid marching, fused network
+// evaluation on tensor cores and front-to-back compositing without any HBM round trip for network inputs/outputs and
+// without host synchronisation.
+//
+// ≙ render_nerf (src/testbed_nerf.cu:1894-2150): NerfTracer::init_rays_from_camera (init_rays_with_payload_kernel_nerf
+// :1414-1528 + advance_pos_nerf :398-452), NerfTracer::trace (:1677-1860: compact_kernel_nerf / host sync per round,
+// generate_next_nerf_network_inputs :523-577, inference, composite_kernel_nerf :579-689) and shade_kernel_nerf :1333-1378.
+//
+// Design: a CTA owns 128 ray slots (thread = slot = UMMA row).  Every iteration each live ray advances to its next
+// occupied sample, the 128 samples go through the fused hash-grid + MLP evaluation (tcgen05), and each thread composites
+// its own sample.  A ray that terminates writes its pixel and its slot immediately pulls the next pixel from a global
+// queue, so tiles stay full until the image is exhausted (the reference either re-compacts with a host sync per round or,
+// in its JIT megakernel, lets finished threads idle until the whole warp is done: fused_kernels/render_nerf.cuh:106-167).
+// Per-ray arithmetic is the reference's; the order in which rays are processed does not influence any ray's result.
+#include "march.cuh"
+#include "nerf_net.cuh"
+
+namespace ngpb {
+
+// ---- low-discrepancy jitter (random_val.cuh:162-325): Owen-scrambled Sobol, dimension 0 ---------------------------------
+__host__ __device__ inline uint32_t reverse_bits32(uint32_t x) {
+	x = (((x & 0xaaaaaaaau) >> 1) | ((x & 0x55555555u) << 1));
+	x = (((x & 0xccccccccu) >> 2) | ((x & 0x33333333u) << 2));
+	x = (((x & 0xf0f0f0f0u) >> 4) | ((x & 0x0f0f0f0fu) << 4));
+	x = (((x & 0xff00ff00u) >> 8) | ((x & 0x00ff00ffu) << 8));
+	return (x >> 16) | (x << 16);
+}
+__host__ __device__ inline uint32_t laine_karras_permutation(uint32_t x, uint32_t seed) {
+	x += seed;
+	x ^= x * 0x6c50b47cu;
+	x ^= x * 0xb82f1e52u;
+	x ^= x * 0xc7afe638u;
+	x ^= x * 0x8d22f6e6u;
+	return x;
+}
+__host__ __device__ inline uint32_t nested_uniform_scramble_base2(uint32_t x, uint32_t seed) {
+	return reverse_bits32(laine_karras_permutation(reverse_bits32(x), seed));
+}
+__host__ __device__ inline uint32_t hash_combine(uint32_t seed, uint32_t v) { return seed ^ (v + (seed << 6) + (seed >> 2)); }
+// Sobol dimension 0 has the identity direction matrix in bit-reversed order: sobol(index, 0) == reverse_bits(index).
+__host__ __device__ inline float ld_random_val_dim0(uint32_t index, uint32_t seed) {
+	index = nested_uniform_scramble_base2(index, seed);
+	return (float)nested_uniform_scramble_base2(reverse_bits32(index), hash_combine(seed, 0u)) * 2.3283064365386963e-10f;
+}
+
+struct RenderSmemExtra {
+	uint32_t queue_base;
+};
+
+template <uint32_t F>
+__global__ void __launch_bounds__(TILE, 3) k_render_nerf(
+	const __grid_constant__ NetDev net, const __grid_constant__ ngp_render_cfg cfg, const int32_t y0, const int32_t y1,
+	const __half* __restrict__ params, const uint8_t* __restrict__ bitfield, float* __restrict__ rgba_out, float* __restrict__ depth_out,
+	uint32_t* __restrict__ queue /* [0] next pixel, [1] total steps */
+) {
+	extern __shared__ __align__(128) uint8_t smem[];
+	const FwdSmem L = fwd_smem_layout(net.n_hidden_density, net.n_hidden_rgb);
+	const uint32_t tid = threadIdx.x, lane = tid & 31u;
+	uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L.bar_off);
+	uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L.bar_off + 8);
+	const uint32_t wr_off = mlp_n_params(net.n_hidden_density) * 2u;
+
+	for (uint32_t l = 0; l <= net.n_hidden_density; ++l)
+		stage_weights(params + net.density_off + mlp_layer_off(net.n_hidden_density, l), mlp_layer_out(net.n_hidden_density, l),
+			mlp_layer_in(net.n_hidden_density, l), smem + mlp_layer_off(net.n_hidden_density, l) * 2u, tid, TILE);
+	for (uint32_t l = 0; l <= net.n_hidden_rgb; ++l)
+		stage_weights(params + net.rgb_off + mlp_layer_off(net.n_hidden_rgb, l), mlp_layer_out(net.n_hidden_rgb, l), mlp_layer_in(net.n_hidden_rgb, l),
+			smem + wr_off + mlp_layer_off(net.n_hidden_rgb, l) * 2u, tid, TILE);
+	if (tid < 32) umma::tmem_alloc<64>(tmem_slot);
+	if (tid == 0) {
+		umma::mbar_init(bar, 1);
+		umma::mbar_fence_init();
+	}
+	umma::fence_before_sync();
+	__syncthreads();
+	umma::fence_after_sync();
+	const uint32_t tmem_base = *tmem_slot;
+	uint32_t phase = 0;
+	const __half* grid = params + net.grid_off;
+
+	const Aabb train_aabb{V3{cfg.aabb_min[0], cfg.aabb_min[1], cfg.aabb_min[2]}, V3{cfg.aabb_max[0], cfg.aabb_max[1], cfg.aabb_max[2]}};
+	const Aabb render_aabb{V3{cfg.render_aabb_min[0], cfg.render_aabb_min[1], cfg.render_aabb_min[2]},
+		V3{cfg.render_aabb_max[0], cfg.render_aabb_max[1], cfg.render_aabb_max[2]}};
+	const uint32_t n_pixels = (uint32_t)(y1 - y0) * (uint32_t)cfg.width;
+	const V3 cam_fwd = xform_col(cfg.camera, 2), cam_o = xform_col(cfg.camera, 3);
+
+	// per-slot ray state (NerfPayload + accumulators)
+	bool alive = false;
+	uint32_t pix = 0, n_steps = 0;
+	V3 ro{0, 0, 0}, rd{0, 0, 1}, idir{0, 0, 0};
+	float t = 0.0f, max_weight = 0.0f, depth = 0.0f;
+	float acc_r = 0.0f, acc_g = 0.0f, acc_b = 0.0f, acc_a = 0.0f;
+	bool queue_empty = false;
+	uint32_t local_steps = 0;
+
+	auto finish_ray = [&]() {
+		// shade_kernel_nerf, Shade mode, frame buffer starts at zero: rgb is predicted in sRGB (linear_colors == false)
+		float r = acc_r, g = acc_g, b = acc_b;
+		r = srgb_to_linear(r);
+		g = srgb_to_linear(g);
+		b = srgb_to_linear(b);
+		float4 o = make_float4(r, g, b, acc_a);
+		reinterpret_cast<float4*>(rgba_out)[pix] = o;
+		depth_out[pix] = acc_a > 0.2f ? depth : max_depth();
+		alive = false;
+	};
+
+	for (;;) {
+		// ---- refill empty slots from the pixel queue (one atomic per warp)
+		const bool want = !alive && !queue_empty;
+		const uint32_t want_mask = __ballot_sync(0xFFFFFFFFu, want);
+		if (want_mask) {
+			uint32_t base = 0;
+			if (lane == 0) base = atomicAdd(&queue[0], __popc(want_mask));
+			base = __shfl_sync(0xFFFFFFFFu, base, 0);
+			if (want) {
+				const uint32_t q = base + __popc(want_mask & ((1u << lane) - 1u));
+				if (q >= n_pixels) {
+					queue_empty = true;
+				} else {
+					// init_rays_with_payload_kernel_nerf with snap_to_pixel_centers: pixel offset = 0.5
+					const uint32_t x = q % (uint32_t)cfg.width, y = (uint32_t)y0 + q / (uint32_t)cfg.width;
+					pix = x + (uint32_t)cfg.width * y;
+					const float u = ((float)x + 0.5f) / (float)cfg.width, v = ((float)y + 0.5f) / (float)cfg.height;
+					V3 o, d;
+					uv_to_ray(u, v, cfg.width, cfg.height, cfg.focal_x, cfg.focal_y, cfg.screen_x, cfg.screen_y, NGP_LENS_PERSPECTIVE, nullptr, cfg.camera, o, d);
+					o = o + d * cfg.near_distance;
+					d = normalize3(d);
+					ro = o;
+					rd = d;
+					idir = V3{1.0f / d.x, 1.0f / d.y, 1.0f / d.z};
+					acc_r = acc_g = acc_b = acc_a = 0.0f;
+					max_weight = 0.0f;
+					depth = max_depth();
+					n_steps = 0;
+					float tmin, tmax;
+					aabb_ray_intersect(render_aabb, o, d, tmin, tmax);
+					float t0 = fmaxf(tmin, 0.0f) + 1e-6f;
+					alive = render_aabb.contains(o + t0 * d);
+					if (alive) {
+						// advance_pos_nerf: jittered first step (ld_random_val(sample_index, idx * 786433))
+						t = advance_n_steps(t0, cfg.march, ld_random_val_dim0(cfg.spp_index, pix * 786433u));
+					} else {
+						reinterpret_cast<float4*>(rgba_out)[pix] = make_float4(0.f, 0.f, 0.f, 0.f);
+						depth_out[pix] = max_depth();
+					}
+				}
+			}
+		}
+
+		// ---- march to the next occupied sample (if_unoccupied_advance_to_next_occupied_voxel, MIP_FROM_DT = false)
+		bool has_sample = false;
+		V3 pos{0.5f, 0.5f, 0.5f};
+		float dt = 0.0f;
+		if (alive) {
+			for (;;) {
+				pos = ro + t * rd;
+				if (t >= max_depth() || !render_aabb.contains(pos)) {
+					t = max_depth();
+					break;
+				}
+				uint32_t mip = mip_from_pos(pos, NGP_NERF_CASCADES - 1);
+				mip = mip > cfg.max_cascade ? cfg.max_cascade : mip;  // clamp(mip, min_mip = 0, max_mip)
+				if (density_grid_occupied_at(pos, bitfield, mip)) {
+					has_sample = true;
+					break;
+				}
+				while (mip < cfg.max_cascade && !density_grid_occupied_at(pos, bitfield, mip + 1)) ++mip;
+				t = advance_to_next_voxel(t, cfg.march, pos, rd, idir, mip);
+			}
+			if (!has_sample) finish_ray();
+		}
+		const uint32_t any_sample = __syncthreads_or(has_sample ? 1 : 0);
+		const uint32_t any_pending = __syncthreads_or((alive || !queue_empty) ? 1 : 0);
+		if (!any_sample) {
+			if (!any_pending) break;
+			continue;
+		}
+
+		// ---- network: encode + MLPs for the tile
+		float wx = 0.5f, wy = 0.5f, wz = 0.5f;
+		if (has_sample) {
+			dt = calc_dt(t, cfg.march);
+			const V3 wp = warp_position(pos, train_aabb);
+			wx = wp.x; wy = wp.y; wz = wp.z;
+		}
+		{
+			__half2 enc[16];
+			grid_gather<F>(net, grid, wx, wy, wz, enc);
+#pragma unroll
+			for (uint32_t kc = 0; kc < 4; ++kc) {
+				const __half2 h[4] = {enc[kc * 4 + 0], enc[kc * 4 + 1], enc[kc * 4 + 2], enc[kc * 4 + 3]};
+				store_chunk(smem + L.a0_off, tid, kc, h);
+			}
+			const V3 wd = warp_direction(rd);
+			__half2 sh[8];
+			sh4_encode(wd.x, wd.y, wd.z, sh);
+			const __half2 h0[4] = {sh[0], sh[1], sh[2], sh[3]};
+			const __half2 h1[4] = {sh[4], sh[5], sh[6], sh[7]};
+			store_chunk(smem + L.a2_off, tid, 2, h0);
+			store_chunk(smem + L.a2_off, tid, 3, h1);
+		}
+		__half2 dens[8], rgbh[8];
+		run_mlp_fwd(smem, L.a0_off, L.h_off, 0, net.n_hidden_density, tmem_base, bar, phase, tid, dens);
+		{
+			const __half2 h0[4] = {dens[0], dens[1], dens[2], dens[3]};
+			const __half2 h1[4] = {dens[4], dens[5], dens[6], dens[7]};
+			store_chunk(smem + L.a2_off, tid, 0, h0);
+			store_chunk(smem + L.a2_off, tid, 1, h1);
+		}
+		run_mlp_fwd(smem, L.a2_off, L.h_off, wr_off, net.n_hidden_rgb, tmem_base, bar, phase, tid, rgbh);
+
+		// ---- composite (composite_kernel_nerf :621-680); inputs round-trip through fp32 warp/unwarp like the reference
+		if (has_sample) {
+			++n_steps;
+			++local_steps;
+			const float o0 = __low2float(rgbh[0]), o1 = __high2float(rgbh[0]), o2 = __low2float(rgbh[1]), o3 = __low2float(dens[0]);
+			const float T = 1.0f - acc_a;
+			const float dtu = unwarp_dt(warp_dt(dt));
+			const float alpha = 1.0f - ngp_expf(-network_to_density(o3, cfg.density_activation) * dtu);
+			const float weight = alpha * T;
+			acc_r += network_to_rgb(o0, cfg.rgb_activation) * weight;
+			acc_g += network_to_rgb(o1, cfg.rgb_activation) * weight;
+			acc_b += network_to_rgb(o2, cfg.rgb_activation) * weight;
+			acc_a += weight;
+			if (weight > max_weight) {
+				max_weight = weight;
+				const V3 p = unwarp_position(V3{wx, wy, wz}, train_aabb);
+				depth = dot3(cam_fwd, p - cam_o);
+			}
+			t += dt;
+			if (acc_a > (1.0f - cfg.min_transmittance)) {
+				acc_r /= acc_a;
+				acc_g /= acc_a;
+				acc_b /= acc_a;
+				acc_a /= acc_a;
+				finish_ray();
+			}
+		}
+	}
+
+	// total network evaluations, for Mrays/s and steps/ray reporting
+#pragma unroll
+	for (uint32_t o = 16; o > 0; o >>= 1) local_steps += __shfl_xor_sync(0xFFFFFFFFu, local_steps, o);
+	if (lane == 0 && local_steps) atomicAdd(&queue[1], local_steps);
+
+	umma::fence_before_sync();
+	__syncthreads();
+	if (tid < 32) umma::tmem_dealloc<64>(tmem_base);
+}
+
+size_t render_scratch_bytes(int32_t, int32_t) { return 256; }
+
+void render_nerf(const ngp_nerf_desc& d, cudaStream_t stream, const ngp_render_cfg& cfg, int32_t y0, int32_t y1, const __half* params,
+	const uint8_t* bitfield, float* rgba, float* depth, void* scratch, uint32_t* n_steps_total) {
+	NGPB_CHECK(cfg.width > 0 && cfg.height > 0 && y0 >= 0 && y1 <= cfg.height && y0 < y1, "render: bad tile");
+	const NetDev net = make_netdev(d);
+	const FwdSmem L = fwd_smem_layout(net.n_hidden_density, net.n_hidden_rgb);
+	uint32_t* queue = reinterpret_cast<uint32_t*>(scratch);
+	NGPB_CUDA_CHECK(cudaMemsetAsync(queue, 0, 16, stream));
+	const uint32_t n_pixels = (uint32_t)(y1 - y0) * (uint32_t)cfg.width;
+	const uint32_t n_tiles = div_round_up(n_pixels, TILE);
+	const uint32_t max_ctas = (uint32_t)device_sm_count() * 3u;
+	const uint32_t grid = n_tiles < max_ctas ? n_tiles : max_ctas;
+	if (net.n_features == 2) {
+		auto kern = k_render_nerf<2>;
+		static bool attr = false;
+		if (!attr) { NGPB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); attr = true; }
+		kern<<<grid, TILE, L.total, stream>>>(net, cfg, y0, y1, params, bitfield, rgba, depth, queue);
+	} else {
+		auto kern = k_render_nerf<4>;
+		static bool attr = false;
+		if (!attr) { NGPB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); attr = true; }
+		kern<<<grid, TILE, L.total, stream>>>(net, cfg, y0, y1, params, bitfield, rgba, depth, queue);
+	}
+	NGPB_LAUNCHED();
+	NGPB_CUDA_CHECK(cudaGetLastError());
+	if (n_steps_total) NGPB_CUDA_CHECK(cudaMemcpyAsync(n_steps_total, queue + 1, 4, cudaMemcpyDeviceToDevice, stream));
+}
+
+// sum of n floats in a fixed order (1024 strided partials, then sequential) — NerfCounters::update_after_training's
+// reduce_sum(loss) (testbed_nerf.cu:2693-2696), made order-deterministic.
+__global__ void k_sum_partial(const float* __restrict__ data, uint32_t n, float* __restrict__ partial) {
+	const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+	float s = 0.0f;
+	for (uint32_t i = t; i < n; i += 1024) s += data[i];
+	partial[t] = s;
+}
+float reduce_sum_f32(cudaStream_t stream, const float* data, uint32_t n, float* scratch_dev) {
+	k_sum_partial<<<4, 256, 0, stream>>>(data, n, scratch_dev);
+	NGPB_LAUNCHED();
+	float host[1024];
+	NGPB_CUDA_CHECK(cudaMemcpyAsync(host, scratch_dev, sizeof(host), cudaMemcpyDeviceToHost, stream));
+	NGPB_CUDA_CHECK(cudaStreamSynchronize(stream));
+	float s = 0.0f;
+	for (int i = 0; i < 1024; ++i) s += host[i];
+	return s;
+}
+
+}  // namespace ngpb

@@ -1,0 +1,1069 @@
+// testbed.cu — host-side Testbed for the NeRF path and the extern "C" boundary (include/ngp_b200.h).
+// Mirrors the parts of Testbed the hot path needs: reset_network (src/testbed.cu:4160-4412), train (:4561-4647),
+// train_nerf / train_nerf_step / training_prep_nerf / NerfCounters (src/testbed_nerf.cu:2669-3398).
+#include <cmath>
+#include <cstring>
+#include <fstream>
+#include <random>
+#include <sstream>
+#include <vector>
+
+#include "common.cuh"
+#include "json_mini.h"
+#include "march.cuh"
+
+namespace ngpb {
+
+unsigned long long g_launch_count = 0;
+static thread_local std::string g_last_error;
+void set_last_error(const std::string& msg) { g_last_error = msg; }
+
+// kernels' host launchers (nerf_net.cu, march.cu, optimizer.cu, render.cu)
+void nerf_inference(const ngp_nerf_desc& d, cudaStream_t stream, uint32_t n, const float* coords, const __half* params, __half* out, uint32_t out_stride);
+void nerf_inference_counted(const ngp_nerf_desc& d, cudaStream_t stream, uint32_t n_max, const uint32_t* n_dev, const float* coords, const __half* params, __half* out);
+void nerf_density(const ngp_nerf_desc& d, cudaStream_t stream, uint32_t n, const float* positions, uint32_t pos_stride, const __half* params, __half* out);
+void grid_encode(const ngp_grid_desc& g, cudaStream_t stream, uint32_t n, const float* positions, uint32_t pos_stride, const __half* grid, __half* out);
+void nerf_forward_backward(const ngp_nerf_desc& d, cudaStream_t stream, uint32_t n, const float* coords, const __half* params, const __half* dL_dout,
+	__half* grads, float* mlp_grads_f32, __half* out);
+void optimizer_step(const ngp_nerf_desc& d, cudaStream_t stream, const ngp_adam_cfg& cfg, float* params_fp32, __half* params_fp16, __half* params_ema,
+	__half* grads, float* m1, float* m2, uint32_t* steps);
+void generate_training_samples(cudaStream_t stream, uint32_t n_rays_local, uint32_t ray_offset, uint32_t n_rays_global, uint64_t rng_state, uint64_t rng_inc,
+	const ngp_nerf_train_cfg& cfg, const ngp_train_view* views, uint32_t n_views, const uint8_t* bitfield, uint32_t max_samples, ngp_nerf_counters* counters,
+	uint32_t* ray_indices, float* rays, uint32_t* numsteps, float* coords);
+void compute_loss(cudaStream_t stream, uint32_t n_rays_local, uint32_t n_rays_global, uint64_t rng_state, uint64_t rng_inc, const ngp_nerf_train_cfg& cfg,
+	const ngp_train_view* views, uint32_t n_views, const __half* network_output, uint32_t max_compacted, ngp_nerf_counters* counters,
+	const uint32_t* ray_indices, const float* rays, uint32_t* numsteps, const float* coords, float* coords_compacted, __half* dloss, float* loss_per_ray,
+	const float* mean_density);
+void fill_rollover(cudaStream_t stream, uint32_t target_batch, const ngp_nerf_counters* counters, float* coords_compacted, __half* dloss);
+void update_bitfield(cudaStream_t stream, uint32_t max_cascade, const float* density_grid, uint8_t* bitfield, float* mean_density, float* partial1024);
+size_t density_grid_scratch_bytes(uint32_t max_cascade);
+void update_density_grid(const ngp_nerf_desc& d, cudaStream_t stream, const ngp_nerf_train_cfg& cfg, const __half* params, uint64_t* grid_rng_state,
+	uint64_t grid_rng_inc, uint32_t training_step, uint32_t ema_step, float decay, const ngp_train_view* views, uint32_t n_views, float* density_grid,
+	uint8_t* bitfield, float* mean_density, void* scratch);
+size_t render_scratch_bytes(int32_t width, int32_t rows);
+void render_nerf(const ngp_nerf_desc& d, cudaStream_t stream, const ngp_render_cfg& cfg, int32_t y0, int32_t y1, const __half* params, const uint8_t* bitfield,
+	float* rgba, float* depth, void* scratch, uint32_t* n_steps_total);
+float reduce_sum_f32(cudaStream_t stream, const float* data, uint32_t n, float* scratch_dev);
+
+// ------------------------------------------------------------------------------------------------------------------
+// descriptors
+// ------------------------------------------------------------------------------------------------------------------
+static uint32_t powi_u32(uint32_t b, uint32_t e) {
+	uint32_t r = 1;
+	for (uint32_t i = 0; i < e; ++i) r *= b;
+	return r;
+}
+
+void grid_desc_init(ngp_grid_desc* g, uint32_t n_levels, uint32_t F, uint32_t log2_hashmap_size, uint32_t base_resolution, float per_level_scale,
+	uint32_t aabb_scale) {
+	NGPB_CHECK(n_levels >= 1 && n_levels <= NGP_MAX_LEVELS, "HashGrid: n_levels out of range");
+	NGPB_CHECK(F == 1 || F == 2 || F == 4 || F == 8, "HashGrid: n_features_per_level must be 1, 2, 4 or 8");
+	memset(g, 0, sizeof(*g));
+	g->n_levels = n_levels;
+	g->n_features_per_level = F;
+	g->log2_hashmap_size = log2_hashmap_size;
+	g->base_resolution = base_resolution;
+	if (per_level_scale <= 0.0f && n_levels > 1) {
+		// src/testbed.cu:4241-4255: finest level resolves 2048 * aabb_scale cells across the cube
+		per_level_scale = std::exp(std::log(2048.0f * (float)aabb_scale / (float)base_resolution) / (float)(n_levels - 1));
+	}
+	if (n_levels == 1 && per_level_scale <= 0.0f) per_level_scale = 1.0f;
+	g->per_level_scale = per_level_scale;
+	const float log2_scale = std::log2(per_level_scale);
+	uint32_t offset = 0;
+	for (uint32_t l = 0; l < n_levels; ++l) {
+		// grid.h:699-722 (GridType::Hash, 3 position dims)
+		const float scale = exp2f((float)l * log2_scale) * (float)base_resolution - 1.0f;
+		const uint32_t res = (uint32_t)ceilf(scale) + 1;
+		const uint32_t max_params = 0xFFFFFFFFu / 2;
+		uint32_t params_in_level = std::pow((float)res, 3.0f) > (float)max_params ? max_params : powi_u32(res, 3);
+		params_in_level = next_multiple(params_in_level, 8u);
+		params_in_level = std::min(params_in_level, 1u << log2_hashmap_size);
+		g->offsets[l] = offset;
+		g->resolutions[l] = res;
+		g->scales[l] = scale;
+		offset += params_in_level;
+	}
+	g->offsets[n_levels] = offset;
+	g->n_params = offset * F;
+}
+
+static uint32_t mlp_params(uint32_t n_hidden) { return 64 * 32 + (n_hidden - 1) * 64 * 64 + 16 * 64; }
+
+void nerf_desc_init(ngp_nerf_desc* d, const ngp_grid_desc* g, uint32_t n_hidden_density, uint32_t n_hidden_rgb) {
+	NGPB_CHECK(n_hidden_density >= 1 && n_hidden_rgb >= 1, "FullyFusedMLP requires at least 1 hidden layer");
+	NGPB_CHECK(g->n_levels * g->n_features_per_level == 32, "this build fuses a 32-wide encoding (n_levels * n_features_per_level == 32)");
+	memset(d, 0, sizeof(*d));
+	d->grid = *g;
+	d->n_hidden_density = n_hidden_density;
+	d->n_hidden_rgb = n_hidden_rgb;
+	d->density_mlp_offset = 0;
+	d->rgb_mlp_offset = mlp_params(n_hidden_density);
+	d->grid_offset = d->rgb_mlp_offset + mlp_params(n_hidden_rgb);
+	d->n_mlp_params = d->grid_offset;
+	d->n_params = d->grid_offset + g->n_params;
+}
+
+void march_consts_init(ngp_march_consts* m, float cone_angle) {
+	memset(m, 0, sizeof(*m));
+	m->cone_angle = cone_angle;
+	if (cone_angle <= 1e-5f) return;
+	// nerf_device.cuh:384-390, evaluated with the deterministic functions of ngp_detmath.h
+	const float log1p_c = ngp_logf(1.0f + cone_angle);
+	m->log1p_c = log1p_c;
+	m->a = (ngp_logf(min_cone_stepsize()) - ngp_logf(log1p_c)) / log1p_c;
+	m->b = (ngp_logf(max_cone_stepsize()) - ngp_logf(log1p_c)) / log1p_c;
+	m->at = ngp_expf(m->a * log1p_c);
+	m->bt = ngp_expf(m->b * log1p_c);
+}
+
+// Trainer::initialize_params: MLPs Xavier-uniform on the host pcg32 (gpu_matrix.h:292-307), hash grid with the GPU fill
+// pattern of generate_random_kernel (random.h:40-67: thread i draws 4 values for indices i + n_threads * j).
+void nerf_init_params_host(const ngp_nerf_desc* d, uint64_t seed, float* out) {
+	std::seed_seq seq{(uint32_t)seed};
+	std::vector<uint32_t> seeds(2);
+	seq.generate(seeds.begin(), seeds.end());
+	Pcg32 rng((uint64_t)seeds.front());
+	auto xavier = [&](float* w, uint32_t rows, uint32_t cols) {
+		const float scale = std::sqrt(6.0f / (float)(rows + cols));
+		for (uint32_t i = 0; i < rows * cols; ++i) w[i] = rng.next_float() * 2.0f * scale - scale;
+	};
+	float* p = out;
+	for (uint32_t net = 0; net < 2; ++net) {
+		const uint32_t nh = net ? d->n_hidden_rgb : d->n_hidden_density;
+		xavier(p, 64, 32);
+		p += 64 * 32;
+		for (uint32_t l = 1; l < nh; ++l) {
+			xavier(p, 64, 64);
+			p += 64 * 64;
+		}
+		xavier(p, 16, 64);
+		p += 16 * 64;
+	}
+	const size_t n = d->grid.n_params;
+	const size_t n_threads_req = (n + 3) / 4;
+	const size_t n_threads = ((n_threads_req + 127) / 128) * 128;
+	for (size_t i = 0; i < n_threads; ++i) {
+		if (i >= n) break;
+		Pcg32 r = rng;
+		r.advance((uint64_t)i * 4);
+		for (size_t j = 0; j < 4; ++j) {
+			const size_t idx = i + n_threads * j;
+			if (idx >= n) break;
+			p[idx] = r.next_float() * (1e-4f - (-1e-4f)) + (-1e-4f);
+		}
+	}
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// device memory helper
+// ------------------------------------------------------------------------------------------------------------------
+template <typename T>
+struct DevBuf {
+	T* p = nullptr;
+	size_t n = 0;
+	~DevBuf() { release(); }
+	void release() {
+		if (p) cudaFree(p);
+		p = nullptr;
+		n = 0;
+	}
+	void ensure(size_t count) {
+		if (count <= n) return;
+		release();
+		NGPB_CUDA_CHECK(cudaMalloc(&p, count * sizeof(T)));
+		n = count;
+	}
+	void ensure_zeroed(size_t count) {
+		const bool fresh = count > n;
+		ensure(count);
+		if (fresh) NGPB_CUDA_CHECK(cudaMemset(p, 0, n * sizeof(T)));
+	}
+};
+
+// ------------------------------------------------------------------------------------------------------------------
+// Testbed
+// ------------------------------------------------------------------------------------------------------------------
+struct OptimizerConfig {
+	float learning_rate = 1e-2f, beta1 = 0.9f, beta2 = 0.99f, epsilon = 1e-15f, l2_reg = 1e-6f;
+	float ema_decay = 0.95f;
+	bool has_ema = true;
+	bool has_decay = true;
+	uint32_t decay_start = 20000, decay_interval = 10000, decay_end = 10000000;
+	float decay_base = 0.33f;
+};
+
+}  // namespace ngpb
+
+using namespace ngpb;
+
+struct ngp_testbed {
+	int device = 0;
+	cudaStream_t stream = nullptr;
+
+	// dataset (NerfDataset: nerf_loader.h)
+	uint32_t n_images = 0, aabb_scale = 1, n_images_for_training = 0;
+	float scene_scale = 0.33f;  // NERF_SCALE
+	float scene_offset[3] = {0.5f, 0.5f, 0.5f};
+	std::vector<ngp_train_view> views;
+	std::vector<void*> pixel_bufs;
+	DevBuf<ngp_train_view> views_dev;
+	bool views_dirty = true;
+
+	// network
+	bool has_network = false;
+	ngp_nerf_desc desc{};
+	OptimizerConfig opt;
+	float lr_factor = 1.0f;
+	uint32_t optimizer_step = 0;
+	uint64_t seed = 1337;
+	bool train_network = true, train_encoding = true;
+
+	DevBuf<float> params_fp32, m1, m2, mlp_grads_f32;
+	DevBuf<__half> params, params_ema, grads;
+	DevBuf<uint32_t> param_steps;
+
+	// nerf state
+	ngp_nerf_train_cfg cfg{};
+	float density_grid_decay = 0.95f;
+	DevBuf<float> density_grid, mean_density;
+	DevBuf<uint8_t> bitfield, grid_scratch;
+	Pcg32 rng{1337}, density_grid_rng{};
+	uint32_t training_step = 0, density_grid_ema_step = 0;
+	uint32_t rays_per_batch = 1u << 12, measured_batch_size = 0, measured_batch_size_before_compaction = 0, n_rays_total = 0;
+	float loss_scalar = 0.0f;
+	bool shall_train = true;
+
+	// per-step scratch
+	DevBuf<ngp_nerf_counters> counters;
+	DevBuf<uint32_t> ray_indices, numsteps;
+	DevBuf<float> rays, coords, coords_compacted, loss_per_ray, reduce_scratch;
+	DevBuf<__half> mlp_out, dloss;
+	uint32_t last_batch = 0;
+	bool grads_pending = false;
+	bool get_loss_pending = false;
+
+	// data parallel
+	uint32_t dp_rank = 0, dp_world = 1;
+
+	// render
+	DevBuf<uint8_t> render_scratch;
+	DevBuf<float> render_rgba, render_depth;
+	DevBuf<uint32_t> render_counter;
+	float render_min_transmittance = 0.01f;
+
+	~ngp_testbed() {
+		for (void* p : pixel_bufs)
+			if (p) cudaFree(p);
+	}
+};
+
+namespace ngpb {
+
+static void tb_set_defaults(ngp_testbed* t) {
+	ngp_nerf_train_cfg& c = t->cfg;
+	memset(&c, 0, sizeof(c));
+	c.snap_to_pixel_centers = 1;
+	c.random_bg_color = 1;
+	c.linear_colors = 0;
+	c.color_space = NGP_COLOR_LINEAR;
+	c.background_color[0] = c.background_color[1] = c.background_color[2] = 0.0f;
+	c.loss_type = NGP_LOSS_L2;
+	c.rgb_activation = NGP_ACT_LOGISTIC;
+	c.density_activation = NGP_ACT_EXPONENTIAL;
+	c.near_distance = 0.1f;
+	c.loss_scale = NGP_LOSS_SCALE;
+}
+
+static void tb_update_scene(ngp_testbed* t) {
+	// load_nerf_post (testbed_nerf.cu:2425-2440)
+	const float half = 0.5f * (float)std::min<uint32_t>(1u << (NGP_NERF_CASCADES - 1), t->aabb_scale);
+	for (int k = 0; k < 3; ++k) {
+		t->cfg.aabb_min[k] = 0.5f - half;
+		t->cfg.aabb_max[k] = 0.5f + half;
+	}
+	t->cfg.max_cascade = 0;
+	while ((1u << t->cfg.max_cascade) < t->aabb_scale) ++t->cfg.max_cascade;
+	march_consts_init(&t->cfg.march, t->aabb_scale <= 1 ? 0.0f : (1.0f / 256.0f));
+}
+
+static void tb_upload_views(ngp_testbed* t) {
+	if (!t->views_dirty) return;
+	t->views_dev.ensure(std::max<size_t>(t->views.size(), 1));
+	if (!t->views.empty())
+		NGPB_CUDA_CHECK(cudaMemcpyAsync(t->views_dev.p, t->views.data(), t->views.size() * sizeof(ngp_train_view), cudaMemcpyHostToDevice, t->stream));
+	t->views_dirty = false;
+}
+
+static void tb_alloc_network(ngp_testbed* t) {
+	const uint32_t n = t->desc.n_params;
+	t->params_fp32.ensure(n);
+	t->params.ensure(n);
+	t->params_ema.ensure(n);
+	t->grads.ensure(n);
+	t->m1.ensure(n);
+	t->m2.ensure(n);
+	t->param_steps.ensure(n);
+	t->mlp_grads_f32.ensure(t->desc.n_mlp_params);
+	NGPB_CUDA_CHECK(cudaMemsetAsync(t->grads.p, 0, n * sizeof(__half), t->stream));
+	NGPB_CUDA_CHECK(cudaMemsetAsync(t->m1.p, 0, n * sizeof(float), t->stream));
+	NGPB_CUDA_CHECK(cudaMemsetAsync(t->m2.p, 0, n * sizeof(float), t->stream));
+	NGPB_CUDA_CHECK(cudaMemsetAsync(t->param_steps.p, 0, n * sizeof(uint32_t), t->stream));
+	NGPB_CUDA_CHECK(cudaMemsetAsync(t->mlp_grads_f32.p, 0, t->desc.n_mlp_params * sizeof(float), t->stream));
+}
+
+__global__ void k_cast_params(const uint32_t n, const float* __restrict__ src, __half* __restrict__ a, __half* __restrict__ b) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const __half h = __float2half_rn(src[i]);
+	a[i] = h;
+	b[i] = h;
+}
+
+static void tb_set_params_fp32(ngp_testbed* t, const float* host, uint32_t n) {
+	NGPB_CHECK(t->has_network, "no network configured");
+	NGPB_CHECK(n == t->desc.n_params, "set_params: wrong parameter count");
+	NGPB_CUDA_CHECK(cudaMemcpyAsync(t->params_fp32.p, host, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, t->stream));
+	k_cast_params<<<div_round_up(n, 256), 256, 0, t->stream>>>(n, t->params_fp32.p, t->params.p, t->params_ema.p);
+	NGPB_LAUNCHED();
+	NGPB_CUDA_CHECK(cudaStreamSynchronize(t->stream));
+}
+
+// Testbed::reset_network (src/testbed.cu:4160-4412), NeRF mode
+static void tb_reset_network(ngp_testbed* t, const Json& config) {
+	const Json& enc = config.sub("encoding");
+	const Json& net = config.sub("network");
+	const Json& rgb = config.sub("rgb_network");
+	const Json& dir = config.sub("dir_encoding");
+	const Json& loss = config.sub("loss");
+
+	const std::string enc_type = to_lower(enc.value("otype", std::string("HashGrid")));
+	NGPB_CHECK(enc_type == "hashgrid" || enc_type == "grid", "encoding.otype '" + enc_type + "' is not supported by ngp_b200 (HashGrid only)");
+	if (enc.contains("type")) NGPB_CHECK(to_lower(enc.value("type", std::string("hash"))) == "hash", "encoding.type must be Hash");
+	if (enc.contains("interpolation")) NGPB_CHECK(to_lower(enc.value("interpolation", std::string("linear"))) == "linear", "encoding.interpolation must be Linear");
+	auto check_mlp = [&](const Json& j, const char* name) {
+		const std::string ot = to_lower(j.value("otype", std::string("FullyFusedMLP")));
+		NGPB_CHECK(ot == "fullyfusedmlp" || ot == "cutlassmlp" || ot == "megakernelmlp", std::string(name) + ".otype not supported");
+		NGPB_CHECK(to_lower(j.value("activation", std::string("ReLU"))) == "relu", std::string(name) + ".activation must be ReLU");
+		NGPB_CHECK(to_lower(j.value("output_activation", std::string("None"))) == "none", std::string(name) + ".output_activation must be None");
+		NGPB_CHECK((uint32_t)j.value("n_neurons", 64.0) == 64, std::string(name) + ".n_neurons must be 64");
+	};
+	check_mlp(net, "network");
+	check_mlp(rgb, "rgb_network");
+	if (dir.contains("otype")) {
+		const std::string dt = to_lower(dir.value("otype", std::string("Composite")));
+		if (dt == "composite") {
+			NGPB_CHECK(dir.sub("nested").type == Json::Array && !dir.sub("nested").arr.empty(), "dir_encoding.nested missing");
+			const Json& sh = dir.sub("nested").arr[0];
+			NGPB_CHECK(to_lower(sh.value("otype", std::string(""))) == "sphericalharmonics" && (uint32_t)sh.value("degree", 4.0) == 4,
+				"dir_encoding must be SphericalHarmonics degree 4");
+		} else {
+			NGPB_CHECK(dt == "sphericalharmonics" && (uint32_t)dir.value("degree", 4.0) == 4, "dir_encoding must be SphericalHarmonics degree 4");
+		}
+	}
+
+	const uint32_t F = (uint32_t)enc.value("n_features_per_level", 2.0);
+	uint32_t L = (uint32_t)enc.value("n_levels", 16.0);
+	if (enc.contains("n_features") && enc.value("n_features", 0.0) > 0) L = (uint32_t)enc.value("n_features", 0.0) / F;
+	const uint32_t log2_T = (uint32_t)enc.value("log2_hashmap_size", 15.0);
+	uint32_t base_res = (uint32_t)enc.value("base_resolution", 0.0);
+	if (!base_res) base_res = 1u << (log2_T / 3);
+	const float pls = (float)enc.value("per_level_scale", 0.0);
+	ngp_grid_desc g;
+	grid_desc_init(&g, L, F, log2_T, base_res, pls, t->aabb_scale);
+	NGPB_CHECK(F == 2 || F == 4, "HashGrid: n_features_per_level must be 2 or 4 in this build");
+	nerf_desc_init(&t->desc, &g, (uint32_t)net.value("n_hidden_layers", 1.0), (uint32_t)rgb.value("n_hidden_layers", 2.0));
+
+	// loss (string_to_loss_type) — NeRF bypasses tcnn's Loss object (src/testbed.cu:4208-4215)
+	const std::string lt = to_lower(loss.value("otype", std::string("L2")));
+	if (lt == "l2") t->cfg.loss_type = NGP_LOSS_L2;
+	else if (lt == "l1") t->cfg.loss_type = NGP_LOSS_L1;
+	else if (lt == "mape") t->cfg.loss_type = NGP_LOSS_MAPE;
+	else if (lt == "smape") t->cfg.loss_type = NGP_LOSS_SMAPE;
+	else if (lt == "huber") t->cfg.loss_type = NGP_LOSS_HUBER;
+	else if (lt == "logl1") t->cfg.loss_type = NGP_LOSS_LOGL1;
+	else if (lt == "relativel2") t->cfg.loss_type = NGP_LOSS_RELATIVE_L2;
+	else NGPB_CHECK(false, "loss.otype '" + lt + "' is not supported");
+
+	// optimizer: Ema{ExponentialDecay{Adam}} or any suffix of that chain
+	t->opt = OptimizerConfig{};
+	t->opt.has_ema = false;
+	t->opt.has_decay = false;
+	t->opt.learning_rate = 1e-3f; t->opt.beta2 = 0.999f; t->opt.epsilon = 1e-8f; t->opt.l2_reg = 1e-8f;  // adam.h defaults
+	const Json* o = &config.sub("optimizer");
+	for (;;) {
+		const std::string ot = to_lower(o->value("otype", std::string("Adam")));
+		if (ot == "ema") {
+			t->opt.has_ema = true;
+			t->opt.ema_decay = (float)o->value("decay", 0.99);
+			NGPB_CHECK(!(o->contains("full_precision") && o->sub("full_precision").b), "Ema.full_precision is not supported");
+		} else if (ot == "exponentialdecay") {
+			t->opt.has_decay = true;
+			t->opt.decay_base = (float)o->value("decay_base", 0.1);
+			t->opt.decay_interval = (uint32_t)o->value("decay_interval", 10000.0);
+			t->opt.decay_start = (uint32_t)o->value("decay_start", 10000.0);
+			t->opt.decay_end = (uint32_t)o->value("decay_end", 10000000.0);
+		} else if (ot == "adam") {
+			t->opt.learning_rate = (float)o->value("learning_rate", 1e-3);
+			t->opt.beta1 = (float)o->value("beta1", 0.9);
+			t->opt.beta2 = (float)o->value("beta2", 0.999);
+			t->opt.epsilon = (float)o->value("epsilon", 1e-8);
+			t->opt.l2_reg = (float)o->value("l2_reg", 1e-8);
+			break;
+		} else {
+			NGPB_CHECK(false, "optimizer.otype '" + ot + "' is not supported (Ema / ExponentialDecay / Adam)");
+		}
+		NGPB_CHECK(o->contains("nested"), "optimizer: missing nested");
+		o = &o->sub("nested");
+	}
+
+	t->has_network = true;
+	tb_alloc_network(t);
+
+	// state reset (src/testbed.cu:4163-4178)
+	t->rng = Pcg32(t->seed);
+	t->rays_per_batch = 1u << 12;
+	t->measured_batch_size = 0;
+	t->measured_batch_size_before_compaction = 0;
+	t->density_grid_rng = Pcg32((uint64_t)t->rng.next_uint());
+	t->training_step = 0;
+	t->optimizer_step = 0;
+	t->lr_factor = 1.0f;
+	t->density_grid_ema_step = 0;
+	t->n_rays_total = 0;
+	t->loss_scalar = 0.0f;
+	t->shall_train = true;
+
+	const uint32_t n_grid = GRID_N_CELLS * (t->cfg.max_cascade + 1);
+	t->density_grid.ensure(GRID_N_CELLS * NGP_NERF_CASCADES);
+	t->bitfield.ensure(GRID_N_CELLS / 8 * NGP_NERF_CASCADES);
+	t->mean_density.ensure(4);
+	NGPB_CUDA_CHECK(cudaMemsetAsync(t->density_grid.p, 0, sizeof(float) * GRID_N_CELLS * NGP_NERF_CASCADES, t->stream));
+	NGPB_CUDA_CHECK(cudaMemsetAsync(t->bitfield.p, 0, GRID_N_CELLS / 8 * NGP_NERF_CASCADES, t->stream));
+	NGPB_CUDA_CHECK(cudaMemsetAsync(t->mean_density.p, 0, 16, t->stream));
+	(void)n_grid;
+
+	std::vector<float> init(t->desc.n_params);
+	nerf_init_params_host(&t->desc, t->seed, init.data());
+	tb_set_params_fp32(t, init.data(), t->desc.n_params);
+}
+
+static void tb_ensure_step_scratch(ngp_testbed* t, uint32_t batch) {
+	const uint32_t max_samples = batch * 16;
+	const uint32_t max_rays = 1u << 18;
+	t->counters.ensure(1);
+	t->ray_indices.ensure(max_rays);
+	t->numsteps.ensure((size_t)max_rays * 2);
+	t->rays.ensure((size_t)max_rays * 6);
+	t->loss_per_ray.ensure(max_rays);
+	t->reduce_scratch.ensure(1024);
+	t->coords.ensure((size_t)max_samples * 7);
+	t->mlp_out.ensure((size_t)max_samples * 4);
+	t->coords_compacted.ensure((size_t)batch * 7);
+	t->dloss.ensure((size_t)batch * 4);
+	t->grid_scratch.ensure(density_grid_scratch_bytes(t->cfg.max_cascade));
+	t->last_batch = batch;
+}
+
+static uint32_t tb_n_views(const ngp_testbed* t) { return std::min(t->n_images_for_training, t->n_images); }
+
+// training_prep_nerf (testbed_nerf.cu:3385-3398)
+static void tb_training_prep(ngp_testbed* t) {
+	tb_upload_views(t);
+	uint64_t state = t->density_grid_rng.state;
+	update_density_grid(t->desc, t->stream, t->cfg, t->params.p, &state, t->density_grid_rng.inc, t->training_step, t->density_grid_ema_step,
+		t->density_grid_decay, t->views_dev.p, tb_n_views(t), t->density_grid.p, t->bitfield.p, t->mean_density.p, t->grid_scratch.p);
+	t->density_grid_rng.state = state;
+	++t->density_grid_ema_step;
+}
+
+// train_nerf_step up to and including the backward pass (testbed_nerf.cu:3007-3382)
+static void tb_compute_grads(ngp_testbed* t, uint32_t batch) {
+	NGPB_CHECK(t->has_network, "Testbed::train: no network (call reload_network_from_json/file first)");
+	NGPB_CHECK(tb_n_views(t) > 0, "Testbed::train: no training images (set nerf.training.n_images_for_training)");
+	NGPB_CHECK(batch % NGP_BATCH_GRANULARITY == 0 && batch > 0, "Testbed::train: batch size must be a positive multiple of 256");
+	for (uint32_t i = 0; i < tb_n_views(t); ++i) NGPB_CHECK(t->views[i].pixels != nullptr, "Testbed::train: training image " + std::to_string(i) + " was never set");
+	tb_ensure_step_scratch(t, batch);
+	tb_upload_views(t);
+
+	// Testbed::train (src/testbed.cu:4596-4614): density-grid prep every clamp(step/16, 1, 16) steps
+	const uint32_t n_prep_to_skip = std::min(std::max(t->training_step / 16u, 1u), 16u);
+	if (t->training_step % n_prep_to_skip == 0) tb_training_prep(t);
+
+	const uint32_t max_samples = batch * 16;
+	uint32_t max_inference;
+	if (t->measured_batch_size_before_compaction == 0) {
+		t->measured_batch_size_before_compaction = max_inference = max_samples;
+	} else {
+		max_inference = next_multiple(std::min(t->measured_batch_size_before_compaction, max_samples), NGP_BATCH_GRANULARITY);
+	}
+	if (t->training_step == 0) t->n_rays_total = 0;
+	const uint32_t n_rays_total = t->n_rays_total;
+	const uint32_t rays_local = t->rays_per_batch;
+	const uint32_t rays_global = rays_local * t->dp_world;
+	t->n_rays_total += rays_global;
+
+	NGPB_CUDA_CHECK(cudaMemsetAsync(t->counters.p, 0, sizeof(ngp_nerf_counters), t->stream));
+	NGPB_CUDA_CHECK(cudaMemsetAsync(t->loss_per_ray.p, 0, sizeof(float) * rays_local, t->stream));
+	(void)n_rays_total;
+	generate_training_samples(t->stream, rays_local, t->dp_rank * rays_local, rays_global, t->rng.state, t->rng.inc, t->cfg, t->views_dev.p, tb_n_views(t),
+		t->bitfield.p, max_inference, t->counters.p, t->ray_indices.p, t->rays.p, t->numsteps.p, t->coords.p);
+	nerf_inference_counted(t->desc, t->stream, max_inference, &t->counters.p->n_samples, t->coords.p, t->params.p, t->mlp_out.p);
+	compute_loss(t->stream, rays_local, rays_global, t->rng.state, t->rng.inc, t->cfg, t->views_dev.p, tb_n_views(t), t->mlp_out.p, batch, t->counters.p,
+		t->ray_indices.p, t->rays.p, t->numsteps.p, t->coords.p, t->coords_compacted.p, t->dloss.p, t->loss_per_ray.p, t->mean_density.p);
+	fill_rollover(t->stream, batch, t->counters.p, t->coords_compacted.p, t->dloss.p);
+	nerf_forward_backward(t->desc, t->stream, batch, t->coords_compacted.p, t->params.p, t->dloss.p, t->grads.p, t->mlp_grads_f32.p, nullptr);
+	t->rng.advance();
+	t->grads_pending = true;
+	t->get_loss_pending = (t->training_step % 16 == 0);
+}
+
+// optimizer_step + NerfCounters::update_after_training (testbed_nerf.cu:2678-2702, 2770-2788)
+static void tb_apply_grads(ngp_testbed* t) {
+	NGPB_CHECK(t->grads_pending, "train_apply_grads without train_compute_grads");
+	const uint32_t batch = t->last_batch;
+	// ExponentialDecayOptimizer::step (exponential_decay.h:60-72)
+	if (t->optimizer_step == 0) t->lr_factor = 1.0f;
+	if (t->opt.has_decay && t->optimizer_step >= t->opt.decay_start && (t->optimizer_step - t->opt.decay_start) % t->opt.decay_interval == 0 &&
+		t->optimizer_step <= t->opt.decay_end) {
+		t->lr_factor *= t->opt.decay_base;
+	}
+	++t->optimizer_step;
+	ngp_adam_cfg a{};
+	a.learning_rate = t->opt.learning_rate * t->lr_factor;
+	a.beta1 = t->opt.beta1;
+	a.beta2 = t->opt.beta2;
+	a.epsilon = t->opt.epsilon;
+	a.l2_reg = t->opt.l2_reg;
+	a.loss_scale = t->cfg.loss_scale;
+	a.ema_decay = t->opt.has_ema ? t->opt.ema_decay : 0.0f;
+	a.ema_step = t->optimizer_step;
+	a.optimize_matrix_params = t->train_network;
+	a.optimize_non_matrix_params = t->train_encoding;
+	optimizer_step(t->desc, t->stream, a, t->params_fp32.p, t->params.p, t->params_ema.p, t->grads.p, t->m1.p, t->m2.p, t->param_steps.p);
+	++t->training_step;
+	t->grads_pending = false;
+
+	ngp_nerf_counters c{};
+	NGPB_CUDA_CHECK(cudaMemcpyAsync(&c, t->counters.p, sizeof(c), cudaMemcpyDeviceToHost, t->stream));
+	NGPB_CUDA_CHECK(cudaStreamSynchronize(t->stream));
+	// with data parallelism the caller has summed the counters over ranks; use the per-rank mean
+	const uint32_t n_samples = c.n_samples / t->dp_world, n_compacted = c.n_samples_compacted / t->dp_world;
+	t->measured_batch_size = 0;
+	t->measured_batch_size_before_compaction = 0;
+	if (n_samples == 0 || n_compacted == 0) {
+		t->loss_scalar = 0.0f;
+		t->shall_train = false;  // "Nerf training generated 0 samples. Aborting training."
+		return;
+	}
+	t->measured_batch_size_before_compaction = n_samples;
+	t->measured_batch_size = n_compacted;
+	if (t->get_loss_pending) {
+		const float s = reduce_sum_f32(t->stream, t->loss_per_ray.p, t->rays_per_batch, t->reduce_scratch.p);
+		t->loss_scalar = s * (float)t->measured_batch_size / (float)batch;
+	}
+	t->rays_per_batch = (uint32_t)((float)t->rays_per_batch * (float)batch / (float)t->measured_batch_size);
+	t->rays_per_batch = std::min(next_multiple(t->rays_per_batch, NGP_BATCH_GRANULARITY), 1u << 18);
+}
+
+}  // namespace ngpb
+
+// ------------------------------------------------------------------------------------------------------------------
+// extern "C"
+// ------------------------------------------------------------------------------------------------------------------
+#define NGPB_TRY(...)                      \
+	try {                                    \
+		__VA_ARGS__;                           \
+		return 0;                              \
+	} catch (const std::exception& e) {      \
+		ngpb::set_last_error(e.what());        \
+		return 1;                              \
+	}
+
+extern "C" {
+
+const char* ngp_last_error(void) { return g_last_error.c_str(); }
+int ngp_version(void) { return 1; }
+int ngp_device_count(void) {
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess) {
+		cudaGetLastError();
+		return 0;
+	}
+	return n;
+}
+uint64_t ngp_launch_count(void) { return g_launch_count; }
+
+int ngp_grid_desc_init(ngp_grid_desc* g, uint32_t n_levels, uint32_t F, uint32_t log2_T, uint32_t base_res, float pls, uint32_t aabb_scale) {
+	NGPB_TRY(grid_desc_init(g, n_levels, F, log2_T, base_res, pls, aabb_scale));
+}
+int ngp_nerf_desc_init(ngp_nerf_desc* d, const ngp_grid_desc* g, uint32_t nhd, uint32_t nhr) { NGPB_TRY(nerf_desc_init(d, g, nhd, nhr)); }
+int ngp_march_consts_init(ngp_march_consts* m, float cone_angle) { NGPB_TRY(march_consts_init(m, cone_angle)); }
+int ngp_nerf_init_params_host(const ngp_nerf_desc* d, uint64_t seed, float* out) { NGPB_TRY(nerf_init_params_host(d, seed, out)); }
+
+static void require_device() { NGPB_CHECK(ngp_device_count() > 0, "no CUDA device: libngp_b200 has no CPU fallback"); }
+
+int ngp_nerf_inference(const ngp_nerf_desc* d, void* stream, uint32_t n, const float* coords, const void* params, void* out, uint32_t out_stride) {
+	NGPB_TRY(require_device(); nerf_inference(*d, (cudaStream_t)stream, n, coords, (const __half*)params, (__half*)out, out_stride));
+}
+int ngp_nerf_density(const ngp_nerf_desc* d, void* stream, uint32_t n, const float* positions, uint32_t pos_stride, const void* params, void* out) {
+	NGPB_TRY(require_device(); nerf_density(*d, (cudaStream_t)stream, n, positions, pos_stride, (const __half*)params, (__half*)out));
+}
+int ngp_grid_encode(const ngp_grid_desc* g, void* stream, uint32_t n, const float* positions, uint32_t pos_stride, const void* grid, void* out) {
+	NGPB_TRY(require_device(); grid_encode(*g, (cudaStream_t)stream, n, positions, pos_stride, (const __half*)grid, (__half*)out));
+}
+int ngp_nerf_forward_backward(const ngp_nerf_desc* d, void* stream, uint32_t n, const float* coords, const void* params, const void* dL_dout, void* grads,
+	void* out) {
+	NGPB_TRY({
+		require_device();
+		// transient fp32 accumulator for the MLP weight gradients
+		float* tmp = nullptr;
+		NGPB_CUDA_CHECK(cudaMallocAsync(&tmp, d->n_mlp_params * sizeof(float), (cudaStream_t)stream));
+		NGPB_CUDA_CHECK(cudaMemsetAsync(tmp, 0, d->n_mlp_params * sizeof(float), (cudaStream_t)stream));
+		nerf_forward_backward(*d, (cudaStream_t)stream, n, coords, (const __half*)params, (const __half*)dL_dout, (__half*)grads, tmp, (__half*)out);
+		NGPB_CUDA_CHECK(cudaFreeAsync(tmp, (cudaStream_t)stream));
+	});
+}
+int ngp_optimizer_step(const ngp_nerf_desc* d, void* stream, const ngp_adam_cfg* cfg, float* p32, void* p16, void* ema, void* grads, float* m1, float* m2,
+	uint32_t* steps) {
+	NGPB_TRY(require_device(); optimizer_step(*d, (cudaStream_t)stream, *cfg, p32, (__half*)p16, (__half*)ema, (__half*)grads, m1, m2, steps));
+}
+int ngp_nerf_generate_training_samples(void* stream, uint32_t n_rays, uint32_t n_rays_total, uint64_t rng_state, uint64_t rng_inc,
+	const ngp_nerf_train_cfg* cfg, const ngp_train_view* views, uint32_t n_views, const uint8_t* bitfield, uint32_t max_samples, ngp_nerf_counters* counters,
+	uint32_t* ray_indices, float* rays, uint32_t* numsteps, float* coords) {
+	(void)n_rays_total;
+	NGPB_TRY(require_device(); generate_training_samples((cudaStream_t)stream, n_rays, 0, n_rays, rng_state, rng_inc, *cfg, views, n_views, bitfield,
+		max_samples, counters, ray_indices, rays, numsteps, coords));
+}
+int ngp_nerf_compute_loss(void* stream, uint32_t n_rays, uint32_t n_rays_total, uint64_t rng_state, uint64_t rng_inc, const ngp_nerf_train_cfg* cfg,
+	const ngp_train_view* views, uint32_t n_views, const void* network_output, uint32_t max_compacted, ngp_nerf_counters* counters,
+	const uint32_t* ray_indices, const float* rays, uint32_t* numsteps, const float* coords, float* coords_compacted, void* dloss, float* loss_per_ray,
+	const float* mean_density) {
+	(void)n_rays_total;
+	NGPB_TRY(require_device(); compute_loss((cudaStream_t)stream, n_rays, n_rays, rng_state, rng_inc, *cfg, views, n_views, (const __half*)network_output,
+		max_compacted, counters, ray_indices, rays, numsteps, coords, coords_compacted, (__half*)dloss, loss_per_ray, mean_density));
+}
+int ngp_nerf_fill_rollover(void* stream, uint32_t target_batch, const ngp_nerf_counters* counters, float* coords_compacted, void* dloss) {
+	NGPB_TRY(require_device(); fill_rollover((cudaStream_t)stream, target_batch, counters, coords_compacted, (__half*)dloss));
+}
+size_t ngp_nerf_density_grid_scratch_bytes(uint32_t max_cascade) { return density_grid_scratch_bytes(max_cascade); }
+int ngp_nerf_update_density_grid(const ngp_nerf_desc* d, void* stream, const ngp_nerf_train_cfg* cfg, const void* params, uint64_t* rng_state,
+	uint64_t rng_inc, uint32_t training_step, uint32_t ema_step, float decay, const ngp_train_view* views, uint32_t n_views, float* density_grid,
+	uint8_t* bitfield, float* mean_density, void* scratch) {
+	NGPB_TRY(require_device(); update_density_grid(*d, (cudaStream_t)stream, *cfg, (const __half*)params, rng_state, rng_inc, training_step, ema_step, decay,
+		views, n_views, density_grid, bitfield, mean_density, scratch));
+}
+int ngp_nerf_update_bitfield(void* stream, uint32_t max_cascade, const float* density_grid, uint8_t* bitfield, float* mean_density) {
+	NGPB_TRY({
+		require_device();
+		float* partial = nullptr;
+		NGPB_CUDA_CHECK(cudaMallocAsync(&partial, 1024 * sizeof(float), (cudaStream_t)stream));
+		update_bitfield((cudaStream_t)stream, max_cascade, density_grid, bitfield, mean_density, partial);
+		NGPB_CUDA_CHECK(cudaFreeAsync(partial, (cudaStream_t)stream));
+	});
+}
+size_t ngp_nerf_render_scratch_bytes(int32_t width, int32_t rows) { return render_scratch_bytes(width, rows); }
+int ngp_nerf_render(const ngp_nerf_desc* d, void* stream, const ngp_render_cfg* cfg, int32_t y0, int32_t y1, const void* params, const uint8_t* bitfield,
+	float* rgba, float* depth, void* scratch, uint32_t* n_steps_total) {
+	NGPB_TRY(require_device(); render_nerf(*d, (cudaStream_t)stream, *cfg, y0, y1, (const __half*)params, bitfield, rgba, depth, scratch, n_steps_total));
+}
+
+// ---- B2 ----------------------------------------------------------------------------------------------------------
+ngp_testbed* ngp_testbed_create(int device, void* stream) {
+	try {
+		require_device();
+		NGPB_CUDA_CHECK(cudaSetDevice(device));
+		auto* t = new ngp_testbed();
+		t->device = device;
+		t->stream = (cudaStream_t)stream;
+		tb_set_defaults(t);
+		tb_update_scene(t);
+		return t;
+	} catch (const std::exception& e) {
+		set_last_error(e.what());
+		return nullptr;
+	}
+}
+void ngp_testbed_destroy(ngp_testbed* t) {
+	if (!t) return;
+	cudaStreamSynchronize(t->stream);
+	delete t;
+}
+int ngp_testbed_create_empty_nerf_dataset(ngp_testbed* t, uint32_t n_images, uint32_t aabb_scale) {
+	NGPB_TRY({
+		NGPB_CHECK(n_images > 0, "create_empty_nerf_dataset: n_images must be > 0");
+		NGPB_CHECK(aabb_scale >= 1 && aabb_scale <= 128 && (aabb_scale & (aabb_scale - 1)) == 0, "aabb_scale must be a power of two in [1, 128]");
+		for (void* p : t->pixel_bufs)
+			if (p) cudaFree(p);
+		t->n_images = n_images;
+		t->aabb_scale = aabb_scale;
+		t->n_images_for_training = 0;  // Testbed::create_empty_nerf_dataset, testbed_nerf.cu:2349
+		t->views.assign(n_images, ngp_train_view{});
+		t->pixel_bufs.assign(n_images, nullptr);
+		for (auto& v : t->views) {
+			v.focal_x = v.focal_y = 1000.0f;
+			v.principal_x = v.principal_y = 0.5f;
+			const float ident[12] = {1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0};
+			memcpy(v.xform, ident, sizeof(ident));
+		}
+		t->views_dirty = true;
+		tb_update_scene(t);
+	});
+}
+int ngp_testbed_set_image(ngp_testbed* t, uint32_t idx, const float* rgba_host, int32_t w, int32_t h) {
+	NGPB_TRY({
+		NGPB_CHECK(idx < t->n_images, "Invalid frame index");
+		NGPB_CHECK(w > 0 && h > 0, "image must have positive size");
+		if (t->pixel_bufs[idx]) cudaFree(t->pixel_bufs[idx]);
+		void* p = nullptr;
+		const size_t bytes = (size_t)w * h * 4 * sizeof(float);
+		NGPB_CUDA_CHECK(cudaMalloc(&p, bytes));
+		NGPB_CUDA_CHECK(cudaMemcpy(p, rgba_host, bytes, cudaMemcpyHostToDevice));
+		t->pixel_bufs[idx] = p;
+		t->views[idx].pixels = p;
+		t->views[idx].image_type = NGP_IMAGE_FLOAT;  // python_api.cu:45-72 keeps float images as they are
+		t->views[idx].width = w;
+		t->views[idx].height = h;
+		t->views_dirty = true;
+	});
+}
+int ngp_testbed_set_camera_extrinsics(ngp_testbed* t, uint32_t idx, const float* m, int convert_to_ngp) {
+	NGPB_TRY({
+		NGPB_CHECK(idx < t->n_images, "Invalid frame index");
+		// input: row-major 3x4 camera-to-world; columns c0,c1,c2,origin
+		float col[4][3];
+		for (int c = 0; c < 4; ++c)
+			for (int r = 0; r < 3; ++r) col[c][r] = m[r * 4 + c];
+		if (convert_to_ngp) {
+			// nerf_matrix_to_ngp (nerf_loader.h:101-120)
+			for (int r = 0; r < 3; ++r) {
+				col[1][r] *= -1.0f;
+				col[2][r] *= -1.0f;
+				col[3][r] = col[3][r] * t->scene_scale + t->scene_offset[r];
+			}
+			// cycle axes xyz <- yzx (row 0 <- row 1, row 1 <- row 2, row 2 <- old row 0)
+			for (int c = 0; c < 4; ++c) {
+				const float tmp = col[c][0];
+				col[c][0] = col[c][1];
+				col[c][1] = col[c][2];
+				col[c][2] = tmp;
+			}
+		}
+		for (int c = 0; c < 4; ++c)
+			for (int r = 0; r < 3; ++r) t->views[idx].xform[c * 3 + r] = col[c][r];
+		t->views_dirty = true;
+	});
+}
+int ngp_testbed_set_camera_intrinsics(ngp_testbed* t, uint32_t idx, float fx, float fy, float cx, float cy, float k1, float k2, float p1, float p2) {
+	NGPB_TRY({
+		NGPB_CHECK(idx < t->n_images, "Invalid frame index");
+		ngp_train_view& v = t->views[idx];
+		NGPB_CHECK(v.width > 0, "set_camera_intrinsics: set the image first (principal point is relative to the resolution)");
+		// testbed_nerf.cu:2151-2186
+		if (fx <= 0.0f) fx = fy;
+		if (fy <= 0.0f) fy = fx;
+		cx = cx < 0.0f ? -cx : cx / (float)v.width;
+		cy = cy < 0.0f ? -cy : cy / (float)v.height;
+		v.lens_mode = NGP_LENS_PERSPECTIVE;
+		memset(v.lens_params, 0, sizeof(v.lens_params));
+		if (k1 != 0.0f || k2 != 0.0f || p1 != 0.0f || p2 != 0.0f) {
+			v.lens_mode = NGP_LENS_OPENCV;
+			v.lens_params[0] = k1; v.lens_params[1] = k2; v.lens_params[2] = p1; v.lens_params[3] = p2;
+		}
+		v.principal_x = cx;
+		v.principal_y = cy;
+		v.focal_x = fx;
+		v.focal_y = fy;
+		t->views_dirty = true;
+	});
+}
+int ngp_testbed_reload_network_from_json(ngp_testbed* t, const char* json_text) {
+	NGPB_TRY({
+		const std::string text(json_text);
+		Json cfg = JsonParser(text).parse();
+		tb_reset_network(t, cfg);
+	});
+}
+int ngp_testbed_reload_network_from_file(ngp_testbed* t, const char* path) {
+	NGPB_TRY({
+		std::ifstream f(path);
+		NGPB_CHECK(f.good(), std::string("network config not found: ") + path);
+		std::stringstream ss;
+		ss << f.rdbuf();
+		const std::string text = ss.str();
+		Json cfg = JsonParser(text).parse();
+		NGPB_CHECK(!cfg.contains("parent"), "config inheritance ('parent') is not supported");
+		tb_reset_network(t, cfg);
+	});
+}
+int ngp_testbed_set_seed(ngp_testbed* t, uint64_t seed) {
+	t->seed = seed;
+	return 0;
+}
+int ngp_testbed_set_option(ngp_testbed* t, const char* name_c, double value) {
+	NGPB_TRY({
+		const std::string n(name_c);
+		ngp_nerf_train_cfg& c = t->cfg;
+		if (n == "nerf.training.n_images_for_training") { NGPB_CHECK(value >= 0 && value <= t->n_images, "n_images_for_training out of range"); t->n_images_for_training = (uint32_t)value; }
+		else if (n == "nerf.training.random_bg_color") c.random_bg_color = value != 0;
+		else if (n == "nerf.training.linear_colors") c.linear_colors = value != 0;
+		else if (n == "nerf.training.snap_to_pixel_centers") c.snap_to_pixel_centers = value != 0;
+		else if (n == "nerf.training.near_distance") c.near_distance = (float)value;
+		else if (n == "nerf.training.loss_type") c.loss_type = (uint32_t)value;
+		else if (n == "nerf.training.density_grid_decay") t->density_grid_decay = (float)value;
+		else if (n == "nerf.rgb_activation") c.rgb_activation = (uint32_t)value;
+		else if (n == "nerf.density_activation") c.density_activation = (uint32_t)value;
+		else if (n == "nerf.cone_angle_constant") march_consts_init(&c.march, (float)value);
+		else if (n == "nerf.render_min_transmittance") t->render_min_transmittance = (float)value;
+		else if (n == "color_space") c.color_space = (uint32_t)value;
+		else if (n == "background_color.r") c.background_color[0] = (float)value;
+		else if (n == "background_color.g") c.background_color[1] = (float)value;
+		else if (n == "background_color.b") c.background_color[2] = (float)value;
+		else if (n == "train_network") t->train_network = value != 0;
+		else if (n == "train_encoding") t->train_encoding = value != 0;
+		else if (n == "shall_train") t->shall_train = value != 0;
+		else if (n == "nerf.training.dataset.scale") t->scene_scale = (float)value;
+		else NGPB_CHECK(false, "unknown option '" + n + "'");
+	});
+}
+double ngp_testbed_get_option(ngp_testbed* t, const char* name_c) {
+	const std::string n(name_c);
+	const ngp_nerf_train_cfg& c = t->cfg;
+	if (n == "nerf.training.n_images_for_training") return t->n_images_for_training;
+	if (n == "nerf.training.random_bg_color") return c.random_bg_color;
+	if (n == "nerf.training.linear_colors") return c.linear_colors;
+	if (n == "nerf.training.snap_to_pixel_centers") return c.snap_to_pixel_centers;
+	if (n == "nerf.training.near_distance") return c.near_distance;
+	if (n == "nerf.training.loss_type") return c.loss_type;
+	if (n == "nerf.training.density_grid_decay") return t->density_grid_decay;
+	if (n == "nerf.rgb_activation") return c.rgb_activation;
+	if (n == "nerf.density_activation") return c.density_activation;
+	if (n == "nerf.cone_angle_constant") return c.march.cone_angle;
+	if (n == "nerf.render_min_transmittance") return t->render_min_transmittance;
+	if (n == "nerf.max_cascade") return c.max_cascade;
+	if (n == "color_space") return c.color_space;
+	if (n == "shall_train") return t->shall_train;
+	if (n == "aabb_scale") return t->aabb_scale;
+	if (n == "learning_rate") return t->opt.learning_rate * t->lr_factor;
+	set_last_error("unknown option '" + n + "'");
+	return NAN;
+}
+int ngp_testbed_set_dp(ngp_testbed* t, uint32_t rank, uint32_t world) {
+	NGPB_TRY({
+		NGPB_CHECK(world >= 1 && rank < world, "set_dp: rank must be < world");
+		t->dp_rank = rank;
+		t->dp_world = world;
+	});
+}
+int ngp_testbed_train_compute_grads(ngp_testbed* t, uint32_t batch) { NGPB_TRY(tb_compute_grads(t, batch)); }
+int ngp_testbed_train_apply_grads(ngp_testbed* t) { NGPB_TRY(tb_apply_grads(t)); }
+int ngp_testbed_train(ngp_testbed* t, uint32_t batch) {
+	NGPB_TRY({
+		if (!t->shall_train) return 0;
+		tb_compute_grads(t, batch);
+		tb_apply_grads(t);
+	});
+}
+void* ngp_testbed_grads(ngp_testbed* t) { return t->grads.p; }
+void* ngp_testbed_params(ngp_testbed* t) { return t->params.p; }
+void* ngp_testbed_params_inference(ngp_testbed* t) { return t->params_ema.p; }
+float* ngp_testbed_params_fp32(ngp_testbed* t) { return t->params_fp32.p; }
+uint32_t* ngp_testbed_dp_counters(ngp_testbed* t) { return reinterpret_cast<uint32_t*>(t->counters.p); }
+uint32_t ngp_testbed_n_params(ngp_testbed* t) { return t->has_network ? t->desc.n_params : 0; }
+uint32_t ngp_testbed_training_step(ngp_testbed* t) { return t->training_step; }
+float ngp_testbed_loss(ngp_testbed* t) { return t->loss_scalar; }
+int ngp_testbed_get_counters(ngp_testbed* t, uint32_t* rpb, uint32_t* mbs, uint32_t* mbsb) {
+	if (rpb) *rpb = t->rays_per_batch;
+	if (mbs) *mbs = t->measured_batch_size;
+	if (mbsb) *mbsb = t->measured_batch_size_before_compaction;
+	return 0;
+}
+int ngp_testbed_get_desc(ngp_testbed* t, ngp_nerf_desc* out) {
+	NGPB_TRY({
+		NGPB_CHECK(t->has_network, "no network configured");
+		*out = t->desc;
+	});
+}
+int ngp_testbed_set_params_fp32(ngp_testbed* t, const float* host, uint32_t n) { NGPB_TRY(tb_set_params_fp32(t, host, n)); }
+int ngp_testbed_get_params_fp16(ngp_testbed* t, void* host, uint32_t n, int inference) {
+	NGPB_TRY({
+		NGPB_CHECK(t->has_network && n == t->desc.n_params, "get_params: wrong parameter count");
+		NGPB_CUDA_CHECK(cudaMemcpyAsync(host, inference ? t->params_ema.p : t->params.p, (size_t)n * 2, cudaMemcpyDeviceToHost, t->stream));
+		NGPB_CUDA_CHECK(cudaStreamSynchronize(t->stream));
+	});
+}
+int ngp_testbed_get_density_grid(ngp_testbed* t, float* grid_host, uint32_t n, uint8_t* bitfield_host, uint32_t n_bytes) {
+	NGPB_TRY({
+		NGPB_CHECK(t->density_grid.p, "no density grid yet");
+		if (grid_host) {
+			NGPB_CHECK(n <= GRID_N_CELLS * NGP_NERF_CASCADES, "density grid read too large");
+			NGPB_CUDA_CHECK(cudaMemcpyAsync(grid_host, t->density_grid.p, (size_t)n * 4, cudaMemcpyDeviceToHost, t->stream));
+		}
+		if (bitfield_host) {
+			NGPB_CHECK(n_bytes <= GRID_N_CELLS / 8 * NGP_NERF_CASCADES, "bitfield read too large");
+			NGPB_CUDA_CHECK(cudaMemcpyAsync(bitfield_host, t->bitfield.p, n_bytes, cudaMemcpyDeviceToHost, t->stream));
+		}
+		NGPB_CUDA_CHECK(cudaStreamSynchronize(t->stream));
+	});
+}
+int ngp_testbed_set_density_grid(ngp_testbed* t, const float* grid_host, uint32_t n) {
+	NGPB_TRY({
+		NGPB_CHECK(t->density_grid.p, "configure a network first");
+		NGPB_CHECK(n <= GRID_N_CELLS * NGP_NERF_CASCADES, "density grid too large");
+		NGPB_CUDA_CHECK(cudaMemcpyAsync(t->density_grid.p, grid_host, (size_t)n * 4, cudaMemcpyHostToDevice, t->stream));
+		t->reduce_scratch.ensure(1024);
+		update_bitfield(t->stream, t->cfg.max_cascade, t->density_grid.p, t->bitfield.p, t->mean_density.p, t->reduce_scratch.p);
+		NGPB_CUDA_CHECK(cudaStreamSynchronize(t->stream));
+	});
+}
+
+static void tb_fill_render_cfg(ngp_testbed* t, ngp_render_cfg& rc, int32_t width, int32_t height, const float* cam, float fx, float fy, float cx, float cy) {
+	memset(&rc, 0, sizeof(rc));
+	rc.width = width;
+	rc.height = height;
+	rc.focal_x = fx;
+	rc.focal_y = fy;
+	rc.screen_x = cx;
+	rc.screen_y = cy;
+	for (int c = 0; c < 4; ++c)
+		for (int r = 0; r < 3; ++r) rc.camera[c * 3 + r] = cam[r * 4 + c];
+	for (int k = 0; k < 3; ++k) {
+		rc.aabb_min[k] = rc.render_aabb_min[k] = t->cfg.aabb_min[k];
+		rc.aabb_max[k] = rc.render_aabb_max[k] = t->cfg.aabb_max[k];
+	}
+	rc.max_cascade = t->cfg.max_cascade;
+	rc.march = t->cfg.march;
+	rc.rgb_activation = t->cfg.rgb_activation;
+	rc.density_activation = t->cfg.density_activation;
+	rc.min_transmittance = t->render_min_transmittance;
+	rc.spp_index = 0;
+	rc.near_distance = 0.0f;
+}
+
+int ngp_testbed_render_device(ngp_testbed* t, int32_t width, int32_t height, const float* cam, float fx, float fy, float cx, float cy, int32_t y0,
+	int32_t y1, float* rgba_dev, float* depth_dev) {
+	NGPB_TRY({
+		NGPB_CHECK(t->has_network, "render: no network");
+		NGPB_CHECK(width > 0 && height > 0 && y0 >= 0 && y1 <= height && y0 < y1, "render: bad frame / tile bounds");
+		ngp_render_cfg rc;
+		tb_fill_render_cfg(t, rc, width, height, cam, fx, fy, cx, cy);
+		t->render_scratch.ensure(render_scratch_bytes(width, y1 - y0));
+		t->render_counter.ensure(4);
+		render_nerf(t->desc, t->stream, rc, y0, y1, t->params_ema.p, t->bitfield.p, rgba_dev, depth_dev, t->render_scratch.p, t->render_counter.p);
+	});
+}
+int ngp_testbed_render(ngp_testbed* t, int32_t width, int32_t height, const float* cam, float fx, float fy, float cx, float cy, int32_t y0, int32_t y1,
+	float* rgba_host, float* depth_host, uint32_t* n_steps_total) {
+	NGPB_TRY({
+		NGPB_CHECK(width > 0 && height > 0, "render: bad frame size");
+		const size_t n_px = (size_t)width * height;
+		t->render_rgba.ensure(n_px * 4);
+		t->render_depth.ensure(n_px);
+		if (ngp_testbed_render_device(t, width, height, cam, fx, fy, cx, cy, y0, y1, t->render_rgba.p, t->render_depth.p)) throw std::runtime_error(g_last_error);
+		const size_t off = (size_t)y0 * width, cnt = (size_t)(y1 - y0) * width;
+		NGPB_CUDA_CHECK(cudaMemcpyAsync(rgba_host + off * 4, t->render_rgba.p + off * 4, cnt * 16, cudaMemcpyDeviceToHost, t->stream));
+		if (depth_host) NGPB_CUDA_CHECK(cudaMemcpyAsync(depth_host + off, t->render_depth.p + off, cnt * 4, cudaMemcpyDeviceToHost, t->stream));
+		uint32_t steps = 0;
+		NGPB_CUDA_CHECK(cudaMemcpyAsync(&steps, t->render_counter.p, 4, cudaMemcpyDeviceToHost, t->stream));
+		NGPB_CUDA_CHECK(cudaStreamSynchronize(t->stream));
+		if (n_steps_total) *n_steps_total = steps;
+	});
+}
+
+// Snapshot: the payload of Testbed::save_snapshot (src/testbed.cu:5288-5355) — training step, counters, fp32 master +
+// EMA params, optimizer moments, density grid — in a flat little-endian container (".ngpb").  The reference's
+// msgpack/zlib .ingp container is the next row of SURVEY §8f and is not read or written yet.
+struct SnapshotHeader {
+	char magic[8];
+	uint32_t version, n_params, n_grid, training_step, optimizer_step, rays_per_batch, measured_batch_size, measured_before, ema_step, aabb_scale;
+	float lr_factor;
+	uint64_t rng_state, rng_inc, grng_state, grng_inc;
+	ngp_nerf_desc desc;
+};
+int ngp_testbed_save_snapshot(ngp_testbed* t, const char* path) {
+	NGPB_TRY({
+		NGPB_CHECK(t->has_network, "save_snapshot: no network");
+		NGPB_CUDA_CHECK(cudaStreamSynchronize(t->stream));
+		SnapshotHeader h{};
+		memcpy(h.magic, "NGPB200\0", 8);
+		h.version = 1;
+		h.n_params = t->desc.n_params;
+		h.n_grid = GRID_N_CELLS * (t->cfg.max_cascade + 1);
+		h.training_step = t->training_step;
+		h.optimizer_step = t->optimizer_step;
+		h.rays_per_batch = t->rays_per_batch;
+		h.measured_batch_size = t->measured_batch_size;
+		h.measured_before = t->measured_batch_size_before_compaction;
+		h.ema_step = t->density_grid_ema_step;
+		h.aabb_scale = t->aabb_scale;
+		h.lr_factor = t->lr_factor;
+		h.rng_state = t->rng.state; h.rng_inc = t->rng.inc; h.grng_state = t->density_grid_rng.state; h.grng_inc = t->density_grid_rng.inc;
+		h.desc = t->desc;
+		std::ofstream f(path, std::ios::binary);
+		NGPB_CHECK(f.good(), std::string("cannot open ") + path);
+		f.write(reinterpret_cast<const char*>(&h), sizeof(h));
+		auto dump = [&](const void* dev, size_t bytes) {
+			std::vector<char> buf(bytes);
+			NGPB_CUDA_CHECK(cudaMemcpy(buf.data(), dev, bytes, cudaMemcpyDeviceToHost));
+			f.write(buf.data(), (std::streamsize)bytes);
+		};
+		const size_t n = h.n_params;
+		dump(t->params_fp32.p, n * 4);
+		dump(t->params_ema.p, n * 2);
+		dump(t->m1.p, n * 4);
+		dump(t->m2.p, n * 4);
+		dump(t->param_steps.p, n * 4);
+		dump(t->density_grid.p, (size_t)h.n_grid * 4);
+		NGPB_CHECK(f.good(), "snapshot write failed");
+	});
+}
+int ngp_testbed_load_snapshot(ngp_testbed* t, const char* path) {
+	NGPB_TRY({
+		std::ifstream f(path, std::ios::binary);
+		NGPB_CHECK(f.good(), std::string("snapshot not found: ") + path);
+		SnapshotHeader h{};
+		f.read(reinterpret_cast<char*>(&h), sizeof(h));
+		NGPB_CHECK(f.good() && memcmp(h.magic, "NGPB200\0", 8) == 0 && h.version == 1, "not an ngp_b200 snapshot");
+		t->aabb_scale = h.aabb_scale;
+		tb_update_scene(t);
+		t->desc = h.desc;
+		t->has_network = true;
+		tb_alloc_network(t);
+		t->density_grid.ensure(GRID_N_CELLS * NGP_NERF_CASCADES);
+		t->bitfield.ensure(GRID_N_CELLS / 8 * NGP_NERF_CASCADES);
+		t->mean_density.ensure(4);
+		NGPB_CUDA_CHECK(cudaMemset(t->density_grid.p, 0, sizeof(float) * GRID_N_CELLS * NGP_NERF_CASCADES));
+		auto load = [&](void* dev, size_t bytes) {
+			std::vector<char> buf(bytes);
+			f.read(buf.data(), (std::streamsize)bytes);
+			NGPB_CHECK(f.good(), "snapshot truncated");
+			NGPB_CUDA_CHECK(cudaMemcpy(dev, buf.data(), bytes, cudaMemcpyHostToDevice));
+		};
+		const size_t n = h.n_params;
+		load(t->params_fp32.p, n * 4);
+		load(t->params_ema.p, n * 2);
+		load(t->m1.p, n * 4);
+		load(t->m2.p, n * 4);
+		load(t->param_steps.p, n * 4);
+		load(t->density_grid.p, (size_t)h.n_grid * 4);
+		// fp16 working copy = cast of the master weights (Trainer::deserialize rewrites all three buffers, trainer.h:457-482)
+		std::vector<__half> tmp_unused;
+		k_cast_params<<<div_round_up((uint32_t)n, 256), 256, 0, t->stream>>>((uint32_t)n, t->params_fp32.p, t->params.p, t->params.p);
+		NGPB_LAUNCHED();
+		t->training_step = h.training_step;
+		t->optimizer_step = h.optimizer_step;
+		t->rays_per_batch = h.rays_per_batch;
+		t->measured_batch_size = h.measured_batch_size;
+		t->measured_batch_size_before_compaction = h.measured_before;
+		t->density_grid_ema_step = h.ema_step;
+		t->lr_factor = h.lr_factor;
+		t->rng = Pcg32(h.rng_state, h.rng_inc, true);
+		t->density_grid_rng = Pcg32(h.grng_state, h.grng_inc, true);
+		t->reduce_scratch.ensure(1024);
+		update_bitfield(t->stream, t->cfg.max_cascade, t->density_grid.p, t->bitfield.p, t->mean_density.p, t->reduce_scratch.p);
+		NGPB_CUDA_CHECK(cudaStreamSynchronize(t->stream));
+	});
+}
+int ngp_testbed_sync(ngp_testbed* t) { NGPB_TRY(NGPB_CUDA_CHECK(cudaStreamSynchronize(t->stream))); }
+
+}  // extern "C"

@@ -1,0 +1,307 @@
+"""`pyngp.Testbed`-compatible surface over libngp_b200.so for the NeRF path.
+
+Mirrors src/python_api.cu:439-853 name for name where the hot path needs it: ``create_empty_nerf_dataset``,
+``nerf.training.set_image / set_camera_extrinsics / set_camera_intrinsics / n_images_for_training``,
+``reload_network_from_file / _from_json``, ``train``, ``render``, ``loss``, ``training_step``, ``n_params``,
+``save_snapshot / load_snapshot``.  Everything heavy happens inside the shared library.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import enum
+import json
+from pathlib import Path
+
+import numpy as np
+
+from . import binding as B
+
+
+class TestbedMode(enum.IntEnum):
+    Nerf = 0
+    Sdf = 1
+    Image = 2
+    Volume = 3
+    None_ = 4
+
+
+class LossType(enum.IntEnum):  # ELossType
+    L2 = 0
+    L1 = 1
+    Mape = 2
+    Smape = 3
+    Huber = 4
+    LogL1 = 5
+    RelativeL2 = 6
+
+
+class NerfActivation(enum.IntEnum):  # ENerfActivation
+    None_ = 0
+    ReLU = 1
+    Logistic = 2
+    Exponential = 3
+
+
+class ColorSpace(enum.IntEnum):
+    Linear = 0
+    SRGB = 1
+
+
+def _opt_property(name: str, cast=float):
+    def getter(self):
+        return cast(self._tb._get(name))
+
+    def setter(self, value):
+        self._tb._set(name, float(value))
+
+    return property(getter, setter)
+
+
+class _Training:
+    """``testbed.nerf.training`` (python_api.cu:781-853)."""
+
+    def __init__(self, tb: "Testbed"):
+        self._tb = tb
+
+    n_images_for_training = _opt_property("nerf.training.n_images_for_training", int)
+    random_bg_color = _opt_property("nerf.training.random_bg_color", bool)
+    linear_colors = _opt_property("nerf.training.linear_colors", bool)
+    snap_to_pixel_centers = _opt_property("nerf.training.snap_to_pixel_centers", bool)
+    near_distance = _opt_property("nerf.training.near_distance", float)
+    density_grid_decay = _opt_property("nerf.training.density_grid_decay", float)
+
+    @property
+    def loss_type(self) -> LossType:
+        return LossType(int(self._tb._get("nerf.training.loss_type")))
+
+    @loss_type.setter
+    def loss_type(self, v) -> None:
+        self._tb._set("nerf.training.loss_type", float(int(v)))
+
+    def set_image(self, frame_idx: int, img: np.ndarray, depth_img=None, depth_scale: float = 1.0) -> None:
+        img = np.ascontiguousarray(img, dtype=np.float32)
+        if img.ndim != 3 or img.shape[2] != 4:
+            raise ValueError("image should be (H,W,C) where C=4")
+        B.check(B.lib().ngp_testbed_set_image(self._tb._h, frame_idx, img.ctypes.data, img.shape[1], img.shape[0]))
+
+    def set_camera_extrinsics(self, frame_idx: int, camera_to_world: np.ndarray, convert_to_ngp: bool = True) -> None:
+        m = np.ascontiguousarray(np.asarray(camera_to_world, dtype=np.float32)[:3, :4])
+        B.check(B.lib().ngp_testbed_set_camera_extrinsics(self._tb._h, frame_idx, m.ctypes.data, int(convert_to_ngp)))
+
+    def set_camera_intrinsics(self, frame_idx: int, fx: float = 0.0, fy: float = 0.0, cx: float = -0.5, cy: float = -0.5, k1: float = 0.0,
+                              k2: float = 0.0, p1: float = 0.0, p2: float = 0.0) -> None:
+        B.check(B.lib().ngp_testbed_set_camera_intrinsics(self._tb._h, frame_idx, fx, fy, cx, cy, k1, k2, p1, p2))
+
+
+class _Nerf:
+    """``testbed.nerf`` (python_api.cu:714-742)."""
+
+    def __init__(self, tb: "Testbed"):
+        self._tb = tb
+        self.training = _Training(tb)
+
+    cone_angle_constant = _opt_property("nerf.cone_angle_constant", float)
+    render_min_transmittance = _opt_property("nerf.render_min_transmittance", float)
+
+    @property
+    def rgb_activation(self) -> NerfActivation:
+        return NerfActivation(int(self._tb._get("nerf.rgb_activation")))
+
+    @rgb_activation.setter
+    def rgb_activation(self, v) -> None:
+        self._tb._set("nerf.rgb_activation", float(int(v)))
+
+    @property
+    def density_activation(self) -> NerfActivation:
+        return NerfActivation(int(self._tb._get("nerf.density_activation")))
+
+    @density_activation.setter
+    def density_activation(self, v) -> None:
+        self._tb._set("nerf.density_activation", float(int(v)))
+
+
+class Testbed:
+    """Drop-in for ``pyngp.Testbed`` on the NeRF path."""
+
+    def __init__(self, mode: TestbedMode = TestbedMode.Nerf, device: int = 0, stream: int | None = None):
+        if mode != TestbedMode.Nerf:
+            raise B.NgpError("ngp_b200 implements the NeRF mode only")
+        if stream is None:
+            try:  # run on torch's current stream when torch drives the process (bench / DP); plain default stream otherwise
+                import torch
+
+                stream = torch.cuda.current_stream(device).cuda_stream if torch.cuda.is_available() else 0
+            except Exception:  # pragma: no cover
+                stream = 0
+        self._h = B.lib().ngp_testbed_create(device, C.c_void_p(stream))
+        if not self._h:
+            raise B.NgpError(B.lib().ngp_last_error().decode())
+        self.nerf = _Nerf(self)
+        self.training_batch_size = 1 << 18
+        self.root_dir = ""
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            try:
+                B.lib().ngp_testbed_destroy(h)
+            except Exception:  # pragma: no cover
+                pass
+
+    # -- options ---------------------------------------------------------------------------------------------------
+    def _set(self, name: str, value: float) -> None:
+        B.check(B.lib().ngp_testbed_set_option(self._h, name.encode(), value))
+
+    def _get(self, name: str) -> float:
+        v = B.lib().ngp_testbed_get_option(self._h, name.encode())
+        if v != v:
+            raise B.NgpError(B.lib().ngp_last_error().decode())
+        return v
+
+    shall_train = _opt_property("shall_train", bool)
+
+    @property
+    def _tb(self):
+        return self
+
+    @property
+    def color_space(self) -> ColorSpace:
+        return ColorSpace(int(self._get("color_space")))
+
+    @color_space.setter
+    def color_space(self, v) -> None:
+        self._set("color_space", float(int(v)))
+
+    @property
+    def background_color(self):
+        raise AttributeError("write-only here")
+
+    @background_color.setter
+    def background_color(self, rgba) -> None:
+        self._set("background_color.r", float(rgba[0]))
+        self._set("background_color.g", float(rgba[1]))
+        self._set("background_color.b", float(rgba[2]))
+
+    # -- data ------------------------------------------------------------------------------------------------------
+    def create_empty_nerf_dataset(self, n_images: int, aabb_scale: int = 1, is_hdr: bool = False) -> None:
+        if is_hdr:
+            raise B.NgpError("is_hdr datasets are not supported")
+        B.check(B.lib().ngp_testbed_create_empty_nerf_dataset(self._h, n_images, aabb_scale))
+
+    # -- network ---------------------------------------------------------------------------------------------------
+    def reload_network_from_file(self, path: str = "") -> None:
+        B.check(B.lib().ngp_testbed_reload_network_from_file(self._h, str(path).encode()))
+
+    def reload_network_from_json(self, config, config_base_path: str = "") -> None:
+        text = config if isinstance(config, str) else json.dumps(config)
+        B.check(B.lib().ngp_testbed_reload_network_from_json(self._h, text.encode()))
+
+    def set_seed(self, seed: int) -> None:
+        B.check(B.lib().ngp_testbed_set_seed(self._h, seed))
+
+    @property
+    def n_params(self) -> int:
+        return int(B.lib().ngp_testbed_n_params(self._h))
+
+    @property
+    def training_step(self) -> int:
+        return int(B.lib().ngp_testbed_training_step(self._h))
+
+    @property
+    def loss(self) -> float:
+        return float(B.lib().ngp_testbed_loss(self._h))
+
+    def desc(self) -> B.NerfDesc:
+        d = B.NerfDesc()
+        B.check(B.lib().ngp_testbed_get_desc(self._h, C.byref(d)))
+        return d
+
+    def counters(self) -> dict:
+        a, b, c = C.c_uint32(), C.c_uint32(), C.c_uint32()
+        B.lib().ngp_testbed_get_counters(self._h, C.byref(a), C.byref(b), C.byref(c))
+        return {"rays_per_batch": a.value, "measured_batch_size": b.value, "measured_batch_size_before_compaction": c.value}
+
+    # -- training --------------------------------------------------------------------------------------------------
+    def train(self, batch_size: int | None = None) -> None:
+        B.check(B.lib().ngp_testbed_train(self._h, int(batch_size or self.training_batch_size)))
+
+    def frame(self) -> bool:
+        if self.shall_train:
+            self.train(self.training_batch_size)
+        return True
+
+    def set_data_parallel(self, rank: int, world: int) -> None:
+        B.check(B.lib().ngp_testbed_set_dp(self._h, rank, world))
+
+    def train_compute_grads(self, batch_size: int | None = None) -> None:
+        B.check(B.lib().ngp_testbed_train_compute_grads(self._h, int(batch_size or self.training_batch_size)))
+
+    def train_apply_grads(self) -> None:
+        B.check(B.lib().ngp_testbed_train_apply_grads(self._h))
+
+    def grads_ptr(self) -> int:
+        return int(B.lib().ngp_testbed_grads(self._h) or 0)
+
+    def dp_counters_ptr(self) -> int:
+        return int(B.lib().ngp_testbed_dp_counters(self._h) or 0)
+
+    def params_ptr(self, inference: bool = False) -> int:
+        f = B.lib().ngp_testbed_params_inference if inference else B.lib().ngp_testbed_params
+        return int(f(self._h) or 0)
+
+    # -- params / grid exchange ------------------------------------------------------------------------------------
+    def set_params(self, params_fp32: np.ndarray) -> None:
+        p = np.ascontiguousarray(params_fp32, dtype=np.float32)
+        B.check(B.lib().ngp_testbed_set_params_fp32(self._h, p.ctypes.data, p.size))
+
+    def get_params(self, inference: bool = False) -> np.ndarray:
+        out = np.empty(self.n_params, dtype=np.float16)
+        B.check(B.lib().ngp_testbed_get_params_fp16(self._h, out.ctypes.data, out.size, int(inference)))
+        return out
+
+    def get_density_grid(self):
+        n_casc = int(self._get("nerf.max_cascade")) + 1
+        grid = np.empty(128 ** 3 * n_casc, dtype=np.float32)
+        bits = np.empty(128 ** 3 * 8 // 8, dtype=np.uint8)
+        B.check(B.lib().ngp_testbed_get_density_grid(self._h, grid.ctypes.data, grid.size, bits.ctypes.data, bits.size))
+        return grid, bits
+
+    def set_density_grid(self, grid: np.ndarray) -> None:
+        g = np.ascontiguousarray(grid, dtype=np.float32)
+        B.check(B.lib().ngp_testbed_set_density_grid(self._h, g.ctypes.data, g.size))
+
+    # -- render ----------------------------------------------------------------------------------------------------
+    def render(self, width: int, height: int, camera_matrix: np.ndarray, focal_length, screen_center=(0.5, 0.5), spp: int = 1, linear: bool = True,
+               rows=None, return_depth: bool = False):
+        """≙ Testbed.render(width, height, spp, linear) with an explicit ngp-convention 3x4 camera-to-world matrix
+        (the reference takes it from testbed.set_nerf_camera_matrix).  Returns float32 [H, W, 4] linear premultiplied RGBA."""
+        if spp != 1 or not linear:
+            raise B.NgpError("render: spp=1, linear=True only")
+        cam = np.ascontiguousarray(np.asarray(camera_matrix, dtype=np.float32)[:3, :4])
+        fx, fy = (focal_length, focal_length) if np.isscalar(focal_length) else focal_length
+        y0, y1 = rows if rows is not None else (0, height)
+        rgba = np.zeros((height, width, 4), dtype=np.float32)
+        depth = np.zeros((height, width), dtype=np.float32)
+        steps = C.c_uint32(0)
+        B.check(B.lib().ngp_testbed_render(self._h, width, height, cam.ctypes.data, fx, fy, screen_center[0], screen_center[1], y0, y1, rgba.ctypes.data,
+                                           depth.ctypes.data, C.byref(steps)))
+        self.last_render_steps = steps.value
+        return (rgba, depth) if return_depth else rgba
+
+    def render_device(self, width: int, height: int, camera_matrix: np.ndarray, focal_length, rgba_ptr: int, depth_ptr: int, screen_center=(0.5, 0.5),
+                      rows=None) -> None:
+        cam = np.ascontiguousarray(np.asarray(camera_matrix, dtype=np.float32)[:3, :4])
+        fx, fy = (focal_length, focal_length) if np.isscalar(focal_length) else focal_length
+        y0, y1 = rows if rows is not None else (0, height)
+        B.check(B.lib().ngp_testbed_render_device(self._h, width, height, cam.ctypes.data, fx, fy, screen_center[0], screen_center[1], y0, y1,
+                                                  C.c_void_p(rgba_ptr), C.c_void_p(depth_ptr)))
+
+    # -- snapshots -------------------------------------------------------------------------------------------------
+    def save_snapshot(self, path: str, include_optimizer_state: bool = False, compress: bool = True) -> None:
+        B.check(B.lib().ngp_testbed_save_snapshot(self._h, str(Path(path)).encode()))
+
+    def load_snapshot(self, path: str) -> None:
+        B.check(B.lib().ngp_testbed_load_snapshot(self._h, str(Path(path)).encode()))
+
+    def sync(self) -> None:
+        B.check(B.lib().ngp_testbed_sync(self._h))
