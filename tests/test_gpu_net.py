@@ -100,9 +100,8 @@ def test_inference_matches_oracle(lib, cfg, n, stride):
     assert err.max() <= 1e-2 * max(1.0, np.abs(want).max())
     # tail rows beyond the sample are finite and computed
     assert np.isfinite(got[:, :4]).all()
-    if n > m:
+    if n >= 2 * m:
         # size-independent property: the kernel is a pure function of each row -> duplicates give identical outputs
-        assert np.array_equal(got[0, :4], got[0, :4])
         t_c2 = dev(np.concatenate([coords[m:2 * m], coords[:m]]))
         t_out2 = torch.zeros(2 * m, stride, dtype=torch.float16, device="cuda")
         assert lib.ngp_nerf_inference(C.byref(d), stream(), 2 * m, t_c2.data_ptr(), t_p.data_ptr(), t_out2.data_ptr(), stride) == 0
