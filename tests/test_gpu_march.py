@@ -1,0 +1,253 @@
+"""GPU parity: training-ray generation / occupancy marching, compositing + loss + compaction, roll-over padding and the
+occupancy-grid maintenance kernels against the C oracle — BIT-EXACT for ray indices, per-ray sample counts, marched
+coordinates, loss gradients and occupancy bits (north_star: "bit-exact ray indices and sample counts")."""
+import ctypes as C
+import importlib
+
+import numpy as np
+import pytest
+
+import util
+from oracle import march_oracle as M
+from oracle import net_oracle as O
+
+pytestmark = pytest.mark.gpu
+S = importlib.import_module("instant-ngp_b200.synthetic")
+
+
+@pytest.fixture(scope="module")
+def lib():
+    l = util.pkg().load_library()
+    assert l.ngp_device_count() > 0
+    return l
+
+
+def stream():
+    import torch
+
+    return torch.cuda.current_stream().cuda_stream
+
+
+def dev(x):
+    import torch
+
+    return torch.from_numpy(np.ascontiguousarray(x)).cuda()
+
+
+SCENES = [
+    dict(aabb_scale=1, lens=None, full=False, radius=1.3),
+    dict(aabb_scale=4, lens=None, full=False, radius=1.6),
+    dict(aabb_scale=4, lens=(0.0578421, -0.0805099, -0.000980296, 0.00015575), full=True, radius=1.2),  # fox-like OpenCV lens
+]
+
+
+def run_generator(lib, scene, n_rays, max_samples, seed=1337):
+    import torch
+
+    imgs, cams, focal = S.make_dataset(n_images=7, width=96, height=64, radius=scene["radius"])
+    cfg = util.make_train_cfg(aabb_scale=scene["aabb_scale"])
+    bf = util.sphere_bitfield(radius=0.3, max_cascade=cfg.max_cascade, full=scene["full"])
+    views, keep = util.make_views(imgs, cams, focal, lens=scene["lens"])
+    t_views, tens = util.views_to_device(views, keep)
+    rng = M.pcg32_seed(seed)
+    want = M.generate_training_samples(n_rays, 0, n_rays, rng, cfg, views, len(views), bf, max_samples)
+
+    t_bf = dev(bf)
+    t_cnt = torch.zeros(4, dtype=torch.int32, device="cuda")
+    t_ri = torch.zeros(n_rays, dtype=torch.int32, device="cuda")
+    t_rays = torch.zeros(n_rays, 6, dtype=torch.float32, device="cuda")
+    t_ns = torch.zeros(n_rays, 2, dtype=torch.int32, device="cuda")
+    t_co = torch.zeros(max_samples, 7, dtype=torch.float32, device="cuda")
+    rc = lib.ngp_nerf_generate_training_samples(stream(), n_rays, 0, rng[0], rng[1], C.byref(cfg), t_views.data_ptr(), len(views), t_bf.data_ptr(), max_samples,
+                                                t_cnt.data_ptr(), t_ri.data_ptr(), t_rays.data_ptr(), t_ns.data_ptr(), t_co.data_ptr())
+    assert rc == 0, lib.ngp_last_error()
+    torch.cuda.synchronize()
+    cnt = t_cnt.cpu().numpy().view(np.uint32)
+    got = dict(n_kept=int(cnt[0]), n_samples=int(cnt[1]), ray_indices=t_ri.cpu().numpy().view(np.uint32), rays=t_rays.cpu().numpy(),
+               numsteps=t_ns.cpu().numpy().view(np.uint32), coords=t_co.cpu().numpy())
+    ctx = dict(cfg=cfg, views=views, keep=keep, t_views=t_views, tens=tens, bf=bf, t_bf=t_bf, rng=rng, dev=dict(cnt=t_cnt, ri=t_ri, rays=t_rays, ns=t_ns, co=t_co))
+    return want, got, ctx
+
+
+@pytest.mark.parametrize("scene", SCENES)
+def test_training_samples_bit_exact(lib, scene):
+    n_rays, max_samples = 4096, 4096 * 64
+    want, got, _ = run_generator(lib, scene, n_rays, max_samples)
+    assert want["n_samples"] > 1000, "degenerate scene"
+    assert got["n_kept"] == want["n_kept"]
+    assert got["n_samples"] == want["n_samples"]
+    k = got["n_kept"]
+    # the reference's slot order depends on atomics; compare as a map ray id -> (count, ray, coordinates)
+    gmap = {int(r): j for j, r in enumerate(got["ray_indices"][:k])}
+    wmap = {int(r): j for j, r in enumerate(want["ray_indices"])}
+    assert set(gmap) == set(wmap)
+    for rid, wj in wmap.items():
+        gj = gmap[rid]
+        wn, wb = want["numsteps"][wj]
+        gn, gb = got["numsteps"][gj]
+        assert gn == wn == want["per_ray_numsteps"][rid]
+        assert got["rays"][gj].tobytes() == want["rays"][wj].tobytes()
+        assert got["coords"][gb:gb + gn].tobytes() == want["coords"][wb:wb + wn].tobytes()
+    # slots tile [0, n_samples) without gaps or overlaps
+    order = np.argsort(got["numsteps"][:k, 1])
+    ends = got["numsteps"][:k, 1][order] + got["numsteps"][:k, 0][order]
+    assert got["numsteps"][:k, 1][order][0] == 0 and np.array_equal(ends[:-1], got["numsteps"][:k, 1][order][1:]) and ends[-1] == got["n_samples"]
+
+
+def test_training_samples_overflow_drops_rays_like_the_reference(lib):
+    want, got, _ = run_generator(lib, SCENES[0], 4096, 2048)  # far too small on purpose
+    assert got["n_samples"] == want["n_samples"]          # the counter keeps counting past the limit
+    k = got["n_kept"]
+    assert 0 < k < 4096
+    assert (got["numsteps"][:k, 0] + got["numsteps"][:k, 1] <= 2048).all()
+
+
+def test_empty_and_ragged_inputs(lib):
+    import torch
+
+    # zero rays is a no-op; an empty occupancy grid yields zero samples and zero rays
+    imgs, cams, focal = S.make_dataset(n_images=3, width=32, height=32)
+    cfg = util.make_train_cfg(aabb_scale=1)
+    views, keep = util.make_views(imgs, cams, focal)
+    t_views, tens = util.views_to_device(views, keep)
+    t_bf = torch.zeros(128 ** 3, dtype=torch.uint8, device="cuda")
+    t_cnt = torch.zeros(4, dtype=torch.int32, device="cuda")
+    buf = torch.zeros(1 << 16, dtype=torch.float32, device="cuda")
+    rng = M.pcg32_seed(7)
+    for n in (0, 1, 33):
+        assert lib.ngp_nerf_generate_training_samples(stream(), n, 0, rng[0], rng[1], C.byref(cfg), t_views.data_ptr(), 3, t_bf.data_ptr(), 1024, t_cnt.data_ptr(),
+                                                      buf.data_ptr(), buf.data_ptr(), buf.data_ptr(), buf.data_ptr()) == 0
+    torch.cuda.synchronize()
+    assert t_cnt.cpu().numpy().tolist() == [0, 0, 0, 0]
+
+
+@pytest.mark.parametrize("scene", SCENES[:2])
+@pytest.mark.parametrize("loss_type,random_bg", [(4, 1), (0, 0)])
+def test_loss_and_compaction_bit_exact(lib, scene, loss_type, random_bg):
+    import torch
+
+    n_rays, max_samples, batch = 4096, 4096 * 64, 1 << 15
+    want, got, ctx = run_generator(lib, scene, n_rays, max_samples)
+    cfg = ctx["cfg"]
+    cfg.loss_type, cfg.random_bg_color = loss_type, random_bg
+    k, ns = got["n_kept"], got["n_samples"]
+    # synthetic network outputs: moderately dense medium so that rays terminate at different depths
+    rng = np.random.default_rng(5)
+    net_out = np.zeros((max_samples, 4), dtype=np.float16)
+    net_out[:, 0:3] = rng.normal(0, 1.5, size=(max_samples, 3)).astype(np.float16)
+    net_out[:, 3] = rng.normal(1.0, 2.5, size=max_samples).astype(np.float16)
+    mean_density = np.float32(0.02)
+
+    # oracle on the GPU's own slot assignment (so that outputs line up index by index)
+    ns_host = got["numsteps"][:k].copy()
+    co_w = np.zeros((batch, 7), dtype=np.float32)
+    dl_w = np.zeros((batch, 4), dtype=np.float16)
+    loss_w = np.zeros(n_rays, dtype=np.float32)
+    comp_w = M.lib().orc_compute_loss(k, n_rays, ctx["rng"][0], ctx["rng"][1], C.byref(cfg), C.addressof(ctx["views"]), len(ctx["views"]),
+                                      net_out.ctypes.data, batch, got["ray_indices"].ctypes.data, got["rays"].ctypes.data, ns_host.ctypes.data,
+                                      got["coords"].ctypes.data, co_w.ctypes.data, dl_w.ctypes.data, loss_w.ctypes.data, mean_density)
+
+    d = ctx["dev"]
+    t_no = dev(net_out)
+    t_coc = torch.zeros(batch, 7, dtype=torch.float32, device="cuda")
+    t_dl = torch.zeros(batch, 4, dtype=torch.float16, device="cuda")
+    t_loss = torch.zeros(n_rays, dtype=torch.float32, device="cuda")
+    t_md = dev(np.array([mean_density], dtype=np.float32))
+    rc = lib.ngp_nerf_compute_loss(stream(), n_rays, 0, ctx["rng"][0], ctx["rng"][1], C.byref(cfg), ctx["t_views"].data_ptr(), len(ctx["views"]), t_no.data_ptr(), batch,
+                                   d["cnt"].data_ptr(), d["ri"].data_ptr(), d["rays"].data_ptr(), d["ns"].data_ptr(), d["co"].data_ptr(), t_coc.data_ptr(),
+                                   t_dl.data_ptr(), t_loss.data_ptr(), t_md.data_ptr())
+    assert rc == 0, lib.ngp_last_error()
+    torch.cuda.synchronize()
+    cnt = d["cnt"].cpu().numpy().view(np.uint32)
+    assert int(cnt[2]) == comp_w and comp_w > 0
+    ns_g = d["ns"].cpu().numpy().view(np.uint32)[:k]
+    co_g, dl_g, loss_g = t_coc.cpu().numpy(), t_dl.cpu().numpy(), t_loss.cpu().numpy()
+    # per-ray compacted counts are exact; the compacted base differs (warp order vs ray order) -> compare ray by ray
+    assert np.array_equal(ns_g[:, 0], ns_host[:, 0])
+    assert loss_g[:k].tobytes() == loss_w[:k].tobytes()
+    checked = 0
+    for i in range(k):
+        n_i = int(ns_g[i, 0])
+        if n_i == 0:
+            continue
+        gb, wb = int(ns_g[i, 1]), int(ns_host[i, 1])
+        assert co_g[gb:gb + n_i].tobytes() == co_w[wb:wb + n_i].tobytes()
+        assert dl_g[gb:gb + n_i].tobytes() == dl_w[wb:wb + n_i].tobytes(), f"ray slot {i}"
+        checked += n_i
+    assert checked == min(comp_w, batch) or comp_w > batch
+
+    # roll-over padding (fill_rollover_and_rescale + fill_rollover)
+    t_c3 = torch.zeros(4, dtype=torch.int32, device="cuda")
+    n_comp_small = 1000
+    t_c3[2] = n_comp_small
+    co_pad, dl_pad = co_g.copy(), dl_g.copy()
+    M.lib().orc_fill_rollover(batch, n_comp_small, co_pad.ctypes.data, dl_pad.ctypes.data)
+    assert lib.ngp_nerf_fill_rollover(stream(), batch, t_c3.data_ptr(), t_coc.data_ptr(), t_dl.data_ptr()) == 0
+    torch.cuda.synchronize()
+    assert t_coc.cpu().numpy().tobytes() == co_pad.tobytes()
+    assert t_dl.cpu().numpy().tobytes() == dl_pad.tobytes()
+
+
+@pytest.mark.parametrize("aabb_scale", [1, 4])
+def test_density_grid_update_matches_oracle(lib, aabb_scale):
+    import torch
+
+    d, L = util.make_desc(n_levels=16, F=2, log2_T=17, aabb_scale=aabb_scale)
+    params = util.random_params(L, seed=21, trained_like=True).astype(np.float16)
+    imgs, cams, focal = S.make_dataset(n_images=5, width=48, height=48, radius=1.3)
+    cfg = util.make_train_cfg(aabb_scale=aabb_scale)
+    views, keep = util.make_views(imgs, cams, focal)
+    t_views, tens = util.views_to_device(views, keep)
+    n_casc = cfg.max_cascade + 1
+    n_el = 128 ** 3 * n_casc
+    t_p = dev(params)
+    t_grid = torch.zeros(128 ** 3 * 8, dtype=torch.float32, device="cuda")
+    t_bf = torch.zeros(128 ** 3, dtype=torch.uint8, device="cuda")
+    t_mean = torch.zeros(4, dtype=torch.float32, device="cuda")
+    scratch_bytes = lib.ngp_nerf_density_grid_scratch_bytes(cfg.max_cascade)
+    t_scr = torch.zeros(scratch_bytes, dtype=torch.uint8, device="cuda")
+    rng = M.pcg32_seed(99)
+
+    grid_w = np.zeros(n_el, dtype=np.float32)
+    tmp_w = np.zeros(n_el, dtype=np.float32)
+    state = C.c_uint64(rng[0])
+    state_w = C.c_uint64(rng[0])
+    for step, ema_step in [(0, 0), (16, 1), (300, 2)]:
+        rc = lib.ngp_nerf_update_density_grid(C.byref(d), stream(), C.byref(cfg), t_p.data_ptr(), C.byref(state), rng[1], step, ema_step, 0.95, t_views.data_ptr(), len(views),
+                                              t_grid.data_ptr(), t_bf.data_ptr(), t_mean.data_ptr(), t_scr.data_ptr())
+        assert rc == 0, lib.ngp_last_error()
+        torch.cuda.synchronize()
+        # ---- oracle, fed with the GPU's density-network outputs so that the integer / bit results can be compared exactly
+        if step == 0:
+            M.lib().orc_mark_untrained_density_grid(n_el, grid_w.ctypes.data, len(views), C.addressof(views), 1)
+        n_uni = n_el if step < 256 else n_el // 4
+        n_non = 0 if step < 256 else n_el // 4
+        pos_w = np.zeros((n_uni + n_non, 4), dtype=np.float32)
+        idx_w = np.zeros(n_uni + n_non, dtype=np.uint32)
+        M.lib().orc_generate_grid_samples(n_uni, state_w.value, rng[1], ema_step, C.byref(cfg), grid_w.ctypes.data, pos_w.ctypes.data, idx_w.ctypes.data, n_casc, -0.01)
+        M.lib().orc_pcg32_advance(C.byref(state_w), rng[1], 1 << 32)
+        if n_non:
+            M.lib().orc_generate_grid_samples(n_non, state_w.value, rng[1], ema_step, C.byref(cfg), grid_w.ctypes.data, pos_w[n_uni:].ctypes.data, idx_w[n_uni:].ctypes.data,
+                                              n_casc, 0.01)
+        M.lib().orc_pcg32_advance(C.byref(state_w), rng[1], 1 << 32)
+        assert state.value == state_w.value
+        scr = t_scr.cpu().numpy()
+        n_tot = n_uni + n_non
+        pos_g = scr[: n_el * 16].view(np.float32).reshape(-1, 4)[:n_tot]
+        idx_g = scr[n_el * 16: n_el * 20].view(np.uint32)[:n_tot]
+        mlp_g = scr[n_el * 24: n_el * 24 + n_tot * 2].view(np.float16)
+        assert idx_g.tobytes() == idx_w.tobytes()
+        assert pos_g.tobytes() == pos_w.tobytes()
+        # network: tolerance parity on a sample
+        sel = np.random.default_rng(step).choice(n_tot, 2048, replace=False)
+        want_d = O.nerf_density(L, params, pos_w[sel, :3]).astype(np.float32)
+        assert np.abs(mlp_g[sel].astype(np.float32) - want_d).max() <= 1e-2 * max(1.0, np.abs(want_d).max())
+        M.lib().orc_splat_and_ema(n_tot, idx_w.ctypes.data, np.ascontiguousarray(mlp_g).ctypes.data, cfg.density_activation, n_el, 0.95, tmp_w.ctypes.data, grid_w.ctypes.data)
+        grid_g = t_grid.cpu().numpy()[:n_el]
+        assert grid_g.tobytes() == grid_w.tobytes()
+        mean_w = M.lib().orc_density_mean(grid_w.ctypes.data)
+        assert np.float32(mean_w).tobytes() == t_mean.cpu().numpy()[:1].tobytes()
+        bf_w = np.zeros(128 ** 3, dtype=np.uint8)
+        M.lib().orc_update_bitfield(cfg.max_cascade, grid_w.ctypes.data, mean_w, bf_w.ctypes.data)
+        assert t_bf.cpu().numpy().tobytes() == bf_w.tobytes()
+    assert (grid_w < 0).sum() > 0 and (grid_w > 0).sum() > 0  # some voxels culled as unseen, some populated

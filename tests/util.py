@@ -55,3 +55,104 @@ def rel_err(a, b, eps=1e-3):
     a = np.asarray(a, dtype=np.float64)
     b = np.asarray(b, dtype=np.float64)
     return np.abs(a - b) / (np.abs(b) + eps)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# march / loss helpers
+# ---------------------------------------------------------------------------------------------------------------------
+def sphere_bitfield(radius=0.25, max_cascade=0, full=False):
+    """occupancy bitfield (128^3 * 8 / 8 bytes incl. all mips): solid sphere of the given radius around the cube centre
+    in every cascade <= max_cascade (SURVEY §8d synthetic occupancy), or everything occupied."""
+    idx = np.arange(128 ** 3, dtype=np.uint32)
+
+    def compact(x):
+        x = x & 0x49249249
+        x = (x | (x >> 2)) & 0xC30C30C3
+        x = (x | (x >> 4)) & 0x0F00F00F
+        x = (x | (x >> 8)) & 0xFF0000FF
+        x = (x | (x >> 16)) & 0x0000FFFF
+        return x
+
+    X, Y, Z = compact(idx), compact(idx >> 1), compact(idx >> 2)
+    bf = np.zeros(128 ** 3 * 8 // 8, dtype=np.uint8)
+    for mip in range(max_cascade + 1):
+        if full:
+            occ = np.ones(128 ** 3, dtype=bool)
+        else:
+            s = np.float32(2.0 ** mip)
+            p = [((c.astype(np.float32) + np.float32(0.5)) / np.float32(128.0) - np.float32(0.5)) * s + np.float32(0.5) for c in (X, Y, Z)]
+            dist = np.sqrt((p[0] - 0.5) ** 2 + (p[1] - 0.5) ** 2 + (p[2] - 0.5) ** 2)
+            occ = dist < radius
+        bf[mip * 128 ** 3 // 8:(mip + 1) * 128 ** 3 // 8] = np.packbits(occ.reshape(-1, 8), axis=1, bitorder="little").reshape(-1)
+    return bf
+
+
+def make_train_cfg(aabb_scale=1, **kw):
+    P = pkg()
+    lib = P.load_library()
+    c = P.NerfTrainCfg()
+    half = 0.5 * min(128, aabb_scale)
+    for k in range(3):
+        c.aabb_min[k] = 0.5 - half
+        c.aabb_max[k] = 0.5 + half
+    mc = 0
+    while (1 << mc) < aabb_scale:
+        mc += 1
+    c.max_cascade = mc
+    assert lib.ngp_march_consts_init(C.byref(c.march), 0.0 if aabb_scale <= 1 else 1.0 / 256.0) == 0
+    c.snap_to_pixel_centers = 1
+    c.random_bg_color = 1
+    c.linear_colors = 0
+    c.color_space = 0
+    c.loss_type = 4  # Huber, as configs/nerf/base.json
+    c.rgb_activation = 2
+    c.density_activation = 3
+    c.near_distance = 0.1
+    c.loss_scale = 128.0
+    for k, v in kw.items():
+        setattr(c, k, v)
+    return c
+
+
+def make_views(imgs, cams, focal, lens=None, image_type=3):
+    """(host view array whose pixel pointers are numpy buffers, list of buffers to keep alive)"""
+    P = pkg()
+    n, h, w, _ = imgs.shape
+    arr = (P.TrainView * n)()
+    keep = []
+    for i in range(n):
+        v = arr[i]
+        buf = np.ascontiguousarray(imgs[i])
+        keep.append(buf)
+        v.pixels = buf.ctypes.data
+        v.image_type = image_type
+        v.width, v.height = w, h
+        v.focal_x = v.focal_y = focal
+        v.principal_x = v.principal_y = 0.5
+        if lens is not None:
+            v.lens_mode = 1
+            for k in range(4):
+                v.lens_params[k] = lens[k]
+        m = np.asarray(cams[i], dtype=np.float32)
+        for c in range(4):
+            for r in range(3):
+                v.xform[c * 3 + r] = m[r, c]
+    return arr, keep
+
+
+def views_to_device(arr, keep):
+    """copy of the view array whose pixel pointers are CUDA buffers; returns (torch uint8 tensor holding the structs, keepalive)"""
+    import torch
+
+    P = pkg()
+    n = len(arr)
+    dev_arr = (P.TrainView * n)()
+    C.memmove(dev_arr, arr, C.sizeof(arr))
+    tens = []
+    for i in range(n):
+        t = torch.from_numpy(keep[i]).cuda()
+        tens.append(t)
+        dev_arr[i].pixels = t.data_ptr()
+    raw = np.frombuffer(bytes(dev_arr), dtype=np.uint8).copy()
+    t_views = torch.from_numpy(raw).cuda()
+    return t_views, tens
