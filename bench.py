@@ -1,0 +1,349 @@
+#!/usr/bin/env python
+"""bench.py — the driver's measurement contract for the NeRF hot path.
+
+    python bench.py --gpus N --steps K --warmup W            (N > 1: launched through torch.distributed.run)
+    python bench.py --impl reference --gpus N --steps K --warmup W
+
+Metric (BASELINE.json): NeRF training samples/s on the configuration it is quoted on — hash grid L=16 F=2 T=2^19, 64-wide
+MLPs (density 1 hidden, rgb 2 hidden), 2^18-sample batches — over a synthetic 100-view 800x800 scene (the fox JPEGs and
+NeRF-synthetic cannot reach the GPU box).  One "step" = one Testbed.train(2^18): occupancy-grid maintenance on the
+reference's schedule, training-ray generation + marching, inference, loss + compaction, fused forward/backward, optimizer.
+
+value  : compacted samples trained per second, all ranks, dataset resident in HBM (device-timed with CUDA events).
+e2e    : the same through the public pyngp-style API while one training image per step is streamed from pinned host
+         memory (H2D inside the timed region) and the step's counters + loss are read back (D2H).
+N > 1  : weak scaling — every rank trains its own 2^18-sample batch on its shard of the global ray batch; one
+         torch.distributed (NCCL) all-reduce of the flat fp16 gradient buffer per step.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+BATCH = 1 << 18
+N_VIEWS, RES = 100, 800
+WORKLOAD = "nerf-synthetic-ball-100x800x800 L16 F2 T2^19 mlp64x(1,2) batch 2^18 aabb_scale 1"
+
+
+def pkg():
+    return importlib.import_module("instant-ngp_b200")
+
+
+def syn():
+    return importlib.import_module("instant-ngp_b200.synthetic")
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """samples nvidia-smi SM clocks / throttle reasons while the timed region runs (B200_PROFILING.md)."""
+
+    def __init__(self, gpu_index: int):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def __enter__(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self) -> dict:
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for n, v in zip(names, r[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+class DevicePtrTensor:
+    """zero-copy torch view of a device buffer owned by libngp_b200 (for the NCCL all-reduce)"""
+
+    def __init__(self, ptr: int, n: int, typestr: str):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+def build_testbed(rank: int, world: int, n_views: int = N_VIEWS, res: int = RES):
+    P, S = pkg(), syn()
+    tb = P.Testbed()
+    imgs, cams, focal = S.make_dataset(n_images=n_views, width=res, height=res)
+    S.load_into_testbed(tb, imgs, cams, focal, aabb_scale=1)
+    tb.reload_network_from_json(S.base_config(16, 2, 19))
+    if world > 1:
+        tb.set_data_parallel(rank, world)
+    return tb, imgs
+
+
+def peaks() -> dict:
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return {"hbm_gbs": d["hbm_gbs"], "source": "measured"}
+    return {"hbm_gbs": 6650.0, "source": "fallback"}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port (tiny-cuda-nn has no CPU path) on a bounded sample of the same workload
+# ---------------------------------------------------------------------------------------------------------------------
+def cpu_training_sample(n_rays: int = 2048, n_net: int = 16384, repeats: int = 1):
+    """times the oracle on a slice of one training step: march + loss of n_rays rays (C, single thread) and forward+backward of
+    n_net samples through the numpy network oracle (BLAS threads).  Returns (samples_per_second, description, cores)."""
+    sys.path.insert(0, str(ROOT / "tests"))
+    import util
+    from oracle import march_oracle as M
+    from oracle import net_oracle as O
+
+    S = syn()
+    imgs, cams, focal = S.make_dataset(n_images=8, width=200, height=200)
+    cfg = util.make_train_cfg(aabb_scale=1)
+    views, keep = util.make_views(imgs, cams, focal)
+    bf = util.sphere_bitfield(radius=0.3, max_cascade=0)
+    d, L = util.make_desc(n_levels=16, F=2, log2_T=19, aabb_scale=1)
+    params = util.random_params(L, seed=0, trained_like=True).astype(np.float16)
+    rng = M.pcg32_seed(1337)
+    best = None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        g = M.generate_training_samples(n_rays, 0, n_rays, rng, cfg, views, len(views), bf, n_rays * 128)
+        t_march = time.perf_counter() - t0
+        ns = max(g["n_samples"], 1)
+        coords = g["coords"][:min(ns, n_net)]
+        if coords.shape[0] < n_net:
+            coords = np.concatenate([coords, util.random_coords(n_net - coords.shape[0], seed=3)])
+        dl = (np.random.default_rng(1).normal(0, 1, size=(n_net, 4)) * 0.1).astype(np.float16)
+        t1 = time.perf_counter()
+        O.nerf_forward(L, params, coords)            # the pre-compaction inference pass
+        O.nerf_backward(L, params, coords, dl)       # forward + backward of the training pass
+        t_net = time.perf_counter() - t1
+        # scale the march part to the same number of samples as the network part
+        t_total = t_net + t_march * (n_net / ns)
+        sps = n_net / t_total
+        best = sps if best is None else max(best, sps)
+    desc = f"oracle port: C march+loss of {n_rays} rays, numpy hash-grid+MLP fwd and fwd+bwd of {n_net} samples (L16F2T19)"
+    return best, desc, os.cpu_count() or 1
+
+
+def run_reference_arm(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    vals = []
+    desc, cores = "", 1
+    for i in range(args.warmup + args.steps):
+        sps, desc, cores = cpu_training_sample(n_rays=1024, n_net=8192)
+        if i >= args.warmup:
+            vals.append(sps)
+    v = float(np.mean(vals))
+    ms = 8192 / v * 1e3
+    line = {
+        "impl": "reference", "metric": "nerf_training_samples_per_sec", "value": v, "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "note": "tiny-cuda-nn has no CPU implementation (SURVEY.md §0.2); this is the CPU oracle port of the same path on a bounded sample per step"},
+        "cpu_baseline": {"value": v, "unit": "samples/s", "cores": cores, "kind": "port", "sample": desc},
+        "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=300)
+    ap.add_argument("--impl", default="ngp_b200", choices=["ngp_b200", "reference"])
+    ap.add_argument("--views", type=int, default=N_VIEWS)
+    ap.add_argument("--res", type=int, default=RES)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--render", action="store_true", help="also time a 1920x1080 render (reported as extra keys)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+    assert args.warmup >= 3, "timing rules: at least 3 warm-up steps"
+
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}: launch through torch.distributed.run"
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    __import__("__graft_entry__").build() if not (ROOT / "instant-ngp_b200" / "libngp_b200.so").exists() else None
+    P = pkg()
+    lib = P.load_library()
+    tb, imgs = build_testbed(rank, world, args.views, args.res)
+    n_params = tb.n_params
+
+    grads_t = counters_t = None
+    if world > 1:
+        grads_t = torch.as_tensor(DevicePtrTensor(tb.grads_ptr(), n_params, "<f2"), device="cuda")
+
+    def step():
+        if world == 1:
+            tb.train(BATCH)
+        else:
+            tb.train_compute_grads(BATCH)
+            nonlocal counters_t
+            if counters_t is None:
+                counters_t = torch.as_tensor(DevicePtrTensor(tb.dp_counters_ptr(), 4, "<i4"), device="cuda")
+            dist.all_reduce(grads_t)       # one NCCL all-reduce of the flat fp16 gradient buffer (hash grid + MLPs)
+            dist.all_reduce(counters_t)    # 16 bytes: ray / sample counters for the shared rays_per_batch controller
+            tb.train_apply_grads()
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- warm-up (reaches the steady state of the rays_per_batch controller and of the occupancy grid)
+    for _ in range(args.warmup):
+        step()
+    sync_all()
+
+    # ---- timed region: device-resident dataset
+    launches0 = lib.ngp_launch_count()
+    tb.set_profiling(True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    samples = 0
+    rays = 0
+    with ClockSampler(local_rank) as clk:
+        sync_all()
+        e0.record()
+        for _ in range(args.steps):
+            step()
+            c = tb.counters()
+            samples += c["measured_batch_size"]
+            rays += c["rays_per_batch"]
+        e1.record()
+        sync_all()
+    ms_total = e0.elapsed_time(e1)
+    launches = lib.ngp_launch_count() - launches0
+    phases = tb.phase_ms()
+    tb.set_profiling(False)
+    clocks = clk.summary()
+
+    # ---- e2e: one training view streamed from pinned host memory per step + counters/loss read back
+    pinned = torch.from_numpy(np.ascontiguousarray(imgs[0])).pin_memory()
+    h2d_bytes = pinned.numel() * 4
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2e_samples = 0
+    sync_all()
+    f0.record()
+    for i in range(args.steps):
+        tb.update_image_async(i % args.views, pinned.data_ptr())   # H2D of this step's new training view
+        step()
+        e2e_samples += tb.counters()["measured_batch_size"]        # D2H: counters (16 B) each step, loss every 16th
+        _ = tb.loss
+    f1.record()
+    sync_all()
+    ms_e2e = f0.elapsed_time(f1)
+
+    # ---- reduce over ranks: time = max, work = sum
+    t = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device="cuda")
+    w = torch.tensor([samples, e2e_samples, rays], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(w)
+    ms_total, ms_e2e = t.tolist()
+    samples, e2e_samples, rays = w.tolist()
+
+    if rank == 0:
+        value = samples / (ms_total * 1e-3)
+        e2e = e2e_samples / (ms_e2e * 1e-3)
+        pk = peaks()
+        # dominant kernel: the fused forward/backward (k_nerf_train).  Algorithmic bytes per trained sample (SURVEY.md §8d,
+        # DESIGN.md): 512 B hash-table reads + 512 B fp16 gradient reductions (1024 B read-modify-write traffic) + 28 B
+        # coordinates + 8 B dL/dout = 1572 B.
+        n_fb = max(phases["steps"], 1)
+        fb_ms = phases["forward_backward"] / n_fb
+        alg_bytes = 1572.0 * BATCH
+        achieved = alg_bytes / (fb_ms * 1e-3) / 1e9 if fb_ms > 0 else None
+        roofline = {"bound": "hbm", "kernel": "k_nerf_train (+k_mlp_grads_finalize)", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                    "frac": (achieved / pk["hbm_gbs"]) if achieved else None, "traffic": None, "peak_source": pk["source"], "ms_per_launch": fb_ms,
+                    "algorithmic_bytes_per_launch": alg_bytes,
+                    "note": "the 26 MB fp16 table is L2-resident on B200: gathers/reductions are L2-bound, so algorithmic GB/s may exceed the HBM copy peak"}
+        line = {
+            "metric": "nerf_training_samples_per_sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+            "config": {"workload": WORKLOAD if (args.views, args.res) == (N_VIEWS, RES) else f"synthetic ball {args.views}x{args.res}^2 L16F2T19 batch 2^18",
+                       "batch_per_gpu": BATCH, "l2_policy": "inputs larger than L2: 1.0 GB image set + 340 MB parameter/optimizer state per step, no explicit flush",
+                       "parallelism": f"dp{world}"},
+            "rays_per_sec": rays / (ms_total * 1e-3),
+            "phase_ms_per_step": {k: v / n_fb for k, v in phases.items() if k != "steps"},
+            "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 20, "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": roofline,
+        }
+        if args.render:
+            S = syn()
+            cam = S.sphere_cameras(8, radius=1.3)[3]
+            W, H = 1920, 1080
+            focal = 0.5 * H / np.tan(0.5 * np.deg2rad(40.0))
+            rgba = torch.zeros(H, W, 4, device="cuda")
+            depth = torch.zeros(H, W, device="cuda")
+            for _ in range(3):
+                tb.render_device(W, H, cam, focal, rgba.data_ptr(), depth.data_ptr())
+            r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            r0.record()
+            for _ in range(10):
+                tb.render_device(W, H, cam, focal, rgba.data_ptr(), depth.data_ptr())
+            r1.record()
+            torch.cuda.synchronize()
+            ms = r0.elapsed_time(r1) / 10
+            line["render"] = {"ms_per_frame": ms, "mrays_per_sec": W * H / ms / 1e3, "resolution": [W, H], "coverage": float((rgba[..., 3] > 0.5).float().mean())}
+        if world == 1 and not args.no_cpu_baseline:
+            sps, desc, cores = cpu_training_sample()
+            line["cpu_baseline"] = {"value": sps, "unit": "samples/s", "cores": cores, "kind": "port", "sample": desc}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -180,17 +180,20 @@ int ngp_optimizer_step(const ngp_nerf_desc* d, void* stream, const ngp_adam_cfg*
  * ------------------------------------------------------------------------------------------------------------- */
 
 /* ≙ generate_training_samples_nerf (testbed_nerf.cu:691-849).  rng_state/rng_inc: the Testbed pcg32 by value.
- * Outputs: ray_indices[n_rays], rays (6 floats o,d per ray), numsteps[2*n_rays] (count, base), coords[max_samples x 7].
- * counters must be zeroed by the caller.  Slot order is deterministic here (warp-ordered reservation), unlike the
- * reference's per-thread atomics; compare as a map ray_id -> (count). */
-int ngp_nerf_generate_training_samples(void* stream, uint32_t n_rays, uint32_t n_rays_total, uint64_t rng_state, uint64_t rng_inc,
+ * This call handles rays [ray_offset, ray_offset + n_rays) of a logical batch of n_rays_global rays (single GPU:
+ * ray_offset = 0, n_rays_global = n_rays; data parallel: one shard per rank — image selection and the per-ray random
+ * stream are keyed on the global ray id, so the union of shards is the batch one GPU would draw).
+ * Outputs: ray_indices[n_rays] (global ids), rays (6 floats o,d per ray), numsteps[2*n_rays] (count, base),
+ * coords[max_samples x 7].  counters must be zeroed by the caller.  Slot order is warp-ordered here, atomics-ordered in
+ * the reference; compare as a map ray_id -> (count, coordinates). */
+int ngp_nerf_generate_training_samples(void* stream, uint32_t n_rays, uint32_t ray_offset, uint32_t n_rays_global, uint64_t rng_state, uint64_t rng_inc,
 	const ngp_nerf_train_cfg* cfg, const ngp_train_view* views_dev, uint32_t n_views, const uint8_t* density_grid_bitfield,
 	uint32_t max_samples, ngp_nerf_counters* counters_dev, uint32_t* ray_indices, float* rays, uint32_t* numsteps, float* coords);
 
 /* ≙ compute_loss_kernel_train_nerf (testbed_nerf.cu:852-1180): composite, loss, compaction, dL/doutput.
  * network_output: n_samples x 4 halves. Writes coords_compacted [max_compacted x 7], dloss [max_compacted x 4 halves],
- * loss_per_ray[n_rays] (may be NULL). */
-int ngp_nerf_compute_loss(void* stream, uint32_t n_rays, uint32_t n_rays_total, uint64_t rng_state, uint64_t rng_inc,
+ * loss_per_ray[n_rays] (may be NULL).  Loss and gradients are normalised by n_rays_global (testbed_nerf.cu:1039,1073). */
+int ngp_nerf_compute_loss(void* stream, uint32_t n_rays, uint32_t n_rays_global, uint64_t rng_state, uint64_t rng_inc,
 	const ngp_nerf_train_cfg* cfg, const ngp_train_view* views_dev, uint32_t n_views, const void* network_output_fp16,
 	uint32_t max_compacted, ngp_nerf_counters* counters_dev, const uint32_t* ray_indices, const float* rays, uint32_t* numsteps,
 	const float* coords, float* coords_compacted, void* dloss_fp16, float* loss_per_ray, const float* mean_density_dev);
@@ -286,6 +289,16 @@ int ngp_testbed_render_device(ngp_testbed* t, int32_t width, int32_t height, con
 int ngp_testbed_save_snapshot(ngp_testbed* t, const char* path);
 int ngp_testbed_load_snapshot(ngp_testbed* t, const char* path);
 int ngp_testbed_sync(ngp_testbed* t);
+/* Per-phase device time of Testbed::train, measured with CUDA events on the Testbed stream (the reference only has host
+ * wall-clock EMAs m_training_prep_ms / m_training_ms, testbed.h:1023-1027).  Phases: 0 occupancy-grid update, 1 training
+ * sample generation, 2 inference over the generated samples, 3 loss + compaction + roll-over, 4 fused forward/backward,
+ * 5 optimizer.  get_phase_ms returns the accumulated milliseconds and the number of steps since the last call. */
+#define NGP_N_PHASES 6
+int ngp_testbed_set_profiling(ngp_testbed* t, int enable);
+int ngp_testbed_get_phase_ms(ngp_testbed* t, float* ms_out, uint32_t* n_steps);
+/* Streaming data: overwrite training image `idx` (already set once with ngp_testbed_set_image, same size) from a host
+ * buffer, asynchronously on the Testbed stream (pinned memory makes the copy truly asynchronous). */
+int ngp_testbed_update_image_async(ngp_testbed* t, uint32_t idx, const float* rgba_host);
 /* number of kernel launches issued by this library since load (bench.py's gpu_launches). */
 uint64_t ngp_launch_count(void);
 

@@ -141,7 +141,7 @@ PROTOTYPES = {
     "ngp_nerf_forward_backward": (C.c_int, [P(NerfDesc), vp, u32, vp, vp, vp, vp, vp]),
     "ngp_grid_encode": (C.c_int, [P(GridDesc), vp, u32, vp, u32, vp, vp]),
     "ngp_optimizer_step": (C.c_int, [P(NerfDesc), vp, P(AdamCfg), vp, vp, vp, vp, vp, vp, vp]),
-    "ngp_nerf_generate_training_samples": (C.c_int, [vp, u32, u32, u64, u64, P(NerfTrainCfg), vp, u32, vp, u32, vp, vp, vp, vp, vp]),
+    "ngp_nerf_generate_training_samples": (C.c_int, [vp, u32, u32, u32, u64, u64, P(NerfTrainCfg), vp, u32, vp, u32, vp, vp, vp, vp, vp]),
     "ngp_nerf_compute_loss": (C.c_int, [vp, u32, u32, u64, u64, P(NerfTrainCfg), vp, u32, vp, u32, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "ngp_nerf_fill_rollover": (C.c_int, [vp, u32, vp, vp, vp]),
     "ngp_nerf_density_grid_scratch_bytes": (C.c_size_t, [u32]),
@@ -183,6 +183,9 @@ PROTOTYPES = {
     "ngp_testbed_save_snapshot": (C.c_int, [vp, cp]),
     "ngp_testbed_load_snapshot": (C.c_int, [vp, cp]),
     "ngp_testbed_sync": (C.c_int, [vp]),
+    "ngp_testbed_set_profiling": (C.c_int, [vp, C.c_int]),
+    "ngp_testbed_get_phase_ms": (C.c_int, [vp, P(f32), P(u32)]),
+    "ngp_testbed_update_image_async": (C.c_int, [vp, u32, vp]),
 }
 
 _lib = None

@@ -246,6 +246,13 @@ struct ngp_testbed {
 	// data parallel
 	uint32_t dp_rank = 0, dp_world = 1;
 
+	// profiling (CUDA events per phase)
+	bool profiling = false;
+	cudaEvent_t ev[NGP_N_PHASES][2] = {};
+	bool ev_used[NGP_N_PHASES] = {};
+	float phase_ms[NGP_N_PHASES] = {};
+	uint32_t phase_steps = 0;
+
 	// render
 	DevBuf<uint8_t> render_scratch;
 	DevBuf<float> render_rgba, render_depth;
@@ -465,6 +472,34 @@ static void tb_ensure_step_scratch(ngp_testbed* t, uint32_t batch) {
 	t->last_batch = batch;
 }
 
+struct PhaseTimer {
+	ngp_testbed* t;
+	int phase;
+	PhaseTimer(ngp_testbed* tb, int ph) : t(tb), phase(ph) {
+		if (!t->profiling) return;
+		if (!t->ev[phase][0]) {
+			cudaEventCreate(&t->ev[phase][0]);
+			cudaEventCreate(&t->ev[phase][1]);
+		}
+		cudaEventRecord(t->ev[phase][0], t->stream);
+	}
+	~PhaseTimer() {
+		if (!t->profiling) return;
+		cudaEventRecord(t->ev[phase][1], t->stream);
+		t->ev_used[phase] = true;
+	}
+};
+static void tb_collect_phases(ngp_testbed* t) {
+	if (!t->profiling) return;
+	for (int p = 0; p < NGP_N_PHASES; ++p) {
+		if (!t->ev_used[p]) continue;
+		float ms = 0.0f;
+		if (cudaEventElapsedTime(&ms, t->ev[p][0], t->ev[p][1]) == cudaSuccess) t->phase_ms[p] += ms;
+		t->ev_used[p] = false;
+	}
+	++t->phase_steps;
+}
+
 static uint32_t tb_n_views(const ngp_testbed* t) { return std::min(t->n_images_for_training, t->n_images); }
 
 // training_prep_nerf (testbed_nerf.cu:3385-3398)
@@ -488,7 +523,10 @@ static void tb_compute_grads(ngp_testbed* t, uint32_t batch) {
 
 	// Testbed::train (src/testbed.cu:4596-4614): density-grid prep every clamp(step/16, 1, 16) steps
 	const uint32_t n_prep_to_skip = std::min(std::max(t->training_step / 16u, 1u), 16u);
-	if (t->training_step % n_prep_to_skip == 0) tb_training_prep(t);
+	if (t->training_step % n_prep_to_skip == 0) {
+		PhaseTimer pt(t, 0);
+		tb_training_prep(t);
+	}
 
 	const uint32_t max_samples = batch * 16;
 	uint32_t max_inference;
@@ -506,13 +544,25 @@ static void tb_compute_grads(ngp_testbed* t, uint32_t batch) {
 	NGPB_CUDA_CHECK(cudaMemsetAsync(t->counters.p, 0, sizeof(ngp_nerf_counters), t->stream));
 	NGPB_CUDA_CHECK(cudaMemsetAsync(t->loss_per_ray.p, 0, sizeof(float) * rays_local, t->stream));
 	(void)n_rays_total;
-	generate_training_samples(t->stream, rays_local, t->dp_rank * rays_local, rays_global, t->rng.state, t->rng.inc, t->cfg, t->views_dev.p, tb_n_views(t),
-		t->bitfield.p, max_inference, t->counters.p, t->ray_indices.p, t->rays.p, t->numsteps.p, t->coords.p);
-	nerf_inference_counted(t->desc, t->stream, max_inference, &t->counters.p->n_samples, t->coords.p, t->params.p, t->mlp_out.p);
-	compute_loss(t->stream, rays_local, rays_global, t->rng.state, t->rng.inc, t->cfg, t->views_dev.p, tb_n_views(t), t->mlp_out.p, batch, t->counters.p,
-		t->ray_indices.p, t->rays.p, t->numsteps.p, t->coords.p, t->coords_compacted.p, t->dloss.p, t->loss_per_ray.p, t->mean_density.p);
-	fill_rollover(t->stream, batch, t->counters.p, t->coords_compacted.p, t->dloss.p);
-	nerf_forward_backward(t->desc, t->stream, batch, t->coords_compacted.p, t->params.p, t->dloss.p, t->grads.p, t->mlp_grads_f32.p, nullptr);
+	{
+		PhaseTimer pt(t, 1);
+		generate_training_samples(t->stream, rays_local, t->dp_rank * rays_local, rays_global, t->rng.state, t->rng.inc, t->cfg, t->views_dev.p, tb_n_views(t),
+			t->bitfield.p, max_inference, t->counters.p, t->ray_indices.p, t->rays.p, t->numsteps.p, t->coords.p);
+	}
+	{
+		PhaseTimer pt(t, 2);
+		nerf_inference_counted(t->desc, t->stream, max_inference, &t->counters.p->n_samples, t->coords.p, t->params.p, t->mlp_out.p);
+	}
+	{
+		PhaseTimer pt(t, 3);
+		compute_loss(t->stream, rays_local, rays_global, t->rng.state, t->rng.inc, t->cfg, t->views_dev.p, tb_n_views(t), t->mlp_out.p, batch, t->counters.p,
+			t->ray_indices.p, t->rays.p, t->numsteps.p, t->coords.p, t->coords_compacted.p, t->dloss.p, t->loss_per_ray.p, t->mean_density.p);
+		fill_rollover(t->stream, batch, t->counters.p, t->coords_compacted.p, t->dloss.p);
+	}
+	{
+		PhaseTimer pt(t, 4);
+		nerf_forward_backward(t->desc, t->stream, batch, t->coords_compacted.p, t->params.p, t->dloss.p, t->grads.p, t->mlp_grads_f32.p, nullptr);
+	}
 	t->rng.advance();
 	t->grads_pending = true;
 	t->get_loss_pending = (t->training_step % 16 == 0);
@@ -540,13 +590,17 @@ static void tb_apply_grads(ngp_testbed* t) {
 	a.ema_step = t->optimizer_step;
 	a.optimize_matrix_params = t->train_network;
 	a.optimize_non_matrix_params = t->train_encoding;
-	optimizer_step(t->desc, t->stream, a, t->params_fp32.p, t->params.p, t->params_ema.p, t->grads.p, t->m1.p, t->m2.p, t->param_steps.p);
+	{
+		PhaseTimer pt(t, 5);
+		optimizer_step(t->desc, t->stream, a, t->params_fp32.p, t->params.p, t->params_ema.p, t->grads.p, t->m1.p, t->m2.p, t->param_steps.p);
+	}
 	++t->training_step;
 	t->grads_pending = false;
 
 	ngp_nerf_counters c{};
 	NGPB_CUDA_CHECK(cudaMemcpyAsync(&c, t->counters.p, sizeof(c), cudaMemcpyDeviceToHost, t->stream));
 	NGPB_CUDA_CHECK(cudaStreamSynchronize(t->stream));
+	tb_collect_phases(t);
 	// with data parallelism the caller has summed the counters over ranks; use the per-rank mean
 	const uint32_t n_samples = c.n_samples / t->dp_world, n_compacted = c.n_samples_compacted / t->dp_world;
 	t->measured_batch_size = 0;
@@ -628,19 +682,18 @@ int ngp_optimizer_step(const ngp_nerf_desc* d, void* stream, const ngp_adam_cfg*
 	uint32_t* steps) {
 	NGPB_TRY(require_device(); optimizer_step(*d, (cudaStream_t)stream, *cfg, p32, (__half*)p16, (__half*)ema, (__half*)grads, m1, m2, steps));
 }
-int ngp_nerf_generate_training_samples(void* stream, uint32_t n_rays, uint32_t n_rays_total, uint64_t rng_state, uint64_t rng_inc,
+int ngp_nerf_generate_training_samples(void* stream, uint32_t n_rays, uint32_t ray_offset, uint32_t n_rays_global, uint64_t rng_state, uint64_t rng_inc,
 	const ngp_nerf_train_cfg* cfg, const ngp_train_view* views, uint32_t n_views, const uint8_t* bitfield, uint32_t max_samples, ngp_nerf_counters* counters,
 	uint32_t* ray_indices, float* rays, uint32_t* numsteps, float* coords) {
-	(void)n_rays_total;
-	NGPB_TRY(require_device(); generate_training_samples((cudaStream_t)stream, n_rays, 0, n_rays, rng_state, rng_inc, *cfg, views, n_views, bitfield,
+	NGPB_TRY(require_device(); NGPB_CHECK(n_rays_global >= n_rays && ray_offset <= n_rays_global - n_rays, "ray shard outside the global batch");
+		generate_training_samples((cudaStream_t)stream, n_rays, ray_offset, n_rays_global, rng_state, rng_inc, *cfg, views, n_views, bitfield,
 		max_samples, counters, ray_indices, rays, numsteps, coords));
 }
-int ngp_nerf_compute_loss(void* stream, uint32_t n_rays, uint32_t n_rays_total, uint64_t rng_state, uint64_t rng_inc, const ngp_nerf_train_cfg* cfg,
+int ngp_nerf_compute_loss(void* stream, uint32_t n_rays, uint32_t n_rays_global, uint64_t rng_state, uint64_t rng_inc, const ngp_nerf_train_cfg* cfg,
 	const ngp_train_view* views, uint32_t n_views, const void* network_output, uint32_t max_compacted, ngp_nerf_counters* counters,
 	const uint32_t* ray_indices, const float* rays, uint32_t* numsteps, const float* coords, float* coords_compacted, void* dloss, float* loss_per_ray,
 	const float* mean_density) {
-	(void)n_rays_total;
-	NGPB_TRY(require_device(); compute_loss((cudaStream_t)stream, n_rays, n_rays, rng_state, rng_inc, *cfg, views, n_views, (const __half*)network_output,
+	NGPB_TRY(require_device(); compute_loss((cudaStream_t)stream, n_rays, n_rays_global, rng_state, rng_inc, *cfg, views, n_views, (const __half*)network_output,
 		max_compacted, counters, ray_indices, rays, numsteps, coords, coords_compacted, (__half*)dloss, loss_per_ray, mean_density));
 }
 int ngp_nerf_fill_rollover(void* stream, uint32_t target_batch, const ngp_nerf_counters* counters, float* coords_compacted, void* dloss) {
@@ -1062,6 +1115,31 @@ int ngp_testbed_load_snapshot(ngp_testbed* t, const char* path) {
 		t->reduce_scratch.ensure(1024);
 		update_bitfield(t->stream, t->cfg.max_cascade, t->density_grid.p, t->bitfield.p, t->mean_density.p, t->reduce_scratch.p);
 		NGPB_CUDA_CHECK(cudaStreamSynchronize(t->stream));
+	});
+}
+int ngp_testbed_set_profiling(ngp_testbed* t, int enable) {
+	t->profiling = enable != 0;
+	for (int p = 0; p < NGP_N_PHASES; ++p) {
+		t->phase_ms[p] = 0.0f;
+		t->ev_used[p] = false;
+	}
+	t->phase_steps = 0;
+	return 0;
+}
+int ngp_testbed_get_phase_ms(ngp_testbed* t, float* ms_out, uint32_t* n_steps) {
+	for (int p = 0; p < NGP_N_PHASES; ++p) {
+		ms_out[p] = t->phase_ms[p];
+		t->phase_ms[p] = 0.0f;
+	}
+	if (n_steps) *n_steps = t->phase_steps;
+	t->phase_steps = 0;
+	return 0;
+}
+int ngp_testbed_update_image_async(ngp_testbed* t, uint32_t idx, const float* rgba_host) {
+	NGPB_TRY({
+		NGPB_CHECK(idx < t->n_images && t->pixel_bufs[idx], "update_image_async: image slot was never set");
+		const ngp_train_view& v = t->views[idx];
+		NGPB_CUDA_CHECK(cudaMemcpyAsync(t->pixel_bufs[idx], rgba_host, (size_t)v.width * v.height * 16, cudaMemcpyHostToDevice, t->stream));
 	});
 }
 int ngp_testbed_sync(ngp_testbed* t) { NGPB_TRY(NGPB_CUDA_CHECK(cudaStreamSynchronize(t->stream))); }

@@ -303,5 +303,20 @@ class Testbed:
     def load_snapshot(self, path: str) -> None:
         B.check(B.lib().ngp_testbed_load_snapshot(self._h, str(Path(path)).encode()))
 
+    # -- profiling / streaming data --------------------------------------------------------------------------------------
+    PHASES = ("occupancy_grid", "sample_generation", "inference", "loss_compaction", "forward_backward", "optimizer")
+
+    def set_profiling(self, enable: bool) -> None:
+        B.check(B.lib().ngp_testbed_set_profiling(self._h, int(enable)))
+
+    def phase_ms(self) -> dict:
+        ms = (C.c_float * 6)()
+        n = C.c_uint32(0)
+        B.check(B.lib().ngp_testbed_get_phase_ms(self._h, ms, C.byref(n)))
+        return {"steps": n.value, **{k: float(ms[i]) for i, k in enumerate(self.PHASES)}}
+
+    def update_image_async(self, frame_idx: int, host_ptr: int) -> None:
+        B.check(B.lib().ngp_testbed_update_image_async(self._h, frame_idx, C.c_void_p(host_ptr)))
+
     def sync(self) -> None:
         B.check(B.lib().ngp_testbed_sync(self._h))

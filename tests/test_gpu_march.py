@@ -41,8 +41,12 @@ SCENES = [
 ]
 
 
-def run_generator(lib, scene, n_rays, max_samples, seed=1337):
+def run_generator(lib, scene, n_rays, max_samples, seed=1337, ray_offset=0, n_rays_global=None):
+    import time
+
     import torch
+
+    t_start = time.time()
 
     imgs, cams, focal = S.make_dataset(n_images=7, width=96, height=64, radius=scene["radius"])
     cfg = util.make_train_cfg(aabb_scale=scene["aabb_scale"])
@@ -50,7 +54,8 @@ def run_generator(lib, scene, n_rays, max_samples, seed=1337):
     views, keep = util.make_views(imgs, cams, focal, lens=scene["lens"])
     t_views, tens = util.views_to_device(views, keep)
     rng = M.pcg32_seed(seed)
-    want = M.generate_training_samples(n_rays, 0, n_rays, rng, cfg, views, len(views), bf, max_samples)
+    n_rays_global = n_rays_global or n_rays
+    want = M.generate_training_samples(n_rays, ray_offset, n_rays_global, rng, cfg, views, len(views), bf, max_samples)
 
     t_bf = dev(bf)
     t_cnt = torch.zeros(4, dtype=torch.int32, device="cuda")
@@ -58,21 +63,25 @@ def run_generator(lib, scene, n_rays, max_samples, seed=1337):
     t_rays = torch.zeros(n_rays, 6, dtype=torch.float32, device="cuda")
     t_ns = torch.zeros(n_rays, 2, dtype=torch.int32, device="cuda")
     t_co = torch.zeros(max_samples, 7, dtype=torch.float32, device="cuda")
-    rc = lib.ngp_nerf_generate_training_samples(stream(), n_rays, 0, rng[0], rng[1], C.byref(cfg), t_views.data_ptr(), len(views), t_bf.data_ptr(), max_samples,
+    rc = lib.ngp_nerf_generate_training_samples(stream(), n_rays, ray_offset, n_rays_global, rng[0], rng[1], C.byref(cfg), t_views.data_ptr(), len(views), t_bf.data_ptr(), max_samples,
                                                 t_cnt.data_ptr(), t_ri.data_ptr(), t_rays.data_ptr(), t_ns.data_ptr(), t_co.data_ptr())
     assert rc == 0, lib.ngp_last_error()
     torch.cuda.synchronize()
+    print(f"run_generator: {time.time() - t_start:.2f} s total")
     cnt = t_cnt.cpu().numpy().view(np.uint32)
     got = dict(n_kept=int(cnt[0]), n_samples=int(cnt[1]), ray_indices=t_ri.cpu().numpy().view(np.uint32), rays=t_rays.cpu().numpy(),
                numsteps=t_ns.cpu().numpy().view(np.uint32), coords=t_co.cpu().numpy())
     ctx = dict(cfg=cfg, views=views, keep=keep, t_views=t_views, tens=tens, bf=bf, t_bf=t_bf, rng=rng, dev=dict(cnt=t_cnt, ri=t_ri, rays=t_rays, ns=t_ns, co=t_co))
+    want["ray_offset"] = ray_offset
     return want, got, ctx
 
 
 @pytest.mark.parametrize("scene", SCENES)
-def test_training_samples_bit_exact(lib, scene):
-    n_rays, max_samples = 4096, 4096 * 64
-    want, got, _ = run_generator(lib, scene, n_rays, max_samples)
+@pytest.mark.parametrize("shard", [(0, None), (4096, 16384)])
+def test_training_samples_bit_exact(lib, scene, shard):
+    n_rays, max_samples = 4096, 4096 * 384
+    want, got, _ = run_generator(lib, scene, n_rays, max_samples, ray_offset=shard[0], n_rays_global=shard[1])
+    assert want["n_samples"] <= max_samples, "test scene overflows: slot order would decide which rays are kept"
     assert want["n_samples"] > 1000, "degenerate scene"
     assert got["n_kept"] == want["n_kept"]
     assert got["n_samples"] == want["n_samples"]
@@ -85,7 +94,7 @@ def test_training_samples_bit_exact(lib, scene):
         gj = gmap[rid]
         wn, wb = want["numsteps"][wj]
         gn, gb = got["numsteps"][gj]
-        assert gn == wn == want["per_ray_numsteps"][rid]
+        assert gn == wn == want["per_ray_numsteps"][rid - want.get("ray_offset", 0)]
         assert got["rays"][gj].tobytes() == want["rays"][wj].tobytes()
         assert got["coords"][gb:gb + gn].tobytes() == want["coords"][wb:wb + wn].tobytes()
     # slots tile [0, n_samples) without gaps or overlaps
@@ -115,7 +124,7 @@ def test_empty_and_ragged_inputs(lib):
     buf = torch.zeros(1 << 16, dtype=torch.float32, device="cuda")
     rng = M.pcg32_seed(7)
     for n in (0, 1, 33):
-        assert lib.ngp_nerf_generate_training_samples(stream(), n, 0, rng[0], rng[1], C.byref(cfg), t_views.data_ptr(), 3, t_bf.data_ptr(), 1024, t_cnt.data_ptr(),
+        assert lib.ngp_nerf_generate_training_samples(stream(), n, 0, n, rng[0], rng[1], C.byref(cfg), t_views.data_ptr(), 3, t_bf.data_ptr(), 1024, t_cnt.data_ptr(),
                                                       buf.data_ptr(), buf.data_ptr(), buf.data_ptr(), buf.data_ptr()) == 0
     torch.cuda.synchronize()
     assert t_cnt.cpu().numpy().tolist() == [0, 0, 0, 0]
@@ -126,7 +135,7 @@ def test_empty_and_ragged_inputs(lib):
 def test_loss_and_compaction_bit_exact(lib, scene, loss_type, random_bg):
     import torch
 
-    n_rays, max_samples, batch = 4096, 4096 * 64, 1 << 15
+    n_rays, max_samples, batch = 4096, 4096 * 384, 1 << 15
     want, got, ctx = run_generator(lib, scene, n_rays, max_samples)
     cfg = ctx["cfg"]
     cfg.loss_type, cfg.random_bg_color = loss_type, random_bg
@@ -153,7 +162,7 @@ def test_loss_and_compaction_bit_exact(lib, scene, loss_type, random_bg):
     t_dl = torch.zeros(batch, 4, dtype=torch.float16, device="cuda")
     t_loss = torch.zeros(n_rays, dtype=torch.float32, device="cuda")
     t_md = dev(np.array([mean_density], dtype=np.float32))
-    rc = lib.ngp_nerf_compute_loss(stream(), n_rays, 0, ctx["rng"][0], ctx["rng"][1], C.byref(cfg), ctx["t_views"].data_ptr(), len(ctx["views"]), t_no.data_ptr(), batch,
+    rc = lib.ngp_nerf_compute_loss(stream(), n_rays, n_rays, ctx["rng"][0], ctx["rng"][1], C.byref(cfg), ctx["t_views"].data_ptr(), len(ctx["views"]), t_no.data_ptr(), batch,
                                    d["cnt"].data_ptr(), d["ri"].data_ptr(), d["rays"].data_ptr(), d["ns"].data_ptr(), d["co"].data_ptr(), t_coc.data_ptr(),
                                    t_dl.data_ptr(), t_loss.data_ptr(), t_md.data_ptr())
     assert rc == 0, lib.ngp_last_error()
