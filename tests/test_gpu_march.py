@@ -79,7 +79,7 @@ def run_generator(lib, scene, n_rays, max_samples, seed=1337, ray_offset=0, n_ra
 @pytest.mark.parametrize("scene", SCENES)
 @pytest.mark.parametrize("shard", [(0, None), (4096, 16384)])
 def test_training_samples_bit_exact(lib, scene, shard):
-    n_rays, max_samples = 4096, 4096 * 384
+    n_rays, max_samples = 4096, 4096 * 1024
     want, got, _ = run_generator(lib, scene, n_rays, max_samples, ray_offset=shard[0], n_rays_global=shard[1])
     assert want["n_samples"] <= max_samples, "test scene overflows: slot order would decide which rays are kept"
     assert want["n_samples"] > 1000, "degenerate scene"
@@ -135,7 +135,7 @@ def test_empty_and_ragged_inputs(lib):
 def test_loss_and_compaction_bit_exact(lib, scene, loss_type, random_bg):
     import torch
 
-    n_rays, max_samples, batch = 4096, 4096 * 384, 1 << 15
+    n_rays, max_samples, batch = 4096, 4096 * 1024, 1 << 15
     want, got, ctx = run_generator(lib, scene, n_rays, max_samples)
     cfg = ctx["cfg"]
     cfg.loss_type, cfg.random_bg_color = loss_type, random_bg

@@ -1,0 +1,121 @@
+"""GPU parity: the persistent render kernel against the oracle (march: bit-exact sample positions; colours: tolerance)."""
+import ctypes as C
+import importlib
+
+import numpy as np
+import pytest
+
+import util
+from oracle import march_oracle as M
+from oracle import net_oracle as O
+
+pytestmark = pytest.mark.gpu
+S = importlib.import_module("instant-ngp_b200.synthetic")
+
+
+def make_render_cfg(P, lib, w, h, cam, focal, aabb_scale, spp_index=0):
+    rc = P.RenderCfg()
+    rc.width, rc.height = w, h
+    rc.focal_x = rc.focal_y = focal
+    rc.screen_x = rc.screen_y = 0.5
+    m = np.asarray(cam, dtype=np.float32)
+    for c in range(4):
+        for r in range(3):
+            rc.camera[c * 3 + r] = m[r, c]
+    half = 0.5 * aabb_scale
+    for k in range(3):
+        rc.aabb_min[k] = rc.render_aabb_min[k] = 0.5 - half
+        rc.aabb_max[k] = rc.render_aabb_max[k] = 0.5 + half
+    mc = 0
+    while (1 << mc) < aabb_scale:
+        mc += 1
+    rc.max_cascade = mc
+    assert lib.ngp_march_consts_init(C.byref(rc.march), 0.0 if aabb_scale <= 1 else 1.0 / 256.0) == 0
+    rc.rgb_activation, rc.density_activation = 2, 3
+    rc.min_transmittance = 0.01
+    rc.spp_index = spp_index
+    rc.near_distance = 0.0
+    return rc
+
+
+@pytest.mark.parametrize("aabb_scale", [1, 4])
+def test_render_matches_oracle(aabb_scale):
+    import torch
+
+    P = util.pkg()
+    lib = P.load_library()
+    d, L = util.make_desc(n_levels=16, F=2, log2_T=15, aabb_scale=aabb_scale)
+    rng = np.random.default_rng(4)
+    params = util.random_params(L, seed=31, trained_like=True)
+    # make the medium moderately dense so that rays terminate after a varying number of steps
+    params = params.astype(np.float16)
+    cams = S.sphere_cameras(4, radius=1.25)
+    w, h = 48, 40
+    focal = 0.5 * w / np.tan(0.5 * np.deg2rad(45.0))
+    rc = make_render_cfg(P, lib, w, h, cams[1], focal, aabb_scale)
+    bf = util.sphere_bitfield(radius=0.3, max_cascade=rc.max_cascade)
+    max_steps = 1024
+    n_px = w * h
+    counts = np.zeros(n_px, dtype=np.uint32)
+    coords = np.zeros((n_px, max_steps, 7), dtype=np.float32)
+    M.lib().orc_render_march(C.byref(rc), 0, h, bf.ctypes.data, max_steps, counts.ctypes.data, coords.ctypes.data)
+    assert counts.max() < max_steps and counts.max() > 10
+    flat = np.concatenate([coords[q, :counts[q]] for q in range(n_px)]) if counts.sum() else np.zeros((0, 7), np.float32)
+    net = O.nerf_forward(L, params, flat)
+    # boost density so that early termination happens (composited alpha crosses 1 - min_transmittance)
+    net_out = np.zeros((n_px, max_steps, 4), dtype=np.float16)
+    o = 0
+    for q in range(n_px):
+        net_out[q, :counts[q]] = net[o:o + counts[q]]
+        o += counts[q]
+    rgba_w = np.zeros((n_px, 4), dtype=np.float32)
+    depth_w = np.zeros(n_px, dtype=np.float32)
+    used_w = np.zeros(n_px, dtype=np.uint32)
+    M.lib().orc_render_composite(C.byref(rc), 0, h, max_steps, counts.ctypes.data, coords.ctypes.data, net_out.ctypes.data, rgba_w.ctypes.data, depth_w.ctypes.data,
+                                 used_w.ctypes.data)
+
+    t_p = torch.from_numpy(params).cuda()
+    t_bf = torch.from_numpy(bf).cuda()
+    t_rgba = torch.full((h, w, 4), -1.0, dtype=torch.float32, device="cuda")
+    t_depth = torch.full((h, w), -1.0, dtype=torch.float32, device="cuda")
+    t_scr = torch.zeros(lib.ngp_nerf_render_scratch_bytes(w, h), dtype=torch.uint8, device="cuda")
+    t_steps = torch.zeros(1, dtype=torch.int32, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+    assert lib.ngp_nerf_render(C.byref(d), stream, C.byref(rc), 0, h, t_p.data_ptr(), t_bf.data_ptr(), t_rgba.data_ptr(), t_depth.data_ptr(), t_scr.data_ptr(),
+                               t_steps.data_ptr()) == 0, lib.ngp_last_error()
+    torch.cuda.synchronize()
+    rgba_g = t_rgba.cpu().numpy().reshape(n_px, 4)
+    depth_g = t_depth.cpu().numpy().reshape(n_px)
+    steps_g = int(t_steps.cpu().numpy().view(np.uint32)[0])
+    assert (rgba_g >= 0).all(), "pixels left unwritten"
+    # network evaluations: equal to the oracle's unless a ray terminates one step earlier/later within network tolerance
+    assert abs(steps_g - int(used_w.sum())) <= 0.01 * used_w.sum() + 8, (steps_g, used_w.sum())
+    err = np.abs(rgba_g - rgba_w)
+    print("render max abs err", err.max(axis=0), "mean alpha", rgba_w[:, 3].mean(), "steps", steps_g)
+    assert err.max() <= 2e-2
+    assert np.mean(err) <= 1e-3
+    hit = rgba_w[:, 3] > 0.2
+    close = np.abs(depth_g[hit] - depth_w[hit]) <= 2e-2
+    assert close.mean() > 0.98  # the max-weight sample can flip between near-equal weights
+
+
+def test_render_empty_and_tiles():
+    import torch
+
+    P = util.pkg()
+    lib = P.load_library()
+    d, L = util.make_desc(n_levels=8, F=4, log2_T=14, aabb_scale=1)
+    params = util.random_params(L, seed=3).astype(np.float16)
+    cam = S.sphere_cameras(3, radius=1.3)[0]
+    w, h = 33, 17  # ragged: not a multiple of the 128-ray tile
+    rc = make_render_cfg(P, lib, w, h, cam, 40.0, 1)
+    t_p = torch.from_numpy(params).cuda()
+    t_bf = torch.zeros(128 ** 3, dtype=torch.uint8, device="cuda")  # nothing occupied
+    t_rgba = torch.full((h, w, 4), -1.0, dtype=torch.float32, device="cuda")
+    t_depth = torch.full((h, w), -1.0, dtype=torch.float32, device="cuda")
+    t_scr = torch.zeros(256, dtype=torch.uint8, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+    assert lib.ngp_nerf_render(C.byref(d), stream, C.byref(rc), 0, h, t_p.data_ptr(), t_bf.data_ptr(), t_rgba.data_ptr(), t_depth.data_ptr(), t_scr.data_ptr(), None) == 0
+    torch.cuda.synchronize()
+    assert (t_rgba == 0).all() and (t_depth == 16384.0).all()
+    assert lib.ngp_nerf_render(C.byref(d), stream, C.byref(rc), 5, 5, t_p.data_ptr(), t_bf.data_ptr(), t_rgba.data_ptr(), t_depth.data_ptr(), t_scr.data_ptr(), None) != 0
