@@ -249,6 +249,7 @@ def main() -> None:
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     samples = 0
     rays = 0
+    pre = 0
     with ClockSampler(local_rank) as clk:
         sync_all()
         e0.record()
@@ -257,6 +258,7 @@ def main() -> None:
             c = tb.counters()
             samples += c["measured_batch_size"]
             rays += c["rays_per_batch"]
+            pre += c["measured_batch_size_before_compaction"]
         e1.record()
         sync_all()
     ms_total = e0.elapsed_time(e1)
@@ -312,6 +314,7 @@ def main() -> None:
                        "batch_per_gpu": BATCH, "l2_policy": "inputs larger than L2: 1.0 GB image set + 340 MB parameter/optimizer state per step, no explicit flush",
                        "parallelism": f"dp{world}"},
             "rays_per_sec": rays / (ms_total * 1e-3),
+            "per_step": {"rays": rays / args.steps / world, "samples_before_compaction": pre / args.steps, "samples_compacted": samples / args.steps / world},
             "phase_ms_per_step": {k: v / n_fb for k, v in phases.items() if k != "steps"},
             "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 20, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches),

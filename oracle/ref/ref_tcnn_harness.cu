@@ -8,7 +8,7 @@
 //
 // File layout (little endian): u32 magic 'NGPR', u32 n_levels, u32 F, u32 log2_T, f32 per_level_scale, u32 n_params,
 //   u32 n_samples, then fp16 params[n_params], f32 coords[n*7], fp16 inference_out[n*16], fp16 forward_out[n*16],
-//   fp16 dL_dout[n*16], fp16 grads[n_params], then 3 optimizer steps: f32 w32[n_params], fp16 w16[n_params], fp16 ema[n_params].
+//   fp16 dL_dout[n*16], fp16 grads[n_params], then 2 optimizer steps: f32 w32[n_params], fp16 w16[n_params], fp16 ema[n_params], fp16 grads[n_params] (the gradient consumed by that step).
 #include <neural-graphics-primitives/common.h>
 #include <neural-graphics-primitives/nerf_network.h>
 
@@ -107,7 +107,7 @@ static int run(const char* path, uint32_t n_levels, uint32_t F, uint32_t log2_T,
 	// the trainer points inference params at the EMA weights and seeds them with the cast master weights (trainer.h:409-421)
 	precision_t* ema = optimizer->custom_weights();
 	CUDA_CHECK_THROW(cudaMemcpy(ema, params.data(), n_params * sizeof(precision_t), cudaMemcpyDeviceToDevice));
-	for (int step = 0; step < 3; ++step) {
+	for (int step = 0; step < 2; ++step) {
 		if (step > 0) {
 			// new gradients for steps 2 and 3: a fresh backward pass with the updated weights
 			auto c2 = network->forward(stream, input, &out_fwd, false, false);
@@ -132,9 +132,9 @@ int main(int argc, char** argv) {
 	}
 	try {
 		std::string dir = argv[1];
-		int rc = run((dir + "/ref_tcnn_L16F2.bin").c_str(), 16, 2, 12, 1.5157166f, 512);
+		int rc = run((dir + "/ref_tcnn_L16F2.bin").c_str(), 16, 2, 10, 1.5157166f, 512);
 		if (rc) return rc;
-		rc = run((dir + "/ref_tcnn_L8F4.bin").c_str(), 8, 4, 12, 2.4380093f, 512);
+		rc = run((dir + "/ref_tcnn_L8F4.bin").c_str(), 8, 4, 10, 2.4380093f, 512);
 		return rc;
 	} catch (const std::exception& e) {
 		fprintf(stderr, "ref_tcnn failed: %s\n", e.what());

@@ -135,8 +135,10 @@ def test_empty_and_ragged_inputs(lib):
 def test_loss_and_compaction_bit_exact(lib, scene, loss_type, random_bg):
     import torch
 
-    n_rays, max_samples, batch = 4096, 4096 * 1024, 1 << 15
+    n_rays, max_samples = 4096, 4096 * 1024
     want, got, ctx = run_generator(lib, scene, n_rays, max_samples)
+    # no overflow of the compacted buffer here: which rays get clipped depends on slot order (atomics-dependent in the reference too)
+    batch = 1 << int(np.ceil(np.log2(max(got["n_samples"], 2))))
     cfg = ctx["cfg"]
     cfg.loss_type, cfg.random_bg_color = loss_type, random_bg
     k, ns = got["n_kept"], got["n_samples"]
@@ -188,6 +190,7 @@ def test_loss_and_compaction_bit_exact(lib, scene, loss_type, random_bg):
     # roll-over padding (fill_rollover_and_rescale + fill_rollover)
     t_c3 = torch.zeros(4, dtype=torch.int32, device="cuda")
     n_comp_small = 1000
+    batch = min(batch, 1 << 16)
     t_c3[2] = n_comp_small
     co_pad, dl_pad = co_g.copy(), dl_g.copy()
     M.lib().orc_fill_rollover(batch, n_comp_small, co_pad.ctypes.data, dl_pad.ctypes.data)
@@ -259,4 +262,6 @@ def test_density_grid_update_matches_oracle(lib, aabb_scale):
         bf_w = np.zeros(128 ** 3, dtype=np.uint8)
         M.lib().orc_update_bitfield(cfg.max_cascade, grid_w.ctypes.data, mean_w, bf_w.ctypes.data)
         assert t_bf.cpu().numpy().tobytes() == bf_w.tobytes()
-    assert (grid_w < 0).sum() > 0 and (grid_w > 0).sum() > 0  # some voxels culled as unseen, some populated
+    assert (grid_w > 0).sum() > 0
+    if aabb_scale > 1:
+        assert (grid_w < 0).sum() > 0  # voxels no camera sees were culled at step 0
