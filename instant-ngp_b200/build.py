@@ -26,7 +26,7 @@ COMMON = ["-std=c++17", "-O3", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler",
 # bit-identical to the CPU oracle (see include/ngp_detmath.h).
 UNITS = {
     "nerf_net.cu": [],
-    "optimizer.cu": [],
+    "optimizer.cu": ["--use_fast_math"],
     "testbed.cu": ["-fmad=false"],
     "march.cu": ["-fmad=false"],
     "render.cu": ["-fmad=false"],

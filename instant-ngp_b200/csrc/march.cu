@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(128) k_generate_training_samples(
 	const Aabb aabb{V3{cfg.aabb_min[0], cfg.aabb_min[1], cfg.aabb_min[2]}, V3{cfg.aabb_max[0], cfg.aabb_max[1], cfg.aabb_max[2]}};
 	uint32_t numsteps = 0;
 	V3 ro{0, 0, 0}, rd{0, 0, 0}, rdn{0, 0, 1}, idir{0, 0, 0};
-	float startt = 0.0f;
+	float startt = 0.0f, t_first = 0.0f;
 
 	if (in_range) {
 		const uint32_t img = image_idx(i, n_rays_global, n_views);
@@ -96,7 +96,8 @@ __global__ void __launch_bounds__(128) k_generate_training_samples(
 			startt = advance_n_steps(tmin, cfg.march, rng.next_float());
 			idir = V3{1.0f / rdn.x, 1.0f / rdn.y, 1.0f / rdn.z};
 
-			// pass 1: count the occupied steps
+			// pass 1: count the occupied steps; remember where the first one sits so that pass 2 does not re-traverse the
+			// empty space in front of it (it would reach exactly this t by exactly the same arithmetic)
 			uint32_t j = 0;
 			float t = startt;
 			V3 pos;
@@ -104,6 +105,7 @@ __global__ void __launch_bounds__(128) k_generate_training_samples(
 				const float dt = calc_dt(t, cfg.march);
 				const uint32_t mip = mip_from_dt(dt, pos, cfg.max_cascade);
 				if (density_grid_occupied_at(pos, bitfield, mip)) {
+					if (j == 0) t_first = t;
 					++j;
 					t += dt;
 				} else {
@@ -143,7 +145,7 @@ __global__ void __launch_bounds__(128) k_generate_training_samples(
 	// pass 2: write the coordinates
 	const V3 wdir = warp_direction(rdn);
 	float* co = coords_out + (size_t)base * 7;
-	float t = startt;
+	float t = t_first;
 	uint32_t j = 0;
 	V3 pos;
 	while (aabb.contains(pos = ro + t * rdn) && j < numsteps) {
@@ -188,6 +190,29 @@ __device__ inline void loss_and_gradient1(float target, float pred, uint32_t typ
 // compute_loss_kernel_train_nerf (testbed_nerf.cu:852-1180), Nerf train mode, no envmap / depth / exposure / error map.
 // network_output: 4 halves per sample (rgb raw x3, density raw).
 // ------------------------------------------------------------------------------------------------------------------
+// One WARP per ray: the 32 lanes evaluate the activations / transmittance factors of 32 consecutive samples in parallel
+// (all transcendentals live there) and the ray's running sums are then advanced in the reference's sequential order by
+// every lane redundantly from warp shuffles, so every value is produced by exactly the arithmetic of the one-thread-per-ray
+// reference kernel — and of the oracle — while 32x more threads are in flight and long rays no longer stall a warp.
+struct SampleTerms {
+	float r, g, b;   // network_to_rgb of the three colour channels
+	float alpha;     // 1 - exp(-density * dt)
+};
+__device__ __forceinline__ SampleTerms sample_terms(const __half* __restrict__ no, const float* __restrict__ ci, uint32_t k, const ngp_nerf_train_cfg& cfg,
+	float& o0, float& o1, float& o2, float& o3, float& dt) {
+	const uint2 raw = *reinterpret_cast<const uint2*>(no + (size_t)k * 4);
+	const __half2 h01 = *reinterpret_cast<const __half2*>(&raw.x), h23 = *reinterpret_cast<const __half2*>(&raw.y);
+	o0 = __low2float(h01); o1 = __high2float(h01); o2 = __low2float(h23); o3 = __high2float(h23);
+	dt = unwarp_dt(ci[(size_t)k * 7 + 3]);
+	SampleTerms s;
+	s.r = network_to_rgb(o0, cfg.rgb_activation);
+	s.g = network_to_rgb(o1, cfg.rgb_activation);
+	s.b = network_to_rgb(o2, cfg.rgb_activation);
+	const float density = network_to_density(o3, cfg.density_activation);
+	s.alpha = 1.0f - ngp_expf(-density * dt);
+	return s;
+}
+
 __global__ void __launch_bounds__(128) k_compute_loss(
 	const uint32_t n_rays_global, Pcg32 rng_in, const ngp_nerf_train_cfg cfg, const ngp_train_view* __restrict__ views, const uint32_t n_views,
 	const __half* __restrict__ network_output, const uint32_t max_compacted, ngp_nerf_counters* __restrict__ counters,
@@ -195,150 +220,155 @@ __global__ void __launch_bounds__(128) k_compute_loss(
 	const float* __restrict__ coords_in, float* __restrict__ coords_out, __half* __restrict__ dloss_out, float* __restrict__ loss_output,
 	const float* __restrict__ mean_density_ptr
 ) {
-	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // ray slot
 	const uint32_t lane = threadIdx.x & 31u;
-	const uint32_t n_rays_kept = counters->n_rays;
-	const bool active = i < n_rays_kept;
+	if (i >= counters->n_rays) return;  // warp-uniform
 	const Aabb aabb{V3{cfg.aabb_min[0], cfg.aabb_min[1], cfg.aabb_min[2]}, V3{cfg.aabb_max[0], cfg.aabb_max[1], cfg.aabb_max[2]}};
+	const float EPSILON = 1e-4f;
 
-	uint32_t numsteps = 0, base = 0, compacted_numsteps = 0;
+	const uint32_t numsteps = numsteps_in[i * 2 + 0];
+	const uint32_t base = numsteps_in[i * 2 + 1];
+	const V3 ray_o = V3{rays_in[(size_t)i * 6 + 0], rays_in[(size_t)i * 6 + 1], rays_in[(size_t)i * 6 + 2]};
+	const __half* no = network_output + (size_t)base * 4;
+	const float* ci = coords_in + (size_t)base * 7;
+
+	// ---- pass 1: composite front to back until T < EPSILON (testbed_nerf.cu:926-948)
 	float T = 1.0f;
 	V3 rgb_ray{0, 0, 0};
-	V3 ray_o{0, 0, 0};
-	const float EPSILON = 1e-4f;
-	if (active) {
-		numsteps = numsteps_in[i * 2 + 0];
-		base = numsteps_in[i * 2 + 1];
-		ray_o = V3{rays_in[(size_t)i * 6 + 0], rays_in[(size_t)i * 6 + 1], rays_in[(size_t)i * 6 + 2]};
-		const __half* no = network_output + (size_t)base * 4;
-		const float* ci = coords_in + (size_t)base * 7;
-		for (; compacted_numsteps < numsteps; ++compacted_numsteps) {
-			if (T < EPSILON) break;
-			const uint2 raw = *reinterpret_cast<const uint2*>(no + (size_t)compacted_numsteps * 4);
-			const __half2 h01 = *reinterpret_cast<const __half2*>(&raw.x), h23 = *reinterpret_cast<const __half2*>(&raw.y);
-			const V3 rgb = V3{network_to_rgb(__low2float(h01), cfg.rgb_activation), network_to_rgb(__high2float(h01), cfg.rgb_activation),
-				network_to_rgb(__low2float(h23), cfg.rgb_activation)};
-			const float dt = unwarp_dt(ci[(size_t)compacted_numsteps * 7 + 3]);
-			const float density = network_to_density(__high2float(h23), cfg.density_activation);
-			const float alpha = 1.0f - ngp_expf(-density * dt);
-			const float weight = alpha * T;
-			rgb_ray = rgb_ray + weight * rgb;
-			T *= (1.0f - alpha);
+	uint32_t compacted_numsteps = 0;
+	bool stopped = false;
+	for (uint32_t c0 = 0; c0 < numsteps && !stopped; c0 += 32) {
+		const uint32_t k = c0 + lane;
+		SampleTerms st{0, 0, 0, 0};
+		float o0, o1, o2, o3, dt;
+		if (k < numsteps) st = sample_terms(no, ci, k, cfg, o0, o1, o2, o3, dt);
+		const uint32_t n_here = (numsteps - c0) < 32u ? (numsteps - c0) : 32u;
+		for (uint32_t j = 0; j < n_here; ++j) {
+			if (T < EPSILON) {
+				stopped = true;
+				break;
+			}
+			const float a = __shfl_sync(0xFFFFFFFFu, st.alpha, j);
+			const float r = __shfl_sync(0xFFFFFFFFu, st.r, j), g = __shfl_sync(0xFFFFFFFFu, st.g, j), b = __shfl_sync(0xFFFFFFFFu, st.b, j);
+			const float weight = a * T;
+			rgb_ray = rgb_ray + weight * V3{r, g, b};
+			T *= (1.0f - a);
+			++compacted_numsteps;
 		}
 	}
 
-	// Same draws as the generator (testbed_nerf.cu:951-967)
-	V3 lg_grad{0, 0, 0};
-	float mean_loss = 0.0f;
+	// ---- target colour: same draws as the generator (testbed_nerf.cu:951-1004); computed by every lane (identical values)
+	const uint32_t ray_idx = ray_indices_in[i];
+	Pcg32 rng = rng_in;
+	rng.advance((uint64_t)ray_idx * N_MAX_RANDOM_SAMPLES_PER_RAY);
+	const uint32_t img = image_idx(ray_idx, n_rays_global, n_views);
+	const ngp_train_view* vw = &views[img];
+	float u, v;
+	random_image_pos_training(rng, vw->width, vw->height, cfg.snap_to_pixel_centers != 0, u, v);
+	rng.advance(1);  // motion-blur time
 	V3 bg{cfg.background_color[0], cfg.background_color[1], cfg.background_color[2]};
-	if (active) {
-		const uint32_t ray_idx = ray_indices_in[i];
-		Pcg32 rng = rng_in;
-		rng.advance((uint64_t)ray_idx * N_MAX_RANDOM_SAMPLES_PER_RAY);
-		const uint32_t img = image_idx(ray_idx, n_rays_global, n_views);
-		const ngp_train_view vw = views[img];
-		float u, v;
-		random_image_pos_training(rng, vw.width, vw.height, cfg.snap_to_pixel_centers != 0, u, v);
-		rng.advance(1);  // motion-blur time
-		if (cfg.random_bg_color) {
-			bg.x = rng.next_float();
-			bg.y = rng.next_float();
-			bg.z = rng.next_float();
-		}
-		bg = V3{srgb_to_linear(bg.x), srgb_to_linear(bg.y), srgb_to_linear(bg.z)};
-		const Rgba tex = read_rgba_uv(u, v, vw.width, vw.height, vw.pixels, vw.image_type);
-		V3 target;
-		if (cfg.linear_colors || cfg.color_space == NGP_COLOR_LINEAR) {
-			target = V3{tex.r + (1.0f - tex.a) * bg.x, tex.g + (1.0f - tex.a) * bg.y, tex.b + (1.0f - tex.a) * bg.z};
-			if (!cfg.linear_colors) {
-				target = V3{linear_to_srgb(target.x), linear_to_srgb(target.y), linear_to_srgb(target.z)};
-				bg = V3{linear_to_srgb(bg.x), linear_to_srgb(bg.y), linear_to_srgb(bg.z)};
-			}
-		} else {
+	if (cfg.random_bg_color) {
+		bg.x = rng.next_float();
+		bg.y = rng.next_float();
+		bg.z = rng.next_float();
+	}
+	bg = V3{srgb_to_linear(bg.x), srgb_to_linear(bg.y), srgb_to_linear(bg.z)};
+	const Rgba tex = read_rgba_uv(u, v, vw->width, vw->height, vw->pixels, vw->image_type);
+	V3 target;
+	if (cfg.linear_colors || cfg.color_space == NGP_COLOR_LINEAR) {
+		target = V3{tex.r + (1.0f - tex.a) * bg.x, tex.g + (1.0f - tex.a) * bg.y, tex.b + (1.0f - tex.a) * bg.z};
+		if (!cfg.linear_colors) {
+			target = V3{linear_to_srgb(target.x), linear_to_srgb(target.y), linear_to_srgb(target.z)};
 			bg = V3{linear_to_srgb(bg.x), linear_to_srgb(bg.y), linear_to_srgb(bg.z)};
-			if (tex.a > 0.0f) {
-				target = V3{linear_to_srgb(tex.r / tex.a) * tex.a + (1.0f - tex.a) * bg.x, linear_to_srgb(tex.g / tex.a) * tex.a + (1.0f - tex.a) * bg.y,
-					linear_to_srgb(tex.b / tex.a) * tex.a + (1.0f - tex.a) * bg.z};
-			} else {
-				target = bg;
-			}
 		}
-		if (compacted_numsteps == numsteps) rgb_ray = rgb_ray + T * bg;
-
-		float lx, ly, lz;
-		loss_and_gradient1(target.x, rgb_ray.x, cfg.loss_type, lx, lg_grad.x);
-		loss_and_gradient1(target.y, rgb_ray.y, cfg.loss_type, ly, lg_grad.y);
-		loss_and_gradient1(target.z, rgb_ray.z, cfg.loss_type, lz, lg_grad.z);
-		mean_loss = ((lx + ly) + lz) / 3.0f;
+	} else {
+		bg = V3{linear_to_srgb(bg.x), linear_to_srgb(bg.y), linear_to_srgb(bg.z)};
+		if (tex.a > 0.0f) {
+			target = V3{linear_to_srgb(tex.r / tex.a) * tex.a + (1.0f - tex.a) * bg.x, linear_to_srgb(tex.g / tex.a) * tex.a + (1.0f - tex.a) * bg.y,
+				linear_to_srgb(tex.b / tex.a) * tex.a + (1.0f - tex.a) * bg.z};
+		} else {
+			target = bg;
+		}
 	}
+	if (compacted_numsteps == numsteps) rgb_ray = rgb_ray + T * bg;
+	V3 lg_grad;
+	float lx, ly, lz;
+	loss_and_gradient1(target.x, rgb_ray.x, cfg.loss_type, lx, lg_grad.x);
+	loss_and_gradient1(target.y, rgb_ray.y, cfg.loss_type, ly, lg_grad.y);
+	loss_and_gradient1(target.z, rgb_ray.z, cfg.loss_type, lz, lg_grad.z);
+	const float mean_loss = ((lx + ly) + lz) / 3.0f;
 
-	// ---- compaction: reserve [compacted_base, +compacted_numsteps) once per warp (testbed_nerf.cu:1010-1016)
-	uint32_t incl = compacted_numsteps;
-#pragma unroll
-	for (uint32_t o = 1; o < 32; o <<= 1) {
-		const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-		if (lane >= o) incl += t;
-	}
-	const uint32_t warp_total = __shfl_sync(0xFFFFFFFFu, incl, 31);
-	uint32_t warp_base = 0;
-	if (lane == 0 && warp_total > 0) warp_base = atomicAdd(&counters->n_samples_compacted, warp_total);
-	warp_base = __shfl_sync(0xFFFFFFFFu, warp_base, 0);
-	if (!active) return;
-	const uint32_t compacted_base = warp_base + incl - compacted_numsteps;
+	// ---- compaction: one reservation per ray (testbed_nerf.cu:1010-1016)
+	uint32_t compacted_base = 0;
+	if (lane == 0) compacted_base = atomicAdd(&counters->n_samples_compacted, compacted_numsteps);
+	compacted_base = __shfl_sync(0xFFFFFFFFu, compacted_base, 0);
 	const uint32_t cb_clamped = compacted_base < max_compacted ? compacted_base : max_compacted;
 	const uint32_t room = max_compacted - cb_clamped;
 	compacted_numsteps = room < compacted_numsteps ? room : compacted_numsteps;
-	numsteps_in[i * 2 + 0] = compacted_numsteps;
-	numsteps_in[i * 2 + 1] = compacted_base;
+	if (lane == 0) {
+		numsteps_in[i * 2 + 0] = compacted_numsteps;
+		numsteps_in[i * 2 + 1] = compacted_base;
+	}
 	if (compacted_numsteps == 0) return;
-
-	if (loss_output) loss_output[i] = mean_loss / (float)n_rays_global;
+	if (loss_output && lane == 0) loss_output[i] = mean_loss / (float)n_rays_global;
 
 	const float loss_scale = cfg.loss_scale / (float)n_rays_global;
 	const float output_l2_reg = cfg.rgb_activation == NGP_ACT_EXPONENTIAL ? 1e-4f : 0.0f;
 	const float output_l1_reg_density = *mean_density_ptr < min_optical_thickness() ? 1e-4f : 0.0f;
 
-	const __half* no = network_output + (size_t)base * 4;
-	const float* ci = coords_in + (size_t)base * 7;
+	// ---- pass 2: gradients and compaction (testbed_nerf.cu:1078-1140)
 	float* co = coords_out + (size_t)compacted_base * 7;
 	__half* dl = dloss_out + (size_t)compacted_base * 4;
 	V3 rgb_ray2{0, 0, 0};
 	T = 1.0f;
-	for (uint32_t j = 0; j < compacted_numsteps; ++j) {
-		float c[7];
+	for (uint32_t c0 = 0; c0 < compacted_numsteps; c0 += 32) {
+		const uint32_t k = c0 + lane;
+		const bool mine = k < compacted_numsteps;
+		SampleTerms st{0, 0, 0, 0};
+		float o0 = 0, o1 = 0, o2 = 0, o3 = 0, dt = 0;
+		float c[7] = {0, 0, 0, 0, 0, 0, 0};
+		if (mine) {
+			st = sample_terms(no, ci, k, cfg, o0, o1, o2, o3, dt);
 #pragma unroll
-		for (int k = 0; k < 7; ++k) {
-			c[k] = ci[(size_t)j * 7 + k];
-			co[(size_t)j * 7 + k] = c[k];
+			for (int q = 0; q < 7; ++q) {
+				c[q] = ci[(size_t)k * 7 + q];
+				co[(size_t)k * 7 + q] = c[q];
+			}
 		}
-		const V3 pos = unwarp_position(V3{c[0], c[1], c[2]}, aabb);
-		const V3 dp = pos - ray_o;
-		const float depth = length3(dp);
-		const float dt = unwarp_dt(c[3]);
-		const uint2 raw = *reinterpret_cast<const uint2*>(no + (size_t)j * 4);
-		const __half2 h01 = *reinterpret_cast<const __half2*>(&raw.x), h23 = *reinterpret_cast<const __half2*>(&raw.y);
-		const float o0 = __low2float(h01), o1 = __high2float(h01), o2 = __low2float(h23), o3 = __high2float(h23);
-		const V3 rgb = V3{network_to_rgb(o0, cfg.rgb_activation), network_to_rgb(o1, cfg.rgb_activation), network_to_rgb(o2, cfg.rgb_activation)};
-		const float density = network_to_density(o3, cfg.density_activation);
-		const float alpha = 1.0f - ngp_expf(-density * dt);
-		const float weight = alpha * T;
-		rgb_ray2 = rgb_ray2 + weight * rgb;
-		T *= (1.0f - alpha);
-
-		const V3 suffix = rgb_ray - rgb_ray2;
-		const V3 dloss_by_drgb = weight * lg_grad;
-		const float d0 = loss_scale * (dloss_by_drgb.x * network_to_rgb_derivative(o0, cfg.rgb_activation) + fmaxf(0.0f, output_l2_reg * o0));
-		const float d1 = loss_scale * (dloss_by_drgb.y * network_to_rgb_derivative(o1, cfg.rgb_activation) + fmaxf(0.0f, output_l2_reg * o1));
-		const float d2 = loss_scale * (dloss_by_drgb.z * network_to_rgb_derivative(o2, cfg.rgb_activation) + fmaxf(0.0f, output_l2_reg * o2));
-		const float density_derivative = network_to_density_derivative(o3, cfg.density_activation);
-		const V3 tr = T * rgb - suffix;
-		const float dloss_by_dmlp = density_derivative * (dt * dot3(lg_grad, tr));
-		const float d3 = loss_scale * dloss_by_dmlp + (o3 < 0.0f ? -output_l1_reg_density : 0.0f) + (o3 > -10.0f && depth < cfg.near_distance ? 1e-4f : 0.0f);
-		const __half2 w01 = __floats2half2_rn(d0, d1), w23 = __floats2half2_rn(d2, d3);
-		uint2 outv;
-		outv.x = *reinterpret_cast<const uint32_t*>(&w01);
-		outv.y = *reinterpret_cast<const uint32_t*>(&w23);
-		*reinterpret_cast<uint2*>(dl + (size_t)j * 4) = outv;
+		const uint32_t n_here = (compacted_numsteps - c0) < 32u ? (compacted_numsteps - c0) : 32u;
+		float my_weight = 0.0f, my_T = 0.0f;
+		V3 my_rgb_ray2{0, 0, 0};
+		for (uint32_t j = 0; j < n_here; ++j) {
+			const float a = __shfl_sync(0xFFFFFFFFu, st.alpha, j);
+			const float r = __shfl_sync(0xFFFFFFFFu, st.r, j), g = __shfl_sync(0xFFFFFFFFu, st.g, j), b = __shfl_sync(0xFFFFFFFFu, st.b, j);
+			const float weight = a * T;
+			rgb_ray2 = rgb_ray2 + weight * V3{r, g, b};
+			T *= (1.0f - a);
+			if (lane == j) {
+				my_weight = weight;
+				my_T = T;
+				my_rgb_ray2 = rgb_ray2;
+			}
+		}
+		if (mine) {
+			const V3 pos = unwarp_position(V3{c[0], c[1], c[2]}, aabb);
+			const float depth = length3(pos - ray_o);
+			const V3 rgb = V3{st.r, st.g, st.b};
+			const V3 suffix = rgb_ray - my_rgb_ray2;
+			const V3 dloss_by_drgb = my_weight * lg_grad;
+			const float d0 = loss_scale * (dloss_by_drgb.x * network_to_rgb_derivative(o0, cfg.rgb_activation) + fmaxf(0.0f, output_l2_reg * o0));
+			const float d1 = loss_scale * (dloss_by_drgb.y * network_to_rgb_derivative(o1, cfg.rgb_activation) + fmaxf(0.0f, output_l2_reg * o1));
+			const float d2 = loss_scale * (dloss_by_drgb.z * network_to_rgb_derivative(o2, cfg.rgb_activation) + fmaxf(0.0f, output_l2_reg * o2));
+			const float density_derivative = network_to_density_derivative(o3, cfg.density_activation);
+			const V3 tr = my_T * rgb - suffix;
+			const float dloss_by_dmlp = density_derivative * (dt * dot3(lg_grad, tr));
+			const float d3 = loss_scale * dloss_by_dmlp + (o3 < 0.0f ? -output_l1_reg_density : 0.0f) + (o3 > -10.0f && depth < cfg.near_distance ? 1e-4f : 0.0f);
+			const __half2 w01 = __floats2half2_rn(d0, d1), w23 = __floats2half2_rn(d2, d3);
+			uint2 outv;
+			outv.x = *reinterpret_cast<const uint32_t*>(&w01);
+			outv.y = *reinterpret_cast<const uint32_t*>(&w23);
+			*reinterpret_cast<uint2*>(dl + (size_t)k * 4) = outv;
+		}
 	}
 }
 
@@ -520,7 +550,8 @@ void compute_loss(cudaStream_t stream, uint32_t n_rays_local, uint32_t n_rays_gl
 	ngp_nerf_counters* counters, const uint32_t* ray_indices, const float* rays, uint32_t* numsteps, const float* coords, float* coords_compacted,
 	__half* dloss, float* loss_per_ray, const float* mean_density) {
 	if (n_rays_local == 0) return;
-	k_compute_loss<<<div_round_up(n_rays_local, 128), 128, 0, stream>>>(n_rays_global, Pcg32(rng_state, rng_inc, true), cfg, views, n_views,
+	// one warp per ray, 4 rays per CTA
+	k_compute_loss<<<div_round_up(n_rays_local, 4), 128, 0, stream>>>(n_rays_global, Pcg32(rng_state, rng_inc, true), cfg, views, n_views,
 		network_output, max_compacted, counters, ray_indices, rays, numsteps, coords, coords_compacted, dloss, loss_per_ray, mean_density);
 	NGPB_LAUNCHED();
 	NGPB_CUDA_CHECK(cudaGetLastError());

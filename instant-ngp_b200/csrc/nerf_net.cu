@@ -184,13 +184,41 @@ __host__ __device__ inline uint32_t wgrad_col_base(uint32_t nhd, uint32_t nhr, b
 }
 __host__ __device__ inline uint32_t train_tmem_cols(uint32_t nhd, uint32_t nhr) { return wgrad_col_base(nhd, nhr, true, nhr + 1); }
 
-// forward of one MLP keeping every hidden activation: layer l writes hidden buffer l.
+// ---- two threads per sample -------------------------------------------------------------------------------------------
+// The training CTA has 256 threads for its 128-sample tile: thread t and thread t+128 own the same sample (row t & 127,
+// TMEM lane t & 127 — warps w and w+4 address the same 32-lane TMEM window).  "half" h = t >> 7 selects which half of the
+// per-sample work a thread does: levels [h*L/2, (h+1)*L/2) of the gather / scatter, columns [32h, 32h+32) of every
+// 64-wide epilogue.  Same shared memory and TMEM per CTA as one thread per sample, twice the warps in flight per SM
+// (ncu of the one-thread version: 12 % warps active, latency bound; profiles/r1_kernels.md).
+constexpr uint32_t TRAIN_THREADS = 2 * TILE;
+
+// epilogue of a hidden layer for this thread's 32 columns: TMEM row -> ReLU -> fp16 -> operand buffer
+__device__ __forceinline__ void tmem_row_to_smem32_relu(uint32_t taddr_row, uint32_t half, uint8_t* buf, uint32_t row) {
+	uint32_t v0[16], v1[16];
+	umma::tmem_ld16(taddr_row + half * 32u + 0, v0);
+	umma::tmem_ld16(taddr_row + half * 32u + 16, v1);
+	umma::tmem_ld_wait();
+	auto emit = [&](const uint32_t(&v)[16], uint32_t kc0) {
+#pragma unroll
+		for (uint32_t c = 0; c < 2; ++c) {
+			__half2 h[4];
+#pragma unroll
+			for (uint32_t j = 0; j < 4; ++j) h[j] = relu2(__floats2half2_rn(__uint_as_float(v[c * 8 + 2 * j]), __uint_as_float(v[c * 8 + 2 * j + 1])));
+			store_chunk(buf, row, kc0 + c, h);
+		}
+	};
+	emit(v0, half * 4u + 0);
+	emit(v1, half * 4u + 2);
+}
+
+// forward of one MLP keeping every hidden activation: layer l writes hidden buffer l.  Returns the 16 outputs of the row.
 __device__ __forceinline__ void run_mlp_fwd_keep(
 	uint8_t* smem, uint32_t in_off, uint32_t hid_off, uint32_t w_off, uint32_t n_hidden, uint32_t tmem_base, uint64_t* bar, uint32_t& phase,
 	uint32_t tid, __half2 (&out)[8]
 ) {
 	const uint32_t smem_base = umma::smem_u32(smem);
-	const uint32_t lane_taddr = tmem_base + ((tid & ~31u) << 16);
+	const uint32_t row = tid & (TILE - 1), half = tid >> 7;
+	const uint32_t lane_taddr = tmem_base + ((row & ~31u) << 16);
 	for (uint32_t l = 0; l <= n_hidden; ++l) {
 		const uint32_t K = mlp_layer_in(n_hidden, l), N = mlp_layer_out(n_hidden, l);
 		const uint32_t a_off = (l == 0) ? in_off : hid_off + (l - 1) * TILE * MLP_WIDTH * 2u;
@@ -205,7 +233,7 @@ __device__ __forceinline__ void run_mlp_fwd_keep(
 		phase ^= 1u;
 		umma::fence_after_sync();
 		if (l < n_hidden) {
-			tmem_row_to_smem64<true>(lane_taddr, smem + hid_off + l * TILE * MLP_WIDTH * 2u, tid);
+			tmem_row_to_smem32_relu(lane_taddr, half, smem + hid_off + l * TILE * MLP_WIDTH * 2u, row);
 		} else {
 			tmem_row_to_regs16(lane_taddr, out);
 		}
@@ -213,35 +241,30 @@ __device__ __forceinline__ void run_mlp_fwd_keep(
 }
 
 // backward of one MLP.  On entry g16 holds dL/d(output) [128 x 16].  For every layer, weight gradient and data
-// gradient are issued back to back and waited for together.  Returns this thread's row of dL/d(mlp input) (32 fp32).
+// gradient are issued back to back and waited for together.  Returns this thread's 16 columns [16*half, 16*half+16) of
+// dL/d(mlp input) (the MLP input is 32 wide).
 __device__ __forceinline__ void run_mlp_bwd(
 	uint8_t* smem, uint32_t in_off, uint32_t hid_off, uint32_t g64_off, uint32_t g16_off, uint32_t w_off, uint32_t n_hidden, uint32_t tmem_base,
-	uint32_t wg_col0, uint32_t wg_accumulate, uint64_t* bar, uint32_t& phase, uint32_t tid, float (&dx)[32]
+	uint32_t wg_col0, uint32_t wg_accumulate, uint64_t* bar, uint32_t& phase, uint32_t tid, float (&dx)[16]
 ) {
 	const uint32_t smem_base = umma::smem_u32(smem);
-	const uint32_t lane_taddr = tmem_base + ((tid & ~31u) << 16);
-	// column base of each layer's weight-gradient accumulator
-	uint32_t wg_col[MAX_HIDDEN + 1];
-	{
-		uint32_t c = wg_col0;
-		for (uint32_t l = 0; l <= n_hidden; ++l) {
-			wg_col[l] = c;
-			c += wgrad_cols(n_hidden, l);
-		}
-	}
+	const uint32_t row = tid & (TILE - 1), half = tid >> 7;
+	const uint32_t lane_taddr = tmem_base + ((row & ~31u) << 16);
 	for (int32_t l = (int32_t)n_hidden; l >= 0; --l) {
 		const uint32_t K = mlp_layer_in(n_hidden, l), N = mlp_layer_out(n_hidden, l);
 		const uint32_t x_off = (l == 0) ? in_off : hid_off + (l - 1) * TILE * MLP_WIDTH * 2u;
 		const uint32_t dy_off = ((uint32_t)l == n_hidden) ? g16_off : g64_off;
+		uint32_t wg_col = wg_col0;
+		for (int32_t i = 0; i < l; ++i) wg_col += wgrad_cols(n_hidden, (uint32_t)i);
 		umma::fence_smem_to_async();
 		umma::fence_before_sync();
 		__syncthreads();
 		if (tid == 0) {
 			umma::fence_after_sync();
 			if ((uint32_t)l == n_hidden) {
-				issue_wgrad(smem_base + x_off, MLP_WIDTH, smem_base + dy_off, MLP_OUT, tmem_base + wg_col[l], wg_accumulate);  // dW^T [in x out]
+				issue_wgrad(smem_base + x_off, MLP_WIDTH, smem_base + dy_off, MLP_OUT, tmem_base + wg_col, wg_accumulate);  // dW^T [in x out]
 			} else {
-				issue_wgrad(smem_base + dy_off, MLP_WIDTH, smem_base + x_off, K, tmem_base + wg_col[l], wg_accumulate);  // dW [out x in]
+				issue_wgrad(smem_base + dy_off, MLP_WIDTH, smem_base + x_off, K, tmem_base + wg_col, wg_accumulate);  // dW [out x in]
 			}
 			issue_layer_dgrad(smem_base + dy_off, N, smem_base + w_off + mlp_layer_off(n_hidden, l) * 2u, K, tmem_base, bar);
 		}
@@ -249,19 +272,17 @@ __device__ __forceinline__ void run_mlp_bwd(
 		phase ^= 1u;
 		umma::fence_after_sync();
 		if (l > 0) {
-			// dL/d(hidden l-1 pre-activation) = dX * (hidden_{l-1} > 0)  -> g64
-			uint32_t v0[16], v1[16], v2[16], v3[16];
-			umma::tmem_ld16(lane_taddr + 0, v0);
-			umma::tmem_ld16(lane_taddr + 16, v1);
-			umma::tmem_ld16(lane_taddr + 32, v2);
-			umma::tmem_ld16(lane_taddr + 48, v3);
+			// dL/d(hidden l-1 pre-activation) = dX * (hidden_{l-1} > 0)  -> g64, this thread's 32 columns
+			uint32_t v0[16], v1[16];
+			umma::tmem_ld16(lane_taddr + half * 32u + 0, v0);
+			umma::tmem_ld16(lane_taddr + half * 32u + 16, v1);
 			umma::tmem_ld_wait();
 			const uint8_t* act = smem + x_off;
 			uint8_t* g = smem + g64_off;
 			auto emit = [&](const uint32_t(&v)[16], uint32_t kc0) {
 #pragma unroll
 				for (uint32_t c = 0; c < 2; ++c) {
-					const uint4 a = *reinterpret_cast<const uint4*>(act + (kc0 + c) * (TILE * 16u) + tid * 16u);
+					const uint4 a = *reinterpret_cast<const uint4*>(act + (kc0 + c) * (TILE * 16u) + row * 16u);
 					const __half2 ah[4] = {*reinterpret_cast<const __half2*>(&a.x), *reinterpret_cast<const __half2*>(&a.y),
 						*reinterpret_cast<const __half2*>(&a.z), *reinterpret_cast<const __half2*>(&a.w)};
 					__half2 h[4];
@@ -271,35 +292,76 @@ __device__ __forceinline__ void run_mlp_bwd(
 						const __half2 m = __hgt2(ah[j], __float2half2_rn(0.0f));  // 1.0 where act > 0
 						h[j] = __hmul2(t, m);
 					}
-					store_chunk(g, tid, kc0 + c, h);
+					store_chunk(g, row, kc0 + c, h);
 				}
 			};
-			emit(v0, 0);
-			emit(v1, 2);
-			emit(v2, 4);
-			emit(v3, 6);
+			emit(v0, half * 4u + 0);
+			emit(v1, half * 4u + 2);
 		} else {
-			uint32_t v0[16], v1[16];
-			umma::tmem_ld16(lane_taddr + 0, v0);
-			umma::tmem_ld16(lane_taddr + 16, v1);
+			uint32_t v0[16];
+			umma::tmem_ld16(lane_taddr + half * 16u, v0);
 			umma::tmem_ld_wait();
 #pragma unroll
-			for (uint32_t j = 0; j < 16; ++j) {
-				dx[j] = __uint_as_float(v0[j]);
-				dx[16 + j] = __uint_as_float(v1[j]);
-			}
+			for (uint32_t j = 0; j < 16; ++j) dx[j] = __uint_as_float(v0[j]);
 		}
 	}
 }
 
-// scatter dL/d(encoding) of one sample into the fp16 gradient table (≙ kernel_grid_backward, grid.h:214-320).
+// gather of HALF of the levels of one sample: 16 encoded features (8 half2) = chunks {2*half, 2*half+1} of the A0 row
 template <uint32_t F>
-__device__ __forceinline__ void grid_scatter(const NetDev& net, __half* __restrict__ grid_grad, float x, float y, float z, const __half2 (&g)[16]) {
+__device__ __forceinline__ void grid_gather_half(const NetDev& net, const __half* __restrict__ grid, uint32_t half, float x, float y, float z, __half2 (&enc)[8]) {
 	constexpr uint32_t H2_PER_LEVEL = F / 2;
-	const uint32_t n_levels = ENC_WIDTH / F;
+	constexpr uint32_t LEVELS_PER_HALF = (ENC_WIDTH / F) / 2;
+#pragma unroll
+	for (uint32_t ll = 0; ll < LEVELS_PER_HALF; ++ll) {
+		const LevelMeta lv = net.levels[half * LEVELS_PER_HALF + ll];
+		const float px = fmaf(lv.scale, x, 0.5f), py = fmaf(lv.scale, y, 0.5f), pz = fmaf(lv.scale, z, 0.5f);
+		const float fx = floorf(px), fy = floorf(py), fz = floorf(pz);
+		const uint32_t gx = (uint32_t)(int)fx, gy = (uint32_t)(int)fy, gz = (uint32_t)(int)fz;
+		const float wx1 = px - fx, wy1 = py - fy, wz1 = pz - fz;
+		const float wx0 = 1.0f - wx1, wy0 = 1.0f - wy1, wz0 = 1.0f - wz1;
+		const __half* lgrid = grid + (size_t)lv.offset * F;
+		uint32_t idx[8];
+#pragma unroll
+		for (uint32_t c = 0; c < 8; ++c) idx[c] = grid_index_3d(gx + (c & 1u), gy + ((c >> 1) & 1u), gz + ((c >> 2) & 1u), lv.resolution, lv.size, lv.dense != 0);
+		if constexpr (F == 2) {
+			__half2 v[8];
+#pragma unroll
+			for (uint32_t c = 0; c < 8; ++c) v[c] = __ldg(reinterpret_cast<const __half2*>(lgrid) + idx[c]);
+			__half2 acc = __float2half2_rn(0.0f);
+#pragma unroll
+			for (uint32_t c = 0; c < 8; ++c) {
+				const float w = ((c & 1u) ? wx1 : wx0) * ((c & 2u) ? wy1 : wy0) * ((c & 4u) ? wz1 : wz0);
+				acc = __hfma2(__float2half2_rn(w), v[c], acc);
+			}
+			enc[ll] = acc;
+		} else {
+			uint2 v[8];
+#pragma unroll
+			for (uint32_t c = 0; c < 8; ++c) v[c] = __ldg(reinterpret_cast<const uint2*>(lgrid) + idx[c]);
+			__half2 a0 = __float2half2_rn(0.0f), a1 = a0;
+#pragma unroll
+			for (uint32_t c = 0; c < 8; ++c) {
+				const float w = ((c & 1u) ? wx1 : wx0) * ((c & 2u) ? wy1 : wy0) * ((c & 4u) ? wz1 : wz0);
+				const __half2 wh = __float2half2_rn(w);
+				a0 = __hfma2(wh, *reinterpret_cast<const __half2*>(&v[c].x), a0);
+				a1 = __hfma2(wh, *reinterpret_cast<const __half2*>(&v[c].y), a1);
+			}
+			enc[ll * H2_PER_LEVEL + 0] = a0;
+			enc[ll * H2_PER_LEVEL + 1] = a1;
+		}
+	}
+}
+
+// scatter dL/d(encoding) of HALF of the levels of one sample into the fp16 gradient table
+// (≙ kernel_grid_backward, grid.h:214-320: fp16 weight x fp16 gradient, red.global.add.f16x2 per corner).
+template <uint32_t F>
+__device__ __forceinline__ void grid_scatter_half(const NetDev& net, __half* __restrict__ grid_grad, uint32_t half, float x, float y, float z, const __half2 (&g)[8]) {
+	constexpr uint32_t H2_PER_LEVEL = F / 2;
+	constexpr uint32_t LEVELS_PER_HALF = (ENC_WIDTH / F) / 2;
 #pragma unroll 2
-	for (uint32_t l = 0; l < n_levels; ++l) {
-		const LevelMeta lv = net.levels[l];
+	for (uint32_t ll = 0; ll < LEVELS_PER_HALF; ++ll) {
+		const LevelMeta lv = net.levels[half * LEVELS_PER_HALF + ll];
 		const float px = fmaf(lv.scale, x, 0.5f), py = fmaf(lv.scale, y, 0.5f), pz = fmaf(lv.scale, z, 0.5f);
 		const float fx = floorf(px), fy = floorf(py), fz = floorf(pz);
 		const uint32_t gx = (uint32_t)(int)fx, gy = (uint32_t)(int)fy, gz = (uint32_t)(int)fz;
@@ -308,20 +370,17 @@ __device__ __forceinline__ void grid_scatter(const NetDev& net, __half* __restri
 		__half2* lgrad = reinterpret_cast<__half2*>(grid_grad + (size_t)lv.offset * F);
 #pragma unroll
 		for (uint32_t c = 0; c < 8; ++c) {
-			const uint32_t cx = gx + (c & 1u), cy = gy + ((c >> 1) & 1u), cz = gz + ((c >> 2) & 1u);
-			const uint32_t idx = grid_index_3d(cx, cy, cz, lv.resolution, lv.size, lv.dense != 0);
+			const uint32_t idx = grid_index_3d(gx + (c & 1u), gy + ((c >> 1) & 1u), gz + ((c >> 2) & 1u), lv.resolution, lv.size, lv.dense != 0);
 			const float w = ((c & 1u) ? wx1 : wx0) * ((c & 2u) ? wy1 : wy0) * ((c & 4u) ? wz1 : wz0);
 			const __half2 wh = __float2half2_rn(w);
 #pragma unroll
-			for (uint32_t h = 0; h < H2_PER_LEVEL; ++h) {
-				atomicAdd(lgrad + (size_t)idx * H2_PER_LEVEL + h, __hmul2(wh, g[l * H2_PER_LEVEL + h]));
-			}
+			for (uint32_t h = 0; h < H2_PER_LEVEL; ++h) atomicAdd(lgrad + (size_t)idx * H2_PER_LEVEL + h, __hmul2(wh, g[ll * H2_PER_LEVEL + h]));
 		}
 	}
 }
 
 template <uint32_t F, uint32_t TMEM_COLS>
-__global__ void __launch_bounds__(TILE, 2) k_nerf_train(
+__global__ void __launch_bounds__(TRAIN_THREADS, 2) k_nerf_train(
 	const __grid_constant__ NetDev net, const uint32_t n, const float* __restrict__ coords, const __half* __restrict__ params,
 	const __half* __restrict__ dL_dout, __half* __restrict__ grads, float* __restrict__ mlp_grads_f32, __half* __restrict__ out
 ) {
@@ -329,14 +388,15 @@ __global__ void __launch_bounds__(TILE, 2) k_nerf_train(
 	const uint32_t nhd = net.n_hidden_density, nhr = net.n_hidden_rgb;
 	const TrainSmem L = train_smem_layout(nhd, nhr);
 	const uint32_t tid = threadIdx.x;
+	const uint32_t row = tid & (TILE - 1), half = tid >> 7;
 	uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L.bar_off);
 	uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L.bar_off + 8);
 	const uint32_t wr_off = mlp_n_params(nhd) * 2u;
 
 	for (uint32_t l = 0; l <= nhd; ++l)
-		stage_weights(params + net.density_off + mlp_layer_off(nhd, l), mlp_layer_out(nhd, l), mlp_layer_in(nhd, l), smem + mlp_layer_off(nhd, l) * 2u, tid, TILE);
+		stage_weights(params + net.density_off + mlp_layer_off(nhd, l), mlp_layer_out(nhd, l), mlp_layer_in(nhd, l), smem + mlp_layer_off(nhd, l) * 2u, tid, TRAIN_THREADS);
 	for (uint32_t l = 0; l <= nhr; ++l)
-		stage_weights(params + net.rgb_off + mlp_layer_off(nhr, l), mlp_layer_out(nhr, l), mlp_layer_in(nhr, l), smem + wr_off + mlp_layer_off(nhr, l) * 2u, tid, TILE);
+		stage_weights(params + net.rgb_off + mlp_layer_off(nhr, l), mlp_layer_out(nhr, l), mlp_layer_in(nhr, l), smem + wr_off + mlp_layer_off(nhr, l) * 2u, tid, TRAIN_THREADS);
 	if (tid < 32) umma::tmem_alloc<TMEM_COLS>(tmem_slot);
 	if (tid == 0) {
 		umma::mbar_init(bar, 1);
@@ -353,35 +413,34 @@ __global__ void __launch_bounds__(TILE, 2) k_nerf_train(
 	const uint32_t n_tiles = n / TILE;
 	uint32_t iter = 0;
 	for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++iter) {
-		const uint32_t i = tile * TILE + tid;
+		const uint32_t i = tile * TILE + row;
 		const float* c = coords + (size_t)i * 7;
 		const float x = c[0], y = c[1], z = c[2];
 		{
-			__half2 enc[16];
-			grid_gather<F>(net, grid, x, y, z, enc);
-#pragma unroll
-			for (uint32_t kc = 0; kc < 4; ++kc) {
-				const __half2 h[4] = {enc[kc * 4 + 0], enc[kc * 4 + 1], enc[kc * 4 + 2], enc[kc * 4 + 3]};
-				store_chunk(smem + L.a0_off, tid, kc, h);
+			__half2 enc[8];
+			grid_gather_half<F>(net, grid, half, x, y, z, enc);
+			const __half2 h0[4] = {enc[0], enc[1], enc[2], enc[3]};
+			const __half2 h1[4] = {enc[4], enc[5], enc[6], enc[7]};
+			store_chunk(smem + L.a0_off, row, 2 * half + 0, h0);
+			store_chunk(smem + L.a0_off, row, 2 * half + 1, h1);
+			if (half == 1) {
+				__half2 sh[8];
+				sh4_encode(c[4], c[5], c[6], sh);
+				const __half2 s0[4] = {sh[0], sh[1], sh[2], sh[3]};
+				const __half2 s1[4] = {sh[4], sh[5], sh[6], sh[7]};
+				store_chunk(smem + L.a2_off, row, 2, s0);
+				store_chunk(smem + L.a2_off, row, 3, s1);
 			}
-			__half2 sh[8];
-			sh4_encode(c[4], c[5], c[6], sh);
-			const __half2 h0[4] = {sh[0], sh[1], sh[2], sh[3]};
-			const __half2 h1[4] = {sh[4], sh[5], sh[6], sh[7]};
-			store_chunk(smem + L.a2_off, tid, 2, h0);
-			store_chunk(smem + L.a2_off, tid, 3, h1);
 		}
 		// ---------------- forward
 		__half2 dens[8], rgb[8];
 		run_mlp_fwd_keep(smem, L.a0_off, L.hd_off, 0, nhd, tmem_base, bar, phase, tid, dens);
 		{
-			const __half2 h0[4] = {dens[0], dens[1], dens[2], dens[3]};
-			const __half2 h1[4] = {dens[4], dens[5], dens[6], dens[7]};
-			store_chunk(smem + L.a2_off, tid, 0, h0);
-			store_chunk(smem + L.a2_off, tid, 1, h1);
+			const __half2 h0[4] = {dens[4 * half + 0], dens[4 * half + 1], dens[4 * half + 2], dens[4 * half + 3]};
+			store_chunk(smem + L.a2_off, row, half, h0);
 		}
 		run_mlp_fwd_keep(smem, L.a2_off, L.hr_off, wr_off, nhr, tmem_base, bar, phase, tid, rgb);
-		if (out) {
+		if (out && half == 0) {
 			uint2 o;
 			o.x = *reinterpret_cast<const uint32_t*>(&rgb[0]);
 			const __half2 t = __halves2half2(__low2half(rgb[1]), __low2half(dens[0]));
@@ -395,45 +454,51 @@ __global__ void __launch_bounds__(TILE, 2) k_nerf_train(
 		const __half2 dl23 = *reinterpret_cast<const __half2*>(&dl.y);  // d rgb2, d density
 		{
 			const __half2 zero = __float2half2_rn(0.0f);
-			const __half2 h0[4] = {dl01, __halves2half2(__low2half(dl23), __float2half_rn(0.0f)), zero, zero};
-			const __half2 h1[4] = {zero, zero, zero, zero};
-			store_chunk(smem + L.g16_off, tid, 0, h0);
-			store_chunk(smem + L.g16_off, tid, 1, h1);
+			if (half == 0) {
+				const __half2 h0[4] = {dl01, __halves2half2(__low2half(dl23), __float2half_rn(0.0f)), zero, zero};
+				store_chunk(smem + L.g16_off, row, 0, h0);
+			} else {
+				const __half2 h1[4] = {zero, zero, zero, zero};
+				store_chunk(smem + L.g16_off, row, 1, h1);
+			}
 		}
-		float dx[32];
+		float dx[16];
 		run_mlp_bwd(smem, L.a2_off, L.hr_off, L.g64_off, L.g16_off, wr_off, nhr, tmem_base, wgrad_col_base(nhd, nhr, true, 0), iter > 0 ? 1u : 0u, bar,
 			phase, tid, dx);
-		{
-			// dL/d(density-net output) = first 16 columns of dL/d(rgb-net input); the density gradient joins column 0 in fp16
-			// (add_density_gradient, nerf_network.h:62-74).
+		if (half == 0) {
+			// dL/d(density-net output) = first 16 columns of dL/d(rgb-net input) (held by half 0); the density gradient joins
+			// column 0 in fp16 (add_density_gradient, nerf_network.h:62-74).  Columns 16..31 (SH inputs) carry no parameters.
 			__half2 h[8];
 #pragma unroll
 			for (uint32_t j = 0; j < 8; ++j) h[j] = __floats2half2_rn(dx[2 * j], dx[2 * j + 1]);
 			h[0] = __halves2half2(__hadd(__low2half(h[0]), __high2half(dl23)), __high2half(h[0]));
 			const __half2 h0[4] = {h[0], h[1], h[2], h[3]};
 			const __half2 h1[4] = {h[4], h[5], h[6], h[7]};
-			store_chunk(smem + L.g16_off, tid, 0, h0);
-			store_chunk(smem + L.g16_off, tid, 1, h1);
+			store_chunk(smem + L.g16_off, row, 0, h0);
+			store_chunk(smem + L.g16_off, row, 1, h1);
 		}
 		run_mlp_bwd(smem, L.a0_off, L.hd_off, L.g64_off, L.g16_off, 0, nhd, tmem_base, wgrad_col_base(nhd, nhr, false, 0), iter > 0 ? 1u : 0u, bar, phase,
 			tid, dx);
 		{
-			__half2 g[16];
+			// this thread's 16 columns of dL/d(encoding) are exactly the features of its own levels
+			__half2 g[8];
 #pragma unroll
-			for (uint32_t j = 0; j < 16; ++j) g[j] = __floats2half2_rn(dx[2 * j], dx[2 * j + 1]);
-			grid_scatter<F>(net, grid_grad, x, y, z, g);
+			for (uint32_t j = 0; j < 8; ++j) g[j] = __floats2half2_rn(dx[2 * j], dx[2 * j + 1]);
+			grid_scatter_half<F>(net, grid_grad, half, x, y, z, g);
 		}
 	}
 
 	// ---------------- flush the weight-gradient accumulators (M = 64 accumulator layout: row m sits in TMEM lane
-	// (m % 16) + 32 * (m / 16), i.e. the low 16 lanes of each warp's 32-lane window)
+	// (m % 16) + 32 * (m / 16), i.e. the low 16 lanes of each warp's 32-lane window); the two halves take alternate
+	// 16-column groups
 	umma::fence_before_sync();
 	__syncthreads();
 	umma::fence_after_sync();
 	if (iter > 0) {
-		const uint32_t warp = tid >> 5, lane = tid & 31u;
-		const uint32_t row = warp * 16u + lane;  // valid for lane < 16
-		const uint32_t lane_taddr = tmem_base + ((tid & ~31u) << 16);
+		const uint32_t warp4 = (tid >> 5) & 3u, lane = tid & 31u;
+		const uint32_t wrow = warp4 * 16u + lane;  // valid for lane < 16
+		const uint32_t lane_taddr = tmem_base + ((row & ~31u) << 16);
+		uint32_t group = 0;
 		for (uint32_t net_i = 0; net_i < 2; ++net_i) {
 			const uint32_t nh = net_i ? nhr : nhd;
 			const uint32_t goff = net_i ? net.rgb_off : net.density_off;
@@ -442,7 +507,8 @@ __global__ void __launch_bounds__(TILE, 2) k_nerf_train(
 				const uint32_t cbase = wgrad_col_base(nhd, nhr, net_i != 0, l);
 				const uint32_t K = mlp_layer_in(nh, l);
 				float* dst = mlp_grads_f32 + goff + mlp_layer_off(nh, l);
-				for (uint32_t c0 = 0; c0 < cols; c0 += 16) {
+				for (uint32_t c0 = 0; c0 < cols; c0 += 16, ++group) {
+					if ((group & 1u) != half) continue;  // warp-uniform
 					uint32_t v[16];
 					umma::tmem_ld16(lane_taddr + cbase + c0, v);
 					umma::tmem_ld_wait();
@@ -451,7 +517,7 @@ __global__ void __launch_bounds__(TILE, 2) k_nerf_train(
 						for (uint32_t j = 0; j < 16; ++j) {
 							const uint32_t col = c0 + j;
 							// hidden layer: accumulator = dW[out=row][in=col]; output layer: accumulator = dW^T[in=row][out=col]
-							const uint32_t idx = (l == nh) ? (col * MLP_WIDTH + row) : (row * K + col);
+							const uint32_t idx = (l == nh) ? (col * MLP_WIDTH + wrow) : (wrow * K + col);
 							atomicAdd(dst + idx, __uint_as_float(v[j]));
 						}
 					}
@@ -602,7 +668,7 @@ static void launch_train(const NetDev& net, cudaStream_t stream, uint32_t n, con
 	if (per_sm < 1) per_sm = 1;
 	const uint32_t max_ctas = (uint32_t)device_sm_count() * per_sm;
 	const uint32_t grid = n_tiles < max_ctas ? n_tiles : max_ctas;
-	kern<<<grid, TILE, L.total, stream>>>(net, n, coords, params, dL_dout, grads, mlp_grads_f32, out);
+	kern<<<grid, TRAIN_THREADS, L.total, stream>>>(net, n, coords, params, dL_dout, grads, mlp_grads_f32, out);
 	NGPB_LAUNCHED();
 	NGPB_CUDA_CHECK(cudaGetLastError());
 }

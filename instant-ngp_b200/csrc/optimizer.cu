@@ -12,13 +12,15 @@ namespace ngpb {
 
 struct AdamDev {
 	float lr, beta1, beta2, epsilon, l2_reg, inv_loss_scale;
+	float log2_beta1, log2_beta2;
 	float ema_decay, ema_debias_old, ema_debias_new;
 	uint32_t n_matrix, n_total;
 	uint32_t optimize_matrix, optimize_non_matrix;
 };
 
-// integer power by repeated multiplication would differ from powf; Adam's bias correction uses powf(beta, step)
-// (adam.h:111-113).  powf is evaluated with the CUDA libm (not fast-math) here; tests compare with a 1e-6 tolerance.
+// Adam's bias correction uses powf(beta, step) with a per-parameter step (adam.h:111-113).  beta^step is evaluated as
+// exp2(step * log2(beta)) with the hardware ex2 unit (2 ulp): the libm powf costs ~100 instructions per parameter and made
+// this HBM-streaming kernel instruction-bound (ncu: 17 % DRAM throughput, profiles/r1_kernels.md).
 __device__ __forceinline__ void adam_one(const AdamDev& a, uint32_t i, float g_scaled, float* __restrict__ w32, __half* __restrict__ w16,
 	float* __restrict__ m1, float* __restrict__ m2, uint32_t* __restrict__ steps) {
 	float gradient = g_scaled * a.inv_loss_scale;
@@ -29,7 +31,8 @@ __device__ __forceinline__ void adam_one(const AdamDev& a, uint32_t i, float g_s
 	m1[i] = m;
 	m2[i] = v;
 	const uint32_t step = ++steps[i];
-	const float lr = a.lr * sqrtf(1.0f - powf(a.beta2, (float)step)) / (1.0f - powf(a.beta1, (float)step));
+	const float fs = (float)step;
+	const float lr = a.lr * sqrtf(1.0f - exp2f(fs * a.log2_beta2)) / (1.0f - exp2f(fs * a.log2_beta1));
 	const float eff = fminf(fmaxf(lr / (sqrtf(v) + a.epsilon), 0.0f), 3.402823466e+38f);
 	const float nw = w - eff * m;
 	w32[i] = nw;
@@ -101,6 +104,8 @@ void optimizer_step(const ngp_nerf_desc& d, cudaStream_t stream, const ngp_adam_
 	a.epsilon = cfg.epsilon;
 	a.l2_reg = cfg.l2_reg;
 	a.inv_loss_scale = 1.0f / cfg.loss_scale;
+	a.log2_beta1 = std::log2(cfg.beta1);
+	a.log2_beta2 = std::log2(cfg.beta2);
 	a.ema_decay = cfg.ema_decay;
 	a.ema_debias_old = 1.0f - (float)std::pow(cfg.ema_decay, (float)(cfg.ema_step - 1));
 	a.ema_debias_new = 1.0f / (1.0f - (float)std::pow(cfg.ema_decay, (float)cfg.ema_step));
