@@ -154,6 +154,14 @@ int ngp_nerf_init_params_host(const ngp_nerf_desc* d, uint64_t seed, float* para
 int ngp_nerf_inference(const ngp_nerf_desc* d, void* stream, uint32_t n, const float* coords, const void* params_fp16,
 	void* out_fp16, uint32_t out_stride);
 
+/* The same network evaluation restricted to what compute_loss_kernel_train_nerf will read: rays are taken from
+ * numsteps[2*r] = (count, base) for r < counters->n_rays, their samples evaluated in order, 8 at a time, until the ray is
+ * exhausted or its transmittance drops below 1e-4 (testbed_nerf.cu:926-929).  out rows that are evaluated are bit-identical
+ * to ngp_nerf_inference(out_stride = 4); rows that the loss kernel never reads are left untouched.
+ * queue: a zeroed device uint32 (work-queue head).  n_rays_max bounds the launch (>= counters->n_rays). */
+int ngp_nerf_inference_rays(const ngp_nerf_desc* d, void* stream, uint32_t n_rays_max, const ngp_nerf_counters* counters_dev, uint32_t* queue_dev,
+	const uint32_t* numsteps, const float* coords, const void* params_fp16, uint32_t density_activation, void* out_fp16);
+
 /* ≙ NerfNetwork::density (nerf_network.h:270-280): hash grid + density MLP only. positions: n x pos_stride floats
  * (NerfPosition, pos_stride >= 3), out: n halves (raw density). */
 int ngp_nerf_density(const ngp_nerf_desc* d, void* stream, uint32_t n, const float* positions, uint32_t pos_stride,

@@ -373,8 +373,17 @@ __device__ __forceinline__ void grid_scatter_half(const NetDev& net, __half* __r
 			const uint32_t idx = grid_index_3d(gx + (c & 1u), gy + ((c >> 1) & 1u), gz + ((c >> 2) & 1u), lv.resolution, lv.size, lv.dense != 0);
 			const float w = ((c & 1u) ? wx1 : wx0) * ((c & 2u) ? wy1 : wy0) * ((c & 4u) ? wz1 : wz0);
 			const __half2 wh = __float2half2_rn(w);
-#pragma unroll
-			for (uint32_t h = 0; h < H2_PER_LEVEL; ++h) atomicAdd(lgrad + (size_t)idx * H2_PER_LEVEL + h, __hmul2(wh, g[ll * H2_PER_LEVEL + h]));
+			// fire-and-forget reductions.  NOT atomicAdd(__half2*): on a generic pointer that compiles to ATOM + predicate + retry
+			// branch (a full L2 round trip per corner, serialised per thread: 59 % of all stall samples, profiles/r1_kernels.md).
+			if constexpr (F == 2) {
+				const __half2 v = __hmul2(wh, g[ll]);
+				asm volatile("red.relaxed.gpu.global.add.noftz.f16x2 [%0], %1;" ::"l"(lgrad + idx), "r"(*reinterpret_cast<const uint32_t*>(&v)) : "memory");
+			} else {
+				const __half2 v0 = __hmul2(wh, g[ll * 2 + 0]), v1 = __hmul2(wh, g[ll * 2 + 1]);
+				asm volatile("red.relaxed.gpu.global.add.noftz.v2.f16x2 [%0], {%1, %2};" ::"l"(lgrad + (size_t)idx * 2), "r"(*reinterpret_cast<const uint32_t*>(&v0)),
+							 "r"(*reinterpret_cast<const uint32_t*>(&v1))
+							 : "memory");
+			}
 		}
 	}
 }

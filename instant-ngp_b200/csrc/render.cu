@@ -249,6 +249,180 @@ __global__ void __launch_bounds__(TILE, 3) k_render_nerf(
 	if (tid < 32) umma::tmem_dealloc<64>(tmem_base);
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// k_nerf_forward_rays — the training-time inference pass, evaluated ray by ray with early termination.
+//
+// The reference evaluates the network on EVERY generated sample (m_network->inference_mixed_precision over max_inference
+// samples, testbed_nerf.cu:3233-3235) and only then composites; compute_loss_kernel_train_nerf stops reading a ray's samples
+// at the first one where the transmittance has dropped below 1e-4 (:926-929), so on a trained scene ~90 % of the evaluated
+// samples are never looked at (measured here: 3.0 M evaluated for 0.26 M used per step).  This kernel produces exactly the
+// network outputs the loss kernel will read and nothing else: a CTA holds 16 ray slots x 8 consecutive samples = one
+// 128-row tensor-core tile; after each tile the 8 lanes of a slot advance the ray's transmittance with the loss kernel's own
+// arithmetic (same expression order, ngp_expf, no FMA contraction) and a slot whose ray is exhausted or has T < 1e-4 pulls the
+// next ray from a device-side queue.  Outputs for the samples the loss kernel reads are bit-identical to the all-samples pass.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr uint32_t RAY_CHUNK = 8;
+
+template <uint32_t F>
+__global__ void __launch_bounds__(TILE, 3) k_nerf_forward_rays(
+	const __grid_constant__ NetDev net, const ngp_nerf_counters* __restrict__ counters, uint32_t* __restrict__ queue, const uint32_t* __restrict__ numsteps,
+	const float* __restrict__ coords, const __half* __restrict__ params, const uint32_t density_activation, __half* __restrict__ out
+) {
+	extern __shared__ __align__(128) uint8_t smem[];
+	const FwdSmem L = fwd_smem_layout(net.n_hidden_density, net.n_hidden_rgb);
+	const uint32_t tid = threadIdx.x, lane = tid & 31u;
+	const uint32_t sub = lane & (RAY_CHUNK - 1), group_lane0 = lane & ~(RAY_CHUNK - 1);
+	uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L.bar_off);
+	uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L.bar_off + 8);
+	const uint32_t wr_off = mlp_n_params(net.n_hidden_density) * 2u;
+	const uint32_t n_rays = counters->n_rays;
+	if (blockIdx.x * (TILE / RAY_CHUNK) >= n_rays) return;
+
+	for (uint32_t l = 0; l <= net.n_hidden_density; ++l)
+		stage_weights(params + net.density_off + mlp_layer_off(net.n_hidden_density, l), mlp_layer_out(net.n_hidden_density, l),
+			mlp_layer_in(net.n_hidden_density, l), smem + mlp_layer_off(net.n_hidden_density, l) * 2u, tid, TILE);
+	for (uint32_t l = 0; l <= net.n_hidden_rgb; ++l)
+		stage_weights(params + net.rgb_off + mlp_layer_off(net.n_hidden_rgb, l), mlp_layer_out(net.n_hidden_rgb, l), mlp_layer_in(net.n_hidden_rgb, l),
+			smem + wr_off + mlp_layer_off(net.n_hidden_rgb, l) * 2u, tid, TILE);
+	if (tid < 32) umma::tmem_alloc<64>(tmem_slot);
+	if (tid == 0) {
+		umma::mbar_init(bar, 1);
+		umma::mbar_fence_init();
+	}
+	umma::fence_before_sync();
+	__syncthreads();
+	umma::fence_after_sync();
+	const uint32_t tmem_base = *tmem_slot;
+	uint32_t phase = 0;
+	const __half* grid = params + net.grid_off;
+
+	// slot state, replicated in the 8 lanes of the slot
+	bool have_ray = false, queue_empty = false;
+	uint32_t n = 0, base = 0, k0 = 0;
+	float T = 1.0f;
+	const float EPSILON = 1e-4f;
+
+	for (;;) {
+		// ---- refill: one queue pop per slot (lane `sub == 0` of each slot asks), one atomic per warp
+		const bool want = !have_ray && !queue_empty && sub == 0;
+		const uint32_t want_mask = __ballot_sync(0xFFFFFFFFu, want);
+		if (want_mask) {
+			uint32_t qbase = 0;
+			if (lane == 0) qbase = atomicAdd(queue, __popc(want_mask));
+			qbase = __shfl_sync(0xFFFFFFFFu, qbase, 0);
+			uint32_t r = 0xFFFFFFFFu;
+			if (want) r = qbase + __popc(want_mask & ((1u << lane) - 1u));
+			r = __shfl_sync(0xFFFFFFFFu, r, group_lane0);
+			if (!have_ray && !queue_empty) {
+				if (r >= n_rays) {
+					queue_empty = true;
+				} else {
+					n = numsteps[r * 2 + 0];
+					base = numsteps[r * 2 + 1];
+					k0 = 0;
+					T = 1.0f;
+					have_ray = n > 0;
+				}
+			}
+		}
+		const uint32_t any_ray = __syncthreads_or(have_ray ? 1 : 0);
+		if (!any_ray) {
+			const uint32_t any_pending = __syncthreads_or(queue_empty ? 0 : 1);
+			if (!any_pending) break;
+			continue;
+		}
+
+		// ---- this row's sample
+		const uint32_t k = k0 + sub;
+		const bool valid = have_ray && k < n;
+		float c[7] = {0.5f, 0.5f, 0.5f, 0.0f, 0.5f, 0.5f, 0.5f};
+		if (valid) {
+			const float* cp = coords + (size_t)(base + k) * 7;
+#pragma unroll
+			for (int q = 0; q < 7; ++q) c[q] = cp[q];
+		}
+		{
+			__half2 enc[16];
+			grid_gather<F>(net, grid, c[0], c[1], c[2], enc);
+#pragma unroll
+			for (uint32_t kc = 0; kc < 4; ++kc) {
+				const __half2 h[4] = {enc[kc * 4 + 0], enc[kc * 4 + 1], enc[kc * 4 + 2], enc[kc * 4 + 3]};
+				store_chunk(smem + L.a0_off, tid, kc, h);
+			}
+			__half2 sh[8];
+			sh4_encode(c[4], c[5], c[6], sh);
+			const __half2 h0[4] = {sh[0], sh[1], sh[2], sh[3]};
+			const __half2 h1[4] = {sh[4], sh[5], sh[6], sh[7]};
+			store_chunk(smem + L.a2_off, tid, 2, h0);
+			store_chunk(smem + L.a2_off, tid, 3, h1);
+		}
+		__half2 dens[8], rgbh[8];
+		run_mlp_fwd(smem, L.a0_off, L.h_off, 0, net.n_hidden_density, tmem_base, bar, phase, tid, dens);
+		{
+			const __half2 h0[4] = {dens[0], dens[1], dens[2], dens[3]};
+			const __half2 h1[4] = {dens[4], dens[5], dens[6], dens[7]};
+			store_chunk(smem + L.a2_off, tid, 0, h0);
+			store_chunk(smem + L.a2_off, tid, 1, h1);
+		}
+		run_mlp_fwd(smem, L.a2_off, L.h_off, wr_off, net.n_hidden_rgb, tmem_base, bar, phase, tid, rgbh);
+		float alpha = 0.0f;
+		if (valid) {
+			uint2 o;
+			o.x = *reinterpret_cast<const uint32_t*>(&rgbh[0]);
+			const __half2 t = __halves2half2(__low2half(rgbh[1]), __low2half(dens[0]));
+			o.y = *reinterpret_cast<const uint32_t*>(&t);
+			*reinterpret_cast<uint2*>(out + (size_t)(base + k) * 4) = o;
+			// compute_loss_kernel_train_nerf :931-944 — the density read back from the fp16 output, as the loss kernel will
+			const float density = network_to_density(__half2float(__low2half(dens[0])), density_activation);
+			alpha = 1.0f - ngp_expf(-density * unwarp_dt(c[3]));
+		}
+		// ---- advance the slot's transmittance in sample order (all 8 lanes of the slot compute the same sequence)
+		if (have_ray) {
+			bool done = false;
+			for (uint32_t j = 0; j < RAY_CHUNK; ++j) {
+				const float a = __shfl_sync(0xFFFFFFFFu, alpha, group_lane0 + j);
+				if (done) continue;
+				if (k0 + j >= n) { done = true; continue; }
+				// the loss kernel reads sample k0+j only if T >= EPSILON before it; it was evaluated above either way
+				if (T < EPSILON) { done = true; continue; }
+				T *= (1.0f - a);
+			}
+			k0 += RAY_CHUNK;
+			if (done || k0 >= n || T < EPSILON) have_ray = false;
+		} else {
+#pragma unroll
+			for (uint32_t j = 0; j < RAY_CHUNK; ++j) (void)__shfl_sync(0xFFFFFFFFu, alpha, group_lane0 + j);
+		}
+	}
+	umma::fence_before_sync();
+	__syncthreads();
+	if (tid < 32) umma::tmem_dealloc<64>(tmem_base);
+}
+
+// queue: a zeroed u32 (the `pad` word of the step's counter block).  Grid sized for the worst case (n_rays_max rays).
+void nerf_inference_rays(const ngp_nerf_desc& d, cudaStream_t stream, uint32_t n_rays_max, const ngp_nerf_counters* counters, uint32_t* queue,
+	const uint32_t* numsteps, const float* coords, const __half* params, uint32_t density_activation, __half* out) {
+	if (n_rays_max == 0) return;
+	const NetDev net = make_netdev(d);
+	const FwdSmem L = fwd_smem_layout(net.n_hidden_density, net.n_hidden_rgb);
+	const uint32_t n_tiles = div_round_up(n_rays_max, TILE / RAY_CHUNK);
+	const uint32_t max_ctas = (uint32_t)device_sm_count() * 3u;
+	const uint32_t grid = n_tiles < max_ctas ? n_tiles : max_ctas;
+	if (net.n_features == 2) {
+		auto kern = k_nerf_forward_rays<2>;
+		static bool attr = false;
+		if (!attr) { NGPB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); attr = true; }
+		kern<<<grid, TILE, L.total, stream>>>(net, counters, queue, numsteps, coords, params, density_activation, out);
+	} else {
+		auto kern = k_nerf_forward_rays<4>;
+		static bool attr = false;
+		if (!attr) { NGPB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); attr = true; }
+		kern<<<grid, TILE, L.total, stream>>>(net, counters, queue, numsteps, coords, params, density_activation, out);
+	}
+	NGPB_LAUNCHED();
+	NGPB_CUDA_CHECK(cudaGetLastError());
+}
+
 size_t render_scratch_bytes(int32_t, int32_t) { return 256; }
 
 void render_nerf(const ngp_nerf_desc& d, cudaStream_t stream, const ngp_render_cfg& cfg, int32_t y0, int32_t y1, const __half* params,

@@ -21,6 +21,8 @@ void set_last_error(const std::string& msg) { g_last_error = msg; }
 // kernels' host launchers (nerf_net.cu, march.cu, optimizer.cu, render.cu)
 void nerf_inference(const ngp_nerf_desc& d, cudaStream_t stream, uint32_t n, const float* coords, const __half* params, __half* out, uint32_t out_stride);
 void nerf_inference_counted(const ngp_nerf_desc& d, cudaStream_t stream, uint32_t n_max, const uint32_t* n_dev, const float* coords, const __half* params, __half* out);
+void nerf_inference_rays(const ngp_nerf_desc& d, cudaStream_t stream, uint32_t n_rays_max, const ngp_nerf_counters* counters, uint32_t* queue,
+	const uint32_t* numsteps, const float* coords, const __half* params, uint32_t density_activation, __half* out);
 void nerf_density(const ngp_nerf_desc& d, cudaStream_t stream, uint32_t n, const float* positions, uint32_t pos_stride, const __half* params, __half* out);
 void grid_encode(const ngp_grid_desc& g, cudaStream_t stream, uint32_t n, const float* positions, uint32_t pos_stride, const __half* grid, __half* out);
 void nerf_forward_backward(const ngp_nerf_desc& d, cudaStream_t stream, uint32_t n, const float* coords, const __half* params, const __half* dL_dout,
@@ -218,6 +220,7 @@ struct ngp_testbed {
 	uint32_t optimizer_step = 0;
 	uint64_t seed = 1337;
 	bool train_network = true, train_encoding = true;
+	bool full_inference = false;
 
 	DevBuf<float> params_fp32, m1, m2, mlp_grads_f32;
 	DevBuf<__half> params, params_ema, grads;
@@ -551,7 +554,14 @@ static void tb_compute_grads(ngp_testbed* t, uint32_t batch) {
 	}
 	{
 		PhaseTimer pt(t, 2);
-		nerf_inference_counted(t->desc, t->stream, max_inference, &t->counters.p->n_samples, t->coords.p, t->params.p, t->mlp_out.p);
+		if (t->full_inference) {
+			// the reference's schedule: evaluate every generated sample (testbed_nerf.cu:3233-3235)
+			nerf_inference_counted(t->desc, t->stream, max_inference, &t->counters.p->n_samples, t->coords.p, t->params.p, t->mlp_out.p);
+		} else {
+			// evaluate, ray by ray, only the samples the loss kernel will read (bit-identical outputs for those)
+			nerf_inference_rays(t->desc, t->stream, rays_local, t->counters.p, &t->counters.p->pad, t->numsteps.p, t->coords.p, t->params.p,
+				t->cfg.density_activation, t->mlp_out.p);
+		}
 	}
 	{
 		PhaseTimer pt(t, 3);
@@ -659,6 +669,11 @@ static void require_device() { NGPB_CHECK(ngp_device_count() > 0, "no CUDA devic
 
 int ngp_nerf_inference(const ngp_nerf_desc* d, void* stream, uint32_t n, const float* coords, const void* params, void* out, uint32_t out_stride) {
 	NGPB_TRY(require_device(); nerf_inference(*d, (cudaStream_t)stream, n, coords, (const __half*)params, (__half*)out, out_stride));
+}
+int ngp_nerf_inference_rays(const ngp_nerf_desc* d, void* stream, uint32_t n_rays_max, const ngp_nerf_counters* counters, uint32_t* queue, const uint32_t* numsteps,
+	const float* coords, const void* params, uint32_t density_activation, void* out) {
+	NGPB_TRY(require_device(); nerf_inference_rays(*d, (cudaStream_t)stream, n_rays_max, counters, queue, numsteps, coords, (const __half*)params, density_activation,
+		(__half*)out));
 }
 int ngp_nerf_density(const ngp_nerf_desc* d, void* stream, uint32_t n, const float* positions, uint32_t pos_stride, const void* params, void* out) {
 	NGPB_TRY(require_device(); nerf_density(*d, (cudaStream_t)stream, n, positions, pos_stride, (const __half*)params, (__half*)out));
@@ -872,6 +887,7 @@ int ngp_testbed_set_option(ngp_testbed* t, const char* name_c, double value) {
 		else if (n == "background_color.r") c.background_color[0] = (float)value;
 		else if (n == "background_color.g") c.background_color[1] = (float)value;
 		else if (n == "background_color.b") c.background_color[2] = (float)value;
+		else if (n == "nerf.training.full_inference") t->full_inference = value != 0;
 		else if (n == "train_network") t->train_network = value != 0;
 		else if (n == "train_encoding") t->train_encoding = value != 0;
 		else if (n == "shall_train") t->shall_train = value != 0;

@@ -265,3 +265,50 @@ def test_density_grid_update_matches_oracle(lib, aabb_scale):
     assert (grid_w > 0).sum() > 0
     if aabb_scale > 1:
         assert (grid_w < 0).sum() > 0  # voxels no camera sees were culled at step 0
+
+
+@pytest.mark.parametrize("scene", SCENES[:2])
+def test_ray_ordered_inference_equals_full_inference_where_the_loss_reads(lib, scene):
+    """the early-terminating inference pass (k_nerf_forward_rays) writes, for every ray, exactly the rows the loss kernel
+    consumes, bit-identical to the evaluate-everything pass of the reference schedule"""
+    import torch
+
+    n_rays, max_samples = 4096, 4096 * 1024
+    want, got, ctx = run_generator(lib, scene, n_rays, max_samples)
+    cfg = ctx["cfg"]
+    k, ns = got["n_kept"], got["n_samples"]
+    d, L = util.make_desc(n_levels=16, F=2, log2_T=16, aabb_scale=scene["aabb_scale"])
+    rng = np.random.default_rng(77)
+    params = util.random_params(L, seed=41, trained_like=True)
+    # bias the density head so that rays saturate after a varying, finite number of samples
+    dens_out_off = 64 * 32
+    params[dens_out_off:dens_out_off + 64] = np.abs(params[dens_out_off:dens_out_off + 64]) * 3.0
+    params = params.astype(np.float16)
+    t_p = dev(params)
+    dv = ctx["dev"]
+    full = torch.zeros(ns, 4, dtype=torch.float16, device="cuda")
+    assert lib.ngp_nerf_inference(C.byref(d), stream(), ns, dv["co"].data_ptr(), t_p.data_ptr(), full.data_ptr(), 4) == 0, lib.ngp_last_error()
+    rays_out = torch.full((ns, 4), float("nan"), dtype=torch.float16, device="cuda")
+    queue = torch.zeros(1, dtype=torch.int32, device="cuda")
+    assert lib.ngp_nerf_inference_rays(C.byref(d), stream(), n_rays, dv["cnt"].data_ptr(), queue.data_ptr(), dv["ns"].data_ptr(), dv["co"].data_ptr(), t_p.data_ptr(),
+                                       cfg.density_activation, rays_out.data_ptr()) == 0, lib.ngp_last_error()
+    # run the loss kernel on the FULL outputs to learn what it consumes
+    batch = 1 << int(np.ceil(np.log2(max(ns, 2))))
+    t_coc = torch.zeros(batch, 7, dtype=torch.float32, device="cuda")
+    t_dl = torch.zeros(batch, 4, dtype=torch.float16, device="cuda")
+    t_md = dev(np.array([0.02], dtype=np.float32))
+    ns_before = dv["ns"].cpu().numpy().view(np.uint32)[:k].copy()
+    assert lib.ngp_nerf_compute_loss(stream(), n_rays, n_rays, ctx["rng"][0], ctx["rng"][1], C.byref(cfg), ctx["t_views"].data_ptr(), len(ctx["views"]), full.data_ptr(), batch,
+                                     dv["cnt"].data_ptr(), dv["ri"].data_ptr(), dv["rays"].data_ptr(), dv["ns"].data_ptr(), dv["co"].data_ptr(), t_coc.data_ptr(),
+                                     t_dl.data_ptr(), None, t_md.data_ptr()) == 0, lib.ngp_last_error()
+    torch.cuda.synchronize()
+    consumed = dv["ns"].cpu().numpy().view(np.uint32)[:k, 0]
+    full_h, rays_h = full.cpu().numpy().view(np.uint16), rays_out.cpu().numpy().view(np.uint16)
+    n_eval = int((~np.isnan(rays_out.float().cpu().numpy()[:, 0])).sum())
+    assert consumed.sum() > 0 and (consumed < ns_before[:, 0]).any(), "scene does not exercise early termination"
+    for i in range(k):
+        b, c = int(ns_before[i, 1]), int(consumed[i])
+        assert np.array_equal(rays_h[b:b + c], full_h[b:b + c]), f"ray slot {i}"
+    # and it evaluates far fewer samples than the full pass: at most one 8-sample chunk beyond what is consumed
+    assert n_eval <= consumed.sum() + 8 * k
+    print("evaluated", n_eval, "of", ns, "consumed", int(consumed.sum()))
