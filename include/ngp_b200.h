@@ -84,6 +84,8 @@ typedef struct ngp_train_view {
 	uint32_t lens_mode;
 	float lens_params[4]; /* k1 k2 p1 p2 */
 	float xform[12];
+	uint32_t no_mask; /* 1: the image is known to contain no masked-away pixels (negative red / 0x00FF00FF), so the sample
+	                     generator need not read it; 0: unknown, pixels are inspected like the reference does */
 } ngp_train_view;
 
 /* Exponential-stepping constants, evaluated once on the host with ngp_detmath.h so the device march and the oracle

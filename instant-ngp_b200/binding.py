@@ -55,6 +55,7 @@ class TrainView(C.Structure):
         ("lens_mode", C.c_uint32),
         ("lens_params", C.c_float * 4),
         ("xform", C.c_float * 12),
+        ("no_mask", C.c_uint32),
     ]
 
 

@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(128) k_generate_training_samples(
 		rng.advance((uint64_t)i * N_MAX_RANDOM_SAMPLES_PER_RAY);
 		float u, v;
 		random_image_pos_training(rng, vw.width, vw.height, cfg.snap_to_pixel_centers != 0, u, v);
-		const bool masked = read_rgba_uv(u, v, vw.width, vw.height, vw.pixels, vw.image_type).r < 0.0f;
+		const bool masked = !vw.no_mask && read_rgba_uv(u, v, vw.width, vw.height, vw.pixels, vw.image_type).r < 0.0f;
 		if (!masked) {
 			(void)rng.next_float();  // motion-blur time (testbed_nerf.cu:740) — consumed, unused without rolling shutter
 			uv_to_ray(u, v, vw.width, vw.height, vw.focal_x, vw.focal_y, vw.principal_x, vw.principal_y, vw.lens_mode, vw.lens_params, vw.xform, ro, rd);

@@ -237,14 +237,33 @@ struct ngp_testbed {
 	float loss_scalar = 0.0f;
 	bool shall_train = true;
 
-	// per-step scratch
-	DevBuf<ngp_nerf_counters> counters;
-	DevBuf<uint32_t> ray_indices, numsteps;
-	DevBuf<float> rays, coords, coords_compacted, loss_per_ray, reduce_scratch;
+	// per-step scratch.  Everything the sample generator writes exists twice: while step k trains, the generator of step
+	// k+1 already runs on a side stream into the other set (it depends only on the occupancy bitfield, the RNG and
+	// rays_per_batch, all known once step k's counters are back).
+	struct RaySet {
+		DevBuf<ngp_nerf_counters> counters;
+		DevBuf<uint32_t> ray_indices, numsteps;
+		DevBuf<float> rays, coords;
+	} set[2];
+	uint32_t cur = 0;                     // set used by the step in flight
+	DevBuf<float> coords_compacted, loss_per_ray, reduce_scratch;
 	DevBuf<__half> mlp_out, dloss;
 	uint32_t last_batch = 0;
 	bool grads_pending = false;
 	bool get_loss_pending = false;
+	bool overlap_sample_generation = true;
+	cudaStream_t side_stream = nullptr;
+	cudaEvent_t ev_front_done = nullptr, ev_prefetch_done = nullptr, ev_main_ready = nullptr;
+	struct Readback {
+		ngp_nerf_counters counters;
+		float loss_partial[1024];
+	}* readback = nullptr;                // pinned host memory
+	// a sample-generator launch that has been issued ahead of time
+	bool prefetch_valid = false;
+	uint32_t prefetch_step = 0, prefetch_batch = 0, prefetch_rays = 0, prefetch_max_inference = 0;
+	uint64_t prefetch_rng_state = 0;
+	uint32_t step_rays_local = 0, step_max_inference = 0;
+	DevBuf<ngp_nerf_counters> dp_counters;  // stable address for the caller's all-reduce of the counter block
 
 	// data parallel
 	uint32_t dp_rank = 0, dp_world = 1;
@@ -263,6 +282,13 @@ struct ngp_testbed {
 	float render_min_transmittance = 0.01f;
 
 	~ngp_testbed() {
+		if (side_stream) {
+			cudaStreamSynchronize(side_stream);
+			cudaStreamDestroy(side_stream);
+		}
+		for (cudaEvent_t e : {ev_front_done, ev_prefetch_done, ev_main_ready})
+			if (e) cudaEventDestroy(e);
+		if (readback) cudaFreeHost(readback);
 		for (void* p : pixel_bufs)
 			if (p) cudaFree(p);
 	}
@@ -461,14 +487,24 @@ static void tb_reset_network(ngp_testbed* t, const Json& config) {
 static void tb_ensure_step_scratch(ngp_testbed* t, uint32_t batch) {
 	const uint32_t max_samples = batch * 16;
 	const uint32_t max_rays = 1u << 18;
-	t->counters.ensure(1);
-	t->ray_indices.ensure(max_rays);
-	t->numsteps.ensure((size_t)max_rays * 2);
-	t->rays.ensure((size_t)max_rays * 6);
+	t->dp_counters.ensure(1);
+	for (auto& rs : t->set) {
+		rs.counters.ensure(1);
+		rs.ray_indices.ensure(max_rays);
+		rs.numsteps.ensure((size_t)max_rays * 2);
+		rs.rays.ensure((size_t)max_rays * 6);
+		rs.coords.ensure((size_t)max_samples * 7);
+	}
 	t->loss_per_ray.ensure(max_rays);
 	t->reduce_scratch.ensure(1024);
-	t->coords.ensure((size_t)max_samples * 7);
 	t->mlp_out.ensure((size_t)max_samples * 4);
+	if (!t->side_stream) {
+		NGPB_CUDA_CHECK(cudaStreamCreateWithFlags(&t->side_stream, cudaStreamNonBlocking));
+		NGPB_CUDA_CHECK(cudaEventCreateWithFlags(&t->ev_front_done, cudaEventDisableTiming));
+		NGPB_CUDA_CHECK(cudaEventCreateWithFlags(&t->ev_prefetch_done, cudaEventDisableTiming));
+		NGPB_CUDA_CHECK(cudaEventCreateWithFlags(&t->ev_main_ready, cudaEventDisableTiming));
+		NGPB_CUDA_CHECK(cudaHostAlloc(reinterpret_cast<void**>(&t->readback), sizeof(*t->readback), cudaHostAllocDefault));
+	}
 	t->coords_compacted.ensure((size_t)batch * 7);
 	t->dloss.ensure((size_t)batch * 4);
 	t->grid_scratch.ensure(density_grid_scratch_bytes(t->cfg.max_cascade));
@@ -497,6 +533,7 @@ static void tb_collect_phases(ngp_testbed* t) {
 	for (int p = 0; p < NGP_N_PHASES; ++p) {
 		if (!t->ev_used[p]) continue;
 		float ms = 0.0f;
+		cudaEventSynchronize(t->ev[p][1]);
 		if (cudaEventElapsedTime(&ms, t->ev[p][0], t->ev[p][1]) == cudaSuccess) t->phase_ms[p] += ms;
 		t->ev_used[p] = false;
 	}
@@ -515,59 +552,103 @@ static void tb_training_prep(ngp_testbed* t) {
 	++t->density_grid_ema_step;
 }
 
-// train_nerf_step up to and including the backward pass (testbed_nerf.cu:3007-3382)
+__global__ void k_sum_partial_1024(const float* __restrict__ data, uint32_t n, float* __restrict__ partial) {
+	const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+	float s = 0.0f;
+	for (uint32_t i = t; i < n; i += 1024) s += data[i];
+	partial[t] = s;
+}
+
+static uint32_t tb_max_inference(const ngp_testbed* t, uint32_t batch) {
+	const uint32_t max_samples = batch * 16;
+	if (t->measured_batch_size_before_compaction == 0) return max_samples;
+	return next_multiple(std::min(t->measured_batch_size_before_compaction, max_samples), NGP_BATCH_GRANULARITY);
+}
+static bool tb_prep_due(uint32_t training_step) {
+	// Testbed::train (src/testbed.cu:4596-4614): density-grid prep every clamp(step/16, 1, 16) steps
+	const uint32_t n_prep_to_skip = std::min(std::max(training_step / 16u, 1u), 16u);
+	return training_step % n_prep_to_skip == 0;
+}
+// Any state change the prefetched generator launch could not have seen makes it void.
+static void tb_invalidate_prefetch(ngp_testbed* t) {
+	if (t->prefetch_valid && t->side_stream) cudaStreamSynchronize(t->side_stream);
+	t->prefetch_valid = false;
+}
+static void tb_launch_generator(ngp_testbed* t, cudaStream_t stream, uint32_t set, uint32_t rays_local, uint32_t max_inference) {
+	ngp_testbed::RaySet& rs = t->set[set];
+	NGPB_CUDA_CHECK(cudaMemsetAsync(rs.counters.p, 0, sizeof(ngp_nerf_counters), stream));
+	generate_training_samples(stream, rays_local, t->dp_rank * rays_local, rays_local * t->dp_world, t->rng.state, t->rng.inc, t->cfg, t->views_dev.p, tb_n_views(t),
+		t->bitfield.p, max_inference, rs.counters.p, rs.ray_indices.p, rs.rays.p, rs.numsteps.p, rs.coords.p);
+}
+
+// train_nerf_step up to and including the backward pass (testbed_nerf.cu:3007-3382).  Everything is asynchronous; the
+// host learns the step's counters from a pinned read-back guarded by ev_front_done (waited for in tb_apply_grads, while the
+// GPU is busy with the forward/backward kernel).
 static void tb_compute_grads(ngp_testbed* t, uint32_t batch) {
 	NGPB_CHECK(t->has_network, "Testbed::train: no network (call reload_network_from_json/file first)");
 	NGPB_CHECK(tb_n_views(t) > 0, "Testbed::train: no training images (set nerf.training.n_images_for_training)");
 	NGPB_CHECK(batch % NGP_BATCH_GRANULARITY == 0 && batch > 0, "Testbed::train: batch size must be a positive multiple of 256");
+	NGPB_CHECK(!t->grads_pending, "train_compute_grads called twice without train_apply_grads");
 	for (uint32_t i = 0; i < tb_n_views(t); ++i) NGPB_CHECK(t->views[i].pixels != nullptr, "Testbed::train: training image " + std::to_string(i) + " was never set");
+	if (batch != t->last_batch) tb_invalidate_prefetch(t);  // buffers may be re-allocated
 	tb_ensure_step_scratch(t, batch);
 	tb_upload_views(t);
 
-	// Testbed::train (src/testbed.cu:4596-4614): density-grid prep every clamp(step/16, 1, 16) steps
-	const uint32_t n_prep_to_skip = std::min(std::max(t->training_step / 16u, 1u), 16u);
-	if (t->training_step % n_prep_to_skip == 0) {
+	const bool prep = tb_prep_due(t->training_step);
+	if (prep) {
+		tb_invalidate_prefetch(t);  // the bitfield is about to change (a prefetch is never issued for such a step anyway)
 		PhaseTimer pt(t, 0);
 		tb_training_prep(t);
 	}
-
-	const uint32_t max_samples = batch * 16;
-	uint32_t max_inference;
-	if (t->measured_batch_size_before_compaction == 0) {
-		t->measured_batch_size_before_compaction = max_inference = max_samples;
-	} else {
-		max_inference = next_multiple(std::min(t->measured_batch_size_before_compaction, max_samples), NGP_BATCH_GRANULARITY);
-	}
 	if (t->training_step == 0) t->n_rays_total = 0;
-	const uint32_t n_rays_total = t->n_rays_total;
 	const uint32_t rays_local = t->rays_per_batch;
 	const uint32_t rays_global = rays_local * t->dp_world;
+	const uint32_t max_inference = tb_max_inference(t, batch);
+	if (t->measured_batch_size_before_compaction == 0) t->measured_batch_size_before_compaction = max_inference;
 	t->n_rays_total += rays_global;
 
-	NGPB_CUDA_CHECK(cudaMemsetAsync(t->counters.p, 0, sizeof(ngp_nerf_counters), t->stream));
-	NGPB_CUDA_CHECK(cudaMemsetAsync(t->loss_per_ray.p, 0, sizeof(float) * rays_local, t->stream));
-	(void)n_rays_total;
-	{
+	const bool use_prefetch = t->prefetch_valid && t->prefetch_step == t->training_step && t->prefetch_batch == batch && t->prefetch_rays == rays_local &&
+		t->prefetch_max_inference == max_inference && t->prefetch_rng_state == t->rng.state;
+	if (use_prefetch) {
+		// the generator of this step already ran (or is finishing) on the side stream into the other buffer set
+		t->cur ^= 1u;
+		NGPB_CUDA_CHECK(cudaStreamWaitEvent(t->stream, t->ev_prefetch_done, 0));
+	} else {
+		tb_invalidate_prefetch(t);
 		PhaseTimer pt(t, 1);
-		generate_training_samples(t->stream, rays_local, t->dp_rank * rays_local, rays_global, t->rng.state, t->rng.inc, t->cfg, t->views_dev.p, tb_n_views(t),
-			t->bitfield.p, max_inference, t->counters.p, t->ray_indices.p, t->rays.p, t->numsteps.p, t->coords.p);
+		tb_launch_generator(t, t->stream, t->cur, rays_local, max_inference);
 	}
+	t->prefetch_valid = false;
+	ngp_testbed::RaySet& rs = t->set[t->cur];
+	NGPB_CUDA_CHECK(cudaMemsetAsync(t->loss_per_ray.p, 0, sizeof(float) * rays_local, t->stream));
 	{
 		PhaseTimer pt(t, 2);
 		if (t->full_inference) {
 			// the reference's schedule: evaluate every generated sample (testbed_nerf.cu:3233-3235)
-			nerf_inference_counted(t->desc, t->stream, max_inference, &t->counters.p->n_samples, t->coords.p, t->params.p, t->mlp_out.p);
+			nerf_inference_counted(t->desc, t->stream, max_inference, &rs.counters.p->n_samples, rs.coords.p, t->params.p, t->mlp_out.p);
 		} else {
 			// evaluate, ray by ray, only the samples the loss kernel will read (bit-identical outputs for those)
-			nerf_inference_rays(t->desc, t->stream, rays_local, t->counters.p, &t->counters.p->pad, t->numsteps.p, t->coords.p, t->params.p,
+			nerf_inference_rays(t->desc, t->stream, rays_local, rs.counters.p, &rs.counters.p->pad, rs.numsteps.p, rs.coords.p, t->params.p,
 				t->cfg.density_activation, t->mlp_out.p);
 		}
 	}
 	{
 		PhaseTimer pt(t, 3);
-		compute_loss(t->stream, rays_local, rays_global, t->rng.state, t->rng.inc, t->cfg, t->views_dev.p, tb_n_views(t), t->mlp_out.p, batch, t->counters.p,
-			t->ray_indices.p, t->rays.p, t->numsteps.p, t->coords.p, t->coords_compacted.p, t->dloss.p, t->loss_per_ray.p, t->mean_density.p);
-		fill_rollover(t->stream, batch, t->counters.p, t->coords_compacted.p, t->dloss.p);
+		compute_loss(t->stream, rays_local, rays_global, t->rng.state, t->rng.inc, t->cfg, t->views_dev.p, tb_n_views(t), t->mlp_out.p, batch, rs.counters.p,
+			rs.ray_indices.p, rs.rays.p, rs.numsteps.p, rs.coords.p, t->coords_compacted.p, t->dloss.p, t->loss_per_ray.p, t->mean_density.p);
+		fill_rollover(t->stream, batch, rs.counters.p, t->coords_compacted.p, t->dloss.p);
+	}
+	t->get_loss_pending = (t->training_step % 16 == 0);
+	if (t->get_loss_pending) {
+		k_sum_partial_1024<<<4, 256, 0, t->stream>>>(t->loss_per_ray.p, rays_local, t->reduce_scratch.p);
+		NGPB_LAUNCHED();
+		NGPB_CUDA_CHECK(cudaMemcpyAsync(t->readback->loss_partial, t->reduce_scratch.p, sizeof(float) * 1024, cudaMemcpyDeviceToHost, t->stream));
+	}
+	if (t->dp_world == 1) {
+		NGPB_CUDA_CHECK(cudaMemcpyAsync(&t->readback->counters, rs.counters.p, sizeof(ngp_nerf_counters), cudaMemcpyDeviceToHost, t->stream));
+		NGPB_CUDA_CHECK(cudaEventRecord(t->ev_front_done, t->stream));
+	} else {
+		NGPB_CUDA_CHECK(cudaMemcpyAsync(t->dp_counters.p, rs.counters.p, sizeof(ngp_nerf_counters), cudaMemcpyDeviceToDevice, t->stream));
 	}
 	{
 		PhaseTimer pt(t, 4);
@@ -575,13 +656,20 @@ static void tb_compute_grads(ngp_testbed* t, uint32_t batch) {
 	}
 	t->rng.advance();
 	t->grads_pending = true;
-	t->get_loss_pending = (t->training_step % 16 == 0);
+	t->step_rays_local = rays_local;
+	t->step_max_inference = max_inference;
 }
 
-// optimizer_step + NerfCounters::update_after_training (testbed_nerf.cu:2678-2702, 2770-2788)
+// optimizer_step + NerfCounters::update_after_training (testbed_nerf.cu:2678-2702, 2770-2788), then the generator of the
+// next step is put on the side stream.
 static void tb_apply_grads(ngp_testbed* t) {
 	NGPB_CHECK(t->grads_pending, "train_apply_grads without train_compute_grads");
 	const uint32_t batch = t->last_batch;
+	if (t->dp_world > 1) {
+		// the caller has summed the counter block over ranks (after the forward/backward kernel in stream order)
+		NGPB_CUDA_CHECK(cudaMemcpyAsync(&t->readback->counters, t->dp_counters.p, sizeof(ngp_nerf_counters), cudaMemcpyDeviceToHost, t->stream));
+		NGPB_CUDA_CHECK(cudaEventRecord(t->ev_front_done, t->stream));
+	}
 	// ExponentialDecayOptimizer::step (exponential_decay.h:60-72)
 	if (t->optimizer_step == 0) t->lr_factor = 1.0f;
 	if (t->opt.has_decay && t->optimizer_step >= t->opt.decay_start && (t->optimizer_step - t->opt.decay_start) % t->opt.decay_interval == 0 &&
@@ -607,11 +695,13 @@ static void tb_apply_grads(ngp_testbed* t) {
 	++t->training_step;
 	t->grads_pending = false;
 
-	ngp_nerf_counters c{};
-	NGPB_CUDA_CHECK(cudaMemcpyAsync(&c, t->counters.p, sizeof(c), cudaMemcpyDeviceToHost, t->stream));
-	NGPB_CUDA_CHECK(cudaStreamSynchronize(t->stream));
-	tb_collect_phases(t);
-	// with data parallelism the caller has summed the counters over ranks; use the per-rank mean
+	// the counters were copied out before the forward/backward kernel was queued: this wait ends while the GPU still works
+	NGPB_CUDA_CHECK(cudaEventSynchronize(t->ev_front_done));
+	const ngp_nerf_counters c = t->readback->counters;
+	if (t->profiling) {
+		NGPB_CUDA_CHECK(cudaStreamSynchronize(t->stream));  // phase timing wants completed events; only paid while profiling
+		tb_collect_phases(t);
+	}
 	const uint32_t n_samples = c.n_samples / t->dp_world, n_compacted = c.n_samples_compacted / t->dp_world;
 	t->measured_batch_size = 0;
 	t->measured_batch_size_before_compaction = 0;
@@ -623,11 +713,40 @@ static void tb_apply_grads(ngp_testbed* t) {
 	t->measured_batch_size_before_compaction = n_samples;
 	t->measured_batch_size = n_compacted;
 	if (t->get_loss_pending) {
-		const float s = reduce_sum_f32(t->stream, t->loss_per_ray.p, t->rays_per_batch, t->reduce_scratch.p);
-		t->loss_scalar = s * (float)t->measured_batch_size / (float)batch;
+		float sum = 0.0f;
+		for (int i = 0; i < 1024; ++i) sum += t->readback->loss_partial[i];
+		t->loss_scalar = sum * (float)t->measured_batch_size / (float)batch;
 	}
 	t->rays_per_batch = (uint32_t)((float)t->rays_per_batch * (float)batch / (float)t->measured_batch_size);
 	t->rays_per_batch = std::min(next_multiple(t->rays_per_batch, NGP_BATCH_GRANULARITY), 1u << 18);
+
+	// ---- generator of the next step, concurrently with this step's forward/backward + optimizer
+	if (t->overlap_sample_generation && t->shall_train && !tb_prep_due(t->training_step) && !t->views_dirty) {
+		const uint32_t next = t->cur ^ 1u;
+		const uint32_t max_inference = tb_max_inference(t, batch);
+		// the other buffer set was last read by the loss kernel of the previous step, which precedes ev_front_done on the main
+		// stream; the bitfield and the views are not written by anything in flight
+		NGPB_CUDA_CHECK(cudaStreamWaitEvent(t->side_stream, t->ev_front_done, 0));
+		if (t->profiling) {
+			if (!t->ev[1][0]) {
+				cudaEventCreate(&t->ev[1][0]);
+				cudaEventCreate(&t->ev[1][1]);
+			}
+			cudaEventRecord(t->ev[1][0], t->side_stream);
+		}
+		tb_launch_generator(t, t->side_stream, next, t->rays_per_batch, max_inference);
+		if (t->profiling) {
+			cudaEventRecord(t->ev[1][1], t->side_stream);
+			t->ev_used[1] = true;
+		}
+		NGPB_CUDA_CHECK(cudaEventRecord(t->ev_prefetch_done, t->side_stream));
+		t->prefetch_valid = true;
+		t->prefetch_step = t->training_step;
+		t->prefetch_batch = batch;
+		t->prefetch_rays = t->rays_per_batch;
+		t->prefetch_max_inference = max_inference;
+		t->prefetch_rng_state = t->rng.state;
+	}
 }
 
 }  // namespace ngpb
@@ -759,6 +878,7 @@ void ngp_testbed_destroy(ngp_testbed* t) {
 }
 int ngp_testbed_create_empty_nerf_dataset(ngp_testbed* t, uint32_t n_images, uint32_t aabb_scale) {
 	NGPB_TRY({
+		tb_invalidate_prefetch(t);
 		NGPB_CHECK(n_images > 0, "create_empty_nerf_dataset: n_images must be > 0");
 		NGPB_CHECK(aabb_scale >= 1 && aabb_scale <= 128 && (aabb_scale & (aabb_scale - 1)) == 0, "aabb_scale must be a power of two in [1, 128]");
 		for (void* p : t->pixel_bufs)
@@ -780,6 +900,7 @@ int ngp_testbed_create_empty_nerf_dataset(ngp_testbed* t, uint32_t n_images, uin
 }
 int ngp_testbed_set_image(ngp_testbed* t, uint32_t idx, const float* rgba_host, int32_t w, int32_t h) {
 	NGPB_TRY({
+		tb_invalidate_prefetch(t);
 		NGPB_CHECK(idx < t->n_images, "Invalid frame index");
 		NGPB_CHECK(w > 0 && h > 0, "image must have positive size");
 		if (t->pixel_bufs[idx]) cudaFree(t->pixel_bufs[idx]);
@@ -790,6 +911,12 @@ int ngp_testbed_set_image(ngp_testbed* t, uint32_t idx, const float* rgba_host, 
 		t->pixel_bufs[idx] = p;
 		t->views[idx].pixels = p;
 		t->views[idx].image_type = NGP_IMAGE_FLOAT;  // python_api.cu:45-72 keeps float images as they are
+		{
+			bool any_masked = false;  // read_rgba(...).x < 0 marks a masked-away pixel (testbed_nerf.cu:732-736)
+			const size_t n_px = (size_t)w * h;
+			for (size_t k = 0; k < n_px && !any_masked; ++k) any_masked = rgba_host[k * 4] < 0.0f;
+			t->views[idx].no_mask = any_masked ? 0u : 1u;
+		}
 		t->views[idx].width = w;
 		t->views[idx].height = h;
 		t->views_dirty = true;
@@ -797,6 +924,7 @@ int ngp_testbed_set_image(ngp_testbed* t, uint32_t idx, const float* rgba_host, 
 }
 int ngp_testbed_set_camera_extrinsics(ngp_testbed* t, uint32_t idx, const float* m, int convert_to_ngp) {
 	NGPB_TRY({
+		tb_invalidate_prefetch(t);
 		NGPB_CHECK(idx < t->n_images, "Invalid frame index");
 		// input: row-major 3x4 camera-to-world; columns c0,c1,c2,origin
 		float col[4][3];
@@ -824,6 +952,7 @@ int ngp_testbed_set_camera_extrinsics(ngp_testbed* t, uint32_t idx, const float*
 }
 int ngp_testbed_set_camera_intrinsics(ngp_testbed* t, uint32_t idx, float fx, float fy, float cx, float cy, float k1, float k2, float p1, float p2) {
 	NGPB_TRY({
+		tb_invalidate_prefetch(t);
 		NGPB_CHECK(idx < t->n_images, "Invalid frame index");
 		ngp_train_view& v = t->views[idx];
 		NGPB_CHECK(v.width > 0, "set_camera_intrinsics: set the image first (principal point is relative to the resolution)");
@@ -847,6 +976,7 @@ int ngp_testbed_set_camera_intrinsics(ngp_testbed* t, uint32_t idx, float fx, fl
 }
 int ngp_testbed_reload_network_from_json(ngp_testbed* t, const char* json_text) {
 	NGPB_TRY({
+		tb_invalidate_prefetch(t);
 		const std::string text(json_text);
 		Json cfg = JsonParser(text).parse();
 		tb_reset_network(t, cfg);
@@ -854,6 +984,7 @@ int ngp_testbed_reload_network_from_json(ngp_testbed* t, const char* json_text) 
 }
 int ngp_testbed_reload_network_from_file(ngp_testbed* t, const char* path) {
 	NGPB_TRY({
+		tb_invalidate_prefetch(t);
 		std::ifstream f(path);
 		NGPB_CHECK(f.good(), std::string("network config not found: ") + path);
 		std::stringstream ss;
@@ -865,11 +996,13 @@ int ngp_testbed_reload_network_from_file(ngp_testbed* t, const char* path) {
 	});
 }
 int ngp_testbed_set_seed(ngp_testbed* t, uint64_t seed) {
+	tb_invalidate_prefetch(t);
 	t->seed = seed;
 	return 0;
 }
 int ngp_testbed_set_option(ngp_testbed* t, const char* name_c, double value) {
 	NGPB_TRY({
+		tb_invalidate_prefetch(t);
 		const std::string n(name_c);
 		ngp_nerf_train_cfg& c = t->cfg;
 		if (n == "nerf.training.n_images_for_training") { NGPB_CHECK(value >= 0 && value <= t->n_images, "n_images_for_training out of range"); t->n_images_for_training = (uint32_t)value; }
@@ -888,6 +1021,7 @@ int ngp_testbed_set_option(ngp_testbed* t, const char* name_c, double value) {
 		else if (n == "background_color.g") c.background_color[1] = (float)value;
 		else if (n == "background_color.b") c.background_color[2] = (float)value;
 		else if (n == "nerf.training.full_inference") t->full_inference = value != 0;
+		else if (n == "nerf.training.overlap_sample_generation") t->overlap_sample_generation = value != 0;
 		else if (n == "train_network") t->train_network = value != 0;
 		else if (n == "train_encoding") t->train_encoding = value != 0;
 		else if (n == "shall_train") t->shall_train = value != 0;
@@ -919,6 +1053,7 @@ double ngp_testbed_get_option(ngp_testbed* t, const char* name_c) {
 }
 int ngp_testbed_set_dp(ngp_testbed* t, uint32_t rank, uint32_t world) {
 	NGPB_TRY({
+		tb_invalidate_prefetch(t);
 		NGPB_CHECK(world >= 1 && rank < world, "set_dp: rank must be < world");
 		t->dp_rank = rank;
 		t->dp_world = world;
@@ -937,7 +1072,10 @@ void* ngp_testbed_grads(ngp_testbed* t) { return t->grads.p; }
 void* ngp_testbed_params(ngp_testbed* t) { return t->params.p; }
 void* ngp_testbed_params_inference(ngp_testbed* t) { return t->params_ema.p; }
 float* ngp_testbed_params_fp32(ngp_testbed* t) { return t->params_fp32.p; }
-uint32_t* ngp_testbed_dp_counters(ngp_testbed* t) { return reinterpret_cast<uint32_t*>(t->counters.p); }
+uint32_t* ngp_testbed_dp_counters(ngp_testbed* t) {
+	t->dp_counters.ensure(1);
+	return reinterpret_cast<uint32_t*>(t->dp_counters.p);
+}
 uint32_t ngp_testbed_n_params(ngp_testbed* t) { return t->has_network ? t->desc.n_params : 0; }
 uint32_t ngp_testbed_training_step(ngp_testbed* t) { return t->training_step; }
 float ngp_testbed_loss(ngp_testbed* t) { return t->loss_scalar; }
@@ -977,6 +1115,7 @@ int ngp_testbed_get_density_grid(ngp_testbed* t, float* grid_host, uint32_t n, u
 }
 int ngp_testbed_set_density_grid(ngp_testbed* t, const float* grid_host, uint32_t n) {
 	NGPB_TRY({
+		tb_invalidate_prefetch(t);
 		NGPB_CHECK(t->density_grid.p, "configure a network first");
 		NGPB_CHECK(n <= GRID_N_CELLS * NGP_NERF_CASCADES, "density grid too large");
 		NGPB_CUDA_CHECK(cudaMemcpyAsync(t->density_grid.p, grid_host, (size_t)n * 4, cudaMemcpyHostToDevice, t->stream));
@@ -1088,6 +1227,7 @@ int ngp_testbed_save_snapshot(ngp_testbed* t, const char* path) {
 }
 int ngp_testbed_load_snapshot(ngp_testbed* t, const char* path) {
 	NGPB_TRY({
+		tb_invalidate_prefetch(t);
 		std::ifstream f(path, std::ios::binary);
 		NGPB_CHECK(f.good(), std::string("snapshot not found: ") + path);
 		SnapshotHeader h{};
@@ -1155,6 +1295,10 @@ int ngp_testbed_update_image_async(ngp_testbed* t, uint32_t idx, const float* rg
 	NGPB_TRY({
 		NGPB_CHECK(idx < t->n_images && t->pixel_bufs[idx], "update_image_async: image slot was never set");
 		const ngp_train_view& v = t->views[idx];
+		// The sample generator looks at pixels only to skip masked ones.  A view registered without masked pixels
+		// (no_mask, established by set_image) promises that replacement frames have none either, so a generator launch
+		// already in flight for the next step stays valid; otherwise it is discarded.
+		if (!v.no_mask) tb_invalidate_prefetch(t);
 		NGPB_CUDA_CHECK(cudaMemcpyAsync(t->pixel_bufs[idx], rgba_host, (size_t)v.width * v.height * 16, cudaMemcpyHostToDevice, t->stream));
 	});
 }

@@ -282,7 +282,7 @@ def test_ray_ordered_inference_equals_full_inference_where_the_loss_reads(lib, s
     params = util.random_params(L, seed=41, trained_like=True)
     # bias the density head so that rays saturate after a varying, finite number of samples
     dens_out_off = 64 * 32
-    params[dens_out_off:dens_out_off + 64] = np.abs(params[dens_out_off:dens_out_off + 64]) * 3.0
+    params[dens_out_off:dens_out_off + 64] = np.abs(params[dens_out_off:dens_out_off + 64]) * 60.0
     params = params.astype(np.float16)
     t_p = dev(params)
     dv = ctx["dev"]
