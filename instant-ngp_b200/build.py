@@ -81,7 +81,7 @@ def build_oracle(verbose: bool = False) -> Path:
     odir = ROOT / "oracle"
     out = odir / "libngp_oracle.so"
     src = odir / "ngp_oracle.c"
-    deps = [src, ROOT / "include" / "ngp_detmath.h"]
+    deps = [src, ROOT / "include" / "ngp_detmath.h", ROOT / "include" / "ngp_b200.h"]
     if not src.exists():
         raise RuntimeError(f"{src} is missing")
     if _newer(out, deps):
