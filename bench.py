@@ -193,6 +193,8 @@ def main() -> None:
     ap.add_argument("--res", type=int, default=RES)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="disable the side-stream prefetch of the next step's sample generation")
+    ap.add_argument("--chunk", type=int, default=0, help="ray-ordered inference chunk (4 or 8)")
+    ap.add_argument("--overlap", action="store_true", help="enable the side-stream prefetch of the next step's sample generation")
     ap.add_argument("--full-inference", action="store_true", help="evaluate every generated sample like the reference schedule")
     ap.add_argument("--render", action="store_true", help="also time a 1920x1080 render (reported as extra keys)")
     args = ap.parse_args()
@@ -218,6 +220,10 @@ def main() -> None:
     tb, imgs = build_testbed(rank, world, args.views, args.res)
     if args.no_overlap:
         tb._set("nerf.training.overlap_sample_generation", 0.0)
+    if args.chunk:
+        tb._set("nerf.training.inference_chunk", float(args.chunk))
+    if args.overlap:
+        tb._set("nerf.training.overlap_sample_generation", 1.0)
     if args.full_inference:
         tb._set("nerf.training.full_inference", 1.0)
     n_params = tb.n_params

@@ -104,26 +104,34 @@ __device__ __forceinline__ void grid_gather(const NetDev& net, const __half* __r
 // ------------------------------------------------------------------------------------------------------------------
 // SH degree 4 (16 coefficients) of d = 2*dir - 1, rounded to fp16 (sh_enc, common_device.h:475-503).
 // ------------------------------------------------------------------------------------------------------------------
+// Written with explicit single-rounding multiplies / adds: the same values whether or not the including translation unit
+// allows FMA contraction (render.cu is built with -fmad=false, nerf_net.cu is not), and the same as the oracle.
 __device__ __forceinline__ void sh4_encode(float dx, float dy, float dz, __half2 (&o)[8]) {
-	const float x = dx * 2.f - 1.f, y = dy * 2.f - 1.f, z = dz * 2.f - 1.f;
-	const float xy = x * y, xz = x * z, yz = y * z, x2 = x * x, y2 = y * y, z2 = z * z;
+#define M(a, b) __fmul_rn((a), (b))
+#define A(a, b) __fadd_rn((a), (b))
+#define S(a, b) __fsub_rn((a), (b))
+	const float x = S(M(dx, 2.f), 1.f), y = S(M(dy, 2.f), 1.f), z = S(M(dz, 2.f), 1.f);
+	const float xy = M(x, y), xz = M(x, z), yz = M(y, z), x2 = M(x, x), y2 = M(y, y), z2 = M(z, z);
 	float s[16];
 	s[0] = 0.28209479177387814f;
-	s[1] = -0.48860251190291987f * y;
-	s[2] = 0.48860251190291987f * z;
-	s[3] = -0.48860251190291987f * x;
-	s[4] = 1.0925484305920792f * xy;
-	s[5] = -1.0925484305920792f * yz;
-	s[6] = 0.94617469575755997f * z2 - 0.31539156525251999f;
-	s[7] = -1.0925484305920792f * xz;
-	s[8] = 0.54627421529603959f * x2 - 0.54627421529603959f * y2;
-	s[9] = 0.59004358992664352f * y * (-3.0f * x2 + y2);
-	s[10] = 2.8906114426405538f * xy * z;
-	s[11] = 0.45704579946446572f * y * (1.0f - 5.0f * z2);
-	s[12] = 0.3731763325901154f * z * (5.0f * z2 - 3.0f);
-	s[13] = 0.45704579946446572f * x * (1.0f - 5.0f * z2);
-	s[14] = 1.4453057213202769f * z * (x2 - y2);
-	s[15] = 0.59004358992664352f * x * (-x2 + 3.0f * y2);
+	s[1] = M(-0.48860251190291987f, y);
+	s[2] = M(0.48860251190291987f, z);
+	s[3] = M(-0.48860251190291987f, x);
+	s[4] = M(1.0925484305920792f, xy);
+	s[5] = M(-1.0925484305920792f, yz);
+	s[6] = S(M(0.94617469575755997f, z2), 0.31539156525251999f);
+	s[7] = M(-1.0925484305920792f, xz);
+	s[8] = S(M(0.54627421529603959f, x2), M(0.54627421529603959f, y2));
+	s[9] = M(M(0.59004358992664352f, y), A(M(-3.0f, x2), y2));
+	s[10] = M(M(2.8906114426405538f, xy), z);
+	s[11] = M(M(0.45704579946446572f, y), S(1.0f, M(5.0f, z2)));
+	s[12] = M(M(0.3731763325901154f, z), S(M(5.0f, z2), 3.0f));
+	s[13] = M(M(0.45704579946446572f, x), S(1.0f, M(5.0f, z2)));
+	s[14] = M(M(1.4453057213202769f, z), S(x2, y2));
+	s[15] = M(M(0.59004358992664352f, x), A(-x2, M(3.0f, y2)));
+#undef M
+#undef A
+#undef S
 #pragma unroll
 	for (int i = 0; i < 8; ++i) o[i] = __floats2half2_rn(s[2 * i], s[2 * i + 1]);
 }

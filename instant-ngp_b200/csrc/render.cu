@@ -261,9 +261,7 @@ __global__ void __launch_bounds__(TILE, 3) k_render_nerf(
 // arithmetic (same expression order, ngp_expf, no FMA contraction) and a slot whose ray is exhausted or has T < 1e-4 pulls the
 // next ray from a device-side queue.  Outputs for the samples the loss kernel reads are bit-identical to the all-samples pass.
 // ------------------------------------------------------------------------------------------------------------------
-constexpr uint32_t RAY_CHUNK = 8;
-
-template <uint32_t F>
+template <uint32_t F, uint32_t RAY_CHUNK>
 __global__ void __launch_bounds__(TILE, 3) k_nerf_forward_rays(
 	const __grid_constant__ NetDev net, const ngp_nerf_counters* __restrict__ counters, uint32_t* __restrict__ queue, const uint32_t* __restrict__ numsteps,
 	const float* __restrict__ coords, const __half* __restrict__ params, const uint32_t density_activation, __half* __restrict__ out
@@ -400,27 +398,34 @@ __global__ void __launch_bounds__(TILE, 3) k_nerf_forward_rays(
 }
 
 // queue: a zeroed u32 (the `pad` word of the step's counter block).  Grid sized for the worst case (n_rays_max rays).
-void nerf_inference_rays(const ngp_nerf_desc& d, cudaStream_t stream, uint32_t n_rays_max, const ngp_nerf_counters* counters, uint32_t* queue,
+template <uint32_t F, uint32_t CHUNK>
+static void launch_forward_rays(const NetDev& net, cudaStream_t stream, uint32_t n_rays_max, const ngp_nerf_counters* counters, uint32_t* queue,
 	const uint32_t* numsteps, const float* coords, const __half* params, uint32_t density_activation, __half* out) {
-	if (n_rays_max == 0) return;
-	const NetDev net = make_netdev(d);
 	const FwdSmem L = fwd_smem_layout(net.n_hidden_density, net.n_hidden_rgb);
-	const uint32_t n_tiles = div_round_up(n_rays_max, TILE / RAY_CHUNK);
+	const uint32_t n_tiles = div_round_up(n_rays_max, TILE / CHUNK);
 	const uint32_t max_ctas = (uint32_t)device_sm_count() * 3u;
 	const uint32_t grid = n_tiles < max_ctas ? n_tiles : max_ctas;
-	if (net.n_features == 2) {
-		auto kern = k_nerf_forward_rays<2>;
-		static bool attr = false;
-		if (!attr) { NGPB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); attr = true; }
-		kern<<<grid, TILE, L.total, stream>>>(net, counters, queue, numsteps, coords, params, density_activation, out);
-	} else {
-		auto kern = k_nerf_forward_rays<4>;
-		static bool attr = false;
-		if (!attr) { NGPB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); attr = true; }
-		kern<<<grid, TILE, L.total, stream>>>(net, counters, queue, numsteps, coords, params, density_activation, out);
-	}
+	auto kern = k_nerf_forward_rays<F, CHUNK>;
+	static bool attr = false;
+	if (!attr) { NGPB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); attr = true; }
+	kern<<<grid, TILE, L.total, stream>>>(net, counters, queue, numsteps, coords, params, density_activation, out);
 	NGPB_LAUNCHED();
 	NGPB_CUDA_CHECK(cudaGetLastError());
+}
+
+// chunk: samples of a ray evaluated per tensor-core tile (4 or 8; 128 / chunk ray slots per CTA)
+void nerf_inference_rays(const ngp_nerf_desc& d, cudaStream_t stream, uint32_t n_rays_max, const ngp_nerf_counters* counters, uint32_t* queue,
+	const uint32_t* numsteps, const float* coords, const __half* params, uint32_t density_activation, __half* out, uint32_t chunk) {
+	if (n_rays_max == 0) return;
+	NGPB_CHECK(chunk == 4 || chunk == 8, "inference chunk must be 4 or 8");
+	const NetDev net = make_netdev(d);
+	if (net.n_features == 2) {
+		if (chunk == 4) launch_forward_rays<2, 4>(net, stream, n_rays_max, counters, queue, numsteps, coords, params, density_activation, out);
+		else launch_forward_rays<2, 8>(net, stream, n_rays_max, counters, queue, numsteps, coords, params, density_activation, out);
+	} else {
+		if (chunk == 4) launch_forward_rays<4, 4>(net, stream, n_rays_max, counters, queue, numsteps, coords, params, density_activation, out);
+		else launch_forward_rays<4, 8>(net, stream, n_rays_max, counters, queue, numsteps, coords, params, density_activation, out);
+	}
 }
 
 size_t render_scratch_bytes(int32_t, int32_t) { return 256; }

@@ -22,7 +22,7 @@ void set_last_error(const std::string& msg) { g_last_error = msg; }
 void nerf_inference(const ngp_nerf_desc& d, cudaStream_t stream, uint32_t n, const float* coords, const __half* params, __half* out, uint32_t out_stride);
 void nerf_inference_counted(const ngp_nerf_desc& d, cudaStream_t stream, uint32_t n_max, const uint32_t* n_dev, const float* coords, const __half* params, __half* out);
 void nerf_inference_rays(const ngp_nerf_desc& d, cudaStream_t stream, uint32_t n_rays_max, const ngp_nerf_counters* counters, uint32_t* queue,
-	const uint32_t* numsteps, const float* coords, const __half* params, uint32_t density_activation, __half* out);
+	const uint32_t* numsteps, const float* coords, const __half* params, uint32_t density_activation, __half* out, uint32_t chunk);
 void nerf_density(const ngp_nerf_desc& d, cudaStream_t stream, uint32_t n, const float* positions, uint32_t pos_stride, const __half* params, __half* out);
 void grid_encode(const ngp_grid_desc& g, cudaStream_t stream, uint32_t n, const float* positions, uint32_t pos_stride, const __half* grid, __half* out);
 void nerf_forward_backward(const ngp_nerf_desc& d, cudaStream_t stream, uint32_t n, const float* coords, const __half* params, const __half* dL_dout,
@@ -221,6 +221,7 @@ struct ngp_testbed {
 	uint64_t seed = 1337;
 	bool train_network = true, train_encoding = true;
 	bool full_inference = false;
+	uint32_t inference_chunk = 8;
 
 	DevBuf<float> params_fp32, m1, m2, mlp_grads_f32;
 	DevBuf<__half> params, params_ema, grads;
@@ -251,7 +252,7 @@ struct ngp_testbed {
 	uint32_t last_batch = 0;
 	bool grads_pending = false;
 	bool get_loss_pending = false;
-	bool overlap_sample_generation = true;
+	bool overlap_sample_generation = false;  // measured on B200: the generator competes with the forward/backward kernel for registers (profiles/)
 	cudaStream_t side_stream = nullptr;
 	cudaEvent_t ev_front_done = nullptr, ev_prefetch_done = nullptr, ev_main_ready = nullptr;
 	struct Readback {
@@ -629,7 +630,7 @@ static void tb_compute_grads(ngp_testbed* t, uint32_t batch) {
 		} else {
 			// evaluate, ray by ray, only the samples the loss kernel will read (bit-identical outputs for those)
 			nerf_inference_rays(t->desc, t->stream, rays_local, rs.counters.p, &rs.counters.p->pad, rs.numsteps.p, rs.coords.p, t->params.p,
-				t->cfg.density_activation, t->mlp_out.p);
+				t->cfg.density_activation, t->mlp_out.p, t->inference_chunk);
 		}
 	}
 	{
@@ -792,7 +793,7 @@ int ngp_nerf_inference(const ngp_nerf_desc* d, void* stream, uint32_t n, const f
 int ngp_nerf_inference_rays(const ngp_nerf_desc* d, void* stream, uint32_t n_rays_max, const ngp_nerf_counters* counters, uint32_t* queue, const uint32_t* numsteps,
 	const float* coords, const void* params, uint32_t density_activation, void* out) {
 	NGPB_TRY(require_device(); nerf_inference_rays(*d, (cudaStream_t)stream, n_rays_max, counters, queue, numsteps, coords, (const __half*)params, density_activation,
-		(__half*)out));
+		(__half*)out, 8));
 }
 int ngp_nerf_density(const ngp_nerf_desc* d, void* stream, uint32_t n, const float* positions, uint32_t pos_stride, const void* params, void* out) {
 	NGPB_TRY(require_device(); nerf_density(*d, (cudaStream_t)stream, n, positions, pos_stride, (const __half*)params, (__half*)out));
@@ -1021,6 +1022,7 @@ int ngp_testbed_set_option(ngp_testbed* t, const char* name_c, double value) {
 		else if (n == "background_color.g") c.background_color[1] = (float)value;
 		else if (n == "background_color.b") c.background_color[2] = (float)value;
 		else if (n == "nerf.training.full_inference") t->full_inference = value != 0;
+		else if (n == "nerf.training.inference_chunk") { NGPB_CHECK(value == 4 || value == 8, "inference_chunk must be 4 or 8"); t->inference_chunk = (uint32_t)value; }
 		else if (n == "nerf.training.overlap_sample_generation") t->overlap_sample_generation = value != 0;
 		else if (n == "train_network") t->train_network = value != 0;
 		else if (n == "train_encoding") t->train_encoding = value != 0;
