@@ -39,57 +39,41 @@ __device__ __forceinline__ void adam_one(const AdamDev& a, uint32_t i, float g_s
 	w16[i] = __float2half_rn(nw);
 }
 
-// 8 parameters per thread: one 128-bit gradient load; the heavy fp32 state is touched only where the gradient is non-zero.
+// One warp owns 256 consecutive parameters and walks them as 4 rows of 64: lane l takes the pair (2l, 2l+1) of each row, so
+// every access of the warp is one fully used 128-byte (fp16 arrays) or 256-byte (fp32 arrays) segment.  The first version
+// gave each thread 8 consecutive parameters: every scalar access of a warp then straddled 32 sectors and the kernel ran at
+// 18 % of DRAM throughput (profiles/r1a_first_correct_path.md).  The heavy fp32 state is touched only where needed.
 __global__ void __launch_bounds__(256) k_adam_ema(const AdamDev a, float* __restrict__ w32, __half* __restrict__ w16, __half* __restrict__ ema,
 	__half* __restrict__ grads, float* __restrict__ m1, float* __restrict__ m2, uint32_t* __restrict__ steps) {
-	const uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) * 8u;
-	if (base >= a.n_total) return;
-	const uint32_t n = (a.n_total - base) < 8u ? (a.n_total - base) : 8u;
-	__half g[8];
-	if (n == 8) {
-		*reinterpret_cast<uint4*>(g) = *reinterpret_cast<const uint4*>(grads + base);
-		*reinterpret_cast<uint4*>(grads + base) = make_uint4(0, 0, 0, 0);
-	} else {
-		for (uint32_t k = 0; k < n; ++k) {
-			g[k] = grads[base + k];
-			grads[base + k] = __float2half_rn(0.0f);
-		}
-	}
-	bool touched[8];
-	bool any = false;
+	const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
+	const uint32_t warp_base = warp * 256u;
+	if (warp_base >= a.n_total) return;
+	const float ema_w = 1.0f - a.ema_decay;
 #pragma unroll
-	for (uint32_t k = 0; k < 8; ++k) {
-		touched[k] = false;
-		if (k < n) {
-			const uint32_t i = base + k;
-			const float gv = __half2float(g[k]);
-			if (i < a.n_matrix) {
-				touched[k] = a.optimize_matrix != 0;
-			} else {
-				touched[k] = a.optimize_non_matrix != 0 && gv != 0.0f;
-			}
-			if (touched[k]) {
-				adam_one(a, i, gv, w32, w16, m1, m2, steps);
-				any = true;
-			}
-		}
-	}
-	// EMA of the working weights -> inference weights (ema.h:63-77); every entry, every step
-	(void)any;
-	if (n == 8) {
-		__half wv[8], ev[8];
-		*reinterpret_cast<uint4*>(wv) = *reinterpret_cast<const uint4*>(w16 + base);
-		*reinterpret_cast<uint4*>(ev) = *reinterpret_cast<const uint4*>(ema + base);
-#pragma unroll
-		for (uint32_t k = 0; k < 8; ++k) {
-			const float f = (__half2float(ev[k]) * a.ema_decay * a.ema_debias_old + __half2float(wv[k]) * (1.0f - a.ema_decay)) * a.ema_debias_new;
-			ev[k] = __float2half_rn(f);
-		}
-		*reinterpret_cast<uint4*>(ema + base) = *reinterpret_cast<const uint4*>(ev);
-	} else {
-		for (uint32_t k = 0; k < n; ++k) {
-			const float f = (__half2float(ema[base + k]) * a.ema_decay * a.ema_debias_old + __half2float(w16[base + k]) * (1.0f - a.ema_decay)) * a.ema_debias_new;
-			ema[base + k] = __float2half_rn(f);
+	for (uint32_t row = 0; row < 4; ++row) {
+		const uint32_t i = warp_base + row * 64u + lane * 2u;
+		if (i >= a.n_total) break;
+		if (i + 1 < a.n_total) {
+			const __half2 g2 = *reinterpret_cast<const __half2*>(grads + i);
+			*reinterpret_cast<__half2*>(grads + i) = __float2half2_rn(0.0f);
+			const float g0 = __low2float(g2), g1 = __high2float(g2);
+			const bool t0 = (i < a.n_matrix) ? (a.optimize_matrix != 0) : (a.optimize_non_matrix != 0 && g0 != 0.0f);
+			const bool t1 = (i + 1 < a.n_matrix) ? (a.optimize_matrix != 0) : (a.optimize_non_matrix != 0 && g1 != 0.0f);
+			if (t0) adam_one(a, i, g0, w32, w16, m1, m2, steps);
+			if (t1) adam_one(a, i + 1, g1, w32, w16, m1, m2, steps);
+			// EMA of the working weights -> inference weights (ema.h:63-77); every entry, every step
+			const __half2 w2 = *reinterpret_cast<const __half2*>(w16 + i);
+			const __half2 e2 = *reinterpret_cast<const __half2*>(ema + i);
+			const float f0 = (__low2float(e2) * a.ema_decay * a.ema_debias_old + __low2float(w2) * ema_w) * a.ema_debias_new;
+			const float f1 = (__high2float(e2) * a.ema_decay * a.ema_debias_old + __high2float(w2) * ema_w) * a.ema_debias_new;
+			*reinterpret_cast<__half2*>(ema + i) = __floats2half2_rn(f0, f1);
+		} else {
+			const float g0 = __half2float(grads[i]);
+			grads[i] = __float2half_rn(0.0f);
+			const bool t0 = (i < a.n_matrix) ? (a.optimize_matrix != 0) : (a.optimize_non_matrix != 0 && g0 != 0.0f);
+			if (t0) adam_one(a, i, g0, w32, w16, m1, m2, steps);
+			const float f0 = (__half2float(ema[i]) * a.ema_decay * a.ema_debias_old + __half2float(w16[i]) * ema_w) * a.ema_debias_new;
+			ema[i] = __float2half_rn(f0);
 		}
 	}
 }
@@ -113,8 +97,8 @@ void optimizer_step(const ngp_nerf_desc& d, cudaStream_t stream, const ngp_adam_
 	a.n_total = d.n_params;
 	a.optimize_matrix = cfg.optimize_matrix_params;
 	a.optimize_non_matrix = cfg.optimize_non_matrix_params;
-	const uint32_t n_threads = div_round_up(d.n_params, 8);
-	k_adam_ema<<<div_round_up(n_threads, 256), 256, 0, stream>>>(a, params_fp32, params_fp16, params_ema, grads, m1, m2, steps);
+	const uint32_t n_warps = div_round_up(d.n_params, 256);
+	k_adam_ema<<<div_round_up(n_warps * 32, 256), 256, 0, stream>>>(a, params_fp32, params_fp16, params_ema, grads, m1, m2, steps);
 	NGPB_LAUNCHED();
 	NGPB_CUDA_CHECK(cudaGetLastError());
 }

@@ -168,3 +168,50 @@ def test_backward_accumulates_and_is_linear_in_dloss(lib):
     a, b = g1.float().cpu().numpy()[: L.n_mlp_params], g2.float().cpu().numpy()[: L.n_mlp_params]
     assert np.isfinite(a).all() and np.isfinite(b).all() and np.abs(a).max() > 0
     assert np.abs(b - 2 * a).max() <= 2e-2 * np.abs(b).max()
+
+
+def test_optimizer_step_matches_oracle(lib):
+    """fused Adam + EMA + gradient zeroing against the oracle (which is itself pinned to the reference's adam_step / ema_step
+    outputs, tests/test_oracle_vs_reference_tcnn.py)"""
+    import torch
+
+    P = util.pkg()
+    d, L = util.make_desc(n_levels=16, F=2, log2_T=14, aabb_scale=1)
+    n = d.n_params
+    rng = np.random.default_rng(5)
+    w32 = util.random_params(L, seed=9, trained_like=True)
+    w16 = w32.astype(np.float16)
+    ema = w16.copy()
+    m1, m2, steps = np.zeros(n, np.float32), np.zeros(n, np.float32), np.zeros(n, np.uint32)
+    t = {k: dev(v) for k, v in dict(w32=w32, w16=w16, ema=ema, m1=m1, m2=m2, steps=steps.view(np.int32)).items()}
+    cfg = P.AdamCfg()
+    cfg.learning_rate, cfg.beta1, cfg.beta2, cfg.epsilon, cfg.l2_reg, cfg.loss_scale, cfg.ema_decay = 1e-2, 0.9, 0.99, 1e-15, 1e-6, 128.0, 0.95
+    cfg.optimize_matrix_params = cfg.optimize_non_matrix_params = 1
+    for step in (1, 2, 3):
+        g = (rng.normal(0, 1, size=n) * 0.05).astype(np.float16)
+        g[L.n_mlp_params:][rng.random(n - L.n_mlp_params) < 0.6] = 0  # sparse hash-grid gradients
+        if n % 2 == 0:
+            pass
+        t_g = dev(g)
+        cfg.ema_step = step
+        assert lib.ngp_optimizer_step(C.byref(d), stream(), C.byref(cfg), t["w32"].data_ptr(), t["w16"].data_ptr(), t["ema"].data_ptr(), t_g.data_ptr(),
+                                      t["m1"].data_ptr(), t["m2"].data_ptr(), t["steps"].data_ptr()) == 0, lib.ngp_last_error()
+        torch.cuda.synchronize()
+        go = g.copy()
+        O.adam_ema_step(L.n_mlp_params, w32, w16, ema, go, m1, m2, steps, lr=1e-2, beta1=0.9, beta2=0.99, eps=1e-15, l2_reg=1e-6, loss_scale=128.0,
+                        ema_decay=0.95, step=step)
+        assert (t_g == 0).all(), "gradients must be consumed (zeroed)"
+        gw32 = t["w32"].cpu().numpy()
+        assert np.abs(gw32 - w32).max() <= 2e-6 * np.abs(w32).max() + 1e-9
+        assert np.array_equal(t["steps"].cpu().numpy().view(np.uint32), steps)
+        assert np.abs(t["m1"].cpu().numpy() - m1).max() <= 1e-6 * (np.abs(m1).max() + 1e-12)
+        assert (t["w16"].cpu().numpy().view(np.uint16) != w16.view(np.uint16)).mean() < 2e-3
+        assert np.abs(t["ema"].cpu().numpy().astype(np.float32) - ema.astype(np.float32)).max() < 2e-3
+        # continue from the device state so that rounding differences do not compound
+        w32[:] = gw32
+        w16[:] = t["w16"].cpu().numpy()
+        ema[:] = t["ema"].cpu().numpy()
+        m1[:] = t["m1"].cpu().numpy()
+        m2[:] = t["m2"].cpu().numpy()
+    # untouched hash entries keep a zero step count (per-parameter bias correction, adam.h:109-113)
+    assert (steps[L.n_mlp_params:] < 3).any() and (steps[: L.n_mlp_params] == 3).all()
