@@ -132,6 +132,39 @@ __host__ __device__ inline uint32_t grid_index_3d(uint32_t x, uint32_t y, uint32
 	return index % size;
 }
 
+// The 8 corner indices of one level (corner c = x + 2y + 4z offsets, the order kernel_grid visits them) without an integer
+// division: `index % size` of grid_index (common_device.h:880) costs ~20 instructions per corner and was a third of all
+// instructions of the gather.  Hashed levels have a power-of-two size (checked in make_netdev), so the modulo is a mask and
+// the per-axis products are shared by the corners; dense levels have index <= res + res^2 + res^3 < 2*size whenever the
+// cell is inside the grid, so one conditional subtract is exact.  Cells outside [0, res) (positions outside the unit cube)
+// take the generic path, which keeps the wrap-around semantics of the reference bit for bit.
+__device__ __forceinline__ void level_corner_indices(const LevelMeta& lv, uint32_t gx, uint32_t gy, uint32_t gz, uint32_t (&idx)[8]) {
+	if (lv.dense) {
+		const uint32_t res = lv.resolution;
+		if (gx < res && gy < res && gz < res) {
+			const uint32_t r2 = res * res;
+			const uint32_t b = gx + gy * res + gz * r2;
+#pragma unroll
+			for (uint32_t c = 0; c < 8; ++c) {
+				uint32_t i = b + (c & 1u) + ((c & 2u) ? res : 0u) + ((c & 4u) ? r2 : 0u);
+				if (i >= lv.size) i -= lv.size;
+				idx[c] = i;
+			}
+		} else {
+#pragma unroll
+			for (uint32_t c = 0; c < 8; ++c) idx[c] = grid_index_3d(gx + (c & 1u), gy + ((c >> 1) & 1u), gz + ((c >> 2) & 1u), res, lv.size, true);
+		}
+	} else {
+		const uint32_t mask = lv.size - 1u;
+		const uint32_t hx[2] = {gx, gx + 1u};
+		const uint32_t hy0 = gy * 2654435761u, hz0 = gz * 805459861u;
+		const uint32_t hy[2] = {hy0, hy0 + 2654435761u};
+		const uint32_t hz[2] = {hz0, hz0 + 805459861u};
+#pragma unroll
+		for (uint32_t c = 0; c < 8; ++c) idx[c] = (hx[c & 1u] ^ hy[(c >> 1) & 1u] ^ hz[(c >> 2) & 1u]) & mask;
+	}
+}
+
 // Is a 3-D level stored densely?  grid_index (common_device.h:866-881): stride = res^3 when res <= 0x659, else
 // 0xFFFFFFFF; hashed iff size < stride.
 inline bool level_is_dense_3d(uint32_t resolution, uint32_t size) {

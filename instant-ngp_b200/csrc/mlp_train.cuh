@@ -1,0 +1,220 @@
+// mlp_train.cuh — device building blocks shared by the training kernels (k_nerf_train in nerf_net.cu, k_field_train in
+// field.cu): the two-threads-per-sample epilogues, forward-with-kept-activations, the backward chain with tcgen05 data- and
+// weight-gradient MMAs, and the half-of-the-levels hash-grid gather / scatter.
+#pragma once
+
+#include "nerf_net.cuh"
+
+namespace ngpb {
+
+// weight-gradient accumulator width (TMEM columns) of layer l: hidden layers hold dW [64(out) x K(in)] (K columns);
+// 16-wide output layers hold dW^T [64(in) x 16(out)] (16 columns).
+__host__ __device__ inline uint32_t wgrad_cols(uint32_t n_hidden, uint32_t l) { return l == n_hidden ? MLP_OUT : mlp_layer_in(n_hidden, l); }
+
+// ---- two threads per sample -------------------------------------------------------------------------------------------
+// The training CTA has 256 threads for its 128-sample tile: thread t and thread t+128 own the same sample (row t & 127,
+// TMEM lane t & 127 — warps w and w+4 address the same 32-lane TMEM window).  "half" h = t >> 7 selects which half of the
+// per-sample work a thread does: levels [h*L/2, (h+1)*L/2) of the gather / scatter, columns [32h, 32h+32) of every
+// 64-wide epilogue.  Same shared memory and TMEM per CTA as one thread per sample, twice the warps in flight per SM
+// (ncu of the one-thread version: 12 % warps active, latency bound; profiles/r1_kernels.md).
+constexpr uint32_t TRAIN_THREADS = 2 * TILE;
+
+// epilogue of a hidden layer for this thread's 32 columns: TMEM row -> ReLU -> fp16 -> operand buffer
+__device__ __forceinline__ void tmem_row_to_smem32_relu(uint32_t taddr_row, uint32_t half, uint8_t* buf, uint32_t row) {
+	uint32_t v0[16], v1[16];
+	umma::tmem_ld16(taddr_row + half * 32u + 0, v0);
+	umma::tmem_ld16(taddr_row + half * 32u + 16, v1);
+	umma::tmem_ld_wait();
+	auto emit = [&](const uint32_t(&v)[16], uint32_t kc0) {
+#pragma unroll
+		for (uint32_t c = 0; c < 2; ++c) {
+			__half2 h[4];
+#pragma unroll
+			for (uint32_t j = 0; j < 4; ++j) h[j] = relu2(__floats2half2_rn(__uint_as_float(v[c * 8 + 2 * j]), __uint_as_float(v[c * 8 + 2 * j + 1])));
+			store_chunk(buf, row, kc0 + c, h);
+		}
+	};
+	emit(v0, half * 4u + 0);
+	emit(v1, half * 4u + 2);
+}
+
+// forward of one MLP keeping every hidden activation: layer l writes hidden buffer l.  Returns the 16 outputs of the row.
+__device__ __forceinline__ void run_mlp_fwd_keep(
+	uint8_t* smem, uint32_t in_off, uint32_t hid_off, uint32_t w_off, uint32_t n_hidden, uint32_t tmem_base, uint64_t* bar, uint32_t& phase,
+	uint32_t tid, __half2 (&out)[8]
+) {
+	const uint32_t smem_base = umma::smem_u32(smem);
+	const uint32_t row = tid & (TILE - 1), half = tid >> 7;
+	const uint32_t lane_taddr = tmem_base + ((row & ~31u) << 16);
+	for (uint32_t l = 0; l <= n_hidden; ++l) {
+		const uint32_t K = mlp_layer_in(n_hidden, l), N = mlp_layer_out(n_hidden, l);
+		const uint32_t a_off = (l == 0) ? in_off : hid_off + (l - 1) * TILE * MLP_WIDTH * 2u;
+		umma::fence_smem_to_async();
+		umma::fence_before_sync();
+		__syncthreads();
+		if (tid == 0) {
+			umma::fence_after_sync();
+			issue_layer_fwd(smem_base + a_off, K, smem_base + w_off + mlp_layer_off(n_hidden, l) * 2u, N, tmem_base, bar);
+		}
+		umma::mbar_wait(bar, phase);
+		phase ^= 1u;
+		umma::fence_after_sync();
+		if (l < n_hidden) {
+			tmem_row_to_smem32_relu(lane_taddr, half, smem + hid_off + l * TILE * MLP_WIDTH * 2u, row);
+		} else {
+			tmem_row_to_regs16(lane_taddr, out);
+		}
+	}
+}
+
+// backward of one MLP.  On entry g16 holds dL/d(output) [128 x 16].  For every layer, weight gradient and data
+// gradient are issued back to back and waited for together.  Returns this thread's 16 columns [16*half, 16*half+16) of
+// dL/d(mlp input) (the MLP input is 32 wide).
+__device__ __forceinline__ void run_mlp_bwd(
+	uint8_t* smem, uint32_t in_off, uint32_t hid_off, uint32_t g64_off, uint32_t g16_off, uint32_t w_off, uint32_t n_hidden, uint32_t tmem_base,
+	uint32_t wg_col0, uint32_t wg_accumulate, uint64_t* bar, uint32_t& phase, uint32_t tid, float (&dx)[16]
+) {
+	const uint32_t smem_base = umma::smem_u32(smem);
+	const uint32_t row = tid & (TILE - 1), half = tid >> 7;
+	const uint32_t lane_taddr = tmem_base + ((row & ~31u) << 16);
+	for (int32_t l = (int32_t)n_hidden; l >= 0; --l) {
+		const uint32_t K = mlp_layer_in(n_hidden, l), N = mlp_layer_out(n_hidden, l);
+		const uint32_t x_off = (l == 0) ? in_off : hid_off + (l - 1) * TILE * MLP_WIDTH * 2u;
+		const uint32_t dy_off = ((uint32_t)l == n_hidden) ? g16_off : g64_off;
+		uint32_t wg_col = wg_col0;
+		for (int32_t i = 0; i < l; ++i) wg_col += wgrad_cols(n_hidden, (uint32_t)i);
+		umma::fence_smem_to_async();
+		umma::fence_before_sync();
+		__syncthreads();
+		if (tid == 0) {
+			umma::fence_after_sync();
+			if ((uint32_t)l == n_hidden) {
+				issue_wgrad(smem_base + x_off, MLP_WIDTH, smem_base + dy_off, MLP_OUT, tmem_base + wg_col, wg_accumulate);  // dW^T [in x out]
+			} else {
+				issue_wgrad(smem_base + dy_off, MLP_WIDTH, smem_base + x_off, K, tmem_base + wg_col, wg_accumulate);  // dW [out x in]
+			}
+			issue_layer_dgrad(smem_base + dy_off, N, smem_base + w_off + mlp_layer_off(n_hidden, l) * 2u, K, tmem_base, bar);
+		}
+		umma::mbar_wait(bar, phase);
+		phase ^= 1u;
+		umma::fence_after_sync();
+		if (l > 0) {
+			// dL/d(hidden l-1 pre-activation) = dX * (hidden_{l-1} > 0)  -> g64, this thread's 32 columns
+			uint32_t v0[16], v1[16];
+			umma::tmem_ld16(lane_taddr + half * 32u + 0, v0);
+			umma::tmem_ld16(lane_taddr + half * 32u + 16, v1);
+			umma::tmem_ld_wait();
+			const uint8_t* act = smem + x_off;
+			uint8_t* g = smem + g64_off;
+			auto emit = [&](const uint32_t(&v)[16], uint32_t kc0) {
+#pragma unroll
+				for (uint32_t c = 0; c < 2; ++c) {
+					const uint4 a = *reinterpret_cast<const uint4*>(act + (kc0 + c) * (TILE * 16u) + row * 16u);
+					const __half2 ah[4] = {*reinterpret_cast<const __half2*>(&a.x), *reinterpret_cast<const __half2*>(&a.y),
+						*reinterpret_cast<const __half2*>(&a.z), *reinterpret_cast<const __half2*>(&a.w)};
+					__half2 h[4];
+#pragma unroll
+					for (uint32_t j = 0; j < 4; ++j) {
+						const __half2 t = __floats2half2_rn(__uint_as_float(v[c * 8 + 2 * j]), __uint_as_float(v[c * 8 + 2 * j + 1]));
+						const __half2 m = __hgt2(ah[j], __float2half2_rn(0.0f));  // 1.0 where act > 0
+						h[j] = __hmul2(t, m);
+					}
+					store_chunk(g, row, kc0 + c, h);
+				}
+			};
+			emit(v0, half * 4u + 0);
+			emit(v1, half * 4u + 2);
+		} else {
+			uint32_t v0[16];
+			umma::tmem_ld16(lane_taddr + half * 16u, v0);
+			umma::tmem_ld_wait();
+#pragma unroll
+			for (uint32_t j = 0; j < 16; ++j) dx[j] = __uint_as_float(v0[j]);
+		}
+	}
+}
+
+// gather of HALF of the levels of one sample: 16 encoded features (8 half2) = chunks {2*half, 2*half+1} of the A0 row
+template <uint32_t F>
+__device__ __forceinline__ void grid_gather_half(const NetDev& net, const __half* __restrict__ grid, uint32_t half, float x, float y, float z, __half2 (&enc)[8]) {
+	constexpr uint32_t H2_PER_LEVEL = F / 2;
+	constexpr uint32_t LEVELS_PER_HALF = (ENC_WIDTH / F) / 2;
+#pragma unroll
+	for (uint32_t ll = 0; ll < LEVELS_PER_HALF; ++ll) {
+		const LevelMeta lv = net.levels[half * LEVELS_PER_HALF + ll];
+		const float px = fmaf(lv.scale, x, 0.5f), py = fmaf(lv.scale, y, 0.5f), pz = fmaf(lv.scale, z, 0.5f);
+		const float fx = floorf(px), fy = floorf(py), fz = floorf(pz);
+		const uint32_t gx = (uint32_t)(int)fx, gy = (uint32_t)(int)fy, gz = (uint32_t)(int)fz;
+		const float wx1 = px - fx, wy1 = py - fy, wz1 = pz - fz;
+		const float wx0 = 1.0f - wx1, wy0 = 1.0f - wy1, wz0 = 1.0f - wz1;
+		const __half* lgrid = grid + (size_t)lv.offset * F;
+		uint32_t idx[8];
+		level_corner_indices(lv, gx, gy, gz, idx);
+		if constexpr (F == 2) {
+			__half2 v[8];
+#pragma unroll
+			for (uint32_t c = 0; c < 8; ++c) v[c] = __ldg(reinterpret_cast<const __half2*>(lgrid) + idx[c]);
+			__half2 acc = __float2half2_rn(0.0f);
+#pragma unroll
+			for (uint32_t c = 0; c < 8; ++c) {
+				const float w = ((c & 1u) ? wx1 : wx0) * ((c & 2u) ? wy1 : wy0) * ((c & 4u) ? wz1 : wz0);
+				acc = __hfma2(__float2half2_rn(w), v[c], acc);
+			}
+			enc[ll] = acc;
+		} else {
+			uint2 v[8];
+#pragma unroll
+			for (uint32_t c = 0; c < 8; ++c) v[c] = __ldg(reinterpret_cast<const uint2*>(lgrid) + idx[c]);
+			__half2 a0 = __float2half2_rn(0.0f), a1 = a0;
+#pragma unroll
+			for (uint32_t c = 0; c < 8; ++c) {
+				const float w = ((c & 1u) ? wx1 : wx0) * ((c & 2u) ? wy1 : wy0) * ((c & 4u) ? wz1 : wz0);
+				const __half2 wh = __float2half2_rn(w);
+				a0 = __hfma2(wh, *reinterpret_cast<const __half2*>(&v[c].x), a0);
+				a1 = __hfma2(wh, *reinterpret_cast<const __half2*>(&v[c].y), a1);
+			}
+			enc[ll * H2_PER_LEVEL + 0] = a0;
+			enc[ll * H2_PER_LEVEL + 1] = a1;
+		}
+	}
+}
+
+// scatter dL/d(encoding) of HALF of the levels of one sample into the fp16 gradient table
+// (≙ kernel_grid_backward, grid.h:214-320: fp16 weight x fp16 gradient, red.global.add.f16x2 per corner).
+template <uint32_t F>
+__device__ __forceinline__ void grid_scatter_half(const NetDev& net, __half* __restrict__ grid_grad, uint32_t half, float x, float y, float z, const __half2 (&g)[8]) {
+	constexpr uint32_t H2_PER_LEVEL = F / 2;
+	constexpr uint32_t LEVELS_PER_HALF = (ENC_WIDTH / F) / 2;
+#pragma unroll 2
+	for (uint32_t ll = 0; ll < LEVELS_PER_HALF; ++ll) {
+		const LevelMeta lv = net.levels[half * LEVELS_PER_HALF + ll];
+		const float px = fmaf(lv.scale, x, 0.5f), py = fmaf(lv.scale, y, 0.5f), pz = fmaf(lv.scale, z, 0.5f);
+		const float fx = floorf(px), fy = floorf(py), fz = floorf(pz);
+		const uint32_t gx = (uint32_t)(int)fx, gy = (uint32_t)(int)fy, gz = (uint32_t)(int)fz;
+		const float wx1 = px - fx, wy1 = py - fy, wz1 = pz - fz;
+		const float wx0 = 1.0f - wx1, wy0 = 1.0f - wy1, wz0 = 1.0f - wz1;
+		__half2* lgrad = reinterpret_cast<__half2*>(grid_grad + (size_t)lv.offset * F);
+		uint32_t cidx[8];
+		level_corner_indices(lv, gx, gy, gz, cidx);
+#pragma unroll
+		for (uint32_t c = 0; c < 8; ++c) {
+			const uint32_t idx = cidx[c];
+			const float w = ((c & 1u) ? wx1 : wx0) * ((c & 2u) ? wy1 : wy0) * ((c & 4u) ? wz1 : wz0);
+			const __half2 wh = __float2half2_rn(w);
+			// fire-and-forget reductions.  NOT atomicAdd(__half2*): on a generic pointer that compiles to ATOM + predicate + retry
+			// branch (a full L2 round trip per corner, serialised per thread: 59 % of all stall samples, profiles/r1_kernels.md).
+			if constexpr (F == 2) {
+				const __half2 v = __hmul2(wh, g[ll]);
+				asm volatile("red.relaxed.gpu.global.add.noftz.f16x2 [%0], %1;" ::"l"(lgrad + idx), "r"(*reinterpret_cast<const uint32_t*>(&v)) : "memory");
+			} else {
+				const __half2 v0 = __hmul2(wh, g[ll * 2 + 0]), v1 = __hmul2(wh, g[ll * 2 + 1]);
+				asm volatile("red.relaxed.gpu.global.add.noftz.v2.f16x2 [%0], {%1, %2};" ::"l"(lgrad + (size_t)idx * 2), "r"(*reinterpret_cast<const uint32_t*>(&v0)),
+							 "r"(*reinterpret_cast<const uint32_t*>(&v1))
+							 : "memory");
+			}
+		}
+	}
+}
+
+
+}  // namespace ngpb

@@ -70,11 +70,7 @@ __device__ __forceinline__ void grid_gather(const NetDev& net, const __half* __r
 
 		// issue all 8 corner loads before using them
 		uint32_t idx[8];
-#pragma unroll
-		for (uint32_t c = 0; c < 8; ++c) {
-			const uint32_t cx = gx + (c & 1u), cy = gy + ((c >> 1) & 1u), cz = gz + ((c >> 2) & 1u);
-			idx[c] = grid_index_3d(cx, cy, cz, lv.resolution, lv.size, lv.dense != 0);
-		}
+		level_corner_indices(lv, gx, gy, gz, idx);
 		if constexpr (F == 2) {
 			__half2 v[8];
 #pragma unroll
@@ -239,7 +235,7 @@ __device__ __forceinline__ void tmem_row_to_regs16(uint32_t taddr_row, __half2 (
 // ----------------------------------------------------------------------------------------------------------------
 struct FwdSmem {
 	uint32_t w_bytes;   // all MLP weights
-	uint32_t a0_off;    // [128 x 32] encoded positions
+	uint32_t a0_off;    // [128 x 32] encoded positions (aliases h)
 	uint32_t h_off;     // [128 x 64] hidden activations
 	uint32_t a2_off;    // [128 x 32] rgb-net input: density-net output | SH
 	uint32_t bar_off;   // mbarrier (8 B) + tmem base (4 B)
@@ -248,8 +244,10 @@ struct FwdSmem {
 __host__ __device__ inline FwdSmem fwd_smem_layout(uint32_t n_hidden_density, uint32_t n_hidden_rgb) {
 	FwdSmem s;
 	s.w_bytes = (mlp_n_params(n_hidden_density) + mlp_n_params(n_hidden_rgb)) * 2u;
-	s.a0_off = s.w_bytes;
-	s.h_off = s.a0_off + TILE * ENC_WIDTH * 2u;
+	// A0 aliases the first half of H: a layer's epilogue writes H only after its MMA (the last reader of A0) has committed,
+	// and the next tile's gather writes A0 only after the last layer's commit.  44 KB per CTA -> 5 CTAs per SM.
+	s.h_off = s.w_bytes;
+	s.a0_off = s.h_off;
 	s.a2_off = s.h_off + TILE * MLP_WIDTH * 2u;
 	s.bar_off = s.a2_off + TILE * ENC_WIDTH * 2u;
 	s.total = s.bar_off + 16u;

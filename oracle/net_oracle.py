@@ -114,7 +114,8 @@ class NerfLayout:
 # hash grid
 # --------------------------------------------------------------------------------------------------------------------
 PRIMES = (np.uint32(1), np.uint32(2654435761), np.uint32(805459861))
-MAX_BASE_3D = 0x659
+MAX_BASES = {2: 0xFFFF, 3: 0x659}   # common_device.h:854-866, indexed by N_DIMS
+MAX_BASE_3D = MAX_BASES[3]
 
 
 def _fma32(a, b, c):
@@ -122,24 +123,32 @@ def _fma32(a, b, c):
     return (a.astype(np.float64) * b.astype(np.float64) + np.float64(c)).astype(F32)
 
 
-def _grid_index(g: GridLayout, level: int, cx, cy, cz):
+def _grid_index(g: GridLayout, level: int, *corner):
+    """grid_index<N_DIMS, CoherentPrime> (common_device.h:847-884) for N_DIMS = len(corner) in {2, 3}."""
+    D = len(corner)
     res = np.uint32(g.resolutions[level])
     size = np.uint32(g.offsets[level + 1] - g.offsets[level])
     with np.errstate(over="ignore"):
-        if int(res) <= MAX_BASE_3D:
-            stride = int(res) ** 3
-            index = cx + cy * res + cz * (res * res)
+        if int(res) <= MAX_BASES[D]:
+            stride = 1
+            index = np.zeros_like(corner[0])
+            for d in range(D):
+                index = index + corner[d] * np.uint32(stride & 0xFFFFFFFF)
+                stride *= int(res)
         else:
             stride = 0xFFFFFFFF
-            index = np.zeros_like(cx)
+            index = np.zeros_like(corner[0])
         if int(size) < stride:
-            index = (cx * PRIMES[0]) ^ (cy * PRIMES[1]) ^ (cz * PRIMES[2])
+            index = np.zeros_like(corner[0])
+            for d in range(D):
+                index = index ^ (corner[d] * PRIMES[d])
     return index % size
 
 
 def _level_setup(g: GridLayout, level: int, pos):
     scale = F32(g.scales[level])
-    p = [_fma32(np.full_like(pos[:, d], scale), pos[:, d], 0.5) for d in range(3)]
+    D = g.n_pos_dims
+    p = [_fma32(np.full_like(pos[:, d], scale), pos[:, d], 0.5) for d in range(D)]
     fl = [np.floor(q) for q in p]
     gi = [f.astype(np.int32).astype(np.uint32) for f in fl]
     w1 = [(q - f).astype(F32) for q, f in zip(p, fl)]
@@ -147,8 +156,19 @@ def _level_setup(g: GridLayout, level: int, pos):
     return gi, w0, w1
 
 
+def _corner(g, l, c, gi, w0, w1):
+    """index and fp32 weight of corner c (bit d of c = offset along axis d); weight product in axis order (grid.h:144-156)."""
+    D = g.n_pos_dims
+    bits = [(c >> d) & 1 for d in range(D)]
+    idx = _grid_index(g, l, *[gi[d] + np.uint32(bits[d]) for d in range(D)])
+    w = (w1[0] if bits[0] else w0[0])
+    for d in range(1, D):
+        w = (w * (w1[d] if bits[d] else w0[d])).astype(F32)
+    return idx, w.astype(F32)
+
+
 def grid_encode(g: GridLayout, grid_fp16: np.ndarray, pos: np.ndarray) -> np.ndarray:
-    """kernel_grid: returns [n, L*F] float16, bit-exact with fp16 fused multiply-adds in corner order 0..7."""
+    """kernel_grid: returns [n, L*F] float16, bit-exact with fp16 fused multiply-adds in corner order 0..2^D-1."""
     pos = np.ascontiguousarray(pos, dtype=F32)
     n = pos.shape[0]
     Fe = g.n_features
@@ -157,11 +177,8 @@ def grid_encode(g: GridLayout, grid_fp16: np.ndarray, pos: np.ndarray) -> np.nda
     for l in range(g.n_levels):
         gi, w0, w1 = _level_setup(g, l, pos)
         acc = np.zeros((n, Fe), dtype=np.float64)
-        for c in range(8):
-            bx, by, bz = c & 1, (c >> 1) & 1, (c >> 2) & 1
-            idx = _grid_index(g, l, gi[0] + np.uint32(bx), gi[1] + np.uint32(by), gi[2] + np.uint32(bz))
-            w = ((w1[0] if bx else w0[0]) * (w1[1] if by else w0[1])).astype(F32)
-            w = (w * (w1[2] if bz else w0[2])).astype(F32)
+        for c in range(1 << g.n_pos_dims):
+            idx, w = _corner(g, l, c, gi, w0, w1)
             wh = w.astype(F16).astype(np.float64)[:, None]
             val = table[g.offsets[l] + idx.astype(np.int64)].astype(np.float64)
             acc = (wh * val + acc).astype(F16).astype(np.float64)  # one fp16 rounding per fma
@@ -170,7 +187,7 @@ def grid_encode(g: GridLayout, grid_fp16: np.ndarray, pos: np.ndarray) -> np.nda
 
 
 def grid_backward(g: GridLayout, pos: np.ndarray, dL_denc: np.ndarray, accumulate_fp16: bool = False) -> np.ndarray:
-    """kernel_grid_backward: scatter (fp16)weight * (fp16)grad to the 8 corners.  Returns float64 sums of the fp16 products
+    """kernel_grid_backward: scatter (fp16)weight * (fp16)grad to the 2^D corners.  Returns float64 sums of the fp16 products
     (the reference accumulates them with fp16 atomics in arbitrary order; tests allow for that)."""
     pos = np.ascontiguousarray(pos, dtype=F32)
     Fe = g.n_features
@@ -179,11 +196,8 @@ def grid_backward(g: GridLayout, pos: np.ndarray, dL_denc: np.ndarray, accumulat
     for l in range(g.n_levels):
         gi, w0, w1 = _level_setup(g, l, pos)
         gl = dl[:, l * Fe:(l + 1) * Fe].astype(np.float64)
-        for c in range(8):
-            bx, by, bz = c & 1, (c >> 1) & 1, (c >> 2) & 1
-            idx = _grid_index(g, l, gi[0] + np.uint32(bx), gi[1] + np.uint32(by), gi[2] + np.uint32(bz))
-            w = ((w1[0] if bx else w0[0]) * (w1[1] if by else w0[1])).astype(F32)
-            w = (w * (w1[2] if bz else w0[2])).astype(F32)
+        for c in range(1 << g.n_pos_dims):
+            idx, w = _corner(g, l, c, gi, w0, w1)
             contrib = (w.astype(F16).astype(np.float64)[:, None] * gl).astype(F16).astype(np.float64)
             np.add.at(grad, g.offsets[l] + idx.astype(np.int64), contrib)
     return grad.reshape(-1)
