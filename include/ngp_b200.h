@@ -244,6 +244,61 @@ int ngp_nerf_render(const ngp_nerf_desc* d, void* stream, const ngp_render_cfg* 
 	const uint8_t* density_grid_bitfield, float* rgba, float* depth, void* scratch, uint32_t* n_steps_total_dev);
 
 /* ---------------------------------------------------------------------------------------------------------------
+ * B1 (fields) — NetworkWithInputEncoding: HashGrid over 2-D or 3-D positions + one FullyFusedMLP
+ * (tiny-cuda-nn/include/tiny-cuda-nn/network_with_input_encoding.h:38-170), the model of the image and SDF primitives
+ * (src/testbed_image.cu:231-302 train_image, src/testbed_sdf.cu:1578-1619 train_sdf).
+ *   pos[D] -HashGrid-> 32 -[64 x n_hidden, ReLU]-> 16 padded (n_output_dims used)
+ * Flat parameter order: MLP | hash grid (network_with_input_encoding.h:121-128); weights row-major [out x in].
+ * ------------------------------------------------------------------------------------------------------------- */
+typedef struct ngp_field_desc {
+	ngp_grid_desc grid;
+	uint32_t n_pos_dims;    /* 2 (image) or 3 (sdf) */
+	uint32_t n_hidden;      /* hidden layers of 64 neurons, 1..4 */
+	uint32_t n_output_dims; /* 1..16; output rows are padded to 16 like the reference (m_padded_output_width) */
+	uint32_t mlp_offset;    /* 0 */
+	uint32_t grid_offset;   /* = n_mlp_params */
+	uint32_t n_mlp_params;
+	uint32_t n_params;
+} ngp_field_desc;
+
+/* GridEncodingTemplated constructor (grid.h:673-737) for n_pos_dims in {2, 3}; per_level_scale must be > 0. */
+int ngp_grid_desc_init_nd(ngp_grid_desc* g, uint32_t n_pos_dims, uint32_t n_levels, uint32_t n_features_per_level, uint32_t log2_hashmap_size,
+	uint32_t base_resolution, float per_level_scale);
+int ngp_field_desc_init(ngp_field_desc* d, const ngp_grid_desc* g, uint32_t n_pos_dims, uint32_t n_hidden, uint32_t n_output_dims);
+/* Trainer::initialize_params for this model: MLP Xavier-uniform then grid U(-1e-4, 1e-4), one pcg32 stream. */
+int ngp_field_init_params_host(const ngp_field_desc* d, uint64_t seed, float* params_fp32_out);
+
+/* ≙ Module::inference (cpp_api.h:100): positions [n x n_pos_dims] float32 sample-contiguous -> out [n x out_stride] fp16
+ * (out_stride >= 16: the padded row; otherwise the first min(out_stride, n_output_dims) columns).  Any n. */
+int ngp_field_inference(const ngp_field_desc* d, void* stream, uint32_t n, const float* positions, const void* params_fp16, void* out, uint32_t out_stride);
+
+/* One fused forward + loss + backward kernel (≙ Trainer::training_step, trainer.h:163-357: forward, Loss::evaluate, backward).
+ * targets != NULL: [n x n_output_dims] float32, dL/dout from `loss_type` (tcnn losses/{l2,l1,mape,smape,relative_l2}.h) with
+ *   n_total = n * n_output_dims; loss_values (optional) [n x n_output_dims] float32 per-element loss terms (their sum is the loss).
+ * targets == NULL: dL_dout_ext [n x 16] fp16 is used instead (≙ the external dL/dy form, Module::backward cpp_api.h:108).
+ * grads: flat fp16 gradient buffer; hash-grid entries are ACCUMULATED (caller zeroes, or ngp_optimizer_step_flat does), MLP
+ * weights overwritten.  out (optional): [n x 16] fp16 network output.  n % 128 == 0 (the reference requires 256, common.h:246). */
+int ngp_field_train_step(const ngp_field_desc* d, void* stream, uint32_t n, const float* positions, const float* targets, uint32_t loss_type,
+	float loss_scale, const void* dL_dout_ext, const void* params_fp16, void* grads_fp16, float* loss_values, void* out);
+
+/* ≙ Loss<T>::evaluate (loss.h:44-60) for L2 / L1 / MAPE / SMAPE / RelativeL2: predictions [n x stride] fp16, targets
+ * [n x dims] float32 -> values [n x stride] float32, gradients [n x stride] fp16 (zero in the padding). */
+int ngp_loss_evaluate(void* stream, uint32_t loss_type, uint32_t n, uint32_t stride, uint32_t dims, float loss_scale, const void* predictions,
+	const float* targets, float* values, void* gradients);
+
+/* ≙ Trainer::optimizer_step (trainer.h:155) for any flat parameter vector: the first n_matrix_params entries are MLP weights. */
+int ngp_optimizer_step_flat(uint32_t n_matrix_params, uint32_t n_params, void* stream, const ngp_adam_cfg* cfg, float* params_fp32, void* params_fp16,
+	void* params_ema_fp16, void* grads_fp16, float* adam_m1, float* adam_m2, uint32_t* param_steps);
+
+/* ≙ train_image's data generation (src/testbed_image.cu:231-283): generate_random_uniform (random.h:40-67) of 2n floats from the
+ * pcg32 (rng_state, rng_inc), optional stratify2_kernel (:66-82, n must be 4^k), eval_image_kernel_and_snap (:176-229) on an
+ * RGBA image (image_type NGP_IMAGE_FLOAT or NGP_IMAGE_HALF, 4 channels, row-major).  positions [n x 2], targets [n x 3]. */
+int ngp_image_generate_training_data(void* stream, uint32_t n, uint64_t rng_state, uint64_t rng_inc, int stratify, const void* image, uint32_t image_type,
+	int32_t width, int32_t height, int snap_to_pixel_centers, int linear_colors, float* positions, float* targets);
+/* ≙ shuffle<T> (common_device.h:1097-1111): out[i] = in[permute(i / stride + seed, n_elements)] per member. */
+int ngp_shuffle(void* stream, uint32_t n_elements, uint32_t stride, uint32_t seed, const float* in, float* out);
+
+/* ---------------------------------------------------------------------------------------------------------------
  * B2 — Testbed handle (≙ pyngp.Testbed, src/python_api.cu:439-853; Testbed::train src/testbed.cu:4561-4647)
  * ------------------------------------------------------------------------------------------------------------- */
 typedef struct ngp_testbed ngp_testbed;
@@ -310,6 +365,38 @@ int ngp_testbed_get_phase_ms(ngp_testbed* t, float* ms_out, uint32_t* n_steps);
  * buffer, asynchronously on the Testbed stream (pinned memory makes the copy truly asynchronous). */
 int ngp_testbed_update_image_async(ngp_testbed* t, uint32_t idx, const float* rgba_host);
 /* number of kernel launches issued by this library since load (bench.py's gpu_launches). */
+/* ---------------------------------------------------------------------------------------------------------------
+ * B2 (fields) — Testbed(ETestbedMode::Image) and Testbed(ETestbedMode::Sdf) (common.h:149-155; python_api.cu:440-442):
+ * train_image (src/testbed_image.cu:231-302) and train_sdf on caller-provided records (override_sdf_training_data,
+ * python_api.cu:74-113,551; src/testbed_sdf.cu:1578-1619).  Mesh loading / BVH sampling of the SDF mode are out of scope.
+ * ------------------------------------------------------------------------------------------------------------- */
+typedef enum ngp_testbed_mode { NGP_MODE_NERF = 0, NGP_MODE_SDF = 1, NGP_MODE_IMAGE = 2 } ngp_testbed_mode;
+typedef struct ngp_field_testbed ngp_field_testbed;
+ngp_field_testbed* ngp_field_testbed_create(uint32_t mode, int device, void* stream);
+void ngp_field_testbed_destroy(ngp_field_testbed* t);
+/* image: w*h*4 float32 RGBA, linear colour (≙ load_image's EDataType::Float path, testbed_image.cu:420-470) */
+int ngp_field_testbed_set_image(ngp_field_testbed* t, const float* rgba_host, int32_t w, int32_t h);
+/* positions [n x 3] already in the unit cube, distances [n] (what override_sdf_training_data stores after its normalisation) */
+int ngp_field_testbed_set_sdf_training_data(ngp_field_testbed* t, const float* positions_host, const float* distances_host, uint32_t n);
+int ngp_field_testbed_reload_network_from_json(ngp_field_testbed* t, const char* json_text);
+int ngp_field_testbed_set_seed(ngp_field_testbed* t, uint64_t seed);
+/* options: image.training.snap_to_pixel_centers, image.training.linear_colors, image.random_mode_stratified, train_network,
+ * train_encoding, loss_scale */
+int ngp_field_testbed_set_option(ngp_field_testbed* t, const char* name, double value);
+int ngp_field_testbed_train(ngp_field_testbed* t, uint32_t batch_size);
+float ngp_field_testbed_loss(const ngp_field_testbed* t);
+uint32_t ngp_field_testbed_training_step(const ngp_field_testbed* t);
+size_t ngp_field_testbed_n_params(const ngp_field_testbed* t);
+int ngp_field_testbed_get_desc(const ngp_field_testbed* t, ngp_field_desc* out);
+void* ngp_field_testbed_params(ngp_field_testbed* t);           /* device fp16 */
+void* ngp_field_testbed_params_inference(ngp_field_testbed* t); /* device fp16 (EMA weights) */
+void* ngp_field_testbed_grads(ngp_field_testbed* t);            /* device fp16 */
+int ngp_field_testbed_set_params_fp32(ngp_field_testbed* t, const float* params_host, size_t n);
+int ngp_field_testbed_get_params_fp16(ngp_field_testbed* t, void* params_host, size_t n, int inference);
+int ngp_field_testbed_evaluate(ngp_field_testbed* t, const float* positions_host, uint32_t n, float* out_host);
+int ngp_field_testbed_render_image(ngp_field_testbed* t, int32_t w, int32_t h, float* rgba_host);
+int ngp_field_testbed_sync(ngp_field_testbed* t);
+
 uint64_t ngp_launch_count(void);
 
 #ifdef __cplusplus

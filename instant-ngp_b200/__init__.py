@@ -10,6 +10,7 @@ from __future__ import annotations
 from .binding import (  # noqa: F401
     LIB_PATH,
     AdamCfg,
+    FieldDesc,
     GridDesc,
     MarchConsts,
     NerfCounters,
@@ -23,6 +24,7 @@ from .binding import (  # noqa: F401
 )
 from .pyngp import (  # noqa: F401
     ColorSpace,
+    FieldTestbed,
     LossType,
     NerfActivation,
     Testbed,

@@ -42,6 +42,19 @@ class NerfDesc(C.Structure):
     ]
 
 
+class FieldDesc(C.Structure):
+    _fields_ = [
+        ("grid", GridDesc),
+        ("n_pos_dims", C.c_uint32),
+        ("n_hidden", C.c_uint32),
+        ("n_output_dims", C.c_uint32),
+        ("mlp_offset", C.c_uint32),
+        ("grid_offset", C.c_uint32),
+        ("n_mlp_params", C.c_uint32),
+        ("n_params", C.c_uint32),
+    ]
+
+
 class TrainView(C.Structure):
     _fields_ = [
         ("pixels", C.c_void_p),
@@ -188,6 +201,36 @@ PROTOTYPES = {
     "ngp_testbed_set_profiling": (C.c_int, [vp, C.c_int]),
     "ngp_testbed_get_phase_ms": (C.c_int, [vp, P(f32), P(u32)]),
     "ngp_testbed_update_image_async": (C.c_int, [vp, u32, vp]),
+    # fields (image / SDF primitives)
+    "ngp_grid_desc_init_nd": (C.c_int, [P(GridDesc), u32, u32, u32, u32, u32, f32]),
+    "ngp_field_desc_init": (C.c_int, [P(FieldDesc), P(GridDesc), u32, u32, u32]),
+    "ngp_field_init_params_host": (C.c_int, [P(FieldDesc), u64, vp]),
+    "ngp_field_inference": (C.c_int, [P(FieldDesc), vp, u32, vp, vp, vp, u32]),
+    "ngp_field_train_step": (C.c_int, [P(FieldDesc), vp, u32, vp, vp, u32, f32, vp, vp, vp, vp, vp]),
+    "ngp_loss_evaluate": (C.c_int, [vp, u32, u32, u32, u32, f32, vp, vp, vp, vp]),
+    "ngp_optimizer_step_flat": (C.c_int, [u32, u32, vp, P(AdamCfg), vp, vp, vp, vp, vp, vp, vp]),
+    "ngp_image_generate_training_data": (C.c_int, [vp, u32, u64, u64, C.c_int, vp, u32, i32, i32, C.c_int, C.c_int, vp, vp]),
+    "ngp_shuffle": (C.c_int, [vp, u32, u32, u32, vp, vp]),
+    "ngp_field_testbed_create": (vp, [u32, C.c_int, vp]),
+    "ngp_field_testbed_destroy": (None, [vp]),
+    "ngp_field_testbed_set_image": (C.c_int, [vp, vp, i32, i32]),
+    "ngp_field_testbed_set_sdf_training_data": (C.c_int, [vp, vp, vp, u32]),
+    "ngp_field_testbed_reload_network_from_json": (C.c_int, [vp, cp]),
+    "ngp_field_testbed_set_seed": (C.c_int, [vp, u64]),
+    "ngp_field_testbed_set_option": (C.c_int, [vp, cp, C.c_double]),
+    "ngp_field_testbed_train": (C.c_int, [vp, u32]),
+    "ngp_field_testbed_loss": (f32, [vp]),
+    "ngp_field_testbed_training_step": (u32, [vp]),
+    "ngp_field_testbed_n_params": (C.c_size_t, [vp]),
+    "ngp_field_testbed_get_desc": (C.c_int, [vp, P(FieldDesc)]),
+    "ngp_field_testbed_params": (vp, [vp]),
+    "ngp_field_testbed_params_inference": (vp, [vp]),
+    "ngp_field_testbed_grads": (vp, [vp]),
+    "ngp_field_testbed_set_params_fp32": (C.c_int, [vp, vp, C.c_size_t]),
+    "ngp_field_testbed_get_params_fp16": (C.c_int, [vp, vp, C.c_size_t, C.c_int]),
+    "ngp_field_testbed_evaluate": (C.c_int, [vp, vp, u32, vp]),
+    "ngp_field_testbed_render_image": (C.c_int, [vp, i32, i32, vp]),
+    "ngp_field_testbed_sync": (C.c_int, [vp]),
 }
 
 _lib = None

@@ -30,6 +30,7 @@ UNITS = {
     "testbed.cu": ["-fmad=false"],
     "march.cu": ["-fmad=false"],
     "render.cu": ["-fmad=false"],
+    "field.cu": ["-fmad=false"],
 }
 
 

@@ -38,17 +38,18 @@ __device__ __forceinline__ void tmem_row_to_smem32_relu(uint32_t taddr_row, uint
 	emit(v1, half * 4u + 2);
 }
 
-// forward of one MLP keeping every hidden activation: layer l writes hidden buffer l.  Returns the 16 outputs of the row.
+// forward of one MLP keeping every hidden activation: layer l writes hidden buffer l (buffers `hid_stride` bytes apart;
+// 0 = inference, every layer overwrites the same buffer once its MMA has read it).  Returns the 16 outputs of the row.
 __device__ __forceinline__ void run_mlp_fwd_keep(
 	uint8_t* smem, uint32_t in_off, uint32_t hid_off, uint32_t w_off, uint32_t n_hidden, uint32_t tmem_base, uint64_t* bar, uint32_t& phase,
-	uint32_t tid, __half2 (&out)[8]
+	uint32_t tid, __half2 (&out)[8], uint32_t hid_stride = TILE * MLP_WIDTH * 2u
 ) {
 	const uint32_t smem_base = umma::smem_u32(smem);
 	const uint32_t row = tid & (TILE - 1), half = tid >> 7;
 	const uint32_t lane_taddr = tmem_base + ((row & ~31u) << 16);
 	for (uint32_t l = 0; l <= n_hidden; ++l) {
 		const uint32_t K = mlp_layer_in(n_hidden, l), N = mlp_layer_out(n_hidden, l);
-		const uint32_t a_off = (l == 0) ? in_off : hid_off + (l - 1) * TILE * MLP_WIDTH * 2u;
+		const uint32_t a_off = (l == 0) ? in_off : hid_off + (l - 1) * hid_stride;
 		umma::fence_smem_to_async();
 		umma::fence_before_sync();
 		__syncthreads();
@@ -60,7 +61,7 @@ __device__ __forceinline__ void run_mlp_fwd_keep(
 		phase ^= 1u;
 		umma::fence_after_sync();
 		if (l < n_hidden) {
-			tmem_row_to_smem32_relu(lane_taddr, half, smem + hid_off + l * TILE * MLP_WIDTH * 2u, row);
+			tmem_row_to_smem32_relu(lane_taddr, half, smem + hid_off + l * hid_stride, row);
 		} else {
 			tmem_row_to_regs16(lane_taddr, out);
 		}
@@ -134,42 +135,89 @@ __device__ __forceinline__ void run_mlp_bwd(
 	}
 }
 
-// gather of HALF of the levels of one sample: 16 encoded features (8 half2) = chunks {2*half, 2*half+1} of the A0 row
-template <uint32_t F>
-__device__ __forceinline__ void grid_gather_half(const NetDev& net, const __half* __restrict__ grid, uint32_t half, float x, float y, float z, __half2 (&enc)[8]) {
+// 2-D variant of level_corner_indices (common.cuh): corner c = x + 2y.  grid_index<2> (common_device.h:847-884): dense
+// iff res <= 0xFFFF and size >= res^2; hash = x ^ y * 2654435761.
+__device__ __forceinline__ void level_corner_indices_2d(const LevelMeta& lv, uint32_t gx, uint32_t gy, uint32_t (&idx)[4]) {
+	if (lv.dense) {
+		const uint32_t res = lv.resolution;
+		if (gx < res && gy < res) {
+			const uint32_t b = gx + gy * res;
+#pragma unroll
+			for (uint32_t c = 0; c < 4; ++c) {
+				uint32_t i = b + (c & 1u) + ((c & 2u) ? res : 0u);
+				if (i >= lv.size) i -= lv.size;
+				idx[c] = i;
+			}
+		} else {
+#pragma unroll
+			for (uint32_t c = 0; c < 4; ++c) idx[c] = ((gx + (c & 1u)) + (gy + (c >> 1)) * res) % lv.size;
+		}
+	} else {
+		const uint32_t mask = lv.size - 1u;
+		const uint32_t hy0 = gy * 2654435761u;
+		const uint32_t hy[2] = {hy0, hy0 + 2654435761u};
+#pragma unroll
+		for (uint32_t c = 0; c < 4; ++c) idx[c] = ((gx + (c & 1u)) ^ hy[c >> 1]) & mask;
+	}
+}
+
+// per-level cell + interpolation weights of a D-dimensional position (kernel_grid, grid.h:95-110: pos_fract)
+template <uint32_t D>
+struct LevelCell {
+	uint32_t g[D];
+	float w0[D], w1[D];
+	__device__ __forceinline__ LevelCell(const LevelMeta& lv, const float (&x)[D]) {
+#pragma unroll
+		for (uint32_t d = 0; d < D; ++d) {
+			const float p = fmaf(lv.scale, x[d], 0.5f);
+			const float f = floorf(p);
+			g[d] = (uint32_t)(int)f;
+			w1[d] = p - f;
+			w0[d] = 1.0f - w1[d];
+		}
+	}
+	__device__ __forceinline__ float weight(uint32_t c) const {
+		float w = (c & 1u) ? w1[0] : w0[0];
+#pragma unroll
+		for (uint32_t d = 1; d < D; ++d) w *= ((c >> d) & 1u) ? w1[d] : w0[d];
+		return w;
+	}
+	__device__ __forceinline__ void corners(const LevelMeta& lv, uint32_t (&idx)[1u << D]) const {
+		if constexpr (D == 3) level_corner_indices(lv, g[0], g[1], g[2], idx);
+		else level_corner_indices_2d(lv, g[0], g[1], idx);
+	}
+};
+
+// gather of HALF of the levels of one sample: 16 encoded features (8 half2) = chunks {2*half, 2*half+1} of the A0 row.
+// NET is any struct with a `levels` table (NetDev, FieldDev).
+template <uint32_t F, uint32_t D, typename NET>
+__device__ __forceinline__ void grid_gather_half_nd(const NET& net, const __half* __restrict__ grid, uint32_t half, const float (&x)[D], __half2 (&enc)[8]) {
 	constexpr uint32_t H2_PER_LEVEL = F / 2;
 	constexpr uint32_t LEVELS_PER_HALF = (ENC_WIDTH / F) / 2;
+	constexpr uint32_t NC = 1u << D;
 #pragma unroll
 	for (uint32_t ll = 0; ll < LEVELS_PER_HALF; ++ll) {
 		const LevelMeta lv = net.levels[half * LEVELS_PER_HALF + ll];
-		const float px = fmaf(lv.scale, x, 0.5f), py = fmaf(lv.scale, y, 0.5f), pz = fmaf(lv.scale, z, 0.5f);
-		const float fx = floorf(px), fy = floorf(py), fz = floorf(pz);
-		const uint32_t gx = (uint32_t)(int)fx, gy = (uint32_t)(int)fy, gz = (uint32_t)(int)fz;
-		const float wx1 = px - fx, wy1 = py - fy, wz1 = pz - fz;
-		const float wx0 = 1.0f - wx1, wy0 = 1.0f - wy1, wz0 = 1.0f - wz1;
+		const LevelCell<D> cell(lv, x);
 		const __half* lgrid = grid + (size_t)lv.offset * F;
-		uint32_t idx[8];
-		level_corner_indices(lv, gx, gy, gz, idx);
+		uint32_t idx[NC];
+		cell.corners(lv, idx);
 		if constexpr (F == 2) {
-			__half2 v[8];
+			__half2 v[NC];
 #pragma unroll
-			for (uint32_t c = 0; c < 8; ++c) v[c] = __ldg(reinterpret_cast<const __half2*>(lgrid) + idx[c]);
+			for (uint32_t c = 0; c < NC; ++c) v[c] = __ldg(reinterpret_cast<const __half2*>(lgrid) + idx[c]);
 			__half2 acc = __float2half2_rn(0.0f);
 #pragma unroll
-			for (uint32_t c = 0; c < 8; ++c) {
-				const float w = ((c & 1u) ? wx1 : wx0) * ((c & 2u) ? wy1 : wy0) * ((c & 4u) ? wz1 : wz0);
-				acc = __hfma2(__float2half2_rn(w), v[c], acc);
-			}
+			for (uint32_t c = 0; c < NC; ++c) acc = __hfma2(__float2half2_rn(cell.weight(c)), v[c], acc);
 			enc[ll] = acc;
 		} else {
-			uint2 v[8];
+			uint2 v[NC];
 #pragma unroll
-			for (uint32_t c = 0; c < 8; ++c) v[c] = __ldg(reinterpret_cast<const uint2*>(lgrid) + idx[c]);
+			for (uint32_t c = 0; c < NC; ++c) v[c] = __ldg(reinterpret_cast<const uint2*>(lgrid) + idx[c]);
 			__half2 a0 = __float2half2_rn(0.0f), a1 = a0;
 #pragma unroll
-			for (uint32_t c = 0; c < 8; ++c) {
-				const float w = ((c & 1u) ? wx1 : wx0) * ((c & 2u) ? wy1 : wy0) * ((c & 4u) ? wz1 : wz0);
-				const __half2 wh = __float2half2_rn(w);
+			for (uint32_t c = 0; c < NC; ++c) {
+				const __half2 wh = __float2half2_rn(cell.weight(c));
 				a0 = __hfma2(wh, *reinterpret_cast<const __half2*>(&v[c].x), a0);
 				a1 = __hfma2(wh, *reinterpret_cast<const __half2*>(&v[c].y), a1);
 			}
@@ -181,26 +229,21 @@ __device__ __forceinline__ void grid_gather_half(const NetDev& net, const __half
 
 // scatter dL/d(encoding) of HALF of the levels of one sample into the fp16 gradient table
 // (≙ kernel_grid_backward, grid.h:214-320: fp16 weight x fp16 gradient, red.global.add.f16x2 per corner).
-template <uint32_t F>
-__device__ __forceinline__ void grid_scatter_half(const NetDev& net, __half* __restrict__ grid_grad, uint32_t half, float x, float y, float z, const __half2 (&g)[8]) {
-	constexpr uint32_t H2_PER_LEVEL = F / 2;
+template <uint32_t F, uint32_t D, typename NET>
+__device__ __forceinline__ void grid_scatter_half_nd(const NET& net, __half* __restrict__ grid_grad, uint32_t half, const float (&x)[D], const __half2 (&g)[8]) {
 	constexpr uint32_t LEVELS_PER_HALF = (ENC_WIDTH / F) / 2;
+	constexpr uint32_t NC = 1u << D;
 #pragma unroll 2
 	for (uint32_t ll = 0; ll < LEVELS_PER_HALF; ++ll) {
 		const LevelMeta lv = net.levels[half * LEVELS_PER_HALF + ll];
-		const float px = fmaf(lv.scale, x, 0.5f), py = fmaf(lv.scale, y, 0.5f), pz = fmaf(lv.scale, z, 0.5f);
-		const float fx = floorf(px), fy = floorf(py), fz = floorf(pz);
-		const uint32_t gx = (uint32_t)(int)fx, gy = (uint32_t)(int)fy, gz = (uint32_t)(int)fz;
-		const float wx1 = px - fx, wy1 = py - fy, wz1 = pz - fz;
-		const float wx0 = 1.0f - wx1, wy0 = 1.0f - wy1, wz0 = 1.0f - wz1;
+		const LevelCell<D> cell(lv, x);
 		__half2* lgrad = reinterpret_cast<__half2*>(grid_grad + (size_t)lv.offset * F);
-		uint32_t cidx[8];
-		level_corner_indices(lv, gx, gy, gz, cidx);
+		uint32_t cidx[NC];
+		cell.corners(lv, cidx);
 #pragma unroll
-		for (uint32_t c = 0; c < 8; ++c) {
+		for (uint32_t c = 0; c < NC; ++c) {
 			const uint32_t idx = cidx[c];
-			const float w = ((c & 1u) ? wx1 : wx0) * ((c & 2u) ? wy1 : wy0) * ((c & 4u) ? wz1 : wz0);
-			const __half2 wh = __float2half2_rn(w);
+			const __half2 wh = __float2half2_rn(cell.weight(c));
 			// fire-and-forget reductions.  NOT atomicAdd(__half2*): on a generic pointer that compiles to ATOM + predicate + retry
 			// branch (a full L2 round trip per corner, serialised per thread: 59 % of all stall samples, profiles/r1_kernels.md).
 			if constexpr (F == 2) {
@@ -216,5 +259,15 @@ __device__ __forceinline__ void grid_scatter_half(const NetDev& net, __half* __r
 	}
 }
 
+template <uint32_t F>
+__device__ __forceinline__ void grid_gather_half(const NetDev& net, const __half* __restrict__ grid, uint32_t half, float x, float y, float z, __half2 (&enc)[8]) {
+	const float p[3] = {x, y, z};
+	grid_gather_half_nd<F, 3>(net, grid, half, p, enc);
+}
+template <uint32_t F>
+__device__ __forceinline__ void grid_scatter_half(const NetDev& net, __half* __restrict__ grid_grad, uint32_t half, float x, float y, float z, const __half2 (&g)[8]) {
+	const float p[3] = {x, y, z};
+	grid_scatter_half_nd<F, 3>(net, grid_grad, half, p, g);
+}
 
 }  // namespace ngpb

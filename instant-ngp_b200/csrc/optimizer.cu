@@ -116,8 +116,9 @@ __global__ void __launch_bounds__(256) k_adam_ema(const AdamDev a, float* __rest
 	}
 }
 
-void optimizer_step(const ngp_nerf_desc& d, cudaStream_t stream, const ngp_adam_cfg& cfg, float* params_fp32, __half* params_fp16, __half* params_ema,
-	__half* grads, float* m1, float* m2, uint32_t* steps) {
+// n_matrix_params leading "matrix" parameters (MLP weights: L2-regularised, always stepped), the rest are hash-grid entries
+void optimizer_step_flat(uint32_t n_matrix_params, uint32_t n_params, cudaStream_t stream, const ngp_adam_cfg& cfg, float* params_fp32, __half* params_fp16,
+	__half* params_ema, __half* grads, float* m1, float* m2, uint32_t* steps) {
 	NGPB_CHECK(cfg.ema_step >= 1, "ngp_optimizer_step: ema_step is 1-based");
 	AdamDev a;
 	a.lr = cfg.learning_rate;
@@ -131,14 +132,19 @@ void optimizer_step(const ngp_nerf_desc& d, cudaStream_t stream, const ngp_adam_
 	a.ema_decay = cfg.ema_decay;
 	a.ema_debias_old = 1.0f - (float)std::pow(cfg.ema_decay, (float)(cfg.ema_step - 1));
 	a.ema_debias_new = 1.0f / (1.0f - (float)std::pow(cfg.ema_decay, (float)cfg.ema_step));
-	a.n_matrix = d.n_mlp_params;
-	a.n_total = d.n_params;
+	a.n_matrix = n_matrix_params;
+	a.n_total = n_params;
 	a.optimize_matrix = cfg.optimize_matrix_params;
 	a.optimize_non_matrix = cfg.optimize_non_matrix_params;
-	const uint32_t n_warps = div_round_up(d.n_params, 64u * ADAM_ROWS);
+	const uint32_t n_warps = div_round_up(n_params, 64u * ADAM_ROWS);
 	k_adam_ema<<<div_round_up(n_warps * 32, 256), 256, 0, stream>>>(a, params_fp32, params_fp16, params_ema, grads, m1, m2, steps);
 	NGPB_LAUNCHED();
 	NGPB_CUDA_CHECK(cudaGetLastError());
+}
+
+void optimizer_step(const ngp_nerf_desc& d, cudaStream_t stream, const ngp_adam_cfg& cfg, float* params_fp32, __half* params_fp16, __half* params_ema,
+	__half* grads, float* m1, float* m2, uint32_t* steps) {
+	optimizer_step_flat(d.n_mlp_params, d.n_params, stream, cfg, params_fp32, params_fp16, params_ema, grads, m1, m2, steps);
 }
 
 }  // namespace ngpb

@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "host_util.h"
 #include "json_mini.h"
 #include "march.cuh"
 
@@ -156,44 +157,6 @@ void nerf_init_params_host(const ngp_nerf_desc* d, uint64_t seed, float* out) {
 		}
 	}
 }
-
-// ------------------------------------------------------------------------------------------------------------------
-// device memory helper
-// ------------------------------------------------------------------------------------------------------------------
-template <typename T>
-struct DevBuf {
-	T* p = nullptr;
-	size_t n = 0;
-	~DevBuf() { release(); }
-	void release() {
-		if (p) cudaFree(p);
-		p = nullptr;
-		n = 0;
-	}
-	void ensure(size_t count) {
-		if (count <= n) return;
-		release();
-		NGPB_CUDA_CHECK(cudaMalloc(&p, count * sizeof(T)));
-		n = count;
-	}
-	void ensure_zeroed(size_t count) {
-		const bool fresh = count > n;
-		ensure(count);
-		if (fresh) NGPB_CUDA_CHECK(cudaMemset(p, 0, n * sizeof(T)));
-	}
-};
-
-// ------------------------------------------------------------------------------------------------------------------
-// Testbed
-// ------------------------------------------------------------------------------------------------------------------
-struct OptimizerConfig {
-	float learning_rate = 1e-2f, beta1 = 0.9f, beta2 = 0.99f, epsilon = 1e-15f, l2_reg = 1e-6f;
-	float ema_decay = 0.95f;
-	bool has_ema = true;
-	bool has_decay = true;
-	uint32_t decay_start = 20000, decay_interval = 10000, decay_end = 10000000;
-	float decay_base = 0.33f;
-};
 
 }  // namespace ngpb
 
@@ -412,47 +375,9 @@ static void tb_reset_network(ngp_testbed* t, const Json& config) {
 	nerf_desc_init(&t->desc, &g, (uint32_t)net.value("n_hidden_layers", 1.0), (uint32_t)rgb.value("n_hidden_layers", 2.0));
 
 	// loss (string_to_loss_type) — NeRF bypasses tcnn's Loss object (src/testbed.cu:4208-4215)
-	const std::string lt = to_lower(loss.value("otype", std::string("L2")));
-	if (lt == "l2") t->cfg.loss_type = NGP_LOSS_L2;
-	else if (lt == "l1") t->cfg.loss_type = NGP_LOSS_L1;
-	else if (lt == "mape") t->cfg.loss_type = NGP_LOSS_MAPE;
-	else if (lt == "smape") t->cfg.loss_type = NGP_LOSS_SMAPE;
-	else if (lt == "huber") t->cfg.loss_type = NGP_LOSS_HUBER;
-	else if (lt == "logl1") t->cfg.loss_type = NGP_LOSS_LOGL1;
-	else if (lt == "relativel2") t->cfg.loss_type = NGP_LOSS_RELATIVE_L2;
-	else NGPB_CHECK(false, "loss.otype '" + lt + "' is not supported");
+	t->cfg.loss_type = parse_loss_type(loss);
 
-	// optimizer: Ema{ExponentialDecay{Adam}} or any suffix of that chain
-	t->opt = OptimizerConfig{};
-	t->opt.has_ema = false;
-	t->opt.has_decay = false;
-	t->opt.learning_rate = 1e-3f; t->opt.beta2 = 0.999f; t->opt.epsilon = 1e-8f; t->opt.l2_reg = 1e-8f;  // adam.h defaults
-	const Json* o = &config.sub("optimizer");
-	for (;;) {
-		const std::string ot = to_lower(o->value("otype", std::string("Adam")));
-		if (ot == "ema") {
-			t->opt.has_ema = true;
-			t->opt.ema_decay = (float)o->value("decay", 0.99);
-			NGPB_CHECK(!(o->contains("full_precision") && o->sub("full_precision").b), "Ema.full_precision is not supported");
-		} else if (ot == "exponentialdecay") {
-			t->opt.has_decay = true;
-			t->opt.decay_base = (float)o->value("decay_base", 0.1);
-			t->opt.decay_interval = (uint32_t)o->value("decay_interval", 10000.0);
-			t->opt.decay_start = (uint32_t)o->value("decay_start", 10000.0);
-			t->opt.decay_end = (uint32_t)o->value("decay_end", 10000000.0);
-		} else if (ot == "adam") {
-			t->opt.learning_rate = (float)o->value("learning_rate", 1e-3);
-			t->opt.beta1 = (float)o->value("beta1", 0.9);
-			t->opt.beta2 = (float)o->value("beta2", 0.999);
-			t->opt.epsilon = (float)o->value("epsilon", 1e-8);
-			t->opt.l2_reg = (float)o->value("l2_reg", 1e-8);
-			break;
-		} else {
-			NGPB_CHECK(false, "optimizer.otype '" + ot + "' is not supported (Ema / ExponentialDecay / Adam)");
-		}
-		NGPB_CHECK(o->contains("nested"), "optimizer: missing nested");
-		o = &o->sub("nested");
-	}
+	t->opt = parse_optimizer_chain(config.sub("optimizer"));
 
 	t->has_network = true;
 	tb_alloc_network(t);
@@ -671,24 +596,7 @@ static void tb_apply_grads(ngp_testbed* t) {
 		NGPB_CUDA_CHECK(cudaMemcpyAsync(&t->readback->counters, t->dp_counters.p, sizeof(ngp_nerf_counters), cudaMemcpyDeviceToHost, t->stream));
 		NGPB_CUDA_CHECK(cudaEventRecord(t->ev_front_done, t->stream));
 	}
-	// ExponentialDecayOptimizer::step (exponential_decay.h:60-72)
-	if (t->optimizer_step == 0) t->lr_factor = 1.0f;
-	if (t->opt.has_decay && t->optimizer_step >= t->opt.decay_start && (t->optimizer_step - t->opt.decay_start) % t->opt.decay_interval == 0 &&
-		t->optimizer_step <= t->opt.decay_end) {
-		t->lr_factor *= t->opt.decay_base;
-	}
-	++t->optimizer_step;
-	ngp_adam_cfg a{};
-	a.learning_rate = t->opt.learning_rate * t->lr_factor;
-	a.beta1 = t->opt.beta1;
-	a.beta2 = t->opt.beta2;
-	a.epsilon = t->opt.epsilon;
-	a.l2_reg = t->opt.l2_reg;
-	a.loss_scale = t->cfg.loss_scale;
-	a.ema_decay = t->opt.has_ema ? t->opt.ema_decay : 0.0f;
-	a.ema_step = t->optimizer_step;
-	a.optimize_matrix_params = t->train_network;
-	a.optimize_non_matrix_params = t->train_encoding;
+	const ngp_adam_cfg a = next_adam_cfg(t->opt, t->optimizer_step, t->lr_factor, t->cfg.loss_scale, t->train_network, t->train_encoding);
 	{
 		PhaseTimer pt(t, 5);
 		optimizer_step(t->desc, t->stream, a, t->params_fp32.p, t->params.p, t->params_ema.p, t->grads.p, t->m1.p, t->m2.p, t->param_steps.p);
@@ -755,15 +663,6 @@ static void tb_apply_grads(ngp_testbed* t) {
 // ------------------------------------------------------------------------------------------------------------------
 // extern "C"
 // ------------------------------------------------------------------------------------------------------------------
-#define NGPB_TRY(...)                      \
-	try {                                    \
-		__VA_ARGS__;                           \
-		return 0;                              \
-	} catch (const std::exception& e) {      \
-		ngpb::set_last_error(e.what());        \
-		return 1;                              \
-	}
-
 extern "C" {
 
 const char* ngp_last_error(void) { return g_last_error.c_str(); }
@@ -785,7 +684,6 @@ int ngp_nerf_desc_init(ngp_nerf_desc* d, const ngp_grid_desc* g, uint32_t nhd, u
 int ngp_march_consts_init(ngp_march_consts* m, float cone_angle) { NGPB_TRY(march_consts_init(m, cone_angle)); }
 int ngp_nerf_init_params_host(const ngp_nerf_desc* d, uint64_t seed, float* out) { NGPB_TRY(nerf_init_params_host(d, seed, out)); }
 
-static void require_device() { NGPB_CHECK(ngp_device_count() > 0, "no CUDA device: libngp_b200 has no CPU fallback"); }
 
 int ngp_nerf_inference(const ngp_nerf_desc* d, void* stream, uint32_t n, const float* coords, const void* params, void* out, uint32_t out_stride) {
 	NGPB_TRY(require_device(); nerf_inference(*d, (cudaStream_t)stream, n, coords, (const __half*)params, (__half*)out, out_stride));

@@ -120,19 +120,179 @@ class _Nerf:
         self._tb._set("nerf.density_activation", float(int(v)))
 
 
+def _default_stream(device: int) -> int:
+    try:  # run on torch's current stream when torch drives the process (bench / DP); plain default stream otherwise
+        import torch
+
+        return torch.cuda.current_stream(device).cuda_stream if torch.cuda.is_available() else 0
+    except Exception:  # pragma: no cover
+        return 0
+
+
+class _ImageTraining:
+    """``testbed.image.training`` (python_api.cu:755-765)."""
+
+    def __init__(self, tb: "FieldTestbed"):
+        self._tb = tb
+        self._snap, self._linear = False, False
+
+    @property
+    def snap_to_pixel_centers(self) -> bool:
+        return self._snap
+
+    @snap_to_pixel_centers.setter
+    def snap_to_pixel_centers(self, v) -> None:
+        self._snap = bool(v)
+        self._tb._set("image.training.snap_to_pixel_centers", float(self._snap))
+
+    @property
+    def linear_colors(self) -> bool:
+        return self._linear
+
+    @linear_colors.setter
+    def linear_colors(self, v) -> None:
+        self._linear = bool(v)
+        self._tb._set("image.training.linear_colors", float(self._linear))
+
+
+class _Image:
+    def __init__(self, tb: "FieldTestbed"):
+        self.training = _ImageTraining(tb)
+
+
+class FieldTestbed:
+    """``pyngp.Testbed(TestbedMode.Image)`` / ``(TestbedMode.Sdf)``: the image and SDF primitives (train_image,
+    src/testbed_image.cu:231-302; train_sdf on caller-provided records, src/testbed_sdf.cu:1578-1619)."""
+
+    def __init__(self, mode: TestbedMode, device: int = 0, stream: int | None = None):
+        if mode not in (TestbedMode.Image, TestbedMode.Sdf):
+            raise B.NgpError("FieldTestbed: mode must be Image or Sdf")
+        self.mode = TestbedMode(mode)
+        if stream is None:
+            stream = _default_stream(device)
+        self._h = B.lib().ngp_field_testbed_create(int(mode), device, C.c_void_p(stream))
+        if not self._h:
+            raise B.NgpError(B.lib().ngp_last_error().decode())
+        self.image = _Image(self)
+        self.training_batch_size = 1 << 18  # testbed.h:1089
+        self.shall_train = True
+        self.root_dir = ""
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            try:
+                B.lib().ngp_field_testbed_destroy(h)
+            except Exception:  # pragma: no cover
+                pass
+
+    def _set(self, name: str, value: float) -> None:
+        B.check(B.lib().ngp_field_testbed_set_option(self._h, name.encode(), float(value)))
+
+    # -- data ------------------------------------------------------------------------------------------------------
+    def set_image(self, img: np.ndarray) -> None:
+        """[H, W, 4] (or [H, W, 3]) float32 linear colour — what load_image leaves in m_image.data for a float image."""
+        a = np.asarray(img, dtype=np.float32)
+        if a.ndim != 3 or a.shape[2] not in (3, 4):
+            raise B.NgpError("set_image: expected [H, W, 3|4]")
+        if a.shape[2] == 3:
+            a = np.concatenate([a, np.ones(a.shape[:2] + (1,), np.float32)], axis=2)
+        a = np.ascontiguousarray(a)
+        B.check(B.lib().ngp_field_testbed_set_image(self._h, a.ctypes.data_as(C.c_void_p), a.shape[1], a.shape[0]))
+
+    def override_sdf_training_data(self, points: np.ndarray, distances: np.ndarray) -> None:
+        """python_api.cu:74-113.  Points are taken as unit-cube coordinates (no mesh is loaded, so there is no raw AABB to
+        normalise by)."""
+        p = np.ascontiguousarray(points, dtype=np.float32)
+        d = np.ascontiguousarray(distances, dtype=np.float32)
+        if p.ndim != 2 or d.ndim != 1 or p.shape[0] != d.shape[0] or p.shape[1] != 3:
+            raise B.NgpError("Invalid Points<->Distances data")
+        B.check(B.lib().ngp_field_testbed_set_sdf_training_data(self._h, p.ctypes.data_as(C.c_void_p), d.ctypes.data_as(C.c_void_p), p.shape[0]))
+
+    # -- network ---------------------------------------------------------------------------------------------------
+    def reload_network_from_file(self, path: str = "") -> None:
+        with open(path, "r") as f:
+            self.reload_network_from_json(f.read())
+
+    def reload_network_from_json(self, config, config_base_path: str = "") -> None:
+        text = config if isinstance(config, str) else json.dumps(config)
+        B.check(B.lib().ngp_field_testbed_reload_network_from_json(self._h, text.encode()))
+
+    def set_seed(self, seed: int) -> None:
+        B.check(B.lib().ngp_field_testbed_set_seed(self._h, seed))
+
+    @property
+    def n_params(self) -> int:
+        return int(B.lib().ngp_field_testbed_n_params(self._h))
+
+    @property
+    def training_step(self) -> int:
+        return int(B.lib().ngp_field_testbed_training_step(self._h))
+
+    @property
+    def loss(self) -> float:
+        return float(B.lib().ngp_field_testbed_loss(self._h))
+
+    def desc(self) -> B.FieldDesc:
+        d = B.FieldDesc()
+        B.check(B.lib().ngp_field_testbed_get_desc(self._h, C.byref(d)))
+        return d
+
+    def train(self, batch_size: int | None = None) -> None:
+        B.check(B.lib().ngp_field_testbed_train(self._h, int(batch_size or self.training_batch_size)))
+
+    def frame(self) -> bool:
+        if self.shall_train:
+            self.train(self.training_batch_size)
+        return True
+
+    def params_ptr(self, inference: bool = False) -> int:
+        f = B.lib().ngp_field_testbed_params_inference if inference else B.lib().ngp_field_testbed_params
+        return int(f(self._h) or 0)
+
+    def grads_ptr(self) -> int:
+        return int(B.lib().ngp_field_testbed_grads(self._h) or 0)
+
+    def set_params(self, params_fp32: np.ndarray) -> None:
+        a = np.ascontiguousarray(params_fp32, dtype=np.float32)
+        B.check(B.lib().ngp_field_testbed_set_params_fp32(self._h, a.ctypes.data_as(C.c_void_p), a.size))
+
+    def get_params(self, inference: bool = False) -> np.ndarray:
+        out = np.empty(self.n_params, dtype=np.float16)
+        B.check(B.lib().ngp_field_testbed_get_params_fp16(self._h, out.ctypes.data_as(C.c_void_p), out.size, int(inference)))
+        return out
+
+    def evaluate(self, positions: np.ndarray) -> np.ndarray:
+        """network output (inference weights) at [n, D] positions -> [n, n_output_dims] float32"""
+        d = self.desc()
+        p = np.ascontiguousarray(positions, dtype=np.float32).reshape(-1, d.n_pos_dims)
+        out = np.empty((p.shape[0], d.n_output_dims), dtype=np.float32)
+        B.check(B.lib().ngp_field_testbed_evaluate(self._h, p.ctypes.data_as(C.c_void_p), p.shape[0], out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def render(self, width: int, height: int, spp: int = 1, linear: bool = True) -> np.ndarray:
+        """Image mode: the learned image at every pixel centre, float32 [H, W, 4] (render_image, default full-frame view)."""
+        out = np.empty((height, width, 4), dtype=np.float32)
+        B.check(B.lib().ngp_field_testbed_render_image(self._h, width, height, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def sync(self) -> None:
+        B.check(B.lib().ngp_field_testbed_sync(self._h))
+
+
 class Testbed:
-    """Drop-in for ``pyngp.Testbed`` on the NeRF path."""
+    """Drop-in for ``pyngp.Testbed``: the NeRF path; ``Testbed(TestbedMode.Image | TestbedMode.Sdf)`` gives a FieldTestbed."""
+
+    def __new__(cls, mode: TestbedMode = TestbedMode.Nerf, device: int = 0, stream: int | None = None):
+        if cls is Testbed and mode in (TestbedMode.Image, TestbedMode.Sdf):
+            return FieldTestbed(mode, device, stream)
+        return super().__new__(cls)
 
     def __init__(self, mode: TestbedMode = TestbedMode.Nerf, device: int = 0, stream: int | None = None):
         if mode != TestbedMode.Nerf:
-            raise B.NgpError("ngp_b200 implements the NeRF mode only")
+            raise B.NgpError("ngp_b200 implements the NeRF, Image and Sdf modes only")
         if stream is None:
-            try:  # run on torch's current stream when torch drives the process (bench / DP); plain default stream otherwise
-                import torch
-
-                stream = torch.cuda.current_stream(device).cuda_stream if torch.cuda.is_available() else 0
-            except Exception:  # pragma: no cover
-                stream = 0
+            stream = _default_stream(device)
         self._h = B.lib().ngp_testbed_create(device, C.c_void_p(stream))
         if not self._h:
             raise B.NgpError(B.lib().ngp_last_error().decode())

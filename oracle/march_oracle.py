@@ -38,6 +38,8 @@ def lib() -> C.CDLL:
             "orc_uv_to_ray": (None, [f32, f32, C.POINTER(B.TrainView), vp]),
             "orc_srgb_to_linear": (f32, [f32]),
             "orc_linear_to_srgb": (f32, [f32]),
+            "orc_linear_to_srgb_n": (None, [vp, vp, u32]),
+            "orc_srgb_to_linear_n": (None, [vp, vp, u32]),
             "orc_half_to_float": (f32, [C.c_uint16]),
             "orc_float_to_half": (C.c_uint16, [f32]),
             "orc_morton3d": (u32, [u32, u32, u32]),

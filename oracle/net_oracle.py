@@ -328,6 +328,33 @@ def adam_ema_step(n_matrix, w32, w16, ema16, grads16, m1, m2, steps, *, lr, beta
     grads16[:] = 0
 
 
+def seed_seq_first(seed: int, n: int = 2) -> int:
+    """First word of std::seed_seq{(uint32_t)seed}.generate over n words ([rand.util.seedseq]); the reference seeds its
+    default_rng_t this way (trainer.h / testbed.cu: `std::seed_seq seq{seed}; seq.generate(...); rng = pcg32(seeds.front())`)."""
+    M = 0xFFFFFFFF
+    v = [seed & M]
+    s = len(v)
+    b = [0x8b8b8b8b] * n
+    t = 11 if n >= 623 else 7 if n >= 68 else 5 if n >= 39 else 3 if n >= 7 else (n - 1) // 2
+    p = (n - t) // 2
+    q = p + t
+    m = max(s + 1, n)
+    T = lambda x: (x ^ (x >> 27)) & M
+    for k in range(m):
+        r1 = (1664525 * T(b[k % n] ^ b[(k + p) % n] ^ b[(k - 1) % n])) & M
+        r2 = (r1 + (s if k == 0 else (k % n + v[k - 1]) if k <= s else k % n)) & M
+        b[(k + p) % n] = (b[(k + p) % n] + r1) & M
+        b[(k + q) % n] = (b[(k + q) % n] + r2) & M
+        b[k % n] = r2
+    for k in range(m, m + n):
+        r3 = (1566083941 * T((b[k % n] + b[(k + p) % n] + b[(k - 1) % n]) & M)) & M
+        r4 = (r3 - k % n) & M
+        b[(k + p) % n] ^= r3
+        b[(k + q) % n] ^= r4
+        b[k % n] = r4
+    return b[0]
+
+
 # --------------------------------------------------------------------------------------------------------------------
 # pcg32 (for seeded test inputs that mirror the reference's generators; pcg32.h)
 # --------------------------------------------------------------------------------------------------------------------

@@ -268,6 +268,12 @@ static float srgb_to_linear(float s) { return s <= 0.04045f ? s / 12.92f : ngp_p
 static float linear_to_srgb(float l) { return l < 0.0031308f ? 12.92f * l : 1.055f * ngp_powf(l, 0.41666f) - 0.055f; }
 EXPORT float orc_srgb_to_linear(float s) { return srgb_to_linear(s); }
 EXPORT float orc_linear_to_srgb(float l) { return linear_to_srgb(l); }
+EXPORT void orc_linear_to_srgb_n(const float* in, float* out, uint32_t n) {
+	for (uint32_t i = 0; i < n; ++i) out[i] = linear_to_srgb(in[i]);
+}
+EXPORT void orc_srgb_to_linear_n(const float* in, float* out, uint32_t n) {
+	for (uint32_t i = 0; i < n; ++i) out[i] = srgb_to_linear(in[i]);
+}
 
 /* fp16 <-> fp32 (IEEE binary16, round-to-nearest-even) */
 static float half_to_float(uint16_t h) {

@@ -1,0 +1,302 @@
+"""GPU parity: the image / SDF primitive (NetworkWithInputEncoding: hash grid over 2-D / 3-D positions + one fused MLP, tcnn
+losses, train_image's data generation) against the CPU oracle, through the C-ABI."""
+import ctypes as C
+import json
+
+import numpy as np
+import pytest
+
+import util
+from oracle import field_oracle as FO
+from oracle import net_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def lib():
+    P = util.pkg()
+    l = P.load_library()
+    assert l.ngp_device_count() > 0, "GPU tests need a CUDA device; the library has no CPU fallback"
+    return l
+
+
+def dev(x):
+    import torch
+
+    return torch.from_numpy(np.ascontiguousarray(x)).cuda()
+
+
+def stream():
+    import torch
+
+    return torch.cuda.current_stream().cuda_stream
+
+
+FIELD_CONFIGS = [
+    dict(n_pos_dims=2, n_levels=16, F=2, log2_T=24, per_level_scale=1.3819128274917603, n_hidden=2, n_out=3),  # configs/image/base.json
+    dict(n_pos_dims=3, n_levels=16, F=2, log2_T=19, per_level_scale=1.3819128274917603, n_hidden=2, n_out=1),  # configs/sdf/base.json
+    dict(n_pos_dims=2, n_levels=8, F=4, log2_T=15, per_level_scale=2.0, n_hidden=1, n_out=3),
+    dict(n_pos_dims=3, n_levels=8, F=4, log2_T=14, per_level_scale=1.7, n_hidden=3, n_out=4),
+]
+
+
+def positions_for(cfg, n, seed):
+    rng = np.random.default_rng(seed)
+    p = rng.uniform(0, 1, size=(n, cfg["n_pos_dims"])).astype(np.float32)
+    p[0] = 0.0      # exact corner
+    if n > 1:
+        p[1] = 1.0  # the far boundary (dense levels wrap their index there)
+    return p
+
+
+@pytest.mark.parametrize("cfg", FIELD_CONFIGS)
+@pytest.mark.parametrize("n", [1, 300, 4096])
+def test_field_inference_matches_oracle(lib, cfg, n):
+    import torch
+
+    d, L = util.make_field_desc(**cfg)
+    params = util.random_field_params(L, seed=3).astype(np.float16)
+    pos = positions_for(cfg, n, n)
+    want = FO.field_forward(L, params, pos).astype(np.float32)
+    t_p, t_x = dev(params), dev(pos)
+    for stride in (16, cfg["n_out"]):
+        t_out = torch.full((n, stride), 7.0, dtype=torch.float16, device="cuda")
+        assert lib.ngp_field_inference(C.byref(d), stream(), n, t_x.data_ptr(), t_p.data_ptr(), t_out.data_ptr(), stride) == 0, lib.ngp_last_error()
+        torch.cuda.synchronize()
+        got = t_out.cpu().numpy().astype(np.float32)
+        # tolerance: 1e-2 relative to the output scale (fp32 accumulation here vs fp16 activations rounding in both; the reference's own
+        # JIT-vs-offline tolerance, tests/test_common.h:177)
+        assert np.abs(got - want[:, :stride]).max() <= 1e-2 * max(1.0, np.abs(want).max())
+
+
+@pytest.mark.parametrize("cfg", FIELD_CONFIGS)
+@pytest.mark.parametrize("loss", [FO.LOSS_L2, FO.LOSS_MAPE])
+def test_field_train_step_matches_oracle(lib, cfg, loss):
+    import torch
+
+    n = 1024
+    d, L = util.make_field_desc(**cfg)
+    params = util.random_field_params(L, seed=6).astype(np.float16)
+    pos = positions_for(cfg, n, 17)
+    tgt = np.random.default_rng(5).uniform(0.05, 1.0, size=(n, cfg["n_out"])).astype(np.float32)
+    loss_scale = 128.0
+    t_p, t_x, t_t = dev(params), dev(pos), dev(tgt)
+    t_out = torch.zeros(n, 16, dtype=torch.float16, device="cuda")
+    t_val = torch.zeros(n, cfg["n_out"], dtype=torch.float32, device="cuda")
+    t_g = torch.zeros(d.n_params, dtype=torch.float16, device="cuda")
+    assert lib.ngp_field_train_step(C.byref(d), stream(), n, t_x.data_ptr(), t_t.data_ptr(), loss, loss_scale, None, t_p.data_ptr(), t_g.data_ptr(),
+                                    t_val.data_ptr(), t_out.data_ptr()) == 0, lib.ngp_last_error()
+    torch.cuda.synchronize()
+    out16 = t_out.cpu().numpy()
+    want_out = FO.field_forward(L, params, pos).astype(np.float32)
+    assert np.abs(out16.astype(np.float32) - want_out).max() <= 1e-2 * max(1.0, np.abs(want_out).max())
+    # the loss arithmetic itself is IEEE on both sides: on the kernel's own fp16 prediction it must agree bit for bit
+    want_val, want_dl = FO.loss_evaluate(loss, out16, tgt, loss_scale, cfg["n_out"])
+    assert t_val.cpu().numpy().tobytes() == want_val.tobytes()
+    # gradients: backward of the oracle from the kernel's dL/dout
+    want_g = FO.field_backward(L, params, pos, want_dl)
+    g = t_g.cpu().numpy().astype(np.float64)
+    o = 0
+    for (r, c) in L.shapes:
+        a, b = g[o:o + r * c], want_g[o:o + r * c]
+        scale = np.abs(b).max() + 1e-9
+        err = np.abs(a - b).max() / scale
+        print(f"layer {r}x{c}: rel err {err:.3e} (scale {scale:.3e})")
+        assert err < 2e-2, f"weight gradient of layer {r}x{c}"
+        o += r * c
+    gg, wg = g[o:], want_g[o:]
+    nz = np.abs(wg) > 0
+    assert (np.abs(gg[~nz]) == 0).all(), "gradient written to untouched hash entries"
+    scale = np.abs(wg).max()
+    assert np.abs(gg - wg).max() / scale < 3e-2
+    assert abs(gg.sum() - wg.sum()) <= 2e-2 * np.abs(wg).sum()
+
+
+def test_field_external_gradient_equals_fused_loss(lib):
+    """Module::backward form: feeding the oracle's dL/dout as an external gradient gives the same parameter gradients as the fused loss."""
+    import torch
+
+    cfg = FIELD_CONFIGS[0]
+    n = 512
+    d, L = util.make_field_desc(**cfg)
+    params = util.random_field_params(L, seed=9).astype(np.float16)
+    pos = positions_for(cfg, n, 23)
+    tgt = np.random.default_rng(6).uniform(0, 1, size=(n, 3)).astype(np.float32)
+    t_p, t_x, t_t = dev(params), dev(pos), dev(tgt)
+    t_out = torch.zeros(n, 16, dtype=torch.float16, device="cuda")
+    g1 = torch.zeros(d.n_params, dtype=torch.float16, device="cuda")
+    g2 = torch.zeros(d.n_params, dtype=torch.float16, device="cuda")
+    assert lib.ngp_field_train_step(C.byref(d), stream(), n, t_x.data_ptr(), t_t.data_ptr(), FO.LOSS_L2, 128.0, None, t_p.data_ptr(), g1.data_ptr(), None, t_out.data_ptr()) == 0
+    torch.cuda.synchronize()
+    _, dl = FO.loss_evaluate(FO.LOSS_L2, t_out.cpu().numpy(), tgt, 128.0, 3)
+    t_dl = dev(dl)
+    assert lib.ngp_field_train_step(C.byref(d), stream(), n, t_x.data_ptr(), None, 0, 0.0, t_dl.data_ptr(), t_p.data_ptr(), g2.data_ptr(), None, None) == 0, lib.ngp_last_error()
+    torch.cuda.synchronize()
+    a, b = g1.float().cpu().numpy(), g2.float().cpu().numpy()
+    nm = L.n_mlp_params
+    assert np.array_equal(a[:nm], b[:nm])                                  # MLP part: same MMAs on the same operands
+    assert np.abs(a[nm:] - b[nm:]).max() <= 2e-2 * np.abs(a[nm:]).max()    # grid part: fp16 reductions in arbitrary order
+
+
+@pytest.mark.parametrize("loss", [FO.LOSS_L2, FO.LOSS_L1, FO.LOSS_MAPE, FO.LOSS_SMAPE, FO.LOSS_RELATIVE_L2])
+def test_loss_evaluate_is_bit_exact(lib, loss):
+    import torch
+
+    rng = np.random.default_rng(loss + 1)
+    n, dims = 1000, 3
+    pred = rng.normal(0.4, 0.5, size=(n, 16)).astype(np.float16)
+    tgt = rng.uniform(-0.2, 1.0, size=(n, dims)).astype(np.float32)
+    want_v, want_g = FO.loss_evaluate(loss, pred, tgt, 128.0, dims)
+    t_pred, t_t = dev(pred), dev(tgt)
+    t_v = torch.full((n, 16), 9.0, dtype=torch.float32, device="cuda")
+    t_g = torch.full((n, 16), 9.0, dtype=torch.float16, device="cuda")
+    assert lib.ngp_loss_evaluate(stream(), loss, n, 16, dims, 128.0, t_pred.data_ptr(), t_t.data_ptr(), t_v.data_ptr(), t_g.data_ptr()) == 0, lib.ngp_last_error()
+    torch.cuda.synchronize()
+    v, g = t_v.cpu().numpy(), t_g.cpu().numpy()
+    assert (v[:, dims:] == 0).all() and (g[:, dims:] == 0).all()
+    assert v[:, :dims].tobytes() == want_v.tobytes()
+    assert g.view(np.uint16).tolist() == want_g.view(np.uint16).tolist()
+
+
+@pytest.mark.parametrize("snap,linear,stratify", [(False, False, True), (True, True, False), (False, True, False), (True, False, True)])
+def test_image_training_data_is_bit_exact(lib, snap, linear, stratify):
+    import torch
+
+    img = util.test_image(96, 64, seed=2)
+    n = 4096
+    rng = O.Pcg32(1337)
+    rng.advance(12345)
+    state, inc = rng.state, rng.inc
+    want_pos, want_tgt = FO.image_training_data(rng, n, img, stratify, snap, linear)
+    t_img = dev(img)
+    t_pos = torch.zeros(n, 2, dtype=torch.float32, device="cuda")
+    t_tgt = torch.zeros(n, 3, dtype=torch.float32, device="cuda")
+    assert lib.ngp_image_generate_training_data(stream(), n, state, inc, int(stratify), t_img.data_ptr(), 3, 96, 64, int(snap), int(linear),
+                                                t_pos.data_ptr(), t_tgt.data_ptr()) == 0, lib.ngp_last_error()
+    torch.cuda.synchronize()
+    assert t_pos.cpu().numpy().tobytes() == want_pos.astype(np.float32).tobytes()
+    assert t_tgt.cpu().numpy().tobytes() == want_tgt.astype(np.float32).tobytes()
+    # half-precision image (the EXR path of the reference stores __half)
+    t_img16 = dev(img.astype(np.float16))
+    want_pos16, want_tgt16 = FO.eval_image_and_snap(img.astype(np.float16), FO.stratify2(FO.tcnn_random_uniform(_rng_at(state, inc), 2 * n).reshape(n, 2), 12)
+                                                    if stratify else FO.tcnn_random_uniform(_rng_at(state, inc), 2 * n).reshape(n, 2), snap, linear)
+    assert lib.ngp_image_generate_training_data(stream(), n, state, inc, int(stratify), t_img16.data_ptr(), 2, 96, 64, int(snap), int(linear),
+                                                t_pos.data_ptr(), t_tgt.data_ptr()) == 0, lib.ngp_last_error()
+    torch.cuda.synchronize()
+    assert t_tgt.cpu().numpy().tobytes() == want_tgt16.astype(np.float32).tobytes()
+
+
+def _rng_at(state, inc):
+    r = O.Pcg32(0)
+    r.state, r.inc = state, inc
+    return r
+
+
+def test_shuffle_is_bit_exact(lib):
+    import torch
+
+    a = np.random.default_rng(3).uniform(size=(5000, 3)).astype(np.float32)
+    t_in = dev(a)
+    t_out = torch.zeros_like(t_in)
+    assert lib.ngp_shuffle(stream(), 5000, 3, 77, t_in.data_ptr(), t_out.data_ptr()) == 0
+    torch.cuda.synchronize()
+    assert np.array_equal(t_out.cpu().numpy(), FO.shuffle(a, 3, 77))
+
+
+IMAGE_CONFIG = {
+    "loss": {"otype": "L2"},
+    "optimizer": {"otype": "ExponentialDecay", "decay_start": 20000, "decay_interval": 10000, "decay_base": 0.33,
+                  "nested": {"otype": "Adam", "learning_rate": 1e-2, "beta1": 0.9, "beta2": 0.99, "epsilon": 1e-15, "l2_reg": 1e-6}},
+    "encoding": {"otype": "HashGrid", "n_levels": 16, "n_features_per_level": 2, "log2_hashmap_size": 15, "base_resolution": 16},
+    "network": {"otype": "FullyFusedMLP", "activation": "ReLU", "output_activation": "None", "n_neurons": 64, "n_hidden_layers": 2},
+}
+
+
+def test_image_testbed_first_steps_follow_the_oracle(lib):
+    """Testbed(Image): two training steps driven through the B2 surface against the oracle chain
+    (init -> data generation -> forward/loss/backward -> Adam), compared on the fp16 parameters."""
+    ngp = util.pkg()
+    img = util.test_image(64, 48, seed=1)
+    tb = ngp.Testbed(ngp.TestbedMode.Image)
+    tb.set_image(img)
+    tb.reload_network_from_json(IMAGE_CONFIG)
+    d = tb.desc()
+    # per_level_scale derives from the image resolution (src/testbed.cu:4236-4255)
+    pls = float(np.float32(np.exp(np.float32(np.log(np.float32(32.0) / np.float32(16.0))) / np.float32(15))))
+    og = O.grid_layout(16, 2, 15, 16, pls, n_pos_dims=2)
+    assert list(d.grid.offsets[:17]) == og.offsets
+    L = FO.FieldLayout(og, 2, 3)
+    w32 = FO.field_init_params(L, 1337)
+    w16 = w32.astype(np.float16)
+    assert tb.get_params().tobytes() == w16.tobytes()
+
+    rng = O.Pcg32(1337)
+    n = 4096
+    m1, m2 = np.zeros_like(w32), np.zeros_like(w32)
+    steps = np.zeros(w32.size, dtype=np.uint32)
+    ema = w16.copy()
+    for step in range(1, 3):
+        pos, tgt = FO.image_training_data(rng, n, img, True, False, False)
+        out, values, g = FO.field_train_step(L, w16, pos, tgt, FO.LOSS_L2, 128.0)
+        g16 = g.astype(np.float16)
+        O.adam_ema_step(L.n_mlp_params, w32, w16, ema, g16, m1, m2, steps, lr=1e-2, beta1=0.9, beta2=0.99, eps=1e-15, l2_reg=1e-6, loss_scale=128.0,
+                        ema_decay=0.0, step=step)
+        tb.train(n)
+        assert abs(tb.loss - float(values.sum())) <= 2e-3 * float(values.sum()) + 1e-6
+        got = tb.get_params().astype(np.float32)
+        # Adam's first steps move every touched parameter by ~lr regardless of the gradient's size, so a sign flip of a
+        # near-zero gradient shows up as 2*lr; the bulk must agree closely
+        diff = np.abs(got - w16.astype(np.float32))
+        assert np.median(diff) <= 1e-4 and (diff > 5e-3).mean() < 0.02, (np.median(diff), (diff > 5e-3).mean())
+    assert tb.training_step == 2
+
+
+def test_image_testbed_learns_the_image(lib):
+    ngp = util.pkg()
+    img = util.test_image(128, 96, seed=4)
+    tb = ngp.Testbed(ngp.TestbedMode.Image)
+    tb.set_image(img)
+    tb.image.training.linear_colors = True
+    cfg = json.loads(json.dumps(IMAGE_CONFIG))
+    cfg["encoding"]["log2_hashmap_size"] = 17
+    tb.reload_network_from_json(cfg)
+    tb.train(1 << 14)
+    first = tb.loss
+    for _ in range(300):
+        tb.train(1 << 14)
+    assert tb.loss < 0.05 * first, (first, tb.loss)
+    out = tb.render(128, 96)
+    mse = float(np.mean((out[..., :3] - img[..., :3]) ** 2))
+    psnr = -10 * np.log10(mse)
+    print("image psnr", psnr)
+    assert psnr > 30.0 and np.all(out[..., 3] == 1.0)
+
+
+def test_sdf_testbed_learns_a_sphere(lib):
+    ngp = util.pkg()
+    rng = np.random.default_rng(0)
+    pts = rng.uniform(0, 1, size=(1 << 16, 3)).astype(np.float32)
+    dist = (np.linalg.norm(pts - 0.5, axis=1) - 0.3).astype(np.float32)
+    tb = ngp.Testbed(ngp.TestbedMode.Sdf)
+    tb.override_sdf_training_data(pts, dist)
+    cfg = {
+        "loss": {"otype": "MAPE"},
+        "optimizer": {"otype": "Ema", "decay": 0.95, "nested": {"otype": "ExponentialDecay", "decay_start": 10000, "decay_interval": 5000, "decay_base": 0.33,
+                      "nested": {"otype": "Adam", "learning_rate": 1e-3, "beta1": 0.9, "beta2": 0.99, "epsilon": 1e-15, "l2_reg": 1e-6}}},
+        "encoding": {"otype": "HashGrid", "n_levels": 16, "n_features_per_level": 2, "log2_hashmap_size": 15, "base_resolution": 16},
+        "network": {"otype": "FullyFusedMLP", "activation": "ReLU", "output_activation": "None", "n_neurons": 64, "n_hidden_layers": 2},
+    }
+    tb.reload_network_from_json(cfg)
+    assert tb.desc().n_pos_dims == 3 and tb.desc().n_output_dims == 1
+    tb.train(1 << 14)
+    first = tb.loss
+    for _ in range(400):
+        tb.train(1 << 14)
+    assert tb.loss < 0.3 * first, (first, tb.loss)
+    q = rng.uniform(0.1, 0.9, size=(2000, 3)).astype(np.float32)
+    pred = tb.evaluate(q)[:, 0]
+    true = np.linalg.norm(q - 0.5, axis=1) - 0.3
+    assert np.abs(pred - true).mean() < 0.02
+    with pytest.raises(ngp.NgpError):
+        tb.train(1 << 17)   # more than the available records (testbed_sdf.cu:1582 silently skips; here it is an error)

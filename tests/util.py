@@ -156,3 +156,48 @@ def views_to_device(arr, keep):
     raw = np.frombuffer(bytes(dev_arr), dtype=np.uint8).copy()
     t_views = torch.from_numpy(raw).cuda()
     return t_views, tens
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# field (image / SDF primitive) helpers
+# ---------------------------------------------------------------------------------------------------------------------
+def make_field_desc(n_pos_dims=2, n_levels=16, F=2, log2_T=19, base_res=16, per_level_scale=1.5, n_hidden=2, n_out=3):
+    """(C descriptor from the library, independent oracle layout) of a NetworkWithInputEncoding."""
+    from oracle import field_oracle as FO
+
+    P = pkg()
+    lib = P.load_library()
+    g = P.GridDesc()
+    assert lib.ngp_grid_desc_init_nd(C.byref(g), n_pos_dims, n_levels, F, log2_T, base_res, per_level_scale) == 0, lib.ngp_last_error()
+    d = P.FieldDesc()
+    assert lib.ngp_field_desc_init(C.byref(d), C.byref(g), n_pos_dims, n_hidden, n_out) == 0, lib.ngp_last_error()
+    og = O.grid_layout(n_levels, F, log2_T, base_res, per_level_scale, n_pos_dims=n_pos_dims)
+    return d, FO.FieldLayout(og, n_hidden, n_out)
+
+
+def random_field_params(L, seed=0, trained_like=True):
+    rng = np.random.default_rng(seed)
+    parts = []
+    for (r, c) in L.shapes:
+        s = np.sqrt(6.0 / (r + c))
+        parts.append(rng.uniform(-s, s, size=r * c))
+    if trained_like:
+        parts.append(np.clip(rng.normal(0.0, 0.1, size=L.grid.n_params), -1, 1))
+    else:
+        parts.append(rng.uniform(-1e-4, 1e-4, size=L.grid.n_params))
+    return np.concatenate(parts).astype(np.float32)
+
+
+def test_image(w=96, h=64, seed=0):
+    """smooth + sharp synthetic RGBA float image, linear colour"""
+    y, x = np.mgrid[0:h, 0:w].astype(np.float32)
+    u, v = x / w, y / h
+    img = np.zeros((h, w, 4), dtype=np.float32)
+    img[..., 0] = 0.5 + 0.5 * np.sin(9 * u + 3 * v)
+    img[..., 1] = (np.hypot(u - 0.5, v - 0.5) < 0.3).astype(np.float32) * 0.8 + 0.1
+    img[..., 2] = u * v
+    img[..., 3] = 1.0
+    rng = np.random.default_rng(seed)
+    img[..., :3] += rng.uniform(0, 0.02, size=(h, w, 3)).astype(np.float32)
+    img[..., :3] = np.clip(img[..., :3], 0.0, 1.0)
+    return img
