@@ -262,10 +262,24 @@ __global__ void __launch_bounds__(TILE, 3) k_render_nerf(
 // next ray from a device-side queue.  Outputs for the samples the loss kernel reads are bit-identical to the all-samples pass.
 // ------------------------------------------------------------------------------------------------------------------
 constexpr uint32_t FWD_RAYS_CTAS_PER_SM = 3;   // measured: 3 -> 0.249 ms, 4 -> 0.280 ms, 5 (spills) -> 0.341 ms
-template <uint32_t F, uint32_t RAY_CHUNK>
+// What the lazy variant needs to march a ray itself: generate_training_samples_nerf's pass 2 (testbed_nerf.cu:822-848) moved
+// to the consumer.  The generator then only counts (numsteps, base, t of the first sample); a ray's coordinates are produced
+// here chunk by chunk, by the same arithmetic, and only as far as the transmittance test lets the loss kernel read —
+// ~6 % of the 4 M samples a step generates on a trained scene (profiles/r1b).
+struct LazyMarch {
+	float aabb_min[3], aabb_max[3];
+	ngp_march_consts march;
+	uint32_t max_cascade;
+	const float* rays;        // [n_rays x 6] origin, direction (unnormalised) as written by the generator
+	const float* t_first;     // [n_rays]
+	const uint8_t* bitfield;
+};
+
+template <uint32_t F, uint32_t RAY_CHUNK, bool LAZY>
 __global__ void __launch_bounds__(TILE, FWD_RAYS_CTAS_PER_SM) k_nerf_forward_rays(
 	const __grid_constant__ NetDev net, const ngp_nerf_counters* __restrict__ counters, uint32_t* __restrict__ queue, const uint32_t* __restrict__ numsteps,
-	const float* __restrict__ coords, const __half* __restrict__ params, const uint32_t density_activation, __half* __restrict__ out
+	float* __restrict__ coords, const __half* __restrict__ params, const uint32_t density_activation, __half* __restrict__ out,
+	const __grid_constant__ LazyMarch lazy
 ) {
 	extern __shared__ __align__(128) uint8_t smem[];
 	const FwdSmem L = fwd_smem_layout(net.n_hidden_density, net.n_hidden_rgb);
@@ -297,9 +311,10 @@ __global__ void __launch_bounds__(TILE, FWD_RAYS_CTAS_PER_SM) k_nerf_forward_ray
 
 	// slot state, replicated in the 8 lanes of the slot
 	bool have_ray = false, queue_empty = false;
-	uint32_t n = 0, base = 0, k0 = 0;
-	float T = 1.0f;
+	uint32_t n = 0, base = 0, k0 = 0, ray = 0;
+	float T = 1.0f, t_cur = 0.0f;
 	const float EPSILON = 1e-4f;
+	const Aabb aabb{V3{lazy.aabb_min[0], lazy.aabb_min[1], lazy.aabb_min[2]}, V3{lazy.aabb_max[0], lazy.aabb_max[1], lazy.aabb_max[2]}};
 
 	for (;;) {
 		// ---- refill: one queue pop per slot (lane `sub == 0` of each slot asks), one atomic per warp
@@ -320,6 +335,8 @@ __global__ void __launch_bounds__(TILE, FWD_RAYS_CTAS_PER_SM) k_nerf_forward_ray
 					base = numsteps[r * 2 + 1];
 					k0 = 0;
 					T = 1.0f;
+					ray = r;
+					if (LAZY) t_cur = lazy.t_first[r];
 					have_ray = n > 0;
 				}
 			}
@@ -333,9 +350,47 @@ __global__ void __launch_bounds__(TILE, FWD_RAYS_CTAS_PER_SM) k_nerf_forward_ray
 
 		// ---- this row's sample
 		const uint32_t k = k0 + sub;
-		const bool valid = have_ray && k < n;
+		bool valid = have_ray && k < n;
 		float c[7] = {0.5f, 0.5f, 0.5f, 0.0f, 0.5f, 0.5f, 0.5f};
-		if (valid) {
+		if constexpr (LAZY) {
+			if (have_ray) {
+				// the RAY_CHUNK lanes of the slot march the ray together (same arithmetic, same result); lane `sub` keeps sample k0 + sub
+				const float* rp = lazy.rays + (size_t)ray * 6;
+				const V3 ro{rp[0], rp[1], rp[2]};
+				const V3 rdn = normalize3(V3{rp[3], rp[4], rp[5]});
+				const V3 idir{1.0f / rdn.x, 1.0f / rdn.y, 1.0f / rdn.z};
+				const uint32_t todo = (n - k0) < RAY_CHUNK ? (n - k0) : RAY_CHUNK;
+				uint32_t j = 0;
+				float t = t_cur;
+				V3 pos;
+				while (aabb.contains(pos = ro + t * rdn) && j < todo) {
+					const float dt = calc_dt(t, lazy.march);
+					const uint32_t mip = mip_from_dt(dt, pos, lazy.max_cascade);
+					if (density_grid_occupied_at(pos, lazy.bitfield, mip)) {
+						if (j == sub) {
+							const V3 wp = warp_position(pos, aabb);
+							c[0] = wp.x; c[1] = wp.y; c[2] = wp.z; c[3] = warp_dt(dt);
+						}
+						++j;
+						t += dt;
+					} else {
+						t = advance_to_next_voxel(t, lazy.march, pos, rdn, idir, mip);
+					}
+				}
+				t_cur = t;
+				valid = valid && sub < j;
+				if (valid) {
+					const V3 wdir = warp_direction(rdn);
+					c[4] = wdir.x; c[5] = wdir.y; c[6] = wdir.z;
+					float* cp = coords + (size_t)(base + k) * 7;
+#pragma unroll
+					for (int q = 0; q < 7; ++q) cp[q] = c[q];
+				} else {
+					c[0] = c[1] = c[2] = 0.5f;
+					c[3] = 0.0f;
+				}
+			}
+		} else if (valid) {
 			const float* cp = coords + (size_t)(base + k) * 7;
 #pragma unroll
 			for (int q = 0; q < 7; ++q) c[q] = cp[q];
@@ -399,19 +454,31 @@ __global__ void __launch_bounds__(TILE, FWD_RAYS_CTAS_PER_SM) k_nerf_forward_ray
 }
 
 // queue: a zeroed u32 (the `pad` word of the step's counter block).  Grid sized for the worst case (n_rays_max rays).
-template <uint32_t F, uint32_t CHUNK>
+template <uint32_t F, uint32_t CHUNK, bool LAZY>
 static void launch_forward_rays(const NetDev& net, cudaStream_t stream, uint32_t n_rays_max, const ngp_nerf_counters* counters, uint32_t* queue,
-	const uint32_t* numsteps, const float* coords, const __half* params, uint32_t density_activation, __half* out) {
+	const uint32_t* numsteps, float* coords, const __half* params, uint32_t density_activation, __half* out, const LazyMarch& lazy) {
 	const FwdSmem L = fwd_smem_layout(net.n_hidden_density, net.n_hidden_rgb);
 	const uint32_t n_tiles = div_round_up(n_rays_max, TILE / CHUNK);
 	const uint32_t max_ctas = (uint32_t)device_sm_count() * FWD_RAYS_CTAS_PER_SM;
 	const uint32_t grid = n_tiles < max_ctas ? n_tiles : max_ctas;
-	auto kern = k_nerf_forward_rays<F, CHUNK>;
+	auto kern = k_nerf_forward_rays<F, CHUNK, LAZY>;
 	static bool attr = false;
 	if (!attr) { NGPB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); attr = true; }
-	kern<<<grid, TILE, L.total, stream>>>(net, counters, queue, numsteps, coords, params, density_activation, out);
+	kern<<<grid, TILE, L.total, stream>>>(net, counters, queue, numsteps, coords, params, density_activation, out, lazy);
 	NGPB_LAUNCHED();
 	NGPB_CUDA_CHECK(cudaGetLastError());
+}
+
+template <bool LAZY>
+static void dispatch_forward_rays(const NetDev& net, cudaStream_t stream, uint32_t n_rays_max, const ngp_nerf_counters* counters, uint32_t* queue,
+	const uint32_t* numsteps, float* coords, const __half* params, uint32_t density_activation, __half* out, uint32_t chunk, const LazyMarch& lazy) {
+	if (net.n_features == 2) {
+		if (chunk == 4) launch_forward_rays<2, 4, LAZY>(net, stream, n_rays_max, counters, queue, numsteps, coords, params, density_activation, out, lazy);
+		else launch_forward_rays<2, 8, LAZY>(net, stream, n_rays_max, counters, queue, numsteps, coords, params, density_activation, out, lazy);
+	} else {
+		if (chunk == 4) launch_forward_rays<4, 4, LAZY>(net, stream, n_rays_max, counters, queue, numsteps, coords, params, density_activation, out, lazy);
+		else launch_forward_rays<4, 8, LAZY>(net, stream, n_rays_max, counters, queue, numsteps, coords, params, density_activation, out, lazy);
+	}
 }
 
 // chunk: samples of a ray evaluated per tensor-core tile (4 or 8; 128 / chunk ray slots per CTA)
@@ -420,13 +487,28 @@ void nerf_inference_rays(const ngp_nerf_desc& d, cudaStream_t stream, uint32_t n
 	if (n_rays_max == 0) return;
 	NGPB_CHECK(chunk == 4 || chunk == 8, "inference chunk must be 4 or 8");
 	const NetDev net = make_netdev(d);
-	if (net.n_features == 2) {
-		if (chunk == 4) launch_forward_rays<2, 4>(net, stream, n_rays_max, counters, queue, numsteps, coords, params, density_activation, out);
-		else launch_forward_rays<2, 8>(net, stream, n_rays_max, counters, queue, numsteps, coords, params, density_activation, out);
-	} else {
-		if (chunk == 4) launch_forward_rays<4, 4>(net, stream, n_rays_max, counters, queue, numsteps, coords, params, density_activation, out);
-		else launch_forward_rays<4, 8>(net, stream, n_rays_max, counters, queue, numsteps, coords, params, density_activation, out);
+	dispatch_forward_rays<false>(net, stream, n_rays_max, counters, queue, numsteps, const_cast<float*>(coords), params, density_activation, out, chunk, LazyMarch{});
+}
+
+// As nerf_inference_rays, but the coordinates are marched here (`coords` is an OUTPUT: the samples the loss kernel will read
+// are written at their reserved slots [base, base + numsteps) of each ray; the rest of a ray's slots stay untouched).
+void nerf_march_inference_rays(const ngp_nerf_desc& d, cudaStream_t stream, uint32_t n_rays_max, const ngp_nerf_train_cfg& cfg, const ngp_nerf_counters* counters,
+	uint32_t* queue, const uint32_t* numsteps, const float* rays, const float* t_first, const uint8_t* bitfield, float* coords, const __half* params,
+	__half* out, uint32_t chunk) {
+	if (n_rays_max == 0) return;
+	NGPB_CHECK(chunk == 4 || chunk == 8, "inference chunk must be 4 or 8");
+	const NetDev net = make_netdev(d);
+	LazyMarch lazy{};
+	for (int k = 0; k < 3; ++k) {
+		lazy.aabb_min[k] = cfg.aabb_min[k];
+		lazy.aabb_max[k] = cfg.aabb_max[k];
 	}
+	lazy.march = cfg.march;
+	lazy.max_cascade = cfg.max_cascade;
+	lazy.rays = rays;
+	lazy.t_first = t_first;
+	lazy.bitfield = bitfield;
+	dispatch_forward_rays<true>(net, stream, n_rays_max, counters, queue, numsteps, coords, params, cfg.density_activation, out, chunk, lazy);
 }
 
 size_t render_scratch_bytes(int32_t, int32_t) { return 256; }

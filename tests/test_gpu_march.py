@@ -312,3 +312,66 @@ def test_ray_ordered_inference_equals_full_inference_where_the_loss_reads(lib, s
     # and it evaluates far fewer samples than the full pass: at most one 8-sample chunk beyond what is consumed
     assert n_eval <= consumed.sum() + 8 * k
     print("evaluated", n_eval, "of", ns, "consumed", int(consumed.sum()))
+
+
+@pytest.mark.parametrize("scene", SCENES[:2])
+def test_lazy_march_inference_equals_generate_all_where_the_loss_reads(lib, scene):
+    """count-only generator + march-inside-the-inference kernel (the default training schedule) against the reference
+    schedule generate-all -> evaluate-all: per ray id the same sample count, and bit-identical coordinates and network outputs
+    for every sample the loss kernel consumes"""
+    import torch
+
+    n_rays, max_samples = 4096, 4096 * 1024
+    want, got, ctx = run_generator(lib, scene, n_rays, max_samples)
+    cfg, dv = ctx["cfg"], ctx["dev"]
+    k, ns = got["n_kept"], got["n_samples"]
+    d, L = util.make_desc(n_levels=16, F=2, log2_T=16, aabb_scale=scene["aabb_scale"])
+    params = util.random_params(L, seed=41, trained_like=True)
+    params[64 * 32:64 * 32 + 64] = np.abs(params[64 * 32:64 * 32 + 64]) * 60.0
+    params = params.astype(np.float16)
+    t_p = dev(params)
+    full = torch.zeros(ns, 4, dtype=torch.float16, device="cuda")
+    assert lib.ngp_nerf_inference(C.byref(d), stream(), ns, dv["co"].data_ptr(), t_p.data_ptr(), full.data_ptr(), 4) == 0, lib.ngp_last_error()
+    batch = 1 << int(np.ceil(np.log2(max(ns, 2))))
+    t_coc = torch.zeros(batch, 7, dtype=torch.float32, device="cuda")
+    t_dl = torch.zeros(batch, 4, dtype=torch.float16, device="cuda")
+    t_md = dev(np.array([0.02], dtype=np.float32))
+    ns_full = dv["ns"].cpu().numpy().view(np.uint32)[:k].copy()
+    assert lib.ngp_nerf_compute_loss(stream(), n_rays, n_rays, ctx["rng"][0], ctx["rng"][1], C.byref(cfg), ctx["t_views"].data_ptr(), len(ctx["views"]), full.data_ptr(), batch,
+                                     dv["cnt"].data_ptr(), dv["ri"].data_ptr(), dv["rays"].data_ptr(), dv["ns"].data_ptr(), dv["co"].data_ptr(), t_coc.data_ptr(),
+                                     t_dl.data_ptr(), None, t_md.data_ptr()) == 0, lib.ngp_last_error()
+    torch.cuda.synchronize()
+    consumed = dv["ns"].cpu().numpy().view(np.uint32)[:k, 0]
+    full_h = full.cpu().numpy().view(np.uint16)
+    coords_full = got["coords"]
+    by_id_full = {int(r): (int(ns_full[j, 0]), int(ns_full[j, 1]), int(consumed[j])) for j, r in enumerate(got["ray_indices"][:k])}
+
+    # ---- the lazy schedule
+    l_cnt = torch.zeros(4, dtype=torch.int32, device="cuda")
+    l_ri = torch.zeros(n_rays, dtype=torch.int32, device="cuda")
+    l_rays = torch.zeros(n_rays, 6, dtype=torch.float32, device="cuda")
+    l_ns = torch.zeros(n_rays, 2, dtype=torch.int32, device="cuda")
+    l_tf = torch.zeros(n_rays, dtype=torch.float32, device="cuda")
+    l_co = torch.full((max_samples, 7), float("nan"), dtype=torch.float32, device="cuda")
+    l_out = torch.full((ns, 4), float("nan"), dtype=torch.float16, device="cuda")
+    assert lib.ngp_nerf_count_training_samples(stream(), n_rays, 0, n_rays, ctx["rng"][0], ctx["rng"][1], C.byref(cfg), ctx["t_views"].data_ptr(), len(ctx["views"]),
+                                               ctx["t_bf"].data_ptr(), max_samples, l_cnt.data_ptr(), l_ri.data_ptr(), l_rays.data_ptr(), l_ns.data_ptr(),
+                                               l_tf.data_ptr()) == 0, lib.ngp_last_error()
+    queue = l_cnt[3:4]
+    assert lib.ngp_nerf_march_inference_rays(C.byref(d), stream(), n_rays, C.byref(cfg), l_cnt.data_ptr(), queue.data_ptr(), l_ns.data_ptr(), l_rays.data_ptr(),
+                                             l_tf.data_ptr(), ctx["t_bf"].data_ptr(), l_co.data_ptr(), t_p.data_ptr(), l_out.data_ptr()) == 0, lib.ngp_last_error()
+    torch.cuda.synchronize()
+    cnt = l_cnt.cpu().numpy().view(np.uint32)
+    assert int(cnt[0]) == k and int(cnt[1]) == ns
+    l_ns_h, l_ri_h = l_ns.cpu().numpy().view(np.uint32), l_ri.cpu().numpy().view(np.uint32)
+    l_co_h, l_out_h = l_co.cpu().numpy(), l_out.cpu().numpy().view(np.uint16)
+    n_written = int((~np.isnan(l_co_h[:, 0])).sum())
+    for j in range(k):
+        rid = int(l_ri_h[j])
+        n_f, b_f, c_f = by_id_full[rid]
+        n_l, b_l = int(l_ns_h[j, 0]), int(l_ns_h[j, 1])
+        assert n_l == n_f
+        assert l_co_h[b_l:b_l + c_f].tobytes() == coords_full[b_f:b_f + c_f].tobytes(), f"coordinates of ray {rid}"
+        assert np.array_equal(l_out_h[b_l:b_l + c_f], full_h[b_f:b_f + c_f]), f"network outputs of ray {rid}"
+    assert n_written <= consumed.sum() + 8 * k and n_written < ns
+    print("marched", n_written, "of", ns, "samples; consumed", int(consumed.sum()))
