@@ -200,17 +200,19 @@ int ngp_nerf_generate_training_samples(void* stream, uint32_t n_rays, uint32_t r
 	const ngp_nerf_train_cfg* cfg, const ngp_train_view* views_dev, uint32_t n_views, const uint8_t* density_grid_bitfield,
 	uint32_t max_samples, ngp_nerf_counters* counters_dev, uint32_t* ray_indices, float* rays, uint32_t* numsteps, float* coords);
 
-/* The two halves of generate_training_samples_nerf, split so that coordinates are produced only where they are consumed:
- * ngp_nerf_count_training_samples is the generator's counting pass alone (ray records, numsteps = (count, base), and
- * t_first[ray] = t of the ray's first sample; no coordinates), and ngp_nerf_march_inference_rays is ngp_nerf_inference_rays with
- * the march inside: it walks each ray from t_first with the generator's own arithmetic, chunk by chunk, writes the coordinates of
- * the samples it evaluates into coords [base + k] and stops a ray where compute_loss_kernel_train_nerf would (T < 1e-4).
- * Everything the loss kernel reads (coordinates, network outputs) is bit-identical to the generate-all / evaluate-all schedule. */
-int ngp_nerf_count_training_samples(void* stream, uint32_t n_rays, uint32_t ray_offset, uint32_t n_rays_global, uint64_t rng_state, uint64_t rng_inc,
+/* generate_training_samples_nerf with its coordinate pass cut short, so that coordinates are produced only where they are
+ * consumed: ngp_nerf_generate_training_samples_prefix counts every ray in full (ray records, numsteps = (count, base): identical
+ * to ngp_nerf_generate_training_samples) but writes only the first `prefix` (multiple of 8) coordinates of each ray, plus
+ * t_resume[ray] = the t at which the march continues.  ngp_nerf_march_inference_rays is ngp_nerf_inference_rays with that
+ * continuation inside: past the prefix it walks the ray from t_resume with the generator's own arithmetic, 8 samples at a time,
+ * writes the coordinates of the samples it evaluates into coords [base + k] and stops a ray where
+ * compute_loss_kernel_train_nerf would (T < 1e-4).  Everything the loss kernel reads (coordinates, network outputs) is
+ * bit-identical to the generate-all / evaluate-all schedule; prefix = 0 marches everything on demand. */
+int ngp_nerf_generate_training_samples_prefix(void* stream, uint32_t n_rays, uint32_t ray_offset, uint32_t n_rays_global, uint64_t rng_state, uint64_t rng_inc,
 	const ngp_nerf_train_cfg* cfg, const ngp_train_view* views_dev, uint32_t n_views, const uint8_t* density_grid_bitfield, uint32_t max_samples,
-	ngp_nerf_counters* counters, uint32_t* ray_indices, float* rays, uint32_t* numsteps, float* t_first);
+	ngp_nerf_counters* counters, uint32_t* ray_indices, float* rays, uint32_t* numsteps, float* coords, float* t_resume, uint32_t prefix);
 int ngp_nerf_march_inference_rays(const ngp_nerf_desc* d, void* stream, uint32_t n_rays_max, const ngp_nerf_train_cfg* cfg, const ngp_nerf_counters* counters,
-	uint32_t* queue, const uint32_t* numsteps, const float* rays, const float* t_first, const uint8_t* density_grid_bitfield, float* coords,
+	uint32_t* queue, const uint32_t* numsteps, const float* rays, const float* t_resume, uint32_t prefix, const uint8_t* density_grid_bitfield, float* coords,
 	const void* params_fp16, void* out_fp16);
 
 /* ≙ compute_loss_kernel_train_nerf (testbed_nerf.cu:852-1180): composite, loss, compaction, dL/doutput.

@@ -157,8 +157,8 @@ PROTOTYPES = {
     "ngp_grid_encode": (C.c_int, [P(GridDesc), vp, u32, vp, u32, vp, vp]),
     "ngp_optimizer_step": (C.c_int, [P(NerfDesc), vp, P(AdamCfg), vp, vp, vp, vp, vp, vp, vp]),
     "ngp_nerf_generate_training_samples": (C.c_int, [vp, u32, u32, u32, u64, u64, P(NerfTrainCfg), vp, u32, vp, u32, vp, vp, vp, vp, vp]),
-    "ngp_nerf_count_training_samples": (C.c_int, [vp, u32, u32, u32, u64, u64, P(NerfTrainCfg), vp, u32, vp, u32, vp, vp, vp, vp, vp]),
-    "ngp_nerf_march_inference_rays": (C.c_int, [P(NerfDesc), vp, u32, P(NerfTrainCfg), vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "ngp_nerf_generate_training_samples_prefix": (C.c_int, [vp, u32, u32, u32, u64, u64, P(NerfTrainCfg), vp, u32, vp, u32, vp, vp, vp, vp, vp, vp, u32]),
+    "ngp_nerf_march_inference_rays": (C.c_int, [P(NerfDesc), vp, u32, P(NerfTrainCfg), vp, vp, vp, vp, vp, u32, vp, vp, vp, vp]),
     "ngp_nerf_compute_loss": (C.c_int, [vp, u32, u32, u64, u64, P(NerfTrainCfg), vp, u32, vp, u32, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "ngp_nerf_fill_rollover": (C.c_int, [vp, u32, vp, vp, vp]),
     "ngp_nerf_density_grid_scratch_bytes": (C.c_size_t, [u32]),

@@ -62,14 +62,16 @@ __device__ inline void random_image_pos_training(Pcg32& rng, int w, int h, bool 
 // One thread per ray.  Slots are reserved once per warp (prefix sum + one atomic) instead of two atomics per ray.
 // ray ids are GLOBAL: ray_id = ray_offset + local index, so that W ranks reproduce the single-GPU batch.
 // ------------------------------------------------------------------------------------------------------------------
-// WRITE_COORDS = false is the counting half alone: it emits (ray, numsteps, base) and the t of the ray's first sample, and
-// leaves the coordinates to the consumer (k_nerf_forward_rays marches a ray only as far as the loss will read it, render.cu).
-template <bool WRITE_COORDS>
+// WRITE_ALL = false: the kernel counts every ray in full (numsteps and the slot layout are those of the reference) but writes
+// the coordinates of only the first `prefix` samples of each ray and the t at which the march would continue; the consumer
+// (k_nerf_forward_rays, render.cu) marches on from there for the few rays whose transmittance is still above 1e-4 after the
+// prefix — the loss kernel reads ~6 % of the 4 M samples a step reserves on a trained scene (profiles/r1b).
+template <bool WRITE_ALL>
 __global__ void __launch_bounds__(128) k_generate_training_samples(
 	const uint32_t n_rays_local, const uint32_t ray_offset, const uint32_t n_rays_global, Pcg32 rng_in, const ngp_nerf_train_cfg cfg,
 	const ngp_train_view* __restrict__ views, const uint32_t n_views, const uint8_t* __restrict__ bitfield, const uint32_t max_samples,
 	ngp_nerf_counters* __restrict__ counters, uint32_t* __restrict__ ray_indices_out, float* __restrict__ rays_out,
-	uint32_t* __restrict__ numsteps_out, float* __restrict__ coords_out, float* __restrict__ t_first_out
+	uint32_t* __restrict__ numsteps_out, float* __restrict__ coords_out, float* __restrict__ t_resume_out, const uint32_t prefix
 ) {
 	const uint32_t li = blockIdx.x * blockDim.x + threadIdx.x;
 	const uint32_t lane = threadIdx.x & 31u;
@@ -144,8 +146,7 @@ __global__ void __launch_bounds__(128) k_generate_training_samples(
 	r[0] = ro.x; r[1] = ro.y; r[2] = ro.z; r[3] = rd.x; r[4] = rd.y; r[5] = rd.z;
 	numsteps_out[ray_idx * 2 + 0] = numsteps;
 	numsteps_out[ray_idx * 2 + 1] = base;
-	if (t_first_out) t_first_out[ray_idx] = t_first;
-	if (!WRITE_COORDS) return;
+	const uint32_t n_write = WRITE_ALL ? numsteps : (numsteps < prefix ? numsteps : prefix);
 
 	// pass 2: write the coordinates
 	const V3 wdir = warp_direction(rdn);
@@ -153,7 +154,7 @@ __global__ void __launch_bounds__(128) k_generate_training_samples(
 	float t = t_first;
 	uint32_t j = 0;
 	V3 pos;
-	while (aabb.contains(pos = ro + t * rdn) && j < numsteps) {
+	while (aabb.contains(pos = ro + t * rdn) && j < n_write) {
 		const float dt = calc_dt(t, cfg.march);
 		const uint32_t mip = mip_from_dt(dt, pos, cfg.max_cascade);
 		if (density_grid_occupied_at(pos, bitfield, mip)) {
@@ -166,6 +167,7 @@ __global__ void __launch_bounds__(128) k_generate_training_samples(
 			t = advance_to_next_voxel(t, cfg.march, pos, rdn, idir, mip);
 		}
 	}
+	if (!WRITE_ALL) t_resume_out[ray_idx] = t;
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -541,16 +543,17 @@ static Aabb cfg_aabb(const ngp_nerf_train_cfg& cfg) {
 
 void generate_training_samples(cudaStream_t stream, uint32_t n_rays_local, uint32_t ray_offset, uint32_t n_rays_global, uint64_t rng_state,
 	uint64_t rng_inc, const ngp_nerf_train_cfg& cfg, const ngp_train_view* views, uint32_t n_views, const uint8_t* bitfield, uint32_t max_samples,
-	ngp_nerf_counters* counters, uint32_t* ray_indices, float* rays, uint32_t* numsteps, float* coords, float* t_first) {
+	ngp_nerf_counters* counters, uint32_t* ray_indices, float* rays, uint32_t* numsteps, float* coords, float* t_resume, uint32_t prefix) {
 	if (n_rays_local == 0) return;
 	NGPB_CHECK(n_views > 0, "generate_training_samples: no training views");
-	NGPB_CHECK(coords || t_first, "generate_training_samples: need a coordinate buffer or a t_first buffer");
-	if (coords) {
+	NGPB_CHECK(coords != nullptr, "generate_training_samples: no coordinate buffer");
+	if (!t_resume) {
 		k_generate_training_samples<true><<<div_round_up(n_rays_local, 128), 128, 0, stream>>>(n_rays_local, ray_offset, n_rays_global,
-			Pcg32(rng_state, rng_inc, true), cfg, views, n_views, bitfield, max_samples, counters, ray_indices, rays, numsteps, coords, t_first);
+			Pcg32(rng_state, rng_inc, true), cfg, views, n_views, bitfield, max_samples, counters, ray_indices, rays, numsteps, coords, nullptr, 0u);
 	} else {
+		NGPB_CHECK(prefix % 8u == 0u, "generate_training_samples: the eager prefix must be a multiple of 8");
 		k_generate_training_samples<false><<<div_round_up(n_rays_local, 128), 128, 0, stream>>>(n_rays_local, ray_offset, n_rays_global,
-			Pcg32(rng_state, rng_inc, true), cfg, views, n_views, bitfield, max_samples, counters, ray_indices, rays, numsteps, nullptr, t_first);
+			Pcg32(rng_state, rng_inc, true), cfg, views, n_views, bitfield, max_samples, counters, ray_indices, rays, numsteps, coords, t_resume, prefix);
 	}
 	NGPB_LAUNCHED();
 	NGPB_CUDA_CHECK(cudaGetLastError());

@@ -262,16 +262,18 @@ __global__ void __launch_bounds__(TILE, 3) k_render_nerf(
 // next ray from a device-side queue.  Outputs for the samples the loss kernel reads are bit-identical to the all-samples pass.
 // ------------------------------------------------------------------------------------------------------------------
 constexpr uint32_t FWD_RAYS_CTAS_PER_SM = 3;   // measured: 3 -> 0.249 ms, 4 -> 0.280 ms, 5 (spills) -> 0.341 ms
-// What the lazy variant needs to march a ray itself: generate_training_samples_nerf's pass 2 (testbed_nerf.cu:822-848) moved
-// to the consumer.  The generator then only counts (numsteps, base, t of the first sample); a ray's coordinates are produced
-// here chunk by chunk, by the same arithmetic, and only as far as the transmittance test lets the loss kernel read —
-// ~6 % of the 4 M samples a step generates on a trained scene (profiles/r1b).
+// What the lazy variant needs to march a ray itself: the tail of generate_training_samples_nerf's pass 2
+// (testbed_nerf.cu:822-848) moved to the consumer.  The generator counts every ray in full but writes only the first `prefix`
+// coordinates of each; beyond the prefix a ray's coordinates are produced here chunk by chunk, by the same arithmetic, and only
+// as far as the transmittance test lets the loss kernel read.  (Marching everything here was measured too: it puts a
+// sequential 8-sample march on the critical path of every tile and costs what the generator saves, profiles/r1c.)
 struct LazyMarch {
 	float aabb_min[3], aabb_max[3];
 	ngp_march_consts march;
 	uint32_t max_cascade;
 	const float* rays;        // [n_rays x 6] origin, direction (unnormalised) as written by the generator
-	const float* t_first;     // [n_rays]
+	const float* t_resume;    // [n_rays] t at which the march continues after the prefix
+	uint32_t prefix;          // samples per ray already written by the generator (multiple of RAY_CHUNK)
 	const uint8_t* bitfield;
 };
 
@@ -336,7 +338,7 @@ __global__ void __launch_bounds__(TILE, FWD_RAYS_CTAS_PER_SM) k_nerf_forward_ray
 					k0 = 0;
 					T = 1.0f;
 					ray = r;
-					if (LAZY) t_cur = lazy.t_first[r];
+					if (LAZY) t_cur = lazy.t_resume[r];
 					have_ray = n > 0;
 				}
 			}
@@ -352,8 +354,10 @@ __global__ void __launch_bounds__(TILE, FWD_RAYS_CTAS_PER_SM) k_nerf_forward_ray
 		const uint32_t k = k0 + sub;
 		bool valid = have_ray && k < n;
 		float c[7] = {0.5f, 0.5f, 0.5f, 0.0f, 0.5f, 0.5f, 0.5f};
+		bool from_buffer = valid;
 		if constexpr (LAZY) {
-			if (have_ray) {
+			from_buffer = valid && k0 < lazy.prefix;
+			if (have_ray && k0 >= lazy.prefix) {
 				// the RAY_CHUNK lanes of the slot march the ray together (same arithmetic, same result); lane `sub` keeps sample k0 + sub
 				const float* rp = lazy.rays + (size_t)ray * 6;
 				const V3 ro{rp[0], rp[1], rp[2]};
@@ -390,7 +394,8 @@ __global__ void __launch_bounds__(TILE, FWD_RAYS_CTAS_PER_SM) k_nerf_forward_ray
 					c[3] = 0.0f;
 				}
 			}
-		} else if (valid) {
+		}
+		if (from_buffer) {
 			const float* cp = coords + (size_t)(base + k) * 7;
 #pragma unroll
 			for (int q = 0; q < 7; ++q) c[q] = cp[q];
@@ -490,11 +495,11 @@ void nerf_inference_rays(const ngp_nerf_desc& d, cudaStream_t stream, uint32_t n
 	dispatch_forward_rays<false>(net, stream, n_rays_max, counters, queue, numsteps, const_cast<float*>(coords), params, density_activation, out, chunk, LazyMarch{});
 }
 
-// As nerf_inference_rays, but the coordinates are marched here (`coords` is an OUTPUT: the samples the loss kernel will read
-// are written at their reserved slots [base, base + numsteps) of each ray; the rest of a ray's slots stay untouched).
+// As nerf_inference_rays, but coordinates beyond each ray's first `prefix` samples are marched here (`coords` is IN/OUT: the
+// samples the loss kernel will read are written at their reserved slots; the rest of a ray's slots stay untouched).
 void nerf_march_inference_rays(const ngp_nerf_desc& d, cudaStream_t stream, uint32_t n_rays_max, const ngp_nerf_train_cfg& cfg, const ngp_nerf_counters* counters,
-	uint32_t* queue, const uint32_t* numsteps, const float* rays, const float* t_first, const uint8_t* bitfield, float* coords, const __half* params,
-	__half* out, uint32_t chunk) {
+	uint32_t* queue, const uint32_t* numsteps, const float* rays, const float* t_resume, uint32_t prefix, const uint8_t* bitfield, float* coords,
+	const __half* params, __half* out, uint32_t chunk) {
 	if (n_rays_max == 0) return;
 	NGPB_CHECK(chunk == 4 || chunk == 8, "inference chunk must be 4 or 8");
 	const NetDev net = make_netdev(d);
@@ -506,7 +511,9 @@ void nerf_march_inference_rays(const ngp_nerf_desc& d, cudaStream_t stream, uint
 	lazy.march = cfg.march;
 	lazy.max_cascade = cfg.max_cascade;
 	lazy.rays = rays;
-	lazy.t_first = t_first;
+	NGPB_CHECK(prefix % chunk == 0, "the eager prefix must be a multiple of the inference chunk");
+	lazy.t_resume = t_resume;
+	lazy.prefix = prefix;
 	lazy.bitfield = bitfield;
 	dispatch_forward_rays<true>(net, stream, n_rays_max, counters, queue, numsteps, coords, params, cfg.density_activation, out, chunk, lazy);
 }

@@ -32,10 +32,10 @@ void optimizer_step(const ngp_nerf_desc& d, cudaStream_t stream, const ngp_adam_
 	__half* grads, float* m1, float* m2, uint32_t* steps);
 void generate_training_samples(cudaStream_t stream, uint32_t n_rays_local, uint32_t ray_offset, uint32_t n_rays_global, uint64_t rng_state, uint64_t rng_inc,
 	const ngp_nerf_train_cfg& cfg, const ngp_train_view* views, uint32_t n_views, const uint8_t* bitfield, uint32_t max_samples, ngp_nerf_counters* counters,
-	uint32_t* ray_indices, float* rays, uint32_t* numsteps, float* coords, float* t_first);
+	uint32_t* ray_indices, float* rays, uint32_t* numsteps, float* coords, float* t_resume, uint32_t prefix);
 void nerf_march_inference_rays(const ngp_nerf_desc& d, cudaStream_t stream, uint32_t n_rays_max, const ngp_nerf_train_cfg& cfg, const ngp_nerf_counters* counters,
-	uint32_t* queue, const uint32_t* numsteps, const float* rays, const float* t_first, const uint8_t* bitfield, float* coords, const __half* params,
-	__half* out, uint32_t chunk);
+	uint32_t* queue, const uint32_t* numsteps, const float* rays, const float* t_resume, uint32_t prefix, const uint8_t* bitfield, float* coords,
+	const __half* params, __half* out, uint32_t chunk);
 void compute_loss(cudaStream_t stream, uint32_t n_rays_local, uint32_t n_rays_global, uint64_t rng_state, uint64_t rng_inc, const ngp_nerf_train_cfg& cfg,
 	const ngp_train_view* views, uint32_t n_views, const __half* network_output, uint32_t max_compacted, ngp_nerf_counters* counters,
 	const uint32_t* ray_indices, const float* rays, uint32_t* numsteps, const float* coords, float* coords_compacted, __half* dloss, float* loss_per_ray,
@@ -187,7 +187,8 @@ struct ngp_testbed {
 	uint64_t seed = 1337;
 	bool train_network = true, train_encoding = true;
 	bool full_inference = false;
-	bool lazy_sample_generation = true;   // the generator only counts; coordinates are marched by the ray-ordered inference kernel
+	bool lazy_sample_generation = true;   // the generator writes a prefix of each ray's coordinates; the ray-ordered inference kernel marches the rest on demand
+	uint32_t eager_prefix = 16;
 	uint32_t inference_chunk = 8;
 
 	DevBuf<float> params_fp32, m1, m2, mlp_grads_f32;
@@ -211,7 +212,7 @@ struct ngp_testbed {
 	struct RaySet {
 		DevBuf<ngp_nerf_counters> counters;
 		DevBuf<uint32_t> ray_indices, numsteps;
-		DevBuf<float> rays, coords, t_first;
+		DevBuf<float> rays, coords, t_resume;
 	} set[2];
 	uint32_t cur = 0;                     // set used by the step in flight
 	DevBuf<float> coords_compacted, loss_per_ray, reduce_scratch;
@@ -424,7 +425,7 @@ static void tb_ensure_step_scratch(ngp_testbed* t, uint32_t batch) {
 		rs.numsteps.ensure((size_t)max_rays * 2);
 		rs.rays.ensure((size_t)max_rays * 6);
 		rs.coords.ensure((size_t)max_samples * 7);
-		rs.t_first.ensure(max_rays);
+		rs.t_resume.ensure(max_rays);
 	}
 	t->loss_per_ray.ensure(max_rays);
 	t->reduce_scratch.ensure(1024);
@@ -510,7 +511,7 @@ static void tb_launch_generator(ngp_testbed* t, cudaStream_t stream, uint32_t se
 	ngp_testbed::RaySet& rs = t->set[set];
 	NGPB_CUDA_CHECK(cudaMemsetAsync(rs.counters.p, 0, sizeof(ngp_nerf_counters), stream));
 	generate_training_samples(stream, rays_local, t->dp_rank * rays_local, rays_local * t->dp_world, t->rng.state, t->rng.inc, t->cfg, t->views_dev.p, tb_n_views(t),
-		t->bitfield.p, max_inference, rs.counters.p, rs.ray_indices.p, rs.rays.p, rs.numsteps.p, tb_lazy(t) ? nullptr : rs.coords.p, rs.t_first.p);
+		t->bitfield.p, max_inference, rs.counters.p, rs.ray_indices.p, rs.rays.p, rs.numsteps.p, rs.coords.p, tb_lazy(t) ? rs.t_resume.p : nullptr, t->eager_prefix);
 }
 
 // train_nerf_step up to and including the backward pass (testbed_nerf.cu:3007-3382).  Everything is asynchronous; the
@@ -560,7 +561,7 @@ static void tb_compute_grads(ngp_testbed* t, uint32_t batch) {
 			nerf_inference_counted(t->desc, t->stream, max_inference, &rs.counters.p->n_samples, rs.coords.p, t->params.p, t->mlp_out.p);
 		} else if (tb_lazy(t)) {
 			// march + evaluate, ray by ray, only the samples the loss kernel will read
-			nerf_march_inference_rays(t->desc, t->stream, rays_local, t->cfg, rs.counters.p, &rs.counters.p->pad, rs.numsteps.p, rs.rays.p, rs.t_first.p,
+			nerf_march_inference_rays(t->desc, t->stream, rays_local, t->cfg, rs.counters.p, &rs.counters.p->pad, rs.numsteps.p, rs.rays.p, rs.t_resume.p, t->eager_prefix,
 				t->bitfield.p, rs.coords.p, t->params.p, t->mlp_out.p, t->inference_chunk);
 		} else {
 			// evaluate, ray by ray, only the samples the loss kernel will read (bit-identical outputs for those)
@@ -730,20 +731,21 @@ int ngp_nerf_generate_training_samples(void* stream, uint32_t n_rays, uint32_t r
 	uint32_t* ray_indices, float* rays, uint32_t* numsteps, float* coords) {
 	NGPB_TRY(require_device(); NGPB_CHECK(n_rays_global >= n_rays && ray_offset <= n_rays_global - n_rays, "ray shard outside the global batch");
 		generate_training_samples((cudaStream_t)stream, n_rays, ray_offset, n_rays_global, rng_state, rng_inc, *cfg, views, n_views, bitfield,
-		max_samples, counters, ray_indices, rays, numsteps, coords, nullptr));
+		max_samples, counters, ray_indices, rays, numsteps, coords, nullptr, 0u));
 }
-int ngp_nerf_count_training_samples(void* stream, uint32_t n_rays, uint32_t ray_offset, uint32_t n_rays_global, uint64_t rng_state, uint64_t rng_inc,
+int ngp_nerf_generate_training_samples_prefix(void* stream, uint32_t n_rays, uint32_t ray_offset, uint32_t n_rays_global, uint64_t rng_state, uint64_t rng_inc,
 	const ngp_nerf_train_cfg* cfg, const ngp_train_view* views, uint32_t n_views, const uint8_t* bitfield, uint32_t max_samples, ngp_nerf_counters* counters,
-	uint32_t* ray_indices, float* rays, uint32_t* numsteps, float* t_first) {
+	uint32_t* ray_indices, float* rays, uint32_t* numsteps, float* coords, float* t_resume, uint32_t prefix) {
 	NGPB_TRY(require_device(); NGPB_CHECK(n_rays_global >= n_rays && ray_offset <= n_rays_global - n_rays, "ray shard outside the global batch");
-		NGPB_CHECK(t_first != nullptr, "ngp_nerf_count_training_samples: t_first is required");
+		NGPB_CHECK(t_resume != nullptr, "ngp_nerf_generate_training_samples_prefix: t_resume is required");
 		generate_training_samples((cudaStream_t)stream, n_rays, ray_offset, n_rays_global, rng_state, rng_inc, *cfg, views, n_views, bitfield,
-		max_samples, counters, ray_indices, rays, numsteps, nullptr, t_first));
+		max_samples, counters, ray_indices, rays, numsteps, coords, t_resume, prefix));
 }
 int ngp_nerf_march_inference_rays(const ngp_nerf_desc* d, void* stream, uint32_t n_rays_max, const ngp_nerf_train_cfg* cfg, const ngp_nerf_counters* counters,
-	uint32_t* queue, const uint32_t* numsteps, const float* rays, const float* t_first, const uint8_t* bitfield, float* coords, const void* params, void* out) {
-	NGPB_TRY(require_device(); nerf_march_inference_rays(*d, (cudaStream_t)stream, n_rays_max, *cfg, counters, queue, numsteps, rays, t_first, bitfield, coords,
-		(const __half*)params, (__half*)out, 8));
+	uint32_t* queue, const uint32_t* numsteps, const float* rays, const float* t_resume, uint32_t prefix, const uint8_t* bitfield, float* coords, const void* params,
+	void* out) {
+	NGPB_TRY(require_device(); nerf_march_inference_rays(*d, (cudaStream_t)stream, n_rays_max, *cfg, counters, queue, numsteps, rays, t_resume, prefix, bitfield,
+		coords, (const __half*)params, (__half*)out, 8));
 }
 int ngp_nerf_compute_loss(void* stream, uint32_t n_rays, uint32_t n_rays_global, uint64_t rng_state, uint64_t rng_inc, const ngp_nerf_train_cfg* cfg,
 	const ngp_train_view* views, uint32_t n_views, const void* network_output, uint32_t max_compacted, ngp_nerf_counters* counters,
@@ -944,6 +946,7 @@ int ngp_testbed_set_option(ngp_testbed* t, const char* name_c, double value) {
 		else if (n == "background_color.b") c.background_color[2] = (float)value;
 		else if (n == "nerf.training.full_inference") { tb_invalidate_prefetch(t); t->full_inference = value != 0; }
 		else if (n == "nerf.training.lazy_sample_generation") { tb_invalidate_prefetch(t); t->lazy_sample_generation = value != 0; }
+		else if (n == "nerf.training.eager_prefix") { NGPB_CHECK(value >= 0 && ((uint32_t)value % 8u) == 0u, "eager_prefix must be a multiple of 8"); tb_invalidate_prefetch(t); t->eager_prefix = (uint32_t)value; }
 		else if (n == "nerf.training.inference_chunk") { NGPB_CHECK(value == 4 || value == 8, "inference_chunk must be 4 or 8"); t->inference_chunk = (uint32_t)value; }
 		else if (n == "nerf.training.overlap_sample_generation") t->overlap_sample_generation = value != 0;
 		else if (n == "train_network") t->train_network = value != 0;

@@ -315,8 +315,9 @@ def test_ray_ordered_inference_equals_full_inference_where_the_loss_reads(lib, s
 
 
 @pytest.mark.parametrize("scene", SCENES[:2])
-def test_lazy_march_inference_equals_generate_all_where_the_loss_reads(lib, scene):
-    """count-only generator + march-inside-the-inference kernel (the default training schedule) against the reference
+@pytest.mark.parametrize("prefix", [16, 0, 64])
+def test_lazy_march_inference_equals_generate_all_where_the_loss_reads(lib, scene, prefix):
+    """prefix-only generator + march-inside-the-inference kernel (the default training schedule) against the reference
     schedule generate-all -> evaluate-all: per ray id the same sample count, and bit-identical coordinates and network outputs
     for every sample the loss kernel consumes"""
     import torch
@@ -354,12 +355,12 @@ def test_lazy_march_inference_equals_generate_all_where_the_loss_reads(lib, scen
     l_tf = torch.zeros(n_rays, dtype=torch.float32, device="cuda")
     l_co = torch.full((max_samples, 7), float("nan"), dtype=torch.float32, device="cuda")
     l_out = torch.full((ns, 4), float("nan"), dtype=torch.float16, device="cuda")
-    assert lib.ngp_nerf_count_training_samples(stream(), n_rays, 0, n_rays, ctx["rng"][0], ctx["rng"][1], C.byref(cfg), ctx["t_views"].data_ptr(), len(ctx["views"]),
-                                               ctx["t_bf"].data_ptr(), max_samples, l_cnt.data_ptr(), l_ri.data_ptr(), l_rays.data_ptr(), l_ns.data_ptr(),
-                                               l_tf.data_ptr()) == 0, lib.ngp_last_error()
+    assert lib.ngp_nerf_generate_training_samples_prefix(stream(), n_rays, 0, n_rays, ctx["rng"][0], ctx["rng"][1], C.byref(cfg), ctx["t_views"].data_ptr(),
+                                                         len(ctx["views"]), ctx["t_bf"].data_ptr(), max_samples, l_cnt.data_ptr(), l_ri.data_ptr(), l_rays.data_ptr(),
+                                                         l_ns.data_ptr(), l_co.data_ptr(), l_tf.data_ptr(), prefix) == 0, lib.ngp_last_error()
     queue = l_cnt[3:4]
     assert lib.ngp_nerf_march_inference_rays(C.byref(d), stream(), n_rays, C.byref(cfg), l_cnt.data_ptr(), queue.data_ptr(), l_ns.data_ptr(), l_rays.data_ptr(),
-                                             l_tf.data_ptr(), ctx["t_bf"].data_ptr(), l_co.data_ptr(), t_p.data_ptr(), l_out.data_ptr()) == 0, lib.ngp_last_error()
+                                             l_tf.data_ptr(), prefix, ctx["t_bf"].data_ptr(), l_co.data_ptr(), t_p.data_ptr(), l_out.data_ptr()) == 0, lib.ngp_last_error()
     torch.cuda.synchronize()
     cnt = l_cnt.cpu().numpy().view(np.uint32)
     assert int(cnt[0]) == k and int(cnt[1]) == ns
@@ -373,5 +374,5 @@ def test_lazy_march_inference_equals_generate_all_where_the_loss_reads(lib, scen
         assert n_l == n_f
         assert l_co_h[b_l:b_l + c_f].tobytes() == coords_full[b_f:b_f + c_f].tobytes(), f"coordinates of ray {rid}"
         assert np.array_equal(l_out_h[b_l:b_l + c_f], full_h[b_f:b_f + c_f]), f"network outputs of ray {rid}"
-    assert n_written <= consumed.sum() + 8 * k and n_written < ns
-    print("marched", n_written, "of", ns, "samples; consumed", int(consumed.sum()))
+    assert n_written <= consumed.sum() + (8 + prefix) * k and n_written < ns
+    print("written", n_written, "of", ns, "coordinates; consumed", int(consumed.sum()))
