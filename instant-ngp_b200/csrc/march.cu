@@ -66,8 +66,16 @@ __device__ inline void random_image_pos_training(Pcg32& rng, int w, int h, bool 
 // the coordinates of only the first `prefix` samples of each ray and the t at which the march would continue; the consumer
 // (k_nerf_forward_rays, render.cu) marches on from there for the few rays whose transmittance is still above 1e-4 after the
 // prefix — the loss kernel reads ~6 % of the 4 M samples a step reserves on a trained scene (profiles/r1b).
+//
+// Pass 1 leaves the t of each of a ray's first GEN_T_SLOTS samples in shared memory; the coordinate pass then does not march
+// at all for those: the warp walks its 32 rays one after the other and its lanes turn consecutive samples of the same ray
+// into coordinates (pos = o + t d, dt = calc_dt(t): the values pass 2 of the reference recomputes, testbed_nerf.cu:822-848),
+// so the work is balanced across lanes whatever the rays' lengths and the 28-byte records leave the warp contiguously.
+// Only the samples beyond GEN_T_SLOTS of a long ray are re-marched by the ray's own thread.
+constexpr uint32_t GEN_THREADS = 128;
+constexpr uint32_t GEN_T_SLOTS = 96;   // 96 x 128 x 4 B = 48 KB of shared memory per CTA
 template <bool WRITE_ALL>
-__global__ void __launch_bounds__(128) k_generate_training_samples(
+__global__ void __launch_bounds__(GEN_THREADS) k_generate_training_samples(
 	const uint32_t n_rays_local, const uint32_t ray_offset, const uint32_t n_rays_global, Pcg32 rng_in, const ngp_nerf_train_cfg cfg,
 	const ngp_train_view* __restrict__ views, const uint32_t n_views, const uint8_t* __restrict__ bitfield, const uint32_t max_samples,
 	ngp_nerf_counters* __restrict__ counters, uint32_t* __restrict__ ray_indices_out, float* __restrict__ rays_out,
@@ -79,9 +87,10 @@ __global__ void __launch_bounds__(128) k_generate_training_samples(
 	const uint32_t i = ray_offset + li;
 
 	const Aabb aabb{V3{cfg.aabb_min[0], cfg.aabb_min[1], cfg.aabb_min[2]}, V3{cfg.aabb_max[0], cfg.aabb_max[1], cfg.aabb_max[2]}};
+	extern __shared__ float t_list[];   // [GEN_T_SLOTS][GEN_THREADS]
 	uint32_t numsteps = 0;
 	V3 ro{0, 0, 0}, rd{0, 0, 0}, rdn{0, 0, 1}, idir{0, 0, 0};
-	float startt = 0.0f, t_first = 0.0f;
+	float startt = 0.0f, t_over = 0.0f;
 
 	if (in_range) {
 		const uint32_t img = image_idx(i, n_rays_global, n_views);
@@ -101,8 +110,7 @@ __global__ void __launch_bounds__(128) k_generate_training_samples(
 			startt = advance_n_steps(tmin, cfg.march, rng.next_float());
 			idir = V3{1.0f / rdn.x, 1.0f / rdn.y, 1.0f / rdn.z};
 
-			// pass 1: count the occupied steps; remember where the first one sits so that pass 2 does not re-traverse the
-			// empty space in front of it (it would reach exactly this t by exactly the same arithmetic)
+			// pass 1: count the occupied steps, keeping the t of the first GEN_T_SLOTS samples and the march state right after them
 			uint32_t j = 0;
 			float t = startt;
 			V3 pos;
@@ -110,9 +118,10 @@ __global__ void __launch_bounds__(128) k_generate_training_samples(
 				const float dt = calc_dt(t, cfg.march);
 				const uint32_t mip = mip_from_dt(dt, pos, cfg.max_cascade);
 				if (density_grid_occupied_at(pos, bitfield, mip)) {
-					if (j == 0) t_first = t;
+					if (j < GEN_T_SLOTS) t_list[j * GEN_THREADS + threadIdx.x] = t;
 					++j;
 					t += dt;
+					if (j == GEN_T_SLOTS) t_over = t;
 				} else {
 					t = advance_to_next_voxel(t, cfg.march, pos, rdn, idir, mip);
 				}
@@ -138,36 +147,72 @@ __global__ void __launch_bounds__(128) k_generate_training_samples(
 	uint32_t ray_base = 0;
 	if (lane == 0 && keep_mask) ray_base = atomicAdd(&counters->n_rays, __popc(keep_mask));
 	ray_base = __shfl_sync(0xFFFFFFFFu, ray_base, 0);
-	if (!keep) return;
 	const uint32_t ray_idx = ray_base + __popc(keep_mask & ((1u << lane) - 1u));
+	const uint32_t n_write = !keep ? 0u : (WRITE_ALL ? numsteps : (numsteps < prefix ? numsteps : prefix));
+	if (keep) {
+		ray_indices_out[ray_idx] = i;
+		float* r = rays_out + (size_t)ray_idx * 6;
+		r[0] = ro.x; r[1] = ro.y; r[2] = ro.z; r[3] = rd.x; r[4] = rd.y; r[5] = rd.z;
+		numsteps_out[ray_idx * 2 + 0] = numsteps;
+		numsteps_out[ray_idx * 2 + 1] = base;
+	}
 
-	ray_indices_out[ray_idx] = i;
-	float* r = rays_out + (size_t)ray_idx * 6;
-	r[0] = ro.x; r[1] = ro.y; r[2] = ro.z; r[3] = rd.x; r[4] = rd.y; r[5] = rd.z;
-	numsteps_out[ray_idx * 2 + 0] = numsteps;
-	numsteps_out[ray_idx * 2 + 1] = base;
-	const uint32_t n_write = WRITE_ALL ? numsteps : (numsteps < prefix ? numsteps : prefix);
-
-	// pass 2: write the coordinates
-	const V3 wdir = warp_direction(rdn);
-	float* co = coords_out + (size_t)base * 7;
-	float t = t_first;
-	uint32_t j = 0;
-	V3 pos;
-	while (aabb.contains(pos = ro + t * rdn) && j < n_write) {
-		const float dt = calc_dt(t, cfg.march);
-		const uint32_t mip = mip_from_dt(dt, pos, cfg.max_cascade);
-		if (density_grid_occupied_at(pos, bitfield, mip)) {
+	// pass 2a: the warp writes the coordinates of the samples whose t is in shared memory, ray after ray
+	__syncwarp();
+	const uint32_t n_listed = n_write < GEN_T_SLOTS ? n_write : GEN_T_SLOTS;
+	const uint32_t warp_col0 = threadIdx.x & ~31u;
+	for (uint32_t src = 0; src < 32; ++src) {
+		const uint32_t n_s = __shfl_sync(0xFFFFFFFFu, n_listed, src);
+		if (n_s == 0) continue;  // warp-uniform
+		const uint32_t base_s = __shfl_sync(0xFFFFFFFFu, base, src);
+		const V3 ro_s{__shfl_sync(0xFFFFFFFFu, ro.x, src), __shfl_sync(0xFFFFFFFFu, ro.y, src), __shfl_sync(0xFFFFFFFFu, ro.z, src)};
+		const V3 rdn_s{__shfl_sync(0xFFFFFFFFu, rdn.x, src), __shfl_sync(0xFFFFFFFFu, rdn.y, src), __shfl_sync(0xFFFFFFFFu, rdn.z, src)};
+		const V3 wdir = warp_direction(rdn_s);
+		for (uint32_t k = lane; k < n_s; k += 32) {
+			const float t = t_list[k * GEN_THREADS + warp_col0 + src];
+			const V3 pos = ro_s + t * rdn_s;
+			const float dt = calc_dt(t, cfg.march);
 			const V3 wp = warp_position(pos, aabb);
-			float* c = co + (size_t)j * 7;
+			float* c = coords_out + (size_t)(base_s + k) * 7;
 			c[0] = wp.x; c[1] = wp.y; c[2] = wp.z; c[3] = warp_dt(dt); c[4] = wdir.x; c[5] = wdir.y; c[6] = wdir.z;
-			++j;
-			t += dt;
-		} else {
-			t = advance_to_next_voxel(t, cfg.march, pos, rdn, idir, mip);
 		}
 	}
-	if (!WRITE_ALL) t_resume_out[ray_idx] = t;
+	if (!keep) return;
+
+	// pass 2b: samples beyond the listed ones of a long ray are re-marched by its own thread, from the state pass 1 left
+	float t = numsteps <= GEN_T_SLOTS ? 0.0f : t_over;
+	if (n_write > GEN_T_SLOTS) {
+		const V3 wdir = warp_direction(rdn);
+		float* co = coords_out + (size_t)base * 7;
+		uint32_t j = GEN_T_SLOTS;
+		V3 pos;
+		while (aabb.contains(pos = ro + t * rdn) && j < n_write) {
+			const float dt = calc_dt(t, cfg.march);
+			const uint32_t mip = mip_from_dt(dt, pos, cfg.max_cascade);
+			if (density_grid_occupied_at(pos, bitfield, mip)) {
+				const V3 wp = warp_position(pos, aabb);
+				float* c = co + (size_t)j * 7;
+				c[0] = wp.x; c[1] = wp.y; c[2] = wp.z; c[3] = warp_dt(dt); c[4] = wdir.x; c[5] = wdir.y; c[6] = wdir.z;
+				++j;
+				t += dt;
+			} else {
+				t = advance_to_next_voxel(t, cfg.march, pos, rdn, idir, mip);
+			}
+		}
+	}
+	if (!WRITE_ALL) {
+		// where the consumer resumes the march: the loop state right after the last written sample (its t plus its dt), or the
+		// first sample itself when nothing was written
+		if (n_write < numsteps && n_write <= GEN_T_SLOTS) {
+			if (n_write == 0) {
+				t = t_list[threadIdx.x];
+			} else {
+				const float tl = t_list[(n_write - 1) * GEN_THREADS + threadIdx.x];
+				t = tl + calc_dt(tl, cfg.march);
+			}
+		}
+		t_resume_out[ray_idx] = t;
+	}
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -548,11 +593,11 @@ void generate_training_samples(cudaStream_t stream, uint32_t n_rays_local, uint3
 	NGPB_CHECK(n_views > 0, "generate_training_samples: no training views");
 	NGPB_CHECK(coords != nullptr, "generate_training_samples: no coordinate buffer");
 	if (!t_resume) {
-		k_generate_training_samples<true><<<div_round_up(n_rays_local, 128), 128, 0, stream>>>(n_rays_local, ray_offset, n_rays_global,
+		k_generate_training_samples<true><<<div_round_up(n_rays_local, GEN_THREADS), GEN_THREADS, GEN_T_SLOTS * GEN_THREADS * sizeof(float), stream>>>(n_rays_local, ray_offset, n_rays_global,
 			Pcg32(rng_state, rng_inc, true), cfg, views, n_views, bitfield, max_samples, counters, ray_indices, rays, numsteps, coords, nullptr, 0u);
 	} else {
 		NGPB_CHECK(prefix % 8u == 0u, "generate_training_samples: the eager prefix must be a multiple of 8");
-		k_generate_training_samples<false><<<div_round_up(n_rays_local, 128), 128, 0, stream>>>(n_rays_local, ray_offset, n_rays_global,
+		k_generate_training_samples<false><<<div_round_up(n_rays_local, GEN_THREADS), GEN_THREADS, GEN_T_SLOTS * GEN_THREADS * sizeof(float), stream>>>(n_rays_local, ray_offset, n_rays_global,
 			Pcg32(rng_state, rng_inc, true), cfg, views, n_views, bitfield, max_samples, counters, ray_indices, rays, numsteps, coords, t_resume, prefix);
 	}
 	NGPB_LAUNCHED();

@@ -187,7 +187,7 @@ struct ngp_testbed {
 	uint64_t seed = 1337;
 	bool train_network = true, train_encoding = true;
 	bool full_inference = false;
-	bool lazy_sample_generation = true;   // the generator writes a prefix of each ray's coordinates; the ray-ordered inference kernel marches the rest on demand
+	bool lazy_sample_generation = false;  // measured slower (profiles/r1c): the generator writes a prefix of each ray's coordinates; the ray-ordered inference kernel marches the rest on demand
 	uint32_t eager_prefix = 16;
 	uint32_t inference_chunk = 8;
 
