@@ -188,6 +188,8 @@ def main() -> None:
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=300)
+    ap.add_argument("--pretrain", type=int, default=700, help="untimed set-up steps before the warm-up: the metric is STEADY-STATE training throughput "
+                    "(SURVEY 8d: steps 500-1000), and the per-step workload (rays, samples per ray) only settles once the scene has formed")
     ap.add_argument("--impl", default="ngp_b200", choices=["ngp_b200", "reference"])
     ap.add_argument("--views", type=int, default=N_VIEWS)
     ap.add_argument("--res", type=int, default=RES)
@@ -254,7 +256,9 @@ def main() -> None:
             dist.barrier()
             torch.cuda.synchronize()
 
-    # ---- warm-up (reaches the steady state of the rays_per_batch controller and of the occupancy grid)
+    # ---- set-up: train until the scene has formed (untimed, not part of the warm-up count), then the warm-up proper
+    for _ in range(args.pretrain):
+        step()
     for _ in range(args.warmup):
         step()
     sync_all()
@@ -334,7 +338,8 @@ def main() -> None:
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
             "config": {"workload": WORKLOAD if (args.views, args.res) == (N_VIEWS, RES) else f"synthetic ball {args.views}x{args.res}^2 L16F2T19 batch 2^18",
                        "batch_per_gpu": BATCH, "l2_policy": "inputs larger than L2: 1.0 GB image set + 340 MB parameter/optimizer state per step, no explicit flush",
-                       "parallelism": f"dp{world}"},
+                       "parallelism": f"dp{world}", "pretrain_steps": args.pretrain,
+                       "timed_steps": f"{args.pretrain + args.warmup}..{args.pretrain + args.warmup + args.steps} of a from-scratch training run"},
             "rays_per_sec": rays / (ms_total * 1e-3),
             "per_step": {"rays": rays / args.steps / world, "samples_before_compaction": pre / args.steps, "samples_compacted": samples / args.steps / world},
             "phase_ms_per_step": {k: v / n_fb for k, v in phases.items() if k != "steps"},
