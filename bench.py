@@ -48,49 +48,76 @@ def syn():
 
 # ---------------------------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """samples nvidia-smi SM clocks / throttle reasons while the timed region runs (B200_PROFILING.md)."""
+    """samples SM clocks / throttle reasons of one GPU while the timed region runs (B200_PROFILING.md's clocks line).  NVML in a
+    thread every 5 ms (a 150 ms timed region still gets ~30 samples); `nvidia-smi -lms` as the fallback when NVML is unusable."""
+
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown"}
 
     def __init__(self, gpu_index: int):
-        self.rows, self.proc, self.gpu = [], None, gpu_index
+        self.gpu, self.sm, self.mx, self.reasons = gpu_index, [], [], set()
+        self.stop, self.thread, self.proc = threading.Event(), None, None
+
+    def _nvml_loop(self, nv, h):
+        while not self.stop.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                bits = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, name in self.REASONS.items():
+                    if bits & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self.stop.wait(0.005)
+
+    def _smi_loop(self):
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.proc.stdout:
+            r = [c.strip() for c in line.split(",")]
+            try:
+                self.sm.append(float(r[0]))
+                self.mx.append(float(r[1]))
+                for n, v in zip(names, r[2:6]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(n)
+            except Exception:
+                pass
 
     def __enter__(self):
-        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
+            import pynvml as nv
+
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.gpu)
+            self.mx.append(float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)))
+            self.thread = threading.Thread(target=self._nvml_loop, args=(nv, h), daemon=True)
             self.thread.start()
         except Exception:
-            self.proc = None
+            q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+            try:
+                self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+                                             stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                self.thread = threading.Thread(target=self._smi_loop, daemon=True)
+                self.thread.start()
+            except Exception:
+                self.proc = None
         return self
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
-
     def __exit__(self, *a):
+        self.stop.set()
         if self.proc:
             self.proc.terminate()
             try:
                 self.proc.wait(timeout=2)
             except Exception:
                 self.proc.kill()
+        elif self.thread:
+            self.thread.join(timeout=1)
 
     def summary(self) -> dict:
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            try:
-                sm.append(float(r[0]))
-                mx.append(float(r[1]))
-                for n, v in zip(names, r[2:6]):
-                    if v.lower().startswith("active"):
-                        reasons.add(n)
-            except Exception:
-                pass
-        if not sm:
+        if not self.sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": float(max(self.mx)) if self.mx else None, "reasons": sorted(self.reasons),
+                "samples": len(self.sm)}
 
 
 class DevicePtrTensor:
@@ -100,9 +127,9 @@ class DevicePtrTensor:
         self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
 
 
-def build_testbed(rank: int, world: int, n_views: int = N_VIEWS, res: int = RES):
+def build_testbed(rank: int, world: int, n_views: int = N_VIEWS, res: int = RES, device: int = 0):
     P, S = pkg(), syn()
-    tb = P.Testbed()
+    tb = P.Testbed(P.TestbedMode.Nerf, device=device)
     imgs, cams, focal = S.make_dataset(n_images=n_views, width=res, height=res)
     S.load_into_testbed(tb, imgs, cams, focal, aabb_scale=1)
     tb.reload_network_from_json(S.base_config(16, 2, 19))
@@ -220,7 +247,7 @@ def main() -> None:
     __import__("__graft_entry__").build() if not (ROOT / "instant-ngp_b200" / "libngp_b200.so").exists() else None
     P = pkg()
     lib = P.load_library()
-    tb, imgs = build_testbed(rank, world, args.views, args.res)
+    tb, imgs = build_testbed(rank, world, args.views, args.res, device=local_rank)
     if args.no_overlap:
         tb._set("nerf.training.overlap_sample_generation", 0.0)
     if args.chunk:
@@ -236,19 +263,20 @@ def main() -> None:
 
     grads_t = counters_t = None
     if world > 1:
-        grads_t = torch.as_tensor(DevicePtrTensor(tb.grads_ptr(), n_params, "<f2"), device="cuda")
+        grads_t = torch.as_tensor(DevicePtrTensor(tb.grads_ptr(), n_params, "<f2"), device=torch.device("cuda", local_rank))
 
     def step():
         if world == 1:
             tb.train(BATCH)
         else:
-            tb.train_compute_grads(BATCH)
+            tb.train_front(BATCH)          # generation .. loss
             nonlocal counters_t
             if counters_t is None:
-                counters_t = torch.as_tensor(DevicePtrTensor(tb.dp_counters_ptr(), 4, "<i4"), device="cuda")
-            dist.all_reduce(grads_t)       # one NCCL all-reduce of the flat fp16 gradient buffer (hash grid + MLPs)
+                counters_t = torch.as_tensor(DevicePtrTensor(tb.dp_counters_ptr(), 4, "<i4"), device=torch.device("cuda", local_rank))
             dist.all_reduce(counters_t)    # 16 bytes: ray / sample counters for the shared rays_per_batch controller
-            tb.train_apply_grads()
+            tb.train_back()                # forward/backward queued; next step's generator queued behind it on a side stream
+            dist.all_reduce(grads_t)       # one NCCL all-reduce of the flat fp16 gradient buffer (hash grid + MLPs), beside that generator
+            tb.train_apply_grads()         # optimizer
 
     def sync_all():
         torch.cuda.synchronize()

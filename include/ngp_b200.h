@@ -343,6 +343,13 @@ int ngp_testbed_train(ngp_testbed* t, uint32_t batch_size);
 int ngp_testbed_set_dp(ngp_testbed* t, uint32_t rank, uint32_t world);
 int ngp_testbed_train_compute_grads(ngp_testbed* t, uint32_t batch_size);
 int ngp_testbed_train_apply_grads(ngp_testbed* t);
+/* Finer split that lets the next step's ray generation run beside the gradient all-reduce (the counters are needed early for that):
+ *   train_front (generation .. loss)  ->  caller sums ngp_testbed_dp_counters() over ranks  ->  train_back (forward/backward queued,
+ *   rays_per_batch controller updated, next generator queued on a side stream behind the backward kernel)  ->  caller all-reduces
+ *   ngp_testbed_grads()  ->  train_apply_grads (optimizer).  train_compute_grads = train_front + train_back with the controller
+ *   update deferred to train_apply_grads (counters may then be summed any time before it). */
+int ngp_testbed_train_front(ngp_testbed* t, uint32_t batch_size);
+int ngp_testbed_train_back(ngp_testbed* t);
 void* ngp_testbed_grads(ngp_testbed* t);          /* device fp16 [n_params] */
 void* ngp_testbed_params(ngp_testbed* t);         /* device fp16 [n_params] (training params) */
 void* ngp_testbed_params_inference(ngp_testbed* t);/* device fp16 EMA params */

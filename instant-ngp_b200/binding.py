@@ -180,6 +180,8 @@ PROTOTYPES = {
     "ngp_testbed_train": (C.c_int, [vp, u32]),
     "ngp_testbed_set_dp": (C.c_int, [vp, u32, u32]),
     "ngp_testbed_train_compute_grads": (C.c_int, [vp, u32]),
+    "ngp_testbed_train_front": (C.c_int, [vp, u32]),
+    "ngp_testbed_train_back": (C.c_int, [vp]),
     "ngp_testbed_train_apply_grads": (C.c_int, [vp]),
     "ngp_testbed_grads": (vp, [vp]),
     "ngp_testbed_params": (vp, [vp]),

@@ -220,9 +220,10 @@ struct ngp_testbed {
 	uint32_t last_batch = 0;
 	bool grads_pending = false;
 	bool get_loss_pending = false;
-	bool overlap_sample_generation = false;  // measured on B200: the generator competes with the forward/backward kernel for registers (profiles/)
+	bool overlap_sample_generation = true;   // next step's generator on the side stream, gated on this step's forward/backward kernel (see tb_prefetch)
+	bool front_done = false, controller_done = false;
 	cudaStream_t side_stream = nullptr;
-	cudaEvent_t ev_front_done = nullptr, ev_prefetch_done = nullptr, ev_main_ready = nullptr;
+	cudaEvent_t ev_front_done = nullptr, ev_prefetch_done = nullptr, ev_main_ready = nullptr, ev_back_done = nullptr;
 	struct Readback {
 		ngp_nerf_counters counters;
 		float loss_partial[1024];
@@ -231,7 +232,7 @@ struct ngp_testbed {
 	bool prefetch_valid = false;
 	uint32_t prefetch_step = 0, prefetch_batch = 0, prefetch_rays = 0, prefetch_max_inference = 0;
 	uint64_t prefetch_rng_state = 0;
-	uint32_t step_rays_local = 0, step_max_inference = 0;
+	uint32_t step_rays_local = 0, step_max_inference = 0, step_batch = 0;
 	DevBuf<ngp_nerf_counters> dp_counters;  // stable address for the caller's all-reduce of the counter block
 
 	// data parallel
@@ -255,7 +256,7 @@ struct ngp_testbed {
 			cudaStreamSynchronize(side_stream);
 			cudaStreamDestroy(side_stream);
 		}
-		for (cudaEvent_t e : {ev_front_done, ev_prefetch_done, ev_main_ready})
+		for (cudaEvent_t e : {ev_front_done, ev_prefetch_done, ev_main_ready, ev_back_done})
 			if (e) cudaEventDestroy(e);
 		if (readback) cudaFreeHost(readback);
 		for (void* p : pixel_bufs)
@@ -434,6 +435,7 @@ static void tb_ensure_step_scratch(ngp_testbed* t, uint32_t batch) {
 		NGPB_CUDA_CHECK(cudaStreamCreateWithFlags(&t->side_stream, cudaStreamNonBlocking));
 		NGPB_CUDA_CHECK(cudaEventCreateWithFlags(&t->ev_front_done, cudaEventDisableTiming));
 		NGPB_CUDA_CHECK(cudaEventCreateWithFlags(&t->ev_prefetch_done, cudaEventDisableTiming));
+		NGPB_CUDA_CHECK(cudaEventCreateWithFlags(&t->ev_back_done, cudaEventDisableTiming));
 		NGPB_CUDA_CHECK(cudaEventCreateWithFlags(&t->ev_main_ready, cudaEventDisableTiming));
 		NGPB_CUDA_CHECK(cudaHostAlloc(reinterpret_cast<void**>(&t->readback), sizeof(*t->readback), cudaHostAllocDefault));
 	}
@@ -514,14 +516,21 @@ static void tb_launch_generator(ngp_testbed* t, cudaStream_t stream, uint32_t se
 		t->bitfield.p, max_inference, rs.counters.p, rs.ray_indices.p, rs.rays.p, rs.numsteps.p, rs.coords.p, tb_lazy(t) ? rs.t_resume.p : nullptr, t->eager_prefix);
 }
 
-// train_nerf_step up to and including the backward pass (testbed_nerf.cu:3007-3382).  Everything is asynchronous; the
-// host learns the step's counters from a pinned read-back guarded by ev_front_done (waited for in tb_apply_grads, while the
-// GPU is busy with the forward/backward kernel).
-static void tb_compute_grads(ngp_testbed* t, uint32_t batch) {
+// A training step (train_nerf_step, testbed_nerf.cu:3007-3382 + optimizer_step :2770) is issued in three parts so that a
+// data-parallel caller can put its collectives where they belong and so that the next step's sample generation overlaps them:
+//   front  occupancy-grid upkeep, ray generation (or the prefetched one), ray-ordered inference, loss + compaction.
+//          Data parallel: the caller now sums the 16-byte counter block over ranks.
+//   back   forward/backward kernel queued; while it runs the host reads the counters, updates the rays_per_batch controller
+//          (NerfCounters::update_after_training, :2678-2702) and queues the NEXT step's generator on the side stream, gated on
+//          the forward/backward kernel.  Data parallel: the caller now all-reduces the gradients — the generator (0.5 ms) runs
+//          beside the all-reduce and the optimizer instead of after them.
+//   apply  optimizer.
+// Everything is asynchronous; the only host wait is for the counters (ready before the forward/backward kernel starts).
+static void tb_front(ngp_testbed* t, uint32_t batch) {
 	NGPB_CHECK(t->has_network, "Testbed::train: no network (call reload_network_from_json/file first)");
 	NGPB_CHECK(tb_n_views(t) > 0, "Testbed::train: no training images (set nerf.training.n_images_for_training)");
 	NGPB_CHECK(batch % NGP_BATCH_GRANULARITY == 0 && batch > 0, "Testbed::train: batch size must be a positive multiple of 256");
-	NGPB_CHECK(!t->grads_pending, "train_compute_grads called twice without train_apply_grads");
+	NGPB_CHECK(!t->grads_pending && !t->front_done, "training step parts out of order: front called twice");
 	for (uint32_t i = 0; i < tb_n_views(t); ++i) NGPB_CHECK(t->views[i].pixels != nullptr, "Testbed::train: training image " + std::to_string(i) + " was never set");
 	if (batch != t->last_batch) tb_invalidate_prefetch(t);  // buffers may be re-allocated
 	tb_ensure_step_scratch(t, batch);
@@ -581,47 +590,47 @@ static void tb_compute_grads(ngp_testbed* t, uint32_t batch) {
 		NGPB_LAUNCHED();
 		NGPB_CUDA_CHECK(cudaMemcpyAsync(t->readback->loss_partial, t->reduce_scratch.p, sizeof(float) * 1024, cudaMemcpyDeviceToHost, t->stream));
 	}
-	if (t->dp_world == 1) {
-		NGPB_CUDA_CHECK(cudaMemcpyAsync(&t->readback->counters, rs.counters.p, sizeof(ngp_nerf_counters), cudaMemcpyDeviceToHost, t->stream));
+	if (t->dp_world > 1) NGPB_CUDA_CHECK(cudaMemcpyAsync(t->dp_counters.p, rs.counters.p, sizeof(ngp_nerf_counters), cudaMemcpyDeviceToDevice, t->stream));
+	t->step_rays_local = rays_local;
+	t->step_max_inference = max_inference;
+	t->step_batch = batch;
+	t->front_done = true;
+	t->controller_done = false;
+}
+
+static void tb_update_controller(ngp_testbed* t);
+static void tb_prefetch(ngp_testbed* t);
+
+// `early_controller`: read the counters and prefetch now (requires that, data parallel, the counter block has been summed)
+static void tb_back(ngp_testbed* t, bool early_controller) {
+	NGPB_CHECK(t->front_done, "training step parts out of order: back without front");
+	ngp_testbed::RaySet& rs = t->set[t->cur];
+	if (t->dp_world == 1 || early_controller) {
+		NGPB_CUDA_CHECK(cudaMemcpyAsync(&t->readback->counters, t->dp_world == 1 ? rs.counters.p : t->dp_counters.p, sizeof(ngp_nerf_counters),
+			cudaMemcpyDeviceToHost, t->stream));
 		NGPB_CUDA_CHECK(cudaEventRecord(t->ev_front_done, t->stream));
-	} else {
-		NGPB_CUDA_CHECK(cudaMemcpyAsync(t->dp_counters.p, rs.counters.p, sizeof(ngp_nerf_counters), cudaMemcpyDeviceToDevice, t->stream));
 	}
 	{
 		PhaseTimer pt(t, 4);
-		nerf_forward_backward(t->desc, t->stream, batch, t->coords_compacted.p, t->params.p, t->dloss.p, t->grads.p, t->mlp_grads_f32.p, nullptr);
+		nerf_forward_backward(t->desc, t->stream, t->step_batch, t->coords_compacted.p, t->params.p, t->dloss.p, t->grads.p, t->mlp_grads_f32.p, nullptr);
 	}
+	NGPB_CUDA_CHECK(cudaEventRecord(t->ev_back_done, t->stream));
 	t->rng.advance();
+	t->front_done = false;
 	t->grads_pending = true;
-	t->step_rays_local = rays_local;
-	t->step_max_inference = max_inference;
+	if (t->dp_world == 1 || early_controller) {
+		tb_update_controller(t);
+		tb_prefetch(t);
+	}
 }
 
-// optimizer_step + NerfCounters::update_after_training (testbed_nerf.cu:2678-2702, 2770-2788), then the generator of the
-// next step is put on the side stream.
-static void tb_apply_grads(ngp_testbed* t) {
-	NGPB_CHECK(t->grads_pending, "train_apply_grads without train_compute_grads");
-	const uint32_t batch = t->last_batch;
-	if (t->dp_world > 1) {
-		// the caller has summed the counter block over ranks (after the forward/backward kernel in stream order)
-		NGPB_CUDA_CHECK(cudaMemcpyAsync(&t->readback->counters, t->dp_counters.p, sizeof(ngp_nerf_counters), cudaMemcpyDeviceToHost, t->stream));
-		NGPB_CUDA_CHECK(cudaEventRecord(t->ev_front_done, t->stream));
-	}
-	const ngp_adam_cfg a = next_adam_cfg(t->opt, t->optimizer_step, t->lr_factor, t->cfg.loss_scale, t->train_network, t->train_encoding);
-	{
-		PhaseTimer pt(t, 5);
-		optimizer_step(t->desc, t->stream, a, t->params_fp32.p, t->params.p, t->params_ema.p, t->grads.p, t->m1.p, t->m2.p, t->param_steps.p);
-	}
-	++t->training_step;
-	t->grads_pending = false;
-
-	// the counters were copied out before the forward/backward kernel was queued: this wait ends while the GPU still works
+// NerfCounters::update_after_training (testbed_nerf.cu:2678-2702).  The counters were copied out before the forward/backward
+// kernel was queued: the wait ends while the GPU still works.
+static void tb_update_controller(ngp_testbed* t) {
+	const uint32_t batch = t->step_batch;
 	NGPB_CUDA_CHECK(cudaEventSynchronize(t->ev_front_done));
 	const ngp_nerf_counters c = t->readback->counters;
-	if (t->profiling) {
-		NGPB_CUDA_CHECK(cudaStreamSynchronize(t->stream));  // phase timing wants completed events; only paid while profiling
-		tb_collect_phases(t);
-	}
+	t->controller_done = true;
 	const uint32_t n_samples = c.n_samples / t->dp_world, n_compacted = c.n_samples_compacted / t->dp_world;
 	t->measured_batch_size = 0;
 	t->measured_batch_size_before_compaction = 0;
@@ -639,34 +648,57 @@ static void tb_apply_grads(ngp_testbed* t) {
 	}
 	t->rays_per_batch = (uint32_t)((float)t->rays_per_batch * (float)batch / (float)t->measured_batch_size);
 	t->rays_per_batch = std::min(next_multiple(t->rays_per_batch, NGP_BATCH_GRANULARITY), 1u << 18);
+}
 
-	// ---- generator of the next step, concurrently with this step's forward/backward + optimizer
-	if (t->overlap_sample_generation && t->shall_train && !tb_prep_due(t->training_step) && !t->views_dirty) {
-		const uint32_t next = t->cur ^ 1u;
-		const uint32_t max_inference = tb_max_inference(t, batch);
-		// the other buffer set was last read by the loss kernel of the previous step, which precedes ev_front_done on the main
-		// stream; the bitfield and the views are not written by anything in flight
-		NGPB_CUDA_CHECK(cudaStreamWaitEvent(t->side_stream, t->ev_front_done, 0));
-		if (t->profiling) {
-			if (!t->ev[1][0]) {
-				cudaEventCreate(&t->ev[1][0]);
-				cudaEventCreate(&t->ev[1][1]);
-			}
-			cudaEventRecord(t->ev[1][0], t->side_stream);
-		}
-		tb_launch_generator(t, t->side_stream, next, t->rays_per_batch, max_inference);
-		if (t->profiling) {
-			cudaEventRecord(t->ev[1][1], t->side_stream);
-			t->ev_used[1] = true;
-		}
-		NGPB_CUDA_CHECK(cudaEventRecord(t->ev_prefetch_done, t->side_stream));
-		t->prefetch_valid = true;
-		t->prefetch_step = t->training_step;
-		t->prefetch_batch = batch;
-		t->prefetch_rays = t->rays_per_batch;
-		t->prefetch_max_inference = max_inference;
-		t->prefetch_rng_state = t->rng.state;
+// The generator of the NEXT step on the side stream.  It depends on nothing the forward/backward kernel or the optimizer write
+// (rays, occupancy bits, views), so it may run beside the optimizer and — data parallel — beside the gradient all-reduce.  It is
+// gated on the forward/backward kernel: run beside THAT kernel it only slowed the step down (k_nerf_train owns the SMs'
+// registers and shared memory: 1.90 vs 1.68 ms, profiles/r1a).
+static void tb_prefetch(ngp_testbed* t) {
+	const uint32_t next_step = t->training_step + 1;
+	if (!(t->overlap_sample_generation && t->shall_train && !tb_prep_due(next_step) && !t->views_dirty && !t->profiling)) return;
+	const uint32_t batch = t->step_batch;
+	const uint32_t next = t->cur ^ 1u;
+	const uint32_t max_inference = tb_max_inference(t, batch);
+	// the other buffer set was last read by the loss kernel of the previous step, which precedes ev_back_done on the main stream;
+	// the bitfield and the views are not written by anything in flight
+	NGPB_CUDA_CHECK(cudaStreamWaitEvent(t->side_stream, t->ev_back_done, 0));
+	tb_launch_generator(t, t->side_stream, next, t->rays_per_batch, max_inference);
+	NGPB_CUDA_CHECK(cudaEventRecord(t->ev_prefetch_done, t->side_stream));
+	t->prefetch_valid = true;
+	t->prefetch_step = next_step;
+	t->prefetch_batch = batch;
+	t->prefetch_rays = t->rays_per_batch;
+	t->prefetch_max_inference = max_inference;
+	t->prefetch_rng_state = t->rng.state;
+}
+
+// optimizer_step (testbed_nerf.cu:2770-2788).  Data parallel without the early controller: the caller has summed the counter
+// block over ranks by now, so the controller update happens here.
+static void tb_apply_grads(ngp_testbed* t) {
+	NGPB_CHECK(t->grads_pending, "train_apply_grads without train_compute_grads / train_back");
+	if (!t->controller_done) {
+		NGPB_CUDA_CHECK(cudaMemcpyAsync(&t->readback->counters, t->dp_counters.p, sizeof(ngp_nerf_counters), cudaMemcpyDeviceToHost, t->stream));
+		NGPB_CUDA_CHECK(cudaEventRecord(t->ev_front_done, t->stream));
 	}
+	const ngp_adam_cfg a = next_adam_cfg(t->opt, t->optimizer_step, t->lr_factor, t->cfg.loss_scale, t->train_network, t->train_encoding);
+	{
+		PhaseTimer pt(t, 5);
+		optimizer_step(t->desc, t->stream, a, t->params_fp32.p, t->params.p, t->params_ema.p, t->grads.p, t->m1.p, t->m2.p, t->param_steps.p);
+	}
+	if (!t->controller_done) tb_update_controller(t);
+	++t->training_step;
+	t->grads_pending = false;
+	if (t->profiling) {
+		NGPB_CUDA_CHECK(cudaStreamSynchronize(t->stream));  // phase timing wants completed events; only paid while profiling
+		tb_collect_phases(t);
+	}
+}
+
+// front + back without the early controller: the (data-parallel) caller sums counters and gradients, then calls apply
+static void tb_compute_grads(ngp_testbed* t, uint32_t batch) {
+	tb_front(t, batch);
+	tb_back(t, t->dp_world == 1);
 }
 
 }  // namespace ngpb
@@ -987,6 +1019,8 @@ int ngp_testbed_set_dp(ngp_testbed* t, uint32_t rank, uint32_t world) {
 	});
 }
 int ngp_testbed_train_compute_grads(ngp_testbed* t, uint32_t batch) { NGPB_TRY(tb_compute_grads(t, batch)); }
+int ngp_testbed_train_front(ngp_testbed* t, uint32_t batch) { NGPB_TRY(tb_front(t, batch)); }
+int ngp_testbed_train_back(ngp_testbed* t) { NGPB_TRY(tb_back(t, true)); }
 int ngp_testbed_train_apply_grads(ngp_testbed* t) { NGPB_TRY(tb_apply_grads(t)); }
 int ngp_testbed_train(ngp_testbed* t, uint32_t batch) {
 	NGPB_TRY({

@@ -396,6 +396,12 @@ class Testbed:
     def train_compute_grads(self, batch_size: int | None = None) -> None:
         B.check(B.lib().ngp_testbed_train_compute_grads(self._h, int(batch_size or self.training_batch_size)))
 
+    def train_front(self, batch_size: int | None = None) -> None:
+        B.check(B.lib().ngp_testbed_train_front(self._h, int(batch_size or self.training_batch_size)))
+
+    def train_back(self) -> None:
+        B.check(B.lib().ngp_testbed_train_back(self._h))
+
     def train_apply_grads(self) -> None:
         B.check(B.lib().ngp_testbed_train_apply_grads(self._h))
 
