@@ -71,9 +71,14 @@ __device__ inline void random_image_pos_training(Pcg32& rng, int w, int h, bool 
 // at all for those: the warp walks its 32 rays one after the other and its lanes turn consecutive samples of the same ray
 // into coordinates (pos = o + t d, dt = calc_dt(t): the values pass 2 of the reference recomputes, testbed_nerf.cu:822-848),
 // so the work is balanced across lanes whatever the rays' lengths and the 28-byte records leave the warp contiguously.
-// Only the samples beyond GEN_T_SLOTS of a long ray are re-marched by the ray's own thread.
+// Beyond GEN_T_SLOTS, pass 1 keeps one checkpoint of its loop state every GEN_SEG samples; the tails of the long rays of a
+// warp are cut into GEN_SEG-sample segments that the lanes re-march in parallel, each from its checkpoint (a 300-sample ray
+// costs 32 sequential steps instead of 220; ncu r1c: the one-thread tail re-march was half of the kernel's instructions).
 constexpr uint32_t GEN_THREADS = 128;
-constexpr uint32_t GEN_T_SLOTS = 96;   // 96 x 128 x 4 B = 48 KB of shared memory per CTA
+constexpr uint32_t GEN_T_SLOTS = 80;    // 80 x 128 x 4 B = 40 KB of shared memory per CTA
+constexpr uint32_t GEN_SEG = 32;
+constexpr uint32_t GEN_N_CKPT = (NGP_NERF_STEPS - GEN_T_SLOTS + GEN_SEG - 1) / GEN_SEG;   // 30 x 128 x 4 B = 15 KB
+constexpr uint32_t GEN_SMEM_BYTES = (GEN_T_SLOTS + GEN_N_CKPT) * GEN_THREADS * sizeof(float);
 template <bool WRITE_ALL>
 __global__ void __launch_bounds__(GEN_THREADS) k_generate_training_samples(
 	const uint32_t n_rays_local, const uint32_t ray_offset, const uint32_t n_rays_global, Pcg32 rng_in, const ngp_nerf_train_cfg cfg,
@@ -87,10 +92,11 @@ __global__ void __launch_bounds__(GEN_THREADS) k_generate_training_samples(
 	const uint32_t i = ray_offset + li;
 
 	const Aabb aabb{V3{cfg.aabb_min[0], cfg.aabb_min[1], cfg.aabb_min[2]}, V3{cfg.aabb_max[0], cfg.aabb_max[1], cfg.aabb_max[2]}};
-	extern __shared__ float t_list[];   // [GEN_T_SLOTS][GEN_THREADS]
+	extern __shared__ float t_list[];   // [GEN_T_SLOTS][GEN_THREADS], then checkpoints [GEN_N_CKPT][GEN_THREADS]
+	float* ckpt = t_list + GEN_T_SLOTS * GEN_THREADS;
 	uint32_t numsteps = 0;
 	V3 ro{0, 0, 0}, rd{0, 0, 0}, rdn{0, 0, 1}, idir{0, 0, 0};
-	float startt = 0.0f, t_over = 0.0f;
+	float startt = 0.0f;
 
 	if (in_range) {
 		const uint32_t img = image_idx(i, n_rays_global, n_views);
@@ -121,7 +127,7 @@ __global__ void __launch_bounds__(GEN_THREADS) k_generate_training_samples(
 					if (j < GEN_T_SLOTS) t_list[j * GEN_THREADS + threadIdx.x] = t;
 					++j;
 					t += dt;
-					if (j == GEN_T_SLOTS) t_over = t;
+					if (j >= GEN_T_SLOTS && ((j - GEN_T_SLOTS) & (GEN_SEG - 1u)) == 0u) ckpt[((j - GEN_T_SLOTS) / GEN_SEG) * GEN_THREADS + threadIdx.x] = t;
 				} else {
 					t = advance_to_next_voxel(t, cfg.march, pos, rdn, idir, mip);
 				}
@@ -177,33 +183,64 @@ __global__ void __launch_bounds__(GEN_THREADS) k_generate_training_samples(
 			c[0] = wp.x; c[1] = wp.y; c[2] = wp.z; c[3] = warp_dt(dt); c[4] = wdir.x; c[5] = wdir.y; c[6] = wdir.z;
 		}
 	}
-	if (!keep) return;
 
-	// pass 2b: samples beyond the listed ones of a long ray are re-marched by its own thread, from the state pass 1 left
-	float t = numsteps <= GEN_T_SLOTS ? 0.0f : t_over;
-	if (n_write > GEN_T_SLOTS) {
-		const V3 wdir = warp_direction(rdn);
-		float* co = coords_out + (size_t)base * 7;
-		uint32_t j = GEN_T_SLOTS;
-		V3 pos;
-		while (aabb.contains(pos = ro + t * rdn) && j < n_write) {
-			const float dt = calc_dt(t, cfg.march);
-			const uint32_t mip = mip_from_dt(dt, pos, cfg.max_cascade);
-			if (density_grid_occupied_at(pos, bitfield, mip)) {
-				const V3 wp = warp_position(pos, aabb);
-				float* c = co + (size_t)j * 7;
-				c[0] = wp.x; c[1] = wp.y; c[2] = wp.z; c[3] = warp_dt(dt); c[4] = wdir.x; c[5] = wdir.y; c[6] = wdir.z;
-				++j;
-				t += dt;
-			} else {
-				t = advance_to_next_voxel(t, cfg.march, pos, rdn, idir, mip);
+	// pass 2b: the tails (samples beyond GEN_T_SLOTS) of the warp's long rays, cut into GEN_SEG-sample segments; lane l of round
+	// r re-marches segment 32 r + l from its checkpoint
+	{
+		const uint32_t n_tail = n_write > GEN_T_SLOTS ? n_write - GEN_T_SLOTS : 0u;
+		const uint32_t nseg = (n_tail + GEN_SEG - 1u) / GEN_SEG;
+		uint32_t seg_incl = nseg;
+#pragma unroll
+		for (uint32_t o = 1; o < 32; o <<= 1) {
+			const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, seg_incl, o);
+			if (lane >= o) seg_incl += v;
+		}
+		const uint32_t total_seg = __shfl_sync(0xFFFFFFFFu, seg_incl, 31);
+		for (uint32_t s0 = 0; s0 < total_seg; s0 += 32) {
+			const uint32_t sidx = s0 + lane;
+			const bool active = sidx < total_seg;
+			const uint32_t sq = active ? sidx : total_seg - 1u;
+			// owner = first lane whose inclusive segment count exceeds sq
+			uint32_t owner = 0;
+#pragma unroll
+			for (uint32_t step = 16; step >= 1; step >>= 1) {
+				const uint32_t cand = owner + step;
+				const uint32_t v = __shfl_sync(0xFFFFFFFFu, seg_incl, (cand - 1u) & 31u);
+				if (cand <= 31u && v <= sq) owner = cand;
+			}
+			const uint32_t o_incl = __shfl_sync(0xFFFFFFFFu, seg_incl, owner), o_nseg = __shfl_sync(0xFFFFFFFFu, nseg, owner);
+			const uint32_t m = sq - (o_incl - o_nseg);
+			const uint32_t o_base = __shfl_sync(0xFFFFFFFFu, base, owner), o_n = __shfl_sync(0xFFFFFFFFu, n_write, owner);
+			const V3 o_ro{__shfl_sync(0xFFFFFFFFu, ro.x, owner), __shfl_sync(0xFFFFFFFFu, ro.y, owner), __shfl_sync(0xFFFFFFFFu, ro.z, owner)};
+			const V3 o_rdn{__shfl_sync(0xFFFFFFFFu, rdn.x, owner), __shfl_sync(0xFFFFFFFFu, rdn.y, owner), __shfl_sync(0xFFFFFFFFu, rdn.z, owner)};
+			if (!active) continue;
+			const V3 o_idir{1.0f / o_rdn.x, 1.0f / o_rdn.y, 1.0f / o_rdn.z};
+			const V3 wdir = warp_direction(o_rdn);
+			float t = ckpt[m * GEN_THREADS + warp_col0 + owner];
+			uint32_t j = GEN_T_SLOTS + m * GEN_SEG;
+			const uint32_t j_end = (j + GEN_SEG < o_n) ? j + GEN_SEG : o_n;
+			float* co = coords_out + (size_t)o_base * 7;
+			V3 pos;
+			while (aabb.contains(pos = o_ro + t * o_rdn) && j < j_end) {
+				const float dt = calc_dt(t, cfg.march);
+				const uint32_t mip = mip_from_dt(dt, pos, cfg.max_cascade);
+				if (density_grid_occupied_at(pos, bitfield, mip)) {
+					const V3 wp = warp_position(pos, aabb);
+					float* c = co + (size_t)j * 7;
+					c[0] = wp.x; c[1] = wp.y; c[2] = wp.z; c[3] = warp_dt(dt); c[4] = wdir.x; c[5] = wdir.y; c[6] = wdir.z;
+					++j;
+					t += dt;
+				} else {
+					t = advance_to_next_voxel(t, cfg.march, pos, o_rdn, o_idir, mip);
+				}
 			}
 		}
 	}
-	if (!WRITE_ALL) {
+	if (!WRITE_ALL && keep) {
 		// where the consumer resumes the march: the loop state right after the last written sample (its t plus its dt), or the
-		// first sample itself when nothing was written
-		if (n_write < numsteps && n_write <= GEN_T_SLOTS) {
+		// first sample itself when nothing was written.  prefix <= GEN_T_SLOTS (checked by the launcher), so it is in the list.
+		float t = 0.0f;
+		if (n_write < numsteps) {
 			if (n_write == 0) {
 				t = t_list[threadIdx.x];
 			} else {
@@ -592,12 +629,18 @@ void generate_training_samples(cudaStream_t stream, uint32_t n_rays_local, uint3
 	if (n_rays_local == 0) return;
 	NGPB_CHECK(n_views > 0, "generate_training_samples: no training views");
 	NGPB_CHECK(coords != nullptr, "generate_training_samples: no coordinate buffer");
+	static bool attr_set = false;
+	if (!attr_set) {
+		NGPB_CUDA_CHECK(cudaFuncSetAttribute(k_generate_training_samples<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEN_SMEM_BYTES));
+		NGPB_CUDA_CHECK(cudaFuncSetAttribute(k_generate_training_samples<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEN_SMEM_BYTES));
+		attr_set = true;
+	}
 	if (!t_resume) {
-		k_generate_training_samples<true><<<div_round_up(n_rays_local, GEN_THREADS), GEN_THREADS, GEN_T_SLOTS * GEN_THREADS * sizeof(float), stream>>>(n_rays_local, ray_offset, n_rays_global,
+		k_generate_training_samples<true><<<div_round_up(n_rays_local, GEN_THREADS), GEN_THREADS, GEN_SMEM_BYTES, stream>>>(n_rays_local, ray_offset, n_rays_global,
 			Pcg32(rng_state, rng_inc, true), cfg, views, n_views, bitfield, max_samples, counters, ray_indices, rays, numsteps, coords, nullptr, 0u);
 	} else {
-		NGPB_CHECK(prefix % 8u == 0u, "generate_training_samples: the eager prefix must be a multiple of 8");
-		k_generate_training_samples<false><<<div_round_up(n_rays_local, GEN_THREADS), GEN_THREADS, GEN_T_SLOTS * GEN_THREADS * sizeof(float), stream>>>(n_rays_local, ray_offset, n_rays_global,
+		NGPB_CHECK(prefix % 8u == 0u && prefix <= GEN_T_SLOTS, "generate_training_samples: the eager prefix must be a multiple of 8, at most 80");
+		k_generate_training_samples<false><<<div_round_up(n_rays_local, GEN_THREADS), GEN_THREADS, GEN_SMEM_BYTES, stream>>>(n_rays_local, ray_offset, n_rays_global,
 			Pcg32(rng_state, rng_inc, true), cfg, views, n_views, bitfield, max_samples, counters, ray_indices, rays, numsteps, coords, t_resume, prefix);
 	}
 	NGPB_LAUNCHED();

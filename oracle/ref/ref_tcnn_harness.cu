@@ -13,6 +13,8 @@
 #include <neural-graphics-primitives/nerf_network.h>
 
 #include <tiny-cuda-nn/gpu_matrix.h>
+#include <tiny-cuda-nn/loss.h>
+#include <tiny-cuda-nn/network_with_input_encoding.h>
 #include <tiny-cuda-nn/optimizer.h>
 
 #include <cstdio>
@@ -125,6 +127,72 @@ static int run(const char* path, uint32_t n_levels, uint32_t F, uint32_t log2_T,
 	return 0;
 }
 
+// ---- image / SDF primitive: the reference's NetworkWithInputEncoding<__half> + Loss objects, as Trainer::forward / backward use
+// them without JIT fusion (trainer.h:95-150).
+// File layout: u32 magic 'NGPF', u32 n_pos_dims, u32 n_levels, u32 F, u32 log2_T, f32 per_level_scale, u32 n_hidden, u32 n_out,
+//   u32 loss_type (0 L2, 2 MAPE), u32 n_params, u32 n_samples, then fp16 params[n_params], f32 positions[n*D], f32 targets[n*n_out],
+//   fp16 inference_out[n*16], fp16 forward_out[n*16], f32 loss_values[n*16], fp16 dL_dout[n*16], fp16 grads[n_params].
+static int run_field(const char* path, uint32_t n_pos, uint32_t n_levels, uint32_t F, uint32_t log2_T, float per_level_scale, uint32_t n_hidden, uint32_t n_out,
+	uint32_t loss_type, uint32_t n_samples) {
+	json enc = {{"otype", "HashGrid"}, {"n_levels", n_levels}, {"n_features_per_level", F}, {"log2_hashmap_size", log2_T}, {"base_resolution", 16},
+		{"per_level_scale", per_level_scale}};
+	json net = {{"otype", "FullyFusedMLP"}, {"activation", "ReLU"}, {"output_activation", "None"}, {"n_neurons", 64}, {"n_hidden_layers", n_hidden}};
+	auto network = std::make_shared<NetworkWithInputEncoding<precision_t>>(n_pos, n_out, enc, net);
+	network->set_jit_fusion(false);
+	std::shared_ptr<Loss<precision_t>> loss{create_loss<precision_t>(json{{"otype", loss_type == 2 ? "MAPE" : "L2"}})};
+	const size_t n_params = network->n_params();
+	const size_t n_mlp = 64 * 32 + (n_hidden - 1) * 64 * 64 + 16 * 64;
+
+	pcg32 rng{20240922};
+	std::vector<float> p32(n_params);
+	for (size_t i = 0; i < n_params; ++i) p32[i] = (rng.next_float() * 2.0f - 1.0f) * (i < n_mlp ? 0.25f : 0.3f);
+	std::vector<precision_t> p16(n_params);
+	for (size_t i = 0; i < n_params; ++i) p16[i] = (precision_t)p32[i];
+	GPUMemory<precision_t> params(n_params), grads(n_params);
+	params.copy_from_host(p16);
+	grads.memset(0);
+	network->set_params(params.data(), params.data(), grads.data());
+
+	std::vector<float> pos((size_t)n_samples * n_pos), tgt((size_t)n_samples * n_out);
+	for (auto& v : pos) v = rng.next_float();
+	for (auto& v : tgt) v = rng.next_float() * 0.9f + 0.05f;
+	for (uint32_t k = 0; k < n_pos; ++k) { pos[k] = 0.0f; pos[n_pos + k] = 1.0f; }  // exact boundary positions
+	cudaStream_t stream = nullptr;
+	GPUMatrix<float> input(n_pos, n_samples), target(n_out, n_samples);
+	CUDA_CHECK_THROW(cudaMemcpy(input.data(), pos.data(), pos.size() * 4, cudaMemcpyHostToDevice));
+	CUDA_CHECK_THROW(cudaMemcpy(target.data(), tgt.data(), tgt.size() * 4, cudaMemcpyHostToDevice));
+	const uint32_t padded = network->padded_output_width();
+	if (padded != 16) return 4;
+	GPUMatrix<precision_t> out_inf(padded, n_samples), out_fwd(padded, n_samples), dL(padded, n_samples);
+	GPUMatrix<float> values(padded, n_samples);
+	out_inf.memset(0);
+	out_fwd.memset(0);
+	network->inference_mixed_precision(stream, input, out_inf, false);
+	auto ctx = network->forward(stream, input, &out_fwd, false, false);
+	loss->evaluate(stream, 128.0f, out_fwd, target, values, dL);
+	network->backward(stream, *ctx, input, out_fwd, dL, nullptr, false, GradientMode::Overwrite);
+	CUDA_CHECK_THROW(cudaDeviceSynchronize());
+
+	FILE* f = fopen(path, "wb");
+	if (!f) return 3;
+	uint32_t hdr[5] = {0x4650474Eu, n_pos, n_levels, F, log2_T};
+	fwrite(hdr, 4, 5, f);
+	fwrite(&per_level_scale, 4, 1, f);
+	uint32_t tail[5] = {n_hidden, n_out, loss_type, (uint32_t)n_params, n_samples};
+	fwrite(tail, 4, 5, f);
+	put(f, p16);
+	put(f, pos);
+	put(f, tgt);
+	put(f, download(out_inf.data(), (size_t)n_samples * 16));
+	put(f, download(out_fwd.data(), (size_t)n_samples * 16));
+	put(f, download(values.data(), (size_t)n_samples * 16));
+	put(f, download(dL.data(), (size_t)n_samples * 16));
+	put(f, download(grads.data(), n_params));
+	fclose(f);
+	printf("wrote %s: D=%u L=%u F=%u T=2^%u hidden=%u out=%u loss=%u n_params=%zu n=%u\n", path, n_pos, n_levels, F, log2_T, n_hidden, n_out, loss_type, n_params, n_samples);
+	return 0;
+}
+
 int main(int argc, char** argv) {
 	if (argc < 2) {
 		fprintf(stderr, "usage: ref_tcnn <out_dir>\n");
@@ -135,6 +203,11 @@ int main(int argc, char** argv) {
 		int rc = run((dir + "/ref_tcnn_L16F2.bin").c_str(), 16, 2, 10, 1.5157166f, 512);
 		if (rc) return rc;
 		rc = run((dir + "/ref_tcnn_L8F4.bin").c_str(), 8, 4, 10, 2.4380093f, 512);
+		if (rc) return rc;
+		// image primitive (2-D grid, 3 outputs, L2) and SDF primitive (3-D grid, 1 output, MAPE), configs/{image,sdf}/base.json shapes
+		rc = run_field((dir + "/ref_field_image.bin").c_str(), 2, 16, 2, 10, 1.3819129f, 2, 3, 0, 512);
+		if (rc) return rc;
+		rc = run_field((dir + "/ref_field_sdf.bin").c_str(), 3, 16, 2, 10, 1.3819129f, 2, 1, 2, 512);
 		return rc;
 	} catch (const std::exception& e) {
 		fprintf(stderr, "ref_tcnn failed: %s\n", e.what());
