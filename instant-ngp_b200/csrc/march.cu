@@ -94,6 +94,7 @@ __global__ void __launch_bounds__(GEN_THREADS) k_generate_training_samples(
 	const Aabb aabb{V3{cfg.aabb_min[0], cfg.aabb_min[1], cfg.aabb_min[2]}, V3{cfg.aabb_max[0], cfg.aabb_max[1], cfg.aabb_max[2]}};
 	extern __shared__ float t_list[];   // [GEN_T_SLOTS][GEN_THREADS], then checkpoints [GEN_N_CKPT][GEN_THREADS]
 	float* ckpt = t_list + GEN_T_SLOTS * GEN_THREADS;
+	__shared__ float coord_tile[GEN_THREADS / 32][32 * 7];
 	uint32_t numsteps = 0;
 	V3 ro{0, 0, 0}, rd{0, 0, 0}, rdn{0, 0, 1}, idir{0, 0, 0};
 	float startt = 0.0f;
@@ -174,13 +175,29 @@ __global__ void __launch_bounds__(GEN_THREADS) k_generate_training_samples(
 		const V3 ro_s{__shfl_sync(0xFFFFFFFFu, ro.x, src), __shfl_sync(0xFFFFFFFFu, ro.y, src), __shfl_sync(0xFFFFFFFFu, ro.z, src)};
 		const V3 rdn_s{__shfl_sync(0xFFFFFFFFu, rdn.x, src), __shfl_sync(0xFFFFFFFFu, rdn.y, src), __shfl_sync(0xFFFFFFFFu, rdn.z, src)};
 		const V3 wdir = warp_direction(rdn_s);
-		for (uint32_t k = lane; k < n_s; k += 32) {
-			const float t = t_list[k * GEN_THREADS + warp_col0 + src];
-			const V3 pos = ro_s + t * rdn_s;
-			const float dt = calc_dt(t, cfg.march);
-			const V3 wp = warp_position(pos, aabb);
-			float* c = coords_out + (size_t)(base_s + k) * 7;
-			c[0] = wp.x; c[1] = wp.y; c[2] = wp.z; c[3] = warp_dt(dt); c[4] = wdir.x; c[5] = wdir.y; c[6] = wdir.z;
+		// 32 records of 28 bytes = 224 consecutive floats: transposed through shared memory so that every store instruction of the
+		// warp covers 128 contiguous bytes (per-lane 4-byte stores at a 28-byte stride hit 32 sectors each: the L2 write path,
+		// not the march, was then what this pass waited for)
+		float* tile = coord_tile[threadIdx.x >> 5];
+		for (uint32_t k0 = 0; k0 < n_s; k0 += 32) {
+			const uint32_t k = k0 + lane;
+			__syncwarp();
+			if (k < n_s) {
+				const float t = t_list[k * GEN_THREADS + warp_col0 + src];
+				const V3 pos = ro_s + t * rdn_s;
+				const float dt = calc_dt(t, cfg.march);
+				const V3 wp = warp_position(pos, aabb);
+				float* c = tile + lane * 7;
+				c[0] = wp.x; c[1] = wp.y; c[2] = wp.z; c[3] = warp_dt(dt); c[4] = wdir.x; c[5] = wdir.y; c[6] = wdir.z;
+			}
+			__syncwarp();
+			const uint32_t cnt = ((n_s - k0) < 32u ? (n_s - k0) : 32u) * 7u;
+			float* dst = coords_out + (size_t)(base_s + k0) * 7;
+#pragma unroll
+			for (uint32_t q = 0; q < 7; ++q) {
+				const uint32_t e = q * 32u + lane;
+				if (e < cnt) dst[e] = tile[e];
+			}
 		}
 	}
 
@@ -419,12 +436,12 @@ __global__ void __launch_bounds__(128) k_compute_loss(
 		if (mine) {
 			st = sample_terms(no, ci, k, cfg, o0, o1, o2, o3, dt);
 #pragma unroll
-			for (int q = 0; q < 7; ++q) {
-				c[q] = ci[(size_t)k * 7 + q];
-				co[(size_t)k * 7 + q] = c[q];
-			}
+			for (int q = 0; q < 7; ++q) c[q] = ci[(size_t)k * 7 + q];
 		}
 		const uint32_t n_here = (compacted_numsteps - c0) < 32u ? (compacted_numsteps - c0) : 32u;
+		// the compacted copy of these n_here coordinate records is one contiguous block: 128 contiguous bytes per store instruction
+		// instead of 4-byte stores at a 28-byte stride
+		for (uint32_t e = lane; e < n_here * 7u; e += 32) co[(size_t)c0 * 7 + e] = ci[(size_t)c0 * 7 + e];
 		float my_weight = 0.0f, my_T = 0.0f;
 		V3 my_rgb_ray2{0, 0, 0};
 		for (uint32_t j = 0; j < n_here; ++j) {
