@@ -322,14 +322,14 @@ def main() -> None:
     tb.set_profiling(False)
 
     # ---- e2e: one training view streamed from pinned host memory per step + counters/loss read back
-    pinned = torch.from_numpy(np.ascontiguousarray(imgs[0])).pin_memory()
-    h2d_bytes = pinned.numel() * 4
+    pinned = torch.from_numpy(np.ascontiguousarray(imgs)).pin_memory()   # the whole image set in pinned host memory, one view re-sent per step
+    h2d_bytes = pinned[0].numel() * 4
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2e_samples = 0
     sync_all()
     f0.record()
     for i in range(args.steps):
-        tb.update_image_async(i % args.views, pinned.data_ptr())   # H2D of this step's new training view
+        tb.update_image_async(i % args.views, pinned[i % args.views].data_ptr())   # H2D of this step's training view
         step()
         e2e_samples += tb.counters()["measured_batch_size"]        # D2H: counters (16 B) each step, loss every 16th
         _ = tb.loss

@@ -75,9 +75,11 @@ __device__ inline void random_image_pos_training(Pcg32& rng, int w, int h, bool 
 // warp are cut into GEN_SEG-sample segments that the lanes re-march in parallel, each from its checkpoint (a 300-sample ray
 // costs 32 sequential steps instead of 220; ncu r1c: the one-thread tail re-march was half of the kernel's instructions).
 constexpr uint32_t GEN_THREADS = 128;
-constexpr uint32_t GEN_T_SLOTS = 80;    // 80 x 128 x 4 B = 40 KB of shared memory per CTA
+constexpr uint32_t GEN_T_SLOTS = 64;    // 64 x 128 x 4 B = 32 KB of shared memory per CTA
 constexpr uint32_t GEN_SEG = 32;
 constexpr uint32_t GEN_N_CKPT = (NGP_NERF_STEPS - GEN_T_SLOTS + GEN_SEG - 1) / GEN_SEG;   // 30 x 128 x 4 B = 15 KB
+// 47 KB dynamic + 3.5 KB static (coordinate tile) + 1 KB reserved = 4 CTAs per SM = 592 resident CTAs = 75 K rays in one wave.
+// (At 3 CTAs per SM a steady-state batch of 57-66 K rays spilled into a second wave: 0.53 -> 0.80 ms, bimodal from run to run.)
 constexpr uint32_t GEN_SMEM_BYTES = (GEN_T_SLOTS + GEN_N_CKPT) * GEN_THREADS * sizeof(float);
 template <bool WRITE_ALL>
 __global__ void __launch_bounds__(GEN_THREADS) k_generate_training_samples(
@@ -656,7 +658,7 @@ void generate_training_samples(cudaStream_t stream, uint32_t n_rays_local, uint3
 		k_generate_training_samples<true><<<div_round_up(n_rays_local, GEN_THREADS), GEN_THREADS, GEN_SMEM_BYTES, stream>>>(n_rays_local, ray_offset, n_rays_global,
 			Pcg32(rng_state, rng_inc, true), cfg, views, n_views, bitfield, max_samples, counters, ray_indices, rays, numsteps, coords, nullptr, 0u);
 	} else {
-		NGPB_CHECK(prefix % 8u == 0u && prefix <= GEN_T_SLOTS, "generate_training_samples: the eager prefix must be a multiple of 8, at most 80");
+		NGPB_CHECK(prefix % 8u == 0u && prefix <= GEN_T_SLOTS, "generate_training_samples: the eager prefix must be a multiple of 8, at most 64");
 		k_generate_training_samples<false><<<div_round_up(n_rays_local, GEN_THREADS), GEN_THREADS, GEN_SMEM_BYTES, stream>>>(n_rays_local, ray_offset, n_rays_global,
 			Pcg32(rng_state, rng_inc, true), cfg, views, n_views, bitfield, max_samples, counters, ray_indices, rays, numsteps, coords, t_resume, prefix);
 	}
