@@ -123,10 +123,11 @@ __global__ void __launch_bounds__(GEN_THREADS) k_generate_training_samples(
 			uint32_t j = 0;
 			float t = startt;
 			V3 pos;
+			OccCache occ;
 			while (aabb.contains(pos = ro + t * rdn) && j < NGP_NERF_STEPS) {
 				const float dt = calc_dt(t, cfg.march);
 				const uint32_t mip = mip_from_dt(dt, pos, cfg.max_cascade);
-				if (density_grid_occupied_at(pos, bitfield, mip)) {
+				if (density_grid_occupied_cached(pos, bitfield, mip, occ)) {
 					if (j < GEN_T_SLOTS) t_list[j * GEN_THREADS + threadIdx.x] = t;
 					++j;
 					t += dt;
@@ -240,10 +241,11 @@ __global__ void __launch_bounds__(GEN_THREADS) k_generate_training_samples(
 			const uint32_t j_end = (j + GEN_SEG < o_n) ? j + GEN_SEG : o_n;
 			float* co = coords_out + (size_t)o_base * 7;
 			V3 pos;
+			OccCache occ;
 			while (aabb.contains(pos = o_ro + t * o_rdn) && j < j_end) {
 				const float dt = calc_dt(t, cfg.march);
 				const uint32_t mip = mip_from_dt(dt, pos, cfg.max_cascade);
-				if (density_grid_occupied_at(pos, bitfield, mip)) {
+				if (density_grid_occupied_cached(pos, bitfield, mip, occ)) {
 					const V3 wp = warp_position(pos, aabb);
 					float* c = co + (size_t)j * 7;
 					c[0] = wp.x; c[1] = wp.y; c[2] = wp.z; c[3] = warp_dt(dt); c[4] = wdir.x; c[5] = wdir.y; c[6] = wdir.z;

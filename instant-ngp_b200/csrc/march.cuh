@@ -99,6 +99,7 @@ __host__ __device__ inline float advance_to_next_voxel(float t, const ngp_march_
 __host__ __device__ inline int clampi(int a, int lo, int hi) { return a < lo ? lo : (hi < a ? hi : a); }
 // nerf_device.cuh:443-460
 __host__ __device__ inline uint32_t mip_from_pos(V3 pos, uint32_t max_cascade) {
+	if (max_cascade == 0) return 0;  // clamp(exponent + 1, 0, 0)
 	int exponent;
 	const float maxval = fmaxf(fmaxf(fabsf(pos.x - 0.5f), fabsf(pos.y - 0.5f)), fabsf(pos.z - 0.5f));
 	frexpf(maxval, &exponent);
@@ -124,6 +125,26 @@ __host__ __device__ inline bool density_grid_occupied_at(V3 pos, const uint8_t* 
 	const uint32_t idx = cascaded_grid_idx_at(pos, mip);
 	if (idx == 0xFFFFFFFFu) return false;
 	return (bitfield[idx / 8 + (GRID_N_CELLS * mip) / 8] & (1u << (idx % 8))) != 0;
+}
+
+// One-entry cache of a march's last occupancy test.  Consecutive samples of a ray mostly fall into the same cell (the minimum
+// step is a 4.6th of a mip-0 cell), and the test is a pure function of (cell, mip): re-using its result is exact.  Saves the
+// Morton interleave and the bitfield load (ncu r1c: that load's latency was the largest single stall of the generator).
+struct OccCache {
+	uint32_t key = 0xFFFFFFFFu;
+	bool occ = false;
+};
+__host__ __device__ inline bool density_grid_occupied_cached(V3 pos, const uint8_t* __restrict__ bitfield, uint32_t mip, OccCache& c) {
+	const float mip_scale = scalbnf(1.0f, -(int)mip);
+	const float px = (pos.x - 0.5f) * mip_scale + 0.5f, py = (pos.y - 0.5f) * mip_scale + 0.5f, pz = (pos.z - 0.5f) * mip_scale + 0.5f;
+	const int ix = (int)(px * 128.0f), iy = (int)(py * 128.0f), iz = (int)(pz * 128.0f);
+	if (ix < 0 || ix >= 128 || iy < 0 || iy >= 128 || iz < 0 || iz >= 128) return false;
+	const uint32_t key = (uint32_t)ix | ((uint32_t)iy << 7) | ((uint32_t)iz << 14) | (mip << 21);
+	if (key == c.key) return c.occ;
+	const uint32_t idx = morton3d((uint32_t)ix, (uint32_t)iy, (uint32_t)iz);
+	c.key = key;
+	c.occ = (bitfield[idx / 8 + (GRID_N_CELLS * mip) / 8] & (1u << (idx % 8))) != 0;
+	return c.occ;
 }
 
 // ---- activations (nerf_device.cuh:204-264) ---------------------------------------------------------------------------
