@@ -200,6 +200,21 @@ int ngp_nerf_generate_training_samples(void* stream, uint32_t n_rays, uint32_t r
 	const ngp_nerf_train_cfg* cfg, const ngp_train_view* views_dev, uint32_t n_views, const uint8_t* density_grid_bitfield,
 	uint32_t max_samples, ngp_nerf_counters* counters_dev, uint32_t* ray_indices, float* rays, uint32_t* numsteps, float* coords);
 
+/* generate_training_samples_nerf as two kernels (what Testbed::train uses): ngp_nerf_count_training_samples does the ray
+ * generation, the counting march and the slot reservation — outputs as ngp_nerf_generate_training_samples minus the
+ * coordinates, plus a checkpoint of the march every 32 samples in ckpt_scratch (ngp_nerf_generator_scratch_floats(n_rays) floats)
+ * and (count, base, slot) per ray in seg_scratch (ngp_nerf_generator_scratch_u32(n_rays) words).  It is bound by the serial
+ * latency of the longest ray, needs no shared memory and may run on a side stream beside the previous step's backward pass.
+ * ngp_nerf_write_training_samples then produces all coordinates, one warp per ray, lane m re-marching samples [32m, 32m+32).
+ * Per ray id the results are bit-identical to ngp_nerf_generate_training_samples. */
+size_t ngp_nerf_generator_scratch_floats(uint32_t max_rays);
+size_t ngp_nerf_generator_scratch_u32(uint32_t max_rays);
+int ngp_nerf_count_training_samples(void* stream, uint32_t n_rays, uint32_t ray_offset, uint32_t n_rays_global, uint64_t rng_state, uint64_t rng_inc,
+	const ngp_nerf_train_cfg* cfg, const ngp_train_view* views_dev, uint32_t n_views, const uint8_t* density_grid_bitfield, uint32_t max_samples,
+	ngp_nerf_counters* counters, uint32_t* ray_indices, float* rays, uint32_t* numsteps, float* ckpt_scratch, uint32_t* seg_scratch);
+int ngp_nerf_write_training_samples(void* stream, uint32_t n_rays, const ngp_nerf_train_cfg* cfg, const uint8_t* density_grid_bitfield, const float* rays,
+	const float* ckpt_scratch, const uint32_t* seg_scratch, float* coords);
+
 /* generate_training_samples_nerf with its coordinate pass cut short, so that coordinates are produced only where they are
  * consumed: ngp_nerf_generate_training_samples_prefix counts every ray in full (ray records, numsteps = (count, base): identical
  * to ngp_nerf_generate_training_samples) but writes only the first `prefix` (multiple of 8) coordinates of each ray, plus

@@ -274,6 +274,137 @@ __global__ void __launch_bounds__(GEN_THREADS) k_generate_training_samples(
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// The generator as two kernels, for the training pipeline (testbed.cu):
+//   k_count_training_samples   ray generation + the counting march + slot reservation.  One thread per ray; its time is the
+//                              serial latency of the batch's longest ray (~0.4 ms), not throughput — it needs no shared memory
+//                              and 64 registers, so it can run beside the previous step's backward kernel and optimizer.  Every
+//                              GEN_SEG-th sample's t goes to a global checkpoint table.
+//   k_write_training_samples   one WARP per ray, lane m re-marches samples [32 m, 32 m + 32) from checkpoint m with the same
+//                              arithmetic: all of a step's coordinates in ~32 sequential march steps.
+// Outputs are those of k_generate_training_samples (same per-ray counts, records and coordinates; slot order differs).
+// ------------------------------------------------------------------------------------------------------------------
+constexpr uint32_t GEN_MAX_SEG = NGP_NERF_STEPS / GEN_SEG;   // 32 checkpoints per ray
+
+__global__ void __launch_bounds__(GEN_THREADS) k_count_training_samples(
+	const uint32_t n_rays_local, const uint32_t ray_offset, const uint32_t n_rays_global, Pcg32 rng_in, const ngp_nerf_train_cfg cfg,
+	const ngp_train_view* __restrict__ views, const uint32_t n_views, const uint8_t* __restrict__ bitfield, const uint32_t max_samples,
+	ngp_nerf_counters* __restrict__ counters, uint32_t* __restrict__ ray_indices_out, float* __restrict__ rays_out,
+	uint32_t* __restrict__ numsteps_out, float* __restrict__ ckpt_out, uint32_t* __restrict__ seg_info_out
+) {
+	const uint32_t li = blockIdx.x * blockDim.x + threadIdx.x;
+	const uint32_t lane = threadIdx.x & 31u;
+	const bool in_range = li < n_rays_local;
+	const uint32_t i = ray_offset + li;
+	const Aabb aabb{V3{cfg.aabb_min[0], cfg.aabb_min[1], cfg.aabb_min[2]}, V3{cfg.aabb_max[0], cfg.aabb_max[1], cfg.aabb_max[2]}};
+	uint32_t numsteps = 0;
+	V3 ro{0, 0, 0}, rd{0, 0, 0};
+
+	if (in_range) {
+		const uint32_t img = image_idx(i, n_rays_global, n_views);
+		const ngp_train_view vw = views[img];
+		Pcg32 rng = rng_in;
+		rng.advance((uint64_t)i * N_MAX_RANDOM_SAMPLES_PER_RAY);
+		float u, v;
+		random_image_pos_training(rng, vw.width, vw.height, cfg.snap_to_pixel_centers != 0, u, v);
+		const bool masked = !vw.no_mask && read_rgba_uv(u, v, vw.width, vw.height, vw.pixels, vw.image_type).r < 0.0f;
+		if (!masked) {
+			(void)rng.next_float();  // motion-blur time (testbed_nerf.cu:740)
+			uv_to_ray(u, v, vw.width, vw.height, vw.focal_x, vw.focal_y, vw.principal_x, vw.principal_y, vw.lens_mode, vw.lens_params, vw.xform, ro, rd);
+			const V3 rdn = normalize3(rd);
+			float tmin, tmax;
+			aabb_ray_intersect(aabb, ro, rdn, tmin, tmax);
+			tmin = fmaxf(tmin, 0.0f);
+			const float startt = advance_n_steps(tmin, cfg.march, rng.next_float());
+			const V3 idir{1.0f / rdn.x, 1.0f / rdn.y, 1.0f / rdn.z};
+			float* ck = ckpt_out + (size_t)li * GEN_MAX_SEG;
+			uint32_t j = 0;
+			float t = startt;
+			V3 pos;
+			OccCache occ;
+			while (aabb.contains(pos = ro + t * rdn) && j < NGP_NERF_STEPS) {
+				const float dt = calc_dt(t, cfg.march);
+				const uint32_t mip = mip_from_dt(dt, pos, cfg.max_cascade);
+				if (density_grid_occupied_cached(pos, bitfield, mip, occ)) {
+					if ((j & (GEN_SEG - 1u)) == 0u) ck[j / GEN_SEG] = t;   // resuming the loop at this t finds sample j first
+					++j;
+					t += dt;
+				} else {
+					t = advance_to_next_voxel(t, cfg.march, pos, rdn, idir, mip);
+				}
+			}
+			numsteps = j;
+		}
+	}
+
+	// ---- warp-level reservation of sample slots and ray slots (as k_generate_training_samples)
+	uint32_t incl = numsteps;
+#pragma unroll
+	for (uint32_t o = 1; o < 32; o <<= 1) {
+		const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+		if (lane >= o) incl += t;
+	}
+	const uint32_t warp_total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+	uint32_t warp_base = 0;
+	if (lane == 0 && warp_total > 0) warp_base = atomicAdd(&counters->n_samples, warp_total);
+	warp_base = __shfl_sync(0xFFFFFFFFu, warp_base, 0);
+	const uint32_t base = warp_base + incl - numsteps;
+	const bool keep = numsteps > 0 && (base + numsteps <= max_samples);
+	const uint32_t keep_mask = __ballot_sync(0xFFFFFFFFu, keep);
+	uint32_t ray_base = 0;
+	if (lane == 0 && keep_mask) ray_base = atomicAdd(&counters->n_rays, __popc(keep_mask));
+	ray_base = __shfl_sync(0xFFFFFFFFu, ray_base, 0);
+	const uint32_t ray_idx = ray_base + __popc(keep_mask & ((1u << lane) - 1u));
+	if (in_range) {
+		seg_info_out[(size_t)li * 3 + 0] = keep ? numsteps : 0u;
+		seg_info_out[(size_t)li * 3 + 1] = base;
+		seg_info_out[(size_t)li * 3 + 2] = ray_idx;
+	}
+	if (!keep) return;
+	ray_indices_out[ray_idx] = i;
+	float* r = rays_out + (size_t)ray_idx * 6;
+	r[0] = ro.x; r[1] = ro.y; r[2] = ro.z; r[3] = rd.x; r[4] = rd.y; r[5] = rd.z;
+	numsteps_out[ray_idx * 2 + 0] = numsteps;
+	numsteps_out[ray_idx * 2 + 1] = base;
+}
+
+__global__ void __launch_bounds__(GEN_THREADS) k_write_training_samples(
+	const uint32_t n_rays_local, const ngp_nerf_train_cfg cfg, const uint8_t* __restrict__ bitfield, const float* __restrict__ rays_in,
+	const float* __restrict__ ckpt_in, const uint32_t* __restrict__ seg_info_in, float* __restrict__ coords_out
+) {
+	const uint32_t li = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;   // one warp per ray
+	const uint32_t m = threadIdx.x & 31u;                               // one lane per 32-sample segment
+	if (li >= n_rays_local) return;
+	const uint32_t n = seg_info_in[(size_t)li * 3 + 0];
+	if (m * GEN_SEG >= n) return;
+	const uint32_t base = seg_info_in[(size_t)li * 3 + 1], ray_idx = seg_info_in[(size_t)li * 3 + 2];
+	const Aabb aabb{V3{cfg.aabb_min[0], cfg.aabb_min[1], cfg.aabb_min[2]}, V3{cfg.aabb_max[0], cfg.aabb_max[1], cfg.aabb_max[2]}};
+	const float* rp = rays_in + (size_t)ray_idx * 6;
+	const V3 ro{rp[0], rp[1], rp[2]};
+	const V3 rdn = normalize3(V3{rp[3], rp[4], rp[5]});
+	const V3 idir{1.0f / rdn.x, 1.0f / rdn.y, 1.0f / rdn.z};
+	const V3 wdir = warp_direction(rdn);
+	float t = ckpt_in[(size_t)li * GEN_MAX_SEG + m];
+	uint32_t j = m * GEN_SEG;
+	const uint32_t j_end = (j + GEN_SEG < n) ? j + GEN_SEG : n;
+	float* co = coords_out + (size_t)base * 7;
+	V3 pos;
+	OccCache occ;
+	while (aabb.contains(pos = ro + t * rdn) && j < j_end) {
+		const float dt = calc_dt(t, cfg.march);
+		const uint32_t mip = mip_from_dt(dt, pos, cfg.max_cascade);
+		if (density_grid_occupied_cached(pos, bitfield, mip, occ)) {
+			const V3 wp = warp_position(pos, aabb);
+			float* c = co + (size_t)j * 7;
+			c[0] = wp.x; c[1] = wp.y; c[2] = wp.z; c[3] = warp_dt(dt); c[4] = wdir.x; c[5] = wdir.y; c[6] = wdir.z;
+			++j;
+			t += dt;
+		} else {
+			t = advance_to_next_voxel(t, cfg.march, pos, rdn, idir, mip);
+		}
+	}
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // losses (nerf_device.cuh:75-143, 601-616)
 // ------------------------------------------------------------------------------------------------------------------
 __device__ inline void loss_and_gradient1(float target, float pred, uint32_t type, float& loss, float& grad) {
@@ -664,6 +795,28 @@ void generate_training_samples(cudaStream_t stream, uint32_t n_rays_local, uint3
 		k_generate_training_samples<false><<<div_round_up(n_rays_local, GEN_THREADS), GEN_THREADS, GEN_SMEM_BYTES, stream>>>(n_rays_local, ray_offset, n_rays_global,
 			Pcg32(rng_state, rng_inc, true), cfg, views, n_views, bitfield, max_samples, counters, ray_indices, rays, numsteps, coords, t_resume, prefix);
 	}
+	NGPB_LAUNCHED();
+	NGPB_CUDA_CHECK(cudaGetLastError());
+}
+
+size_t generator_scratch_floats(uint32_t max_rays) { return (size_t)max_rays * GEN_MAX_SEG; }   // checkpoint table
+size_t generator_scratch_u32(uint32_t max_rays) { return (size_t)max_rays * 3; }                 // (count, base, ray slot) per ray
+
+void count_training_samples(cudaStream_t stream, uint32_t n_rays_local, uint32_t ray_offset, uint32_t n_rays_global, uint64_t rng_state, uint64_t rng_inc,
+	const ngp_nerf_train_cfg& cfg, const ngp_train_view* views, uint32_t n_views, const uint8_t* bitfield, uint32_t max_samples, ngp_nerf_counters* counters,
+	uint32_t* ray_indices, float* rays, uint32_t* numsteps, float* ckpt, uint32_t* seg_info) {
+	if (n_rays_local == 0) return;
+	NGPB_CHECK(n_views > 0, "generate_training_samples: no training views");
+	k_count_training_samples<<<div_round_up(n_rays_local, GEN_THREADS), GEN_THREADS, 0, stream>>>(n_rays_local, ray_offset, n_rays_global,
+		Pcg32(rng_state, rng_inc, true), cfg, views, n_views, bitfield, max_samples, counters, ray_indices, rays, numsteps, ckpt, seg_info);
+	NGPB_LAUNCHED();
+	NGPB_CUDA_CHECK(cudaGetLastError());
+}
+
+void write_training_samples(cudaStream_t stream, uint32_t n_rays_local, const ngp_nerf_train_cfg& cfg, const uint8_t* bitfield, const float* rays, const float* ckpt,
+	const uint32_t* seg_info, float* coords) {
+	if (n_rays_local == 0) return;
+	k_write_training_samples<<<div_round_up(n_rays_local * 32u, GEN_THREADS), GEN_THREADS, 0, stream>>>(n_rays_local, cfg, bitfield, rays, ckpt, seg_info, coords);
 	NGPB_LAUNCHED();
 	NGPB_CUDA_CHECK(cudaGetLastError());
 }

@@ -33,6 +33,13 @@ void optimizer_step(const ngp_nerf_desc& d, cudaStream_t stream, const ngp_adam_
 void generate_training_samples(cudaStream_t stream, uint32_t n_rays_local, uint32_t ray_offset, uint32_t n_rays_global, uint64_t rng_state, uint64_t rng_inc,
 	const ngp_nerf_train_cfg& cfg, const ngp_train_view* views, uint32_t n_views, const uint8_t* bitfield, uint32_t max_samples, ngp_nerf_counters* counters,
 	uint32_t* ray_indices, float* rays, uint32_t* numsteps, float* coords, float* t_resume, uint32_t prefix);
+size_t generator_scratch_floats(uint32_t max_rays);
+size_t generator_scratch_u32(uint32_t max_rays);
+void count_training_samples(cudaStream_t stream, uint32_t n_rays_local, uint32_t ray_offset, uint32_t n_rays_global, uint64_t rng_state, uint64_t rng_inc,
+	const ngp_nerf_train_cfg& cfg, const ngp_train_view* views, uint32_t n_views, const uint8_t* bitfield, uint32_t max_samples, ngp_nerf_counters* counters,
+	uint32_t* ray_indices, float* rays, uint32_t* numsteps, float* ckpt, uint32_t* seg_info);
+void write_training_samples(cudaStream_t stream, uint32_t n_rays_local, const ngp_nerf_train_cfg& cfg, const uint8_t* bitfield, const float* rays, const float* ckpt,
+	const uint32_t* seg_info, float* coords);
 void nerf_march_inference_rays(const ngp_nerf_desc& d, cudaStream_t stream, uint32_t n_rays_max, const ngp_nerf_train_cfg& cfg, const ngp_nerf_counters* counters,
 	uint32_t* queue, const uint32_t* numsteps, const float* rays, const float* t_resume, uint32_t prefix, const uint8_t* bitfield, float* coords,
 	const __half* params, __half* out, uint32_t chunk);
@@ -189,6 +196,8 @@ struct ngp_testbed {
 	bool full_inference = false;
 	bool lazy_sample_generation = false;  // measured slower (profiles/r1c): the generator writes a prefix of each ray's coordinates; the ray-ordered inference kernel marches the rest on demand
 	uint32_t eager_prefix = 16;
+	bool split_generation = true;    // count kernel (prefetchable beside the backward pass) + warp-per-ray write kernel
+	bool overlap_gate = false;       // true: the prefetched generator waits for the forward/backward kernel
 	uint32_t inference_chunk = 8;
 
 	DevBuf<float> params_fp32, m1, m2, mlp_grads_f32;
@@ -212,7 +221,8 @@ struct ngp_testbed {
 	struct RaySet {
 		DevBuf<ngp_nerf_counters> counters;
 		DevBuf<uint32_t> ray_indices, numsteps;
-		DevBuf<float> rays, coords, t_resume;
+		DevBuf<float> rays, coords, t_resume, ckpt;
+		DevBuf<uint32_t> seg_info;
 	} set[2];
 	uint32_t cur = 0;                     // set used by the step in flight
 	DevBuf<float> coords_compacted, loss_per_ray, reduce_scratch;
@@ -427,6 +437,8 @@ static void tb_ensure_step_scratch(ngp_testbed* t, uint32_t batch) {
 		rs.rays.ensure((size_t)max_rays * 6);
 		rs.coords.ensure((size_t)max_samples * 7);
 		rs.t_resume.ensure(max_rays);
+		rs.ckpt.ensure(generator_scratch_floats(max_rays));
+		rs.seg_info.ensure(generator_scratch_u32(max_rays));
 	}
 	t->loss_per_ray.ensure(max_rays);
 	t->reduce_scratch.ensure(1024);
@@ -509,11 +521,24 @@ static void tb_invalidate_prefetch(ngp_testbed* t) {
 	t->prefetch_valid = false;
 }
 static bool tb_lazy(const ngp_testbed* t) { return t->lazy_sample_generation && !t->full_inference; }
+static bool tb_split(const ngp_testbed* t) { return t->split_generation && !tb_lazy(t); }
+// The part of the generator that may be prefetched: everything (fused kernel) or the counting kernel (split generation).
 static void tb_launch_generator(ngp_testbed* t, cudaStream_t stream, uint32_t set, uint32_t rays_local, uint32_t max_inference) {
 	ngp_testbed::RaySet& rs = t->set[set];
 	NGPB_CUDA_CHECK(cudaMemsetAsync(rs.counters.p, 0, sizeof(ngp_nerf_counters), stream));
-	generate_training_samples(stream, rays_local, t->dp_rank * rays_local, rays_local * t->dp_world, t->rng.state, t->rng.inc, t->cfg, t->views_dev.p, tb_n_views(t),
-		t->bitfield.p, max_inference, rs.counters.p, rs.ray_indices.p, rs.rays.p, rs.numsteps.p, rs.coords.p, tb_lazy(t) ? rs.t_resume.p : nullptr, t->eager_prefix);
+	if (tb_split(t)) {
+		count_training_samples(stream, rays_local, t->dp_rank * rays_local, rays_local * t->dp_world, t->rng.state, t->rng.inc, t->cfg, t->views_dev.p, tb_n_views(t),
+			t->bitfield.p, max_inference, rs.counters.p, rs.ray_indices.p, rs.rays.p, rs.numsteps.p, rs.ckpt.p, rs.seg_info.p);
+	} else {
+		generate_training_samples(stream, rays_local, t->dp_rank * rays_local, rays_local * t->dp_world, t->rng.state, t->rng.inc, t->cfg, t->views_dev.p, tb_n_views(t),
+			t->bitfield.p, max_inference, rs.counters.p, rs.ray_indices.p, rs.rays.p, rs.numsteps.p, rs.coords.p, tb_lazy(t) ? rs.t_resume.p : nullptr, t->eager_prefix);
+	}
+}
+// The part that always runs in the step itself, on the main stream
+static void tb_finish_generator(ngp_testbed* t, uint32_t set, uint32_t rays_local) {
+	if (!tb_split(t)) return;
+	ngp_testbed::RaySet& rs = t->set[set];
+	write_training_samples(t->stream, rays_local, t->cfg, t->bitfield.p, rs.rays.p, rs.ckpt.p, rs.seg_info.p, rs.coords.p);
 }
 
 // A training step (train_nerf_step, testbed_nerf.cu:3007-3382 + optimizer_step :2770) is issued in three parts so that a
@@ -555,10 +580,13 @@ static void tb_front(ngp_testbed* t, uint32_t batch) {
 		// the generator of this step already ran (or is finishing) on the side stream into the other buffer set
 		t->cur ^= 1u;
 		NGPB_CUDA_CHECK(cudaStreamWaitEvent(t->stream, t->ev_prefetch_done, 0));
+		PhaseTimer pt(t, 1);
+		tb_finish_generator(t, t->cur, rays_local);
 	} else {
 		tb_invalidate_prefetch(t);
 		PhaseTimer pt(t, 1);
 		tb_launch_generator(t, t->stream, t->cur, rays_local, max_inference);
+		tb_finish_generator(t, t->cur, rays_local);
 	}
 	t->prefetch_valid = false;
 	ngp_testbed::RaySet& rs = t->set[t->cur];
@@ -662,7 +690,9 @@ static void tb_prefetch(ngp_testbed* t) {
 	const uint32_t max_inference = tb_max_inference(t, batch);
 	// the other buffer set was last read by the loss kernel of the previous step, which precedes ev_back_done on the main stream;
 	// the bitfield and the views are not written by anything in flight
-	NGPB_CUDA_CHECK(cudaStreamWaitEvent(t->side_stream, t->ev_back_done, 0));
+	// gate: behind the forward/backward kernel, or only behind the loss kernel (the counting kernel of the split generator needs no
+	// shared memory and few registers: it fits beside k_nerf_train's two CTAs per SM and its ~0.4 ms are latency, not throughput)
+	NGPB_CUDA_CHECK(cudaStreamWaitEvent(t->side_stream, (t->overlap_gate || !tb_split(t)) ? t->ev_back_done : t->ev_front_done, 0));
 	tb_launch_generator(t, t->side_stream, next, t->rays_per_batch, max_inference);
 	NGPB_CUDA_CHECK(cudaEventRecord(t->ev_prefetch_done, t->side_stream));
 	t->prefetch_valid = true;
@@ -778,6 +808,19 @@ int ngp_nerf_march_inference_rays(const ngp_nerf_desc* d, void* stream, uint32_t
 	void* out) {
 	NGPB_TRY(require_device(); nerf_march_inference_rays(*d, (cudaStream_t)stream, n_rays_max, *cfg, counters, queue, numsteps, rays, t_resume, prefix, bitfield,
 		coords, (const __half*)params, (__half*)out, 8));
+}
+size_t ngp_nerf_generator_scratch_floats(uint32_t max_rays) { return generator_scratch_floats(max_rays); }
+size_t ngp_nerf_generator_scratch_u32(uint32_t max_rays) { return generator_scratch_u32(max_rays); }
+int ngp_nerf_count_training_samples(void* stream, uint32_t n_rays, uint32_t ray_offset, uint32_t n_rays_global, uint64_t rng_state, uint64_t rng_inc,
+	const ngp_nerf_train_cfg* cfg, const ngp_train_view* views, uint32_t n_views, const uint8_t* bitfield, uint32_t max_samples, ngp_nerf_counters* counters,
+	uint32_t* ray_indices, float* rays, uint32_t* numsteps, float* ckpt_scratch, uint32_t* seg_scratch) {
+	NGPB_TRY(require_device(); NGPB_CHECK(n_rays_global >= n_rays && ray_offset <= n_rays_global - n_rays, "ray shard outside the global batch");
+		count_training_samples((cudaStream_t)stream, n_rays, ray_offset, n_rays_global, rng_state, rng_inc, *cfg, views, n_views, bitfield, max_samples, counters,
+		ray_indices, rays, numsteps, ckpt_scratch, seg_scratch));
+}
+int ngp_nerf_write_training_samples(void* stream, uint32_t n_rays, const ngp_nerf_train_cfg* cfg, const uint8_t* bitfield, const float* rays, const float* ckpt_scratch,
+	const uint32_t* seg_scratch, float* coords) {
+	NGPB_TRY(require_device(); write_training_samples((cudaStream_t)stream, n_rays, *cfg, bitfield, rays, ckpt_scratch, seg_scratch, coords));
 }
 int ngp_nerf_compute_loss(void* stream, uint32_t n_rays, uint32_t n_rays_global, uint64_t rng_state, uint64_t rng_inc, const ngp_nerf_train_cfg* cfg,
 	const ngp_train_view* views, uint32_t n_views, const void* network_output, uint32_t max_compacted, ngp_nerf_counters* counters,
@@ -978,6 +1021,8 @@ int ngp_testbed_set_option(ngp_testbed* t, const char* name_c, double value) {
 		else if (n == "background_color.b") c.background_color[2] = (float)value;
 		else if (n == "nerf.training.full_inference") { tb_invalidate_prefetch(t); t->full_inference = value != 0; }
 		else if (n == "nerf.training.lazy_sample_generation") { tb_invalidate_prefetch(t); t->lazy_sample_generation = value != 0; }
+		else if (n == "nerf.training.split_generation") { tb_invalidate_prefetch(t); t->split_generation = value != 0; }
+		else if (n == "nerf.training.overlap_gate") { tb_invalidate_prefetch(t); t->overlap_gate = value != 0; }
 		else if (n == "nerf.training.eager_prefix") { NGPB_CHECK(value >= 0 && ((uint32_t)value % 8u) == 0u, "eager_prefix must be a multiple of 8"); tb_invalidate_prefetch(t); t->eager_prefix = (uint32_t)value; }
 		else if (n == "nerf.training.inference_chunk") { NGPB_CHECK(value == 4 || value == 8, "inference_chunk must be 4 or 8"); t->inference_chunk = (uint32_t)value; }
 		else if (n == "nerf.training.overlap_sample_generation") t->overlap_sample_generation = value != 0;

@@ -376,3 +376,44 @@ def test_lazy_march_inference_equals_generate_all_where_the_loss_reads(lib, scen
         assert np.array_equal(l_out_h[b_l:b_l + c_f], full_h[b_f:b_f + c_f]), f"network outputs of ray {rid}"
     assert n_written <= consumed.sum() + (8 + prefix) * k and n_written < ns
     print("written", n_written, "of", ns, "coordinates; consumed", int(consumed.sum()))
+
+
+@pytest.mark.parametrize("scene", SCENES)
+def test_count_and_write_kernels_equal_the_fused_generator(lib, scene):
+    """the split generator of the training pipeline (counting kernel + warp-per-ray write kernel) against the oracle-checked
+    fused kernel: per ray id the same count, ray record and coordinates, bit for bit; slots tile [0, n_samples)"""
+    import torch
+
+    n_rays, max_samples = 4096, 4096 * 1024
+    want, got, ctx = run_generator(lib, scene, n_rays, max_samples)
+    cfg = ctx["cfg"]
+    k, ns = got["n_kept"], got["n_samples"]
+    s_cnt = torch.zeros(4, dtype=torch.int32, device="cuda")
+    s_ri = torch.zeros(n_rays, dtype=torch.int32, device="cuda")
+    s_rays = torch.zeros(n_rays, 6, dtype=torch.float32, device="cuda")
+    s_ns = torch.zeros(n_rays, 2, dtype=torch.int32, device="cuda")
+    s_co = torch.full((max_samples, 7), float("nan"), dtype=torch.float32, device="cuda")
+    ck = torch.zeros(lib.ngp_nerf_generator_scratch_floats(n_rays), dtype=torch.float32, device="cuda")
+    sg = torch.zeros(lib.ngp_nerf_generator_scratch_u32(n_rays), dtype=torch.int32, device="cuda")
+    assert lib.ngp_nerf_count_training_samples(stream(), n_rays, 0, n_rays, ctx["rng"][0], ctx["rng"][1], C.byref(cfg), ctx["t_views"].data_ptr(), len(ctx["views"]),
+                                               ctx["t_bf"].data_ptr(), max_samples, s_cnt.data_ptr(), s_ri.data_ptr(), s_rays.data_ptr(), s_ns.data_ptr(),
+                                               ck.data_ptr(), sg.data_ptr()) == 0, lib.ngp_last_error()
+    assert lib.ngp_nerf_write_training_samples(stream(), n_rays, C.byref(cfg), ctx["t_bf"].data_ptr(), s_rays.data_ptr(), ck.data_ptr(), sg.data_ptr(),
+                                               s_co.data_ptr()) == 0, lib.ngp_last_error()
+    torch.cuda.synchronize()
+    cnt = s_cnt.cpu().numpy().view(np.uint32)
+    assert int(cnt[0]) == k and int(cnt[1]) == ns
+    ri, rays, nsb, co = s_ri.cpu().numpy().view(np.uint32), s_rays.cpu().numpy(), s_ns.cpu().numpy().view(np.uint32), s_co.cpu().numpy()
+    fmap = {int(r): j for j, r in enumerate(got["ray_indices"][:k])}
+    assert set(fmap) == {int(r) for r in ri[:k]}
+    for j in range(k):
+        fj = fmap[int(ri[j])]
+        n_f, b_f = got["numsteps"][fj]
+        n_s, b_s = nsb[j]
+        assert n_s == n_f
+        assert rays[j].tobytes() == got["rays"][fj].tobytes()
+        assert co[b_s:b_s + n_s].tobytes() == got["coords"][b_f:b_f + n_f].tobytes(), f"coordinates of ray {int(ri[j])}"
+    order = np.argsort(nsb[:k, 1])
+    ends = nsb[:k, 1][order] + nsb[:k, 0][order]
+    assert nsb[:k, 1][order][0] == 0 and np.array_equal(ends[:-1], nsb[:k, 1][order][1:]) and ends[-1] == ns
+    assert np.isnan(co[ns:, 0]).all()
