@@ -225,8 +225,8 @@ def main() -> None:
     ap.add_argument("--chunk", type=int, default=0, help="ray-ordered inference chunk (4 or 8)")
     ap.add_argument("--overlap", action="store_true", help="enable the side-stream prefetch of the next step's sample generation")
     ap.add_argument("--full-inference", action="store_true", help="evaluate every generated sample like the reference schedule")
-    ap.add_argument("--no-split", action="store_true", help="A/B: fused generator kernel instead of count + write kernels")
-    ap.add_argument("--gate", action="store_true", help="A/B: the prefetched counting kernel waits for the forward/backward kernel")
+    ap.add_argument("--split", action="store_true", help="A/B: count + write generator kernels instead of the fused one")
+    ap.add_argument("--no-gate", action="store_true", help="A/B: the prefetched generator does not wait for the forward/backward kernel")
     ap.add_argument("--lazy", type=int, default=None, help="A/B: eager coordinate prefix per ray (multiple of 8); the inference kernel marches the rest on demand")
     ap.add_argument("--render", action="store_true", help="also time a 1920x1080 render (reported as extra keys)")
     args = ap.parse_args()
@@ -258,10 +258,10 @@ def main() -> None:
         tb._set("nerf.training.overlap_sample_generation", 1.0)
     if args.full_inference:
         tb._set("nerf.training.full_inference", 1.0)
-    if args.no_split:
-        tb._set("nerf.training.split_generation", 0.0)
-    if args.gate:
-        tb._set("nerf.training.overlap_gate", 1.0)
+    if args.split:
+        tb._set("nerf.training.split_generation", 1.0)
+    if args.no_gate:
+        tb._set("nerf.training.overlap_gate", 0.0)
     if args.lazy is not None:
         tb._set("nerf.training.lazy_sample_generation", 1.0)
         tb._set("nerf.training.eager_prefix", float(args.lazy))

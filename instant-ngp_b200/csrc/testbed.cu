@@ -196,8 +196,10 @@ struct ngp_testbed {
 	bool full_inference = false;
 	bool lazy_sample_generation = false;  // measured slower (profiles/r1c): the generator writes a prefix of each ray's coordinates; the ray-ordered inference kernel marches the rest on demand
 	uint32_t eager_prefix = 16;
-	bool split_generation = true;    // count kernel (prefetchable beside the backward pass) + warp-per-ray write kernel
-	bool overlap_gate = false;       // true: the prefetched generator waits for the forward/backward kernel
+	bool split_generation = false;   // count kernel + warp-per-ray write kernel instead of the fused generator.  Measured (profiles/r1c): beside
+	                                 // k_nerf_train only 2 of its CTAs fit per SM (registers), so the count runs in two waves and hides nothing:
+	                                 // 1.51-1.65 ms/step against 1.50-1.54 for the fused kernel prefetched behind the backward pass
+	bool overlap_gate = true;        // the prefetched generator waits for the forward/backward kernel
 	uint32_t inference_chunk = 8;
 
 	DevBuf<float> params_fp32, m1, m2, mlp_grads_f32;
