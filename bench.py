@@ -47,6 +47,10 @@ def syn():
 
 
 # ---------------------------------------------------------------------------------------------------------------------
+# dram__bytes_read.sum + dram__bytes_write.sum of one k_nerf_train launch at this workload (ncu --set full, profiles/r1c_steady_state.md)
+K_NERF_TRAIN_DRAM_BYTES = 54.13e6 + 0.67e6
+
+
 class ClockSampler:
     """samples SM clocks / throttle reasons of one GPU while the timed region runs (B200_PROFILING.md's clocks line).  NVML in a
     thread every 5 ms (a 150 ms timed region still gets ~30 samples); `nvidia-smi -lms` as the fallback when NVML is unusable."""
@@ -364,9 +368,10 @@ def main() -> None:
         alg_bytes = 1572.0 * BATCH
         achieved = alg_bytes / (fb_ms * 1e-3) / 1e9 if fb_ms > 0 else None
         roofline = {"bound": "hbm", "kernel": "k_nerf_train (+k_mlp_grads_finalize)", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                    "frac": (achieved / pk["hbm_gbs"]) if achieved else None, "traffic": None, "peak_source": pk["source"], "ms_per_launch": fb_ms,
+                    "frac": (achieved / pk["hbm_gbs"]) if achieved else None, "traffic": K_NERF_TRAIN_DRAM_BYTES, "peak_source": pk["source"], "ms_per_launch": fb_ms,
                     "algorithmic_bytes_per_launch": alg_bytes,
-                    "note": "the 26 MB fp16 table is L2-resident on B200: gathers/reductions are L2-bound, so algorithmic GB/s may exceed the HBM copy peak"}
+                    "traffic_source": "profiles/r1c_steady_state.md",
+                    "note": "the 26 MB fp16 table and its gradient table are L2-resident on B200: the kernel is bound by L2 gather/reduction latency, DRAM traffic is an eighth of the algorithmic bytes"}
         line = {
             "metric": "nerf_training_samples_per_sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
