@@ -388,8 +388,18 @@ int ngp_testbed_render(ngp_testbed* t, int32_t width, int32_t height, const floa
 /* device-resident variant: rgba_dev / depth_dev are device buffers of the full frame. */
 int ngp_testbed_render_device(ngp_testbed* t, int32_t width, int32_t height, const float* camera_3x4_rowmajor, float focal_x,
 	float focal_y, float cx, float cy, int32_t y0, int32_t y1, float* rgba_dev, float* depth_dev);
-int ngp_testbed_save_snapshot(ngp_testbed* t, const char* path);
+/* Snapshots (python_api.cu:563-571; Testbed::save_snapshot / load_snapshot src/testbed.cu:5288-5485).  By extension:
+ *   .ingp     the reference's container: gzip(msgpack({network config..., "snapshot": {...}})), same schema (params_binary = fp16
+ *             inference weights, density_grid_binary fp16, nerf.dataset metadata, counters, optional optimizer state in the
+ *             Ema{ExponentialDecay{Adam}} nesting of the config) — files written by either side load on the other;
+ *   .msgpack  the same without gzip;
+ *   other     ".ngpb": flat dump of the full training state (fp32 masters, RNG streams) for exact resume. */
+int ngp_testbed_save_snapshot(ngp_testbed* t, const char* path);  /* include_optimizer_state = false, compress = true */
+int ngp_testbed_save_snapshot_ex(ngp_testbed* t, const char* path, int include_optimizer_state, int compress);
 int ngp_testbed_load_snapshot(ngp_testbed* t, const char* path);
+/* codec hooks (tests): JSON text <-> msgpack bytes as the snapshot writer / reader encode them, optionally gzip-wrapped */
+int ngp_json_to_msgpack(const char* json_text, int gzip, uint8_t* out, size_t capacity, size_t* n_out);
+int ngp_msgpack_to_json(const uint8_t* data, size_t n, int gzip, char* out, size_t capacity, size_t* n_out);
 int ngp_testbed_sync(ngp_testbed* t);
 /* Per-phase device time of Testbed::train, measured with CUDA events on the Testbed stream (the reference only has host
  * wall-clock EMAs m_training_prep_ms / m_training_ms, testbed.h:1023-1027).  Phases: 0 occupancy-grid update, 1 training

@@ -204,6 +204,9 @@ PROTOTYPES = {
     "ngp_testbed_render": (C.c_int, [vp, i32, i32, vp, f32, f32, f32, f32, i32, i32, vp, vp, P(u32)]),
     "ngp_testbed_render_device": (C.c_int, [vp, i32, i32, vp, f32, f32, f32, f32, i32, i32, vp, vp]),
     "ngp_testbed_save_snapshot": (C.c_int, [vp, cp]),
+    "ngp_testbed_save_snapshot_ex": (C.c_int, [vp, cp, C.c_int, C.c_int]),
+    "ngp_json_to_msgpack": (C.c_int, [cp, C.c_int, vp, C.c_size_t, P(C.c_size_t)]),
+    "ngp_msgpack_to_json": (C.c_int, [vp, C.c_size_t, C.c_int, vp, C.c_size_t, P(C.c_size_t)]),
     "ngp_testbed_load_snapshot": (C.c_int, [vp, cp]),
     "ngp_testbed_sync": (C.c_int, [vp]),
     "ngp_testbed_set_profiling": (C.c_int, [vp, C.c_int]),

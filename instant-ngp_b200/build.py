@@ -73,7 +73,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as ex:
             list(ex.map(run, jobs))
     if force or jobs or _newer(LIB, objs):
-        run([nvcc, *ARCH, "-shared", "-cudart", "shared", "-Xlinker", "-rpath=/usr/local/cuda/lib64", "-o", str(LIB), *map(str, objs)])
+        run([nvcc, *ARCH, "-shared", "-cudart", "shared", "-Xlinker", "-rpath=/usr/local/cuda/lib64", "-o", str(LIB), *map(str, objs), "-lz"])
     return LIB
 
 

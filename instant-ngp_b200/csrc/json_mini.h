@@ -3,6 +3,7 @@
 #pragma once
 
 #include <cctype>
+#include <cstdint>
 #include <cstdlib>
 #include <map>
 #include <memory>
@@ -13,10 +14,12 @@
 namespace ngpb {
 
 struct Json {
-	enum Type { Null, Bool, Number, String, Array, Object } type = Null;
+	enum Type { Null, Bool, Number, String, Array, Object, Binary } type = Null;
 	bool b = false;
 	double num = 0.0;
+	bool integer = false;           // Number written without fraction / exponent (msgpack distinguishes integers from floats)
 	std::string str;
+	std::vector<uint8_t> bin;       // Binary (msgpack bin; nlohmann::json::binary_t in the reference's snapshots)
 	std::vector<Json> arr;
 	std::map<std::string, Json> obj;
 
@@ -78,12 +81,16 @@ private:
 		if (s.compare(p, 5, "false") == 0) { p += 5; Json j; j.type = Json::Bool; j.b = false; return j; }
 		if (s.compare(p, 4, "null") == 0) { p += 4; return Json{}; }
 		char* end = nullptr;
+		const size_t p0 = p;
 		const double d = std::strtod(s.c_str() + p, &end);
 		if (end == s.c_str() + p) fail("unexpected token");
 		p = (size_t)(end - s.c_str());
 		Json j;
 		j.type = Json::Number;
 		j.num = d;
+		j.integer = true;
+		for (const char* q = s.c_str() + p0; q < end; ++q)
+			if (*q == '.' || *q == 'e' || *q == 'E' || *q == 'n' || *q == 'i') j.integer = false;
 		return j;
 	}
 	std::string string() {
@@ -144,6 +151,25 @@ private:
 		return j;
 	}
 };
+
+// ---- builders ---------------------------------------------------------------------------------------------------------
+inline Json jnum(double v) { Json j; j.type = Json::Number; j.num = v; return j; }
+inline Json jint(int64_t v) { Json j; j.type = Json::Number; j.num = (double)v; j.integer = true; return j; }
+inline Json jbool(bool v) { Json j; j.type = Json::Bool; j.b = v; return j; }
+inline Json jstr(const std::string& v) { Json j; j.type = Json::String; j.str = v; return j; }
+inline Json jobj() { Json j; j.type = Json::Object; return j; }
+inline Json jarr() { Json j; j.type = Json::Array; return j; }
+inline Json jbin(const void* data, size_t n) {
+	Json j;
+	j.type = Json::Binary;
+	j.bin.assign((const uint8_t*)data, (const uint8_t*)data + n);
+	return j;
+}
+inline Json jvec(const float* v, int n) {
+	Json j = jarr();
+	for (int i = 0; i < n; ++i) j.arr.push_back(jnum(v[i]));
+	return j;
+}
 
 inline std::string to_lower(std::string v) {
 	for (auto& c : v) c = (char)std::tolower((unsigned char)c);

@@ -12,6 +12,7 @@
 #include "host_util.h"
 #include "json_mini.h"
 #include "march.cuh"
+#include "msgpack_mini.h"
 
 namespace ngpb {
 
@@ -187,6 +188,7 @@ struct ngp_testbed {
 
 	// network
 	bool has_network = false;
+	Json network_config;              // as given to reload_network_from_json/file (m_network_config)
 	ngp_nerf_desc desc{};
 	OptimizerConfig opt;
 	float lr_factor = 1.0f;
@@ -348,7 +350,10 @@ static void tb_set_params_fp32(ngp_testbed* t, const float* host, uint32_t n) {
 }
 
 // Testbed::reset_network (src/testbed.cu:4160-4412), NeRF mode
-static void tb_reset_network(ngp_testbed* t, const Json& config) {
+static void tb_reset_network(ngp_testbed* t, const Json& config_in) {
+	t->network_config = config_in;
+	t->network_config.obj.erase("snapshot");
+	const Json& config = t->network_config;
 	const Json& enc = config.sub("encoding");
 	const Json& net = config.sub("network");
 	const Json& rgb = config.sub("rgb_network");
@@ -1196,7 +1201,292 @@ struct SnapshotHeader {
 	uint64_t rng_state, rng_inc, grng_state, grng_inc;
 	ngp_nerf_desc desc;
 };
+}  // extern "C"
+
+// ---- the reference's container: msgpack of {network config..., "snapshot": {...}}, gzip-wrapped for ".ingp"
+// (Testbed::save_snapshot / load_snapshot, src/testbed.cu:5288-5485; Trainer::serialize trainer.h:442-482; Adam / Ema /
+// ExponentialDecay serialize adam.h:304-326, ema.h:190-206, exponential_decay.h:136-148; NerfDataset json_binding.h:112-190).
+static bool has_ext(const std::string& path, const char* ext) {
+	const size_t n = strlen(ext);
+	if (path.size() < n) return false;
+	return to_lower(path.substr(path.size() - n)) == ext;
+}
+template <typename T>
+static Json dev_to_bin(const T* dev, size_t count) {
+	std::vector<T> h(count);
+	NGPB_CUDA_CHECK(cudaMemcpy(h.data(), dev, count * sizeof(T), cudaMemcpyDeviceToHost));
+	return jbin(h.data(), count * sizeof(T));
+}
+static Json mat4x3_to_json(const float* m) {  // tmat<float,4,3>: 3 rows of 4 (vec_json.h:38-46); m is column-major [c*3 + r]
+	Json rows = jarr();
+	for (int r = 0; r < 3; ++r) {
+		Json row = jarr();
+		for (int c = 0; c < 4; ++c) row.arr.push_back(jnum(m[c * 3 + r]));
+		rows.arr.push_back(row);
+	}
+	return rows;
+}
+static void mat4x3_from_json(const Json& j, float* m) {
+	NGPB_CHECK(j.type == Json::Array && j.arr.size() == 3, "snapshot: bad mat4x3");
+	for (int r = 0; r < 3; ++r) {
+		NGPB_CHECK(j.arr[r].type == Json::Array && j.arr[r].arr.size() == 4, "snapshot: bad mat4x3 row");
+		for (int c = 0; c < 4; ++c) m[c * 3 + r] = (float)j.arr[r].arr[c].num;
+	}
+}
+static Json aabb_to_json(const float* mn, const float* mx) {
+	Json b = jobj();
+	b.obj["min"] = jvec(mn, 3);
+	b.obj["max"] = jvec(mx, 3);
+	return b;
+}
+
+static Json tb_snapshot_json(ngp_testbed* t, bool include_optimizer_state) {
+	NGPB_CHECK(t->has_network, "save_snapshot: no network");
+	NGPB_CUDA_CHECK(cudaStreamSynchronize(t->stream));
+	if (t->side_stream) NGPB_CUDA_CHECK(cudaStreamSynchronize(t->side_stream));
+	const size_t n = t->desc.n_params;
+	Json cfg = t->network_config;
+	Json snap = jobj();
+	// Trainer::serialize: the INFERENCE (EMA) weights
+	snap.obj["n_params"] = jint((int64_t)n);
+	snap.obj["params_type"] = jstr("__half");
+	snap.obj["params_binary"] = dev_to_bin(t->params_ema.p, n);
+	if (include_optimizer_state) {
+		Json adam = jobj();
+		adam.obj["current_step"] = jint(t->optimizer_step);
+		adam.obj["base_learning_rate"] = jnum(t->opt.learning_rate);
+		adam.obj["first_moments_binary"] = dev_to_bin(t->m1.p, n);
+		adam.obj["second_moments_binary"] = dev_to_bin(t->m2.p, n);
+		adam.obj["param_steps_binary"] = dev_to_bin(t->param_steps.p, n);
+		Json o = adam;
+		if (t->opt.has_decay) {
+			Json d = jobj();
+			d.obj["nested"] = o;
+			d.obj["learning_rate"] = jnum(t->opt.learning_rate);
+			d.obj["learning_rate_factor"] = jnum(t->lr_factor);
+			o = d;
+		}
+		if (t->opt.has_ema) {
+			Json e = jobj();
+			e.obj["nested"] = o;
+			e.obj["weights_ema_binary"] = dev_to_bin(t->params_ema.p, n);
+			o = e;
+		}
+		snap.obj["optimizer"] = o;
+	}
+	snap.obj["version"] = jint(1);
+	snap.obj["mode"] = jstr("nerf");
+	snap.obj["density_grid_size"] = jint(128);
+	{
+		const size_t n_grid = (size_t)GRID_N_CELLS * (t->cfg.max_cascade + 1);
+		std::vector<float> g(n_grid);
+		NGPB_CUDA_CHECK(cudaMemcpy(g.data(), t->density_grid.p, n_grid * 4, cudaMemcpyDeviceToHost));
+		std::vector<__half> gh(n_grid);
+		for (size_t i = 0; i < n_grid; ++i) gh[i] = __float2half_rn(g[i]);
+		snap.obj["density_grid_binary"] = jbin(gh.data(), n_grid * 2);
+	}
+	Json nerf = jobj();
+	nerf.obj["aabb_scale"] = jint(t->aabb_scale);
+	Json rgb = jobj();
+	rgb.obj["rays_per_batch"] = jint(t->rays_per_batch);
+	rgb.obj["measured_batch_size"] = jint(t->measured_batch_size);
+	rgb.obj["measured_batch_size_before_compaction"] = jint(t->measured_batch_size_before_compaction);
+	nerf.obj["rgb"] = rgb;
+	{
+		Json ds = jobj();
+		ds.obj["n_images"] = jint(t->n_images);
+		Json paths = jarr(), meta = jarr(), xf = jarr();
+		for (uint32_t i = 0; i < t->n_images; ++i) {
+			const ngp_train_view& v = t->views[i];
+			paths.arr.push_back(jstr(""));
+			Json m = jobj();
+			const float fl[2] = {v.focal_x, v.focal_y}, pp[2] = {v.principal_x, v.principal_y}, rs[4] = {0, 0, 0, 0};
+			m.obj["focal_length"] = jvec(fl, 2);
+			Json lens = jobj();
+			if (v.lens_mode == NGP_LENS_OPENCV) {
+				lens.obj["is_fisheye"] = jbool(false);
+				lens.obj["k1"] = jnum(v.lens_params[0]);
+				lens.obj["k2"] = jnum(v.lens_params[1]);
+				lens.obj["p1"] = jnum(v.lens_params[2]);
+				lens.obj["p2"] = jnum(v.lens_params[3]);
+			}
+			m.obj["lens"] = lens;
+			m.obj["principal_point"] = jvec(pp, 2);
+			m.obj["rolling_shutter"] = jvec(rs, 4);
+			Json res = jarr();
+			res.arr.push_back(jint(v.width));
+			res.arr.push_back(jint(v.height));
+			m.obj["resolution"] = res;
+			meta.arr.push_back(m);
+			Json x = jobj();
+			x.obj["start"] = mat4x3_to_json(v.xform);
+			x.obj["end"] = mat4x3_to_json(v.xform);
+			xf.arr.push_back(x);
+		}
+		ds.obj["paths"] = paths;
+		ds.obj["metadata"] = meta;
+		ds.obj["xforms"] = xf;
+		ds.obj["render_aabb"] = aabb_to_json(t->cfg.aabb_min, t->cfg.aabb_max);
+		const float idm[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+		Json rl = jarr();
+		for (int r = 0; r < 3; ++r) rl.arr.push_back(jvec(idm + 3 * r, 3));
+		ds.obj["render_aabb_to_local"] = rl;
+		const float up[3] = {0, 1, 0};
+		ds.obj["up"] = jvec(up, 3);
+		ds.obj["offset"] = jvec(t->scene_offset, 3);
+		Json er = jarr();
+		er.arr.push_back(jint(0));
+		er.arr.push_back(jint(0));
+		ds.obj["envmap_resolution"] = er;
+		ds.obj["scale"] = jnum(t->scene_scale);
+		ds.obj["aabb_scale"] = jint(t->aabb_scale);
+		ds.obj["from_mitsuba"] = jbool(false);
+		ds.obj["is_hdr"] = jbool(false);
+		ds.obj["wants_importance_sampling"] = jbool(true);
+		ds.obj["n_extra_learnable_dims"] = jint(0);
+		nerf.obj["dataset"] = ds;
+	}
+	snap.obj["nerf"] = nerf;
+	snap.obj["training_step"] = jint(t->training_step);
+	snap.obj["loss"] = jnum(t->loss_scalar);
+	snap.obj["aabb"] = aabb_to_json(t->cfg.aabb_min, t->cfg.aabb_max);
+	snap.obj["render_aabb"] = aabb_to_json(t->cfg.aabb_min, t->cfg.aabb_max);
+	snap.obj["bounding_radius"] = jnum(1.0);
+	snap.obj["background_color"] = jvec(t->cfg.background_color, 4);
+	snap.obj["exposure"] = jnum(0.0);
+	cfg.obj["snapshot"] = snap;
+	return cfg;
+}
+
+static void bin_to_dev(const Json& j, void* dev, size_t bytes, const char* what) {
+	NGPB_CHECK(j.type == Json::Binary && j.bin.size() == bytes, std::string("snapshot: '") + what + "' has the wrong size");
+	NGPB_CUDA_CHECK(cudaMemcpy(dev, j.bin.data(), bytes, cudaMemcpyHostToDevice));
+}
+__global__ void k_half_to_float(const uint32_t n, const __half* __restrict__ in, float* __restrict__ out) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) out[i] = __half2float(in[i]);
+}
+static void tb_load_snapshot_json(ngp_testbed* t, const Json& config) {
+	NGPB_CHECK(config.contains("snapshot"), "file does not contain a snapshot");
+	const Json& snap = config.at("snapshot");
+	NGPB_CHECK((uint32_t)snap.value("version", 0.0) >= 1, "Snapshot uses an old format and can not be loaded.");
+	NGPB_CHECK(to_lower(snap.value("mode", std::string("nerf"))) == "nerf", "snapshot mode is not nerf");
+	NGPB_CHECK((uint32_t)snap.value("density_grid_size", 0.0) == 128, "Incompatible grid size.");
+	tb_invalidate_prefetch(t);
+	const Json& nerf = snap.sub("nerf");
+	// dataset: keep a loaded one, else take the metadata from the snapshot (render-only use; src/testbed.cu:5387-5392)
+	if (t->n_images == 0 && nerf.contains("dataset")) {
+		const Json& ds = nerf.at("dataset");
+		const uint32_t n_img = (uint32_t)ds.value("n_images", 0.0);
+		t->n_images = n_img;
+		t->aabb_scale = (uint32_t)ds.value("aabb_scale", 1.0);
+		t->views.assign(n_img, ngp_train_view{});
+		t->pixel_bufs.assign(n_img, nullptr);
+		for (uint32_t i = 0; i < n_img; ++i) {
+			ngp_train_view& v = t->views[i];
+			const Json& m = ds.at("metadata").arr.at(i);
+			v.width = (int32_t)m.at("resolution").arr.at(0).num;
+			v.height = (int32_t)m.at("resolution").arr.at(1).num;
+			v.focal_x = (float)m.at("focal_length").arr.at(0).num;
+			v.focal_y = (float)m.at("focal_length").arr.at(1).num;
+			v.principal_x = (float)m.at("principal_point").arr.at(0).num;
+			v.principal_y = (float)m.at("principal_point").arr.at(1).num;
+			const Json& lens = m.sub("lens");
+			if (lens.contains("k1") && !(lens.contains("is_fisheye") && lens.at("is_fisheye").b)) {
+				v.lens_mode = NGP_LENS_OPENCV;
+				v.lens_params[0] = (float)lens.value("k1", 0.0);
+				v.lens_params[1] = (float)lens.value("k2", 0.0);
+				v.lens_params[2] = (float)lens.value("p1", 0.0);
+				v.lens_params[3] = (float)lens.value("p2", 0.0);
+			}
+			mat4x3_from_json(ds.at("xforms").arr.at(i).at("start"), v.xform);
+		}
+		t->n_images_for_training = 0;  // no pixels: not trainable until images are set
+		t->views_dirty = true;
+	} else if (nerf.contains("aabb_scale")) {
+		t->aabb_scale = (uint32_t)nerf.value("aabb_scale", (double)t->aabb_scale);
+	}
+	tb_update_scene(t);
+	tb_reset_network(t, config);   // reset_network(false) from the snapshot's own config
+	const size_t n = t->desc.n_params;
+	NGPB_CHECK((size_t)snap.value("n_params", 0.0) == n, "snapshot: n_params does not match the network config");
+
+	// Trainer::deserialize: all three parameter buffers from the stored (inference) weights
+	const std::string ptype = snap.value("params_type", std::string("__half"));
+	const Json& pb = snap.at("params_binary");
+	if (ptype == "float") {
+		bin_to_dev(pb, t->params_fp32.p, n * 4, "params_binary");
+	} else {
+		NGPB_CHECK(ptype == "__half", "Trainer: snapshot parameters must be of type float of __half");
+		bin_to_dev(pb, t->params_ema.p, n * 2, "params_binary");
+		k_half_to_float<<<div_round_up((uint32_t)n, 256), 256, 0, t->stream>>>((uint32_t)n, t->params_ema.p, t->params_fp32.p);
+		NGPB_LAUNCHED();
+	}
+	k_cast_params<<<div_round_up((uint32_t)n, 256), 256, 0, t->stream>>>((uint32_t)n, t->params_fp32.p, t->params.p, t->params_ema.p);
+	NGPB_LAUNCHED();
+
+	if (snap.contains("optimizer")) {
+		const Json* o = &snap.at("optimizer");
+		if (t->opt.has_ema) {
+			bin_to_dev(o->at("weights_ema_binary"), t->params_ema.p, n * 2, "weights_ema_binary");
+			o = &o->at("nested");
+		}
+		if (t->opt.has_decay) {
+			t->lr_factor = (float)o->value("learning_rate_factor", 1.0);
+			o = &o->at("nested");
+		}
+		bin_to_dev(o->at("first_moments_binary"), t->m1.p, n * 4, "first_moments_binary");
+		bin_to_dev(o->at("second_moments_binary"), t->m2.p, n * 4, "second_moments_binary");
+		if (o->contains("param_steps_binary")) bin_to_dev(o->at("param_steps_binary"), t->param_steps.p, n * 4, "param_steps_binary");
+		t->optimizer_step = (uint32_t)o->value("current_step", 0.0);
+	}
+
+	// density grid: fp16 -> float, then mean + bitfield (update_density_grid_mean_and_bitfield)
+	const Json& dg = snap.at("density_grid_binary");
+	NGPB_CHECK(dg.type == Json::Binary, "snapshot: density_grid_binary missing");
+	const size_t n_grid = dg.bin.size() / 2;
+	NGPB_CHECK(n_grid == 0 || n_grid == (size_t)GRID_N_CELLS * (t->cfg.max_cascade + 1), "Incompatible number of grid cascades.");
+	if (n_grid) {
+		DevBuf<__half> tmp;
+		tmp.ensure(n_grid);
+		NGPB_CUDA_CHECK(cudaMemcpy(tmp.p, dg.bin.data(), n_grid * 2, cudaMemcpyHostToDevice));
+		k_half_to_float<<<div_round_up((uint32_t)n_grid, 256), 256, 0, t->stream>>>((uint32_t)n_grid, tmp.p, t->density_grid.p);
+		NGPB_LAUNCHED();
+		t->reduce_scratch.ensure(1024);
+		update_bitfield(t->stream, t->cfg.max_cascade, t->density_grid.p, t->bitfield.p, t->mean_density.p, t->reduce_scratch.p);
+		NGPB_CUDA_CHECK(cudaStreamSynchronize(t->stream));
+	}
+	const Json& rgb = nerf.sub("rgb");
+	t->rays_per_batch = (uint32_t)rgb.value("rays_per_batch", (double)t->rays_per_batch);
+	t->measured_batch_size = (uint32_t)rgb.value("measured_batch_size", 0.0);
+	t->measured_batch_size_before_compaction = (uint32_t)rgb.value("measured_batch_size_before_compaction", 0.0);
+	t->training_step = (uint32_t)snap.value("training_step", 0.0);
+	if (!snap.contains("optimizer")) t->optimizer_step = t->training_step;
+	t->loss_scalar = (float)snap.value("loss", 0.0);
+	// the occupancy grid of a trained model is past its warm-up phase
+	t->density_grid_ema_step = t->training_step / 16 + (t->training_step < 256 ? t->training_step : 0);
+	NGPB_CUDA_CHECK(cudaStreamSynchronize(t->stream));
+}
+
+extern "C" {
+
+int ngp_testbed_save_snapshot_ex(ngp_testbed* t, const char* path, int include_optimizer_state, int compress) {
+	NGPB_TRY({
+		const std::string p(path);
+		NGPB_CHECK(has_ext(p, ".ingp") || has_ext(p, ".msgpack"), "save_snapshot_ex: path must end in .ingp or .msgpack");
+		MsgPackWriter w;
+		w.write(tb_snapshot_json(t, include_optimizer_state != 0));
+		std::vector<uint8_t> bytes = std::move(w.out);
+		if (has_ext(p, ".ingp")) bytes = gzip_compress(bytes, compress ? Z_DEFAULT_COMPRESSION : Z_NO_COMPRESSION);
+		std::ofstream f(path, std::ios::binary);
+		NGPB_CHECK(f.good(), std::string("cannot open ") + path);
+		f.write((const char*)bytes.data(), (std::streamsize)bytes.size());
+		NGPB_CHECK(f.good(), "snapshot write failed");
+	});
+}
+
 int ngp_testbed_save_snapshot(ngp_testbed* t, const char* path) {
+	if (has_ext(path, ".ingp") || has_ext(path, ".msgpack")) return ngp_testbed_save_snapshot_ex(t, path, 0, 1);
 	NGPB_TRY({
 		NGPB_CHECK(t->has_network, "save_snapshot: no network");
 		NGPB_CUDA_CHECK(cudaStreamSynchronize(t->stream));
@@ -1234,6 +1524,16 @@ int ngp_testbed_save_snapshot(ngp_testbed* t, const char* path) {
 	});
 }
 int ngp_testbed_load_snapshot(ngp_testbed* t, const char* path) {
+	if (has_ext(path, ".ingp") || has_ext(path, ".msgpack")) {
+		NGPB_TRY({
+			std::ifstream f(path, std::ios::binary);
+			NGPB_CHECK(f.good(), std::string("Network snapshot '") + path + "' does not exist.");
+			std::vector<uint8_t> bytes((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+			if (has_ext(path, ".ingp")) bytes = gzip_decompress(bytes);
+			MsgPackReader r(bytes.data(), bytes.size());
+			tb_load_snapshot_json(t, r.read());
+		});
+	}
 	NGPB_TRY({
 		tb_invalidate_prefetch(t);
 		std::ifstream f(path, std::ios::binary);
@@ -1279,6 +1579,33 @@ int ngp_testbed_load_snapshot(ngp_testbed* t, const char* path) {
 		t->reduce_scratch.ensure(1024);
 		update_bitfield(t->stream, t->cfg.max_cascade, t->density_grid.p, t->bitfield.p, t->mean_density.p, t->reduce_scratch.p);
 		NGPB_CUDA_CHECK(cudaStreamSynchronize(t->stream));
+	});
+}
+// codec hooks for the tests: JSON text -> msgpack (optionally gzip) and back (binary values print as {"bytes": n})
+int ngp_json_to_msgpack(const char* json_text, int gzip, uint8_t* out, size_t capacity, size_t* n_out) {
+	NGPB_TRY({
+		const std::string text(json_text);
+		MsgPackWriter w;
+		w.write(JsonParser(text).parse());
+		std::vector<uint8_t> bytes = std::move(w.out);
+		if (gzip) bytes = gzip_compress(bytes);
+		*n_out = bytes.size();
+		NGPB_CHECK(bytes.size() <= capacity, "ngp_json_to_msgpack: output buffer too small");
+		memcpy(out, bytes.data(), bytes.size());
+	});
+}
+int ngp_msgpack_to_json(const uint8_t* data, size_t n, int gzip, char* out, size_t capacity, size_t* n_out) {
+	NGPB_TRY({
+		std::vector<uint8_t> bytes(data, data + n);
+		if (gzip) bytes = gzip_decompress(bytes);
+		MsgPackReader r(bytes.data(), bytes.size());
+		const Json j = r.read();
+		NGPB_CHECK(r.at_end(), "msgpack: trailing bytes");
+		std::string text;
+		json_dump(j, text);
+		*n_out = text.size();
+		NGPB_CHECK(text.size() + 1 <= capacity, "ngp_msgpack_to_json: output buffer too small");
+		memcpy(out, text.c_str(), text.size() + 1);
 	});
 }
 int ngp_testbed_set_profiling(ngp_testbed* t, int enable) {

@@ -464,7 +464,11 @@ class Testbed:
 
     # -- snapshots -------------------------------------------------------------------------------------------------
     def save_snapshot(self, path: str, include_optimizer_state: bool = False, compress: bool = True) -> None:
-        B.check(B.lib().ngp_testbed_save_snapshot(self._h, str(Path(path)).encode()))
+        p = str(path)
+        if p.lower().endswith((".ingp", ".msgpack")):
+            B.check(B.lib().ngp_testbed_save_snapshot_ex(self._h, p.encode(), int(include_optimizer_state), int(compress)))
+        else:
+            B.check(B.lib().ngp_testbed_save_snapshot(self._h, p.encode()))
 
     def load_snapshot(self, path: str) -> None:
         B.check(B.lib().ngp_testbed_load_snapshot(self._h, str(Path(path)).encode()))

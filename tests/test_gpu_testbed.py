@@ -83,6 +83,100 @@ def test_snapshot_round_trip(trained, tmp_path):
     assert np.array_equal(tb2.get_params(inference=True), tb.get_params(inference=True))
 
 
+def _read_ingp(path):
+    import gzip
+
+    import msgpack
+
+    raw = open(path, "rb").read()
+    if str(path).endswith(".ingp"):
+        raw = gzip.decompress(raw)
+    return msgpack.unpackb(raw, raw=False)
+
+
+def test_ingp_snapshot_has_the_reference_schema_and_round_trips(trained, tmp_path):
+    """.ingp / .msgpack: gzip(msgpack) of {network config, "snapshot": {...}} as Testbed::save_snapshot writes it
+    (src/testbed.cu:5288-5355), read here with the independent msgpack / gzip modules"""
+    tb, imgs, cams, focal, _, _ = trained
+    P = util.pkg()
+    path = tmp_path / "model.ingp"
+    tb.save_snapshot(str(path), include_optimizer_state=True)
+    d = _read_ingp(path)
+    n = tb.n_params
+    assert {"encoding", "network", "rgb_network", "dir_encoding", "loss", "optimizer", "snapshot"} <= set(d)
+    assert d["encoding"]["n_levels"] == 16 and d["encoding"]["log2_hashmap_size"] == 17 and d["optimizer"]["nested"]["nested"]["otype"] == "Adam"
+    s = d["snapshot"]
+    assert s["version"] == 1 and s["mode"] == "nerf" and s["density_grid_size"] == 128 and s["params_type"] == "__half" and s["n_params"] == n
+    assert len(s["params_binary"]) == 2 * n and len(s["density_grid_binary"]) == 2 * 128 ** 3
+    assert np.array_equal(np.frombuffer(s["params_binary"], dtype=np.float16), tb.get_params(inference=True))
+    grid, _ = tb.get_density_grid()
+    assert np.array_equal(np.frombuffer(s["density_grid_binary"], dtype=np.float16), grid.astype(np.float16).reshape(-1))
+    assert s["training_step"] == tb.training_step and s["nerf"]["aabb_scale"] == 1
+    assert set(s["nerf"]["rgb"]) == {"rays_per_batch", "measured_batch_size", "measured_batch_size_before_compaction"}
+    ds = s["nerf"]["dataset"]
+    assert ds["n_images"] == 24 and len(ds["xforms"]) == 24 and np.array(ds["xforms"][3]["start"]).shape == (3, 4)
+    assert ds["metadata"][0]["resolution"] == [160, 160] and abs(ds["metadata"][0]["focal_length"][0] - focal) < 1e-3
+    assert np.allclose(np.array(ds["xforms"][3]["start"]), np.asarray(cams[3])[:3, :4], atol=1e-6)
+    o = s["optimizer"]    # Ema { ExponentialDecay { Adam } } nesting of the config
+    assert len(o["weights_ema_binary"]) == 2 * n and "learning_rate_factor" in o["nested"]
+    adam = o["nested"]["nested"]
+    assert adam["current_step"] == tb.training_step and len(adam["first_moments_binary"]) == 4 * n and len(adam["param_steps_binary"]) == 4 * n
+
+    # a fresh Testbed without a dataset takes everything from the file and renders the same picture
+    res = 96
+    a = tb.render(res, res, cams[2], focal * res / imgs.shape[2])
+    tb2 = P.Testbed()
+    tb2.load_snapshot(str(path))
+    assert tb2.training_step == tb.training_step and tb2.n_params == n
+    assert np.array_equal(tb2.get_params(inference=True), tb.get_params(inference=True))
+    b = tb2.render(res, res, cams[2], focal * res / imgs.shape[2])
+    # the occupancy grid travels as fp16: cells within half an fp16 ulp of the threshold may flip
+    assert psnr(np.clip(a[..., :3], 0, 1), np.clip(b[..., :3], 0, 1)) > 45.0
+    # training resumes from the stored optimizer state once the images are back
+    S.load_into_testbed(tb2, imgs, cams, focal, aabb_scale=1)
+    tb2.load_snapshot(str(path))
+    for _ in range(17):
+        tb2.train(1 << 16)
+    assert tb2.training_step == tb.training_step + 17 and np.isfinite(tb2.loss) and tb2.loss < 2.0 * max(tb.loss, 1e-4)
+
+    # .msgpack (no gzip), without optimizer state
+    p2 = tmp_path / "model.msgpack"
+    tb.save_snapshot(str(p2))
+    d2 = _read_ingp(p2)
+    assert "optimizer" not in d2["snapshot"] and d2["snapshot"]["params_binary"] == s["params_binary"]
+
+
+def test_loads_a_snapshot_written_the_way_the_reference_writes_it(trained, tmp_path):
+    """a file assembled with the independent msgpack module in the reference's schema, float32 parameters
+    (Trainer::deserialize's "float" branch, trainer.h:459-462) and a never-populated density grid"""
+    import gzip
+
+    import msgpack
+
+    tb, imgs, cams, focal, _, _ = trained
+    P = util.pkg()
+    n = tb.n_params
+    w = np.random.default_rng(0).normal(0, 0.05, size=n).astype(np.float32)
+    cfg = S.base_config(16, 2, 17)
+    cfg["snapshot"] = {
+        "version": 1, "mode": "nerf", "density_grid_size": 128, "density_grid_binary": b"", "n_params": n, "params_type": "float",
+        "params_binary": w.tobytes(), "training_step": 1234, "loss": 0.5, "aabb": {"min": [0, 0, 0], "max": [1, 1, 1]}, "bounding_radius": 1.0,
+        "nerf": {"aabb_scale": 1, "rgb": {"rays_per_batch": 4096, "measured_batch_size": 0, "measured_batch_size_before_compaction": 0}},
+    }
+    path = tmp_path / "ref_style.ingp"
+    path.write_bytes(gzip.compress(msgpack.packb(cfg, use_single_float=False)))
+    tb2 = P.Testbed()
+    tb2.load_snapshot(str(path))
+    assert tb2.training_step == 1234 and tb2.n_params == n
+    assert np.array_equal(tb2.get_params(inference=True), w.astype(np.float16))
+    assert np.array_equal(tb2.get_params(inference=False), w.astype(np.float16))
+    bad = dict(cfg)
+    bad["snapshot"] = dict(cfg["snapshot"], version=0)
+    path.write_bytes(gzip.compress(msgpack.packb(bad)))
+    with pytest.raises(P.NgpError, match="old format"):
+        tb2.load_snapshot(str(path))
+
+
 def test_errors_are_reported(trained):
     P = util.pkg()
     tb = P.Testbed()
