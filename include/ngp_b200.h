@@ -273,6 +273,23 @@ size_t ngp_nerf_render_scratch_bytes(int32_t width, int32_t rows);
 int ngp_nerf_render(const ngp_nerf_desc* d, void* stream, const ngp_render_cfg* cfg, int32_t y0, int32_t y1, const void* params_fp16,
 	const uint8_t* density_grid_bitfield, float* rgba, float* depth, void* scratch, uint32_t* n_steps_total_dev);
 
+/* ≙ the render epilogue: CudaRenderBuffer::accumulate / ::tonemap (src/render_buffer.cu:228-262 accumulate_kernel,
+ * :264-342 tonemap, :511-545 tonemap_kernel).  accumulate: acc = (acc * sample_count + frame) / (sample_count + 1), the frame first
+ * converted to sRGB when color_space is NGP_COLOR_SRGB.  tonemap: blend the (sRGB-specified) background behind the premultiplied
+ * colour, back to linear, exposure 2^e, tonemap curve, to the output colour space, optional un-premultiply and clamp. */
+typedef enum ngp_tonemap_curve { NGP_TONEMAP_IDENTITY = 0, NGP_TONEMAP_ACES = 1, NGP_TONEMAP_HABLE = 2, NGP_TONEMAP_REINHARD = 3 } ngp_tonemap_curve;
+typedef struct ngp_tonemap_cfg {
+	float exposure;
+	float background_color[4];
+	uint32_t color_space;        /* space the accumulation buffer is in (ngp_color_space) */
+	uint32_t output_color_space; /* NGP_COLOR_SRGB for render(linear = false) */
+	uint32_t tonemap_curve;      /* ngp_tonemap_curve; Identity by default */
+	uint32_t clamp_output_color;
+	uint32_t unmultiply_alpha;
+} ngp_tonemap_cfg;
+int ngp_render_accumulate(void* stream, int32_t width, int32_t height, const float* frame_rgba, float* accumulate_rgba, float sample_count, uint32_t color_space);
+int ngp_render_tonemap(void* stream, int32_t width, int32_t height, const ngp_tonemap_cfg* cfg, const float* accumulate_rgba, float* out_rgba);
+
 /* ---------------------------------------------------------------------------------------------------------------
  * B1 (fields) — NetworkWithInputEncoding: HashGrid over 2-D or 3-D positions + one FullyFusedMLP
  * (tiny-cuda-nn/include/tiny-cuda-nn/network_with_input_encoding.h:38-170), the model of the image and SDF primitives
@@ -385,6 +402,10 @@ int ngp_testbed_set_density_grid(ngp_testbed* t, const float* grid_host, uint32_
  * camera_3x4: ngp-convention camera-to-world, row major [3][4]. rows [y0,y1) only (pass 0,height for all). */
 int ngp_testbed_render(ngp_testbed* t, int32_t width, int32_t height, const float* camera_3x4_rowmajor, float focal_x, float focal_y,
 	float cx, float cy, int32_t y0, int32_t y1, float* rgba_host, float* depth_host, uint32_t* n_steps_total);
+/* ≙ Testbed::render(width, height, spp, linear) (python_api.cu:507-519, render_to_cpu :138-210): spp frames with sample indices
+ * 0..spp-1 accumulated, then tonemapped (exposure 0, Identity curve, the Testbed's background colour); linear = 0 returns sRGB. */
+int ngp_testbed_render_ex(ngp_testbed* t, int32_t width, int32_t height, const float* camera_3x4_rowmajor, float focal_x, float focal_y, float cx, float cy,
+	uint32_t spp, int linear, float* rgba_host, float* depth_host);
 /* device-resident variant: rgba_dev / depth_dev are device buffers of the full frame. */
 int ngp_testbed_render_device(ngp_testbed* t, int32_t width, int32_t height, const float* camera_3x4_rowmajor, float focal_x,
 	float focal_y, float cx, float cy, int32_t y0, int32_t y1, float* rgba_dev, float* depth_dev);

@@ -18,6 +18,7 @@ from .binding import (  # noqa: F401
     NerfTrainCfg,
     NgpError,
     RenderCfg,
+    TonemapCfg,
     TrainView,
     lib,
     load_library,

@@ -55,6 +55,18 @@ class FieldDesc(C.Structure):
     ]
 
 
+class TonemapCfg(C.Structure):
+    _fields_ = [
+        ("exposure", C.c_float),
+        ("background_color", C.c_float * 4),
+        ("color_space", C.c_uint32),
+        ("output_color_space", C.c_uint32),
+        ("tonemap_curve", C.c_uint32),
+        ("clamp_output_color", C.c_uint32),
+        ("unmultiply_alpha", C.c_uint32),
+    ]
+
+
 class TrainView(C.Structure):
     _fields_ = [
         ("pixels", C.c_void_p),
@@ -203,6 +215,9 @@ PROTOTYPES = {
     "ngp_testbed_set_density_grid": (C.c_int, [vp, vp, u32]),
     "ngp_testbed_render": (C.c_int, [vp, i32, i32, vp, f32, f32, f32, f32, i32, i32, vp, vp, P(u32)]),
     "ngp_testbed_render_device": (C.c_int, [vp, i32, i32, vp, f32, f32, f32, f32, i32, i32, vp, vp]),
+    "ngp_render_accumulate": (C.c_int, [vp, i32, i32, vp, vp, f32, u32]),
+    "ngp_render_tonemap": (C.c_int, [vp, i32, i32, P(TonemapCfg), vp, vp]),
+    "ngp_testbed_render_ex": (C.c_int, [vp, i32, i32, vp, f32, f32, f32, f32, u32, C.c_int, vp, vp]),
     "ngp_testbed_save_snapshot": (C.c_int, [vp, cp]),
     "ngp_testbed_save_snapshot_ex": (C.c_int, [vp, cp, C.c_int, C.c_int]),
     "ngp_json_to_msgpack": (C.c_int, [cp, C.c_int, vp, C.c_size_t, P(C.c_size_t)]),

@@ -547,6 +547,95 @@ void render_nerf(const ngp_nerf_desc& d, cudaStream_t stream, const ngp_render_c
 	if (n_steps_total) NGPB_CUDA_CHECK(cudaMemcpyAsync(n_steps_total, queue + 1, 4, cudaMemcpyDeviceToDevice, stream));
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// render epilogue (src/render_buffer.cu:228-262, 264-342, 511-545)
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void k_accumulate(const uint32_t n_px, const float* __restrict__ frame, float* __restrict__ acc, const float sample_count, const uint32_t color_space) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n_px) return;
+	const float4 c = reinterpret_cast<const float4*>(frame)[i];
+	float4 t = reinterpret_cast<float4*>(acc)[i];
+	float r = c.x, g = c.y, b = c.z;
+	if (color_space == NGP_COLOR_SRGB) {
+		r = linear_to_srgb(r);
+		g = linear_to_srgb(g);
+		b = linear_to_srgb(b);
+	}
+	t.x = (t.x * sample_count + r) / (sample_count + 1.0f);
+	t.y = (t.y * sample_count + g) / (sample_count + 1.0f);
+	t.z = (t.z * sample_count + b) / (sample_count + 1.0f);
+	t.w = (t.w * sample_count + c.w) / (sample_count + 1.0f);
+	reinterpret_cast<float4*>(acc)[i] = t;
+}
+
+__host__ __device__ inline void tonemap_curve3(float (&x)[3], uint32_t curve) {
+	if (curve == NGP_TONEMAP_IDENTITY) return;
+	for (int k = 0; k < 3; ++k) x[k] = fmaxf(x[k], 0.0f);
+	float k0, k1, k2, k3, k4, k5;
+	if (curve == NGP_TONEMAP_ACES) {
+		k0 = 0.6f * 0.6f * 2.51f; k1 = 0.6f * 0.03f; k2 = 0.0f; k3 = 0.6f * 0.6f * 2.43f; k4 = 0.6f * 0.59f; k5 = 0.14f;
+	} else if (curve == NGP_TONEMAP_HABLE) {
+		const float A = 0.15f, B = 0.50f, C = 0.10f, D = 0.20f, E = 0.02f, F = 0.30f;
+		k0 = A * F - A * E; k1 = C * B * F - B * E; k2 = 0.0f; k3 = A * F; k4 = B * F; k5 = D * F * F;
+		const float W = 11.2f;
+		const float nom = k0 * (W * W) + k1 * W + k2, denom = k3 * (W * W) + k4 * W + k5;
+		const float white_scale = denom / nom;
+		k0 = 4.0f * k0 * white_scale; k1 = 2.0f * k1 * white_scale; k2 = k2 * white_scale; k3 = 4.0f * k3; k4 = 2.0f * k4;
+	} else {
+		const float Y = (0.2126f * x[0] + 0.7152f * x[1]) + 0.0722f * x[2];
+		const float s = 1.0f / (Y + 1.0f);
+		for (int k = 0; k < 3; ++k) x[k] = x[k] * s;
+		return;
+	}
+	for (int k = 0; k < 3; ++k) {
+		const float sq = x[k] * x[k];
+		const float nom = (sq * k0 + k1 * x[k]) + k2, denom = (k3 * sq + k4 * x[k]) + k5;
+		x[k] = nom / denom;
+	}
+}
+
+__global__ void k_tonemap(const uint32_t n_px, const ngp_tonemap_cfg cfg, const float* __restrict__ acc, float* __restrict__ out) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n_px) return;
+	float bg[4] = {cfg.background_color[0], cfg.background_color[1], cfg.background_color[2], cfg.background_color[3]};
+	if (cfg.color_space != NGP_COLOR_SRGB)
+		for (int k = 0; k < 3; ++k) bg[k] = srgb_to_linear(bg[k]);
+	const float4 c = reinterpret_cast<const float4*>(acc)[i];
+	const float weight = (1.0f - c.w) * bg[3];
+	float col[3] = {c.x + bg[0] * weight, c.y + bg[1] * weight, c.z + bg[2] * weight};
+	float a = c.w + weight;
+	if (cfg.color_space == NGP_COLOR_SRGB)
+		for (int k = 0; k < 3; ++k) col[k] = srgb_to_linear(col[k]);
+	const float e = ngp_powf(2.0f, cfg.exposure);
+	for (int k = 0; k < 3; ++k) col[k] = col[k] * e;
+	tonemap_curve3(col, cfg.tonemap_curve);
+	if (cfg.output_color_space == NGP_COLOR_SRGB)
+		for (int k = 0; k < 3; ++k) col[k] = linear_to_srgb(col[k]);
+	if (cfg.unmultiply_alpha && a > 0.0f)
+		for (int k = 0; k < 3; ++k) col[k] = col[k] / a;
+	if (cfg.clamp_output_color) {
+		for (int k = 0; k < 3; ++k) col[k] = clampf(col[k], 0.0f, 1.0f);
+		a = clampf(a, 0.0f, 1.0f);
+	}
+	reinterpret_cast<float4*>(out)[i] = make_float4(col[0], col[1], col[2], a);
+}
+
+void render_accumulate(cudaStream_t stream, int32_t w, int32_t h, const float* frame, float* acc, float sample_count, uint32_t color_space) {
+	NGPB_CHECK(w > 0 && h > 0, "render_accumulate: bad frame size");
+	const uint32_t n = (uint32_t)w * (uint32_t)h;
+	k_accumulate<<<div_round_up(n, 256), 256, 0, stream>>>(n, frame, acc, sample_count, color_space);
+	NGPB_LAUNCHED();
+	NGPB_CUDA_CHECK(cudaGetLastError());
+}
+void render_tonemap(cudaStream_t stream, int32_t w, int32_t h, const ngp_tonemap_cfg& cfg, const float* acc, float* out) {
+	NGPB_CHECK(w > 0 && h > 0, "render_tonemap: bad frame size");
+	NGPB_CHECK(cfg.tonemap_curve <= NGP_TONEMAP_REINHARD, "render_tonemap: unknown tonemap curve");
+	const uint32_t n = (uint32_t)w * (uint32_t)h;
+	k_tonemap<<<div_round_up(n, 256), 256, 0, stream>>>(n, cfg, acc, out);
+	NGPB_LAUNCHED();
+	NGPB_CUDA_CHECK(cudaGetLastError());
+}
+
 // sum of n floats in a fixed order (1024 strided partials, then sequential) — NerfCounters::update_after_training's
 // reduce_sum(loss) (testbed_nerf.cu:2693-2696), made order-deterministic.
 __global__ void k_sum_partial(const float* __restrict__ data, uint32_t n, float* __restrict__ partial) {

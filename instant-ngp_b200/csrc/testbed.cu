@@ -58,6 +58,8 @@ size_t render_scratch_bytes(int32_t width, int32_t rows);
 void render_nerf(const ngp_nerf_desc& d, cudaStream_t stream, const ngp_render_cfg& cfg, int32_t y0, int32_t y1, const __half* params, const uint8_t* bitfield,
 	float* rgba, float* depth, void* scratch, uint32_t* n_steps_total);
 float reduce_sum_f32(cudaStream_t stream, const float* data, uint32_t n, float* scratch_dev);
+void render_accumulate(cudaStream_t stream, int32_t w, int32_t h, const float* frame, float* acc, float sample_count, uint32_t color_space);
+void render_tonemap(cudaStream_t stream, int32_t w, int32_t h, const ngp_tonemap_cfg& cfg, const float* acc, float* out);
 
 // ------------------------------------------------------------------------------------------------------------------
 // descriptors
@@ -187,6 +189,7 @@ struct ngp_testbed {
 	bool views_dirty = true;
 
 	// network
+	uint32_t render_spp_index = 0;    // sample index of the next render (jitters each ray's first step, advance_pos_nerf)
 	bool has_network = false;
 	Json network_config;              // as given to reload_network_from_json/file (m_network_config)
 	ngp_nerf_desc desc{};
@@ -1157,7 +1160,7 @@ static void tb_fill_render_cfg(ngp_testbed* t, ngp_render_cfg& rc, int32_t width
 	rc.rgb_activation = t->cfg.rgb_activation;
 	rc.density_activation = t->cfg.density_activation;
 	rc.min_transmittance = t->render_min_transmittance;
-	rc.spp_index = 0;
+	rc.spp_index = t->render_spp_index;
 	rc.near_distance = 0.0f;
 }
 
@@ -1188,6 +1191,48 @@ int ngp_testbed_render(ngp_testbed* t, int32_t width, int32_t height, const floa
 		NGPB_CUDA_CHECK(cudaMemcpyAsync(&steps, t->render_counter.p, 4, cudaMemcpyDeviceToHost, t->stream));
 		NGPB_CUDA_CHECK(cudaStreamSynchronize(t->stream));
 		if (n_steps_total) *n_steps_total = steps;
+	});
+}
+
+int ngp_render_accumulate(void* stream, int32_t w, int32_t h, const float* frame, float* acc, float sample_count, uint32_t color_space) {
+	NGPB_TRY(require_device(); render_accumulate((cudaStream_t)stream, w, h, frame, acc, sample_count, color_space));
+}
+int ngp_render_tonemap(void* stream, int32_t w, int32_t h, const ngp_tonemap_cfg* cfg, const float* acc, float* out) {
+	NGPB_TRY(require_device(); render_tonemap((cudaStream_t)stream, w, h, *cfg, acc, out));
+}
+int ngp_testbed_render_ex(ngp_testbed* t, int32_t width, int32_t height, const float* cam, float fx, float fy, float cx, float cy, uint32_t spp, int linear,
+	float* rgba_host, float* depth_host) {
+	NGPB_TRY({
+		NGPB_CHECK(width > 0 && height > 0 && spp >= 1, "render: bad frame size / spp");
+		const size_t n_px = (size_t)width * height;
+		t->render_rgba.ensure(n_px * 4);
+		t->render_depth.ensure(n_px);
+		DevBuf<float> acc, out;
+		acc.ensure(n_px * 4);
+		out.ensure(n_px * 4);
+		NGPB_CUDA_CHECK(cudaMemsetAsync(acc.p, 0, n_px * 16, t->stream));
+		const uint32_t saved = t->render_spp_index;
+		for (uint32_t sidx = 0; sidx < spp; ++sidx) {
+			t->render_spp_index = sidx;
+			if (ngp_testbed_render_device(t, width, height, cam, fx, fy, cx, cy, 0, height, t->render_rgba.p, t->render_depth.p)) {
+				t->render_spp_index = saved;
+				throw std::runtime_error(g_last_error);
+			}
+			render_accumulate(t->stream, width, height, t->render_rgba.p, acc.p, (float)sidx, NGP_COLOR_LINEAR);
+		}
+		t->render_spp_index = saved;
+		ngp_tonemap_cfg tm{};
+		tm.exposure = 0.0f;
+		for (int k = 0; k < 4; ++k) tm.background_color[k] = t->cfg.background_color[k];
+		tm.color_space = NGP_COLOR_LINEAR;
+		tm.output_color_space = linear ? NGP_COLOR_LINEAR : NGP_COLOR_SRGB;
+		tm.tonemap_curve = NGP_TONEMAP_IDENTITY;
+		tm.clamp_output_color = 0;
+		tm.unmultiply_alpha = 0;
+		render_tonemap(t->stream, width, height, tm, acc.p, out.p);
+		NGPB_CUDA_CHECK(cudaMemcpyAsync(rgba_host, out.p, n_px * 16, cudaMemcpyDeviceToHost, t->stream));
+		if (depth_host) NGPB_CUDA_CHECK(cudaMemcpyAsync(depth_host, t->render_depth.p, n_px * 4, cudaMemcpyDeviceToHost, t->stream));
+		NGPB_CUDA_CHECK(cudaStreamSynchronize(t->stream));
 	});
 }
 

@@ -441,13 +441,18 @@ class Testbed:
                rows=None, return_depth: bool = False):
         """≙ Testbed.render(width, height, spp, linear) with an explicit ngp-convention 3x4 camera-to-world matrix
         (the reference takes it from testbed.set_nerf_camera_matrix).  Returns float32 [H, W, 4] linear premultiplied RGBA."""
-        if spp != 1 or not linear:
-            raise B.NgpError("render: spp=1, linear=True only")
         cam = np.ascontiguousarray(np.asarray(camera_matrix, dtype=np.float32)[:3, :4])
         fx, fy = (focal_length, focal_length) if np.isscalar(focal_length) else focal_length
         y0, y1 = rows if rows is not None else (0, height)
         rgba = np.zeros((height, width, 4), dtype=np.float32)
         depth = np.zeros((height, width), dtype=np.float32)
+        if spp != 1 or not linear:
+            # the accumulate + tonemap epilogue (render_buffer.cu): spp frames averaged, sRGB output for linear=False
+            if rows is not None:
+                raise B.NgpError("render: row tiles are rendered with spp=1, linear=True (accumulate per tile on the caller's side)")
+            B.check(B.lib().ngp_testbed_render_ex(self._h, width, height, cam.ctypes.data, fx, fy, screen_center[0], screen_center[1], int(spp), int(linear),
+                                                  rgba.ctypes.data, depth.ctypes.data))
+            return (rgba, depth) if return_depth else rgba
         steps = C.c_uint32(0)
         B.check(B.lib().ngp_testbed_render(self._h, width, height, cam.ctypes.data, fx, fy, screen_center[0], screen_center[1], y0, y1, rgba.ctypes.data,
                                            depth.ctypes.data, C.byref(steps)))

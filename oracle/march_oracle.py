@@ -57,6 +57,8 @@ def lib() -> C.CDLL:
             "orc_update_bitfield": (None, [u32, vp, f32, vp]),
             "orc_render_march": (None, [RC, C.c_int32, C.c_int32, vp, u32, vp, vp]),
             "orc_render_composite": (None, [RC, C.c_int32, C.c_int32, u32, vp, vp, vp, vp, vp, vp]),
+            "orc_accumulate": (None, [u32, vp, vp, f32, u32]),
+            "orc_tonemap": (None, [u32, C.POINTER(B.TonemapCfg), vp, vp]),
             "orc_version": (C.c_int, []),
         }
         for k, (r, a) in sig.items():

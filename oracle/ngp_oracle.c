@@ -819,4 +819,65 @@ EXPORT void orc_render_composite(const ngp_render_cfg* cfg, int32_t y0, int32_t 
 		depth_out[q] = a > 0.2f ? depth : MAX_DEPTH;
 	}
 }
+/* ---- render epilogue: accumulate_kernel / tonemap_kernel (src/render_buffer.cu:228-262, 264-342, 511-545) ---- */
+EXPORT void orc_accumulate(uint32_t n_px, const float* frame, float* acc, float sample_count, uint32_t color_space) {
+	for (uint32_t i = 0; i < n_px; ++i) {
+		float r = frame[4 * i], g = frame[4 * i + 1], b = frame[4 * i + 2];
+		if (color_space == NGP_COLOR_SRGB) { r = linear_to_srgb(r); g = linear_to_srgb(g); b = linear_to_srgb(b); }
+		acc[4 * i + 0] = (acc[4 * i + 0] * sample_count + r) / (sample_count + 1.0f);
+		acc[4 * i + 1] = (acc[4 * i + 1] * sample_count + g) / (sample_count + 1.0f);
+		acc[4 * i + 2] = (acc[4 * i + 2] * sample_count + b) / (sample_count + 1.0f);
+		acc[4 * i + 3] = (acc[4 * i + 3] * sample_count + frame[4 * i + 3]) / (sample_count + 1.0f);
+	}
+}
+static void tonemap_curve3(float* x, uint32_t curve) {
+	if (curve == NGP_TONEMAP_IDENTITY) return;
+	for (int k = 0; k < 3; ++k) x[k] = fmaxf(x[k], 0.0f);
+	float k0, k1, k2, k3, k4, k5;
+	if (curve == NGP_TONEMAP_ACES) {
+		k0 = 0.6f * 0.6f * 2.51f; k1 = 0.6f * 0.03f; k2 = 0.0f; k3 = 0.6f * 0.6f * 2.43f; k4 = 0.6f * 0.59f; k5 = 0.14f;
+	} else if (curve == NGP_TONEMAP_HABLE) {
+		const float A = 0.15f, B = 0.50f, C = 0.10f, D = 0.20f, E = 0.02f, F = 0.30f;
+		k0 = A * F - A * E; k1 = C * B * F - B * E; k2 = 0.0f; k3 = A * F; k4 = B * F; k5 = D * F * F;
+		const float W = 11.2f;
+		const float nom = k0 * (W * W) + k1 * W + k2, denom = k3 * (W * W) + k4 * W + k5;
+		const float white_scale = denom / nom;
+		k0 = 4.0f * k0 * white_scale; k1 = 2.0f * k1 * white_scale; k2 = k2 * white_scale; k3 = 4.0f * k3; k4 = 2.0f * k4;
+	} else {
+		const float Y = (0.2126f * x[0] + 0.7152f * x[1]) + 0.0722f * x[2];
+		const float s = 1.0f / (Y + 1.0f);
+		for (int k = 0; k < 3; ++k) x[k] = x[k] * s;
+		return;
+	}
+	for (int k = 0; k < 3; ++k) {
+		const float sq = x[k] * x[k];
+		const float nom = (sq * k0 + k1 * x[k]) + k2, denom = (k3 * sq + k4 * x[k]) + k5;
+		x[k] = nom / denom;
+	}
+}
+EXPORT void orc_tonemap(uint32_t n_px, const ngp_tonemap_cfg* cfg, const float* acc, float* out) {
+	float bg[4] = {cfg->background_color[0], cfg->background_color[1], cfg->background_color[2], cfg->background_color[3]};
+	if (cfg->color_space != NGP_COLOR_SRGB)
+		for (int k = 0; k < 3; ++k) bg[k] = srgb_to_linear(bg[k]);
+	const float e = ngp_powf(2.0f, cfg->exposure);
+	for (uint32_t i = 0; i < n_px; ++i) {
+		const float* c = acc + 4 * (size_t)i;
+		const float weight = (1.0f - c[3]) * bg[3];
+		float col[3] = {c[0] + bg[0] * weight, c[1] + bg[1] * weight, c[2] + bg[2] * weight};
+		float a = c[3] + weight;
+		if (cfg->color_space == NGP_COLOR_SRGB)
+			for (int k = 0; k < 3; ++k) col[k] = srgb_to_linear(col[k]);
+		for (int k = 0; k < 3; ++k) col[k] = col[k] * e;
+		tonemap_curve3(col, cfg->tonemap_curve);
+		if (cfg->output_color_space == NGP_COLOR_SRGB)
+			for (int k = 0; k < 3; ++k) col[k] = linear_to_srgb(col[k]);
+		if (cfg->unmultiply_alpha && a > 0.0f)
+			for (int k = 0; k < 3; ++k) col[k] = col[k] / a;
+		if (cfg->clamp_output_color) {
+			for (int k = 0; k < 3; ++k) col[k] = col[k] < 0.0f ? 0.0f : (col[k] > 1.0f ? 1.0f : col[k]);
+			a = a < 0.0f ? 0.0f : (a > 1.0f ? 1.0f : a);
+		}
+		out[4 * (size_t)i + 0] = col[0]; out[4 * (size_t)i + 1] = col[1]; out[4 * (size_t)i + 2] = col[2]; out[4 * (size_t)i + 3] = a;
+	}
+}
 EXPORT int orc_version(void) { return 1; }

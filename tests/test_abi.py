@@ -35,8 +35,8 @@ def test_struct_sizes_match_header(built_lib, ngp):
     src = r'''
 #include "ngp_b200.h"
 #include <stdio.h>
-int main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(ngp_grid_desc), sizeof(ngp_nerf_desc), sizeof(ngp_train_view), sizeof(ngp_march_consts),
- sizeof(ngp_nerf_train_cfg), sizeof(ngp_nerf_counters), sizeof(ngp_adam_cfg), sizeof(ngp_render_cfg), sizeof(ngp_field_desc)); return 0;}
+int main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(ngp_grid_desc), sizeof(ngp_nerf_desc), sizeof(ngp_train_view), sizeof(ngp_march_consts),
+ sizeof(ngp_nerf_train_cfg), sizeof(ngp_nerf_counters), sizeof(ngp_adam_cfg), sizeof(ngp_render_cfg), sizeof(ngp_field_desc), sizeof(ngp_tonemap_cfg)); return 0;}
 '''
     with tempfile.TemporaryDirectory() as td:
         p = Path(td) / "s.c"
@@ -44,7 +44,7 @@ int main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(ngp_grid_desc)
         exe = Path(td) / "s"
         subprocess.check_call(["gcc", "-I", str(ROOT / "include"), str(p), "-o", str(exe)])
         sizes = list(map(int, subprocess.check_output([str(exe)]).split()))
-    got = [C.sizeof(x) for x in (ngp.GridDesc, ngp.NerfDesc, ngp.TrainView, ngp.MarchConsts, ngp.NerfTrainCfg, ngp.NerfCounters, ngp.AdamCfg, ngp.RenderCfg, ngp.FieldDesc)]
+    got = [C.sizeof(x) for x in (ngp.GridDesc, ngp.NerfDesc, ngp.TrainView, ngp.MarchConsts, ngp.NerfTrainCfg, ngp.NerfCounters, ngp.AdamCfg, ngp.RenderCfg, ngp.FieldDesc, ngp.TonemapCfg)]
     assert got == sizes
 
 

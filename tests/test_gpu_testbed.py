@@ -69,6 +69,26 @@ def test_render_matches_training_view(trained):
     assert np.array_equal(top[: h // 2], got[: h // 2]) and np.array_equal(bot[h // 2:], got[h // 2:])
 
 
+def test_render_spp_and_srgb_epilogue(trained):
+    """Testbed.render(width, height, spp, linear): spp frames accumulated, sRGB output for linear=False (python_api.cu:507-519)"""
+    from oracle import march_oracle as M
+
+    tb, imgs, cams, focal, _, _ = trained
+    res = 80
+    f = focal * res / imgs.shape[2]
+    one = tb.render(res, res, cams[4], f)
+    four = tb.render(res, res, cams[4], f, spp=4)
+    # samples differ only in the jitter of each ray's first step: the average stays close to one sample and is not identical
+    assert not np.array_equal(one, four) and psnr(np.clip(one[..., :3], 0, 1), np.clip(four[..., :3], 0, 1)) > 30.0
+    srgb = tb.render(res, res, cams[4], f, spp=1, linear=False)
+    want = np.empty_like(one[..., :3])
+    import ctypes as C
+
+    src = np.ascontiguousarray(one[..., :3])
+    M.lib().orc_linear_to_srgb_n(src.ctypes.data_as(C.c_void_p), want.ctypes.data_as(C.c_void_p), src.size)
+    assert np.array_equal(srgb[..., :3], want) and np.array_equal(srgb[..., 3], one[..., 3])
+
+
 def test_snapshot_round_trip(trained, tmp_path):
     tb, imgs, cams, focal, _, _ = trained
     P = util.pkg()
