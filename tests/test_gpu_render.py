@@ -121,6 +121,13 @@ def test_render_empty_and_tiles():
     assert lib.ngp_nerf_render(C.byref(d), stream, C.byref(rc), 5, 5, t_p.data_ptr(), t_bf.data_ptr(), t_rgba.data_ptr(), t_depth.data_ptr(), t_scr.data_ptr(), None) != 0
 
 
+@pytest.fixture(scope="module")
+def lib():
+    l = util.pkg().load_library()
+    assert l.ngp_device_count() > 0
+    return l
+
+
 @pytest.mark.parametrize("color_space", [0, 1])
 def test_accumulate_is_bit_exact(lib, color_space):
     """accumulate_kernel (src/render_buffer.cu:228-262) against the C oracle"""
