@@ -189,6 +189,7 @@ struct ngp_testbed {
 	bool views_dirty = true;
 
 	// network
+	float background_alpha = 1.0f;    // m_background_color.a (testbed.h:1031): used by the render epilogue only
 	uint32_t render_spp_index = 0;    // sample index of the next render (jitters each ray's first step, advance_pos_nerf)
 	bool has_network = false;
 	Json network_config;              // as given to reload_network_from_json/file (m_network_config)
@@ -1029,6 +1030,7 @@ int ngp_testbed_set_option(ngp_testbed* t, const char* name_c, double value) {
 		else if (n == "background_color.r") c.background_color[0] = (float)value;
 		else if (n == "background_color.g") c.background_color[1] = (float)value;
 		else if (n == "background_color.b") c.background_color[2] = (float)value;
+		else if (n == "background_color.a") t->background_alpha = (float)value;
 		else if (n == "nerf.training.full_inference") { tb_invalidate_prefetch(t); t->full_inference = value != 0; }
 		else if (n == "nerf.training.lazy_sample_generation") { tb_invalidate_prefetch(t); t->lazy_sample_generation = value != 0; }
 		else if (n == "nerf.training.split_generation") { tb_invalidate_prefetch(t); t->split_generation = value != 0; }
@@ -1223,7 +1225,8 @@ int ngp_testbed_render_ex(ngp_testbed* t, int32_t width, int32_t height, const f
 		t->render_spp_index = saved;
 		ngp_tonemap_cfg tm{};
 		tm.exposure = 0.0f;
-		for (int k = 0; k < 4; ++k) tm.background_color[k] = t->cfg.background_color[k];
+		for (int k = 0; k < 3; ++k) tm.background_color[k] = t->cfg.background_color[k];
+		tm.background_color[3] = t->background_alpha;
 		tm.color_space = NGP_COLOR_LINEAR;
 		tm.output_color_space = linear ? NGP_COLOR_LINEAR : NGP_COLOR_SRGB;
 		tm.tonemap_curve = NGP_TONEMAP_IDENTITY;
@@ -1397,7 +1400,10 @@ static Json tb_snapshot_json(ngp_testbed* t, bool include_optimizer_state) {
 	snap.obj["aabb"] = aabb_to_json(t->cfg.aabb_min, t->cfg.aabb_max);
 	snap.obj["render_aabb"] = aabb_to_json(t->cfg.aabb_min, t->cfg.aabb_max);
 	snap.obj["bounding_radius"] = jnum(1.0);
-	snap.obj["background_color"] = jvec(t->cfg.background_color, 4);
+	{
+		const float bg[4] = {t->cfg.background_color[0], t->cfg.background_color[1], t->cfg.background_color[2], t->background_alpha};
+		snap.obj["background_color"] = jvec(bg, 4);
+	}
 	snap.obj["exposure"] = jnum(0.0);
 	cfg.obj["snapshot"] = snap;
 	return cfg;

@@ -341,6 +341,8 @@ class Testbed:
         self._set("background_color.r", float(rgba[0]))
         self._set("background_color.g", float(rgba[1]))
         self._set("background_color.b", float(rgba[2]))
+        if len(rgba) > 3:
+            self._set("background_color.a", float(rgba[3]))
 
     # -- data ------------------------------------------------------------------------------------------------------
     def create_empty_nerf_dataset(self, n_images: int, aabb_scale: int = 1, is_hdr: bool = False) -> None:

@@ -80,6 +80,7 @@ def test_render_spp_and_srgb_epilogue(trained):
     four = tb.render(res, res, cams[4], f, spp=4)
     # samples differ only in the jitter of each ray's first step: the average stays close to one sample and is not identical
     assert not np.array_equal(one, four) and psnr(np.clip(one[..., :3], 0, 1), np.clip(four[..., :3], 0, 1)) > 30.0
+    tb.background_color = [0.0, 0.0, 0.0, 0.0]   # transparent background: the epilogue then leaves alpha alone (default is opaque black, testbed.h:1031)
     srgb = tb.render(res, res, cams[4], f, spp=1, linear=False)
     want = np.empty_like(one[..., :3])
     import ctypes as C
@@ -90,6 +91,9 @@ def test_render_spp_and_srgb_epilogue(trained):
     print("srgb epilogue: max abs diff", diff.max(), "mismatching", int((srgb[..., :3] != want).sum()), "of", want.size)
     big = want > 1e-30   # (sub-denormal dust of empty pixels aside)
     assert np.array_equal(srgb[..., :3][big], want[big]) and diff.max() < 1e-30 and np.array_equal(srgb[..., 3], one[..., 3])
+    tb.background_color = [0.0, 0.0, 0.0, 1.0]
+    opaque = tb.render(res, res, cams[4], f, spp=1, linear=False)
+    assert np.allclose(opaque[..., 3], 1.0, atol=1e-6) and np.array_equal(opaque[..., :3], srgb[..., :3])
 
 
 def test_snapshot_round_trip(trained, tmp_path):
