@@ -1042,6 +1042,9 @@ int ngp_testbed_set_option(ngp_testbed* t, const char* name_c, double value) {
 		else if (n == "train_encoding") t->train_encoding = value != 0;
 		else if (n == "shall_train") t->shall_train = value != 0;
 		else if (n == "nerf.training.dataset.scale") t->scene_scale = (float)value;
+		else if (n == "nerf.training.dataset.offset.x") t->scene_offset[0] = (float)value;
+		else if (n == "nerf.training.dataset.offset.y") t->scene_offset[1] = (float)value;
+		else if (n == "nerf.training.dataset.offset.z") t->scene_offset[2] = (float)value;
 		else NGPB_CHECK(false, "unknown option '" + n + "'");
 	});
 }

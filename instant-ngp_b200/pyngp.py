@@ -350,6 +350,12 @@ class Testbed:
             raise B.NgpError("is_hdr datasets are not supported")
         B.check(B.lib().ngp_testbed_create_empty_nerf_dataset(self._h, n_images, aabb_scale))
 
+    def load_training_data(self, path: str) -> None:
+        """python_api.cu:452 — a transforms.json (or a directory of them) with 8-bit images (nerf_loader.py)"""
+        from . import nerf_loader
+
+        self.dataset = nerf_loader.load_into_testbed(self, path)
+
     # -- network ---------------------------------------------------------------------------------------------------
     def reload_network_from_file(self, path: str = "") -> None:
         B.check(B.lib().ngp_testbed_reload_network_from_file(self._h, str(path).encode()))

@@ -219,3 +219,28 @@ def test_errors_are_reported(trained):
         tb.train(1 << 16)  # n_images_for_training == 0
     with pytest.raises(P.NgpError):
         tb.train(1000)     # not a multiple of 256
+
+
+def test_load_training_data_from_transforms_json(tmp_path):
+    """Testbed.load_training_data (python_api.cu:452): a transforms.json scene on disk trains like the same scene set through the API"""
+    import sys
+
+    sys.path.insert(0, str(Path(__file__).resolve().parent))
+    from test_nerf_loader import write_scene
+
+    imgs, cams, focal = write_scene(tmp_path, n=16, w=96, h=96)
+    P = util.pkg()
+    tb = P.Testbed()
+    tb.load_training_data(str(tmp_path))
+    assert len(tb.dataset["images"]) == 16 and tb.dataset["aabb_scale"] == 1
+    tb.reload_network_from_json(S.base_config(16, 2, 15))
+    losses = []
+    for i in range(200):
+        tb.train(1 << 14)
+        if tb.training_step % 16 == 1:
+            losses.append(tb.loss)
+    assert np.isfinite(losses).all() and losses[-1] < 0.5 * losses[0], losses
+    got = tb.render(96, 96, cams[3], focal)
+    p = psnr(np.clip(got[..., :3], 0, 1), imgs[3][..., :3])
+    print("psnr after 200 steps from disk", p)
+    assert p > 17.0
