@@ -1,5 +1,6 @@
 """GPU: the Testbed surface end to end — train / render / snapshot / counters — on a procedural scene."""
 import importlib
+from pathlib import Path
 
 import numpy as np
 import pytest
