@@ -232,7 +232,7 @@ def main() -> None:
     ap.add_argument("--split", action="store_true", help="A/B: count + write generator kernels instead of the fused one")
     ap.add_argument("--no-gate", action="store_true", help="A/B: the prefetched generator does not wait for the forward/backward kernel")
     ap.add_argument("--lazy", type=int, default=None, help="A/B: eager coordinate prefix per ray (multiple of 8); the inference kernel marches the rest on demand")
-    ap.add_argument("--render", action="store_true", help="also time a 1920x1080 render (reported as extra keys)")
+    ap.add_argument("--no-render", action="store_true", help="skip the 1920x1080 render timing (reported under the extra key `render`)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
@@ -387,7 +387,7 @@ def main() -> None:
             "clocks": clocks,
             "roofline": roofline,
         }
-        if args.render:
+        if not args.no_render:
             S = syn()
             cam = S.sphere_cameras(8, radius=1.3)[3]
             W, H = 1920, 1080
