@@ -200,7 +200,16 @@ int ngp_nerf_generate_training_samples(void* stream, uint32_t n_rays, uint32_t r
 	const ngp_nerf_train_cfg* cfg, const ngp_train_view* views_dev, uint32_t n_views, const uint8_t* density_grid_bitfield,
 	uint32_t max_samples, ngp_nerf_counters* counters_dev, uint32_t* ray_indices, float* rays, uint32_t* numsteps, float* coords);
 
-/* generate_training_samples_nerf as two kernels (what Testbed::train uses): ngp_nerf_count_training_samples does the ray
+/* ngp_nerf_generate_training_samples with the batch's rays first bucketed by expected march length (what Testbed::train uses):
+ * one thread marches one ray and rays differ 4x in length, so in batch order a warp keeps under half of its lanes busy.  The rays,
+ * their counts and coordinates are those of ngp_nerf_generate_training_samples; only the slots they land in differ.
+ * sort_scratch: ngp_nerf_ray_sort_scratch_bytes(n_rays) bytes of device memory. */
+size_t ngp_nerf_ray_sort_scratch_bytes(uint32_t max_rays);
+int ngp_nerf_generate_training_samples_sorted(void* stream, uint32_t n_rays, uint32_t ray_offset, uint32_t n_rays_global, uint64_t rng_state, uint64_t rng_inc,
+	const ngp_nerf_train_cfg* cfg, const ngp_train_view* views_dev, uint32_t n_views, const uint8_t* density_grid_bitfield, uint32_t max_samples,
+	ngp_nerf_counters* counters, uint32_t* ray_indices, float* rays, uint32_t* numsteps, float* coords, void* sort_scratch);
+
+/* generate_training_samples_nerf as two kernels (an option of Testbed::train, nerf.training.split_generation): ngp_nerf_count_training_samples does the ray
  * generation, the counting march and the slot reservation — outputs as ngp_nerf_generate_training_samples minus the
  * coordinates, plus a checkpoint of the march every 32 samples in ckpt_scratch (ngp_nerf_generator_scratch_floats(n_rays) floats)
  * and (count, base, slot) per ray in seg_scratch (ngp_nerf_generator_scratch_u32(n_rays) words).  It is bound by the serial

@@ -169,6 +169,8 @@ PROTOTYPES = {
     "ngp_grid_encode": (C.c_int, [P(GridDesc), vp, u32, vp, u32, vp, vp]),
     "ngp_optimizer_step": (C.c_int, [P(NerfDesc), vp, P(AdamCfg), vp, vp, vp, vp, vp, vp, vp]),
     "ngp_nerf_generate_training_samples": (C.c_int, [vp, u32, u32, u32, u64, u64, P(NerfTrainCfg), vp, u32, vp, u32, vp, vp, vp, vp, vp]),
+    "ngp_nerf_ray_sort_scratch_bytes": (C.c_size_t, [u32]),
+    "ngp_nerf_generate_training_samples_sorted": (C.c_int, [vp, u32, u32, u32, u64, u64, P(NerfTrainCfg), vp, u32, vp, u32, vp, vp, vp, vp, vp, vp]),
     "ngp_nerf_generator_scratch_floats": (C.c_size_t, [u32]),
     "ngp_nerf_generator_scratch_u32": (C.c_size_t, [u32]),
     "ngp_nerf_count_training_samples": (C.c_int, [vp, u32, u32, u32, u64, u64, P(NerfTrainCfg), vp, u32, vp, u32, vp, vp, vp, vp, vp, vp]),

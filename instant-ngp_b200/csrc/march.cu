@@ -86,11 +86,14 @@ __global__ void __launch_bounds__(GEN_THREADS) k_generate_training_samples(
 	const uint32_t n_rays_local, const uint32_t ray_offset, const uint32_t n_rays_global, Pcg32 rng_in, const ngp_nerf_train_cfg cfg,
 	const ngp_train_view* __restrict__ views, const uint32_t n_views, const uint8_t* __restrict__ bitfield, const uint32_t max_samples,
 	ngp_nerf_counters* __restrict__ counters, uint32_t* __restrict__ ray_indices_out, float* __restrict__ rays_out,
-	uint32_t* __restrict__ numsteps_out, float* __restrict__ coords_out, float* __restrict__ t_resume_out, const uint32_t prefix
+	uint32_t* __restrict__ numsteps_out, float* __restrict__ coords_out, float* __restrict__ t_resume_out, const uint32_t prefix,
+	const uint32_t* __restrict__ perm
 ) {
-	const uint32_t li = blockIdx.x * blockDim.x + threadIdx.x;
+	const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
 	const uint32_t lane = threadIdx.x & 31u;
-	const bool in_range = li < n_rays_local;
+	const bool in_range = slot < n_rays_local;
+	// which ray of the batch this thread marches: identity, or the batch ordered by expected march length (k_ray_sort_*)
+	const uint32_t li = (perm && in_range) ? perm[slot] : slot;
 	const uint32_t i = ray_offset + li;
 
 	const Aabb aabb{V3{cfg.aabb_min[0], cfg.aabb_min[1], cfg.aabb_min[2]}, V3{cfg.aabb_max[0], cfg.aabb_max[1], cfg.aabb_max[2]}};
@@ -271,6 +274,116 @@ __global__ void __launch_bounds__(GEN_THREADS) k_generate_training_samples(
 		}
 		t_resume_out[ray_idx] = t;
 	}
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Ordering the rays of a batch by expected march length.
+// One thread marches one ray and the rays of a batch differ 4x in length (background rays skip through an empty cube, rays
+// through the object take hundreds of samples): in batch order a warp keeps 14.7 of its 32 lanes busy (ncu r1c) and, with only
+// 57 K rays for 300 K lanes, nothing hides that.  Which thread marches which ray is free (slot order is atomics-dependent in the
+// reference as well), so the batch is bucketed by an estimate of each ray's loop trips: 24 probes along the ray against the
+// occupancy bitfield coarsened to 16^3 (a coarse cell = 64 consecutive Morton-ordered bytes), occupied stretches counted in
+// steps, empty ones in voxel skips.  Three small kernels (keys + histogram, scan, scatter) produce the permutation; longest first.
+// The rays, their sample counts and their coordinates are unchanged — only their slots move.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr uint32_t SORT_BUCKETS = 64;
+constexpr float SORT_TRIPS_PER_BUCKET = 16.0f;
+constexpr uint32_t SORT_PROBES = 24;
+
+__device__ inline bool coarse_cell_occupied(V3 pos, const uint8_t* __restrict__ bitfield, uint32_t mip) {
+	const float mip_scale = scalbnf(1.0f, -(int)mip);
+	const float px = (pos.x - 0.5f) * mip_scale + 0.5f, py = (pos.y - 0.5f) * mip_scale + 0.5f, pz = (pos.z - 0.5f) * mip_scale + 0.5f;
+	const int ix = (int)(px * 16.0f), iy = (int)(py * 16.0f), iz = (int)(pz * 16.0f);
+	if (ix < 0 || ix >= 16 || iy < 0 || iy >= 16 || iz < 0 || iz >= 16) return false;
+	const uint4* p = reinterpret_cast<const uint4*>(bitfield + (size_t)(GRID_N_CELLS / 8) * mip + (size_t)morton3d((uint32_t)ix, (uint32_t)iy, (uint32_t)iz) * 64u);
+	uint32_t any = 0;
+#pragma unroll
+	for (int k = 0; k < 4; ++k) {
+		const uint4 v = __ldg(p + k);
+		any |= v.x | v.y | v.z | v.w;
+	}
+	return any != 0;
+}
+
+__global__ void __launch_bounds__(GEN_THREADS) k_ray_sort_keys(
+	const uint32_t n_rays_local, const uint32_t ray_offset, const uint32_t n_rays_global, Pcg32 rng_in, const ngp_nerf_train_cfg cfg,
+	const ngp_train_view* __restrict__ views, const uint32_t n_views, const uint8_t* __restrict__ bitfield, uint8_t* __restrict__ keys, uint32_t* __restrict__ hist
+) {
+	__shared__ uint32_t local_hist[SORT_BUCKETS];
+	if (threadIdx.x < SORT_BUCKETS) local_hist[threadIdx.x] = 0;
+	__syncthreads();
+	const uint32_t li = blockIdx.x * blockDim.x + threadIdx.x;
+	if (li < n_rays_local) {
+		const uint32_t i = ray_offset + li;
+		const Aabb aabb{V3{cfg.aabb_min[0], cfg.aabb_min[1], cfg.aabb_min[2]}, V3{cfg.aabb_max[0], cfg.aabb_max[1], cfg.aabb_max[2]}};
+		const uint32_t img = image_idx(i, n_rays_global, n_views);
+		const ngp_train_view vw = views[img];
+		Pcg32 rng = rng_in;
+		rng.advance((uint64_t)i * N_MAX_RANDOM_SAMPLES_PER_RAY);
+		float u, v;
+		random_image_pos_training(rng, vw.width, vw.height, cfg.snap_to_pixel_centers != 0, u, v);
+		V3 ro, rd;
+		uv_to_ray(u, v, vw.width, vw.height, vw.focal_x, vw.focal_y, vw.principal_x, vw.principal_y, vw.lens_mode, vw.lens_params, vw.xform, ro, rd);
+		const V3 rdn = normalize3(rd);
+		float tmin, tmax;
+		aabb_ray_intersect(aabb, ro, rdn, tmin, tmax);
+		tmin = fmaxf(tmin, 0.0f);
+		float trips = 0.0f;
+		if (tmax > tmin) {
+			const float seg = (tmax - tmin) / (float)SORT_PROBES;
+			for (uint32_t k = 0; k < SORT_PROBES; ++k) {
+				const float t = tmin + ((float)k + 0.5f) * seg;
+				const V3 pos = ro + t * rdn;
+				const uint32_t mip = mip_from_pos(pos, cfg.max_cascade);
+				if (coarse_cell_occupied(pos, bitfield, mip)) trips += seg / calc_dt(t, cfg.march);
+				else trips += seg * 128.0f * scalbnf(1.0f, -(int)mip);   // one trip per cell of that cascade
+			}
+		}
+		const uint32_t key = (uint32_t)fminf(trips / SORT_TRIPS_PER_BUCKET, (float)(SORT_BUCKETS - 1));
+		keys[li] = (uint8_t)key;
+		atomicAdd(&local_hist[key], 1u);
+	}
+	__syncthreads();
+	if (threadIdx.x < SORT_BUCKETS && local_hist[threadIdx.x]) atomicAdd(&hist[threadIdx.x], local_hist[threadIdx.x]);
+}
+
+// state: hist[64] | base[64] | cursor[64]; longest bucket first
+__global__ void k_ray_sort_scan(uint32_t* __restrict__ state) {
+	if (threadIdx.x != 0) return;
+	uint32_t acc = 0;
+	for (int b = (int)SORT_BUCKETS - 1; b >= 0; --b) {
+		state[SORT_BUCKETS + b] = acc;
+		acc += state[b];
+		state[2 * SORT_BUCKETS + b] = 0;
+	}
+}
+
+__global__ void __launch_bounds__(GEN_THREADS) k_ray_sort_scatter(const uint32_t n_rays_local, const uint8_t* __restrict__ keys, uint32_t* __restrict__ state,
+	uint32_t* __restrict__ perm) {
+	const uint32_t li = blockIdx.x * blockDim.x + threadIdx.x;
+	if (li >= n_rays_local) return;
+	const uint32_t key = keys[li];
+	const uint32_t slot = state[SORT_BUCKETS + key] + atomicAdd(&state[2 * SORT_BUCKETS + key], 1u);
+	perm[slot] = li;
+}
+
+size_t ray_sort_scratch_bytes(uint32_t max_rays) { return (size_t)max_rays * 4 + next_multiple(max_rays, 16u) + 3 * SORT_BUCKETS * 4; }
+
+// perm_out: [n_rays_local] u32 (also the start of `scratch`): scratch = perm | keys | state
+const uint32_t* sort_training_rays(cudaStream_t stream, uint32_t n_rays_local, uint32_t ray_offset, uint32_t n_rays_global, uint64_t rng_state, uint64_t rng_inc,
+	const ngp_nerf_train_cfg& cfg, const ngp_train_view* views, uint32_t n_views, const uint8_t* bitfield, void* scratch, uint32_t max_rays) {
+	if (n_rays_local == 0) return nullptr;
+	uint32_t* perm = reinterpret_cast<uint32_t*>(scratch);
+	uint8_t* keys = reinterpret_cast<uint8_t*>(scratch) + (size_t)max_rays * 4;
+	uint32_t* state = reinterpret_cast<uint32_t*>(keys + next_multiple(max_rays, 16u));
+	NGPB_CUDA_CHECK(cudaMemsetAsync(state, 0, SORT_BUCKETS * 4, stream));
+	const uint32_t blocks = div_round_up(n_rays_local, GEN_THREADS);
+	k_ray_sort_keys<<<blocks, GEN_THREADS, 0, stream>>>(n_rays_local, ray_offset, n_rays_global, Pcg32(rng_state, rng_inc, true), cfg, views, n_views, bitfield, keys, state);
+	k_ray_sort_scan<<<1, 32, 0, stream>>>(state);
+	k_ray_sort_scatter<<<blocks, GEN_THREADS, 0, stream>>>(n_rays_local, keys, state, perm);
+	NGPB_LAUNCHED(); NGPB_LAUNCHED(); NGPB_LAUNCHED();
+	NGPB_CUDA_CHECK(cudaGetLastError());
+	return perm;
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -777,7 +890,7 @@ static Aabb cfg_aabb(const ngp_nerf_train_cfg& cfg) {
 
 void generate_training_samples(cudaStream_t stream, uint32_t n_rays_local, uint32_t ray_offset, uint32_t n_rays_global, uint64_t rng_state,
 	uint64_t rng_inc, const ngp_nerf_train_cfg& cfg, const ngp_train_view* views, uint32_t n_views, const uint8_t* bitfield, uint32_t max_samples,
-	ngp_nerf_counters* counters, uint32_t* ray_indices, float* rays, uint32_t* numsteps, float* coords, float* t_resume, uint32_t prefix) {
+	ngp_nerf_counters* counters, uint32_t* ray_indices, float* rays, uint32_t* numsteps, float* coords, float* t_resume, uint32_t prefix, const uint32_t* perm) {
 	if (n_rays_local == 0) return;
 	NGPB_CHECK(n_views > 0, "generate_training_samples: no training views");
 	NGPB_CHECK(coords != nullptr, "generate_training_samples: no coordinate buffer");
@@ -789,11 +902,11 @@ void generate_training_samples(cudaStream_t stream, uint32_t n_rays_local, uint3
 	}
 	if (!t_resume) {
 		k_generate_training_samples<true><<<div_round_up(n_rays_local, GEN_THREADS), GEN_THREADS, GEN_SMEM_BYTES, stream>>>(n_rays_local, ray_offset, n_rays_global,
-			Pcg32(rng_state, rng_inc, true), cfg, views, n_views, bitfield, max_samples, counters, ray_indices, rays, numsteps, coords, nullptr, 0u);
+			Pcg32(rng_state, rng_inc, true), cfg, views, n_views, bitfield, max_samples, counters, ray_indices, rays, numsteps, coords, nullptr, 0u, perm);
 	} else {
 		NGPB_CHECK(prefix % 8u == 0u && prefix <= GEN_T_SLOTS, "generate_training_samples: the eager prefix must be a multiple of 8, at most 64");
 		k_generate_training_samples<false><<<div_round_up(n_rays_local, GEN_THREADS), GEN_THREADS, GEN_SMEM_BYTES, stream>>>(n_rays_local, ray_offset, n_rays_global,
-			Pcg32(rng_state, rng_inc, true), cfg, views, n_views, bitfield, max_samples, counters, ray_indices, rays, numsteps, coords, t_resume, prefix);
+			Pcg32(rng_state, rng_inc, true), cfg, views, n_views, bitfield, max_samples, counters, ray_indices, rays, numsteps, coords, t_resume, prefix, perm);
 	}
 	NGPB_LAUNCHED();
 	NGPB_CUDA_CHECK(cudaGetLastError());

@@ -33,7 +33,10 @@ void optimizer_step(const ngp_nerf_desc& d, cudaStream_t stream, const ngp_adam_
 	__half* grads, float* m1, float* m2, uint32_t* steps);
 void generate_training_samples(cudaStream_t stream, uint32_t n_rays_local, uint32_t ray_offset, uint32_t n_rays_global, uint64_t rng_state, uint64_t rng_inc,
 	const ngp_nerf_train_cfg& cfg, const ngp_train_view* views, uint32_t n_views, const uint8_t* bitfield, uint32_t max_samples, ngp_nerf_counters* counters,
-	uint32_t* ray_indices, float* rays, uint32_t* numsteps, float* coords, float* t_resume, uint32_t prefix);
+	uint32_t* ray_indices, float* rays, uint32_t* numsteps, float* coords, float* t_resume, uint32_t prefix, const uint32_t* perm);
+size_t ray_sort_scratch_bytes(uint32_t max_rays);
+const uint32_t* sort_training_rays(cudaStream_t stream, uint32_t n_rays_local, uint32_t ray_offset, uint32_t n_rays_global, uint64_t rng_state, uint64_t rng_inc,
+	const ngp_nerf_train_cfg& cfg, const ngp_train_view* views, uint32_t n_views, const uint8_t* bitfield, void* scratch, uint32_t max_rays);
 size_t generator_scratch_floats(uint32_t max_rays);
 size_t generator_scratch_u32(uint32_t max_rays);
 void count_training_samples(cudaStream_t stream, uint32_t n_rays_local, uint32_t ray_offset, uint32_t n_rays_global, uint64_t rng_state, uint64_t rng_inc,
@@ -202,6 +205,7 @@ struct ngp_testbed {
 	bool full_inference = false;
 	bool lazy_sample_generation = false;  // measured slower (profiles/r1c): the generator writes a prefix of each ray's coordinates; the ray-ordered inference kernel marches the rest on demand
 	uint32_t eager_prefix = 16;
+	bool sort_rays = true;           // the batch's rays bucketed by expected march length before the generator (k_ray_sort_*)
 	bool split_generation = false;   // count kernel + warp-per-ray write kernel instead of the fused generator.  Measured (profiles/r1c): beside
 	                                 // k_nerf_train only 2 of its CTAs fit per SM (registers), so the count runs in two waves and hides nothing:
 	                                 // 1.51-1.65 ms/step against 1.50-1.54 for the fused kernel prefetched behind the backward pass
@@ -231,6 +235,7 @@ struct ngp_testbed {
 		DevBuf<uint32_t> ray_indices, numsteps;
 		DevBuf<float> rays, coords, t_resume, ckpt;
 		DevBuf<uint32_t> seg_info;
+		DevBuf<uint8_t> sort_scratch;
 	} set[2];
 	uint32_t cur = 0;                     // set used by the step in flight
 	DevBuf<float> coords_compacted, loss_per_ray, reduce_scratch;
@@ -450,6 +455,7 @@ static void tb_ensure_step_scratch(ngp_testbed* t, uint32_t batch) {
 		rs.t_resume.ensure(max_rays);
 		rs.ckpt.ensure(generator_scratch_floats(max_rays));
 		rs.seg_info.ensure(generator_scratch_u32(max_rays));
+		rs.sort_scratch.ensure(ray_sort_scratch_bytes(max_rays));
 	}
 	t->loss_per_ray.ensure(max_rays);
 	t->reduce_scratch.ensure(1024);
@@ -541,8 +547,12 @@ static void tb_launch_generator(ngp_testbed* t, cudaStream_t stream, uint32_t se
 		count_training_samples(stream, rays_local, t->dp_rank * rays_local, rays_local * t->dp_world, t->rng.state, t->rng.inc, t->cfg, t->views_dev.p, tb_n_views(t),
 			t->bitfield.p, max_inference, rs.counters.p, rs.ray_indices.p, rs.rays.p, rs.numsteps.p, rs.ckpt.p, rs.seg_info.p);
 	} else {
+		const uint32_t* perm = nullptr;
+		if (t->sort_rays && rays_local >= 4096)
+			perm = sort_training_rays(stream, rays_local, t->dp_rank * rays_local, rays_local * t->dp_world, t->rng.state, t->rng.inc, t->cfg, t->views_dev.p,
+				tb_n_views(t), t->bitfield.p, rs.sort_scratch.p, 1u << 18);
 		generate_training_samples(stream, rays_local, t->dp_rank * rays_local, rays_local * t->dp_world, t->rng.state, t->rng.inc, t->cfg, t->views_dev.p, tb_n_views(t),
-			t->bitfield.p, max_inference, rs.counters.p, rs.ray_indices.p, rs.rays.p, rs.numsteps.p, rs.coords.p, tb_lazy(t) ? rs.t_resume.p : nullptr, t->eager_prefix);
+			t->bitfield.p, max_inference, rs.counters.p, rs.ray_indices.p, rs.rays.p, rs.numsteps.p, rs.coords.p, tb_lazy(t) ? rs.t_resume.p : nullptr, t->eager_prefix, perm);
 	}
 }
 // The part that always runs in the step itself, on the main stream
@@ -804,7 +814,17 @@ int ngp_nerf_generate_training_samples(void* stream, uint32_t n_rays, uint32_t r
 	uint32_t* ray_indices, float* rays, uint32_t* numsteps, float* coords) {
 	NGPB_TRY(require_device(); NGPB_CHECK(n_rays_global >= n_rays && ray_offset <= n_rays_global - n_rays, "ray shard outside the global batch");
 		generate_training_samples((cudaStream_t)stream, n_rays, ray_offset, n_rays_global, rng_state, rng_inc, *cfg, views, n_views, bitfield,
-		max_samples, counters, ray_indices, rays, numsteps, coords, nullptr, 0u));
+		max_samples, counters, ray_indices, rays, numsteps, coords, nullptr, 0u, nullptr));
+}
+size_t ngp_nerf_ray_sort_scratch_bytes(uint32_t max_rays) { return ray_sort_scratch_bytes(max_rays); }
+int ngp_nerf_generate_training_samples_sorted(void* stream, uint32_t n_rays, uint32_t ray_offset, uint32_t n_rays_global, uint64_t rng_state, uint64_t rng_inc,
+	const ngp_nerf_train_cfg* cfg, const ngp_train_view* views, uint32_t n_views, const uint8_t* bitfield, uint32_t max_samples, ngp_nerf_counters* counters,
+	uint32_t* ray_indices, float* rays, uint32_t* numsteps, float* coords, void* sort_scratch) {
+	NGPB_TRY(require_device(); NGPB_CHECK(n_rays_global >= n_rays && ray_offset <= n_rays_global - n_rays, "ray shard outside the global batch");
+		const uint32_t* perm = sort_training_rays((cudaStream_t)stream, n_rays, ray_offset, n_rays_global, rng_state, rng_inc, *cfg, views, n_views, bitfield,
+			sort_scratch, n_rays);
+		generate_training_samples((cudaStream_t)stream, n_rays, ray_offset, n_rays_global, rng_state, rng_inc, *cfg, views, n_views, bitfield,
+		max_samples, counters, ray_indices, rays, numsteps, coords, nullptr, 0u, perm));
 }
 int ngp_nerf_generate_training_samples_prefix(void* stream, uint32_t n_rays, uint32_t ray_offset, uint32_t n_rays_global, uint64_t rng_state, uint64_t rng_inc,
 	const ngp_nerf_train_cfg* cfg, const ngp_train_view* views, uint32_t n_views, const uint8_t* bitfield, uint32_t max_samples, ngp_nerf_counters* counters,
@@ -812,7 +832,7 @@ int ngp_nerf_generate_training_samples_prefix(void* stream, uint32_t n_rays, uin
 	NGPB_TRY(require_device(); NGPB_CHECK(n_rays_global >= n_rays && ray_offset <= n_rays_global - n_rays, "ray shard outside the global batch");
 		NGPB_CHECK(t_resume != nullptr, "ngp_nerf_generate_training_samples_prefix: t_resume is required");
 		generate_training_samples((cudaStream_t)stream, n_rays, ray_offset, n_rays_global, rng_state, rng_inc, *cfg, views, n_views, bitfield,
-		max_samples, counters, ray_indices, rays, numsteps, coords, t_resume, prefix));
+		max_samples, counters, ray_indices, rays, numsteps, coords, t_resume, prefix, nullptr));
 }
 int ngp_nerf_march_inference_rays(const ngp_nerf_desc* d, void* stream, uint32_t n_rays_max, const ngp_nerf_train_cfg* cfg, const ngp_nerf_counters* counters,
 	uint32_t* queue, const uint32_t* numsteps, const float* rays, const float* t_resume, uint32_t prefix, const uint8_t* bitfield, float* coords, const void* params,
@@ -1033,6 +1053,7 @@ int ngp_testbed_set_option(ngp_testbed* t, const char* name_c, double value) {
 		else if (n == "background_color.a") t->background_alpha = (float)value;
 		else if (n == "nerf.training.full_inference") { tb_invalidate_prefetch(t); t->full_inference = value != 0; }
 		else if (n == "nerf.training.lazy_sample_generation") { tb_invalidate_prefetch(t); t->lazy_sample_generation = value != 0; }
+		else if (n == "nerf.training.sort_rays") { tb_invalidate_prefetch(t); t->sort_rays = value != 0; }
 		else if (n == "nerf.training.split_generation") { tb_invalidate_prefetch(t); t->split_generation = value != 0; }
 		else if (n == "nerf.training.overlap_gate") { tb_invalidate_prefetch(t); t->overlap_gate = value != 0; }
 		else if (n == "nerf.training.eager_prefix") { NGPB_CHECK(value >= 0 && ((uint32_t)value % 8u) == 0u, "eager_prefix must be a multiple of 8"); tb_invalidate_prefetch(t); t->eager_prefix = (uint32_t)value; }

@@ -417,3 +417,45 @@ def test_count_and_write_kernels_equal_the_fused_generator(lib, scene):
     ends = nsb[:k, 1][order] + nsb[:k, 0][order]
     assert nsb[:k, 1][order][0] == 0 and np.array_equal(ends[:-1], nsb[:k, 1][order][1:]) and ends[-1] == ns
     assert np.isnan(co[ns:, 0]).all()
+
+
+@pytest.mark.parametrize("scene", SCENES)
+def test_sorted_generator_equals_the_unsorted_one_per_ray(lib, scene):
+    """rays bucketed by expected march length before the generator: per ray id nothing changes; the order is longest first"""
+    import torch
+
+    n_rays, max_samples = 8192, 8192 * 1024
+    want, got, ctx = run_generator(lib, scene, n_rays, max_samples)
+    cfg = ctx["cfg"]
+    k, ns = got["n_kept"], got["n_samples"]
+    s_cnt = torch.zeros(4, dtype=torch.int32, device="cuda")
+    s_ri = torch.zeros(n_rays, dtype=torch.int32, device="cuda")
+    s_rays = torch.zeros(n_rays, 6, dtype=torch.float32, device="cuda")
+    s_ns = torch.zeros(n_rays, 2, dtype=torch.int32, device="cuda")
+    s_co = torch.full((max_samples, 7), float("nan"), dtype=torch.float32, device="cuda")
+    scratch = torch.zeros(lib.ngp_nerf_ray_sort_scratch_bytes(n_rays), dtype=torch.uint8, device="cuda")
+    assert lib.ngp_nerf_generate_training_samples_sorted(stream(), n_rays, 0, n_rays, ctx["rng"][0], ctx["rng"][1], C.byref(cfg), ctx["t_views"].data_ptr(),
+                                                         len(ctx["views"]), ctx["t_bf"].data_ptr(), max_samples, s_cnt.data_ptr(), s_ri.data_ptr(), s_rays.data_ptr(),
+                                                         s_ns.data_ptr(), s_co.data_ptr(), scratch.data_ptr()) == 0, lib.ngp_last_error()
+    torch.cuda.synchronize()
+    cnt = s_cnt.cpu().numpy().view(np.uint32)
+    assert int(cnt[0]) == k and int(cnt[1]) == ns
+    ri, rays, nsb, co = s_ri.cpu().numpy().view(np.uint32), s_rays.cpu().numpy(), s_ns.cpu().numpy().view(np.uint32), s_co.cpu().numpy()
+    fmap = {int(r): j for j, r in enumerate(got["ray_indices"][:k])}
+    assert set(fmap) == {int(r) for r in ri[:k]}
+    for j in range(k):
+        fj = fmap[int(ri[j])]
+        n_f, b_f = got["numsteps"][fj]
+        n_s, b_s = nsb[j]
+        assert n_s == n_f and rays[j].tobytes() == got["rays"][fj].tobytes()
+        assert co[b_s:b_s + n_s].tobytes() == got["coords"][b_f:b_f + n_f].tobytes()
+    # the permutation is a permutation, and it puts long rays together at the front: the per-warp spread of counts shrinks
+    perm = scratch[: n_rays * 4].cpu().numpy().view(np.uint32)
+    assert np.array_equal(np.sort(perm), np.arange(n_rays, dtype=np.uint32))
+    per_ray = np.zeros(n_rays, dtype=np.int64)
+    per_ray[got["ray_indices"][:k]] = got["numsteps"][:k, 0]
+    def waste(order):
+        w = per_ray[order].reshape(-1, 32)
+        return 1.0 - w.sum() / max(1, (w.max(axis=1) * 32).sum())
+    print("lane waste by sample count: batch order", waste(np.arange(n_rays)), "sorted", waste(perm))
+    assert waste(perm) < waste(np.arange(n_rays))
