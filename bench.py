@@ -229,7 +229,7 @@ def main() -> None:
     ap.add_argument("--chunk", type=int, default=0, help="ray-ordered inference chunk (4 or 8)")
     ap.add_argument("--overlap", action="store_true", help="enable the side-stream prefetch of the next step's sample generation")
     ap.add_argument("--full-inference", action="store_true", help="evaluate every generated sample like the reference schedule")
-    ap.add_argument("--no-sort", action="store_true", help="A/B: generator marches the rays in batch order instead of bucketed by expected length")
+    ap.add_argument("--sort", action="store_true", help="A/B: generator marches the rays bucketed by expected length instead of in batch order")
     ap.add_argument("--split", action="store_true", help="A/B: count + write generator kernels instead of the fused one")
     ap.add_argument("--no-gate", action="store_true", help="A/B: the prefetched generator does not wait for the forward/backward kernel")
     ap.add_argument("--lazy", type=int, default=None, help="A/B: eager coordinate prefix per ray (multiple of 8); the inference kernel marches the rest on demand")
@@ -263,8 +263,8 @@ def main() -> None:
         tb._set("nerf.training.overlap_sample_generation", 1.0)
     if args.full_inference:
         tb._set("nerf.training.full_inference", 1.0)
-    if args.no_sort:
-        tb._set("nerf.training.sort_rays", 0.0)
+    if args.sort:
+        tb._set("nerf.training.sort_rays", 1.0)
     if args.split:
         tb._set("nerf.training.split_generation", 1.0)
     if args.no_gate:

@@ -205,7 +205,9 @@ struct ngp_testbed {
 	bool full_inference = false;
 	bool lazy_sample_generation = false;  // measured slower (profiles/r1c): the generator writes a prefix of each ray's coordinates; the ray-ordered inference kernel marches the rest on demand
 	uint32_t eager_prefix = 16;
-	bool sort_rays = true;           // the batch's rays bucketed by expected march length before the generator (k_ray_sort_*)
+	bool sort_rays = false;          // the batch's rays bucketed by expected march length before the generator (k_ray_sort_*).  Measured
+	                                 // (profiles/r1c): the warps that collect the long rays then diverge on every trip and set the kernel's
+	                                 // duration: generator 0.56 -> 0.80 ms, inference 0.28 -> 0.22 ms, net slower.  Parity-tested, OFF.
 	bool split_generation = false;   // count kernel + warp-per-ray write kernel instead of the fused generator.  Measured (profiles/r1c): beside
 	                                 // k_nerf_train only 2 of its CTAs fit per SM (registers), so the count runs in two waves and hides nothing:
 	                                 // 1.51-1.65 ms/step against 1.50-1.54 for the fused kernel prefetched behind the backward pass
