@@ -574,13 +574,9 @@ __global__ void __launch_bounds__(128) k_compute_loss(
 	const float* __restrict__ coords_in, float* __restrict__ coords_out, __half* __restrict__ dloss_out, float* __restrict__ loss_output,
 	const float* __restrict__ mean_density_ptr
 ) {
-	const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // ray slot
 	const uint32_t lane = threadIdx.x & 31u;
-	const uint32_t n_rays_kept = counters->n_rays;
-	if (w >= n_rays_kept) return;  // warp-uniform
-	// Ray slots are handed out by the generator in completion order, i.e. short rays first: walking them backwards starts the
-	// long rays first and leaves the short ones to fill the tail.
-	const uint32_t i = n_rays_kept - 1u - w;  // ray slot
+	if (i >= counters->n_rays) return;  // warp-uniform
 	const Aabb aabb{V3{cfg.aabb_min[0], cfg.aabb_min[1], cfg.aabb_min[2]}, V3{cfg.aabb_max[0], cfg.aabb_max[1], cfg.aabb_max[2]}};
 	const float EPSILON = 1e-4f;
 

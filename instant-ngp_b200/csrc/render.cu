@@ -333,9 +333,6 @@ __global__ void __launch_bounds__(TILE, FWD_RAYS_CTAS_PER_SM) k_nerf_forward_ray
 				if (r >= n_rays) {
 					queue_empty = true;
 				} else {
-					// slots are in the generator's completion order (short rays first): pop from the back, long rays first, so
-					// that the rays still running when the queue drains are short ones
-					r = n_rays - 1u - r;
 					n = numsteps[r * 2 + 0];
 					base = numsteps[r * 2 + 1];
 					k0 = 0;
