@@ -153,26 +153,31 @@ def peaks() -> dict:
 # ---------------------------------------------------------------------------------------------------------------------
 # CPU arm: the oracle port (tiny-cuda-nn has no CPU path) on a bounded sample of the same workload
 # ---------------------------------------------------------------------------------------------------------------------
-def cpu_training_sample(n_rays: int = 2048, n_net: int = 16384, repeats: int = 1):
+class CpuSampler:
     """times the oracle on a slice of one training step: march + loss of n_rays rays (C, single thread) and forward+backward of
-    n_net samples through the numpy network oracle (BLAS threads).  Returns (samples_per_second, description, cores)."""
-    sys.path.insert(0, str(ROOT / "tests"))
-    import util
-    from oracle import march_oracle as M
-    from oracle import net_oracle as O
+    n_net samples through the numpy network oracle (BLAS threads)."""
 
-    S = syn()
-    imgs, cams, focal = S.make_dataset(n_images=8, width=200, height=200)
-    cfg = util.make_train_cfg(aabb_scale=1)
-    views, keep = util.make_views(imgs, cams, focal)
-    bf = util.sphere_bitfield(radius=0.3, max_cascade=0)
-    d, L = util.make_desc(n_levels=16, F=2, log2_T=19, aabb_scale=1)
-    params = util.random_params(L, seed=0, trained_like=True).astype(np.float16)
-    rng = M.pcg32_seed(1337)
-    best = None
-    for _ in range(repeats):
+    def __init__(self):
+        sys.path.insert(0, str(ROOT / "tests"))
+        import util
+        from oracle import march_oracle as M
+        from oracle import net_oracle as O
+
+        self.util, self.M, self.O = util, M, O
+        S = syn()
+        imgs, cams, focal = S.make_dataset(n_images=8, width=200, height=200)
+        self.cfg = util.make_train_cfg(aabb_scale=1)
+        self.views, self.keep = util.make_views(imgs, cams, focal)
+        self.bf = util.sphere_bitfield(radius=0.3, max_cascade=0)
+        _, self.L = util.make_desc(n_levels=16, F=2, log2_T=19, aabb_scale=1)
+        self.params = util.random_params(self.L, seed=0, trained_like=True).astype(np.float16)
+        self.rng = M.pcg32_seed(1337)
+
+    def step(self, n_rays: int, n_net: int):
+        """returns (samples_per_second, seconds spent, description)"""
+        util, M, O = self.util, self.M, self.O
         t0 = time.perf_counter()
-        g = M.generate_training_samples(n_rays, 0, n_rays, rng, cfg, views, len(views), bf, n_rays * 128)
+        g = M.generate_training_samples(n_rays, 0, n_rays, self.rng, self.cfg, self.views, len(self.views), self.bf, n_rays * 128)
         t_march = time.perf_counter() - t0
         ns = max(g["n_samples"], 1)
         coords = g["coords"][:min(ns, n_net)]
@@ -180,34 +185,49 @@ def cpu_training_sample(n_rays: int = 2048, n_net: int = 16384, repeats: int = 1
             coords = np.concatenate([coords, util.random_coords(n_net - coords.shape[0], seed=3)])
         dl = (np.random.default_rng(1).normal(0, 1, size=(n_net, 4)) * 0.1).astype(np.float16)
         t1 = time.perf_counter()
-        O.nerf_forward(L, params, coords)            # the pre-compaction inference pass
-        O.nerf_backward(L, params, coords, dl)       # forward + backward of the training pass
+        O.nerf_forward(self.L, self.params, coords)            # the pre-compaction inference pass
+        O.nerf_backward(self.L, self.params, coords, dl)       # forward + backward of the training pass
         t_net = time.perf_counter() - t1
         # scale the march part to the same number of samples as the network part
         t_total = t_net + t_march * (n_net / ns)
-        sps = n_net / t_total
-        best = sps if best is None else max(best, sps)
-    desc = f"oracle port: C march+loss of {n_rays} rays, numpy hash-grid+MLP fwd and fwd+bwd of {n_net} samples (L16F2T19)"
-    return best, desc, os.cpu_count() or 1
+        desc = f"oracle port: C march+loss of {n_rays} rays, numpy hash-grid+MLP fwd and fwd+bwd of {n_net} samples (L16F2T19)"
+        return n_net / t_total, time.perf_counter() - t0, desc
+
+
+def cpu_training_sample(n_rays: int = 2048, n_net: int = 16384):
+    sps, _, desc = CpuSampler().step(n_rays, n_net)
+    return sps, desc, os.cpu_count() or 1
 
 
 def run_reference_arm(args) -> None:
+    """--impl reference: the CPU oracle port on the host cores (tiny-cuda-nn has no CPU path), rank 0 only.  Every step is a bounded
+    sample of the workload; the sample shrinks if W + K steps of the first size would not finish within ~2.5 minutes."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    vals = []
-    desc, cores = "", 1
-    for i in range(args.warmup + args.steps):
-        sps, desc, cores = cpu_training_sample(n_rays=1024, n_net=8192)
+    sampler = CpuSampler()
+    n_rays, n_net = 1024, 8192
+    n_steps = args.warmup + args.steps
+    vals, desc = [], ""
+    budget_s = 150.0
+    t_start = time.perf_counter()
+    for i in range(n_steps):
+        sps, spent, desc = sampler.step(n_rays, n_net)
         if i >= args.warmup:
             vals.append(sps)
+        remaining = n_steps - 1 - i
+        left = budget_s - (time.perf_counter() - t_start)
+        if remaining > 0 and spent * remaining > max(left, 1.0) and n_net > 512:
+            f = max(left, 1.0) / (spent * remaining)
+            n_net = max(512, int(n_net * f) // 128 * 128)
+            n_rays = max(64, int(n_rays * f) // 32 * 32)
     v = float(np.mean(vals))
     ms = 8192 / v * 1e3
     line = {
         "impl": "reference", "metric": "nerf_training_samples_per_sec", "value": v, "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
         "config": {"workload": WORKLOAD, "note": "tiny-cuda-nn has no CPU implementation (SURVEY.md §0.2); this is the CPU oracle port of the same path on a bounded sample per step"},
-        "cpu_baseline": {"value": v, "unit": "samples/s", "cores": cores, "kind": "port", "sample": desc},
+        "cpu_baseline": {"value": v, "unit": "samples/s", "cores": os.cpu_count() or 1, "kind": "port", "sample": desc + " (last step's size; shrunk to keep W + K steps within ~2.5 min)"},
         "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
