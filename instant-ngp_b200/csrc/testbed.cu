@@ -343,7 +343,7 @@ static void tb_alloc_network(ngp_testbed* t) {
 	NGPB_CUDA_CHECK(cudaMemsetAsync(t->mlp_grads_f32.p, 0, t->desc.n_mlp_params * sizeof(float), t->stream));
 }
 
-__global__ void k_cast_params(const uint32_t n, const float* __restrict__ src, __half* __restrict__ a, __half* __restrict__ b) {
+__global__ void k_cast_params(const uint32_t n, const float* __restrict__ src, __half* a, __half* b) {  // a may equal b
 	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
 	const __half h = __float2half_rn(src[i]);
