@@ -337,6 +337,24 @@ int ngp_field_inference(const ngp_field_desc* d, void* stream, uint32_t n, const
 int ngp_field_train_step(const ngp_field_desc* d, void* stream, uint32_t n, const float* positions, const float* targets, uint32_t loss_type,
 	float loss_scale, const void* dL_dout_ext, const void* params_fp16, void* grads_fp16, float* loss_values, void* out);
 
+/* tcnn::cpp::Module as a C handle (cpp_api.h:92-125; the object tiny-cuda-nn's PyTorch bindings drive): same argument meaning
+ * and layouts — input [n x n_input_dims] float32 sample-contiguous, output / dL_doutput [n x 16] fp16 (the padded width),
+ * caller-owned device params and gradients.  create: cpp_api.h:121 (HashGrid encoding over 2 or 3 dims + FullyFusedMLP, 64
+ * neurons); initialize_params: pcg32{seed}, cpp_api.cu:141-144.  backward overwrites dL_dparams (GradientMode::Overwrite) and
+ * needs no forward context (the fused kernel recomputes the tile's forward); dL_dinput must be NULL; n % 128 == 0. */
+typedef struct ngp_module ngp_module;
+ngp_module* ngp_module_create_network_with_input_encoding(uint32_t n_input_dims, uint32_t n_output_dims, const char* encoding_json, const char* network_json);
+void ngp_module_free(ngp_module* m);
+uint32_t ngp_module_n_input_dims(const ngp_module* m);
+uint32_t ngp_module_n_output_dims(const ngp_module* m); /* padded: 16 */
+size_t ngp_module_n_params(const ngp_module* m);
+int ngp_module_get_desc(const ngp_module* m, ngp_field_desc* out);
+int ngp_module_initialize_params(const ngp_module* m, size_t seed, float* params_fp32, float scale);
+int ngp_module_inference(const ngp_module* m, void* stream, uint32_t n, const float* input, void* output, const void* params);
+int ngp_module_forward(const ngp_module* m, void* stream, uint32_t n, const float* input, void* output, const void* params);
+int ngp_module_backward(const ngp_module* m, void* stream, uint32_t n, float* dL_dinput, const void* dL_doutput, void* dL_dparams, const float* input,
+	const void* output, const void* params);
+
 /* ≙ Loss<T>::evaluate (loss.h:44-60) for L2 / L1 / MAPE / SMAPE / RelativeL2: predictions [n x stride] fp16, targets
  * [n x dims] float32 -> values [n x stride] float32, gradients [n x stride] fp16 (zero in the padding). */
 int ngp_loss_evaluate(void* stream, uint32_t loss_type, uint32_t n, uint32_t stride, uint32_t dims, float loss_scale, const void* predictions,

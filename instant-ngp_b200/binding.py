@@ -239,6 +239,16 @@ PROTOTYPES = {
     "ngp_optimizer_step_flat": (C.c_int, [u32, u32, vp, P(AdamCfg), vp, vp, vp, vp, vp, vp, vp]),
     "ngp_image_generate_training_data": (C.c_int, [vp, u32, u64, u64, C.c_int, vp, u32, i32, i32, C.c_int, C.c_int, vp, vp]),
     "ngp_shuffle": (C.c_int, [vp, u32, u32, u32, vp, vp]),
+    "ngp_module_create_network_with_input_encoding": (vp, [u32, u32, cp, cp]),
+    "ngp_module_free": (None, [vp]),
+    "ngp_module_n_input_dims": (u32, [vp]),
+    "ngp_module_n_output_dims": (u32, [vp]),
+    "ngp_module_n_params": (C.c_size_t, [vp]),
+    "ngp_module_get_desc": (C.c_int, [vp, P(FieldDesc)]),
+    "ngp_module_initialize_params": (C.c_int, [vp, C.c_size_t, vp, f32]),
+    "ngp_module_inference": (C.c_int, [vp, vp, u32, vp, vp, vp]),
+    "ngp_module_forward": (C.c_int, [vp, vp, u32, vp, vp, vp]),
+    "ngp_module_backward": (C.c_int, [vp, vp, u32, vp, vp, vp, vp, vp, vp]),
     "ngp_field_testbed_create": (vp, [u32, C.c_int, vp]),
     "ngp_field_testbed_destroy": (None, [vp]),
     "ngp_field_testbed_set_image": (C.c_int, [vp, vp, i32, i32]),

@@ -504,23 +504,20 @@ static FieldDev make_fielddev(const ngp_field_desc& d) {
 	return n;
 }
 
-// Trainer::initialize_params → NetworkWithInputEncoding::initialize_params: the MLP matrices Xavier-uniform on the host
-// (gpu_matrix.h:292-307), then the hash grid with generate_random_uniform's fill pattern, all from one pcg32.
-void field_init_params_host(const ngp_field_desc* d, uint64_t seed, float* out) {
-	std::seed_seq seq{(uint32_t)seed};
-	std::vector<uint32_t> seeds(2);
-	seq.generate(seeds.begin(), seeds.end());
-	Pcg32 rng((uint64_t)seeds.front());
+// NetworkWithInputEncoding::initialize_params: the MLP matrices Xavier-uniform on the host (gpu_matrix.h:292-307), then the hash
+// grid with generate_random_uniform's fill pattern, all from one pcg32; `scale` multiplies both ranges (cpp_api.cu:141-144).
+static void field_init_params_rng(const ngp_field_desc* d, Pcg32 rng, float scale_all, float* out) {
 	float* p = out;
 	for (uint32_t l = 0; l <= d->n_hidden; ++l) {
 		const uint32_t rows = mlp_layer_out(d->n_hidden, l), cols = mlp_layer_in(d->n_hidden, l);
-		const float scale = std::sqrt(6.0f / (float)(rows + cols));
+		const float scale = std::sqrt(6.0f / (float)(rows + cols)) * scale_all;
 		for (uint32_t i = 0; i < rows * cols; ++i) p[i] = rng.next_float() * 2.0f * scale - scale;
 		p += rows * cols;
 	}
 	const size_t n = d->grid.n_params;
 	const size_t n_threads_req = (n + 3) / 4;
 	const size_t n_threads = ((n_threads_req + 127) / 128) * 128;
+	const float lo = -1e-4f * scale_all, hi = 1e-4f * scale_all;
 	for (size_t i = 0; i < n_threads; ++i) {
 		if (i >= n) break;
 		Pcg32 r = rng;
@@ -528,9 +525,16 @@ void field_init_params_host(const ngp_field_desc* d, uint64_t seed, float* out) 
 		for (size_t j = 0; j < 4; ++j) {
 			const size_t idx = i + n_threads * j;
 			if (idx >= n) break;
-			p[idx] = r.next_float() * (1e-4f - (-1e-4f)) + (-1e-4f);
+			p[idx] = r.next_float() * (hi - lo) + lo;
 		}
 	}
+}
+// Trainer::initialize_params (trainer.h:69-87): the trainer's rng comes from std::seed_seq{seed}
+void field_init_params_host(const ngp_field_desc* d, uint64_t seed, float* out) {
+	std::seed_seq seq{(uint32_t)seed};
+	std::vector<uint32_t> seeds(2);
+	seq.generate(seeds.begin(), seeds.end());
+	field_init_params_rng(d, Pcg32((uint64_t)seeds.front()), 1.0f, out);
 }
 
 template <uint32_t F, uint32_t D>
@@ -870,6 +874,70 @@ int ngp_image_generate_training_data(void* stream, uint32_t n, uint64_t rng_stat
 }
 int ngp_shuffle(void* stream, uint32_t n_elements, uint32_t stride, uint32_t seed, const float* in, float* out) {
 	NGPB_TRY(require_device(); shuffle_f32((cudaStream_t)stream, n_elements, stride, seed, in, out));
+}
+
+// ---- tcnn::cpp::Module as a C handle (cpp_api.h:92-125, cpp_api.cu:72-153) --------------------------------------------------
+struct ngp_module {
+	ngp_field_desc desc;
+};
+ngp_module* ngp_module_create_network_with_input_encoding(uint32_t n_input_dims, uint32_t n_output_dims, const char* encoding_json, const char* network_json) {
+	try {
+		const std::string et(encoding_json), nt(network_json);
+		const Json enc = JsonParser(et).parse(), net = JsonParser(nt).parse();
+		const std::string enc_type = to_lower(enc.value("otype", std::string("HashGrid")));
+		NGPB_CHECK(enc_type == "hashgrid" || enc_type == "grid", "encoding.otype must be HashGrid / Grid");
+		if (enc.contains("type")) NGPB_CHECK(to_lower(enc.value("type", std::string("hash"))) == "hash", "encoding.type must be Hash");
+		const std::string ot = to_lower(net.value("otype", std::string("FullyFusedMLP")));
+		NGPB_CHECK(ot == "fullyfusedmlp" || ot == "megakernelmlp", "network.otype must be FullyFusedMLP");
+		NGPB_CHECK(to_lower(net.value("activation", std::string("ReLU"))) == "relu", "network.activation must be ReLU");
+		NGPB_CHECK(to_lower(net.value("output_activation", std::string("None"))) == "none", "network.output_activation must be None");
+		NGPB_CHECK((uint32_t)net.value("n_neurons", 128.0) == 64, "network.n_neurons must be 64");
+		// GridEncodingTemplated defaults (grid.h:1713-1760 create_grid_encoding): L 16, F 2, T 2^19, base 16, scale 2
+		const uint32_t F = (uint32_t)enc.value("n_features_per_level", 2.0);
+		uint32_t L = (uint32_t)enc.value("n_levels", 16.0);
+		if (enc.contains("n_features") && enc.value("n_features", 0.0) > 0) L = (uint32_t)enc.value("n_features", 0.0) / F;
+		ngp_grid_desc g;
+		grid_desc_init_nd(&g, n_input_dims, L, F, (uint32_t)enc.value("log2_hashmap_size", 19.0), (uint32_t)enc.value("base_resolution", 16.0),
+			(float)enc.value("per_level_scale", 2.0));
+		NGPB_CHECK(F == 2 || F == 4, "HashGrid: n_features_per_level must be 2 or 4 in this build");
+		auto* m = new ngp_module();
+		field_desc_init(&m->desc, &g, n_input_dims, (uint32_t)net.value("n_hidden_layers", 5.0), n_output_dims);
+		return m;
+	} catch (const std::exception& e) {
+		set_last_error(e.what());
+		return nullptr;
+	}
+}
+void ngp_module_free(ngp_module* m) { delete m; }
+uint32_t ngp_module_n_input_dims(const ngp_module* m) { return m->desc.n_pos_dims; }
+uint32_t ngp_module_n_output_dims(const ngp_module* m) { return MLP_OUT; }  // the padded width, as Module::n_output_dims
+size_t ngp_module_n_params(const ngp_module* m) { return m->desc.n_params; }
+int ngp_module_get_desc(const ngp_module* m, ngp_field_desc* out) { NGPB_TRY(*out = m->desc); }
+int ngp_module_initialize_params(const ngp_module* m, size_t seed, float* params_fp32, float scale) {
+	NGPB_TRY(field_init_params_rng(&m->desc, Pcg32((uint64_t)seed), scale, params_fp32));
+}
+int ngp_module_inference(const ngp_module* m, void* stream, uint32_t n, const float* input, void* output, const void* params) {
+	NGPB_TRY(require_device(); field_inference(m->desc, (cudaStream_t)stream, n, input, (const __half*)params, (__half*)output, MLP_OUT));
+}
+// forward needs no context: the fused backward kernel recomputes the tile's forward from `input`
+int ngp_module_forward(const ngp_module* m, void* stream, uint32_t n, const float* input, void* output, const void* params) {
+	return ngp_module_inference(m, stream, n, input, output, params);
+}
+int ngp_module_backward(const ngp_module* m, void* stream, uint32_t n, float* dL_dinput, const void* dL_doutput, void* dL_dparams, const float* input,
+	const void* output, const void* params) {
+	NGPB_TRY({
+		require_device();
+		(void)output;
+		NGPB_CHECK(dL_dinput == nullptr, "ngp_module_backward: gradients w.r.t. the input positions are not implemented");
+		NGPB_CHECK(dL_dparams != nullptr, "ngp_module_backward: dL_dparams is required");
+		// GradientMode::Overwrite (cpp_api.cu:118)
+		NGPB_CUDA_CHECK(cudaMemsetAsync((__half*)dL_dparams + m->desc.grid_offset, 0, (size_t)m->desc.grid.n_params * 2, (cudaStream_t)stream));
+		float* tmp = nullptr;
+		NGPB_CUDA_CHECK(cudaMallocAsync(&tmp, m->desc.n_mlp_params * sizeof(float), (cudaStream_t)stream));
+		NGPB_CUDA_CHECK(cudaMemsetAsync(tmp, 0, m->desc.n_mlp_params * sizeof(float), (cudaStream_t)stream));
+		field_train_step(m->desc, (cudaStream_t)stream, n, input, nullptr, 0, 0.0f, (const __half*)dL_doutput, (const __half*)params, (__half*)dL_dparams, tmp, nullptr, nullptr);
+		NGPB_CUDA_CHECK(cudaFreeAsync(tmp, (cudaStream_t)stream));
+	});
 }
 
 // ---- B2: Testbed(ETestbedMode::Image / ::Sdf) ----------------------------------------------------------------------

@@ -103,3 +103,38 @@ def test_shuffle_is_the_reference_permutation():
     for i in range(10):
         j = ((i + 4) * 1434869437 + 2097192037) % 10
         assert (s[i] == a[j]).all()
+
+
+def test_module_handle_mirrors_tcnn_cpp_module():
+    """tcnn::cpp::Module surface (cpp_api.h:92-125): create from the two JSON configs, sizes, pcg32{seed} initialisation"""
+    lib = util.pkg().load_library()
+    P = util.pkg()
+    enc = b'{"otype": "HashGrid", "n_levels": 16, "n_features_per_level": 2, "log2_hashmap_size": 12, "base_resolution": 16, "per_level_scale": 1.5}'
+    net = b'{"otype": "FullyFusedMLP", "activation": "ReLU", "output_activation": "None", "n_neurons": 64, "n_hidden_layers": 2}'
+    m = lib.ngp_module_create_network_with_input_encoding(3, 1, enc, net)
+    assert m, lib.ngp_last_error()
+    d = P.FieldDesc()
+    assert lib.ngp_module_get_desc(m, C.byref(d)) == 0
+    og = O.grid_layout(16, 2, 12, 16, 1.5, n_pos_dims=3)
+    L = FO.FieldLayout(og, 2, 1)
+    assert lib.ngp_module_n_params(m) == L.n_params == d.n_params
+    assert lib.ngp_module_n_input_dims(m) == 3 and lib.ngp_module_n_output_dims(m) == 16     # padded width, like Module::n_output_dims
+    p = np.zeros(L.n_params, dtype=np.float32)
+    assert lib.ngp_module_initialize_params(m, 42, p.ctypes.data, 1.0) == 0
+    # same generator as the oracle's initialiser, seeded directly with pcg32{seed} (cpp_api.cu:141-144) instead of through seed_seq
+    rng = O.Pcg32(42)
+    want = np.empty(L.n_params, dtype=np.float32)
+    o = 0
+    for (r, c) in L.shapes:
+        scale = np.float32(np.sqrt(np.float32(6.0) / np.float32(r + c)))
+        for i in range(r * c):
+            want[o + i] = np.float32(rng.next_float()) * np.float32(2.0) * scale - scale
+        o += r * c
+    want[o:] = FO.tcnn_random_uniform(rng, L.grid.n_params, np.float32(-1e-4), np.float32(1e-4), advance=False)
+    assert p.tobytes() == want.tobytes()
+    lib.ngp_module_free(m)
+    # unsupported configurations fail loudly with the reason
+    bad = lib.ngp_module_create_network_with_input_encoding(3, 1, b'{"otype": "Frequency"}', net)
+    assert not bad and b"HashGrid" in lib.ngp_last_error()
+    bad = lib.ngp_module_create_network_with_input_encoding(3, 1, enc, b'{"otype": "FullyFusedMLP", "n_neurons": 128}')
+    assert not bad and b"64" in lib.ngp_last_error()

@@ -301,3 +301,36 @@ def test_sdf_testbed_learns_a_sphere(lib):
     assert np.abs(pred - true).mean() < 0.03
     with pytest.raises(ngp.NgpError):
         tb.train(1 << 17)   # more than the available records (testbed_sdf.cu:1582 silently skips; here it is an error)
+
+
+def test_module_handle_inference_and_backward(lib):
+    """tcnn::cpp::Module::inference / backward (cpp_api.h:100-108) through the C handle against the oracle"""
+    import torch
+
+    enc = b'{"otype": "HashGrid", "n_levels": 16, "n_features_per_level": 2, "log2_hashmap_size": 15, "base_resolution": 16, "per_level_scale": 1.5}'
+    net = b'{"otype": "FullyFusedMLP", "activation": "ReLU", "output_activation": "None", "n_neurons": 64, "n_hidden_layers": 2}'
+    m = lib.ngp_module_create_network_with_input_encoding(2, 3, enc, net)
+    assert m, lib.ngp_last_error()
+    og = O.grid_layout(16, 2, 15, 16, 1.5, n_pos_dims=2)
+    L = FO.FieldLayout(og, 2, 3)
+    n = 1024
+    params = util.random_field_params(L, seed=21).astype(np.float16)
+    pos = np.random.default_rng(22).uniform(0, 1, size=(n, 2)).astype(np.float32)
+    dl = np.zeros((n, 16), dtype=np.float16)
+    dl[:, :3] = (np.random.default_rng(23).normal(0, 1, size=(n, 3)) * 0.05).astype(np.float16)
+    t_p, t_x, t_dl = dev(params), dev(pos), dev(dl)
+    t_out = torch.zeros(n, 16, dtype=torch.float16, device="cuda")
+    t_g = torch.full((L.n_params,), 3.0, dtype=torch.float16, device="cuda")    # stale contents: backward overwrites (GradientMode::Overwrite)
+    assert lib.ngp_module_forward(m, stream(), n, t_x.data_ptr(), t_out.data_ptr(), t_p.data_ptr()) == 0, lib.ngp_last_error()
+    assert lib.ngp_module_backward(m, stream(), n, None, t_dl.data_ptr(), t_g.data_ptr(), t_x.data_ptr(), t_out.data_ptr(), t_p.data_ptr()) == 0, lib.ngp_last_error()
+    torch.cuda.synchronize()
+    want_out = FO.field_forward(L, params, pos).astype(np.float32)
+    assert np.abs(t_out.cpu().numpy().astype(np.float32) - want_out).max() <= 1e-2 * max(1.0, np.abs(want_out).max())
+    want_g = FO.field_backward(L, params, pos, dl)
+    g = t_g.cpu().numpy().astype(np.float64)
+    nm = L.n_mlp_params
+    assert np.abs(g[:nm] - want_g[:nm]).max() <= 2e-2 * np.abs(want_g[:nm]).max()
+    assert (g[nm:][want_g[nm:] == 0] == 0).all() and np.abs(g[nm:] - want_g[nm:]).max() <= 3e-2 * np.abs(want_g[nm:]).max()
+    x = torch.zeros(n, 2, device="cuda")
+    assert lib.ngp_module_backward(m, stream(), n, x.data_ptr(), t_dl.data_ptr(), t_g.data_ptr(), t_x.data_ptr(), t_out.data_ptr(), t_p.data_ptr()) != 0
+    lib.ngp_module_free(m)
