@@ -139,7 +139,7 @@ def build_testbed(rank: int, world: int, n_views: int = N_VIEWS, res: int = RES,
     tb.reload_network_from_json(S.base_config(16, 2, 19))
     if world > 1:
         tb.set_data_parallel(rank, world)
-    return tb, imgs
+    return tb, imgs, cams, focal
 
 
 def peaks() -> dict:
@@ -274,7 +274,7 @@ def main() -> None:
     __import__("__graft_entry__").build() if not (ROOT / "instant-ngp_b200" / "libngp_b200.so").exists() else None
     P = pkg()
     lib = P.load_library()
-    tb, imgs = build_testbed(rank, world, args.views, args.res, device=local_rank)
+    tb, imgs, scene_cams, scene_focal = build_testbed(rank, world, args.views, args.res, device=local_rank)
     if args.no_overlap:
         tb._set("nerf.training.overlap_sample_generation", 0.0)
     if args.chunk:
@@ -428,6 +428,10 @@ def main() -> None:
             torch.cuda.synchronize()
             ms = r0.elapsed_time(r1) / 10
             line["render"] = {"ms_per_frame": ms, "mrays_per_sec": W * H / ms / 1e3, "resolution": [W, H], "coverage": float((rgba[..., 3] > 0.5).float().mean())}
+            # quality of the model the timed steps produced: PSNR of training view 0 re-rendered at its own resolution
+            got = tb.render(args.res, args.res, scene_cams[0], scene_focal)
+            mse = float(np.mean((np.clip(got[..., :3], 0, 1) - imgs[0][..., :3]) ** 2))
+            line["quality"] = {"psnr_db_train_view_0": 10.0 * np.log10(1.0 / max(mse, 1e-12)), "after_steps": int(tb.training_step)}
         if world == 1 and not args.no_cpu_baseline:
             sps, desc, cores = cpu_training_sample()
             line["cpu_baseline"] = {"value": sps, "unit": "samples/s", "cores": cores, "kind": "port", "sample": desc}
