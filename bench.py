@@ -12,6 +12,10 @@ reference's schedule, training-ray generation + marching, inference, loss + comp
 value  : compacted samples trained per second, all ranks, dataset resident in HBM (device-timed with CUDA events).
 e2e    : the same through the public pyngp-style API while one training image per step is streamed from pinned host
          memory (H2D inside the timed region) and the step's counters + loss are read back (D2H).
+timing : steady state — 700 untimed set-up steps (--pretrain) + W warm-up steps come first: the per-step workload (rays per batch,
+         samples per ray) only settles once the scene has formed (SURVEY §8d asks for steps 500-1000); then exactly K timed steps.
+extras : roofline (k_nerf_train), cpu_baseline (oracle port, rank 0, N = 1), clocks (NVML during the timed region), render
+         (1920x1080 Mrays/s), quality (PSNR of the trained model), phase_ms_per_step (CUDA events per phase, separate pass).
 N > 1  : weak scaling — every rank trains its own 2^18-sample batch on its shard of the global ray batch; one
          torch.distributed (NCCL) all-reduce of the flat fp16 gradient buffer per step.
 """
