@@ -69,6 +69,10 @@ typedef struct ngp_nerf_desc {
 
 typedef enum ngp_activation { NGP_ACT_NONE = 0, NGP_ACT_RELU = 1, NGP_ACT_LOGISTIC = 2, NGP_ACT_EXPONENTIAL = 3 } ngp_activation;
 typedef enum ngp_loss_type { NGP_LOSS_L2 = 0, NGP_LOSS_L1 = 1, NGP_LOSS_MAPE = 2, NGP_LOSS_SMAPE = 3, NGP_LOSS_HUBER = 4, NGP_LOSS_LOGL1 = 5, NGP_LOSS_RELATIVE_L2 = 6 } ngp_loss_type;
+/* ETrainMode (common.h:47-51).  Rfl / RflRelax change only how the per-sample gradients are formed from the composited ray
+ * (fused_kernels/train_nerf.cuh:391-410): Rfl supervises every sample's colour with the radiance-field loss, RflRelax evaluates
+ * the loss gradient at the colour the ray would have if the medium behind the sample were opaque. */
+typedef enum ngp_train_mode { NGP_TRAIN_NERF = 0, NGP_TRAIN_RFL = 1, NGP_TRAIN_RFL_RELAX = 2 } ngp_train_mode;
 typedef enum ngp_lens_mode { NGP_LENS_PERSPECTIVE = 0, NGP_LENS_OPENCV = 1 } ngp_lens_mode;
 typedef enum ngp_image_type { NGP_IMAGE_NONE = 0, NGP_IMAGE_BYTE = 1, NGP_IMAGE_HALF = 2, NGP_IMAGE_FLOAT = 3 } ngp_image_type;
 typedef enum ngp_color_space { NGP_COLOR_LINEAR = 0, NGP_COLOR_SRGB = 1 } ngp_color_space;
@@ -109,6 +113,7 @@ typedef struct ngp_nerf_train_cfg {
 	uint32_t density_activation; /* default Exponential */
 	float near_distance;
 	float loss_scale;
+	uint32_t train_mode; /* ngp_train_mode; NGP_TRAIN_NERF is what the reference runs without JIT fusion (testbed_nerf.cu:3091-3093) */
 } ngp_nerf_train_cfg;
 
 /* Counters written by the training sample generator / loss kernel (NerfCounters, testbed.h). */

@@ -30,6 +30,7 @@ from .pyngp import (  # noqa: F401
     NerfActivation,
     Testbed,
     TestbedMode,
+    TrainMode,
 )
 
 __all__ = ["Testbed", "TestbedMode", "LossType", "NerfActivation", "ColorSpace", "lib", "load_library", "NgpError"]

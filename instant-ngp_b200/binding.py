@@ -104,6 +104,7 @@ class NerfTrainCfg(C.Structure):
         ("density_activation", C.c_uint32),
         ("near_distance", C.c_float),
         ("loss_scale", C.c_float),
+        ("train_mode", C.c_uint32),
     ]
 
 

@@ -586,31 +586,6 @@ __global__ void __launch_bounds__(128) k_compute_loss(
 	const __half* no = network_output + (size_t)base * 4;
 	const float* ci = coords_in + (size_t)base * 7;
 
-	// ---- pass 1: composite front to back until T < EPSILON (testbed_nerf.cu:926-948)
-	float T = 1.0f;
-	V3 rgb_ray{0, 0, 0};
-	uint32_t compacted_numsteps = 0;
-	bool stopped = false;
-	for (uint32_t c0 = 0; c0 < numsteps && !stopped; c0 += 32) {
-		const uint32_t k = c0 + lane;
-		SampleTerms st{0, 0, 0, 0};
-		float o0, o1, o2, o3, dt;
-		if (k < numsteps) st = sample_terms(no, ci, k, cfg, o0, o1, o2, o3, dt);
-		const uint32_t n_here = (numsteps - c0) < 32u ? (numsteps - c0) : 32u;
-		for (uint32_t j = 0; j < n_here; ++j) {
-			if (T < EPSILON) {
-				stopped = true;
-				break;
-			}
-			const float a = __shfl_sync(0xFFFFFFFFu, st.alpha, j);
-			const float r = __shfl_sync(0xFFFFFFFFu, st.r, j), g = __shfl_sync(0xFFFFFFFFu, st.g, j), b = __shfl_sync(0xFFFFFFFFu, st.b, j);
-			const float weight = a * T;
-			rgb_ray = rgb_ray + weight * V3{r, g, b};
-			T *= (1.0f - a);
-			++compacted_numsteps;
-		}
-	}
-
 	// ---- target colour: same draws as the generator (testbed_nerf.cu:951-1004); computed by every lane (identical values)
 	const uint32_t ray_idx = ray_indices_in[i];
 	Pcg32 rng = rng_in;
@@ -644,7 +619,49 @@ __global__ void __launch_bounds__(128) k_compute_loss(
 			target = bg;
 		}
 	}
-	if (compacted_numsteps == numsteps) rgb_ray = rgb_ray + T * bg;
+	// ---- pass 1: composite front to back until T < EPSILON (testbed_nerf.cu:926-948)
+	float T = 1.0f;
+	V3 rgb_ray{0, 0, 0}, loss_bg{0, 0, 0};
+	uint32_t compacted_numsteps = 0;
+	bool stopped = false;
+	for (uint32_t c0 = 0; c0 < numsteps && !stopped; c0 += 32) {
+		const uint32_t k = c0 + lane;
+		SampleTerms st{0, 0, 0, 0};
+		float o0, o1, o2, o3, dt;
+		if (k < numsteps) st = sample_terms(no, ci, k, cfg, o0, o1, o2, o3, dt);
+		const uint32_t n_here = (numsteps - c0) < 32u ? (numsteps - c0) : 32u;
+		for (uint32_t j = 0; j < n_here; ++j) {
+			if (T < EPSILON) {
+				stopped = true;
+				break;
+			}
+			const float a = __shfl_sync(0xFFFFFFFFu, st.alpha, j);
+			const float r = __shfl_sync(0xFFFFFFFFu, st.r, j), g = __shfl_sync(0xFFFFFFFFu, st.g, j), b = __shfl_sync(0xFFFFFFFFu, st.b, j);
+			const float weight = a * T;
+			rgb_ray = rgb_ray + weight * V3{r, g, b};
+			T *= (1.0f - a);
+			++compacted_numsteps;
+			if (cfg.train_mode == NGP_TRAIN_RFL) {
+				// train_nerf.cuh:231: the ray's accumulated per-sample radiance-field loss
+				float l0, l1, l2, gd;
+				loss_and_gradient1(target.x, r, cfg.loss_type, l0, gd);
+				loss_and_gradient1(target.y, g, cfg.loss_type, l1, gd);
+				loss_and_gradient1(target.z, b, cfg.loss_type, l2, gd);
+				loss_bg = loss_bg + weight * V3{l0, l1, l2};
+			}
+		}
+	}
+
+	if (compacted_numsteps == numsteps) {
+		rgb_ray = rgb_ray + T * bg;
+		if (cfg.train_mode == NGP_TRAIN_RFL) {   // train_nerf.cuh:251-254
+			float l0, l1, l2, gd;
+			loss_and_gradient1(target.x, bg.x, cfg.loss_type, l0, gd);
+			loss_and_gradient1(target.y, bg.y, cfg.loss_type, l1, gd);
+			loss_and_gradient1(target.z, bg.z, cfg.loss_type, l2, gd);
+			loss_bg = loss_bg + T * V3{l0, l1, l2};
+		}
+	}
 	V3 lg_grad;
 	float lx, ly, lz;
 	loss_and_gradient1(target.x, rgb_ray.x, cfg.loss_type, lx, lg_grad.x);
@@ -673,7 +690,7 @@ __global__ void __launch_bounds__(128) k_compute_loss(
 	// ---- pass 2: gradients and compaction (testbed_nerf.cu:1078-1140)
 	float* co = coords_out + (size_t)compacted_base * 7;
 	__half* dl = dloss_out + (size_t)compacted_base * 4;
-	V3 rgb_ray2{0, 0, 0};
+	V3 rgb_ray2{0, 0, 0}, loss_bg2{0, 0, 0};
 	T = 1.0f;
 	for (uint32_t c0 = 0; c0 < compacted_numsteps; c0 += 32) {
 		const uint32_t k = c0 + lane;
@@ -691,17 +708,29 @@ __global__ void __launch_bounds__(128) k_compute_loss(
 		// instead of 4-byte stores at a 28-byte stride
 		for (uint32_t e = lane; e < n_here * 7u; e += 32) co[(size_t)c0 * 7 + e] = ci[(size_t)c0 * 7 + e];
 		float my_weight = 0.0f, my_T = 0.0f;
-		V3 my_rgb_ray2{0, 0, 0};
+		V3 my_rgb_ray2{0, 0, 0}, my_loss_bg2{0, 0, 0};
+		// Rfl: this lane's per-channel loss and gradient at its own sample colour (train_nerf.cuh:393-397)
+		V3 my_ll{0, 0, 0}, my_lgr{0, 0, 0};
+		if (cfg.train_mode == NGP_TRAIN_RFL && mine) {
+			loss_and_gradient1(target.x, st.r, cfg.loss_type, my_ll.x, my_lgr.x);
+			loss_and_gradient1(target.y, st.g, cfg.loss_type, my_ll.y, my_lgr.y);
+			loss_and_gradient1(target.z, st.b, cfg.loss_type, my_ll.z, my_lgr.z);
+		}
 		for (uint32_t j = 0; j < n_here; ++j) {
 			const float a = __shfl_sync(0xFFFFFFFFu, st.alpha, j);
 			const float r = __shfl_sync(0xFFFFFFFFu, st.r, j), g = __shfl_sync(0xFFFFFFFFu, st.g, j), b = __shfl_sync(0xFFFFFFFFu, st.b, j);
 			const float weight = a * T;
 			rgb_ray2 = rgb_ray2 + weight * V3{r, g, b};
 			T *= (1.0f - a);
+			if (cfg.train_mode == NGP_TRAIN_RFL) {
+				const V3 ll{__shfl_sync(0xFFFFFFFFu, my_ll.x, j), __shfl_sync(0xFFFFFFFFu, my_ll.y, j), __shfl_sync(0xFFFFFFFFu, my_ll.z, j)};
+				loss_bg2 = loss_bg2 + weight * ll;
+			}
 			if (lane == j) {
 				my_weight = weight;
 				my_T = T;
 				my_rgb_ray2 = rgb_ray2;
+				my_loss_bg2 = loss_bg2;
 			}
 		}
 		if (mine) {
@@ -709,13 +738,30 @@ __global__ void __launch_bounds__(128) k_compute_loss(
 			const float depth = length3(pos - ray_o);
 			const V3 rgb = V3{st.r, st.g, st.b};
 			const V3 suffix = rgb_ray - my_rgb_ray2;
-			const V3 dloss_by_drgb = my_weight * lg_grad;
+			V3 dloss_by_drgb = my_weight * lg_grad;
+			float dmlp_inner;   // the bracket that multiplies density_derivative * dt (train_nerf.cuh:391-410)
+			if (cfg.train_mode == NGP_TRAIN_RFL) {
+				dloss_by_drgb = my_weight * my_lgr;
+				const V3 e = my_T * my_ll - (loss_bg - my_loss_bg2);
+				dmlp_inner = (e.x + e.y) + e.z;
+			} else if (cfg.train_mode == NGP_TRAIN_RFL_RELAX) {
+				const float tden = fmaxf(1e-6f, my_T);
+				const V3 rgb_bg{suffix.x / tden, suffix.y / tden, suffix.z / tden};
+				const V3 rgb_lerp = (1.0f - st.alpha) * rgb_bg + st.alpha * rgb;
+				V3 ll, lgr;
+				loss_and_gradient1(target.x, rgb_lerp.x, cfg.loss_type, ll.x, lgr.x);
+				loss_and_gradient1(target.y, rgb_lerp.y, cfg.loss_type, ll.y, lgr.y);
+				loss_and_gradient1(target.z, rgb_lerp.z, cfg.loss_type, ll.z, lgr.z);
+				dloss_by_drgb = my_weight * lgr;
+				dmlp_inner = dot3(lgr, my_T * rgb - suffix);
+			} else {
+				dmlp_inner = dot3(lg_grad, my_T * rgb - suffix);
+			}
 			const float d0 = loss_scale * (dloss_by_drgb.x * network_to_rgb_derivative(o0, cfg.rgb_activation) + fmaxf(0.0f, output_l2_reg * o0));
 			const float d1 = loss_scale * (dloss_by_drgb.y * network_to_rgb_derivative(o1, cfg.rgb_activation) + fmaxf(0.0f, output_l2_reg * o1));
 			const float d2 = loss_scale * (dloss_by_drgb.z * network_to_rgb_derivative(o2, cfg.rgb_activation) + fmaxf(0.0f, output_l2_reg * o2));
 			const float density_derivative = network_to_density_derivative(o3, cfg.density_activation);
-			const V3 tr = my_T * rgb - suffix;
-			const float dloss_by_dmlp = density_derivative * (dt * dot3(lg_grad, tr));
+			const float dloss_by_dmlp = density_derivative * (dt * dmlp_inner);
 			const float d3 = loss_scale * dloss_by_dmlp + (o3 < 0.0f ? -output_l1_reg_density : 0.0f) + (o3 > -10.0f && depth < cfg.near_distance ? 1e-4f : 0.0f);
 			const __half2 w01 = __floats2half2_rn(d0, d1), w23 = __floats2half2_rn(d2, d3);
 			uint2 outv;

@@ -1055,6 +1055,7 @@ int ngp_testbed_set_option(ngp_testbed* t, const char* name_c, double value) {
 		else if (n == "background_color.a") t->background_alpha = (float)value;
 		else if (n == "nerf.training.full_inference") { tb_invalidate_prefetch(t); t->full_inference = value != 0; }
 		else if (n == "nerf.training.lazy_sample_generation") { tb_invalidate_prefetch(t); t->lazy_sample_generation = value != 0; }
+		else if (n == "nerf.training.train_mode") { NGPB_CHECK(value == 0 || value == 1 || value == 2, "train_mode must be Nerf (0), Rfl (1) or RflRelax (2)"); c.train_mode = (uint32_t)value; }
 		else if (n == "nerf.training.sort_rays") { tb_invalidate_prefetch(t); t->sort_rays = value != 0; }
 		else if (n == "nerf.training.split_generation") { tb_invalidate_prefetch(t); t->split_generation = value != 0; }
 		else if (n == "nerf.training.overlap_gate") { tb_invalidate_prefetch(t); t->overlap_gate = value != 0; }
@@ -1080,6 +1081,7 @@ double ngp_testbed_get_option(ngp_testbed* t, const char* name_c) {
 	if (n == "nerf.training.snap_to_pixel_centers") return c.snap_to_pixel_centers;
 	if (n == "nerf.training.near_distance") return c.near_distance;
 	if (n == "nerf.training.loss_type") return c.loss_type;
+	if (n == "nerf.training.train_mode") return c.train_mode;
 	if (n == "nerf.training.density_grid_decay") return t->density_grid_decay;
 	if (n == "nerf.rgb_activation") return c.rgb_activation;
 	if (n == "nerf.density_activation") return c.density_activation;

@@ -25,6 +25,12 @@ class TestbedMode(enum.IntEnum):
     None_ = 4
 
 
+class TrainMode(enum.IntEnum):  # ETrainMode (common.h:47-51)
+    Nerf = 0
+    Rfl = 1
+    RflRelax = 2
+
+
 class LossType(enum.IntEnum):  # ELossType
     L2 = 0
     L1 = 1
@@ -77,6 +83,16 @@ class _Training:
     @loss_type.setter
     def loss_type(self, v) -> None:
         self._tb._set("nerf.training.loss_type", float(int(v)))
+
+    @property
+    def train_mode(self) -> TrainMode:
+        """python_api.cu:781.  Default here is Nerf — what the reference runs without JIT fusion (testbed_nerf.cu:3091-3093);
+        its JIT default is RflRelax."""
+        return TrainMode(int(self._tb._get("nerf.training.train_mode")))
+
+    @train_mode.setter
+    def train_mode(self, v) -> None:
+        self._tb._set("nerf.training.train_mode", float(int(v)))
 
     def set_image(self, frame_idx: int, img: np.ndarray, depth_img=None, depth_scale: float = 1.0) -> None:
         img = np.ascontiguousarray(img, dtype=np.float32)

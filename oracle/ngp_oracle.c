@@ -519,7 +519,34 @@ EXPORT uint32_t orc_compute_loss(uint32_t n_rays_kept, uint32_t n_rays_global, u
 					linear_to_srgb(tex.b / tex.a) * tex.a + (1.0f - tex.a) * bg.z);
 			} else target = bg;
 		}
+		const float T_end = T;
 		if (compacted_numsteps == numsteps) rgb_ray = vadd(rgb_ray, vscale(bg, T));
+		/* Rfl (train_nerf.cuh:231, 251-254): the ray's accumulated per-sample loss, background term included */
+		v3 loss_bg = V(0, 0, 0);
+		if (cfg->train_mode == NGP_TRAIN_RFL) {
+			float Tq = 1.f;
+			for (uint32_t q = 0; q < compacted_numsteps; ++q) {
+				const uint16_t* o = no + (size_t)q * 4;
+				v3 rgb = V(network_to_rgb(half_to_float(o[0]), cfg->rgb_activation), network_to_rgb(half_to_float(o[1]), cfg->rgb_activation),
+					network_to_rgb(half_to_float(o[2]), cfg->rgb_activation));
+				float dt = unwarp_dt(ci[(size_t)q * 7 + 3]);
+				float alpha = 1.f - ngp_expf(-network_to_density(half_to_float(o[3]), cfg->density_activation) * dt);
+				float weight = alpha * Tq;
+				Tq *= (1.f - alpha);
+				float l0, l1, l2, gdummy;
+				loss_and_gradient1(target.x, rgb.x, cfg->loss_type, &l0, &gdummy);
+				loss_and_gradient1(target.y, rgb.y, cfg->loss_type, &l1, &gdummy);
+				loss_and_gradient1(target.z, rgb.z, cfg->loss_type, &l2, &gdummy);
+				loss_bg = vadd(loss_bg, vscale(V(l0, l1, l2), weight));
+			}
+			if (compacted_numsteps == numsteps) {
+				float l0, l1, l2, gdummy;
+				loss_and_gradient1(target.x, bg.x, cfg->loss_type, &l0, &gdummy);
+				loss_and_gradient1(target.y, bg.y, cfg->loss_type, &l1, &gdummy);
+				loss_and_gradient1(target.z, bg.z, cfg->loss_type, &l2, &gdummy);
+				loss_bg = vadd(loss_bg, vscale(V(l0, l1, l2), T_end));
+			}
+		}
 
 		uint32_t compacted_base = compacted_counter;
 		compacted_counter += compacted_numsteps;
@@ -543,6 +570,7 @@ EXPORT uint32_t orc_compute_loss(uint32_t n_rays_kept, uint32_t n_rays_global, u
 		float* co = coords_out + (size_t)compacted_base * 7;
 		uint16_t* dl = dloss_out + (size_t)compacted_base * 4;
 		v3 rgb_ray2 = V(0, 0, 0);
+		v3 loss_bg2 = V(0, 0, 0);
 		T = 1.f;
 		for (uint32_t j = 0; j < compacted_numsteps; ++j) {
 			const float* c = ci + (size_t)j * 7;
@@ -560,12 +588,34 @@ EXPORT uint32_t orc_compute_loss(uint32_t n_rays_kept, uint32_t n_rays_global, u
 			T *= (1.f - alpha);
 			v3 suffix = vsub(rgb_ray, rgb_ray2);
 			v3 dloss_by_drgb = vscale(g, weight);
+			float dmlp_inner = 0.0f;   /* the bracket that multiplies density_derivative * dt (train_nerf.cuh:391-410) */
+			if (cfg->train_mode == NGP_TRAIN_RFL) {
+				v3 ll, lgr;
+				loss_and_gradient1(target.x, rgb.x, cfg->loss_type, &ll.x, &lgr.x);
+				loss_and_gradient1(target.y, rgb.y, cfg->loss_type, &ll.y, &lgr.y);
+				loss_and_gradient1(target.z, rgb.z, cfg->loss_type, &ll.z, &lgr.z);
+				loss_bg2 = vadd(loss_bg2, vscale(ll, weight));
+				dloss_by_drgb = vscale(lgr, weight);
+				v3 e = vsub(vscale(ll, T), vsub(loss_bg, loss_bg2));
+				dmlp_inner = (e.x + e.y) + e.z;
+			} else if (cfg->train_mode == NGP_TRAIN_RFL_RELAX) {
+				const float tden = fmaxf(1e-6f, T);
+				v3 rgb_bg = V(suffix.x / tden, suffix.y / tden, suffix.z / tden);
+				v3 rgb_lerp = vadd(vscale(rgb_bg, 1.0f - alpha), vscale(rgb, alpha));
+				v3 ll, lgr;
+				loss_and_gradient1(target.x, rgb_lerp.x, cfg->loss_type, &ll.x, &lgr.x);
+				loss_and_gradient1(target.y, rgb_lerp.y, cfg->loss_type, &ll.y, &lgr.y);
+				loss_and_gradient1(target.z, rgb_lerp.z, cfg->loss_type, &ll.z, &lgr.z);
+				dloss_by_drgb = vscale(lgr, weight);
+				dmlp_inner = vdot(lgr, vsub(vscale(rgb, T), suffix));
+			}
 			float d0 = loss_scale * (dloss_by_drgb.x * network_to_rgb_derivative(o0, cfg->rgb_activation) + fmaxf(0.0f, output_l2_reg * o0));
 			float d1 = loss_scale * (dloss_by_drgb.y * network_to_rgb_derivative(o1, cfg->rgb_activation) + fmaxf(0.0f, output_l2_reg * o1));
 			float d2 = loss_scale * (dloss_by_drgb.z * network_to_rgb_derivative(o2, cfg->rgb_activation) + fmaxf(0.0f, output_l2_reg * o2));
 			float density_derivative = network_to_density_derivative(o3, cfg->density_activation);
 			v3 tr = vsub(vscale(rgb, T), suffix);
-			float dloss_by_dmlp = density_derivative * (dt * vdot(g, tr));
+			if (cfg->train_mode == NGP_TRAIN_NERF) dmlp_inner = vdot(g, tr);
+			float dloss_by_dmlp = density_derivative * (dt * dmlp_inner);
 			float d3 = loss_scale * dloss_by_dmlp + (o3 < 0.0f ? -output_l1_reg_density : 0.0f) + (o3 > -10.0f && depth < cfg->near_distance ? 1e-4f : 0.0f);
 			dl[(size_t)j * 4 + 0] = float_to_half(d0);
 			dl[(size_t)j * 4 + 1] = float_to_half(d1);

@@ -131,8 +131,8 @@ def test_empty_and_ragged_inputs(lib):
 
 
 @pytest.mark.parametrize("scene", SCENES[:2])
-@pytest.mark.parametrize("loss_type,random_bg", [(4, 1), (0, 0)])
-def test_loss_and_compaction_bit_exact(lib, scene, loss_type, random_bg):
+@pytest.mark.parametrize("loss_type,random_bg,train_mode", [(4, 1, 0), (0, 0, 0), (4, 1, 1), (0, 1, 2), (4, 0, 2), (6, 1, 1)])
+def test_loss_and_compaction_bit_exact(lib, scene, loss_type, random_bg, train_mode):
     import torch
 
     n_rays, max_samples = 4096, 4096 * 1024
@@ -140,7 +140,7 @@ def test_loss_and_compaction_bit_exact(lib, scene, loss_type, random_bg):
     # no overflow of the compacted buffer here: which rays get clipped depends on slot order (atomics-dependent in the reference too)
     batch = 1 << int(np.ceil(np.log2(max(got["n_samples"], 2))))
     cfg = ctx["cfg"]
-    cfg.loss_type, cfg.random_bg_color = loss_type, random_bg
+    cfg.loss_type, cfg.random_bg_color, cfg.train_mode = loss_type, random_bg, train_mode   # train_mode: Nerf / Rfl / RflRelax (train_nerf.cuh:391-410)
     k, ns = got["n_kept"], got["n_samples"]
     # synthetic network outputs: moderately dense medium so that rays terminate at different depths
     rng = np.random.default_rng(5)
