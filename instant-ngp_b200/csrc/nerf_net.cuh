@@ -73,8 +73,20 @@ __device__ __forceinline__ void grid_gather(const NetDev& net, const __half* __r
 		level_corner_indices(lv, gx, gy, gz, idx);
 		if constexpr (F == 2) {
 			__half2 v[8];
+			// x-neighbours that are adjacent, aligned entries share one 8-byte load (the LSU takes scattered accesses at about one
+			// lane per clock; see grid_gather_half_nd in mlp_train.cuh)
 #pragma unroll
-			for (uint32_t c = 0; c < 8; ++c) v[c] = __ldg(reinterpret_cast<const __half2*>(lgrid) + idx[c]);
+			for (uint32_t c = 0; c < 8; c += 2) {
+				const __half2* p0 = reinterpret_cast<const __half2*>(lgrid) + idx[c];
+				if (((idx[c] & 1u) == 0u) && idx[c + 1] == idx[c] + 1u) {
+					const uint2 t = __ldg(reinterpret_cast<const uint2*>(p0));
+					v[c] = *reinterpret_cast<const __half2*>(&t.x);
+					v[c + 1] = *reinterpret_cast<const __half2*>(&t.y);
+				} else {
+					v[c] = __ldg(p0);
+					v[c + 1] = __ldg(reinterpret_cast<const __half2*>(lgrid) + idx[c + 1]);
+				}
+			}
 #pragma unroll
 			for (uint32_t c = 0; c < 8; ++c) {
 				const float w = ((c & 1u) ? wx1 : wx0) * ((c & 2u) ? wy1 : wy0) * ((c & 4u) ? wz1 : wz0);
