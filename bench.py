@@ -398,6 +398,12 @@ def main() -> None:
                     "frac": (achieved / pk["hbm_gbs"]) if achieved else None, "traffic": K_NERF_TRAIN_DRAM_BYTES, "peak_source": pk["source"], "ms_per_launch": fb_ms,
                     "algorithmic_bytes_per_launch": alg_bytes,
                     "traffic_source": "profiles/r1c_steady_state.md",
+                    # what actually bounds the kernel: the SM load/store unit takes scattered 4/8-byte accesses at ~1 lane per clock
+                    # (B300_MICROARCH.md: REDG 1.29 cyc/lane, spread addresses).  Per sample: 16 levels x 8 corners gathered + reduced, x-neighbour
+                    # pairs sharing one access when adjacent and aligned (half of them): 96 + 96 lane accesses.
+                    "lsu_floor": {"lane_accesses_per_sample": 192, "cycles_per_lane": 1.29, "sm_count": 148, "sm_mhz": clocks.get("sm_mhz") or 1965.0,
+                                  "floor_ms": 192 * 1.29 * BATCH / 148 / ((clocks.get("sm_mhz") or 1965.0) * 1e3),
+                                  "frac": (192 * 1.29 * BATCH / 148 / ((clocks.get("sm_mhz") or 1965.0) * 1e3)) / fb_ms if fb_ms > 0 else None},
                     "note": "the 26 MB fp16 table and its gradient table are L2-resident on B200: the kernel is bound by L2 gather/reduction latency, DRAM traffic is an eighth of the algorithmic bytes"}
         line = {
             "metric": "nerf_training_samples_per_sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
