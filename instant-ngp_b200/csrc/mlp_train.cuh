@@ -227,7 +227,17 @@ __device__ __forceinline__ void grid_gather_half_nd(const NET& net, const __half
 		} else {
 			uint2 v[NC];
 #pragma unroll
-			for (uint32_t c = 0; c < NC; ++c) v[c] = __ldg(reinterpret_cast<const uint2*>(lgrid) + idx[c]);
+			for (uint32_t c = 0; c < NC; c += 2) {   // F = 4: 8-byte entries, adjacent aligned x-neighbours as one 16-byte load
+				const uint2* p0 = reinterpret_cast<const uint2*>(lgrid) + idx[c];
+				if (((idx[c] & 1u) == 0u) && idx[c + 1] == idx[c] + 1u) {
+					const uint4 t = __ldg(reinterpret_cast<const uint4*>(p0));
+					v[c] = make_uint2(t.x, t.y);
+					v[c + 1] = make_uint2(t.z, t.w);
+				} else {
+					v[c] = __ldg(p0);
+					v[c + 1] = __ldg(reinterpret_cast<const uint2*>(lgrid) + idx[c + 1]);
+				}
+			}
 			__half2 a0 = __float2half2_rn(0.0f), a1 = a0;
 #pragma unroll
 			for (uint32_t c = 0; c < NC; ++c) {
@@ -268,6 +278,27 @@ __device__ __forceinline__ void grid_scatter_half_nd(const NET& net, __half* __r
 				} else {
 					asm volatile("red.relaxed.gpu.global.add.noftz.f16x2 [%0], %1;" ::"l"(lgrad + cidx[c]), "r"(*reinterpret_cast<const uint32_t*>(&v0)) : "memory");
 					asm volatile("red.relaxed.gpu.global.add.noftz.f16x2 [%0], %1;" ::"l"(lgrad + cidx[c + 1]), "r"(*reinterpret_cast<const uint32_t*>(&v1)) : "memory");
+				}
+			}
+			continue;
+		}
+		if constexpr (F == 4) {
+#pragma unroll
+			for (uint32_t c = 0; c < NC; c += 2) {
+				const __half2 w0 = __float2half2_rn(cell.weight(c)), w1 = __float2half2_rn(cell.weight(c + 1));
+				const __half2 a0 = __hmul2(w0, g[ll * 2 + 0]), a1 = __hmul2(w0, g[ll * 2 + 1]), b0 = __hmul2(w1, g[ll * 2 + 0]), b1 = __hmul2(w1, g[ll * 2 + 1]);
+				if (((cidx[c] & 1u) == 0u) && cidx[c + 1] == cidx[c] + 1u) {
+					asm volatile("red.relaxed.gpu.global.add.noftz.v4.f16x2 [%0], {%1, %2, %3, %4};" ::"l"(lgrad + (size_t)cidx[c] * 2),
+								 "r"(*reinterpret_cast<const uint32_t*>(&a0)), "r"(*reinterpret_cast<const uint32_t*>(&a1)), "r"(*reinterpret_cast<const uint32_t*>(&b0)),
+								 "r"(*reinterpret_cast<const uint32_t*>(&b1))
+								 : "memory");
+				} else {
+					asm volatile("red.relaxed.gpu.global.add.noftz.v2.f16x2 [%0], {%1, %2};" ::"l"(lgrad + (size_t)cidx[c] * 2), "r"(*reinterpret_cast<const uint32_t*>(&a0)),
+								 "r"(*reinterpret_cast<const uint32_t*>(&a1))
+								 : "memory");
+					asm volatile("red.relaxed.gpu.global.add.noftz.v2.f16x2 [%0], {%1, %2};" ::"l"(lgrad + (size_t)cidx[c + 1] * 2), "r"(*reinterpret_cast<const uint32_t*>(&b0)),
+								 "r"(*reinterpret_cast<const uint32_t*>(&b1))
+								 : "memory");
 				}
 			}
 			continue;

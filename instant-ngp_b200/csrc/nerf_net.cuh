@@ -95,7 +95,17 @@ __device__ __forceinline__ void grid_gather(const NetDev& net, const __half* __r
 		} else {
 			uint2 v[8];
 #pragma unroll
-			for (uint32_t c = 0; c < 8; ++c) v[c] = __ldg(reinterpret_cast<const uint2*>(lgrid) + idx[c]);
+			for (uint32_t c = 0; c < 8; c += 2) {   // adjacent aligned x-neighbours as one 16-byte load
+				const uint2* p0 = reinterpret_cast<const uint2*>(lgrid) + idx[c];
+				if (((idx[c] & 1u) == 0u) && idx[c + 1] == idx[c] + 1u) {
+					const uint4 t = __ldg(reinterpret_cast<const uint4*>(p0));
+					v[c] = make_uint2(t.x, t.y);
+					v[c + 1] = make_uint2(t.z, t.w);
+				} else {
+					v[c] = __ldg(p0);
+					v[c + 1] = __ldg(reinterpret_cast<const uint2*>(lgrid) + idx[c + 1]);
+				}
+			}
 #pragma unroll
 			for (uint32_t c = 0; c < 8; ++c) {
 				const float w = ((c & 1u) ? wx1 : wx0) * ((c & 2u) ? wy1 : wy0) * ((c & 4u) ? wz1 : wz0);
