@@ -51,8 +51,8 @@ def syn():
 
 
 # ---------------------------------------------------------------------------------------------------------------------
-# dram__bytes_read.sum + dram__bytes_write.sum of one k_nerf_train launch at this workload (ncu --set full, profiles/r1c_steady_state.md)
-K_NERF_TRAIN_DRAM_BYTES = 54.13e6 + 0.67e6
+# dram__bytes_read.sum + dram__bytes_write.sum of one k_nerf_train launch at this workload (ncu --set full, profiles/r1e_end_of_round.md)
+K_NERF_TRAIN_DRAM_BYTES = 54.52e6 + 0.20e6
 
 
 class ClockSampler:
@@ -397,7 +397,7 @@ def main() -> None:
         roofline = {"bound": "hbm", "kernel": "k_nerf_train (+k_mlp_grads_finalize)", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
                     "frac": (achieved / pk["hbm_gbs"]) if achieved else None, "traffic": K_NERF_TRAIN_DRAM_BYTES, "peak_source": pk["source"], "ms_per_launch": fb_ms,
                     "algorithmic_bytes_per_launch": alg_bytes,
-                    "traffic_source": "profiles/r1c_steady_state.md",
+                    "traffic_source": "profiles/r1e_end_of_round.md",
                     # what actually bounds the kernel: the SM load/store unit takes scattered 4/8-byte accesses at ~1 lane per clock
                     # (B300_MICROARCH.md: REDG 1.29 cyc/lane, spread addresses).  Per sample: 16 levels x 8 corners gathered + reduced, x-neighbour
                     # pairs sharing one access when adjacent and aligned (half of them): 96 + 96 lane accesses.
