@@ -104,6 +104,8 @@ def build_reference(verbose: bool = False) -> bool:
         targets.append("harness")
     if (ROOT / "oracle" / "ref" / "ref_host_harness.cu").exists():
         targets.append("host")
+    if (ROOT / "oracle" / "ref" / "ref_snapshot_harness.cu").exists():
+        targets.append("snapshot")
     r = subprocess.run(["make", "-C", str(ROOT / "oracle" / "ref"), "-j8", *targets], capture_output=not verbose, text=True)
     if r.returncode != 0:
         raise RuntimeError("building oracle/_ref failed:\n" + (r.stdout or "") + (r.stderr or ""))

@@ -93,6 +93,20 @@ private:
 			if (*q == '.' || *q == 'e' || *q == 'E' || *q == 'n' || *q == 'i') j.integer = false;
 		return j;
 	}
+	uint32_t hex4() {  // p is on the 'u' of a \uXXXX escape; leaves p on its last hex digit
+		if (p + 4 >= s.size()) fail("truncated \\u escape");
+		uint32_t v = 0;
+		for (int k = 1; k <= 4; ++k) {
+			const char ch = s[p + k];
+			v <<= 4;
+			if (ch >= '0' && ch <= '9') v |= (uint32_t)(ch - '0');
+			else if (ch >= 'a' && ch <= 'f') v |= (uint32_t)(ch - 'a' + 10);
+			else if (ch >= 'A' && ch <= 'F') v |= (uint32_t)(ch - 'A' + 10);
+			else fail("bad hex digit in \\u escape");
+		}
+		p += 4;
+		return v;
+	}
 	std::string string() {
 		++p;
 		std::string out;
@@ -103,6 +117,33 @@ private:
 					case 'n': out += '\n'; break;
 					case 't': out += '\t'; break;
 					case 'r': out += '\r'; break;
+					case 'b': out += '\b'; break;
+					case 'f': out += '\f'; break;
+					case 'u': {
+						uint32_t cp = hex4();
+						if (cp >= 0xD800u && cp < 0xDC00u && p + 2 < s.size() && s[p + 1] == '\\' && s[p + 2] == 'u') {  // surrogate pair
+							p += 2;
+							const uint32_t lo = hex4();
+							if (lo < 0xDC00u || lo > 0xDFFFu) fail("bad low surrogate in \\u escape");
+							cp = 0x10000u + ((cp - 0xD800u) << 10) + (lo - 0xDC00u);
+						}
+						if (cp < 0x80u) {
+							out += (char)cp;
+						} else if (cp < 0x800u) {
+							out += (char)(0xC0u | (cp >> 6));
+							out += (char)(0x80u | (cp & 0x3Fu));
+						} else if (cp < 0x10000u) {
+							out += (char)(0xE0u | (cp >> 12));
+							out += (char)(0x80u | ((cp >> 6) & 0x3Fu));
+							out += (char)(0x80u | (cp & 0x3Fu));
+						} else {
+							out += (char)(0xF0u | (cp >> 18));
+							out += (char)(0x80u | ((cp >> 12) & 0x3Fu));
+							out += (char)(0x80u | ((cp >> 6) & 0x3Fu));
+							out += (char)(0x80u | (cp & 0x3Fu));
+						}
+						break;
+					}
 					default: out += s[p]; break;
 				}
 			} else {

@@ -246,6 +246,7 @@ inline void json_dump(const Json& j, std::string& o) {
 			for (char c : j.str) {
 				if (c == '"' || c == '\\') { o += '\\'; o += c; }
 				else if (c == '\n') o += "\\n";
+				else if ((unsigned char)c < 0x20u) { char b[8]; snprintf(b, sizeof(b), "\\u%04x", (unsigned)(unsigned char)c); o += b; }
 				else o += c;
 			}
 			o += '"';

@@ -205,6 +205,67 @@ def test_loads_a_snapshot_written_the_way_the_reference_writes_it(trained, tmp_p
         tb2.load_snapshot(str(path))
 
 
+def test_loads_a_snapshot_written_by_the_reference_serializer_stack():
+    """tests/golden/ref_snapshot.ingp was written by oracle/ref/ref_snapshot_harness.cu: nlohmann::json::to_msgpack through zstr's
+    gzip stream, every structured value through the reference's own to_json (json_binding.h, vec_json.h), keys as
+    Testbed::save_snapshot / Trainer::serialize assign them (src/testbed.cu:5288-5355, trainer.h:442-455)"""
+    P = util.pkg()
+    golden = Path(__file__).resolve().parent / "golden" / "ref_snapshot.ingp"
+    tb = P.Testbed()
+    tb.load_snapshot(str(golden))
+    n = tb.n_params
+    assert n == 141312 and tb.training_step == 1234 and abs(tb.loss - 0.00123) < 1e-8
+    i = np.arange(n, dtype=np.uint64)
+    pattern = ((((i * 37) % 1001).astype(np.float32) - 500.0) / 4000.0).astype(np.float16)
+    assert np.array_equal(tb.get_params(inference=True), pattern)
+    assert np.array_equal(tb.get_params(inference=False), pattern)
+    grid, bits = tb.get_density_grid()
+    k = np.arange(128 ** 3)
+    want_grid = np.where(k % 7 == 0, np.float32(1.5), np.float32(0.001) * (k % 5).astype(np.float32)).astype(np.float16).astype(np.float32)
+    assert np.array_equal(grid.reshape(-1)[: 128 ** 3], want_grid)
+    # bitfield: cells above min(mean, NERF_MIN_OPTICAL_THICKNESS()) — here exactly the 1.5 cells
+    # (update_density_grid_mean_and_bitfield, testbed_nerf.cu:3357-3377; mean ~ 0.2157 > 0.01)
+    occ = np.unpackbits(bits[: 128 ** 3 // 8], bitorder="little")
+    assert np.array_equal(occ.astype(bool), want_grid > 0.01)
+    c = tb.counters()
+    assert c["rays_per_batch"] == 4096 and c["measured_batch_size"] == 250000 and c["measured_batch_size_before_compaction"] == 300000
+    # dataset metadata came from the file: render through view 1's OpenCV lens works and is finite
+    cam = np.array([[0.0, 1.0, 0.0, 0.5], [0.6, 0.0, 0.8, 0.5], [0.8, 0.0, -0.6, 0.0]], dtype=np.float32)   # xforms[0].start of the file
+    img = tb.render(64, 48, cam, 50.0)
+    assert img.shape == (48, 64, 4) and np.isfinite(img).all()
+
+
+REF_SNAPSHOT = Path(__file__).resolve().parents[1] / "oracle" / "_ref" / "ref_snapshot"
+
+
+@pytest.mark.skipif(not REF_SNAPSHOT.exists(), reason="oracle/_ref/ref_snapshot not built (make -C oracle/ref snapshot; needs /root/reference)")
+def test_the_reference_serializer_stack_reads_our_snapshot(trained, tmp_path):
+    """the other direction: a file written by ngp_testbed_save_snapshot_ex goes through zstr + nlohmann::json::from_msgpack and the
+    reference's from_json for BoundingBox / NerfDataset / Lens / TrainingXForm (the typed reads of Testbed::load_snapshot,
+    src/testbed.cu:5357-5460); binary payloads are compared by checksum"""
+    import json
+    import subprocess
+
+    tb, imgs, cams, focal, _, _ = trained
+    path = tmp_path / "ours.ingp"
+    tb.save_snapshot(str(path), include_optimizer_state=True)
+    d = json.loads(subprocess.check_output([str(REF_SNAPSHOT), "dump", str(path)]))
+    s = d["snapshot"]
+    n = tb.n_params
+    assert s["n_params"] == n and s["params_type"] == "__half" and s["version"] == 1 and s["mode"] == "nerf"
+    params = tb.get_params(inference=True).tobytes()
+    assert s["params_binary"]["bytes"] == 2 * n and s["params_binary"]["wsum64"] == util.wsum64(params)
+    grid, _ = tb.get_density_grid()
+    assert s["density_grid_binary"]["wsum64"] == util.wsum64(grid.astype(np.float16).tobytes())
+    ds = s["nerf"]["dataset"]    # re-emitted by the reference's to_json(NerfDataset) after its from_json accepted ours
+    assert ds["n_images"] == 24 and len(ds["xforms"]) == 24 and ds["aabb_scale"] == 1 and ds["wants_importance_sampling"] is True
+    assert np.allclose(np.array(ds["xforms"][7]["start"]), np.asarray(cams[7])[:3, :4], atol=1e-6)
+    assert ds["metadata"][0]["resolution"] == [160, 160] and abs(ds["metadata"][0]["focal_length"][1] - focal) < 1e-3
+    assert s["aabb"] == {"min": [0.0, 0.0, 0.0], "max": [1.0, 1.0, 1.0]}
+    adam = s["optimizer"]["nested"]["nested"]
+    assert adam["current_step"] == tb.training_step and adam["first_moments_binary"]["bytes"] == 4 * n
+
+
 def test_errors_are_reported(trained):
     P = util.pkg()
     tb = P.Testbed()

@@ -73,3 +73,72 @@ def test_binary_values_and_errors(lib):
     n = C.c_size_t(0)
     bad = (C.c_uint8 * 3)(0x82, 0xA1, 0x61)
     assert lib.ngp_msgpack_to_json(bad, 3, 0, out, 64, C.byref(n)) != 0 and b"truncated" in lib.ngp_last_error()
+
+
+# ---- pinned against the reference's own serializer stack (oracle/ref/ref_snapshot_harness.cu: nlohmann::json, zstr,
+# tcnn vec_json.h, json_binding.h compiled from /root/reference); goldens by tests/golden/make_ref_snapshot_golden.py
+from pathlib import Path
+
+import numpy as np
+
+GOLDEN = Path(__file__).resolve().parent / "golden"
+REF_EXE = Path(__file__).resolve().parents[1] / "oracle" / "_ref" / "ref_snapshot"
+
+
+def fnv1a64(b: bytes) -> str:
+    # 64-bit FNV-1a over the bytes, folded through numpy-free big-int arithmetic in 64 KiB pieces
+    h = 1469598103934665603
+    for x in b:
+        h = ((h ^ x) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+    return f"{h:016x}"
+
+
+def strip(j):
+    """{"bytes": n, "fnv1a64": h, "wsum64": w} -> {"bytes": n}: the product's JSON rendering of a binary value carries the size only"""
+    if isinstance(j, dict):
+        if set(j) == {"bytes", "fnv1a64", "wsum64"}:
+            return {"bytes": j["bytes"]}
+        return {k: strip(v) for k, v in j.items()}
+    if isinstance(j, list):
+        return [strip(v) for v in j]
+    return j
+
+
+def test_writer_is_byte_identical_to_nlohmann_to_msgpack(lib):
+    doc = json.loads((GOLDEN / "ref_pack.json").read_text())
+    want = (GOLDEN / "ref_pack.msgpack").read_bytes()
+    got = to_msgpack(lib, doc)
+    assert got == want
+    assert from_msgpack(lib, want) == doc
+
+
+def test_reads_a_snapshot_written_by_the_reference_serializer(lib):
+    raw = (GOLDEN / "ref_snapshot.ingp").read_bytes()
+    want = json.loads((GOLDEN / "ref_snapshot.dump.json").read_text())
+    got = from_msgpack(lib, raw, gz=True)
+    assert got == strip(want)
+    # and the payload is what the harness says it wrote: closed-form fp16 patterns
+    d = msgpack.unpackb(gzip.decompress(raw), raw=False)
+    s = d["snapshot"]
+    n = s["n_params"]
+    i = np.arange(n, dtype=np.uint64)
+    pattern = (((i * 37) % 1001).astype(np.float32) - 500.0) / 4000.0
+    assert np.array_equal(np.frombuffer(s["params_binary"], dtype=np.float16), pattern.astype(np.float16))
+    assert want["snapshot"]["params_binary"] == {"bytes": 2 * n, "fnv1a64": fnv1a64(s["params_binary"]), "wsum64": util.wsum64(s["params_binary"])}
+    assert len(s["density_grid_binary"]) == 2 * 128 ** 3
+    ds = s["nerf"]["dataset"]
+    assert ds["n_images"] == 3 and ds["metadata"][1]["lens"] == {"is_fisheye": False, "k1": 0.0625, "k2": -0.03125, "p1": 0.001953125, "p2": -0.0009765625}
+    assert ds["metadata"][0]["lens"] is None or ds["metadata"][0]["lens"] == {}   # perspective: to_json(Lens) assigns nothing
+
+
+@pytest.mark.skipif(not REF_EXE.exists(), reason="oracle/_ref/ref_snapshot not built (make -C oracle/ref snapshot; needs /root/reference)")
+def test_live_reference_serializer_agrees_on_fresh_documents(lib, tmp_path):
+    import subprocess
+
+    rng = np.random.default_rng(5)
+    doc = {"f32": [float(np.float32(x)) for x in rng.normal(size=64)], "f64": [float(x) for x in rng.normal(size=64)],
+           "i": [int(x) for x in rng.integers(-2 ** 40, 2 ** 40, size=64)], "u": [int(x) for x in rng.integers(0, 2 ** 53, size=16)],   # the product's Json holds numbers as double: integers exact to 2^53
+           "s": ["x" * int(k) for k in rng.integers(0, 400, size=16)] + ["tab\there", "caf\u00e9 \U0001F600", "q\"b\\"], "cfg": CONFIG}
+    (tmp_path / "d.json").write_text(json.dumps(doc))
+    subprocess.check_call([str(REF_EXE), "pack", str(tmp_path / "d.json"), str(tmp_path / "d.msgpack")])
+    assert to_msgpack(lib, doc) == (tmp_path / "d.msgpack").read_bytes()

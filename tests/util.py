@@ -201,3 +201,10 @@ def test_image(w=96, h=64, seed=0):
     img[..., :3] += rng.uniform(0, 0.02, size=(h, w, 3)).astype(np.float32)
     img[..., :3] = np.clip(img[..., :3], 0.0, 1.0)
     return img
+
+
+def wsum64(b: bytes) -> str:
+    """sum of byte[i] * (i + 1) mod 2^64, as oracle/ref/ref_snapshot_harness.cu prints it for binary values"""
+    a = np.frombuffer(b, dtype=np.uint8).astype(np.uint64)
+    with np.errstate(over="ignore"):
+        return str(int((a * (np.arange(a.size, dtype=np.uint64) + np.uint64(1))).sum(dtype=np.uint64)))
