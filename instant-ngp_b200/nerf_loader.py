@@ -7,8 +7,13 @@ nerf -> ngp coordinate change) lives here; pixels are decoded with PIL and hande
 and stored premultiplied fp16 by `ngp_testbed_set_image` (the reference keeps the bytes and converts on every read,
 common_device.cuh:661-735 — same values up to the fp16 rounding of the stored pixel).
 
+Pinned against the reference's own `ngp::load_nerf`, compiled from /root/reference and run over the scenes of
+tests/loader_scenes.py (oracle/ref/ref_loader_harness.cu -> tests/golden/ref_loader.json, tests/test_nerf_loader.py): frame order
+and culling, scale / offset / up / render_aabb, per-image focal length, principal point, lens, transform and the stored pixel bytes.
+
 Not supported (raises): EXR images, depth supervision, per-pixel ray files, dynamic masks, rolling shutter, fisheye /
-f-theta / lat-long lenses, environment maps."""
+f-theta / lat-long lenses, environment maps.  Several transform files with different `scale` / `offset` use the final values for
+every frame (the reference converts matrices on pool threads racing the parse of the next file, nerf_loader.cu:536-706)."""
 from __future__ import annotations
 
 import json
@@ -60,7 +65,8 @@ def read_lens(j: dict, lens: dict) -> dict:
     out = dict(lens)
     if j.get("is_fisheye", False) or any(k in j for k in ("ftheta_p0", "latlong", "equirectangular", "orthographic")):
         raise ValueError("only perspective and OpenCV lenses are supported")
-    for name, idx in (("k1", 0), ("k2", 1), ("p1", 2), ("p2", 3)):
+    # k3 / k4 land in the slots p1 / p2 overwrite afterwards, exactly as in the reference (:41-47)
+    for name, idx in (("k1", 0), ("k2", 1), ("k3", 2), ("k4", 3), ("p1", 2), ("p2", 3)):
         if name in j:
             out["params"] = list(out["params"])
             out["params"][idx] = float(j[name])
@@ -75,12 +81,17 @@ def read_lens(j: dict, lens: dict) -> dict:
     return out
 
 
-def nerf_matrix_to_ngp(m: np.ndarray, scale: float, offset) -> np.ndarray:
-    """NerfDataset::nerf_matrix_to_ngp (nerf_loader.h:101-120): flip y and z columns, scale + offset the origin, cycle axes"""
+def nerf_matrix_to_ngp(m: np.ndarray, scale: float, offset, from_mitsuba: bool = False) -> np.ndarray:
+    """NerfDataset::nerf_matrix_to_ngp (nerf_loader.h:101-120): flip the y and z columns, scale + offset the origin, then cycle the
+    axes xyz <- yzx — or, for Mitsuba scenes, negate the x and z columns instead"""
     m = np.asarray(m, dtype=np.float32)[:3, :4].copy()
     m[:, 1] *= -1
     m[:, 2] *= -1
     m[:, 3] = m[:, 3] * np.float32(scale) + np.asarray(offset, dtype=np.float32)
+    if from_mitsuba:
+        m[:, 0] *= -1
+        m[:, 2] *= -1
+        return m
     return m[[1, 2, 0], :]
 
 
@@ -101,7 +112,7 @@ def load_metadata(json_paths) -> dict:
     if not json_paths:
         raise ValueError("Cannot load NeRF data from an empty set of paths.")
     ds = dict(images=[], scale=NERF_SCALE, offset=[0.5, 0.5, 0.5], aabb_scale=1, up=[0.0, 1.0, 0.0], render_aabb=None, from_mitsuba=False,
-              white_transparent=False, black_transparent=False)
+              white_transparent=False, black_transparent=False, wants_importance_sampling=True, n_extra_learnable_dims=0)
     for jp in json_paths:
         j = json.loads(_strip_json_comments(jp.read_text()))
         if isinstance(j.get("camera"), list):
@@ -135,6 +146,12 @@ def load_metadata(json_paths) -> dict:
                 ds[k] = bool(j[k])
         if "scale" in j:
             ds["scale"] = float(j["scale"])
+        if "importance_sampling" in j:
+            ds["wants_importance_sampling"] = bool(j["importance_sampling"])
+        if "n_extra_learnable_dims" in j:
+            ds["n_extra_learnable_dims"] = int(j["n_extra_learnable_dims"])
+            if ds["n_extra_learnable_dims"]:
+                raise ValueError("'n_extra_learnable_dims' is not supported")
         for k in ("enable_depth_loading", "integer_depth_scale", "envmap"):
             if j.get(k):
                 raise ValueError(f"'{k}' is not supported")
@@ -157,35 +174,68 @@ def load_metadata(json_paths) -> dict:
                 raise FileNotFoundError(f"Could not find image file '{path}'.")
             if "transform_matrix_start" in f or "transform_matrix_end" in f:
                 raise ValueError("per-frame start / end transforms (motion blur) are not supported")
-            ds["images"].append(dict(path=path, frame=f, globals=j, lens=read_lens(f, lens)))
+            if (path.parent / f"dynamic_mask_{path.stem}.png").exists():
+                raise ValueError("dynamic masks are not supported")
+            if (path.parent / f"rays_{path.stem}.dat").exists() and j.get("enable_ray_loading", True):
+                raise ValueError("per-pixel ray files are not supported")
+            if "driver_parameters" in f:
+                raise ValueError("light directions (driver_parameters) are not supported")
+            ds["images"].append(dict(path=path, json_path=str(f["file_path"]), frame=f, globals=j, lens=read_lens(f, lens)))
     if not ds["images"]:
         raise ValueError("No training images were found for NeRF training!")
     # the transform needs the final scale / offset (the reference applies them as it walks the files; one file = same thing)
     for im in ds["images"]:
-        im["xform"] = nerf_matrix_to_ngp(np.asarray(im["frame"]["transform_matrix"], dtype=np.float32), ds["scale"], ds["offset"])
+        im["xform"] = nerf_matrix_to_ngp(np.asarray(im["frame"]["transform_matrix"], dtype=np.float32), ds["scale"], ds["offset"], ds["from_mitsuba"])
+        # focal length: the file's, overridden by the frame's (nerf_loader.cu:676-680); needs the image size for the fov forms
+        im["resolution"] = image_size(im["path"])
+        fl = read_focal_length(im["frame"], im["resolution"]) or read_focal_length(im["globals"], im["resolution"])
+        if fl is None:
+            raise ValueError("Couldn't read fov.")
+        im["focal_length"] = fl
     return ds
 
 
-def read_image_linear_rgba(path: Path, white_transparent=False, black_transparent=False) -> np.ndarray:
-    """decode to [H, W, 4] float32, linear colour, straight alpha (load_stbi + the Byte branch of read_rgba, common_device.cuh:698-735)"""
+def image_size(path: Path):
+    """(width, height) from the file header"""
     from PIL import Image
 
+    if Path(path).suffix.lower() == ".exr":
+        raise ValueError("EXR images are not supported")
+    with Image.open(path) as im:
+        return im.size
+
+
+def read_image_bytes_rgba(path: Path, white_transparent=False, black_transparent=False) -> np.ndarray:
+    """[H, W, 4] uint8, sRGB colour + straight alpha: the Byte image as the reference stores it — load_stbi(..., 4), the optional
+    `<name>.alpha.<ext>` companion (nerf_loader.cu:581-599) and convert_rgba32's white / black -> transparent (:41-63)"""
+    from PIL import Image
+
+    path = Path(path)
     if path.suffix.lower() == ".exr":
         raise ValueError("EXR images are not supported")
-    img = np.asarray(Image.open(path).convert("RGBA"), dtype=np.uint8)
+    img = np.array(Image.open(path).convert("RGBA"), dtype=np.uint8)
     alpha_path = Path(f"{path.with_suffix('')}.alpha{path.suffix}")
     if alpha_path.exists():
-        a = np.asarray(Image.open(alpha_path).convert("RGBA"), dtype=np.uint8)[..., 0].astype(np.float32) / 255.0
-        img = img.copy()
-        img[..., 3] = (255.0 * np.where(a <= 0.04045, a / 12.92, ((a + 0.055) / 1.055) ** 2.4)).astype(np.uint8)
+        a = np.asarray(Image.open(alpha_path).convert("RGBA"), dtype=np.uint8)
+        if a.shape != img.shape:
+            raise ValueError(f"Alpha image {alpha_path} has wrong resolution.")
+        r = a[..., 0].astype(np.float32) * np.float32(1.0 / 255.0)
+        lin = np.where(r <= np.float32(0.04045), r / np.float32(12.92), np.power((r + np.float32(0.055)) / np.float32(1.055), np.float32(2.4)))
+        img[..., 3] = (np.float32(255.0) * lin.astype(np.float32)).astype(np.uint8)
+    if white_transparent:
+        img[(img[..., :3] == 255).all(axis=-1), 3] = 0
+    if black_transparent:
+        img[(img[..., :3] == 0).all(axis=-1), 3] = 0
+    return img
+
+
+def read_image_linear_rgba(path: Path, white_transparent=False, black_transparent=False) -> np.ndarray:
+    """decode to [H, W, 4] float32, linear colour, straight alpha (the Byte branch of read_rgba, common_device.cuh:698-735)"""
+    img = read_image_bytes_rgba(path, white_transparent, black_transparent)
     s = img[..., :3].astype(np.float32) / 255.0
     out = np.empty(img.shape, dtype=np.float32)
     out[..., :3] = np.where(s <= 0.04045, s / 12.92, ((s + 0.055) / 1.055) ** 2.4)
     out[..., 3] = img[..., 3].astype(np.float32) / 255.0
-    if white_transparent:
-        out[(img[..., :3] == 255).all(axis=-1), 3] = 0.0
-    if black_transparent:
-        out[(img[..., :3] == 0).all(axis=-1), 3] = 0.0
     return out
 
 
@@ -212,13 +262,7 @@ def load_into_testbed(tb, path) -> dict:
         tb._set(f"nerf.training.dataset.offset.{ax}", ds["offset"][k])
     for i, im in enumerate(ds["images"]):
         rgba = read_image_linear_rgba(im["path"], ds["white_transparent"], ds["black_transparent"])
-        h, w = rgba.shape[:2]
-        fl = read_focal_length(im["globals"], (w, h))
-        fl_frame = read_focal_length(im["frame"], (w, h))
-        fl = fl_frame or fl
-        if fl is None:
-            raise ValueError("Couldn't read fov.")
-        im["focal_length"], im["resolution"] = fl, (w, h)
+        fl = im["focal_length"]
         tb.nerf.training.set_image(i, rgba)
         tb.nerf.training.set_camera_extrinsics(i, im["xform"], convert_to_ngp=False)
         lens = im["lens"]
