@@ -398,6 +398,10 @@ int ngp_testbed_set_camera_intrinsics(ngp_testbed* t, uint32_t idx, float fx, fl
 int ngp_testbed_reload_network_from_json(ngp_testbed* t, const char* json_text);
 int ngp_testbed_reload_network_from_file(ngp_testbed* t, const char* path);
 int ngp_testbed_set_seed(ngp_testbed* t, uint64_t seed);
+/* Testbed::reset_network(clear_density_grid) (src/testbed.cu:4163-4178; pyngp "reset", python_api.cu:534) */
+int ngp_testbed_reset(ngp_testbed* t, int reset_density_grid);
+/* one training view as held by the Testbed (what set_camera_to_training_view reads, src/testbed.cu:486-505) */
+int ngp_testbed_get_view(ngp_testbed* t, uint32_t idx, ngp_train_view* out);
 int ngp_testbed_set_option(ngp_testbed* t, const char* name, double value); /* nerf.training.* knobs by name */
 double ngp_testbed_get_option(ngp_testbed* t, const char* name);
 /* Testbed::train(batch_size): density-grid prep on the reference's schedule, one training step, optimizer step. */

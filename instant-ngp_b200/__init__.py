@@ -28,9 +28,10 @@ from .pyngp import (  # noqa: F401
     FieldTestbed,
     LossType,
     NerfActivation,
+    RenderMode,
     Testbed,
     TestbedMode,
     TrainMode,
 )
 
-__all__ = ["Testbed", "TestbedMode", "LossType", "NerfActivation", "ColorSpace", "lib", "load_library", "NgpError"]
+__all__ = ["Testbed", "TestbedMode", "LossType", "NerfActivation", "ColorSpace", "RenderMode", "TrainMode", "FieldTestbed", "lib", "load_library", "NgpError"]

@@ -194,6 +194,8 @@ PROTOTYPES = {
     "ngp_testbed_reload_network_from_json": (C.c_int, [vp, cp]),
     "ngp_testbed_reload_network_from_file": (C.c_int, [vp, cp]),
     "ngp_testbed_set_seed": (C.c_int, [vp, u64]),
+    "ngp_testbed_reset": (C.c_int, [vp, C.c_int]),
+    "ngp_testbed_get_view": (C.c_int, [vp, u32, P(TrainView)]),
     "ngp_testbed_set_option": (C.c_int, [vp, cp, C.c_double]),
     "ngp_testbed_get_option": (C.c_double, [vp, cp]),
     "ngp_testbed_train": (C.c_int, [vp, u32]),

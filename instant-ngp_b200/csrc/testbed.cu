@@ -193,6 +193,7 @@ struct ngp_testbed {
 
 	// network
 	float background_alpha = 1.0f;    // m_background_color.a (testbed.h:1031): used by the render epilogue only
+	float exposure = 0.0f;            // m_exposure (testbed.h:1030): stops, applied by the render epilogue's tonemap
 	uint32_t render_spp_index = 0;    // sample index of the next render (jitters each ray's first step, advance_pos_nerf)
 	bool has_network = false;
 	Json network_config;              // as given to reload_network_from_json/file (m_network_config)
@@ -1032,6 +1033,32 @@ int ngp_testbed_set_seed(ngp_testbed* t, uint64_t seed) {
 	t->seed = seed;
 	return 0;
 }
+// Testbed::reset_network(clear_density_grid) (src/testbed.cu:4163-4178, python_api.cu:534 "reset"): the network of the current
+// config re-initialised from the seed, optimizer and counters cleared; the occupancy grid is kept on request
+int ngp_testbed_reset(ngp_testbed* t, int reset_density_grid) {
+	NGPB_TRY({
+		NGPB_CHECK(t->has_network, "reset: no network");
+		tb_invalidate_prefetch(t);
+		std::vector<float> kept;
+		const size_t n_grid = (size_t)GRID_N_CELLS * (t->cfg.max_cascade + 1);
+		if (!reset_density_grid) {
+			kept.resize(n_grid);
+			NGPB_CUDA_CHECK(cudaStreamSynchronize(t->stream));
+			NGPB_CUDA_CHECK(cudaMemcpy(kept.data(), t->density_grid.p, n_grid * sizeof(float), cudaMemcpyDeviceToHost));
+		}
+		const Json cfg = t->network_config;
+		tb_reset_network(t, cfg);
+		if (!reset_density_grid && ngp_testbed_set_density_grid(t, kept.data(), (uint32_t)n_grid)) throw std::runtime_error(g_last_error);
+	});
+}
+// one training view as the Testbed holds it (TrainingImageMetadata + TrainingXForm.start); `pixels` is a device pointer
+int ngp_testbed_get_view(ngp_testbed* t, uint32_t idx, ngp_train_view* out) {
+	NGPB_TRY({
+		NGPB_CHECK(out != nullptr, "get_view: null output");
+		NGPB_CHECK(idx < t->n_images, "get_view: image index out of range");
+		*out = t->views[idx];
+	});
+}
 int ngp_testbed_set_option(ngp_testbed* t, const char* name_c, double value) {
 	NGPB_TRY({
 		tb_invalidate_prefetch(t);
@@ -1053,6 +1080,7 @@ int ngp_testbed_set_option(ngp_testbed* t, const char* name_c, double value) {
 		else if (n == "background_color.g") c.background_color[1] = (float)value;
 		else if (n == "background_color.b") c.background_color[2] = (float)value;
 		else if (n == "background_color.a") t->background_alpha = (float)value;
+		else if (n == "exposure") t->exposure = (float)value;
 		else if (n == "nerf.training.full_inference") { tb_invalidate_prefetch(t); t->full_inference = value != 0; }
 		else if (n == "nerf.training.lazy_sample_generation") { tb_invalidate_prefetch(t); t->lazy_sample_generation = value != 0; }
 		else if (n == "nerf.training.train_mode") { NGPB_CHECK(value == 0 || value == 1 || value == 2, "train_mode must be Nerf (0), Rfl (1) or RflRelax (2)"); c.train_mode = (uint32_t)value; }
@@ -1092,6 +1120,16 @@ double ngp_testbed_get_option(ngp_testbed* t, const char* name_c) {
 	if (n == "shall_train") return t->shall_train;
 	if (n == "aabb_scale") return t->aabb_scale;
 	if (n == "learning_rate") return t->opt.learning_rate * t->lr_factor;
+	if (n == "exposure") return t->exposure;
+	if (n == "background_color.r") return c.background_color[0];
+	if (n == "background_color.g") return c.background_color[1];
+	if (n == "background_color.b") return c.background_color[2];
+	if (n == "background_color.a") return t->background_alpha;
+	if (n == "nerf.training.dataset.scale") return t->scene_scale;
+	if (n == "nerf.training.dataset.offset.x") return t->scene_offset[0];
+	if (n == "nerf.training.dataset.offset.y") return t->scene_offset[1];
+	if (n == "nerf.training.dataset.offset.z") return t->scene_offset[2];
+	if (n == "nerf.training.dataset.n_images") return t->n_images;
 	set_last_error("unknown option '" + n + "'");
 	return NAN;
 }
@@ -1252,7 +1290,7 @@ int ngp_testbed_render_ex(ngp_testbed* t, int32_t width, int32_t height, const f
 		}
 		t->render_spp_index = saved;
 		ngp_tonemap_cfg tm{};
-		tm.exposure = 0.0f;
+		tm.exposure = t->exposure;
 		for (int k = 0; k < 3; ++k) tm.background_color[k] = t->cfg.background_color[k];
 		tm.background_color[3] = t->background_alpha;
 		tm.color_space = NGP_COLOR_LINEAR;
@@ -1432,7 +1470,7 @@ static Json tb_snapshot_json(ngp_testbed* t, bool include_optimizer_state) {
 		const float bg[4] = {t->cfg.background_color[0], t->cfg.background_color[1], t->cfg.background_color[2], t->background_alpha};
 		snap.obj["background_color"] = jvec(bg, 4);
 	}
-	snap.obj["exposure"] = jnum(0.0);
+	snap.obj["exposure"] = jnum(t->exposure);
 	cfg.obj["snapshot"] = snap;
 	return cfg;
 }
@@ -1542,6 +1580,12 @@ static void tb_load_snapshot_json(ngp_testbed* t, const Json& config) {
 	t->training_step = (uint32_t)snap.value("training_step", 0.0);
 	if (!snap.contains("optimizer")) t->optimizer_step = t->training_step;
 	t->loss_scalar = (float)snap.value("loss", 0.0);
+	t->exposure = (float)snap.value("exposure", (double)t->exposure);
+	if (snap.contains("background_color") && snap.at("background_color").type == Json::Array && snap.at("background_color").arr.size() == 4) {
+		const Json& bg = snap.at("background_color");
+		for (int k = 0; k < 3; ++k) t->cfg.background_color[k] = (float)bg.arr[k].num;
+		t->background_alpha = (float)bg.arr[3].num;
+	}
 	// the occupancy grid of a trained model is past its warm-up phase
 	t->density_grid_ema_step = t->training_step / 16 + (t->training_step < 256 ? t->training_step : 0);
 	NGPB_CUDA_CHECK(cudaStreamSynchronize(t->stream));

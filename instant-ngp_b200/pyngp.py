@@ -3,7 +3,9 @@
 Mirrors src/python_api.cu:439-853 name for name where the hot path needs it: ``create_empty_nerf_dataset``,
 ``nerf.training.set_image / set_camera_extrinsics / set_camera_intrinsics / n_images_for_training``,
 ``reload_network_from_file / _from_json``, ``train``, ``render``, ``loss``, ``training_step``, ``n_params``,
-``save_snapshot / load_snapshot``.  Everything heavy happens inside the shared library.
+``save_snapshot / load_snapshot``, and the camera a script sets before ``render(width, height, spp, linear)`` (``fov``,
+``fov_axis``, ``set_nerf_camera_matrix``, ``set_camera_to_training_view``, ``screen_center``, ``zoom``, ``exposure``), ``reset``,
+``load_file``.  Everything heavy happens inside the shared library; the camera state is host arithmetic (camera.py).
 """
 from __future__ import annotations
 
@@ -15,6 +17,7 @@ from pathlib import Path
 import numpy as np
 
 from . import binding as B
+from .camera import CameraState
 
 
 class TestbedMode(enum.IntEnum):
@@ -46,6 +49,17 @@ class NerfActivation(enum.IntEnum):  # ENerfActivation
     ReLU = 1
     Logistic = 2
     Exponential = 3
+
+
+class RenderMode(enum.IntEnum):  # ERenderMode (common.h): only the shaded image is produced by this build
+    AO = 0
+    Shade = 1
+    Normals = 2
+    Positions = 3
+    Depth = 4
+    Distortion = 5
+    Cost = 6
+    Slice = 7
 
 
 class ColorSpace(enum.IntEnum):
@@ -215,6 +229,7 @@ class FieldTestbed:
             a = np.concatenate([a, np.ones(a.shape[:2] + (1,), np.float32)], axis=2)
         a = np.ascontiguousarray(a)
         B.check(B.lib().ngp_field_testbed_set_image(self._h, a.ctypes.data_as(C.c_void_p), a.shape[1], a.shape[0]))
+        self._image = a
 
     def override_sdf_training_data(self, points: np.ndarray, distances: np.ndarray) -> None:
         """python_api.cu:74-113.  Points are taken as unit-cube coordinates (no mesh is loaded, so there is no raw AABB to
@@ -286,6 +301,26 @@ class FieldTestbed:
         B.check(B.lib().ngp_field_testbed_evaluate(self._h, p.ctypes.data_as(C.c_void_p), p.shape[0], out.ctypes.data_as(C.c_void_p)))
         return out
 
+    def compute_image_mse(self, quantize: bool = False) -> float:
+        """python_api.cu:659 / src/testbed_image.cu:490-560: the network (inference weights) at every pixel centre against the image
+        itself — snapped read, sRGB-encoded unless `image.training.linear_colors` — mean of |diff|^2 / 3; `quantize` rounds the
+        prediction to 8 bits first.  The reduction runs on the host in float64 (the reference sums floats on the device)."""
+        img = getattr(self, "_image", None)
+        if self.mode != TestbedMode.Image or img is None:
+            raise B.NgpError("compute_image_mse: image mode with an image set")
+        h, w = img.shape[:2]
+        xs = (np.arange(w, dtype=np.float32) + np.float32(0.5)) / np.float32(w)
+        ys = (np.arange(h, dtype=np.float32) + np.float32(0.5)) / np.float32(h)
+        pos = np.stack(np.meshgrid(xs, ys, indexing="xy"), axis=-1).reshape(-1, 2)
+        pred = self.evaluate(pos)[:, :3].astype(np.float32)
+        target = img[..., :3].reshape(-1, 3).astype(np.float32)
+        if not self.image.training.linear_colors:
+            target = np.where(target < 0.0031308, 12.92 * target, 1.055 * np.power(np.maximum(target, 0.0), 0.41666) - 0.055).astype(np.float32)
+        if quantize:
+            pred = np.clip((pred * np.float32(255.0) + np.float32(0.5)).astype(np.int32), 0, 255).astype(np.float32) / np.float32(255.0)
+        d = (target - pred).astype(np.float64)
+        return float(np.mean(np.sum(d * d, axis=1) / 3.0))
+
     def render(self, width: int, height: int, spp: int = 1, linear: bool = True) -> np.ndarray:
         """Image mode: the learned image at every pixel centre, float32 [H, W, 4] (render_image, default full-frame view)."""
         out = np.empty((height, width, 4), dtype=np.float32)
@@ -315,6 +350,8 @@ class Testbed:
         self.nerf = _Nerf(self)
         self.training_batch_size = 1 << 18
         self.root_dir = ""
+        self.jit_fusion = True        # accepted for script compatibility: every kernel here is the fused form
+        self._camera = CameraState()
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
@@ -348,9 +385,113 @@ class Testbed:
     def color_space(self, v) -> None:
         self._set("color_space", float(int(v)))
 
+    exposure = _opt_property("exposure", float)
+
+    @property
+    def snap_to_pixel_centers(self) -> bool:
+        """render rays go through pixel centres (what scripts/run.py sets for screenshots); the jittered form is not built"""
+        return True
+
+    @snap_to_pixel_centers.setter
+    def snap_to_pixel_centers(self, v) -> None:
+        if not v:
+            raise B.NgpError("render: only snap_to_pixel_centers = True is implemented")
+
+    @property
+    def render_mode(self) -> RenderMode:
+        return RenderMode.Shade
+
+    @render_mode.setter
+    def render_mode(self, v) -> None:
+        if RenderMode(int(v)) != RenderMode.Shade:
+            raise B.NgpError("render_mode: only Shade is implemented")
+
+    # -- camera (src/testbed.cu:440, 486-528, 4081-4087, 4649-4657) -------------------------------------------------------
+    @property
+    def fov(self) -> float:
+        return self._camera.fov()
+
+    @fov.setter
+    def fov(self, degrees: float) -> None:
+        self._camera.set_fov(float(degrees))
+
+    @property
+    def fov_xy(self):
+        return self._camera.fov_xy()
+
+    @fov_xy.setter
+    def fov_xy(self, degrees_xy) -> None:
+        self._camera.set_fov_xy(degrees_xy)
+
+    @property
+    def fov_axis(self) -> int:
+        return self._camera.fov_axis
+
+    @fov_axis.setter
+    def fov_axis(self, axis: int) -> None:
+        if int(axis) not in (0, 1):
+            raise ValueError("fov_axis must be 0 or 1")
+        self._camera.fov_axis = int(axis)
+
+    @property
+    def relative_focal_length(self):
+        return self._camera.relative_focal_length
+
+    @relative_focal_length.setter
+    def relative_focal_length(self, v) -> None:
+        self._camera.relative_focal_length = (float(v[0]), float(v[1]))
+
+    @property
+    def screen_center(self):
+        return self._camera.screen_center
+
+    @screen_center.setter
+    def screen_center(self, v) -> None:
+        self._camera.screen_center = (float(v[0]), float(v[1]))
+
+    @property
+    def zoom(self) -> float:
+        return self._camera.zoom
+
+    @zoom.setter
+    def zoom(self, v: float) -> None:
+        self._camera.zoom = float(v)
+
+    @property
+    def camera_matrix(self) -> np.ndarray:
+        """3x4 camera-to-world in ngp convention (m_camera)"""
+        return self._camera.matrix.copy()
+
+    @camera_matrix.setter
+    def camera_matrix(self, m) -> None:
+        self._camera.matrix = np.ascontiguousarray(np.asarray(m, dtype=np.float32)[:3, :4]).copy()
+
+    def reset_camera(self) -> None:
+        self._camera.reset()
+
+    def set_nerf_camera_matrix(self, cam) -> None:
+        """python_api.cu:653: a camera-to-world matrix in the original NeRF convention, through the dataset's scale / offset"""
+        from .nerf_loader import nerf_matrix_to_ngp
+
+        off = [self._get(f"nerf.training.dataset.offset.{ax}") for ax in "xyz"]
+        self._camera.matrix = nerf_matrix_to_ngp(np.asarray(cam, dtype=np.float32), self._get("nerf.training.dataset.scale"), off)
+
+    def training_view(self, idx: int) -> dict:
+        """intrinsics and transform of one training view as the Testbed holds them"""
+        v = B.TrainView()
+        B.check(B.lib().ngp_testbed_get_view(self._h, int(idx), C.byref(v)))
+        xform = np.array(list(v.xform), dtype=np.float32).reshape(4, 3).T.copy()     # stored column major [c * 3 + r]
+        return dict(resolution=(v.width, v.height), focal_length=(v.focal_x, v.focal_y), principal_point=(v.principal_x, v.principal_y),
+                    lens_mode=int(v.lens_mode), lens_params=[float(x) for x in v.lens_params], xform=xform)
+
+    def set_camera_to_training_view(self, trainview: int) -> None:
+        """python_api.cu:654 / src/testbed.cu:486-505.  The render here is a pinhole: a view's lens distortion is not applied."""
+        v = self.training_view(trainview)
+        self._camera.to_training_view(v["xform"], v["focal_length"], v["resolution"], v["principal_point"])
+
     @property
     def background_color(self):
-        raise AttributeError("write-only here")
+        return [self._get(f"background_color.{k}") for k in "rgba"]
 
     @background_color.setter
     def background_color(self, rgba) -> None:
@@ -382,6 +523,40 @@ class Testbed:
 
     def set_seed(self, seed: int) -> None:
         B.check(B.lib().ngp_testbed_set_seed(self._h, seed))
+
+    def reset(self, reset_density_grid: bool = True) -> None:
+        """python_api.cu:534 — Testbed::reset_network: parameters re-initialised from the seed, optimizer / counters / step cleared"""
+        B.check(B.lib().ngp_testbed_reset(self._h, int(reset_density_grid)))
+
+    def find_network_config(self, path) -> Path:
+        """src/testbed.cu:254-270: as given, else <root_dir>/configs/nerf/<path>"""
+        p = Path(path)
+        if p.exists() or p.is_absolute():
+            return p
+        cand = Path(self.root_dir) / "configs" / "nerf" / p
+        return cand if cand.exists() else p
+
+    def load_file(self, path) -> None:
+        """python_api.cu:573 / src/testbed.cu:353-410: snapshot, network config or training data, told apart like the reference does"""
+        p = Path(path)
+        if not p.exists():
+            if p.suffix.lower() == ".json" and self.find_network_config(p).exists():
+                return self.reload_network_from_file(self.find_network_config(p))
+            raise B.NgpError(f"File '{p}' does not exist.")
+        if p.suffix.lower() in (".ingp", ".msgpack", ".ngpb"):
+            return self.load_snapshot(p)
+        if p.suffix.lower() == ".json":
+            from .nerf_loader import _strip_json_comments
+
+            doc = json.loads(_strip_json_comments(p.read_text()))
+            if "snapshot" in doc:
+                raise B.NgpError("snapshots in JSON text are not supported: use .ingp / .msgpack")
+            if any(k in doc for k in ("parent", "network", "encoding", "loss", "optimizer")):
+                return self.reload_network_from_file(p)
+            if "path" in doc:
+                raise B.NgpError("camera paths are not implemented")
+        self.load_training_data(p)
+        self.shall_train = True
 
     @property
     def n_params(self) -> int:
@@ -461,8 +636,35 @@ class Testbed:
         B.check(B.lib().ngp_testbed_set_density_grid(self._h, g.ctypes.data, g.size))
 
     # -- render ----------------------------------------------------------------------------------------------------
-    def render(self, width: int, height: int, camera_matrix: np.ndarray, focal_length, screen_center=(0.5, 0.5), spp: int = 1, linear: bool = True,
-               rows=None, return_depth: bool = False):
+    def render(self, width: int = 1920, height: int = 1080, *args, **kw):
+        """Two call forms.  ``render(width, height, spp=1, linear=True)`` is the reference's (python_api.cu:507-519): the frame of the
+        Testbed's own camera (``set_nerf_camera_matrix`` / ``set_camera_to_training_view`` / ``camera_matrix``, ``fov``, ``zoom``,
+        ``screen_center``).  ``render(width, height, camera_matrix, focal_length, screen_center=(0.5, 0.5), spp=1, linear=True,
+        rows=None, return_depth=False)`` takes the camera explicitly (ngp convention, focal length in pixels).  Both return
+        float32 [H, W, 4] premultiplied RGBA, linear — or sRGB after exposure / tonemap for ``linear=False``."""
+        explicit = "camera_matrix" in kw or (len(args) >= 1 and not isinstance(args[0], (int, np.integer, bool)))
+        if explicit:
+            return self._render_explicit(width, height, *args, **kw)
+        names = ("spp", "linear", "start_t", "end_t", "fps", "shutter_fraction")
+        opts = dict(zip(names, args))
+        for k, v in kw.items():
+            if k in opts:
+                raise TypeError(f"render() got multiple values for argument '{k}'")
+            if k not in names + ("return_depth",):
+                raise TypeError(f"render() got an unexpected keyword argument '{k}'")
+            opts[k] = v
+        if opts.get("start_t", -1.0) >= 0 or opts.get("end_t", -1.0) >= 0:
+            raise B.NgpError("render: camera paths (start_t / end_t) are not implemented")
+        cam, focal, center = self._camera.render_args(width, height)
+        return self._render_explicit(width, height, cam, focal, center, spp=int(opts.get("spp", 1)), linear=bool(opts.get("linear", True)),
+                                     return_depth=bool(opts.get("return_depth", False)))
+
+    def render_with_depth(self, width: int = 1920, height: int = 1080, spp: int = 1, linear: bool = True):
+        """python_api.cu:520-532: (rgba, depth)"""
+        return self.render(width, height, spp, linear, return_depth=True)
+
+    def _render_explicit(self, width: int, height: int, camera_matrix: np.ndarray, focal_length, screen_center=(0.5, 0.5), spp: int = 1,
+                         linear: bool = True, rows=None, return_depth: bool = False):
         """≙ Testbed.render(width, height, spp, linear) with an explicit ngp-convention 3x4 camera-to-world matrix
         (the reference takes it from testbed.set_nerf_camera_matrix).  Returns float32 [H, W, 4] linear premultiplied RGBA."""
         cam = np.ascontiguousarray(np.asarray(camera_matrix, dtype=np.float32)[:3, :4])

@@ -271,6 +271,14 @@ def test_image_testbed_learns_the_image(lib):
     psnr = -10 * np.log10(mse)
     print("image psnr", psnr)
     assert psnr > 30.0 and np.all(out[..., 3] == 1.0)
+    # compute_image_mse (python_api.cu:659, src/testbed_image.cu:490-560): same pixels, linear targets -> the MSE above
+    got = tb.compute_image_mse()
+    assert abs(got - mse) <= 1e-3 * mse + 1e-9, (got, mse)
+    q = tb.compute_image_mse(quantize=True)
+    assert abs(q - mse) < 0.2 * mse + 1e-5       # 8-bit rounding of the prediction: a small change, not a different number
+    tb.image.training.linear_colors = False       # targets sRGB-encoded: a network trained on linear values is now far off
+    assert tb.compute_image_mse() > 2.0 * mse
+    tb.image.training.linear_colors = True
 
 
 def test_sdf_testbed_learns_a_sphere(lib):

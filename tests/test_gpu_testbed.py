@@ -97,6 +97,91 @@ def test_render_spp_and_srgb_epilogue(trained):
     assert np.allclose(opaque[..., 3], 1.0, atol=1e-6) and np.array_equal(opaque[..., :3], srgb[..., :3])
 
 
+def test_reference_shaped_camera_api(trained):
+    """render(width, height, spp, linear) from the Testbed's own camera: set_camera_to_training_view / set_nerf_camera_matrix /
+    fov / zoom / screen_center (python_api.cu:507-519, 653-654; src/testbed.cu:440, 486-505, 4081-4087, 4649-4657)"""
+    import math
+    import sys
+
+    sys.path.insert(0, str(Path(__file__).resolve().parent))
+    import loader_scenes
+
+    tb, imgs, cams, focal, _, _ = trained
+    P = util.pkg()
+    h, w = imgs.shape[1:3]
+    v = tb.training_view(5)
+    assert v["resolution"] == (w, h) and np.allclose(v["xform"], np.asarray(cams[5])[:3, :4], atol=1e-6)
+    assert abs(v["focal_length"][0] - focal) < 1e-3 and v["principal_point"] == (0.5, 0.5)
+    tb.set_camera_to_training_view(5)
+    assert np.array_equal(tb.render(w, h, 1, True), tb.render(w, h, cams[5], focal))
+    assert np.array_equal(tb.render(w, h), tb.render(w, h, cams[5], focal))
+    # another frame size: the focal length follows the resolution along fov_axis
+    half = tb.render(w // 2, h // 2, spp=1, linear=True)
+    assert np.array_equal(half, tb.render(w // 2, h // 2, cams[5], focal / 2))
+    rgba, depth = tb.render_with_depth(w // 2, h // 2, 1, True)
+    assert np.array_equal(rgba, half) and depth.shape == (h // 2, w // 2) and np.isfinite(depth).all()
+    # fov in degrees along fov_axis
+    tb.fov = 40.0
+    assert abs(tb.fov - 40.0) < 1e-4 and tb.fov_axis == 1
+    assert np.array_equal(tb.render(64, 64), tb.render(64, 64, cams[5], 0.5 * 64 / math.tan(math.radians(20.0))))
+    tb.zoom = 2.0
+    assert np.array_equal(tb.render(64, 64), tb.render(64, 64, cams[5], 64 / math.tan(math.radians(20.0))))
+    tb.zoom = 1.0
+    # a camera in the original NeRF convention goes through the dataset's scale / offset
+    tb.set_nerf_camera_matrix(loader_scenes.ngp_to_nerf(cams[3]))
+    assert np.allclose(tb.camera_matrix, np.asarray(cams[3])[:3, :4], atol=1e-5)
+    # exposure (stops) acts in the sRGB epilogue only
+    tb.set_camera_to_training_view(4)
+    lin = tb.render(64, 64, 1, True)
+    base = tb.render(64, 64, 1, False)
+    tb.exposure = 1.0
+    assert tb.exposure == 1.0 and np.array_equal(tb.render(64, 64, 1, True), lin)
+    brighter = tb.render(64, 64, 1, False)
+    tb.exposure = 0.0
+    lit = lin[..., :3].max(axis=-1) > 0.05
+    assert lit.any() and (brighter[..., :3][lit] >= base[..., :3][lit]).all() and brighter[..., :3][lit].mean() > 1.2 * base[..., :3][lit].mean()
+    assert tb.render_mode == P.RenderMode.Shade and tb.snap_to_pixel_centers and tb.jit_fusion
+    with pytest.raises(P.NgpError):
+        tb.render_mode = P.RenderMode.Depth
+    with pytest.raises(P.NgpError):
+        tb.render(64, 64, 1, True, 0.0, 1.0)     # camera paths
+
+
+def test_reset_and_load_file(tmp_path):
+    """Testbed.reset (python_api.cu:534) and load_file (python_api.cu:573, src/testbed.cu:353-410)"""
+    import json
+
+    P = util.pkg()
+    tb = P.Testbed()
+    imgs, cams, focal = S.make_dataset(n_images=8, width=64, height=64)
+    S.load_into_testbed(tb, imgs, cams, focal, aabb_scale=1)
+    cfg_path = tmp_path / "tiny.json"
+    cfg_path.write_text(json.dumps(S.base_config(16, 2, 14)))
+    tb.load_file(cfg_path)                      # has "encoding" / "network": a network config
+    n = tb.n_params
+    assert n > 0 and tb.training_step == 0
+    w0 = tb.get_params()
+    for _ in range(20):
+        tb.train(1 << 14)
+    grid_before, _ = tb.get_density_grid()
+    assert tb.training_step == 20 and not np.array_equal(tb.get_params(), w0) and grid_before.max() > 0
+    tb.reset(reset_density_grid=False)
+    grid_kept, _ = tb.get_density_grid()
+    assert tb.training_step == 0 and np.array_equal(tb.get_params(), w0) and np.array_equal(grid_kept, grid_before)
+    tb.reset()
+    grid_cleared, _ = tb.get_density_grid()
+    assert np.array_equal(tb.get_params(), w0) and grid_cleared.max() == 0
+    for _ in range(3):
+        tb.train(1 << 14)
+    snap = tmp_path / "m.ingp"
+    tb.save_snapshot(str(snap))
+    tb2 = P.Testbed()
+    tb2.load_file(snap)                         # by extension: a snapshot
+    assert tb2.training_step == 3 and tb2.n_params == n
+    with pytest.raises(P.NgpError, match="does not exist"):
+        tb2.load_file(tmp_path / "nothing.ingp")
+
+
 def test_snapshot_round_trip(trained, tmp_path):
     tb, imgs, cams, focal, _, _ = trained
     P = util.pkg()
