@@ -106,6 +106,10 @@ def build_reference(verbose: bool = False) -> bool:
         targets.append("host")
     if (ROOT / "oracle" / "ref" / "ref_snapshot_harness.cu").exists():
         targets.append("snapshot")
+    if (ROOT / "oracle" / "ref" / "ref_loader_harness.cu").exists():
+        targets.append("loader")
+    if (ROOT / "oracle" / "ref" / "ref_exr_harness.cpp").exists():
+        targets.append("exr")
     r = subprocess.run(["make", "-C", str(ROOT / "oracle" / "ref"), "-j8", *targets], capture_output=not verbose, text=True)
     if r.returncode != 0:
         raise RuntimeError("building oracle/_ref failed:\n" + (r.stdout or "") + (r.stderr or ""))

@@ -231,6 +231,26 @@ class FieldTestbed:
         B.check(B.lib().ngp_field_testbed_set_image(self._h, a.ctypes.data_as(C.c_void_p), a.shape[1], a.shape[0]))
         self._image = a
 
+    def load_training_data(self, path) -> None:
+        """python_api.cu:452 for the image mode — Testbed::load_image (src/testbed_image.cu:393-437): .exr, .bin or an 8-bit image"""
+        if self.mode != TestbedMode.Image:
+            raise B.NgpError("load_training_data: the SDF mode trains on override_sdf_training_data (no mesh loader in this build)")
+        from . import image_io
+
+        try:
+            img = image_io.load_image(path)
+        except (OSError, ValueError) as e:
+            raise B.NgpError(str(e)) from e
+        self.set_image(img)
+        self.data_path = str(path)
+
+    def load_file(self, path) -> None:
+        """python_api.cu:573: a network config (.json with network / encoding / loss / optimizer keys) or the training image"""
+        p = Path(path)
+        if p.suffix.lower() == ".json":
+            return self.reload_network_from_file(p)
+        self.load_training_data(p)
+
     def override_sdf_training_data(self, points: np.ndarray, distances: np.ndarray) -> None:
         """python_api.cu:74-113.  Points are taken as unit-cube coordinates (no mesh is loaded, so there is no raw AABB to
         normalise by)."""

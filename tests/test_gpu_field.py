@@ -1,6 +1,7 @@
 """GPU parity: the image / SDF primitive (NetworkWithInputEncoding: hash grid over 2-D / 3-D positions + one fused MLP, tcnn
 losses, train_image's data generation) against the CPU oracle, through the C-ABI."""
 import ctypes as C
+import importlib
 import json
 
 import numpy as np
@@ -279,6 +280,37 @@ def test_image_testbed_learns_the_image(lib):
     tb.image.training.linear_colors = False       # targets sRGB-encoded: a network trained on linear values is now far off
     assert tb.compute_image_mse() > 2.0 * mse
     tb.image.training.linear_colors = True
+
+
+def test_image_testbed_loads_files(lib, tmp_path):
+    """Testbed::load_image (src/testbed_image.cu:393-437): an EXR written by the reference's codec (tests/golden/exr, tinyexr) and a PNG"""
+    from pathlib import Path
+
+    from PIL import Image
+
+    ngp = util.pkg()
+    IO = importlib.import_module("instant-ngp_b200.image_io")
+    exr = Path(__file__).resolve().parent / "golden" / "exr" / "rgba_half_zip_64.exr"
+    tb = ngp.Testbed(ngp.TestbedMode.Image)
+    tb.load_training_data(exr)
+    tb.image.training.linear_colors = True
+    cfg = json.loads(json.dumps(IMAGE_CONFIG))
+    cfg["encoding"]["log2_hashmap_size"] = 15
+    cfg_path = tmp_path / "image.json"
+    cfg_path.write_text(json.dumps(cfg))
+    tb.load_file(cfg_path)
+    want = IO.read_exr(exr)
+    for _ in range(200):
+        tb.train(1 << 14)
+    out = tb.render(64, 64)
+    assert float(np.mean((out[..., :3] - want[..., :3]) ** 2)) < 0.1 * float(np.mean(want[..., :3] ** 2))   # it is learning THIS image
+    px = (util.test_image(48, 32, seed=9) * 255 + 0.5).astype(np.uint8)
+    Image.fromarray(px, "RGBA").save(tmp_path / "img.png")
+    tb2 = ngp.Testbed(ngp.TestbedMode.Image)
+    tb2.load_file(tmp_path / "img.png")
+    assert np.array_equal(tb2._image, IO.rgba32_to_linear_premultiplied(px))
+    with pytest.raises(ngp.NgpError, match="does not exist"):
+        tb2.load_training_data(tmp_path / "nothing.exr")
 
 
 def test_sdf_testbed_learns_a_sphere(lib):
