@@ -1305,9 +1305,8 @@ int ngp_testbed_render_ex(ngp_testbed* t, int32_t width, int32_t height, const f
 	});
 }
 
-// Snapshot: the payload of Testbed::save_snapshot (src/testbed.cu:5288-5355) — training step, counters, fp32 master +
-// EMA params, optimizer moments, density grid — in a flat little-endian container (".ngpb").  The reference's
-// msgpack/zlib .ingp container is the next row of SURVEY §8f and is not read or written yet.
+// ".ngpb": a flat little-endian dump of the full training state (fp32 masters, EMA params, optimizer moments, RNG streams, density
+// grid) for exact resume.  The reference's own container (.ingp / .msgpack) follows below.
 struct SnapshotHeader {
 	char magic[8];
 	uint32_t version, n_params, n_grid, training_step, optimizer_step, rays_per_batch, measured_batch_size, measured_before, ema_step, aabb_scale;
