@@ -110,6 +110,8 @@ def build_reference(verbose: bool = False) -> bool:
         targets.append("loader")
     if (ROOT / "oracle" / "ref" / "ref_exr_harness.cpp").exists():
         targets.append("exr")
+    if (ROOT / "oracle" / "ref" / "ref_nerf_harness.cu").exists():
+        targets.append("nerf")
     r = subprocess.run(["make", "-C", str(ROOT / "oracle" / "ref"), "-j8", *targets], capture_output=not verbose, text=True)
     if r.returncode != 0:
         raise RuntimeError("building oracle/_ref failed:\n" + (r.stdout or "") + (r.stderr or ""))

@@ -1,0 +1,189 @@
+"""CPU: the C oracle's NeRF sample generation, loss / compaction and density-grid upkeep against the REFERENCE's own kernels.
+
+tests/golden/ref_nerf_<case>.npz hold what generate_training_samples_nerf, compute_loss_kernel_train_nerf, mark_untrained_density_grid,
+generate_grid_samples_nerf_nonuniform, splat_grid_samples_nerf_max_nearest_neighbor, ema_grid_samples_nerf, grid_to_bitfield and
+bitfield_max_pool (src/testbed_nerf.cu) produced on a B200 for the seeded cases of tools/ref_nerf_cases.py — the kernels themselves,
+compiled from /root/reference by oracle/ref/Makefile (`nerf` target, oracle/ref/ref_nerf_harness.cu) with the reference's own flags.
+
+The reference is built with --use_fast_math and FMA contraction (CMakeLists.txt:88); the oracle and this library's CUDA march use
+include/ngp_detmath.h without contraction so that THEY agree bit for bit.  Against the reference the bar is therefore: integer work
+(hash indices, bitfield, counters given equal inputs) exact; floating point within the tolerances written below; the few rays whose
+step count changes because a sample sits within an ulp of a voxel face or of the T < 1e-4 cut are counted and bounded."""
+import ctypes as C
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT / "tools"))
+import ref_nerf_cases as RC  # noqa: E402
+from oracle import march_oracle as M  # noqa: E402
+
+GOLD = Path(__file__).resolve().parent / "golden"
+
+
+def golden(name):
+    p = GOLD / f"ref_nerf_{name}.npz"
+    if not p.exists():
+        pytest.skip(f"{p.name} not generated yet (tools/make_ref_nerf_golden.sh on a GPU box)")
+    return np.load(p)
+
+
+@pytest.mark.parametrize("name", list(RC.TRAIN_CASES))
+def test_sample_generation_matches_the_reference_kernel(name):
+    c = RC.build_case(name)
+    n_rays = c["n_rays"]
+    want = M.generate_training_samples(n_rays, 0, n_rays, c["rng"], c["cfg"], c["views"], len(c["views"]), c["bitfield"], RC.MAX_SAMPLES)
+    assert 0 < want["n_samples"] <= RC.MAX_SAMPLES
+    g = golden(name)
+    k_ref, ns_ref = int(g["gen_counters"][0]), int(g["gen_counters"][1])
+    assert ns_ref <= RC.MAX_SAMPLES
+    ref_numsteps = g["numsteps"].reshape(-1, 2)
+    ref_rays = g["rays"].reshape(-1, 6)
+    ref_coords = g["coords"].reshape(-1, 7)
+    rmap = {int(r): j for j, r in enumerate(g["ray_indices"])}
+    wmap = {int(r): j for j, r in enumerate(want["ray_indices"])}
+    assert len(rmap) == k_ref
+    # rays that produce samples: the same set up to rays grazing the occupied region
+    both = set(rmap) & set(wmap)
+    assert len(set(rmap) ^ set(wmap)) <= max(2, 0.003 * k_ref), (len(rmap), len(wmap))
+    same_count, checked = 0, 0
+    max_pos, max_dt, max_dir = 0.0, 0.0, 0.0
+    for rid in sorted(both):
+        rj, wj = rmap[rid], wmap[rid]
+        # the unnormalised ray: identical arithmetic apart from FMA contraction in uv_to_ray / the lens undistortion
+        assert np.allclose(ref_rays[rj], want["rays"][wj], rtol=0, atol=2e-6)
+        rn, rb = ref_numsteps[rj]
+        wn, wb = want["numsteps"][wj]
+        if rn != wn:
+            assert abs(int(rn) - int(wn)) <= max(2, 0.02 * int(rn))   # a sample flipped at a voxel face, not a different march
+            continue
+        same_count += 1
+        if checked < 400:                                              # coordinates of a few hundred rays
+            a, b = ref_coords[rb:rb + rn], want["coords"][wb:wb + wn]
+            max_pos = max(max_pos, float(np.abs(a[:, :3] - b[:, :3]).max()))
+            max_dt = max(max_dt, float((np.abs(a[:, 3] - b[:, 3]) / np.maximum(np.abs(b[:, 3]), 1e-9)).max()))
+            max_dir = max(max_dir, float(np.abs(a[:, 4:] - b[:, 4:]).max()))
+            checked += 1
+    print(f"{name}: {k_ref} rays, {ns_ref} samples (oracle {want['n_samples']}); identical step counts on {same_count}/{len(both)} rays; "
+          f"max |pos| diff {max_pos:.2e}, max rel dt diff {max_dt:.2e}, max |dir| diff {max_dir:.2e}")
+    assert same_count >= 0.985 * len(both)
+    assert abs(ns_ref - want["n_samples"]) <= 0.003 * ns_ref
+    # warped positions live in [0, 1]: 1e-5 is a hundredth of the finest step (sqrt(3)/1024); dt is stored warped as well
+    assert max_pos < 1e-5 and max_dt < 1e-4 and max_dir < 2e-6
+
+
+@pytest.mark.parametrize("name", list(RC.TRAIN_CASES))
+def test_loss_and_compaction_match_the_reference_kernel(name):
+    """the oracle consumes the REFERENCE's samples (its slot assignment included), so the outputs line up ray by ray"""
+    c = RC.build_case(name)
+    g = golden(name)
+    n_rays = c["n_rays"]
+    k = int(g["gen_counters"][0])
+    net_out = c["arrays"]["net_out.bin"]
+    ray_indices = np.ascontiguousarray(g["ray_indices"])
+    rays = np.ascontiguousarray(g["rays"])
+    coords = np.zeros((RC.MAX_SAMPLES, 7), dtype=np.float32)
+    coords[: g["coords"].size // 7] = g["coords"].reshape(-1, 7)
+    cfg = c["cfg"]
+    for v, lv in enumerate(RC.LOSS_VARIANTS):
+        cfg.loss_type, cfg.random_bg_color = lv["loss_type"], lv["random_bg_color"]
+        ns = np.ascontiguousarray(g["numsteps"].reshape(-1, 2).copy())
+        co_w = np.zeros((RC.MAX_SAMPLES, 7), dtype=np.float32)
+        dl_w = np.zeros((RC.MAX_SAMPLES, 4), dtype=np.float16)
+        loss_w = np.zeros(n_rays, dtype=np.float32)
+        total_w = M.lib().orc_compute_loss(k, n_rays, c["rng"][0], c["rng"][1], C.byref(cfg), C.addressof(c["views"]), len(c["views"]), net_out.ctypes.data, RC.MAX_SAMPLES,
+                                           ray_indices.ctypes.data, rays.ctypes.data, ns.ctypes.data, coords.ctypes.data, co_w.ctypes.data, dl_w.ctypes.data,
+                                           loss_w.ctypes.data, np.float32(0.02))
+        total_r = int(g[f"loss{v}_counter"][0])
+        ns_r = g[f"loss{v}_numsteps"].reshape(-1, 2)
+        dl_r = g[f"loss{v}_dloss"].reshape(-1, 4).astype(np.float32)
+        loss_r = g[f"loss{v}_loss"]
+        assert total_r <= RC.MAX_SAMPLES
+        # how many samples each ray keeps (those before T < 1e-4): equal except where T sits within rounding of the threshold
+        same = ns_r[:, 0] == ns[:, 0]
+        assert same.mean() >= 0.99 and abs(total_r - total_w) <= 0.002 * total_r, (same.mean(), total_r, total_w)
+        # per-ray loss: Huber / L2 / L1 / LogL1 of the composited colour against the same target pixel and background
+        lw, lr = loss_w[:k][same].astype(np.float64), loss_r[same].astype(np.float64)
+        assert np.abs(lw - lr).max() <= 2e-4 * max(np.abs(lr).max(), 1e-12), np.abs(lw - lr).max()
+        # gradients, fp16: compare ray by ray through the two slot assignments
+        worst, n_cmp = 0.0, 0
+        for i in np.flatnonzero(same)[:600]:
+            n_i = int(ns[i, 0])
+            if n_i == 0:
+                continue
+            a = dl_r[int(ns_r[i, 1]): int(ns_r[i, 1]) + n_i]
+            b = dl_w[int(ns[i, 1]): int(ns[i, 1]) + n_i].astype(np.float32)
+            scale = max(float(np.abs(a).max()), 1e-6)
+            worst = max(worst, float(np.abs(a - b).max()) / scale)
+            n_cmp += n_i
+        print(f"{name} variant {v} (loss {lv['loss_type']}, random bg {lv['random_bg_color']}): {total_r} compacted samples (oracle {total_w}); "
+              f"{same.mean() * 100:.2f}% rays with equal counts; worst gradient deviation {worst:.2e} of the ray's largest entry over {n_cmp} samples")
+        assert n_cmp > 0 and worst <= 4e-3                       # one fp16 ulp is 1e-3 relative; __expf vs expf adds a little
+        if v == 0:
+            co_r = g["loss0_coords"].reshape(-1, 7)
+            for i in np.flatnonzero(same)[:200]:                 # compacted coordinates are plain copies
+                n_i = int(ns[i, 0])
+                assert np.array_equal(co_r[int(ns_r[i, 1]): int(ns_r[i, 1]) + n_i], co_w[int(ns[i, 1]): int(ns[i, 1]) + n_i])
+
+
+@pytest.mark.parametrize("name", list(RC.GRID_CASES))
+def test_density_grid_upkeep_matches_the_reference_kernels(name):
+    """stage by stage, each oracle stage fed with the reference's output of the stage before (so one flipped cell does not cascade)"""
+    c = RC.build_case(name)
+    cfg = c["cfg"]
+    n_casc = cfg.max_cascade + 1
+    n_el = 128 ** 3 * n_casc
+    # the oracle alone, end to end, always runs (and must be self-consistent) — the comparison needs the golden
+    grid_w = np.zeros(n_el, dtype=np.float32)
+    M.lib().orc_mark_untrained_density_grid(n_el, grid_w.ctypes.data, len(c["views"]), C.addressof(c["views"]), 1)
+    assert set(np.unique(grid_w)) <= {0.0, -1.0}
+    g = golden(name)
+    state = C.c_uint64(c["rng"][0])
+    inc = c["rng"][1]
+    grid_prev = np.zeros(n_el, dtype=np.float32)
+    for k, st in enumerate(RC.GRID_STEPS):
+        n_uni, n_non = st["n_uniform"], st["n_nonuniform"]
+        n_tot = n_uni + n_non
+        if st["mark_untrained"]:
+            marked_r = g[f"grid{k}_marked"]
+            mine = grid_prev.copy()
+            M.lib().orc_mark_untrained_density_grid(n_el, mine.ctypes.data, len(c["views"]), C.addressof(c["views"]), int(st["clear_visible"]))
+            mism = int((mine != marked_r).sum())
+            print(f"{name} step {k}: mark_untrained: {int((marked_r < 0).sum())} culled cells, {mism} cells differ")
+            assert mism <= 2e-5 * n_el                         # corners within rounding of the frustum edge / the 1e-3 ray test
+            grid_in = marked_r
+        else:
+            grid_in = grid_prev
+        pos_w = np.zeros((n_tot, 4), dtype=np.float32)
+        idx_w = np.zeros(n_tot, dtype=np.uint32)
+        M.lib().orc_generate_grid_samples(n_uni, state.value, inc, k, C.byref(cfg), grid_in.ctypes.data, pos_w.ctypes.data, idx_w.ctypes.data, n_casc, -0.01)
+        M.lib().orc_pcg32_advance(C.byref(state), inc, 1 << 32)
+        if n_non:
+            M.lib().orc_generate_grid_samples(n_non, state.value, inc, k, C.byref(cfg), grid_in.ctypes.data, pos_w[n_uni:].ctypes.data, idx_w[n_uni:].ctypes.data, n_casc, 0.01)
+        M.lib().orc_pcg32_advance(C.byref(state), inc, 1 << 32)
+        # cell choice: integer hashing + threshold tests on identical grid values -> exact
+        assert np.array_equal(idx_w, g[f"grid{k}_indices"])
+        pos_r = g[f"grid{k}_positions"].reshape(-1, 3)         # NerfPosition is three floats in the reference build
+        assert np.abs(pos_w[:, :3] - pos_r).max() <= 2.5e-7     # one ulp near 1.0 (FMA contraction in the affine map)
+        net = c["arrays"][f"grid_net_{k}.bin"]
+        tmp_w = np.zeros(n_el, dtype=np.float32)
+        grid_w = grid_in.copy()
+        M.lib().orc_splat_and_ema(n_tot, np.ascontiguousarray(g[f"grid{k}_indices"]).ctypes.data, net.ctypes.data, cfg.density_activation, n_el, 0.95, tmp_w.ctypes.data,
+                                  grid_w.ctypes.data)
+        grid_r = g[f"grid{k}_grid"]
+        assert np.array_equal(grid_w < 0, grid_r < 0)
+        rel = np.abs(grid_w - grid_r) / np.maximum(np.abs(grid_r), 1e-20)
+        assert rel[grid_r > 0].max() <= 2e-6 if (grid_r > 0).any() else True   # exp of the raw density: __expf vs the oracle's expf
+        mean_r = float(g[f"grid{k}_mean"][0])
+        mean_w = float(M.lib().orc_density_mean(np.ascontiguousarray(grid_r).ctypes.data))
+        assert abs(mean_w - mean_r) <= 1e-5 * abs(mean_r) + 1e-12           # summation order
+        bf_w = np.zeros(128 ** 3, dtype=np.uint8)
+        M.lib().orc_update_bitfield(cfg.max_cascade, np.ascontiguousarray(grid_r).ctypes.data, np.float32(mean_r), bf_w.ctypes.data)
+        assert np.array_equal(bf_w, g[f"grid{k}_bitfield"])                  # thresholding + 7 max-pooled mips: bit exact
+        print(f"{name} step {k}: {n_tot} samples, indices and bitfield exact, max |pos| diff {np.abs(pos_w[:, :3] - pos_r).max():.1e}, "
+              f"mean {mean_r:.6g} (oracle {mean_w:.6g})")
+        grid_prev = grid_r.copy()
+    assert state.value == int(g["rng"][0]) and inc == int(g["rng"][1])
