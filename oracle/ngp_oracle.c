@@ -8,7 +8,10 @@
  * Build: gcc -O3 -march=native -ffp-contract=off -fopenmp (FMA contraction must stay off).
  *
  * Pinning status: the stepping / occupancy / camera helpers are validated against the reference's own NGP_HOST_DEVICE
- * functions compiled from /root/reference (oracle/ref/ref_host_harness.cu -> tests/golden/ref_host_*.bin).
+ * functions compiled from /root/reference (oracle/ref/ref_host_harness.cu -> tests/golden/ref_host_*.bin); sample
+ * generation, loss / compaction and the occupancy-grid upkeep against the reference's own kernels run on a B200
+ * (oracle/ref/ref_nerf_harness.cu includes src/testbed_nerf.cu -> tests/golden/ref_nerf_*.npz,
+ * tests/test_oracle_vs_reference_nerf.py).  The render march / composite restatement is not pinned against reference kernels.
  */
 #include <math.h>
 #include <stdint.h>

@@ -10,6 +10,7 @@ include/ngp_detmath.h without contraction so that THEY agree bit for bit.  Again
 (hash indices, bitfield, counters given equal inputs) exact; floating point within the tolerances written below; the few rays whose
 step count changes because a sample sits within an ulp of a voxel face or of the T < 1e-4 cut are counted and bounded."""
 import ctypes as C
+import hashlib
 import sys
 from pathlib import Path
 
@@ -64,15 +65,20 @@ def test_sample_generation_matches_the_reference_kernel(name):
         if checked < 400:                                              # coordinates of a few hundred rays
             a, b = ref_coords[rb:rb + rn], want["coords"][wb:wb + wn]
             max_pos = max(max_pos, float(np.abs(a[:, :3] - b[:, :3]).max()))
-            max_dt = max(max_dt, float((np.abs(a[:, 3] - b[:, 3]) / np.maximum(np.abs(b[:, 3]), 1e-9)).max()))
+            # warped dt lives in [0, 1]; in unit-cube scenes every step is the minimum step, whose warped value is 0 up to rounding
+            max_dt = max(max_dt, float(np.abs(a[:, 3] - b[:, 3]).max()))
             max_dir = max(max_dir, float(np.abs(a[:, 4:] - b[:, 4:]).max()))
             checked += 1
     print(f"{name}: {k_ref} rays, {ns_ref} samples (oracle {want['n_samples']}); identical step counts on {same_count}/{len(both)} rays; "
-          f"max |pos| diff {max_pos:.2e}, max rel dt diff {max_dt:.2e}, max |dir| diff {max_dir:.2e}")
+          f"max |pos| diff {max_pos:.2e}, max |warped dt| diff {max_dt:.2e}, max |dir| diff {max_dir:.2e}")
     assert same_count >= 0.985 * len(both)
     assert abs(ns_ref - want["n_samples"]) <= 0.003 * ns_ref
-    # warped positions live in [0, 1]: 1e-5 is a hundredth of the finest step (sqrt(3)/1024); dt is stored warped as well
-    assert max_pos < 1e-5 and max_dt < 1e-4 and max_dir < 2e-6
+    # Warped positions live in [0, 1].  The reference's t drifts by a few 1e-6 per ray against exact arithmetic: every empty-voxel
+    # skip goes through to_stepping_space's division (nerf_device.cuh:379-395), which --use_fast_math turns into an approximate
+    # reciprocal, so t picks up a relative error of ~1e-7 per skip (measured: 4e-6 at the first sample after ~40 skips, 1e-5 at the
+    # far end); with cone stepping (aabb_scale > 1) the skips go through __logf / __expf instead, to the same effect, and dt = t *
+    # cone_angle inherits t's relative error.  3e-5 is a fiftieth of the finest step (sqrt(3)/1024 = 1.7e-3).
+    assert max_pos < 3e-5 and max_dt < 3e-5 and max_dir < 2e-6
 
 
 @pytest.mark.parametrize("name", list(RC.TRAIN_CASES))
@@ -122,7 +128,7 @@ def test_loss_and_compaction_match_the_reference_kernel(name):
         print(f"{name} variant {v} (loss {lv['loss_type']}, random bg {lv['random_bg_color']}): {total_r} compacted samples (oracle {total_w}); "
               f"{same.mean() * 100:.2f}% rays with equal counts; worst gradient deviation {worst:.2e} of the ray's largest entry over {n_cmp} samples")
         assert n_cmp > 0 and worst <= 4e-3                       # one fp16 ulp is 1e-3 relative; __expf vs expf adds a little
-        if v == 0:
+        if v == 0 and "loss0_coords" in g.files:                 # kept for the smallest case only
             co_r = g["loss0_coords"].reshape(-1, 7)
             for i in np.flatnonzero(same)[:200]:                 # compacted coordinates are plain copies
                 n_i = int(ns[i, 0])
@@ -148,7 +154,11 @@ def test_density_grid_upkeep_matches_the_reference_kernels(name):
         n_uni, n_non = st["n_uniform"], st["n_nonuniform"]
         n_tot = n_uni + n_non
         if st["mark_untrained"]:
-            marked_r = g[f"grid{k}_marked"]
+            if f"grid{k}_marked" in g.files:
+                marked_r = np.ascontiguousarray(g[f"grid{k}_marked"])
+            else:                                              # stored as the difference from the grid of the step before
+                marked_r = grid_prev.copy()
+                marked_r[g[f"grid{k}_marked_changed_idx"]] = g[f"grid{k}_marked_changed_val"]
             mine = grid_prev.copy()
             M.lib().orc_mark_untrained_density_grid(n_el, mine.ctypes.data, len(c["views"]), C.addressof(c["views"]), int(st["clear_visible"]))
             mism = int((mine != marked_r).sum())
@@ -164,26 +174,27 @@ def test_density_grid_upkeep_matches_the_reference_kernels(name):
         if n_non:
             M.lib().orc_generate_grid_samples(n_non, state.value, inc, k, C.byref(cfg), grid_in.ctypes.data, pos_w[n_uni:].ctypes.data, idx_w[n_uni:].ctypes.data, n_casc, 0.01)
         M.lib().orc_pcg32_advance(C.byref(state), inc, 1 << 32)
-        # cell choice: integer hashing + threshold tests on identical grid values -> exact
-        assert np.array_equal(idx_w, g[f"grid{k}_indices"])
-        pos_r = g[f"grid{k}_positions"].reshape(-1, 3)         # NerfPosition is three floats in the reference build
-        assert np.abs(pos_w[:, :3] - pos_r).max() <= 2.5e-7     # one ulp near 1.0 (FMA contraction in the affine map)
+        # cell choice: integer hashing + threshold tests on identical grid values -> exact.  Positions turned out bit-identical as
+        # well; the golden keeps SHA-256 digests of both arrays and their first 4096 rows (NerfPosition is three floats in the
+        # reference build)
+        sha = lambda a: np.frombuffer(hashlib.sha256(np.ascontiguousarray(a).tobytes()).digest(), dtype=np.uint8)   # noqa: E731
+        assert np.array_equal(idx_w[:4096], g[f"grid{k}_indices_head"]) and np.array_equal(sha(idx_w), g[f"grid{k}_indices_sha256"])
+        pos3 = np.ascontiguousarray(pos_w[:, :3])
+        assert np.array_equal(pos3[:4096], g[f"grid{k}_positions_head"]) and np.array_equal(sha(pos3), g[f"grid{k}_positions_sha256"])
         net = c["arrays"][f"grid_net_{k}.bin"]
         tmp_w = np.zeros(n_el, dtype=np.float32)
         grid_w = grid_in.copy()
-        M.lib().orc_splat_and_ema(n_tot, np.ascontiguousarray(g[f"grid{k}_indices"]).ctypes.data, net.ctypes.data, cfg.density_activation, n_el, 0.95, tmp_w.ctypes.data,
-                                  grid_w.ctypes.data)
-        grid_r = g[f"grid{k}_grid"]
+        M.lib().orc_splat_and_ema(n_tot, idx_w.ctypes.data, net.ctypes.data, cfg.density_activation, n_el, 0.95, tmp_w.ctypes.data, grid_w.ctypes.data)
+        grid_r = np.ascontiguousarray(g[f"grid{k}_grid"])
         assert np.array_equal(grid_w < 0, grid_r < 0)
         rel = np.abs(grid_w - grid_r) / np.maximum(np.abs(grid_r), 1e-20)
         assert rel[grid_r > 0].max() <= 2e-6 if (grid_r > 0).any() else True   # exp of the raw density: __expf vs the oracle's expf
         mean_r = float(g[f"grid{k}_mean"][0])
-        mean_w = float(M.lib().orc_density_mean(np.ascontiguousarray(grid_r).ctypes.data))
+        mean_w = float(M.lib().orc_density_mean(grid_r.ctypes.data))
         assert abs(mean_w - mean_r) <= 1e-5 * abs(mean_r) + 1e-12           # summation order
         bf_w = np.zeros(128 ** 3, dtype=np.uint8)
-        M.lib().orc_update_bitfield(cfg.max_cascade, np.ascontiguousarray(grid_r).ctypes.data, np.float32(mean_r), bf_w.ctypes.data)
+        M.lib().orc_update_bitfield(cfg.max_cascade, grid_r.ctypes.data, np.float32(mean_r), bf_w.ctypes.data)
         assert np.array_equal(bf_w, g[f"grid{k}_bitfield"])                  # thresholding + 7 max-pooled mips: bit exact
-        print(f"{name} step {k}: {n_tot} samples, indices and bitfield exact, max |pos| diff {np.abs(pos_w[:, :3] - pos_r).max():.1e}, "
-              f"mean {mean_r:.6g} (oracle {mean_w:.6g})")
+        print(f"{name} step {k}: {n_tot} samples; cell indices, positions and bitfield exact; mean {mean_r:.6g} (oracle {mean_w:.6g})")
         grid_prev = grid_r.copy()
     assert state.value == int(g["rng"][0]) and inc == int(g["rng"][1])
