@@ -6,6 +6,9 @@
 //     generate_training_samples_nerf, compute_loss_kernel_train_nerf                                    (:691-849, :852-1180)
 //     mark_untrained_density_grid, generate_grid_samples_nerf_nonuniform, splat_grid_samples_nerf_max_nearest_neighbor,
 //     ema_grid_samples_nerf, grid_to_bitfield, bitfield_max_pool, the mean reduction                     (:87-396, :2594-2633)
+//     init_rays_with_payload_kernel_nerf, advance_pos_nerf_kernel, compact_kernel_nerf, generate_next_nerf_network_inputs,
+//     composite_kernel_nerf, shade_kernel_nerf in the loop of NerfTracer::init_rays_from_camera / ::trace / render_nerf
+//     (:1380-1528, :398-452, :523-689, :1333-1378, :1588-1800, :2040-2135) with an analytic field in place of the network
 // The Testbed class itself is not constructed and nothing else of the application is linked: oracle/ref/Makefile compiles with the
 // reference's own flags (--use_fast_math as in its CMakeLists.txt:88), supplies a two-line stand-in for the CMake-generated
 // <cmrc/cmrc.hpp> (oracle/ref/stubs) and links with --unresolved-symbols=ignore-all, because the member functions that come along
@@ -244,6 +247,145 @@ static void run_grid_case(const json& j) {
 	f << rng.state << " " << rng.inc << "\n";
 }
 
+// The "network" of the render case: raw outputs as a closed form of the warped position, in round-to-nearest float arithmetic that
+// numpy reproduces exactly (tools/ref_nerf_cases.py: render_field), written where NerfNetwork::inference_mixed_precision would put
+// them — row-major [4 x n_elements] halves (GPUMatrix<network_precision_t, RM>, testbed_nerf.cu:1766).
+__global__ void analytic_field_kernel(const uint32_t n, const uint32_t stride, const float* __restrict__ coords, __half* __restrict__ out, float a, float b, float c) {
+	const uint32_t i = threadIdx.x + blockIdx.x * blockDim.x;
+	if (i >= n) return;
+	const float dx = __fsub_rn(coords[i * 7 + 0], 0.5f), dy = __fsub_rn(coords[i * 7 + 1], 0.5f), dz = __fsub_rn(coords[i * 7 + 2], 0.5f);
+	const float r2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+	out[i + 0 * stride] = __float2half_rn(__fmul_rn(dx, c));
+	out[i + 1 * stride] = __float2half_rn(__fmul_rn(dy, c));
+	out[i + 2 * stride] = __float2half_rn(__fmul_rn(dz, c));
+	out[i + 3 * stride] = __float2half_rn(__fsub_rn(a, __fmul_rn(r2, b)));
+}
+
+struct RaysSoa {
+	GPUMemory<vec4> rgba;
+	GPUMemory<float> depth;
+	GPUMemory<NerfPayload> payload;
+	void resize(size_t n) {
+		rgba.resize(n);
+		depth.resize(n);
+		payload.resize(n);
+		rgba.memset(0);
+		depth.memset(0);
+		payload.memset(0);
+	}
+};
+
+static void run_render_case(const json& j) {
+	cudaStream_t stream = nullptr;
+	const ivec2 resolution((int)j["width"], (int)j["height"]);
+	const uint32_t n_pixels = (uint32_t)resolution.x * (uint32_t)resolution.y;
+	const size_t n_padded = next_multiple((size_t)n_pixels, size_t(BATCH_SIZE_GRANULARITY));
+	const vec2 focal_length((float)j["focal_x"], (float)j["focal_y"]);
+	const vec2 screen_center((float)j["screen_x"], (float)j["screen_y"]);
+	mat4x3 camera;
+	for (int c = 0; c < 4; ++c)
+		for (int r = 0; r < 3; ++r) camera[c][r] = (float)j["camera"][c * 3 + r];
+	const BoundingBox train_aabb = make_aabb(j);
+	const BoundingBox render_aabb{
+		vec3((float)j["render_aabb_min"][0], (float)j["render_aabb_min"][1], (float)j["render_aabb_min"][2]),
+		vec3((float)j["render_aabb_max"][0], (float)j["render_aabb_max"][1], (float)j["render_aabb_max"][2])};
+	const mat3 render_aabb_to_local = mat3::identity();
+	const uint32_t max_cascade = j["max_cascade"], sample_index = j["spp_index"];
+	const float cone_angle_constant = j["cone_angle_constant"], min_transmittance = j["min_transmittance"], near_distance = j["near_distance"];
+	const ENerfActivation rgb_act = (ENerfActivation)(int)j["rgb_activation"], density_act = (ENerfActivation)(int)j["density_activation"];
+	const float fa = j["field_a"], fb = j["field_b"], fc = j["field_c"];
+
+	auto bitfield_h = read_bin<uint8_t>("bitfield.bin");
+	GPUMemory<uint8_t> bitfield;
+	bitfield.resize_and_copy_from_host(bitfield_h);
+
+	GPUMemory<vec4> frame(n_pixels);
+	GPUMemory<float> depth_buffer(n_pixels);
+	frame.memset(0);
+	depth_buffer.memset(0);
+	RaysSoa rays[2], rays_hit;
+	rays[0].resize(n_padded);
+	rays[1].resize(n_padded);
+	rays_hit.resize(n_padded);
+	GPUMemory<__half> network_output(n_padded * MAX_STEPS_INBETWEEN_COMPACTION * 4);
+	GPUMemory<float> network_input(n_padded * MAX_STEPS_INBETWEEN_COMPACTION * 7);
+	GPUMemory<uint32_t> counters(64);
+	counters.memset(0);
+	uint32_t* hit_counter = counters.data();
+	uint32_t* alive_counter = counters.data() + 32;
+
+	// ---- NerfTracer::init_rays_from_camera
+	const dim3 threads = {16, 8, 1};
+	const dim3 blocks = {div_round_up((uint32_t)resolution.x, threads.x), div_round_up((uint32_t)resolution.y, threads.y), 1};
+	init_rays_with_payload_kernel_nerf<<<blocks, threads, 0, stream>>>(
+		sample_index, rays[0].payload.data(), resolution, focal_length, camera, camera, vec4(0.0f), screen_center, vec3(0.0f), true, render_aabb,
+		render_aabb_to_local, near_distance, 1.0f, 0.0f, Foveation{}, Lens{}, Buffer2DView<const vec4>{}, frame.data(), depth_buffer.data(),
+		Buffer2DView<const uint8_t>{}, Buffer2DView<const vec2>{}, ERenderMode::Shade
+	);
+	linear_kernel(
+		advance_pos_nerf_kernel, 0, stream, n_pixels, render_aabb, render_aabb_to_local, camera[2], focal_length, sample_index, rays[0].payload.data(),
+		bitfield.data(), 0u, max_cascade, cone_angle_constant
+	);
+
+	// ---- NerfTracer::trace
+	uint32_t n_alive = n_pixels;
+	uint32_t i = 1;
+	uint32_t double_buffer_index = 0;
+	uint64_t n_queries = 0;
+	while (i < MARCH_ITER) {
+		RaysSoa& rays_current = rays[(double_buffer_index + 1) % 2];
+		RaysSoa& rays_tmp = rays[double_buffer_index % 2];
+		++double_buffer_index;
+		CUDA_CHECK_THROW(cudaMemsetAsync(alive_counter, 0, sizeof(uint32_t), stream));
+		linear_kernel(
+			compact_kernel_nerf, 0, stream, n_alive, rays_tmp.rgba.data(), rays_tmp.depth.data(), rays_tmp.payload.data(), rays_current.rgba.data(),
+			rays_current.depth.data(), rays_current.payload.data(), rays_hit.rgba.data(), rays_hit.depth.data(), rays_hit.payload.data(), alive_counter,
+			hit_counter
+		);
+		CUDA_CHECK_THROW(cudaMemcpyAsync(&n_alive, alive_counter, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+		CUDA_CHECK_THROW(cudaStreamSynchronize(stream));
+		if (n_alive == 0) break;
+		const uint32_t target_n_queries = 2 * 1024 * 1024;
+		const uint32_t n_steps_between_compaction =
+			clamp(target_n_queries / n_alive, (uint32_t)MIN_STEPS_INBETWEEN_COMPACTION, (uint32_t)MAX_STEPS_INBETWEEN_COMPACTION);
+		PitchedPtr<NerfCoordinate> input_data((NerfCoordinate*)network_input.data(), 1, 0, 0);
+		linear_kernel(
+			generate_next_nerf_network_inputs, 0, stream, n_alive, render_aabb, render_aabb_to_local, train_aabb, focal_length, camera[2],
+			rays_current.payload.data(), input_data, n_steps_between_compaction, bitfield.data(), 0u, max_cascade, cone_angle_constant, (const float*)nullptr
+		);
+		const uint32_t n_elements = next_multiple(n_alive * n_steps_between_compaction, BATCH_SIZE_GRANULARITY);
+		// rows a ray did not fill (it left the volume mid-batch) hold stale coordinates; composite_kernel_nerf never reads their outputs
+		linear_kernel(analytic_field_kernel, 0, stream, n_alive * n_steps_between_compaction, n_elements, network_input.data(), network_output.data(), fa, fb, fc);
+		n_queries += (uint64_t)n_alive * n_steps_between_compaction;
+		linear_kernel(
+			composite_kernel_nerf, 0, stream, n_alive, n_elements, i, train_aabb, camera, focal_length, 1.0f, false, rays_current.rgba.data(),
+			rays_current.depth.data(), rays_current.payload.data(), input_data, network_output.data(), 4u, n_steps_between_compaction, ERenderMode::Shade,
+			bitfield.data(), rgb_act, density_act, -1, min_transmittance
+		);
+		i += n_steps_between_compaction;
+	}
+	uint32_t n_hit = 0;
+	CUDA_CHECK_THROW(cudaMemcpy(&n_hit, hit_counter, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+	// ---- render_nerf: shade the rays that hit something
+	linear_kernel(
+		shade_kernel_nerf, 0, stream, n_hit, false, camera, false, 1.0f, rays_hit.rgba.data(), rays_hit.depth.data(), rays_hit.payload.data(),
+		ERenderMode::Shade, false, frame.data(), depth_buffer.data()
+	);
+	CUDA_CHECK_THROW(cudaDeviceSynchronize());
+	write_dev("out_frame.bin", (const float*)frame.data(), (size_t)n_pixels * 4);
+	write_dev("out_depth.bin", depth_buffer.data(), n_pixels);
+	// per pixel: how many steps the ray took (payload.n_steps of the rays that hit), 0 elsewhere
+	std::vector<NerfPayload> ph(n_hit);
+	if (n_hit) CUDA_CHECK_THROW(cudaMemcpy(ph.data(), rays_hit.payload.data(), n_hit * sizeof(NerfPayload), cudaMemcpyDeviceToHost));
+	std::vector<uint32_t> steps(n_pixels, 0);
+	for (const auto& p : ph) steps[p.idx] = p.n_steps;
+	{
+		std::ofstream f{g_dir + "/out_steps.bin", std::ios::binary};
+		f.write((const char*)steps.data(), (std::streamsize)(steps.size() * 4));
+	}
+	printf("render: %u of %u rays hit, %llu field queries, %u march iterations\n", n_hit, n_pixels, (unsigned long long)n_queries, i);
+}
+
 int main(int argc, char** argv) {
 	if (argc != 2) {
 		fprintf(stderr, "usage: ref_nerf <case dir>\n");
@@ -256,6 +398,7 @@ int main(int argc, char** argv) {
 		const std::string type = j["type"];
 		if (type == "train") run_train_case(j);
 		else if (type == "grid") run_grid_case(j);
+		else if (type == "render") run_render_case(j);
 		else throw std::runtime_error("unknown case type " + type);
 	} catch (const std::exception& e) {
 		fprintf(stderr, "error: %s\n", e.what());

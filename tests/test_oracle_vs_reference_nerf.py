@@ -1,8 +1,9 @@
 """CPU: the C oracle's NeRF sample generation, loss / compaction and density-grid upkeep against the REFERENCE's own kernels.
 
 tests/golden/ref_nerf_<case>.npz hold what generate_training_samples_nerf, compute_loss_kernel_train_nerf, mark_untrained_density_grid,
-generate_grid_samples_nerf_nonuniform, splat_grid_samples_nerf_max_nearest_neighbor, ema_grid_samples_nerf, grid_to_bitfield and
-bitfield_max_pool (src/testbed_nerf.cu) produced on a B200 for the seeded cases of tools/ref_nerf_cases.py — the kernels themselves,
+generate_grid_samples_nerf_nonuniform, splat_grid_samples_nerf_max_nearest_neighbor, ema_grid_samples_nerf, grid_to_bitfield,
+bitfield_max_pool and the NerfTracer kernels (init_rays_with_payload_kernel_nerf, advance_pos_nerf_kernel, compact_kernel_nerf,
+generate_next_nerf_network_inputs, composite_kernel_nerf, shade_kernel_nerf) (src/testbed_nerf.cu) produced on a B200 for the seeded cases of tools/ref_nerf_cases.py — the kernels themselves,
 compiled from /root/reference by oracle/ref/Makefile (`nerf` target, oracle/ref/ref_nerf_harness.cu) with the reference's own flags.
 
 The reference is built with --use_fast_math and FMA contraction (CMakeLists.txt:88); the oracle and this library's CUDA march use
@@ -198,3 +199,46 @@ def test_density_grid_upkeep_matches_the_reference_kernels(name):
         print(f"{name} step {k}: {n_tot} samples; cell indices, positions and bitfield exact; mean {mean_r:.6g} (oracle {mean_w:.6g})")
         grid_prev = grid_r.copy()
     assert state.value == int(g["rng"][0]) and inc == int(g["rng"][1])
+
+
+@pytest.mark.parametrize("name", list(RC.RENDER_CASES))
+def test_render_matches_the_reference_tracer_kernels(name):
+    """the reference's NerfTracer loop (init rays, advance, compact, generate inputs, composite, shade) with an analytic field in the
+    network's place, against the oracle's march + composite fed with the same field"""
+    c = RC.build_case(name)
+    rc = c["rc"]
+    w, h = rc.width, rc.height
+    n, ms = w * h, RC.RENDER_MAX_STEPS
+    counts = np.zeros(n, dtype=np.uint32)
+    coords = np.zeros((n, ms, 7), dtype=np.float32)
+    M.lib().orc_render_march(C.byref(rc), 0, h, c["bitfield"].ctypes.data, ms, counts.ctypes.data, coords.ctypes.data)
+    assert 10 < counts.max() < ms
+    net = RC.render_field(coords, *c["field"])
+    rgba_w = np.zeros((n, 4), dtype=np.float32)
+    depth_w = np.zeros(n, dtype=np.float32)
+    used_w = np.zeros(n, dtype=np.uint32)
+    M.lib().orc_render_composite(C.byref(rc), 0, h, ms, counts.ctypes.data, coords.ctypes.data, net.ctypes.data, rgba_w.ctypes.data, depth_w.ctypes.data, used_w.ctypes.data)
+    assert 0.1 < (rgba_w[:, 3] > 0.2).mean() < 0.9 and (used_w < counts).any()          # a ball with soft edges; opaque rays stop early
+    g = golden(name)
+    frame_r = g["frame"].reshape(n, 4)
+    depth_r = g["depth"]
+    steps_r = g["steps"]
+    # the reference shades only rays whose alpha exceeds 0.001 (compact_kernel_nerf); below that the oracle's values are that small too
+    err = np.abs(frame_r - rgba_w)
+    hit_r, hit_w = frame_r[:, 3] > 0.2, rgba_w[:, 3] > 0.2
+    print(f"{name}: max abs colour / alpha error {err.max(axis=0)}, mean {err.mean():.2e}; alpha > 0.2 on {hit_r.sum()} (reference) / {hit_w.sum()} (oracle) pixels")
+    # same positions up to the fast-math drift of t (1e-5), same fp16 field values except where that drift crosses an fp16 rounding
+    # boundary, __expf in the reference's alpha: a few 1e-3 at worst, 1e-4 on average
+    assert err.max() <= 1e-2 and err.mean() <= 2e-4
+    assert (hit_r != hit_w).sum() <= 2
+    both = hit_r & hit_w
+    # depth = camera-space z of the sample with the largest weight: within one step unless two samples tie
+    step = 1.7e-3 * (1 if rc.max_cascade == 0 else 8)
+    close = np.abs(depth_r[both] - depth_w[both]) <= 2 * step
+    assert close.mean() >= 0.98, close.mean()
+    assert np.all(depth_r[~hit_r] == np.float32(depth_r[~hit_r].max()))                    # MAX_DEPTH where nothing was hit
+    # steps taken by rays that end up visible: the reference's payload.n_steps counts the terminating step (+1 when the ray leaves the volume)
+    vis = steps_r > 0
+    d = steps_r[vis].astype(np.int64) - used_w[vis].astype(np.int64)
+    print(f"{name}: steps per visible ray, reference - oracle: min {d.min()}, max {d.max()}, mean {d.mean():.3f}")
+    assert np.abs(d).max() <= 3 and (np.abs(d) <= 1).mean() >= 0.99

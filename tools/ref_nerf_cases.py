@@ -1,6 +1,6 @@
 """Inputs for oracle/_ref/ref_nerf (the reference's own NeRF kernels, oracle/ref/ref_nerf_harness.cu) and the packing of its outputs.
 
-    python tools/ref_nerf_cases.py write <root>      # <root>/<case>/case.json + *.bin for every case below
+    python tools/ref_nerf_cases.py write <root> [case ...]   # <root>/<case>/case.json + *.bin (every case below by default)
     python tools/ref_nerf_cases.py pack <root> <out dir>   # <out dir>/ref_nerf_<case>.npz from the harness's out_*.bin
 
 The same `build_case` is imported by tests/test_oracle_vs_reference_nerf.py, which feeds the CPU oracle with identical inputs and
@@ -37,6 +37,12 @@ GRID_CASES = {
 GRID_STEPS = [dict(mark_untrained=1, clear_visible=1, n_uniform=1 << 18, n_nonuniform=0), dict(mark_untrained=0, clear_visible=0, n_uniform=1 << 17, n_nonuniform=1 << 17),
               dict(mark_untrained=1, clear_visible=0, n_uniform=1 << 16, n_nonuniform=1 << 17)]
 MAX_SAMPLES = 1 << 19
+RENDER_CASES = {
+    # analytic field in warped coordinates: raw density = a - b * |p - 0.5|^2, raw colour = c * (p - 0.5)
+    "render_aabb1": dict(aabb_scale=1, width=96, height=72, field=(7.0, 100.0, 8.0)),
+    "render_aabb4": dict(aabb_scale=4, width=96, height=72, field=(7.0, 1600.0, 32.0)),
+}
+RENDER_MAX_STEPS = 512
 
 
 def _views_json(views, n):
@@ -69,8 +75,59 @@ def grid_net_outputs(n, k, seed):
     return np.random.default_rng(1000 * seed + k).normal(-2.0, 3.0, size=n).astype(np.float16)
 
 
+def make_render_cfg(w, h, cam, focal, aabb_scale, spp_index=0):
+    P = util.pkg()
+    lib = P.load_library()
+    rc = P.RenderCfg()
+    rc.width, rc.height = w, h
+    rc.focal_x = rc.focal_y = focal
+    rc.screen_x = rc.screen_y = 0.5
+    m = np.asarray(cam, dtype=np.float32)
+    for c in range(4):
+        for r in range(3):
+            rc.camera[c * 3 + r] = m[r, c]
+    half = 0.5 * aabb_scale
+    for k in range(3):
+        rc.aabb_min[k] = rc.render_aabb_min[k] = 0.5 - half
+        rc.aabb_max[k] = rc.render_aabb_max[k] = 0.5 + half
+    mc = 0
+    while (1 << mc) < aabb_scale:
+        mc += 1
+    rc.max_cascade = mc
+    assert lib.ngp_march_consts_init(C.byref(rc.march), 0.0 if aabb_scale <= 1 else 1.0 / 256.0) == 0
+    rc.rgb_activation, rc.density_activation = 2, 3
+    rc.min_transmittance = 0.01
+    rc.spp_index = spp_index
+    rc.near_distance = 0.0
+    return rc
+
+
+def render_field(coords, a, b, c):
+    """the harness's analytic_field_kernel in numpy: float32, round to nearest, the same operation order; fp16 [n, 4]"""
+    p = np.asarray(coords, dtype=np.float32)[..., :3]
+    d = p - np.float32(0.5)
+    r2 = (d[..., 0] * d[..., 0] + d[..., 1] * d[..., 1]) + d[..., 2] * d[..., 2]
+    out = np.empty(p.shape[:-1] + (4,), dtype=np.float16)
+    out[..., :3] = (d * np.float32(c)).astype(np.float16)
+    out[..., 3] = (np.float32(a) - r2 * np.float32(b)).astype(np.float16)
+    return out
+
+
 def build_case(name):
     """dict(kind, cfg, views, keep, rng, json, arrays{file name: ndarray}) — arrays are what the harness reads"""
+    if name in RENDER_CASES:
+        rcs = RENDER_CASES[name]
+        w, h = rcs["width"], rcs["height"]
+        cam = S.sphere_cameras(4, radius=1.25)[1]
+        focal = 0.5 * w / np.tan(0.5 * np.deg2rad(45.0))
+        rc = make_render_cfg(w, h, cam, focal, rcs["aabb_scale"])
+        bf = util.sphere_bitfield(radius=0.3, max_cascade=rc.max_cascade)
+        j = dict(type="render", width=w, height=h, focal_x=float(rc.focal_x), focal_y=float(rc.focal_y), screen_x=0.5, screen_y=0.5, camera=[float(x) for x in rc.camera],
+                 aabb_min=[float(x) for x in rc.aabb_min], aabb_max=[float(x) for x in rc.aabb_max], render_aabb_min=[float(x) for x in rc.render_aabb_min],
+                 render_aabb_max=[float(x) for x in rc.render_aabb_max], max_cascade=int(rc.max_cascade), cone_angle_constant=float(rc.march.cone_angle),
+                 min_transmittance=float(rc.min_transmittance), near_distance=float(rc.near_distance), spp_index=int(rc.spp_index), rgb_activation=int(rc.rgb_activation),
+                 density_activation=int(rc.density_activation), field_a=rcs["field"][0], field_b=rcs["field"][1], field_c=rcs["field"][2])
+        return dict(kind="render", rc=rc, bitfield=bf, json=j, arrays={"bitfield.bin": bf}, field=rcs["field"])
     if name in TRAIN_CASES:
         sc = TRAIN_CASES[name]
         imgs, cams, focal = S.make_dataset(n_images=7, width=96, height=64, radius=sc["radius"])
@@ -96,19 +153,20 @@ def build_case(name):
     return dict(kind="grid", cfg=cfg, views=views, keep=keep, rng=rng, json=j, arrays=arrays, seed=gc["seed"])
 
 
-def write_all(root):
+def write_all(root, names=None):
     root = Path(root)
-    for name in list(TRAIN_CASES) + list(GRID_CASES):
+    for name in (names or list(TRAIN_CASES) + list(GRID_CASES) + list(RENDER_CASES)):
         c = build_case(name)
         d = root / name
         d.mkdir(parents=True, exist_ok=True)
         (d / "case.json").write_text(json.dumps(c["json"]))
         for fn, a in c["arrays"].items():
             np.ascontiguousarray(a).tofile(d / fn)
-    return list(TRAIN_CASES) + list(GRID_CASES)
+    return names or list(TRAIN_CASES) + list(GRID_CASES) + list(RENDER_CASES)
 
 
-OUT_DTYPES = {"counters": np.uint32, "counter": np.uint32, "ray_indices": np.uint32, "numsteps": np.uint32, "indices": np.uint32, "dloss": np.float16, "bitfield": np.uint8}
+OUT_DTYPES = {"counters": np.uint32, "counter": np.uint32, "ray_indices": np.uint32, "numsteps": np.uint32, "indices": np.uint32, "dloss": np.float16, "bitfield": np.uint8,
+              "steps": np.uint32}
 
 
 def pack(root, out_dir):
@@ -130,6 +188,6 @@ def pack(root, out_dir):
 
 if __name__ == "__main__":
     if sys.argv[1] == "write":
-        print(" ".join(write_all(sys.argv[2])))
+        print(" ".join(write_all(sys.argv[2], sys.argv[3:] or None)))
     elif sys.argv[1] == "pack":
         pack(sys.argv[2], sys.argv[3])
