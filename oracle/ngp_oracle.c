@@ -11,7 +11,8 @@
  * functions compiled from /root/reference (oracle/ref/ref_host_harness.cu -> tests/golden/ref_host_*.bin); sample
  * generation, loss / compaction and the occupancy-grid upkeep against the reference's own kernels run on a B200
  * (oracle/ref/ref_nerf_harness.cu includes src/testbed_nerf.cu -> tests/golden/ref_nerf_*.npz,
- * tests/test_oracle_vs_reference_nerf.py).  The render march / composite restatement is not pinned against reference kernels.
+ * tests/test_oracle_vs_reference_nerf.py); the render march / composite against the reference's NerfTracer kernels driven with an
+ * analytic field (same harness, render cases).
  */
 #include <math.h>
 #include <stdint.h>
