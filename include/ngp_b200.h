@@ -454,6 +454,10 @@ int ngp_testbed_render_device(ngp_testbed* t, int32_t width, int32_t height, con
 int ngp_testbed_save_snapshot(ngp_testbed* t, const char* path);  /* include_optimizer_state = false, compress = true */
 int ngp_testbed_save_snapshot_ex(ngp_testbed* t, const char* path, int include_optimizer_state, int compress);
 int ngp_testbed_load_snapshot(ngp_testbed* t, const char* path);
+/* Testbed::load_network_config for a .json network config (src/testbed.cu:280-309) with "parent" inheritance resolved
+ * (merge_parent_network_config :86-97: the parent, loaded relative to the child's directory, patched by the child per RFC 7386).
+ * Host only.  ngp_testbed_reload_network_from_file applies the same resolution. */
+int ngp_load_network_config(const char* path, char* json_text_out, size_t capacity, size_t* n_out);
 /* codec hooks (tests): JSON text <-> msgpack bytes as the snapshot writer / reader encode them, optionally gzip-wrapped */
 int ngp_json_to_msgpack(const char* json_text, int gzip, uint8_t* out, size_t capacity, size_t* n_out);
 int ngp_msgpack_to_json(const uint8_t* data, size_t n, int gzip, char* out, size_t capacity, size_t* n_out);

@@ -32,6 +32,7 @@ from .pyngp import (  # noqa: F401
     Testbed,
     TestbedMode,
     TrainMode,
+    load_network_config,
 )
 
-__all__ = ["Testbed", "TestbedMode", "LossType", "NerfActivation", "ColorSpace", "RenderMode", "TrainMode", "FieldTestbed", "lib", "load_library", "NgpError"]
+__all__ = ["Testbed", "TestbedMode", "LossType", "NerfActivation", "ColorSpace", "RenderMode", "TrainMode", "FieldTestbed", "load_network_config", "lib", "load_library", "NgpError"]

@@ -226,6 +226,7 @@ PROTOTYPES = {
     "ngp_testbed_save_snapshot": (C.c_int, [vp, cp]),
     "ngp_testbed_save_snapshot_ex": (C.c_int, [vp, cp, C.c_int, C.c_int]),
     "ngp_json_to_msgpack": (C.c_int, [cp, C.c_int, vp, C.c_size_t, P(C.c_size_t)]),
+    "ngp_load_network_config": (C.c_int, [C.c_char_p, C.c_char_p, C.c_size_t, P(C.c_size_t)]),
     "ngp_msgpack_to_json": (C.c_int, [vp, C.c_size_t, C.c_int, vp, C.c_size_t, P(C.c_size_t)]),
     "ngp_testbed_load_snapshot": (C.c_int, [vp, cp]),
     "ngp_testbed_sync": (C.c_int, [vp]),

@@ -3,6 +3,8 @@
 // extern "C" error convention.
 #pragma once
 
+#include <fstream>
+#include <sstream>
 #include <string>
 
 #include "common.cuh"
@@ -124,6 +126,40 @@ inline ngp_adam_cfg next_adam_cfg(const OptimizerConfig& opt, uint32_t& optimize
 	a.optimize_matrix_params = train_matrix;
 	a.optimize_non_matrix_params = train_non_matrix;
 	return a;
+}
+
+// ---- network config files: Testbed::load_network_config for ".json" + merge_parent_network_config (src/testbed.cu:86-97, 280-309).
+// A config may name a "parent" file (relative to its own directory); the parent is loaded first, recursively, and the child is applied
+// on top as an RFC 7386 merge patch (nlohmann::json::merge_patch): objects merge key by key, null deletes, everything else replaces.
+inline void json_merge_patch(Json& target, const Json& patch) {
+	if (patch.type != Json::Object) {
+		target = patch;
+		return;
+	}
+	if (target.type != Json::Object) target = jobj();
+	for (const auto& kv : patch.obj) {
+		if (kv.second.type == Json::Null) {
+			target.obj.erase(kv.first);
+		} else {
+			json_merge_patch(target.obj[kv.first], kv.second);
+		}
+	}
+}
+inline Json load_network_config_file(const std::string& path, int depth = 0) {
+	NGPB_CHECK(depth < 16, "network config: 'parent' chain too deep (cycle?)");
+	std::ifstream f(path);
+	NGPB_CHECK(f.good(), std::string("Network config '") + path + "' does not exist.");
+	std::stringstream ss;
+	ss << f.rdbuf();
+	const std::string text = ss.str();
+	Json child = JsonParser(text).parse();
+	if (child.type != Json::Object || !child.contains("parent")) return child;
+	NGPB_CHECK(child.at("parent").type == Json::String, "network config: 'parent' must be a file name");
+	const size_t slash = path.find_last_of('/');
+	const std::string dir = slash == std::string::npos ? std::string() : path.substr(0, slash + 1);
+	Json parent = load_network_config_file(dir + child.at("parent").str, depth + 1);
+	json_merge_patch(parent, child);
+	return parent;
 }
 
 }  // namespace ngpb

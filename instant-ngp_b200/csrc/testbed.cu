@@ -1018,13 +1018,7 @@ int ngp_testbed_reload_network_from_json(ngp_testbed* t, const char* json_text) 
 int ngp_testbed_reload_network_from_file(ngp_testbed* t, const char* path) {
 	NGPB_TRY({
 		tb_invalidate_prefetch(t);
-		std::ifstream f(path);
-		NGPB_CHECK(f.good(), std::string("network config not found: ") + path);
-		std::stringstream ss;
-		ss << f.rdbuf();
-		const std::string text = ss.str();
-		Json cfg = JsonParser(text).parse();
-		NGPB_CHECK(!cfg.contains("parent"), "config inheritance ('parent') is not supported");
+		const Json cfg = load_network_config_file(path);   // "parent" chains resolved (merge_parent_network_config, src/testbed.cu:86-97)
 		tb_reset_network(t, cfg);
 	});
 }
@@ -1701,6 +1695,16 @@ int ngp_testbed_load_snapshot(ngp_testbed* t, const char* path) {
 		t->reduce_scratch.ensure(1024);
 		update_bitfield(t->stream, t->cfg.max_cascade, t->density_grid.p, t->bitfield.p, t->mean_density.p, t->reduce_scratch.p);
 		NGPB_CUDA_CHECK(cudaStreamSynchronize(t->stream));
+	});
+}
+// Testbed::load_network_config for a .json file, "parent" inheritance applied; JSON text out (host only, no device needed)
+int ngp_load_network_config(const char* path, char* out, size_t capacity, size_t* n_out) {
+	NGPB_TRY({
+		std::string text;
+		json_dump(load_network_config_file(path), text);
+		*n_out = text.size();
+		NGPB_CHECK(text.size() + 1 <= capacity, "ngp_load_network_config: output buffer too small");
+		memcpy(out, text.c_str(), text.size() + 1);
 	});
 }
 // codec hooks for the tests: JSON text -> msgpack (optionally gzip) and back (binary values print as {"bytes": n})

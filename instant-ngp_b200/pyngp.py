@@ -150,6 +150,16 @@ class _Nerf:
         self._tb._set("nerf.density_activation", float(int(v)))
 
 
+def load_network_config(path) -> dict:
+    """Testbed::load_network_config for a .json file (src/testbed.cu:280-309): comments allowed, "parent" inheritance resolved
+    (merge_parent_network_config :86-97).  Host only; the C library does the work (ngp_load_network_config)."""
+    cap = 1 << 20
+    out = C.create_string_buffer(cap)
+    n = C.c_size_t(0)
+    B.check(B.lib().ngp_load_network_config(str(path).encode(), out, cap, C.byref(n)))
+    return json.loads(out.value.decode())
+
+
 def _default_stream(device: int) -> int:
     try:  # run on torch's current stream when torch drives the process (bench / DP); plain default stream otherwise
         import torch
@@ -261,9 +271,16 @@ class FieldTestbed:
         B.check(B.lib().ngp_field_testbed_set_sdf_training_data(self._h, p.ctypes.data_as(C.c_void_p), d.ctypes.data_as(C.c_void_p), p.shape[0]))
 
     # -- network ---------------------------------------------------------------------------------------------------
+    def find_network_config(self, path) -> Path:
+        """src/testbed.cu:254-270: as given, else <root_dir>/configs/<mode>/<path>"""
+        p = Path(path)
+        if p.exists() or p.is_absolute():
+            return p
+        cand = Path(self.root_dir) / "configs" / ("image" if self.mode == TestbedMode.Image else "sdf") / p
+        return cand if cand.exists() else p
+
     def reload_network_from_file(self, path: str = "") -> None:
-        with open(path, "r") as f:
-            self.reload_network_from_json(f.read())
+        self.reload_network_from_json(load_network_config(self.find_network_config(path)))
 
     def reload_network_from_json(self, config, config_base_path: str = "") -> None:
         text = config if isinstance(config, str) else json.dumps(config)
@@ -535,7 +552,9 @@ class Testbed:
 
     # -- network ---------------------------------------------------------------------------------------------------
     def reload_network_from_file(self, path: str = "") -> None:
-        B.check(B.lib().ngp_testbed_reload_network_from_file(self._h, str(path).encode()))
+        """python_api.cu:543: a config file, looked up under <root_dir>/configs/nerf/ when not found as given; "parent" chains resolve
+        inside the library (ngp_testbed_reload_network_from_file)"""
+        B.check(B.lib().ngp_testbed_reload_network_from_file(self._h, str(self.find_network_config(path)).encode()))
 
     def reload_network_from_json(self, config, config_base_path: str = "") -> None:
         text = config if isinstance(config, str) else json.dumps(config)
