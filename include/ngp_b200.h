@@ -280,9 +280,16 @@ typedef struct ngp_render_cfg {
 	ngp_march_consts march;
 	uint32_t rgb_activation, density_activation;
 	float min_transmittance;  /* 0.01 */
-	uint32_t spp_index;       /* sample index; pixel centres are snapped (snap_to_pixel_centers = true) */
+	uint32_t spp_index;       /* sample index: keys the low-discrepancy jitter of each ray's first step (advance_pos_nerf) */
 	float near_distance;
+	float pixel_offset[2];    /* ld_random_pixel_offset(snap_to_pixel_centers ? 0 : sample_index), random_val.cuh:320-325; the
+	                             host evaluates it (ngp_render_pixel_offset): it depends on the sample index only */
+	uint32_t lens_mode;       /* ngp_lens_mode of the render camera (Testbed::m_render_lens when m_render_with_lens_distortion) */
+	float lens_params[4];
 } ngp_render_cfg;
+/* ld_random_pixel_offset (random_val.cuh:320-325): Owen-scrambled Sobol (0, 1) point of `sample_index`, shifted so that index 0 is the
+ * pixel centre.  Host arithmetic. */
+void ngp_render_pixel_offset(uint32_t sample_index, float* offset_xy);
 size_t ngp_nerf_render_scratch_bytes(int32_t width, int32_t rows);
 int ngp_nerf_render(const ngp_nerf_desc* d, void* stream, const ngp_render_cfg* cfg, int32_t y0, int32_t y1, const void* params_fp16,
 	const uint8_t* density_grid_bitfield, float* rgba, float* depth, void* scratch, uint32_t* n_steps_total_dev);
@@ -390,6 +397,10 @@ int ngp_testbed_create_empty_nerf_dataset(ngp_testbed* t, uint32_t n_images, uin
  * rgba_host: w*h*4 float32, straight alpha, linear colour; stored premultiplied fp16 like the loader
  * (common_device.cuh:698-735). convert_to_ngp applies nerf_matrix_to_ngp (nerf_loader.h:97-116). */
 int ngp_testbed_set_image(ngp_testbed* t, uint32_t idx, const float* rgba_host, int32_t w, int32_t h);
+/* NerfDataset::set_training_image with EImageDataType::Byte (src/nerf_loader.cu:749-850), what load_nerf stores for 8-bit files:
+ * rgba8_host: w*h*4 bytes, sRGB colour + straight alpha, after convert_rgba32 (white / black -> transparent, mask colour ->
+ * 0x00FF00FF).  Pixels are converted to linear premultiplied colour on every read (read_rgba, common_device.cuh:846-872). */
+int ngp_testbed_set_image_bytes(ngp_testbed* t, uint32_t idx, const uint8_t* rgba8_host, int32_t w, int32_t h);
 int ngp_testbed_set_camera_extrinsics(ngp_testbed* t, uint32_t idx, const float* cam_to_world_3x4_rowmajor, int convert_to_ngp);
 int ngp_testbed_set_camera_intrinsics(ngp_testbed* t, uint32_t idx, float fx, float fy, float cx, float cy, float k1, float k2,
 	float p1, float p2);
@@ -469,9 +480,10 @@ int ngp_testbed_sync(ngp_testbed* t);
 #define NGP_N_PHASES 6
 int ngp_testbed_set_profiling(ngp_testbed* t, int enable);
 int ngp_testbed_get_phase_ms(ngp_testbed* t, float* ms_out, uint32_t* n_steps);
-/* Streaming data: overwrite training image `idx` (already set once with ngp_testbed_set_image, same size) from a host
- * buffer, asynchronously on the Testbed stream (pinned memory makes the copy truly asynchronous). */
-int ngp_testbed_update_image_async(ngp_testbed* t, uint32_t idx, const float* rgba_host);
+/* Streaming data: overwrite training image `idx` (already set once with ngp_testbed_set_image / _set_image_bytes, same size and
+ * pixel type: 16 or 4 bytes per pixel) from a host buffer, asynchronously on the Testbed stream (pinned memory makes the copy
+ * truly asynchronous). */
+int ngp_testbed_update_image_async(ngp_testbed* t, uint32_t idx, const void* rgba_host);
 /* number of kernel launches issued by this library since load (bench.py's gpu_launches). */
 /* ---------------------------------------------------------------------------------------------------------------
  * B2 (fields) — Testbed(ETestbedMode::Image) and Testbed(ETestbedMode::Sdf) (common.h:149-155; python_api.cu:440-442):

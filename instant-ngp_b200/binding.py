@@ -147,6 +147,9 @@ class RenderCfg(C.Structure):
         ("min_transmittance", C.c_float),
         ("spp_index", C.c_uint32),
         ("near_distance", C.c_float),
+        ("pixel_offset", C.c_float * 2),
+        ("lens_mode", C.c_uint32),
+        ("lens_params", C.c_float * 4),
     ]
 
 
@@ -189,6 +192,8 @@ PROTOTYPES = {
     "ngp_testbed_destroy": (None, [vp]),
     "ngp_testbed_create_empty_nerf_dataset": (C.c_int, [vp, u32, u32]),
     "ngp_testbed_set_image": (C.c_int, [vp, u32, vp, i32, i32]),
+    "ngp_testbed_set_image_bytes": (C.c_int, [vp, u32, vp, i32, i32]),
+    "ngp_render_pixel_offset": (None, [u32, P(f32)]),
     "ngp_testbed_set_camera_extrinsics": (C.c_int, [vp, u32, vp, C.c_int]),
     "ngp_testbed_set_camera_intrinsics": (C.c_int, [vp, u32, f32, f32, f32, f32, f32, f32, f32, f32]),
     "ngp_testbed_reload_network_from_json": (C.c_int, [vp, cp]),

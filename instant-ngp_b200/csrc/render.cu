@@ -43,6 +43,31 @@ __host__ __device__ inline float ld_random_val_dim0(uint32_t index, uint32_t see
 	return (float)nested_uniform_scramble_base2(reverse_bits32(index), hash_combine(seed, 0u)) * 2.3283064365386963e-10f;
 }
 
+// sobol(index, 1): the dimension-1 direction numbers are Pascal's triangle mod 2, v_k = v_{k-1} ^ (v_{k-1} >> 1) (random_val.cuh:172-179)
+__host__ __device__ inline uint32_t sobol_dim1(uint32_t index) {
+	uint32_t X = 0, v = 0x80000000u;
+	for (uint32_t bit = 0; bit < 32; ++bit) {
+		if ((index >> bit) & 1u) X ^= v;
+		v ^= v >> 1;
+	}
+	return X;
+}
+// ld_random_val_2d (random_val.cuh:289-293, shuffled_scrambled_sobol2d :270-277)
+__host__ __device__ inline void ld_random_val_2d(uint32_t index, uint32_t seed, float& x, float& y) {
+	index = nested_uniform_scramble_base2(index, seed);
+	x = (float)nested_uniform_scramble_base2(reverse_bits32(index), hash_combine(seed, 0u)) * 2.3283064365386963e-10f;
+	y = (float)nested_uniform_scramble_base2(sobol_dim1(index), hash_combine(seed, 1u)) * 2.3283064365386963e-10f;
+}
+// ld_random_pixel_offset (random_val.cuh:320-325)
+void render_pixel_offset(uint32_t spp, float* out) {
+	float ax, ay, bx, by;
+	ld_random_val_2d(0u, 0xdeadbeefu, ax, ay);
+	ld_random_val_2d(spp, 0xdeadbeefu, bx, by);
+	const float ox = (0.5f - ax) + bx, oy = (0.5f - ay) + by;
+	out[0] = ox - floorf(ox);
+	out[1] = oy - floorf(oy);
+}
+
 struct RenderSmemExtra {
 	uint32_t queue_base;
 };
@@ -118,12 +143,13 @@ __global__ void __launch_bounds__(TILE, 3) k_render_nerf(
 				if (q >= n_pixels) {
 					queue_empty = true;
 				} else {
-					// init_rays_with_payload_kernel_nerf with snap_to_pixel_centers: pixel offset = 0.5
+					// init_rays_with_payload_kernel_nerf (:1452-1453): pixel offset = ld_random_pixel_offset(snap ? 0 : sample_index), the
+					// render camera's lens (m_render_lens) in uv_to_ray
 					const uint32_t x = q % (uint32_t)cfg.width, y = (uint32_t)y0 + q / (uint32_t)cfg.width;
 					pix = x + (uint32_t)cfg.width * y;
-					const float u = ((float)x + 0.5f) / (float)cfg.width, v = ((float)y + 0.5f) / (float)cfg.height;
+					const float u = ((float)x + cfg.pixel_offset[0]) / (float)cfg.width, v = ((float)y + cfg.pixel_offset[1]) / (float)cfg.height;
 					V3 o, d;
-					uv_to_ray(u, v, cfg.width, cfg.height, cfg.focal_x, cfg.focal_y, cfg.screen_x, cfg.screen_y, NGP_LENS_PERSPECTIVE, nullptr, cfg.camera, o, d);
+					uv_to_ray(u, v, cfg.width, cfg.height, cfg.focal_x, cfg.focal_y, cfg.screen_x, cfg.screen_y, cfg.lens_mode, cfg.lens_params, cfg.camera, o, d);
 					o = o + d * cfg.near_distance;
 					d = normalize3(d);
 					ro = o;

@@ -63,6 +63,7 @@ void render_nerf(const ngp_nerf_desc& d, cudaStream_t stream, const ngp_render_c
 float reduce_sum_f32(cudaStream_t stream, const float* data, uint32_t n, float* scratch_dev);
 void render_accumulate(cudaStream_t stream, int32_t w, int32_t h, const float* frame, float* acc, float sample_count, uint32_t color_space);
 void render_tonemap(cudaStream_t stream, int32_t w, int32_t h, const ngp_tonemap_cfg& cfg, const float* acc, float* out);
+void render_pixel_offset(uint32_t spp, float* out);
 
 // ------------------------------------------------------------------------------------------------------------------
 // descriptors
@@ -276,6 +277,10 @@ struct ngp_testbed {
 	DevBuf<float> render_rgba, render_depth;
 	DevBuf<uint32_t> render_counter;
 	float render_min_transmittance = 0.01f;
+	bool render_snap_to_pixel_centers = false;   // m_snap_to_pixel_centers (testbed.h): the reference's default jitters pixels per sample index
+	bool render_with_lens_distortion = false;    // m_render_with_lens_distortion / m_render_lens (set by set_camera_to_training_view)
+	uint32_t render_lens_mode = NGP_LENS_PERSPECTIVE;
+	float render_lens_params[4] = {0, 0, 0, 0};
 
 	~ngp_testbed() {
 		if (side_stream) {
@@ -955,6 +960,32 @@ int ngp_testbed_set_image(ngp_testbed* t, uint32_t idx, const float* rgba_host, 
 		t->views_dirty = true;
 	});
 }
+int ngp_testbed_set_image_bytes(ngp_testbed* t, uint32_t idx, const uint8_t* rgba8_host, int32_t w, int32_t h) {
+	NGPB_TRY({
+		tb_invalidate_prefetch(t);
+		NGPB_CHECK(idx < t->n_images, "Invalid frame index");
+		NGPB_CHECK(w > 0 && h > 0, "image must have positive size");
+		if (t->pixel_bufs[idx]) cudaFree(t->pixel_bufs[idx]);
+		void* p = nullptr;
+		const size_t bytes = (size_t)w * h * 4;
+		NGPB_CUDA_CHECK(cudaMalloc(&p, bytes));
+		NGPB_CUDA_CHECK(cudaMemcpy(p, rgba8_host, bytes, cudaMemcpyHostToDevice));
+		t->pixel_bufs[idx] = p;
+		t->views[idx].pixels = p;
+		t->views[idx].image_type = NGP_IMAGE_BYTE;
+		{
+			bool any_masked = false;  // MASK_COLOR 0x00FF00FF marks a masked-away pixel (common_device.cuh:698-707)
+			const uint32_t* px = reinterpret_cast<const uint32_t*>(rgba8_host);
+			const size_t n_px = (size_t)w * h;
+			for (size_t k = 0; k < n_px && !any_masked; ++k) any_masked = px[k] == 0x00FF00FFu;
+			t->views[idx].no_mask = any_masked ? 0u : 1u;
+		}
+		t->views[idx].width = w;
+		t->views[idx].height = h;
+		t->views_dirty = true;
+	});
+}
+void ngp_render_pixel_offset(uint32_t sample_index, float* offset_xy) { render_pixel_offset(sample_index, offset_xy); }
 int ngp_testbed_set_camera_extrinsics(ngp_testbed* t, uint32_t idx, const float* m, int convert_to_ngp) {
 	NGPB_TRY({
 		tb_invalidate_prefetch(t);
@@ -1069,6 +1100,10 @@ int ngp_testbed_set_option(ngp_testbed* t, const char* name_c, double value) {
 		else if (n == "nerf.density_activation") c.density_activation = (uint32_t)value;
 		else if (n == "nerf.cone_angle_constant") march_consts_init(&c.march, (float)value);
 		else if (n == "nerf.render_min_transmittance") t->render_min_transmittance = (float)value;
+		else if (n == "snap_to_pixel_centers") t->render_snap_to_pixel_centers = value != 0;
+		else if (n == "render_with_lens_distortion") t->render_with_lens_distortion = value != 0;
+		else if (n == "render_lens.mode") { NGPB_CHECK(value == NGP_LENS_PERSPECTIVE || value == NGP_LENS_OPENCV, "render_lens.mode: perspective or OpenCV"); t->render_lens_mode = (uint32_t)value; }
+		else if (n.rfind("render_lens.params.", 0) == 0 && n.size() == 20 && n[19] >= '0' && n[19] <= '3') t->render_lens_params[n[19] - '0'] = (float)value;
 		else if (n == "color_space") c.color_space = (uint32_t)value;
 		else if (n == "background_color.r") c.background_color[0] = (float)value;
 		else if (n == "background_color.g") c.background_color[1] = (float)value;
@@ -1110,6 +1145,10 @@ double ngp_testbed_get_option(ngp_testbed* t, const char* name_c) {
 	if (n == "nerf.cone_angle_constant") return c.march.cone_angle;
 	if (n == "nerf.render_min_transmittance") return t->render_min_transmittance;
 	if (n == "nerf.max_cascade") return c.max_cascade;
+	if (n == "snap_to_pixel_centers") return t->render_snap_to_pixel_centers;
+	if (n == "render_with_lens_distortion") return t->render_with_lens_distortion;
+	if (n == "render_lens.mode") return t->render_lens_mode;
+	if (n.rfind("render_lens.params.", 0) == 0 && n.size() == 20 && n[19] >= '0' && n[19] <= '3') return t->render_lens_params[n[19] - '0'];
 	if (n == "color_space") return c.color_space;
 	if (n == "shall_train") return t->shall_train;
 	if (n == "aabb_scale") return t->aabb_scale;
@@ -1224,6 +1263,9 @@ static void tb_fill_render_cfg(ngp_testbed* t, ngp_render_cfg& rc, int32_t width
 	rc.min_transmittance = t->render_min_transmittance;
 	rc.spp_index = t->render_spp_index;
 	rc.near_distance = 0.0f;
+	render_pixel_offset(t->render_snap_to_pixel_centers ? 0u : t->render_spp_index, rc.pixel_offset);
+	rc.lens_mode = t->render_with_lens_distortion ? t->render_lens_mode : (uint32_t)NGP_LENS_PERSPECTIVE;
+	for (int k = 0; k < 4; ++k) rc.lens_params[k] = t->render_with_lens_distortion ? t->render_lens_params[k] : 0.0f;
 }
 
 int ngp_testbed_render_device(ngp_testbed* t, int32_t width, int32_t height, const float* cam, float fx, float fy, float cx, float cy, int32_t y0,
@@ -1752,7 +1794,7 @@ int ngp_testbed_get_phase_ms(ngp_testbed* t, float* ms_out, uint32_t* n_steps) {
 	t->phase_steps = 0;
 	return 0;
 }
-int ngp_testbed_update_image_async(ngp_testbed* t, uint32_t idx, const float* rgba_host) {
+int ngp_testbed_update_image_async(ngp_testbed* t, uint32_t idx, const void* rgba_host) {
 	NGPB_TRY({
 		NGPB_CHECK(idx < t->n_images && t->pixel_bufs[idx], "update_image_async: image slot was never set");
 		const ngp_train_view& v = t->views[idx];
@@ -1760,7 +1802,8 @@ int ngp_testbed_update_image_async(ngp_testbed* t, uint32_t idx, const float* rg
 		// (no_mask, established by set_image) promises that replacement frames have none either, so a generator launch
 		// already in flight for the next step stays valid; otherwise it is discarded.
 		if (!v.no_mask) tb_invalidate_prefetch(t);
-		NGPB_CUDA_CHECK(cudaMemcpyAsync(t->pixel_bufs[idx], rgba_host, (size_t)v.width * v.height * 16, cudaMemcpyHostToDevice, t->stream));
+		const size_t px_bytes = v.image_type == NGP_IMAGE_BYTE ? 4 : (v.image_type == NGP_IMAGE_HALF ? 8 : 16);
+		NGPB_CUDA_CHECK(cudaMemcpyAsync(t->pixel_bufs[idx], rgba_host, (size_t)v.width * v.height * px_bytes, cudaMemcpyHostToDevice, t->stream));
 	});
 }
 int ngp_testbed_sync(ngp_testbed* t) { NGPB_TRY(NGPB_CUDA_CHECK(cudaStreamSynchronize(t->stream))); }

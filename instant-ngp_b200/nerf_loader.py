@@ -3,9 +3,9 @@ read_focal_length :91-119) restated for the `Testbed.load_training_data` entry p
 
 The metadata logic (frame ordering, culling by sharpness, scale / offset / aabb, lens and focal-length precedence, the
 nerf -> ngp coordinate change) lives here; pixels are decoded with PIL and handed to the C++ Testbed through the same
-`set_image` / `set_camera_*` calls a user would make (python_api.cu:809-853).  8-bit images are sRGB: converted to linear
-and stored premultiplied fp16 by `ngp_testbed_set_image` (the reference keeps the bytes and converts on every read,
-common_device.cuh:661-735 — same values up to the fp16 rounding of the stored pixel).
+`set_image` / `set_camera_*` calls a user would make (python_api.cu:809-853).  8-bit images are uploaded as bytes (sRGB colour, straight alpha:
+`ngp_testbed_set_image_bytes` ≙ set_training_image with EImageDataType::Byte) and converted to linear premultiplied colour on
+every read, as the reference does (common_device.cuh:698-735).
 
 Pinned against the reference's own `ngp::load_nerf`, compiled from /root/reference and run over the scenes of
 tests/loader_scenes.py (oracle/ref/ref_loader_harness.cu -> tests/golden/ref_loader.json, tests/test_nerf_loader.py): frame order
@@ -261,9 +261,11 @@ def load_into_testbed(tb, path) -> dict:
     for k, ax in enumerate("xyz"):
         tb._set(f"nerf.training.dataset.offset.{ax}", ds["offset"][k])
     for i, im in enumerate(ds["images"]):
-        rgba = read_image_linear_rgba(im["path"], ds["white_transparent"], ds["black_transparent"])
+        # 8-bit files stay bytes (EImageDataType::Byte, nerf_loader.cu:606-612): read_rgba converts sRGB -> linear and premultiplies
+        # by alpha on every read (common_device.cuh:698-735), exactly what the loss kernel's Byte branch does here
+        rgba8 = read_image_bytes_rgba(im["path"], ds["white_transparent"], ds["black_transparent"])
         fl = im["focal_length"]
-        tb.nerf.training.set_image(i, rgba)
+        tb.nerf.training.set_image_bytes(i, rgba8)
         tb.nerf.training.set_camera_extrinsics(i, im["xform"], convert_to_ngp=False)
         lens = im["lens"]
         k = lens["params"] if lens["opencv"] else [0.0, 0.0, 0.0, 0.0]

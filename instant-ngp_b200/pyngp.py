@@ -114,6 +114,14 @@ class _Training:
             raise ValueError("image should be (H,W,C) where C=4")
         B.check(B.lib().ngp_testbed_set_image(self._tb._h, frame_idx, img.ctypes.data, img.shape[1], img.shape[0]))
 
+    def set_image_bytes(self, frame_idx: int, img: np.ndarray) -> None:
+        """NerfDataset::set_training_image(EImageDataType::Byte) (src/nerf_loader.cu:749-850): [H, W, 4] uint8, sRGB + straight alpha,
+        as load_nerf keeps 8-bit files; converted to linear premultiplied colour on every read like the reference"""
+        img = np.ascontiguousarray(img, dtype=np.uint8)
+        if img.ndim != 3 or img.shape[2] != 4:
+            raise ValueError("image should be (H,W,4) uint8")
+        B.check(B.lib().ngp_testbed_set_image_bytes(self._tb._h, frame_idx, img.ctypes.data, img.shape[1], img.shape[0]))
+
     def set_camera_extrinsics(self, frame_idx: int, camera_to_world: np.ndarray, convert_to_ngp: bool = True) -> None:
         m = np.ascontiguousarray(np.asarray(camera_to_world, dtype=np.float32)[:3, :4])
         B.check(B.lib().ngp_testbed_set_camera_extrinsics(self._tb._h, frame_idx, m.ctypes.data, int(convert_to_ngp)))
@@ -426,13 +434,32 @@ class Testbed:
 
     @property
     def snap_to_pixel_centers(self) -> bool:
-        """render rays go through pixel centres (what scripts/run.py sets for screenshots); the jittered form is not built"""
-        return True
+        """m_snap_to_pixel_centers (python_api.cu:699): False (the reference's default) jitters the pixel position per sample index
+        (ld_random_pixel_offset), True sends every sample through the pixel centre (what scripts/run.py sets for evaluation)"""
+        return bool(self._get("snap_to_pixel_centers"))
 
     @snap_to_pixel_centers.setter
     def snap_to_pixel_centers(self, v) -> None:
-        if not v:
-            raise B.NgpError("render: only snap_to_pixel_centers = True is implemented")
+        self._set("snap_to_pixel_centers", float(bool(v)))
+
+    @property
+    def render_with_lens_distortion(self) -> bool:
+        """m_render_with_lens_distortion (python_api.cu:690): apply `render_lens` (set by set_camera_to_training_view) to the render rays"""
+        return bool(self._get("render_with_lens_distortion"))
+
+    @render_with_lens_distortion.setter
+    def render_with_lens_distortion(self, v) -> None:
+        self._set("render_with_lens_distortion", float(bool(v)))
+
+    @property
+    def render_lens(self) -> dict:
+        return dict(mode=int(self._get("render_lens.mode")), params=[self._get(f"render_lens.params.{k}") for k in range(4)])
+
+    @render_lens.setter
+    def render_lens(self, lens) -> None:
+        self._set("render_lens.mode", float(int(lens["mode"])))
+        for k in range(4):
+            self._set(f"render_lens.params.{k}", float(lens["params"][k]))
 
     @property
     def render_mode(self) -> RenderMode:
@@ -522,9 +549,12 @@ class Testbed:
                     lens_mode=int(v.lens_mode), lens_params=[float(x) for x in v.lens_params], xform=xform)
 
     def set_camera_to_training_view(self, trainview: int) -> None:
-        """python_api.cu:654 / src/testbed.cu:486-505.  The render here is a pinhole: a view's lens distortion is not applied."""
+        """python_api.cu:654 / src/testbed.cu:486-505: camera, focal length, screen centre AND lens of the view
+        (m_render_with_lens_distortion = true, m_render_lens = the view's lens)"""
         v = self.training_view(trainview)
         self._camera.to_training_view(v["xform"], v["focal_length"], v["resolution"], v["principal_point"])
+        self.render_lens = dict(mode=v["lens_mode"], params=v["lens_params"])
+        self.render_with_lens_distortion = True
 
     @property
     def background_color(self):

@@ -140,7 +140,7 @@ def test_reference_shaped_camera_api(trained):
     tb.exposure = 0.0
     lit = lin[..., :3].max(axis=-1) > 0.05
     assert lit.any() and (brighter[..., :3][lit] >= base[..., :3][lit]).all() and brighter[..., :3][lit].mean() > 1.2 * base[..., :3][lit].mean()
-    assert tb.render_mode == P.RenderMode.Shade and tb.snap_to_pixel_centers and tb.jit_fusion
+    assert tb.render_mode == P.RenderMode.Shade and not tb.snap_to_pixel_centers and tb.jit_fusion   # m_snap_to_pixel_centers defaults to false (testbed.h)
     with pytest.raises(P.NgpError):
         tb.render_mode = P.RenderMode.Depth
     with pytest.raises(P.NgpError):

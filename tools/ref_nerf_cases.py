@@ -98,6 +98,7 @@ def make_render_cfg(w, h, cam, focal, aabb_scale, spp_index=0):
     rc.rgb_activation, rc.density_activation = 2, 3
     rc.min_transmittance = 0.01
     rc.spp_index = spp_index
+    rc.pixel_offset[0] = rc.pixel_offset[1] = 0.5   # snap_to_pixel_centers (ld_random_pixel_offset(0) == (0.5, 0.5))
     rc.near_distance = 0.0
     return rc
 
