@@ -1,7 +1,7 @@
 #!/usr/bin/env bash
 # Builds the UNMODIFIED reference (NVlabs/instant-ngp, headless) for sm_100 from a scratch copy of /root/reference and
 # installs the artefacts a GPU box needs into baseline/_ref/ (git-ignored, travels with gpurun):
-#   baseline/_ref/pyngp*.so, baseline/_ref/instant-ngp, baseline/_ref/configs/, baseline/_ref/data/nerf/fox, data/image
+#   baseline/_ref/pyngp*.so, baseline/_ref/configs/, baseline/_ref/data/nerf/fox, data/image
 # Recipe = BASELINE.md section 3.1 / SURVEY.md section 8c.  Nothing from the reference enters the git history.
 set -euo pipefail
 REF=${REF:-/root/reference}
@@ -17,7 +17,6 @@ cmake -S "$SCRATCH/src" -B "$SCRATCH/build" -G Ninja -DNGP_BUILD_WITH_GUI=OFF -D
       -DCMAKE_CUDA_ARCHITECTURES=100 > "$SCRATCH/cmake.log" 2>&1
 cmake --build "$SCRATCH/build" -j "$JOBS" > "$SCRATCH/build.log" 2>&1
 cp "$SCRATCH"/build/pyngp*.so "$OUT/"
-cp "$SCRATCH"/build/instant-ngp "$OUT/" || true
 rm -rf "$OUT/configs" "$OUT/data"
 cp -r "$REF/configs" "$OUT/configs"
 mkdir -p "$OUT/data/nerf" "$OUT/data/image"

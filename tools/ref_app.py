@@ -138,6 +138,7 @@ class Reference(Impl):
         self.tb.training_batch_size = BATCH
 
     def load_transforms(self, path):
+        self.data_dir = Path(path).parent
         self.tb.load_training_data(str(path))
 
     def load_arrays(self, imgs, cams, focal, aabb_scale=1):
@@ -184,7 +185,8 @@ class Reference(Impl):
         return int(r[0]), int(r[1])
 
     def view_path(self, i):
-        return str(self.tb.nerf.training.dataset.paths[i])
+        p = Path(str(self.tb.nerf.training.dataset.paths[i]))
+        return str(p if p.is_absolute() else self.data_dir / p)
 
     def render_view(self, i, w, h, spp=1):
         self.tb.set_camera_to_training_view(i)
@@ -376,6 +378,7 @@ def main():
         rec["samples_per_sec"] = mbs / (steady_ms * 1e-3)
         rec["rays_per_sec"] = c.get("rays_per_batch", 0) / (steady_ms * 1e-3)
         rec["samples_per_sec_nominal"] = BATCH / (steady_ms * 1e-3)
+        out.write_text(json.dumps(rec, indent=1))   # the training record survives a failure in the evaluation below
 
     # ---- evaluation on held-out views
     arte = {}

@@ -16,5 +16,5 @@ run --impl ngp_b200  --scene $SCENE --enc L8F4  --train-mode Nerf --steps $STEPS
 run --impl ngp_b200  --scene $SCENE --enc L16F2 --no-train --load-snapshot $O/ref_${SCENE}_L16F2_jit1_nerf.ingp --out $O/b200_on_refsnap_${SCENE}_L16F2.json
 run --impl reference --scene $SCENE --enc L16F2 --no-train --load-snapshot $O/b200_${SCENE}_L16F2_nerf.ingp --out $O/ref_on_b200snap_${SCENE}_L16F2.json
 run --impl reference --scene $SCENE --enc L16F2 --no-train --load-snapshot $O/ref_${SCENE}_L16F2_jit1_nerf.ingp --out $O/ref_on_refsnap_${SCENE}_L16F2.json
-rm -f $O/*_L8F4_*.ingp $O/ref_${SCENE}_L16F2_jit0_nerf.ingp   # keep the merge-back under 64 MiB
+rm -f $O/*.ingp   # keep the merge-back under 64 MiB (33 MB per snapshot)
 ls -la $O
