@@ -4,10 +4,13 @@
     python bench.py --gpus N --steps K --warmup W            (N > 1: launched through torch.distributed.run)
     python bench.py --impl reference --gpus N --steps K --warmup W
 
-Metric (BASELINE.json): NeRF training samples/s on the configuration it is quoted on — hash grid L=16 F=2 T=2^19, 64-wide
-MLPs (density 1 hidden, rgb 2 hidden), 2^18-sample batches — over a synthetic 100-view 800x800 scene (the fox JPEGs and
-NeRF-synthetic cannot reach the GPU box).  One "step" = one Testbed.train(2^18): occupancy-grid maintenance on the
-reference's schedule, training-ray generation + marching, inference, loss + compaction, fused forward/backward, optimizer.
+Metric (BASELINE.json): NeRF training samples/s on the configuration it is quoted on — BASELINE config #2, nerf/fox (the
+reference's own data/nerf/fox: 50 JPEGs 1080x1920, aabb_scale 4, OpenCV lens; every 5th frame held out as scripts/scenes.py does),
+hash grid L=16 F=2 T=2^19, 64-wide MLPs (density 1 hidden, rgb 2 hidden), 2^18-sample batches.  The scene travels to the GPU box
+inside baseline/_ref/ (git-ignored, shipped by gpurun; baseline/build_ref.sh puts it there); when it is absent the workload
+falls back to the synthetic 100-view 800x800 ball (`--scene ball`, BASELINE config #3's stand-in: NeRF-synthetic is not in the
+reference tree).  One "step" = one Testbed.train(2^18): occupancy-grid maintenance on the reference's schedule, training-ray
+generation + marching, inference, loss + compaction, fused forward/backward, optimizer.
 
 value  : compacted samples trained per second, all ranks, dataset resident in HBM (device-timed with CUDA events).
 e2e    : the same through the public pyngp-style API while one training image per step is streamed from pinned host
@@ -15,7 +18,9 @@ e2e    : the same through the public pyngp-style API while one training image pe
 timing : steady state — 700 untimed set-up steps (--pretrain) + W warm-up steps come first: the per-step workload (rays per batch,
          samples per ray) only settles once the scene has formed (SURVEY §8d asks for steps 500-1000); then exactly K timed steps.
 extras : roofline (k_nerf_train), cpu_baseline (oracle port, rank 0, N = 1), clocks (NVML during the timed region), render
-         (1920x1080 Mrays/s), quality (PSNR of the trained model), phase_ms_per_step (CUDA events per phase, separate pass).
+         (1920x1080 Mrays/s), quality (PSNR of the trained model), phase_ms_per_step (CUDA events per phase, separate pass),
+         reference_gpu (the UNMODIFIED reference application, baseline/_ref/pyngp*.so, driven by tools/ref_app.py on the same
+         box, same scene, same protocol, in a subprocess after this arm's timing; N = 1 only).
 N > 1  : weak scaling — every rank trains its own 2^18-sample batch on its shard of the global ray batch; one
          torch.distributed (NCCL) all-reduce of the flat fp16 gradient buffer per step.
 """
@@ -253,10 +258,6 @@ def main() -> None:
     ap.add_argument("--chunk", type=int, default=0, help="ray-ordered inference chunk (4 or 8)")
     ap.add_argument("--overlap", action="store_true", help="enable the side-stream prefetch of the next step's sample generation")
     ap.add_argument("--full-inference", action="store_true", help="evaluate every generated sample like the reference schedule")
-    ap.add_argument("--sort", action="store_true", help="A/B: generator marches the rays bucketed by expected length instead of in batch order")
-    ap.add_argument("--split", action="store_true", help="A/B: count + write generator kernels instead of the fused one")
-    ap.add_argument("--no-gate", action="store_true", help="A/B: the prefetched generator does not wait for the forward/backward kernel")
-    ap.add_argument("--lazy", type=int, default=None, help="A/B: eager coordinate prefix per ray (multiple of 8); the inference kernel marches the rest on demand")
     ap.add_argument("--no-render", action="store_true", help="skip the 1920x1080 render timing (reported under the extra key `render`)")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -287,15 +288,6 @@ def main() -> None:
         tb._set("nerf.training.overlap_sample_generation", 1.0)
     if args.full_inference:
         tb._set("nerf.training.full_inference", 1.0)
-    if args.sort:
-        tb._set("nerf.training.sort_rays", 1.0)
-    if args.split:
-        tb._set("nerf.training.split_generation", 1.0)
-    if args.no_gate:
-        tb._set("nerf.training.overlap_gate", 0.0)
-    if args.lazy is not None:
-        tb._set("nerf.training.lazy_sample_generation", 1.0)
-        tb._set("nerf.training.eager_prefix", float(args.lazy))
     n_params = tb.n_params
 
     grads_t = counters_t = None

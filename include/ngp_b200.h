@@ -73,6 +73,13 @@ typedef enum ngp_loss_type { NGP_LOSS_L2 = 0, NGP_LOSS_L1 = 1, NGP_LOSS_MAPE = 2
  * (fused_kernels/train_nerf.cuh:391-410): Rfl supervises every sample's colour with the radiance-field loss, RflRelax evaluates
  * the loss gradient at the colour the ray would have if the medium behind the sample were opaque. */
 typedef enum ngp_train_mode { NGP_TRAIN_NERF = 0, NGP_TRAIN_RFL = 1, NGP_TRAIN_RFL_RELAX = 2 } ngp_train_mode;
+/* Arithmetic flavour of the training-ray march (ngp_nerf_generate_training_samples):
+ *   NGP_MATH_DETERMINISTIC  IEEE add / mul / fma only, transcendentals from ngp_detmath.h, no contraction: what the CPU oracle reproduces
+ *                           bit for bit (ray ids, per-ray sample counts, coordinates);
+ *   NGP_MATH_REFERENCE      the reference BUILD's arithmetic — its expression trees compiled with --use_fast_math (approximate division /
+ *                           square root, MUFU log / exp, FMA contraction, CMakeLists.txt:88): the per-ray sample counts of the reference's
+ *                           own generate_training_samples_nerf kernel.  What Testbed::train uses. */
+typedef enum ngp_math_mode { NGP_MATH_DETERMINISTIC = 0, NGP_MATH_REFERENCE = 1 } ngp_math_mode;
 typedef enum ngp_lens_mode { NGP_LENS_PERSPECTIVE = 0, NGP_LENS_OPENCV = 1 } ngp_lens_mode;
 typedef enum ngp_image_type { NGP_IMAGE_NONE = 0, NGP_IMAGE_BYTE = 1, NGP_IMAGE_HALF = 2, NGP_IMAGE_FLOAT = 3 } ngp_image_type;
 typedef enum ngp_color_space { NGP_COLOR_LINEAR = 0, NGP_COLOR_SRGB = 1 } ngp_color_space;
@@ -114,6 +121,11 @@ typedef struct ngp_nerf_train_cfg {
 	float near_distance;
 	float loss_scale;
 	uint32_t train_mode; /* ngp_train_mode; NGP_TRAIN_NERF is what the reference runs without JIT fusion (testbed_nerf.cu:3091-3093) */
+	uint32_t ray_stride; /* sample generator: global ray id = ray_offset + ray_stride * local index (0 reads as 1).  Data parallel, rank r of W
+	                        takes ids r, r + W, r + 2W, ... so that every rank draws from every training view */
+	uint32_t math_mode;  /* ngp_math_mode of the sample generator's march */
+	uint32_t gen_lanes_per_ray; /* sample generator: lanes of a warp that march one ray together (1, 2, 4, 8, 16 or 32); 0 = chosen from the
+	                               batch size.  Changes the schedule only: every ray's samples are the same for every value */
 } ngp_nerf_train_cfg;
 
 /* Counters written by the training sample generator / loss kernel (NerfCounters, testbed.h). */
@@ -205,45 +217,6 @@ int ngp_nerf_generate_training_samples(void* stream, uint32_t n_rays, uint32_t r
 	const ngp_nerf_train_cfg* cfg, const ngp_train_view* views_dev, uint32_t n_views, const uint8_t* density_grid_bitfield,
 	uint32_t max_samples, ngp_nerf_counters* counters_dev, uint32_t* ray_indices, float* rays, uint32_t* numsteps, float* coords);
 
-/* ngp_nerf_generate_training_samples with the batch's rays first bucketed by expected march length (what Testbed::train uses):
- * one thread marches one ray and rays differ 4x in length, so in batch order a warp keeps under half of its lanes busy.  The rays,
- * their counts and coordinates are those of ngp_nerf_generate_training_samples; only the slots they land in differ.
- * sort_scratch: ngp_nerf_ray_sort_scratch_bytes(n_rays) bytes of device memory. */
-size_t ngp_nerf_ray_sort_scratch_bytes(uint32_t max_rays);
-int ngp_nerf_generate_training_samples_sorted(void* stream, uint32_t n_rays, uint32_t ray_offset, uint32_t n_rays_global, uint64_t rng_state, uint64_t rng_inc,
-	const ngp_nerf_train_cfg* cfg, const ngp_train_view* views_dev, uint32_t n_views, const uint8_t* density_grid_bitfield, uint32_t max_samples,
-	ngp_nerf_counters* counters, uint32_t* ray_indices, float* rays, uint32_t* numsteps, float* coords, void* sort_scratch);
-
-/* generate_training_samples_nerf as two kernels (an option of Testbed::train, nerf.training.split_generation): ngp_nerf_count_training_samples does the ray
- * generation, the counting march and the slot reservation — outputs as ngp_nerf_generate_training_samples minus the
- * coordinates, plus a checkpoint of the march every 32 samples in ckpt_scratch (ngp_nerf_generator_scratch_floats(n_rays) floats)
- * and (count, base, slot) per ray in seg_scratch (ngp_nerf_generator_scratch_u32(n_rays) words).  It is bound by the serial
- * latency of the longest ray, needs no shared memory and may run on a side stream beside the previous step's backward pass.
- * ngp_nerf_write_training_samples then produces all coordinates, one warp per ray, lane m re-marching samples [32m, 32m+32).
- * Per ray id the results are bit-identical to ngp_nerf_generate_training_samples. */
-size_t ngp_nerf_generator_scratch_floats(uint32_t max_rays);
-size_t ngp_nerf_generator_scratch_u32(uint32_t max_rays);
-int ngp_nerf_count_training_samples(void* stream, uint32_t n_rays, uint32_t ray_offset, uint32_t n_rays_global, uint64_t rng_state, uint64_t rng_inc,
-	const ngp_nerf_train_cfg* cfg, const ngp_train_view* views_dev, uint32_t n_views, const uint8_t* density_grid_bitfield, uint32_t max_samples,
-	ngp_nerf_counters* counters, uint32_t* ray_indices, float* rays, uint32_t* numsteps, float* ckpt_scratch, uint32_t* seg_scratch);
-int ngp_nerf_write_training_samples(void* stream, uint32_t n_rays, const ngp_nerf_train_cfg* cfg, const uint8_t* density_grid_bitfield, const float* rays,
-	const float* ckpt_scratch, const uint32_t* seg_scratch, float* coords);
-
-/* generate_training_samples_nerf with its coordinate pass cut short, so that coordinates are produced only where they are
- * consumed: ngp_nerf_generate_training_samples_prefix counts every ray in full (ray records, numsteps = (count, base): identical
- * to ngp_nerf_generate_training_samples) but writes only the first `prefix` (multiple of 8) coordinates of each ray, plus
- * t_resume[ray] = the t at which the march continues.  ngp_nerf_march_inference_rays is ngp_nerf_inference_rays with that
- * continuation inside: past the prefix it walks the ray from t_resume with the generator's own arithmetic, 8 samples at a time,
- * writes the coordinates of the samples it evaluates into coords [base + k] and stops a ray where
- * compute_loss_kernel_train_nerf would (T < 1e-4).  Everything the loss kernel reads (coordinates, network outputs) is
- * bit-identical to the generate-all / evaluate-all schedule; prefix = 0 marches everything on demand. */
-int ngp_nerf_generate_training_samples_prefix(void* stream, uint32_t n_rays, uint32_t ray_offset, uint32_t n_rays_global, uint64_t rng_state, uint64_t rng_inc,
-	const ngp_nerf_train_cfg* cfg, const ngp_train_view* views_dev, uint32_t n_views, const uint8_t* density_grid_bitfield, uint32_t max_samples,
-	ngp_nerf_counters* counters, uint32_t* ray_indices, float* rays, uint32_t* numsteps, float* coords, float* t_resume, uint32_t prefix);
-int ngp_nerf_march_inference_rays(const ngp_nerf_desc* d, void* stream, uint32_t n_rays_max, const ngp_nerf_train_cfg* cfg, const ngp_nerf_counters* counters,
-	uint32_t* queue, const uint32_t* numsteps, const float* rays, const float* t_resume, uint32_t prefix, const uint8_t* density_grid_bitfield, float* coords,
-	const void* params_fp16, void* out_fp16);
-
 /* ≙ compute_loss_kernel_train_nerf (testbed_nerf.cu:852-1180): composite, loss, compaction, dL/doutput.
  * network_output: n_samples x 4 halves. Writes coords_compacted [max_compacted x 7], dloss [max_compacted x 4 halves],
  * loss_per_ray[n_rays] (may be NULL).  Loss and gradients are normalised by n_rays_global (testbed_nerf.cu:1039,1073). */
@@ -286,6 +259,9 @@ typedef struct ngp_render_cfg {
 	                             host evaluates it (ngp_render_pixel_offset): it depends on the sample index only */
 	uint32_t lens_mode;       /* ngp_lens_mode of the render camera (Testbed::m_render_lens when m_render_with_lens_distortion) */
 	float lens_params[4];
+	uint32_t math_mode;       /* ngp_math_mode of the march: NGP_MATH_DETERMINISTIC = ngp_detmath.h (bit-exact against the CPU oracle),
+	                             NGP_MATH_REFERENCE = the SFU log / exp / reciprocal the reference build's --use_fast_math compiles its
+	                             stepping functions to (what Testbed::render uses; ~10x cheaper per empty-voxel skip) */
 } ngp_render_cfg;
 /* ld_random_pixel_offset (random_val.cuh:320-325): Owen-scrambled Sobol (0, 1) point of `sample_index`, shifted so that index 0 is the
  * pixel centre.  Host arithmetic. */

@@ -105,6 +105,9 @@ class NerfTrainCfg(C.Structure):
         ("near_distance", C.c_float),
         ("loss_scale", C.c_float),
         ("train_mode", C.c_uint32),
+        ("ray_stride", C.c_uint32),
+        ("math_mode", C.c_uint32),
+        ("gen_lanes_per_ray", C.c_uint32),
     ]
 
 
@@ -150,6 +153,7 @@ class RenderCfg(C.Structure):
         ("pixel_offset", C.c_float * 2),
         ("lens_mode", C.c_uint32),
         ("lens_params", C.c_float * 4),
+        ("math_mode", C.c_uint32),
     ]
 
 
@@ -173,14 +177,6 @@ PROTOTYPES = {
     "ngp_grid_encode": (C.c_int, [P(GridDesc), vp, u32, vp, u32, vp, vp]),
     "ngp_optimizer_step": (C.c_int, [P(NerfDesc), vp, P(AdamCfg), vp, vp, vp, vp, vp, vp, vp]),
     "ngp_nerf_generate_training_samples": (C.c_int, [vp, u32, u32, u32, u64, u64, P(NerfTrainCfg), vp, u32, vp, u32, vp, vp, vp, vp, vp]),
-    "ngp_nerf_ray_sort_scratch_bytes": (C.c_size_t, [u32]),
-    "ngp_nerf_generate_training_samples_sorted": (C.c_int, [vp, u32, u32, u32, u64, u64, P(NerfTrainCfg), vp, u32, vp, u32, vp, vp, vp, vp, vp, vp]),
-    "ngp_nerf_generator_scratch_floats": (C.c_size_t, [u32]),
-    "ngp_nerf_generator_scratch_u32": (C.c_size_t, [u32]),
-    "ngp_nerf_count_training_samples": (C.c_int, [vp, u32, u32, u32, u64, u64, P(NerfTrainCfg), vp, u32, vp, u32, vp, vp, vp, vp, vp, vp]),
-    "ngp_nerf_write_training_samples": (C.c_int, [vp, u32, P(NerfTrainCfg), vp, vp, vp, vp, vp]),
-    "ngp_nerf_generate_training_samples_prefix": (C.c_int, [vp, u32, u32, u32, u64, u64, P(NerfTrainCfg), vp, u32, vp, u32, vp, vp, vp, vp, vp, vp, u32]),
-    "ngp_nerf_march_inference_rays": (C.c_int, [P(NerfDesc), vp, u32, P(NerfTrainCfg), vp, vp, vp, vp, vp, u32, vp, vp, vp, vp]),
     "ngp_nerf_compute_loss": (C.c_int, [vp, u32, u32, u64, u64, P(NerfTrainCfg), vp, u32, vp, u32, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "ngp_nerf_fill_rollover": (C.c_int, [vp, u32, vp, vp, vp]),
     "ngp_nerf_density_grid_scratch_bytes": (C.c_size_t, [u32]),

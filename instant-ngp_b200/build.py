@@ -20,7 +20,7 @@ BUILD = PKG / "_build"
 LIB = PKG / "libngp_b200.so"
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-COMMON = ["-std=c++17", "-O3", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-ffp-contract=off", "-I", str(ROOT / "include")]
+COMMON = ["-std=c++17", "-O3", "-lineinfo", "--extended-lambda", "-Xcompiler", "-fPIC", "-Xcompiler", "-ffp-contract=off", "-I", str(ROOT / "include")]
 
 # translation unit -> extra flags.  march/render are compiled without FMA contraction so that their arithmetic is
 # bit-identical to the CPU oracle (see include/ngp_detmath.h).
@@ -29,6 +29,7 @@ UNITS = {
     "optimizer.cu": ["--use_fast_math"],
     "testbed.cu": ["-fmad=false"],
     "march.cu": ["-fmad=false"],
+    "march_ref.cu": ["--use_fast_math"],   # the reference build's flags (CMakeLists.txt:88): see march_ref.cu
     "render.cu": ["-fmad=false"],
     "field.cu": ["-fmad=false"],
 }

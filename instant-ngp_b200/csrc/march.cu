@@ -1,520 +1,55 @@
 // march.cu — NeRF training-ray generation, occupancy-grid marching, compositing/loss/compaction and density-grid maintenance.
 // Compiled with -fmad=false (see march.cuh).  Restates src/testbed_nerf.cu kernels, cited per kernel.
-#include "march.cuh"
+#include "gen_kernel.cuh"
 
 namespace ngpb {
 
 // ------------------------------------------------------------------------------------------------------------------
-// image access (common_device.cuh:776-872)
+// generate_training_samples_nerf (testbed_nerf.cu:691-849): kernel body in gen_kernel.cuh, here with the deterministic arithmetic
+// of march.cuh / ngp_detmath.h (this translation unit is compiled with -fmad=false), which the CPU oracle follows bit for bit.
+// The reference build's own fast-math arithmetic is the second instantiation, march_ref.cu.
 // ------------------------------------------------------------------------------------------------------------------
-struct Rgba {
-	float r, g, b, a;
-};
-__device__ inline Rgba read_rgba_px(int px, int py, int w, const void* pixels, uint32_t type) {
-	const size_t idx = (size_t)px + (size_t)py * (size_t)w;
-	switch (type) {
-		case NGP_IMAGE_BYTE: {
-			const uint32_t val = reinterpret_cast<const uint32_t*>(pixels)[idx];
-			if (val == 0x00FF00FFu) return Rgba{-1.0f, -1.0f, -1.0f, -1.0f};
-			const float a = (float)((val >> 24) & 0xFFu) * (1.0f / 255.0f);
-			Rgba o;
-			o.r = srgb_to_linear((float)(val & 0xFFu) * (1.0f / 255.0f)) * a;
-			o.g = srgb_to_linear((float)((val >> 8) & 0xFFu) * (1.0f / 255.0f)) * a;
-			o.b = srgb_to_linear((float)((val >> 16) & 0xFFu) * (1.0f / 255.0f)) * a;
-			o.a = a;
-			return o;
-		}
-		case NGP_IMAGE_HALF: {
-			const uint2 v = reinterpret_cast<const uint2*>(pixels)[idx];
-			const __half2 lo = *reinterpret_cast<const __half2*>(&v.x), hi = *reinterpret_cast<const __half2*>(&v.y);
-			return Rgba{__low2float(lo), __high2float(lo), __low2float(hi), __high2float(hi)};
-		}
-		case NGP_IMAGE_FLOAT: {
-			const float4 v = reinterpret_cast<const float4*>(pixels)[idx];
-			return Rgba{v.x, v.y, v.z, v.w};
-		}
-		default: return Rgba{5.0f, 0.0f, 0.0f, 1.0f};
+struct DetMarch {
+	struct Ctx {
+		ngp_march_consts m;
+	};
+	static __device__ __forceinline__ Ctx make_ctx(const ngp_nerf_train_cfg& cfg) { return Ctx{cfg.march}; }
+	static __device__ __forceinline__ float calc_dt(float t, const Ctx& c) { return ngpb::calc_dt(t, c.m); }
+	static __device__ __forceinline__ V3 ray_pos(V3 o, float t, V3 d) { return o + t * d; }
+	static __device__ __forceinline__ uint32_t mip_from_dt(float dt, V3 pos, uint32_t max_cascade) { return ngpb::mip_from_dt(dt, pos, max_cascade); }
+	static __device__ __forceinline__ float advance_to_next_voxel(float t, const Ctx& c, V3 pos, V3 dir, V3 idir, uint32_t mip) {
+		return ngpb::advance_to_next_voxel(t, c.m, pos, dir, idir, mip);
 	}
-}
-__device__ inline Rgba read_rgba_uv(float u, float v, int w, int h, const void* pixels, uint32_t type) {
-	const int px = imin(imax((int)(u * (float)w), 0), w - 1);
-	const int py = imin(imax((int)(v * (float)h), 0), h - 1);
-	return read_rgba_px(px, py, w, pixels, type);
-}
-
-// nerf_device.cuh:578-599 (uniform branch): neighbouring rays of a batch look at the same image
-__host__ __device__ inline uint32_t image_idx(uint32_t base_idx, uint32_t n_rays, uint32_t n_images) {
-	return ((base_idx * n_images) / n_rays) % n_images;  // uint32 arithmetic, as the reference
-}
-
-// nerf_device.cuh:553-576 (no error-map CDF)
-__device__ inline void random_image_pos_training(Pcg32& rng, int w, int h, bool snap, float& u, float& v) {
-	u = rng.next_float();
-	v = rng.next_float();
-	if (snap) {
-		u = ((float)imin(imax((int)(u * (float)w), 0), w - 1) + 0.5f) / (float)w;
-		v = ((float)imin(imax((int)(v * (float)h), 0), h - 1) + 0.5f) / (float)h;
-	}
-}
-
-// ------------------------------------------------------------------------------------------------------------------
-// generate_training_samples_nerf (testbed_nerf.cu:691-849)
-// One thread per ray.  Slots are reserved once per warp (prefix sum + one atomic) instead of two atomics per ray.
-// ray ids are GLOBAL: ray_id = ray_offset + local index, so that W ranks reproduce the single-GPU batch.
-// ------------------------------------------------------------------------------------------------------------------
-// WRITE_ALL = false: the kernel counts every ray in full (numsteps and the slot layout are those of the reference) but writes
-// the coordinates of only the first `prefix` samples of each ray and the t at which the march would continue; the consumer
-// (k_nerf_forward_rays, render.cu) marches on from there for the few rays whose transmittance is still above 1e-4 after the
-// prefix — the loss kernel reads ~6 % of the 4 M samples a step reserves on a trained scene (profiles/r1b).
-//
-// Pass 1 leaves the t of each of a ray's first GEN_T_SLOTS samples in shared memory; the coordinate pass then does not march
-// at all for those: the warp walks its 32 rays one after the other and its lanes turn consecutive samples of the same ray
-// into coordinates (pos = o + t d, dt = calc_dt(t): the values pass 2 of the reference recomputes, testbed_nerf.cu:822-848),
-// so the work is balanced across lanes whatever the rays' lengths and the 28-byte records leave the warp contiguously.
-// Beyond GEN_T_SLOTS, pass 1 keeps one checkpoint of its loop state every GEN_SEG samples; the tails of the long rays of a
-// warp are cut into GEN_SEG-sample segments that the lanes re-march in parallel, each from its checkpoint (a 300-sample ray
-// costs 32 sequential steps instead of 220; ncu r1c: the one-thread tail re-march was half of the kernel's instructions).
-constexpr uint32_t GEN_THREADS = 128;
-constexpr uint32_t GEN_T_SLOTS = 64;    // 64 x 128 x 4 B = 32 KB of shared memory per CTA
-constexpr uint32_t GEN_SEG = 32;
-constexpr uint32_t GEN_N_CKPT = (NGP_NERF_STEPS - GEN_T_SLOTS + GEN_SEG - 1) / GEN_SEG;   // 30 x 128 x 4 B = 15 KB
-// 47 KB dynamic + 3.5 KB static (coordinate tile) + 1 KB reserved = 4 CTAs per SM = 592 resident CTAs = 75 K rays in one wave.
-// (At 3 CTAs per SM a steady-state batch of 57-66 K rays spilled into a second wave: 0.53 -> 0.80 ms, bimodal from run to run.)
-constexpr uint32_t GEN_SMEM_BYTES = (GEN_T_SLOTS + GEN_N_CKPT) * GEN_THREADS * sizeof(float);
-template <bool WRITE_ALL>
-__global__ void __launch_bounds__(GEN_THREADS) k_generate_training_samples(
-	const uint32_t n_rays_local, const uint32_t ray_offset, const uint32_t n_rays_global, Pcg32 rng_in, const ngp_nerf_train_cfg cfg,
-	const ngp_train_view* __restrict__ views, const uint32_t n_views, const uint8_t* __restrict__ bitfield, const uint32_t max_samples,
-	ngp_nerf_counters* __restrict__ counters, uint32_t* __restrict__ ray_indices_out, float* __restrict__ rays_out,
-	uint32_t* __restrict__ numsteps_out, float* __restrict__ coords_out, float* __restrict__ t_resume_out, const uint32_t prefix,
-	const uint32_t* __restrict__ perm
-) {
-	const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
-	const uint32_t lane = threadIdx.x & 31u;
-	const bool in_range = slot < n_rays_local;
-	// which ray of the batch this thread marches: identity, or the batch ordered by expected march length (k_ray_sort_*)
-	const uint32_t li = (perm && in_range) ? perm[slot] : slot;
-	const uint32_t i = ray_offset + li;
-
-	const Aabb aabb{V3{cfg.aabb_min[0], cfg.aabb_min[1], cfg.aabb_min[2]}, V3{cfg.aabb_max[0], cfg.aabb_max[1], cfg.aabb_max[2]}};
-	extern __shared__ float t_list[];   // [GEN_T_SLOTS][GEN_THREADS], then checkpoints [GEN_N_CKPT][GEN_THREADS]
-	float* ckpt = t_list + GEN_T_SLOTS * GEN_THREADS;
-	__shared__ float coord_tile[GEN_THREADS / 32][32 * 7];
-	uint32_t numsteps = 0;
-	V3 ro{0, 0, 0}, rd{0, 0, 0}, rdn{0, 0, 1}, idir{0, 0, 0};
-	float startt = 0.0f;
-
-	if (in_range) {
-		const uint32_t img = image_idx(i, n_rays_global, n_views);
-		const ngp_train_view vw = views[img];
-		Pcg32 rng = rng_in;
-		rng.advance((uint64_t)i * N_MAX_RANDOM_SAMPLES_PER_RAY);
-		float u, v;
-		random_image_pos_training(rng, vw.width, vw.height, cfg.snap_to_pixel_centers != 0, u, v);
-		const bool masked = !vw.no_mask && read_rgba_uv(u, v, vw.width, vw.height, vw.pixels, vw.image_type).r < 0.0f;
-		if (!masked) {
-			(void)rng.next_float();  // motion-blur time (testbed_nerf.cu:740) — consumed, unused without rolling shutter
-			uv_to_ray(u, v, vw.width, vw.height, vw.focal_x, vw.focal_y, vw.principal_x, vw.principal_y, vw.lens_mode, vw.lens_params, vw.xform, ro, rd);
-			rdn = normalize3(rd);
-			float tmin, tmax;
-			aabb_ray_intersect(aabb, ro, rdn, tmin, tmax);
-			tmin = fmaxf(tmin, 0.0f);
-			startt = advance_n_steps(tmin, cfg.march, rng.next_float());
-			idir = V3{1.0f / rdn.x, 1.0f / rdn.y, 1.0f / rdn.z};
-
-			// pass 1: count the occupied steps, keeping the t of the first GEN_T_SLOTS samples and the march state right after them
-			uint32_t j = 0;
-			float t = startt;
-			V3 pos;
-			OccCache occ;
-			while (aabb.contains(pos = ro + t * rdn) && j < NGP_NERF_STEPS) {
-				const float dt = calc_dt(t, cfg.march);
-				const uint32_t mip = mip_from_dt(dt, pos, cfg.max_cascade);
-				if (density_grid_occupied_cached(pos, bitfield, mip, occ)) {
-					if (j < GEN_T_SLOTS) t_list[j * GEN_THREADS + threadIdx.x] = t;
-					++j;
-					t += dt;
-					if (j >= GEN_T_SLOTS && ((j - GEN_T_SLOTS) & (GEN_SEG - 1u)) == 0u) ckpt[((j - GEN_T_SLOTS) / GEN_SEG) * GEN_THREADS + threadIdx.x] = t;
-				} else {
-					t = advance_to_next_voxel(t, cfg.march, pos, rdn, idir, mip);
-				}
-			}
-			numsteps = j;
-		}
-	}
-
-	// ---- warp-level reservation of sample slots and ray slots
-	uint32_t incl = numsteps;
-#pragma unroll
-	for (uint32_t o = 1; o < 32; o <<= 1) {
-		const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-		if (lane >= o) incl += t;
-	}
-	const uint32_t warp_total = __shfl_sync(0xFFFFFFFFu, incl, 31);
-	uint32_t warp_base = 0;
-	if (lane == 0 && warp_total > 0) warp_base = atomicAdd(&counters->n_samples, warp_total);
-	warp_base = __shfl_sync(0xFFFFFFFFu, warp_base, 0);
-	const uint32_t base = warp_base + incl - numsteps;
-	const bool keep = numsteps > 0 && (base + numsteps <= max_samples);
-	const uint32_t keep_mask = __ballot_sync(0xFFFFFFFFu, keep);
-	uint32_t ray_base = 0;
-	if (lane == 0 && keep_mask) ray_base = atomicAdd(&counters->n_rays, __popc(keep_mask));
-	ray_base = __shfl_sync(0xFFFFFFFFu, ray_base, 0);
-	const uint32_t ray_idx = ray_base + __popc(keep_mask & ((1u << lane) - 1u));
-	const uint32_t n_write = !keep ? 0u : (WRITE_ALL ? numsteps : (numsteps < prefix ? numsteps : prefix));
-	if (keep) {
-		ray_indices_out[ray_idx] = i;
-		float* r = rays_out + (size_t)ray_idx * 6;
-		r[0] = ro.x; r[1] = ro.y; r[2] = ro.z; r[3] = rd.x; r[4] = rd.y; r[5] = rd.z;
-		numsteps_out[ray_idx * 2 + 0] = numsteps;
-		numsteps_out[ray_idx * 2 + 1] = base;
-	}
-
-	// pass 2a: the warp writes the coordinates of the samples whose t is in shared memory, ray after ray
-	__syncwarp();
-	const uint32_t n_listed = n_write < GEN_T_SLOTS ? n_write : GEN_T_SLOTS;
-	const uint32_t warp_col0 = threadIdx.x & ~31u;
-	for (uint32_t src = 0; src < 32; ++src) {
-		const uint32_t n_s = __shfl_sync(0xFFFFFFFFu, n_listed, src);
-		if (n_s == 0) continue;  // warp-uniform
-		const uint32_t base_s = __shfl_sync(0xFFFFFFFFu, base, src);
-		const V3 ro_s{__shfl_sync(0xFFFFFFFFu, ro.x, src), __shfl_sync(0xFFFFFFFFu, ro.y, src), __shfl_sync(0xFFFFFFFFu, ro.z, src)};
-		const V3 rdn_s{__shfl_sync(0xFFFFFFFFu, rdn.x, src), __shfl_sync(0xFFFFFFFFu, rdn.y, src), __shfl_sync(0xFFFFFFFFu, rdn.z, src)};
-		const V3 wdir = warp_direction(rdn_s);
-		// 32 records of 28 bytes = 224 consecutive floats: transposed through shared memory so that every store instruction of the
-		// warp covers 128 contiguous bytes (per-lane 4-byte stores at a 28-byte stride hit 32 sectors each: the L2 write path,
-		// not the march, was then what this pass waited for)
-		float* tile = coord_tile[threadIdx.x >> 5];
-		for (uint32_t k0 = 0; k0 < n_s; k0 += 32) {
-			const uint32_t k = k0 + lane;
-			__syncwarp();
-			if (k < n_s) {
-				const float t = t_list[k * GEN_THREADS + warp_col0 + src];
-				const V3 pos = ro_s + t * rdn_s;
-				const float dt = calc_dt(t, cfg.march);
-				const V3 wp = warp_position(pos, aabb);
-				float* c = tile + lane * 7;
-				c[0] = wp.x; c[1] = wp.y; c[2] = wp.z; c[3] = warp_dt(dt); c[4] = wdir.x; c[5] = wdir.y; c[6] = wdir.z;
-			}
-			__syncwarp();
-			const uint32_t cnt = ((n_s - k0) < 32u ? (n_s - k0) : 32u) * 7u;
-			float* dst = coords_out + (size_t)(base_s + k0) * 7;
-#pragma unroll
-			for (uint32_t q = 0; q < 7; ++q) {
-				const uint32_t e = q * 32u + lane;
-				if (e < cnt) dst[e] = tile[e];
-			}
-		}
-	}
-
-	// pass 2b: the tails (samples beyond GEN_T_SLOTS) of the warp's long rays, cut into GEN_SEG-sample segments; lane l of round
-	// r re-marches segment 32 r + l from its checkpoint
-	{
-		const uint32_t n_tail = n_write > GEN_T_SLOTS ? n_write - GEN_T_SLOTS : 0u;
-		const uint32_t nseg = (n_tail + GEN_SEG - 1u) / GEN_SEG;
-		uint32_t seg_incl = nseg;
-#pragma unroll
-		for (uint32_t o = 1; o < 32; o <<= 1) {
-			const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, seg_incl, o);
-			if (lane >= o) seg_incl += v;
-		}
-		const uint32_t total_seg = __shfl_sync(0xFFFFFFFFu, seg_incl, 31);
-		for (uint32_t s0 = 0; s0 < total_seg; s0 += 32) {
-			const uint32_t sidx = s0 + lane;
-			const bool active = sidx < total_seg;
-			const uint32_t sq = active ? sidx : total_seg - 1u;
-			// owner = first lane whose inclusive segment count exceeds sq
-			uint32_t owner = 0;
-#pragma unroll
-			for (uint32_t step = 16; step >= 1; step >>= 1) {
-				const uint32_t cand = owner + step;
-				const uint32_t v = __shfl_sync(0xFFFFFFFFu, seg_incl, (cand - 1u) & 31u);
-				if (cand <= 31u && v <= sq) owner = cand;
-			}
-			const uint32_t o_incl = __shfl_sync(0xFFFFFFFFu, seg_incl, owner), o_nseg = __shfl_sync(0xFFFFFFFFu, nseg, owner);
-			const uint32_t m = sq - (o_incl - o_nseg);
-			const uint32_t o_base = __shfl_sync(0xFFFFFFFFu, base, owner), o_n = __shfl_sync(0xFFFFFFFFu, n_write, owner);
-			const V3 o_ro{__shfl_sync(0xFFFFFFFFu, ro.x, owner), __shfl_sync(0xFFFFFFFFu, ro.y, owner), __shfl_sync(0xFFFFFFFFu, ro.z, owner)};
-			const V3 o_rdn{__shfl_sync(0xFFFFFFFFu, rdn.x, owner), __shfl_sync(0xFFFFFFFFu, rdn.y, owner), __shfl_sync(0xFFFFFFFFu, rdn.z, owner)};
-			if (!active) continue;
-			const V3 o_idir{1.0f / o_rdn.x, 1.0f / o_rdn.y, 1.0f / o_rdn.z};
-			const V3 wdir = warp_direction(o_rdn);
-			float t = ckpt[m * GEN_THREADS + warp_col0 + owner];
-			uint32_t j = GEN_T_SLOTS + m * GEN_SEG;
-			const uint32_t j_end = (j + GEN_SEG < o_n) ? j + GEN_SEG : o_n;
-			float* co = coords_out + (size_t)o_base * 7;
-			V3 pos;
-			OccCache occ;
-			while (aabb.contains(pos = o_ro + t * o_rdn) && j < j_end) {
-				const float dt = calc_dt(t, cfg.march);
-				const uint32_t mip = mip_from_dt(dt, pos, cfg.max_cascade);
-				if (density_grid_occupied_cached(pos, bitfield, mip, occ)) {
-					const V3 wp = warp_position(pos, aabb);
-					float* c = co + (size_t)j * 7;
-					c[0] = wp.x; c[1] = wp.y; c[2] = wp.z; c[3] = warp_dt(dt); c[4] = wdir.x; c[5] = wdir.y; c[6] = wdir.z;
-					++j;
-					t += dt;
-				} else {
-					t = advance_to_next_voxel(t, cfg.march, pos, o_rdn, o_idir, mip);
-				}
-			}
-		}
-	}
-	if (!WRITE_ALL && keep) {
-		// where the consumer resumes the march: the loop state right after the last written sample (its t plus its dt), or the
-		// first sample itself when nothing was written.  prefix <= GEN_T_SLOTS (checked by the launcher), so it is in the list.
-		float t = 0.0f;
-		if (n_write < numsteps) {
-			if (n_write == 0) {
-				t = t_list[threadIdx.x];
-			} else {
-				const float tl = t_list[(n_write - 1) * GEN_THREADS + threadIdx.x];
-				t = tl + calc_dt(tl, cfg.march);
-			}
-		}
-		t_resume_out[ray_idx] = t;
-	}
-}
-
-// ------------------------------------------------------------------------------------------------------------------
-// Ordering the rays of a batch by expected march length.
-// One thread marches one ray and the rays of a batch differ 4x in length (background rays skip through an empty cube, rays
-// through the object take hundreds of samples): in batch order a warp keeps 14.7 of its 32 lanes busy (ncu r1c) and, with only
-// 57 K rays for 300 K lanes, nothing hides that.  Which thread marches which ray is free (slot order is atomics-dependent in the
-// reference as well), so the batch is bucketed by an estimate of each ray's loop trips: 24 probes along the ray against the
-// occupancy bitfield coarsened to 16^3 (a coarse cell = 64 consecutive Morton-ordered bytes), occupied stretches counted in
-// steps, empty ones in voxel skips.  Three small kernels (keys + histogram, scan, scatter) produce the permutation; longest first.
-// The rays, their sample counts and their coordinates are unchanged — only their slots move.
-// ------------------------------------------------------------------------------------------------------------------
-constexpr uint32_t SORT_BUCKETS = 64;
-constexpr float SORT_TRIPS_PER_BUCKET = 16.0f;
-constexpr uint32_t SORT_PROBES = 24;
-
-__device__ inline bool coarse_cell_occupied(V3 pos, const uint8_t* __restrict__ bitfield, uint32_t mip) {
-	const float mip_scale = scalbnf(1.0f, -(int)mip);
-	const float px = (pos.x - 0.5f) * mip_scale + 0.5f, py = (pos.y - 0.5f) * mip_scale + 0.5f, pz = (pos.z - 0.5f) * mip_scale + 0.5f;
-	const int ix = (int)(px * 16.0f), iy = (int)(py * 16.0f), iz = (int)(pz * 16.0f);
-	if (ix < 0 || ix >= 16 || iy < 0 || iy >= 16 || iz < 0 || iz >= 16) return false;
-	const uint4* p = reinterpret_cast<const uint4*>(bitfield + (size_t)(GRID_N_CELLS / 8) * mip + (size_t)morton3d((uint32_t)ix, (uint32_t)iy, (uint32_t)iz) * 64u);
-	uint32_t any = 0;
-#pragma unroll
-	for (int k = 0; k < 4; ++k) {
-		const uint4 v = __ldg(p + k);
-		any |= v.x | v.y | v.z | v.w;
-	}
-	return any != 0;
-}
-
-__global__ void __launch_bounds__(GEN_THREADS) k_ray_sort_keys(
-	const uint32_t n_rays_local, const uint32_t ray_offset, const uint32_t n_rays_global, Pcg32 rng_in, const ngp_nerf_train_cfg cfg,
-	const ngp_train_view* __restrict__ views, const uint32_t n_views, const uint8_t* __restrict__ bitfield, uint8_t* __restrict__ keys, uint32_t* __restrict__ hist
-) {
-	__shared__ uint32_t local_hist[SORT_BUCKETS];
-	if (threadIdx.x < SORT_BUCKETS) local_hist[threadIdx.x] = 0;
-	__syncthreads();
-	const uint32_t li = blockIdx.x * blockDim.x + threadIdx.x;
-	if (li < n_rays_local) {
-		const uint32_t i = ray_offset + li;
-		const Aabb aabb{V3{cfg.aabb_min[0], cfg.aabb_min[1], cfg.aabb_min[2]}, V3{cfg.aabb_max[0], cfg.aabb_max[1], cfg.aabb_max[2]}};
-		const uint32_t img = image_idx(i, n_rays_global, n_views);
-		const ngp_train_view vw = views[img];
-		Pcg32 rng = rng_in;
-		rng.advance((uint64_t)i * N_MAX_RANDOM_SAMPLES_PER_RAY);
-		float u, v;
-		random_image_pos_training(rng, vw.width, vw.height, cfg.snap_to_pixel_centers != 0, u, v);
-		V3 ro, rd;
+	static __device__ __forceinline__ V3 warp_position(V3 p, const Aabb& b) { return ngpb::warp_position(p, b); }
+	static __device__ __forceinline__ V3 warp_direction(V3 d) { return ngpb::warp_direction(d); }
+	static __device__ __forceinline__ float warp_dt(float dt) { return ngpb::warp_dt(dt); }
+	static __device__ __forceinline__ void random_image_pos(Pcg32& rng, int w, int h, bool snap, float& u, float& v) { random_image_pos_training(rng, w, h, snap, u, v); }
+	static __device__ __forceinline__ void make_ray(const ngp_train_view& vw, float u, float v, const Aabb& aabb, const Ctx& c, Pcg32& rng, V3& ro, V3& rd, V3& rdn,
+		V3& idir, float& startt) {
 		uv_to_ray(u, v, vw.width, vw.height, vw.focal_x, vw.focal_y, vw.principal_x, vw.principal_y, vw.lens_mode, vw.lens_params, vw.xform, ro, rd);
-		const V3 rdn = normalize3(rd);
+		rdn = normalize3(rd);
 		float tmin, tmax;
 		aabb_ray_intersect(aabb, ro, rdn, tmin, tmax);
 		tmin = fmaxf(tmin, 0.0f);
-		float trips = 0.0f;
-		if (tmax > tmin) {
-			const float seg = (tmax - tmin) / (float)SORT_PROBES;
-			for (uint32_t k = 0; k < SORT_PROBES; ++k) {
-				const float t = tmin + ((float)k + 0.5f) * seg;
-				const V3 pos = ro + t * rdn;
-				const uint32_t mip = mip_from_pos(pos, cfg.max_cascade);
-				if (coarse_cell_occupied(pos, bitfield, mip)) trips += seg / calc_dt(t, cfg.march);
-				else trips += seg * 128.0f * scalbnf(1.0f, -(int)mip);   // one trip per cell of that cascade
-			}
-		}
-		const uint32_t key = (uint32_t)fminf(trips / SORT_TRIPS_PER_BUCKET, (float)(SORT_BUCKETS - 1));
-		keys[li] = (uint8_t)key;
-		atomicAdd(&local_hist[key], 1u);
+		startt = advance_n_steps(tmin, c.m, rng.next_float());
+		idir = V3{1.0f / rdn.x, 1.0f / rdn.y, 1.0f / rdn.z};
 	}
-	__syncthreads();
-	if (threadIdx.x < SORT_BUCKETS && local_hist[threadIdx.x]) atomicAdd(&hist[threadIdx.x], local_hist[threadIdx.x]);
-}
+};
 
-// state: hist[64] | base[64] | cursor[64]; longest bucket first
-__global__ void k_ray_sort_scan(uint32_t* __restrict__ state) {
-	if (threadIdx.x != 0) return;
-	uint32_t acc = 0;
-	for (int b = (int)SORT_BUCKETS - 1; b >= 0; --b) {
-		state[SORT_BUCKETS + b] = acc;
-		acc += state[b];
-		state[2 * SORT_BUCKETS + b] = 0;
-	}
-}
+void generate_training_samples_ref(cudaStream_t stream, uint32_t n_rays_local, uint32_t ray_offset, uint32_t n_rays_global, uint64_t rng_state,
+	uint64_t rng_inc, const ngp_nerf_train_cfg& cfg, const ngp_train_view* views, uint32_t n_views, const uint8_t* bitfield, uint32_t max_samples,
+	ngp_nerf_counters* counters, uint32_t* ray_indices, float* rays, uint32_t* numsteps, float* coords);   // march_ref.cu
 
-__global__ void __launch_bounds__(GEN_THREADS) k_ray_sort_scatter(const uint32_t n_rays_local, const uint8_t* __restrict__ keys, uint32_t* __restrict__ state,
-	uint32_t* __restrict__ perm) {
-	const uint32_t li = blockIdx.x * blockDim.x + threadIdx.x;
-	if (li >= n_rays_local) return;
-	const uint32_t key = keys[li];
-	const uint32_t slot = state[SORT_BUCKETS + key] + atomicAdd(&state[2 * SORT_BUCKETS + key], 1u);
-	perm[slot] = li;
-}
-
-size_t ray_sort_scratch_bytes(uint32_t max_rays) { return (size_t)max_rays * 4 + next_multiple(max_rays, 16u) + 3 * SORT_BUCKETS * 4; }
-
-// perm_out: [n_rays_local] u32 (also the start of `scratch`): scratch = perm | keys | state
-const uint32_t* sort_training_rays(cudaStream_t stream, uint32_t n_rays_local, uint32_t ray_offset, uint32_t n_rays_global, uint64_t rng_state, uint64_t rng_inc,
-	const ngp_nerf_train_cfg& cfg, const ngp_train_view* views, uint32_t n_views, const uint8_t* bitfield, void* scratch, uint32_t max_rays) {
-	if (n_rays_local == 0) return nullptr;
-	uint32_t* perm = reinterpret_cast<uint32_t*>(scratch);
-	uint8_t* keys = reinterpret_cast<uint8_t*>(scratch) + (size_t)max_rays * 4;
-	uint32_t* state = reinterpret_cast<uint32_t*>(keys + next_multiple(max_rays, 16u));
-	NGPB_CUDA_CHECK(cudaMemsetAsync(state, 0, SORT_BUCKETS * 4, stream));
-	const uint32_t blocks = div_round_up(n_rays_local, GEN_THREADS);
-	k_ray_sort_keys<<<blocks, GEN_THREADS, 0, stream>>>(n_rays_local, ray_offset, n_rays_global, Pcg32(rng_state, rng_inc, true), cfg, views, n_views, bitfield, keys, state);
-	k_ray_sort_scan<<<1, 32, 0, stream>>>(state);
-	k_ray_sort_scatter<<<blocks, GEN_THREADS, 0, stream>>>(n_rays_local, keys, state, perm);
-	NGPB_LAUNCHED(); NGPB_LAUNCHED(); NGPB_LAUNCHED();
-	NGPB_CUDA_CHECK(cudaGetLastError());
-	return perm;
-}
-
-// ------------------------------------------------------------------------------------------------------------------
-// The generator as two kernels, for the training pipeline (testbed.cu):
-//   k_count_training_samples   ray generation + the counting march + slot reservation.  One thread per ray; its time is the
-//                              serial latency of the batch's longest ray (~0.4 ms), not throughput — it needs no shared memory
-//                              and 64 registers, so it can run beside the previous step's backward kernel and optimizer.  Every
-//                              GEN_SEG-th sample's t goes to a global checkpoint table.
-//   k_write_training_samples   one WARP per ray, lane m re-marches samples [32 m, 32 m + 32) from checkpoint m with the same
-//                              arithmetic: all of a step's coordinates in ~32 sequential march steps.
-// Outputs are those of k_generate_training_samples (same per-ray counts, records and coordinates; slot order differs).
-// ------------------------------------------------------------------------------------------------------------------
-constexpr uint32_t GEN_MAX_SEG = NGP_NERF_STEPS / GEN_SEG;   // 32 checkpoints per ray
-
-__global__ void __launch_bounds__(GEN_THREADS) k_count_training_samples(
-	const uint32_t n_rays_local, const uint32_t ray_offset, const uint32_t n_rays_global, Pcg32 rng_in, const ngp_nerf_train_cfg cfg,
-	const ngp_train_view* __restrict__ views, const uint32_t n_views, const uint8_t* __restrict__ bitfield, const uint32_t max_samples,
-	ngp_nerf_counters* __restrict__ counters, uint32_t* __restrict__ ray_indices_out, float* __restrict__ rays_out,
-	uint32_t* __restrict__ numsteps_out, float* __restrict__ ckpt_out, uint32_t* __restrict__ seg_info_out
-) {
-	const uint32_t li = blockIdx.x * blockDim.x + threadIdx.x;
-	const uint32_t lane = threadIdx.x & 31u;
-	const bool in_range = li < n_rays_local;
-	const uint32_t i = ray_offset + li;
-	const Aabb aabb{V3{cfg.aabb_min[0], cfg.aabb_min[1], cfg.aabb_min[2]}, V3{cfg.aabb_max[0], cfg.aabb_max[1], cfg.aabb_max[2]}};
-	uint32_t numsteps = 0;
-	V3 ro{0, 0, 0}, rd{0, 0, 0};
-
-	if (in_range) {
-		const uint32_t img = image_idx(i, n_rays_global, n_views);
-		const ngp_train_view vw = views[img];
-		Pcg32 rng = rng_in;
-		rng.advance((uint64_t)i * N_MAX_RANDOM_SAMPLES_PER_RAY);
-		float u, v;
-		random_image_pos_training(rng, vw.width, vw.height, cfg.snap_to_pixel_centers != 0, u, v);
-		const bool masked = !vw.no_mask && read_rgba_uv(u, v, vw.width, vw.height, vw.pixels, vw.image_type).r < 0.0f;
-		if (!masked) {
-			(void)rng.next_float();  // motion-blur time (testbed_nerf.cu:740)
-			uv_to_ray(u, v, vw.width, vw.height, vw.focal_x, vw.focal_y, vw.principal_x, vw.principal_y, vw.lens_mode, vw.lens_params, vw.xform, ro, rd);
-			const V3 rdn = normalize3(rd);
-			float tmin, tmax;
-			aabb_ray_intersect(aabb, ro, rdn, tmin, tmax);
-			tmin = fmaxf(tmin, 0.0f);
-			const float startt = advance_n_steps(tmin, cfg.march, rng.next_float());
-			const V3 idir{1.0f / rdn.x, 1.0f / rdn.y, 1.0f / rdn.z};
-			float* ck = ckpt_out + (size_t)li * GEN_MAX_SEG;
-			uint32_t j = 0;
-			float t = startt;
-			V3 pos;
-			OccCache occ;
-			while (aabb.contains(pos = ro + t * rdn) && j < NGP_NERF_STEPS) {
-				const float dt = calc_dt(t, cfg.march);
-				const uint32_t mip = mip_from_dt(dt, pos, cfg.max_cascade);
-				if (density_grid_occupied_cached(pos, bitfield, mip, occ)) {
-					if ((j & (GEN_SEG - 1u)) == 0u) ck[j / GEN_SEG] = t;   // resuming the loop at this t finds sample j first
-					++j;
-					t += dt;
-				} else {
-					t = advance_to_next_voxel(t, cfg.march, pos, rdn, idir, mip);
-				}
-			}
-			numsteps = j;
-		}
-	}
-
-	// ---- warp-level reservation of sample slots and ray slots (as k_generate_training_samples)
-	uint32_t incl = numsteps;
-#pragma unroll
-	for (uint32_t o = 1; o < 32; o <<= 1) {
-		const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-		if (lane >= o) incl += t;
-	}
-	const uint32_t warp_total = __shfl_sync(0xFFFFFFFFu, incl, 31);
-	uint32_t warp_base = 0;
-	if (lane == 0 && warp_total > 0) warp_base = atomicAdd(&counters->n_samples, warp_total);
-	warp_base = __shfl_sync(0xFFFFFFFFu, warp_base, 0);
-	const uint32_t base = warp_base + incl - numsteps;
-	const bool keep = numsteps > 0 && (base + numsteps <= max_samples);
-	const uint32_t keep_mask = __ballot_sync(0xFFFFFFFFu, keep);
-	uint32_t ray_base = 0;
-	if (lane == 0 && keep_mask) ray_base = atomicAdd(&counters->n_rays, __popc(keep_mask));
-	ray_base = __shfl_sync(0xFFFFFFFFu, ray_base, 0);
-	const uint32_t ray_idx = ray_base + __popc(keep_mask & ((1u << lane) - 1u));
-	if (in_range) {
-		seg_info_out[(size_t)li * 3 + 0] = keep ? numsteps : 0u;
-		seg_info_out[(size_t)li * 3 + 1] = base;
-		seg_info_out[(size_t)li * 3 + 2] = ray_idx;
-	}
-	if (!keep) return;
-	ray_indices_out[ray_idx] = i;
-	float* r = rays_out + (size_t)ray_idx * 6;
-	r[0] = ro.x; r[1] = ro.y; r[2] = ro.z; r[3] = rd.x; r[4] = rd.y; r[5] = rd.z;
-	numsteps_out[ray_idx * 2 + 0] = numsteps;
-	numsteps_out[ray_idx * 2 + 1] = base;
-}
-
-__global__ void __launch_bounds__(GEN_THREADS) k_write_training_samples(
-	const uint32_t n_rays_local, const ngp_nerf_train_cfg cfg, const uint8_t* __restrict__ bitfield, const float* __restrict__ rays_in,
-	const float* __restrict__ ckpt_in, const uint32_t* __restrict__ seg_info_in, float* __restrict__ coords_out
-) {
-	const uint32_t li = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;   // one warp per ray
-	const uint32_t m = threadIdx.x & 31u;                               // one lane per 32-sample segment
-	if (li >= n_rays_local) return;
-	const uint32_t n = seg_info_in[(size_t)li * 3 + 0];
-	if (m * GEN_SEG >= n) return;
-	const uint32_t base = seg_info_in[(size_t)li * 3 + 1], ray_idx = seg_info_in[(size_t)li * 3 + 2];
-	const Aabb aabb{V3{cfg.aabb_min[0], cfg.aabb_min[1], cfg.aabb_min[2]}, V3{cfg.aabb_max[0], cfg.aabb_max[1], cfg.aabb_max[2]}};
-	const float* rp = rays_in + (size_t)ray_idx * 6;
-	const V3 ro{rp[0], rp[1], rp[2]};
-	const V3 rdn = normalize3(V3{rp[3], rp[4], rp[5]});
-	const V3 idir{1.0f / rdn.x, 1.0f / rdn.y, 1.0f / rdn.z};
-	const V3 wdir = warp_direction(rdn);
-	float t = ckpt_in[(size_t)li * GEN_MAX_SEG + m];
-	uint32_t j = m * GEN_SEG;
-	const uint32_t j_end = (j + GEN_SEG < n) ? j + GEN_SEG : n;
-	float* co = coords_out + (size_t)base * 7;
-	V3 pos;
-	OccCache occ;
-	while (aabb.contains(pos = ro + t * rdn) && j < j_end) {
-		const float dt = calc_dt(t, cfg.march);
-		const uint32_t mip = mip_from_dt(dt, pos, cfg.max_cascade);
-		if (density_grid_occupied_cached(pos, bitfield, mip, occ)) {
-			const V3 wp = warp_position(pos, aabb);
-			float* c = co + (size_t)j * 7;
-			c[0] = wp.x; c[1] = wp.y; c[2] = wp.z; c[3] = warp_dt(dt); c[4] = wdir.x; c[5] = wdir.y; c[6] = wdir.z;
-			++j;
-			t += dt;
-		} else {
-			t = advance_to_next_voxel(t, cfg.march, pos, rdn, idir, mip);
-		}
-	}
+// cfg.math_mode selects the flavour: NGP_MATH_DETERMINISTIC (0) or NGP_MATH_REFERENCE (1)
+void generate_training_samples(cudaStream_t stream, uint32_t n_rays_local, uint32_t ray_offset, uint32_t n_rays_global, uint64_t rng_state,
+	uint64_t rng_inc, const ngp_nerf_train_cfg& cfg, const ngp_train_view* views, uint32_t n_views, const uint8_t* bitfield, uint32_t max_samples,
+	ngp_nerf_counters* counters, uint32_t* ray_indices, float* rays, uint32_t* numsteps, float* coords) {
+	if (cfg.math_mode == NGP_MATH_REFERENCE)
+		generate_training_samples_ref(stream, n_rays_local, ray_offset, n_rays_global, rng_state, rng_inc, cfg, views, n_views, bitfield, max_samples, counters,
+			ray_indices, rays, numsteps, coords);
+	else
+		launch_generate_training_samples<DetMarch>(stream, n_rays_local, ray_offset, n_rays_global, rng_state, rng_inc, cfg, views, n_views, bitfield, max_samples,
+			counters, ray_indices, rays, numsteps, coords);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -932,52 +467,6 @@ void nerf_density(const ngp_nerf_desc& d, cudaStream_t stream, uint32_t n, const
 
 static Aabb cfg_aabb(const ngp_nerf_train_cfg& cfg) {
 	return Aabb{V3{cfg.aabb_min[0], cfg.aabb_min[1], cfg.aabb_min[2]}, V3{cfg.aabb_max[0], cfg.aabb_max[1], cfg.aabb_max[2]}};
-}
-
-void generate_training_samples(cudaStream_t stream, uint32_t n_rays_local, uint32_t ray_offset, uint32_t n_rays_global, uint64_t rng_state,
-	uint64_t rng_inc, const ngp_nerf_train_cfg& cfg, const ngp_train_view* views, uint32_t n_views, const uint8_t* bitfield, uint32_t max_samples,
-	ngp_nerf_counters* counters, uint32_t* ray_indices, float* rays, uint32_t* numsteps, float* coords, float* t_resume, uint32_t prefix, const uint32_t* perm) {
-	if (n_rays_local == 0) return;
-	NGPB_CHECK(n_views > 0, "generate_training_samples: no training views");
-	NGPB_CHECK(coords != nullptr, "generate_training_samples: no coordinate buffer");
-	static bool attr_set = false;
-	if (!attr_set) {
-		NGPB_CUDA_CHECK(cudaFuncSetAttribute(k_generate_training_samples<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEN_SMEM_BYTES));
-		NGPB_CUDA_CHECK(cudaFuncSetAttribute(k_generate_training_samples<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEN_SMEM_BYTES));
-		attr_set = true;
-	}
-	if (!t_resume) {
-		k_generate_training_samples<true><<<div_round_up(n_rays_local, GEN_THREADS), GEN_THREADS, GEN_SMEM_BYTES, stream>>>(n_rays_local, ray_offset, n_rays_global,
-			Pcg32(rng_state, rng_inc, true), cfg, views, n_views, bitfield, max_samples, counters, ray_indices, rays, numsteps, coords, nullptr, 0u, perm);
-	} else {
-		NGPB_CHECK(prefix % 8u == 0u && prefix <= GEN_T_SLOTS, "generate_training_samples: the eager prefix must be a multiple of 8, at most 64");
-		k_generate_training_samples<false><<<div_round_up(n_rays_local, GEN_THREADS), GEN_THREADS, GEN_SMEM_BYTES, stream>>>(n_rays_local, ray_offset, n_rays_global,
-			Pcg32(rng_state, rng_inc, true), cfg, views, n_views, bitfield, max_samples, counters, ray_indices, rays, numsteps, coords, t_resume, prefix, perm);
-	}
-	NGPB_LAUNCHED();
-	NGPB_CUDA_CHECK(cudaGetLastError());
-}
-
-size_t generator_scratch_floats(uint32_t max_rays) { return (size_t)max_rays * GEN_MAX_SEG; }   // checkpoint table
-size_t generator_scratch_u32(uint32_t max_rays) { return (size_t)max_rays * 3; }                 // (count, base, ray slot) per ray
-
-void count_training_samples(cudaStream_t stream, uint32_t n_rays_local, uint32_t ray_offset, uint32_t n_rays_global, uint64_t rng_state, uint64_t rng_inc,
-	const ngp_nerf_train_cfg& cfg, const ngp_train_view* views, uint32_t n_views, const uint8_t* bitfield, uint32_t max_samples, ngp_nerf_counters* counters,
-	uint32_t* ray_indices, float* rays, uint32_t* numsteps, float* ckpt, uint32_t* seg_info) {
-	if (n_rays_local == 0) return;
-	NGPB_CHECK(n_views > 0, "generate_training_samples: no training views");
-	k_count_training_samples<<<div_round_up(n_rays_local, GEN_THREADS), GEN_THREADS, 0, stream>>>(n_rays_local, ray_offset, n_rays_global,
-		Pcg32(rng_state, rng_inc, true), cfg, views, n_views, bitfield, max_samples, counters, ray_indices, rays, numsteps, ckpt, seg_info);
-	NGPB_LAUNCHED();
-	NGPB_CUDA_CHECK(cudaGetLastError());
-}
-
-void write_training_samples(cudaStream_t stream, uint32_t n_rays_local, const ngp_nerf_train_cfg& cfg, const uint8_t* bitfield, const float* rays, const float* ckpt,
-	const uint32_t* seg_info, float* coords) {
-	if (n_rays_local == 0) return;
-	k_write_training_samples<<<div_round_up(n_rays_local * 32u, GEN_THREADS), GEN_THREADS, 0, stream>>>(n_rays_local, cfg, bitfield, rays, ckpt, seg_info, coords);
-	NGPB_LAUNCHED();
-	NGPB_CUDA_CHECK(cudaGetLastError());
 }
 
 void compute_loss(cudaStream_t stream, uint32_t n_rays_local, uint32_t n_rays_global, uint64_t rng_state, uint64_t rng_inc,

@@ -260,4 +260,71 @@ __host__ __device__ inline void uv_to_ray(float u, float v, int w, int h, float 
 __host__ __device__ inline int imin(int a, int b) { return a < b ? a : b; }
 __host__ __device__ inline int imax(int a, int b) { return a > b ? a : b; }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// image access (common_device.cuh:776-872), shared by the sample generator (mask test) and the loss kernel (target colour)
+// ------------------------------------------------------------------------------------------------------------------
+struct Rgba {
+	float r, g, b, a;
+};
+__device__ inline Rgba read_rgba_px(int px, int py, int w, const void* pixels, uint32_t type) {
+	const size_t idx = (size_t)px + (size_t)py * (size_t)w;
+	switch (type) {
+		case NGP_IMAGE_BYTE: {
+			const uint32_t val = reinterpret_cast<const uint32_t*>(pixels)[idx];
+			if (val == 0x00FF00FFu) return Rgba{-1.0f, -1.0f, -1.0f, -1.0f};
+			const float a = (float)((val >> 24) & 0xFFu) * (1.0f / 255.0f);
+			Rgba o;
+			o.r = srgb_to_linear((float)(val & 0xFFu) * (1.0f / 255.0f)) * a;
+			o.g = srgb_to_linear((float)((val >> 8) & 0xFFu) * (1.0f / 255.0f)) * a;
+			o.b = srgb_to_linear((float)((val >> 16) & 0xFFu) * (1.0f / 255.0f)) * a;
+			o.a = a;
+			return o;
+		}
+		case NGP_IMAGE_HALF: {
+			const uint2 v = reinterpret_cast<const uint2*>(pixels)[idx];
+			const __half2 lo = *reinterpret_cast<const __half2*>(&v.x), hi = *reinterpret_cast<const __half2*>(&v.y);
+			return Rgba{__low2float(lo), __high2float(lo), __low2float(hi), __high2float(hi)};
+		}
+		case NGP_IMAGE_FLOAT: {
+			const float4 v = reinterpret_cast<const float4*>(pixels)[idx];
+			return Rgba{v.x, v.y, v.z, v.w};
+		}
+		default: return Rgba{5.0f, 0.0f, 0.0f, 1.0f};
+	}
+}
+__device__ inline Rgba read_rgba_uv(float u, float v, int w, int h, const void* pixels, uint32_t type) {
+	const int px = imin(imax((int)(u * (float)w), 0), w - 1);
+	const int py = imin(imax((int)(v * (float)h), 0), h - 1);
+	return read_rgba_px(px, py, w, pixels, type);
+}
+// is the pixel under (u, v) masked away (read_rgba(...).x < 0, testbed_nerf.cu:732-736)?  Only the sign of red matters, so the
+// colour conversion of read_rgba is skipped: a Byte pixel is negative iff it is MASK_COLOR, half / float pixels carry their sign.
+__device__ inline bool pixel_is_masked(float u, float v, int w, int h, const void* pixels, uint32_t type) {
+	const int px = imin(imax((int)(u * (float)w), 0), w - 1);
+	const int py = imin(imax((int)(v * (float)h), 0), h - 1);
+	const size_t idx = (size_t)px + (size_t)py * (size_t)w;
+	switch (type) {
+		case NGP_IMAGE_BYTE: return reinterpret_cast<const uint32_t*>(pixels)[idx] == 0x00FF00FFu;
+		case NGP_IMAGE_HALF: return __half2float(reinterpret_cast<const __half*>(pixels)[idx * 4]) < 0.0f;
+		case NGP_IMAGE_FLOAT: return reinterpret_cast<const float*>(pixels)[idx * 4] < 0.0f;
+		default: return false;
+	}
+}
+
+// nerf_device.cuh:578-599 (uniform branch): neighbouring rays of a batch look at the same image
+__host__ __device__ inline uint32_t image_idx(uint32_t base_idx, uint32_t n_rays, uint32_t n_images) {
+	return ((base_idx * n_images) / n_rays) % n_images;  // uint32 arithmetic, as the reference
+}
+
+// nerf_device.cuh:553-576 (no error-map CDF)
+__device__ inline void random_image_pos_training(Pcg32& rng, int w, int h, bool snap, float& u, float& v) {
+	u = rng.next_float();
+	v = rng.next_float();
+	if (snap) {
+		u = ((float)imin(imax((int)(u * (float)w), 0), w - 1) + 0.5f) / (float)w;
+		v = ((float)imin(imax((int)(v * (float)h), 0), h - 1) + 0.5f) / (float)h;
+	}
+}
+
 }  // namespace ngpb

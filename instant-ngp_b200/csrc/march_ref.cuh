@@ -47,7 +47,7 @@ __device__ __forceinline__ float length2(V3 a) {
 }
 // normalize (vec.h:467-476): v / sqrt(length2(v))
 __device__ __forceinline__ V3 normalize(V3 v) {
-	const float len = sqrtf(length2(v));
+	const float len = sqrtf(refm::length2(v));
 	if (len <= 0.0f) return V3{1.0f, 0.0f, 0.0f};
 	return V3{v.x / len, v.y / len, v.z / len};
 }
@@ -244,8 +244,8 @@ __device__ __forceinline__ float from_stepping_space(float n, float cone_angle) 
 		return (n - b) * MAX_CONE_STEPSIZE() + bt;
 	}
 }
-__device__ __forceinline__ float advance_n_steps(float t, float cone_angle, float n) { return from_stepping_space(to_stepping_space(t, cone_angle) + n, cone_angle); }
-__device__ __forceinline__ float calc_dt(float t, float cone_angle) { return advance_n_steps(t, cone_angle, 1.0f) - t; }
+__device__ __forceinline__ float advance_n_steps(float t, float cone_angle, float n) { return refm::from_stepping_space(refm::to_stepping_space(t, cone_angle) + n, cone_angle); }
+__device__ __forceinline__ float calc_dt(float t, float cone_angle) { return refm::advance_n_steps(t, cone_angle, 1.0f) - t; }
 
 __device__ __forceinline__ float sign1(float v) { return copysignf(1.0f, v); }   // vec.h:182
 
@@ -261,10 +261,10 @@ __device__ __forceinline__ float distance_to_next_voxel(V3 pos, V3 dir, V3 idir,
 // nerf_device.cuh:431-441
 __device__ __forceinline__ float advance_to_next_voxel(float t, float cone_angle, V3 pos, V3 dir, V3 idir, uint32_t mip) {
 	const float res = scalbnf(128.0f, -(int)mip);
-	float t_target = t + distance_to_next_voxel(pos, dir, idir, res);
-	t = to_stepping_space(t, cone_angle);
-	t_target = to_stepping_space(t_target, cone_angle);
-	return from_stepping_space(t + ceilf(fmaxf(t_target - t, 0.5f)), cone_angle);
+	float t_target = t + refm::distance_to_next_voxel(pos, dir, idir, res);
+	t = refm::to_stepping_space(t, cone_angle);
+	t_target = refm::to_stepping_space(t_target, cone_angle);
+	return refm::from_stepping_space(t + ceilf(fmaxf(t_target - t, 0.5f)), cone_angle);
 }
 
 // nerf_device.cuh:266-272, 291-293, 307-310

@@ -68,15 +68,121 @@ void render_pixel_offset(uint32_t spp, float* out) {
 	out[1] = oy - floorf(oy);
 }
 
-struct RenderSmemExtra {
-	uint32_t queue_base;
+// ---- arithmetic of the render march -----------------------------------------------------------------------------------------
+// RenderDet: march.cuh as is (ngp_detmath.h polynomials, IEEE division) — what the CPU oracle's render march reproduces bit for bit.
+// RenderFast: the same stepping functions on the SFU (lg2 / ex2 / rcp approximations), i.e. the instructions the reference build's
+//   --use_fast_math turns logf / expf / `/` into (nerf_device.cuh:379-441).  A voxel skip is two logs and one exp: 3 MUFU + ~20
+//   instructions instead of ~300 of polynomial arithmetic, and on an aabb_scale-4 scene a 1920x1080 frame makes ~4e8 of them.
+//   Positions agree with RenderDet to ~1e-6; it is the Testbed's default (`render_math`), the oracle tests pin RenderDet.
+struct RenderDet {
+	static __device__ __forceinline__ float calc_dt(float t, const ngp_march_consts& m) { return ngpb::calc_dt(t, m); }
+	static __device__ __forceinline__ float advance_n_steps(float t, const ngp_march_consts& m, float n) { return ngpb::advance_n_steps(t, m, n); }
+	static __device__ __forceinline__ float advance_to_next_voxel(float t, const ngp_march_consts& m, V3 pos, V3 dir, V3 idir, uint32_t mip) {
+		return ngpb::advance_to_next_voxel(t, m, pos, dir, idir, mip);
+	}
+	static __device__ __forceinline__ float expf_(float x) { return ngp_expf(x); }
+};
+struct RenderFast {
+	static __device__ __forceinline__ float to_step(float t, const ngp_march_consts& m) {
+		if (m.cone_angle <= 1e-5f) return t * (1.0f / min_cone_stepsize());
+		if (t <= m.at) return (t - m.at) * (1.0f / min_cone_stepsize()) + m.a;
+		if (t <= m.bt) return __fdividef(__logf(t), m.log1p_c);
+		return (t - m.bt) * (1.0f / max_cone_stepsize()) + m.b;
+	}
+	static __device__ __forceinline__ float from_step(float n, const ngp_march_consts& m) {
+		if (m.cone_angle <= 1e-5f) return n * min_cone_stepsize();
+		if (n <= m.a) return (n - m.a) * min_cone_stepsize() + m.at;
+		if (n <= m.b) return __expf(n * m.log1p_c);
+		return (n - m.b) * max_cone_stepsize() + m.bt;
+	}
+	static __device__ __forceinline__ float advance_n_steps(float t, const ngp_march_consts& m, float n) { return from_step(to_step(t, m) + n, m); }
+	static __device__ __forceinline__ float calc_dt(float t, const ngp_march_consts& m) { return advance_n_steps(t, m, 1.0f) - t; }
+	static __device__ __forceinline__ float advance_to_next_voxel(float t, const ngp_march_consts& m, V3 pos, V3 dir, V3 idir, uint32_t mip) {
+		const float res = scalbnf(128.0f, -(int)mip);
+		const float t_target = t + distance_to_next_voxel(pos, dir, idir, res);
+		const float n = to_step(t, m), n_target = to_step(t_target, m);
+		return from_step(n + ceilf(fmaxf(n_target - n, 0.5f)), m);
+	}
+	static __device__ __forceinline__ float expf_(float x) { return __expf(x); }
 };
 
-template <uint32_t F>
+// init_rays_with_payload_kernel_nerf (:1414-1528) for pixel q of the tile: pixel offset = ld_random_pixel_offset(snap ? 0 : sample_index),
+// the render camera's lens in uv_to_ray, near-plane offset, box entry and the jittered first step of advance_pos_nerf (:398-452).
+// Returns false for a ray that misses the render box.
+template <class M>
+__device__ __forceinline__ bool render_init_ray(const ngp_render_cfg& cfg, const Aabb& render_aabb, const int32_t y0, const uint32_t q, uint32_t& pix, V3& ro, V3& rd,
+	V3& idir, float& t) {
+	const uint32_t x = q % (uint32_t)cfg.width, y = (uint32_t)y0 + q / (uint32_t)cfg.width;
+	pix = x + (uint32_t)cfg.width * y;
+	const float u = ((float)x + cfg.pixel_offset[0]) / (float)cfg.width, v = ((float)y + cfg.pixel_offset[1]) / (float)cfg.height;
+	V3 o, d;
+	uv_to_ray(u, v, cfg.width, cfg.height, cfg.focal_x, cfg.focal_y, cfg.screen_x, cfg.screen_y, cfg.lens_mode, cfg.lens_params, cfg.camera, o, d);
+	o = o + d * cfg.near_distance;
+	d = normalize3(d);
+	ro = o;
+	rd = d;
+	idir = V3{1.0f / d.x, 1.0f / d.y, 1.0f / d.z};
+	float tmin, tmax;
+	aabb_ray_intersect(render_aabb, o, d, tmin, tmax);
+	const float t0 = fmaxf(tmin, 0.0f) + 1e-6f;
+	if (!render_aabb.contains(o + t0 * d)) return false;
+	// advance_pos_nerf: jittered first step (ld_random_val(sample_index, idx * 786433))
+	t = M::advance_n_steps(t0, cfg.march, ld_random_val_dim0(cfg.spp_index, pix * 786433u));
+	return true;
+}
+
+// if_unoccupied_advance_to_next_occupied_voxel<MIP_FROM_DT = false> (nerf_device.cuh:462-495), at most `budget` voxel skips.
+// Returns 1 when t sits on an occupied sample, 2 when the ray has left the box (t = MAX_DEPTH), 0 when the budget ran out first.
+template <class M>
+__device__ __forceinline__ uint32_t render_march(const ngp_render_cfg& cfg, const Aabb& render_aabb, const uint8_t* __restrict__ bitfield, const V3 ro, const V3 rd,
+	const V3 idir, float& t, V3& pos, uint32_t budget) {
+	for (;;) {
+		pos = ro + t * rd;
+		if (t >= max_depth() || !render_aabb.contains(pos)) {
+			t = max_depth();
+			return 2u;
+		}
+		uint32_t mip = mip_from_pos(pos, NGP_NERF_CASCADES - 1);
+		mip = mip > cfg.max_cascade ? cfg.max_cascade : mip;  // clamp(mip, min_mip = 0, max_mip)
+		if (density_grid_occupied_at(pos, bitfield, mip)) return 1u;
+		if (budget == 0u) return 0u;
+		--budget;
+		while (mip < cfg.max_cascade && !density_grid_occupied_at(pos, bitfield, mip + 1)) ++mip;
+		t = M::advance_to_next_voxel(t, cfg.march, pos, rd, idir, mip);
+	}
+}
+
+// The way from the camera to the first occupied cell is the longest empty stretch of a ray (on nerf/fox ~100 voxel skips before a
+// ray reaches the scene).  Inside the tile kernel every one of them would hold a 128-row tensor-core tile hostage (ncu r2a: 5.9 of
+// 32 lanes active, 6e10 warp instructions, 186 ms per frame), so they are walked here, one thread per pixel, nothing else in the
+// way: t_first[q] = the t of the ray's first sample, or MAX_DEPTH for a ray that never meets an occupied cell (its pixel is
+// finished here).  Same functions, same values: a ray's samples do not depend on which kernel walked up to them.
+template <class M>
+__global__ void __launch_bounds__(128) k_render_first_hit(const __grid_constant__ ngp_render_cfg cfg, const int32_t y0, const uint32_t n_pixels,
+	const uint8_t* __restrict__ bitfield, float* __restrict__ rgba_out, float* __restrict__ depth_out, float* __restrict__ t_first) {
+	const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+	if (q >= n_pixels) return;
+	const Aabb render_aabb{V3{cfg.render_aabb_min[0], cfg.render_aabb_min[1], cfg.render_aabb_min[2]},
+		V3{cfg.render_aabb_max[0], cfg.render_aabb_max[1], cfg.render_aabb_max[2]}};
+	uint32_t pix;
+	V3 ro, rd, idir, pos;
+	float t = max_depth();
+	if (render_init_ray<M>(cfg, render_aabb, y0, q, pix, ro, rd, idir, t)) render_march<M>(cfg, render_aabb, bitfield, ro, rd, idir, t, pos, 0xFFFFFFFFu);
+	if (t >= max_depth()) {
+		// shade_kernel_nerf on an empty payload: transparent pixel, depth MAX_DEPTH
+		reinterpret_cast<float4*>(rgba_out)[pix] = make_float4(0.f, 0.f, 0.f, 0.f);
+		depth_out[pix] = max_depth();
+	}
+	t_first[q] = t;
+}
+
+constexpr uint32_t RENDER_SKIPS_PER_TILE = 16;   // voxel skips a slot may spend looking for its next sample before the tile goes ahead without it
+
+template <uint32_t F, class M>
 __global__ void __launch_bounds__(TILE, 3) k_render_nerf(
 	const __grid_constant__ NetDev net, const __grid_constant__ ngp_render_cfg cfg, const int32_t y0, const int32_t y1,
 	const __half* __restrict__ params, const uint8_t* __restrict__ bitfield, float* __restrict__ rgba_out, float* __restrict__ depth_out,
-	uint32_t* __restrict__ queue /* [0] next pixel, [1] total steps */
+	uint32_t* __restrict__ queue /* [0] next pixel, [1] total steps */, const float* __restrict__ t_first
 ) {
 	extern __shared__ __align__(128) uint8_t smem[];
 	const FwdSmem L = fwd_smem_layout(net.n_hidden_density, net.n_hidden_rgb);
@@ -131,7 +237,7 @@ __global__ void __launch_bounds__(TILE, 3) k_render_nerf(
 	};
 
 	for (;;) {
-		// ---- refill empty slots from the pixel queue (one atomic per warp)
+		// ---- refill empty slots from the pixel queue (one atomic per warp); rays without a first sample were finished by k_render_first_hit
 		const bool want = !alive && !queue_empty;
 		const uint32_t want_mask = __ballot_sync(0xFFFFFFFFu, want);
 		if (want_mask) {
@@ -143,58 +249,29 @@ __global__ void __launch_bounds__(TILE, 3) k_render_nerf(
 				if (q >= n_pixels) {
 					queue_empty = true;
 				} else {
-					// init_rays_with_payload_kernel_nerf (:1452-1453): pixel offset = ld_random_pixel_offset(snap ? 0 : sample_index), the
-					// render camera's lens (m_render_lens) in uv_to_ray
-					const uint32_t x = q % (uint32_t)cfg.width, y = (uint32_t)y0 + q / (uint32_t)cfg.width;
-					pix = x + (uint32_t)cfg.width * y;
-					const float u = ((float)x + cfg.pixel_offset[0]) / (float)cfg.width, v = ((float)y + cfg.pixel_offset[1]) / (float)cfg.height;
-					V3 o, d;
-					uv_to_ray(u, v, cfg.width, cfg.height, cfg.focal_x, cfg.focal_y, cfg.screen_x, cfg.screen_y, cfg.lens_mode, cfg.lens_params, cfg.camera, o, d);
-					o = o + d * cfg.near_distance;
-					d = normalize3(d);
-					ro = o;
-					rd = d;
-					idir = V3{1.0f / d.x, 1.0f / d.y, 1.0f / d.z};
-					acc_r = acc_g = acc_b = acc_a = 0.0f;
-					max_weight = 0.0f;
-					depth = max_depth();
-					n_steps = 0;
-					float tmin, tmax;
-					aabb_ray_intersect(render_aabb, o, d, tmin, tmax);
-					float t0 = fmaxf(tmin, 0.0f) + 1e-6f;
-					alive = render_aabb.contains(o + t0 * d);
-					if (alive) {
-						// advance_pos_nerf: jittered first step (ld_random_val(sample_index, idx * 786433))
-						t = advance_n_steps(t0, cfg.march, ld_random_val_dim0(cfg.spp_index, pix * 786433u));
-					} else {
-						reinterpret_cast<float4*>(rgba_out)[pix] = make_float4(0.f, 0.f, 0.f, 0.f);
-						depth_out[pix] = max_depth();
+					const float tf = t_first[q];
+					if (tf < max_depth()) {
+						float t_unused;
+						render_init_ray<M>(cfg, render_aabb, y0, q, pix, ro, rd, idir, t_unused);
+						t = tf;
+						acc_r = acc_g = acc_b = acc_a = 0.0f;
+						max_weight = 0.0f;
+						depth = max_depth();
+						n_steps = 0;
+						alive = true;
 					}
 				}
 			}
 		}
 
-		// ---- march to the next occupied sample (if_unoccupied_advance_to_next_occupied_voxel, MIP_FROM_DT = false)
+		// ---- march to the next occupied sample; a slot still inside an empty stretch after RENDER_SKIPS_PER_TILE skips sits this tile out
 		bool has_sample = false;
 		V3 pos{0.5f, 0.5f, 0.5f};
 		float dt = 0.0f;
 		if (alive) {
-			for (;;) {
-				pos = ro + t * rd;
-				if (t >= max_depth() || !render_aabb.contains(pos)) {
-					t = max_depth();
-					break;
-				}
-				uint32_t mip = mip_from_pos(pos, NGP_NERF_CASCADES - 1);
-				mip = mip > cfg.max_cascade ? cfg.max_cascade : mip;  // clamp(mip, min_mip = 0, max_mip)
-				if (density_grid_occupied_at(pos, bitfield, mip)) {
-					has_sample = true;
-					break;
-				}
-				while (mip < cfg.max_cascade && !density_grid_occupied_at(pos, bitfield, mip + 1)) ++mip;
-				t = advance_to_next_voxel(t, cfg.march, pos, rd, idir, mip);
-			}
-			if (!has_sample) finish_ray();
+			const uint32_t r = render_march<M>(cfg, render_aabb, bitfield, ro, rd, idir, t, pos, RENDER_SKIPS_PER_TILE);
+			has_sample = r == 1u;
+			if (r == 2u) finish_ray();
 		}
 		const uint32_t any_sample = __syncthreads_or(has_sample ? 1 : 0);
 		const uint32_t any_pending = __syncthreads_or((alive || !queue_empty) ? 1 : 0);
@@ -206,7 +283,7 @@ __global__ void __launch_bounds__(TILE, 3) k_render_nerf(
 		// ---- network: encode + MLPs for the tile
 		float wx = 0.5f, wy = 0.5f, wz = 0.5f;
 		if (has_sample) {
-			dt = calc_dt(t, cfg.march);
+			dt = M::calc_dt(t, cfg.march);
 			const V3 wp = warp_position(pos, train_aabb);
 			wx = wp.x; wy = wp.y; wz = wp.z;
 		}
@@ -243,7 +320,7 @@ __global__ void __launch_bounds__(TILE, 3) k_render_nerf(
 			const float o0 = __low2float(rgbh[0]), o1 = __high2float(rgbh[0]), o2 = __low2float(rgbh[1]), o3 = __low2float(dens[0]);
 			const float T = 1.0f - acc_a;
 			const float dtu = unwarp_dt(warp_dt(dt));
-			const float alpha = 1.0f - ngp_expf(-network_to_density(o3, cfg.density_activation) * dtu);
+			const float alpha = 1.0f - M::expf_(-network_to_density(o3, cfg.density_activation) * dtu);
 			const float weight = alpha * T;
 			acc_r += network_to_rgb(o0, cfg.rgb_activation) * weight;
 			acc_g += network_to_rgb(o1, cfg.rgb_activation) * weight;
@@ -288,26 +365,10 @@ __global__ void __launch_bounds__(TILE, 3) k_render_nerf(
 // next ray from a device-side queue.  Outputs for the samples the loss kernel reads are bit-identical to the all-samples pass.
 // ------------------------------------------------------------------------------------------------------------------
 constexpr uint32_t FWD_RAYS_CTAS_PER_SM = 3;   // measured: 3 -> 0.249 ms, 4 -> 0.280 ms, 5 (spills) -> 0.341 ms
-// What the lazy variant needs to march a ray itself: the tail of generate_training_samples_nerf's pass 2
-// (testbed_nerf.cu:822-848) moved to the consumer.  The generator counts every ray in full but writes only the first `prefix`
-// coordinates of each; beyond the prefix a ray's coordinates are produced here chunk by chunk, by the same arithmetic, and only
-// as far as the transmittance test lets the loss kernel read.  (Marching everything here was measured too: it puts a
-// sequential 8-sample march on the critical path of every tile and costs what the generator saves, profiles/r1c.)
-struct LazyMarch {
-	float aabb_min[3], aabb_max[3];
-	ngp_march_consts march;
-	uint32_t max_cascade;
-	const float* rays;        // [n_rays x 6] origin, direction (unnormalised) as written by the generator
-	const float* t_resume;    // [n_rays] t at which the march continues after the prefix
-	uint32_t prefix;          // samples per ray already written by the generator (multiple of RAY_CHUNK)
-	const uint8_t* bitfield;
-};
-
-template <uint32_t F, uint32_t RAY_CHUNK, bool LAZY>
+template <uint32_t F, uint32_t RAY_CHUNK>
 __global__ void __launch_bounds__(TILE, FWD_RAYS_CTAS_PER_SM) k_nerf_forward_rays(
 	const __grid_constant__ NetDev net, const ngp_nerf_counters* __restrict__ counters, uint32_t* __restrict__ queue, const uint32_t* __restrict__ numsteps,
-	float* __restrict__ coords, const __half* __restrict__ params, const uint32_t density_activation, __half* __restrict__ out,
-	const __grid_constant__ LazyMarch lazy
+	const float* __restrict__ coords, const __half* __restrict__ params, const uint32_t density_activation, __half* __restrict__ out
 ) {
 	extern __shared__ __align__(128) uint8_t smem[];
 	const FwdSmem L = fwd_smem_layout(net.n_hidden_density, net.n_hidden_rgb);
@@ -339,10 +400,9 @@ __global__ void __launch_bounds__(TILE, FWD_RAYS_CTAS_PER_SM) k_nerf_forward_ray
 
 	// slot state, replicated in the 8 lanes of the slot
 	bool have_ray = false, queue_empty = false;
-	uint32_t n = 0, base = 0, k0 = 0, ray = 0;
-	float T = 1.0f, t_cur = 0.0f;
+	uint32_t n = 0, base = 0, k0 = 0;
+	float T = 1.0f;
 	const float EPSILON = 1e-4f;
-	const Aabb aabb{V3{lazy.aabb_min[0], lazy.aabb_min[1], lazy.aabb_min[2]}, V3{lazy.aabb_max[0], lazy.aabb_max[1], lazy.aabb_max[2]}};
 
 	for (;;) {
 		// ---- refill: one queue pop per slot (lane `sub == 0` of each slot asks), one atomic per warp
@@ -363,8 +423,6 @@ __global__ void __launch_bounds__(TILE, FWD_RAYS_CTAS_PER_SM) k_nerf_forward_ray
 					base = numsteps[r * 2 + 1];
 					k0 = 0;
 					T = 1.0f;
-					ray = r;
-					if (LAZY) t_cur = lazy.t_resume[r];
 					have_ray = n > 0;
 				}
 			}
@@ -378,49 +436,9 @@ __global__ void __launch_bounds__(TILE, FWD_RAYS_CTAS_PER_SM) k_nerf_forward_ray
 
 		// ---- this row's sample
 		const uint32_t k = k0 + sub;
-		bool valid = have_ray && k < n;
+		const bool valid = have_ray && k < n;
 		float c[7] = {0.5f, 0.5f, 0.5f, 0.0f, 0.5f, 0.5f, 0.5f};
-		bool from_buffer = valid;
-		if constexpr (LAZY) {
-			from_buffer = valid && k0 < lazy.prefix;
-			if (have_ray && k0 >= lazy.prefix) {
-				// the RAY_CHUNK lanes of the slot march the ray together (same arithmetic, same result); lane `sub` keeps sample k0 + sub
-				const float* rp = lazy.rays + (size_t)ray * 6;
-				const V3 ro{rp[0], rp[1], rp[2]};
-				const V3 rdn = normalize3(V3{rp[3], rp[4], rp[5]});
-				const V3 idir{1.0f / rdn.x, 1.0f / rdn.y, 1.0f / rdn.z};
-				const uint32_t todo = (n - k0) < RAY_CHUNK ? (n - k0) : RAY_CHUNK;
-				uint32_t j = 0;
-				float t = t_cur;
-				V3 pos;
-				while (aabb.contains(pos = ro + t * rdn) && j < todo) {
-					const float dt = calc_dt(t, lazy.march);
-					const uint32_t mip = mip_from_dt(dt, pos, lazy.max_cascade);
-					if (density_grid_occupied_at(pos, lazy.bitfield, mip)) {
-						if (j == sub) {
-							const V3 wp = warp_position(pos, aabb);
-							c[0] = wp.x; c[1] = wp.y; c[2] = wp.z; c[3] = warp_dt(dt);
-						}
-						++j;
-						t += dt;
-					} else {
-						t = advance_to_next_voxel(t, lazy.march, pos, rdn, idir, mip);
-					}
-				}
-				t_cur = t;
-				valid = valid && sub < j;
-				if (valid) {
-					const V3 wdir = warp_direction(rdn);
-					c[4] = wdir.x; c[5] = wdir.y; c[6] = wdir.z;
-					float* cp = coords + (size_t)(base + k) * 7;
-#pragma unroll
-					for (int q = 0; q < 7; ++q) cp[q] = c[q];
-				} else {
-					c[0] = c[1] = c[2] = 0.5f;
-					c[3] = 0.0f;
-				}
-			}
-		}
+		const bool from_buffer = valid;
 		if (from_buffer) {
 			const float* cp = coords + (size_t)(base + k) * 7;
 #pragma unroll
@@ -485,31 +503,19 @@ __global__ void __launch_bounds__(TILE, FWD_RAYS_CTAS_PER_SM) k_nerf_forward_ray
 }
 
 // queue: a zeroed u32 (the `pad` word of the step's counter block).  Grid sized for the worst case (n_rays_max rays).
-template <uint32_t F, uint32_t CHUNK, bool LAZY>
+template <uint32_t F, uint32_t CHUNK>
 static void launch_forward_rays(const NetDev& net, cudaStream_t stream, uint32_t n_rays_max, const ngp_nerf_counters* counters, uint32_t* queue,
-	const uint32_t* numsteps, float* coords, const __half* params, uint32_t density_activation, __half* out, const LazyMarch& lazy) {
+	const uint32_t* numsteps, const float* coords, const __half* params, uint32_t density_activation, __half* out) {
 	const FwdSmem L = fwd_smem_layout(net.n_hidden_density, net.n_hidden_rgb);
 	const uint32_t n_tiles = div_round_up(n_rays_max, TILE / CHUNK);
 	const uint32_t max_ctas = (uint32_t)device_sm_count() * FWD_RAYS_CTAS_PER_SM;
 	const uint32_t grid = n_tiles < max_ctas ? n_tiles : max_ctas;
-	auto kern = k_nerf_forward_rays<F, CHUNK, LAZY>;
+	auto kern = k_nerf_forward_rays<F, CHUNK>;
 	static bool attr = false;
 	if (!attr) { NGPB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); attr = true; }
-	kern<<<grid, TILE, L.total, stream>>>(net, counters, queue, numsteps, coords, params, density_activation, out, lazy);
+	kern<<<grid, TILE, L.total, stream>>>(net, counters, queue, numsteps, coords, params, density_activation, out);
 	NGPB_LAUNCHED();
 	NGPB_CUDA_CHECK(cudaGetLastError());
-}
-
-template <bool LAZY>
-static void dispatch_forward_rays(const NetDev& net, cudaStream_t stream, uint32_t n_rays_max, const ngp_nerf_counters* counters, uint32_t* queue,
-	const uint32_t* numsteps, float* coords, const __half* params, uint32_t density_activation, __half* out, uint32_t chunk, const LazyMarch& lazy) {
-	if (net.n_features == 2) {
-		if (chunk == 4) launch_forward_rays<2, 4, LAZY>(net, stream, n_rays_max, counters, queue, numsteps, coords, params, density_activation, out, lazy);
-		else launch_forward_rays<2, 8, LAZY>(net, stream, n_rays_max, counters, queue, numsteps, coords, params, density_activation, out, lazy);
-	} else {
-		if (chunk == 4) launch_forward_rays<4, 4, LAZY>(net, stream, n_rays_max, counters, queue, numsteps, coords, params, density_activation, out, lazy);
-		else launch_forward_rays<4, 8, LAZY>(net, stream, n_rays_max, counters, queue, numsteps, coords, params, density_activation, out, lazy);
-	}
 }
 
 // chunk: samples of a ray evaluated per tensor-core tile (4 or 8; 128 / chunk ray slots per CTA)
@@ -518,58 +524,52 @@ void nerf_inference_rays(const ngp_nerf_desc& d, cudaStream_t stream, uint32_t n
 	if (n_rays_max == 0) return;
 	NGPB_CHECK(chunk == 4 || chunk == 8, "inference chunk must be 4 or 8");
 	const NetDev net = make_netdev(d);
-	dispatch_forward_rays<false>(net, stream, n_rays_max, counters, queue, numsteps, const_cast<float*>(coords), params, density_activation, out, chunk, LazyMarch{});
-}
-
-// As nerf_inference_rays, but coordinates beyond each ray's first `prefix` samples are marched here (`coords` is IN/OUT: the
-// samples the loss kernel will read are written at their reserved slots; the rest of a ray's slots stay untouched).
-void nerf_march_inference_rays(const ngp_nerf_desc& d, cudaStream_t stream, uint32_t n_rays_max, const ngp_nerf_train_cfg& cfg, const ngp_nerf_counters* counters,
-	uint32_t* queue, const uint32_t* numsteps, const float* rays, const float* t_resume, uint32_t prefix, const uint8_t* bitfield, float* coords,
-	const __half* params, __half* out, uint32_t chunk) {
-	if (n_rays_max == 0) return;
-	NGPB_CHECK(chunk == 4 || chunk == 8, "inference chunk must be 4 or 8");
-	const NetDev net = make_netdev(d);
-	LazyMarch lazy{};
-	for (int k = 0; k < 3; ++k) {
-		lazy.aabb_min[k] = cfg.aabb_min[k];
-		lazy.aabb_max[k] = cfg.aabb_max[k];
+	if (net.n_features == 2) {
+		if (chunk == 4) launch_forward_rays<2, 4>(net, stream, n_rays_max, counters, queue, numsteps, coords, params, density_activation, out);
+		else launch_forward_rays<2, 8>(net, stream, n_rays_max, counters, queue, numsteps, coords, params, density_activation, out);
+	} else {
+		if (chunk == 4) launch_forward_rays<4, 4>(net, stream, n_rays_max, counters, queue, numsteps, coords, params, density_activation, out);
+		else launch_forward_rays<4, 8>(net, stream, n_rays_max, counters, queue, numsteps, coords, params, density_activation, out);
 	}
-	lazy.march = cfg.march;
-	lazy.max_cascade = cfg.max_cascade;
-	lazy.rays = rays;
-	NGPB_CHECK(prefix % chunk == 0, "the eager prefix must be a multiple of the inference chunk");
-	lazy.t_resume = t_resume;
-	lazy.prefix = prefix;
-	lazy.bitfield = bitfield;
-	dispatch_forward_rays<true>(net, stream, n_rays_max, counters, queue, numsteps, coords, params, cfg.density_activation, out, chunk, lazy);
 }
 
-size_t render_scratch_bytes(int32_t, int32_t) { return 256; }
+// scratch: [0, 256) queue words | t_first[width * rows]
+size_t render_scratch_bytes(int32_t width, int32_t rows) { return 256 + sizeof(float) * (size_t)(width > 0 ? width : 0) * (size_t)(rows > 0 ? rows : 0); }
+
+template <uint32_t F, class M>
+static void launch_render(const NetDev& net, cudaStream_t stream, const ngp_render_cfg& cfg, int32_t y0, int32_t y1, const __half* params, const uint8_t* bitfield,
+	float* rgba, float* depth, uint32_t* queue, float* t_first) {
+	const FwdSmem L = fwd_smem_layout(net.n_hidden_density, net.n_hidden_rgb);
+	const uint32_t n_pixels = (uint32_t)(y1 - y0) * (uint32_t)cfg.width;
+	k_render_first_hit<M><<<div_round_up(n_pixels, 128), 128, 0, stream>>>(cfg, y0, n_pixels, bitfield, rgba, depth, t_first);
+	NGPB_LAUNCHED();
+	const uint32_t n_tiles = div_round_up(n_pixels, TILE);
+	const uint32_t max_ctas = (uint32_t)device_sm_count() * 3u;
+	const uint32_t grid = n_tiles < max_ctas ? n_tiles : max_ctas;
+	auto kern = k_render_nerf<F, M>;
+	static bool attr = false;
+	if (!attr) { NGPB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); attr = true; }
+	kern<<<grid, TILE, L.total, stream>>>(net, cfg, y0, y1, params, bitfield, rgba, depth, queue, t_first);
+	NGPB_LAUNCHED();
+	NGPB_CUDA_CHECK(cudaGetLastError());
+}
 
 void render_nerf(const ngp_nerf_desc& d, cudaStream_t stream, const ngp_render_cfg& cfg, int32_t y0, int32_t y1, const __half* params,
 	const uint8_t* bitfield, float* rgba, float* depth, void* scratch, uint32_t* n_steps_total) {
 	NGPB_CHECK(cfg.width > 0 && cfg.height > 0 && y0 >= 0 && y1 <= cfg.height && y0 < y1, "render: bad tile");
+	NGPB_CHECK(cfg.math_mode <= NGP_MATH_REFERENCE, "ngp_render_cfg.math_mode: unknown arithmetic flavour");
 	const NetDev net = make_netdev(d);
-	const FwdSmem L = fwd_smem_layout(net.n_hidden_density, net.n_hidden_rgb);
 	uint32_t* queue = reinterpret_cast<uint32_t*>(scratch);
+	float* t_first = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(scratch) + 256);
 	NGPB_CUDA_CHECK(cudaMemsetAsync(queue, 0, 16, stream));
-	const uint32_t n_pixels = (uint32_t)(y1 - y0) * (uint32_t)cfg.width;
-	const uint32_t n_tiles = div_round_up(n_pixels, TILE);
-	const uint32_t max_ctas = (uint32_t)device_sm_count() * 3u;
-	const uint32_t grid = n_tiles < max_ctas ? n_tiles : max_ctas;
+	const bool fast = cfg.math_mode == NGP_MATH_REFERENCE;
 	if (net.n_features == 2) {
-		auto kern = k_render_nerf<2>;
-		static bool attr = false;
-		if (!attr) { NGPB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); attr = true; }
-		kern<<<grid, TILE, L.total, stream>>>(net, cfg, y0, y1, params, bitfield, rgba, depth, queue);
+		if (fast) launch_render<2, RenderFast>(net, stream, cfg, y0, y1, params, bitfield, rgba, depth, queue, t_first);
+		else launch_render<2, RenderDet>(net, stream, cfg, y0, y1, params, bitfield, rgba, depth, queue, t_first);
 	} else {
-		auto kern = k_render_nerf<4>;
-		static bool attr = false;
-		if (!attr) { NGPB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); attr = true; }
-		kern<<<grid, TILE, L.total, stream>>>(net, cfg, y0, y1, params, bitfield, rgba, depth, queue);
+		if (fast) launch_render<4, RenderFast>(net, stream, cfg, y0, y1, params, bitfield, rgba, depth, queue, t_first);
+		else launch_render<4, RenderDet>(net, stream, cfg, y0, y1, params, bitfield, rgba, depth, queue, t_first);
 	}
-	NGPB_LAUNCHED();
-	NGPB_CUDA_CHECK(cudaGetLastError());
 	if (n_steps_total) NGPB_CUDA_CHECK(cudaMemcpyAsync(n_steps_total, queue + 1, 4, cudaMemcpyDeviceToDevice, stream));
 }
 

@@ -33,20 +33,7 @@ void optimizer_step(const ngp_nerf_desc& d, cudaStream_t stream, const ngp_adam_
 	__half* grads, float* m1, float* m2, uint32_t* steps);
 void generate_training_samples(cudaStream_t stream, uint32_t n_rays_local, uint32_t ray_offset, uint32_t n_rays_global, uint64_t rng_state, uint64_t rng_inc,
 	const ngp_nerf_train_cfg& cfg, const ngp_train_view* views, uint32_t n_views, const uint8_t* bitfield, uint32_t max_samples, ngp_nerf_counters* counters,
-	uint32_t* ray_indices, float* rays, uint32_t* numsteps, float* coords, float* t_resume, uint32_t prefix, const uint32_t* perm);
-size_t ray_sort_scratch_bytes(uint32_t max_rays);
-const uint32_t* sort_training_rays(cudaStream_t stream, uint32_t n_rays_local, uint32_t ray_offset, uint32_t n_rays_global, uint64_t rng_state, uint64_t rng_inc,
-	const ngp_nerf_train_cfg& cfg, const ngp_train_view* views, uint32_t n_views, const uint8_t* bitfield, void* scratch, uint32_t max_rays);
-size_t generator_scratch_floats(uint32_t max_rays);
-size_t generator_scratch_u32(uint32_t max_rays);
-void count_training_samples(cudaStream_t stream, uint32_t n_rays_local, uint32_t ray_offset, uint32_t n_rays_global, uint64_t rng_state, uint64_t rng_inc,
-	const ngp_nerf_train_cfg& cfg, const ngp_train_view* views, uint32_t n_views, const uint8_t* bitfield, uint32_t max_samples, ngp_nerf_counters* counters,
-	uint32_t* ray_indices, float* rays, uint32_t* numsteps, float* ckpt, uint32_t* seg_info);
-void write_training_samples(cudaStream_t stream, uint32_t n_rays_local, const ngp_nerf_train_cfg& cfg, const uint8_t* bitfield, const float* rays, const float* ckpt,
-	const uint32_t* seg_info, float* coords);
-void nerf_march_inference_rays(const ngp_nerf_desc& d, cudaStream_t stream, uint32_t n_rays_max, const ngp_nerf_train_cfg& cfg, const ngp_nerf_counters* counters,
-	uint32_t* queue, const uint32_t* numsteps, const float* rays, const float* t_resume, uint32_t prefix, const uint8_t* bitfield, float* coords,
-	const __half* params, __half* out, uint32_t chunk);
+	uint32_t* ray_indices, float* rays, uint32_t* numsteps, float* coords);
 void compute_loss(cudaStream_t stream, uint32_t n_rays_local, uint32_t n_rays_global, uint64_t rng_state, uint64_t rng_inc, const ngp_nerf_train_cfg& cfg,
 	const ngp_train_view* views, uint32_t n_views, const __half* network_output, uint32_t max_compacted, ngp_nerf_counters* counters,
 	const uint32_t* ray_indices, const float* rays, uint32_t* numsteps, const float* coords, float* coords_compacted, __half* dloss, float* loss_per_ray,
@@ -205,15 +192,6 @@ struct ngp_testbed {
 	uint64_t seed = 1337;
 	bool train_network = true, train_encoding = true;
 	bool full_inference = false;
-	bool lazy_sample_generation = false;  // measured slower (profiles/r1c): the generator writes a prefix of each ray's coordinates; the ray-ordered inference kernel marches the rest on demand
-	uint32_t eager_prefix = 16;
-	bool sort_rays = false;          // the batch's rays bucketed by expected march length before the generator (k_ray_sort_*).  Measured
-	                                 // (profiles/r1c): the warps that collect the long rays then diverge on every trip and set the kernel's
-	                                 // duration: generator 0.56 -> 0.80 ms, inference 0.28 -> 0.22 ms, net slower.  Parity-tested, OFF.
-	bool split_generation = false;   // count kernel + warp-per-ray write kernel instead of the fused generator.  Measured (profiles/r1c): beside
-	                                 // k_nerf_train only 2 of its CTAs fit per SM (registers), so the count runs in two waves and hides nothing:
-	                                 // 1.51-1.65 ms/step against 1.50-1.54 for the fused kernel prefetched behind the backward pass
-	bool overlap_gate = true;        // the prefetched generator waits for the forward/backward kernel
 	uint32_t inference_chunk = 8;
 
 	DevBuf<float> params_fp32, m1, m2, mlp_grads_f32;
@@ -237,9 +215,7 @@ struct ngp_testbed {
 	struct RaySet {
 		DevBuf<ngp_nerf_counters> counters;
 		DevBuf<uint32_t> ray_indices, numsteps;
-		DevBuf<float> rays, coords, t_resume, ckpt;
-		DevBuf<uint32_t> seg_info;
-		DevBuf<uint8_t> sort_scratch;
+		DevBuf<float> rays, coords;
 	} set[2];
 	uint32_t cur = 0;                     // set used by the step in flight
 	DevBuf<float> coords_compacted, loss_per_ray, reduce_scratch;
@@ -281,6 +257,7 @@ struct ngp_testbed {
 	bool render_with_lens_distortion = false;    // m_render_with_lens_distortion / m_render_lens (set by set_camera_to_training_view)
 	uint32_t render_lens_mode = NGP_LENS_PERSPECTIVE;
 	float render_lens_params[4] = {0, 0, 0, 0};
+	uint32_t render_math = NGP_MATH_REFERENCE;   // arithmetic of the render march (ngp_render_cfg.math_mode); `render_math` option
 
 	~ngp_testbed() {
 		if (side_stream) {
@@ -310,6 +287,7 @@ static void tb_set_defaults(ngp_testbed* t) {
 	c.density_activation = NGP_ACT_EXPONENTIAL;
 	c.near_distance = 0.1f;
 	c.loss_scale = NGP_LOSS_SCALE;
+	c.math_mode = NGP_MATH_REFERENCE;   // the sample generator marches with the reference build's arithmetic (march_ref.cu); the oracle tests select NGP_MATH_DETERMINISTIC
 }
 
 static void tb_update_scene(ngp_testbed* t) {
@@ -460,10 +438,6 @@ static void tb_ensure_step_scratch(ngp_testbed* t, uint32_t batch) {
 		rs.numsteps.ensure((size_t)max_rays * 2);
 		rs.rays.ensure((size_t)max_rays * 6);
 		rs.coords.ensure((size_t)max_samples * 7);
-		rs.t_resume.ensure(max_rays);
-		rs.ckpt.ensure(generator_scratch_floats(max_rays));
-		rs.seg_info.ensure(generator_scratch_u32(max_rays));
-		rs.sort_scratch.ensure(ray_sort_scratch_bytes(max_rays));
 	}
 	t->loss_per_ray.ensure(max_rays);
 	t->reduce_scratch.ensure(1024);
@@ -545,29 +519,16 @@ static void tb_invalidate_prefetch(ngp_testbed* t) {
 	if (t->prefetch_valid && t->side_stream) cudaStreamSynchronize(t->side_stream);
 	t->prefetch_valid = false;
 }
-static bool tb_lazy(const ngp_testbed* t) { return t->lazy_sample_generation && !t->full_inference; }
-static bool tb_split(const ngp_testbed* t) { return t->split_generation && !tb_lazy(t); }
-// The part of the generator that may be prefetched: everything (fused kernel) or the counting kernel (split generation).
+// Rank r of W marches the global ray ids r, r + W, r + 2W, ... of a batch of W x rays_local rays: image_idx (nerf_device.cuh:598) maps
+// consecutive ids to the same view, so a contiguous block per rank would give every rank a disjoint 1/W slice of the views (and a
+// rank whose views look at empty space idles while the others march); interleaved, every rank draws from every view.
 static void tb_launch_generator(ngp_testbed* t, cudaStream_t stream, uint32_t set, uint32_t rays_local, uint32_t max_inference) {
 	ngp_testbed::RaySet& rs = t->set[set];
 	NGPB_CUDA_CHECK(cudaMemsetAsync(rs.counters.p, 0, sizeof(ngp_nerf_counters), stream));
-	if (tb_split(t)) {
-		count_training_samples(stream, rays_local, t->dp_rank * rays_local, rays_local * t->dp_world, t->rng.state, t->rng.inc, t->cfg, t->views_dev.p, tb_n_views(t),
-			t->bitfield.p, max_inference, rs.counters.p, rs.ray_indices.p, rs.rays.p, rs.numsteps.p, rs.ckpt.p, rs.seg_info.p);
-	} else {
-		const uint32_t* perm = nullptr;
-		if (t->sort_rays && rays_local >= 4096)
-			perm = sort_training_rays(stream, rays_local, t->dp_rank * rays_local, rays_local * t->dp_world, t->rng.state, t->rng.inc, t->cfg, t->views_dev.p,
-				tb_n_views(t), t->bitfield.p, rs.sort_scratch.p, 1u << 18);
-		generate_training_samples(stream, rays_local, t->dp_rank * rays_local, rays_local * t->dp_world, t->rng.state, t->rng.inc, t->cfg, t->views_dev.p, tb_n_views(t),
-			t->bitfield.p, max_inference, rs.counters.p, rs.ray_indices.p, rs.rays.p, rs.numsteps.p, rs.coords.p, tb_lazy(t) ? rs.t_resume.p : nullptr, t->eager_prefix, perm);
-	}
-}
-// The part that always runs in the step itself, on the main stream
-static void tb_finish_generator(ngp_testbed* t, uint32_t set, uint32_t rays_local) {
-	if (!tb_split(t)) return;
-	ngp_testbed::RaySet& rs = t->set[set];
-	write_training_samples(t->stream, rays_local, t->cfg, t->bitfield.p, rs.rays.p, rs.ckpt.p, rs.seg_info.p, rs.coords.p);
+	ngp_nerf_train_cfg cfg = t->cfg;
+	cfg.ray_stride = t->dp_world;
+	generate_training_samples(stream, rays_local, t->dp_rank, rays_local * t->dp_world, t->rng.state, t->rng.inc, cfg, t->views_dev.p, tb_n_views(t),
+		t->bitfield.p, max_inference, rs.counters.p, rs.ray_indices.p, rs.rays.p, rs.numsteps.p, rs.coords.p);
 }
 
 // A training step (train_nerf_step, testbed_nerf.cu:3007-3382 + optimizer_step :2770) is issued in three parts so that a
@@ -609,13 +570,10 @@ static void tb_front(ngp_testbed* t, uint32_t batch) {
 		// the generator of this step already ran (or is finishing) on the side stream into the other buffer set
 		t->cur ^= 1u;
 		NGPB_CUDA_CHECK(cudaStreamWaitEvent(t->stream, t->ev_prefetch_done, 0));
-		PhaseTimer pt(t, 1);
-		tb_finish_generator(t, t->cur, rays_local);
 	} else {
 		tb_invalidate_prefetch(t);
 		PhaseTimer pt(t, 1);
 		tb_launch_generator(t, t->stream, t->cur, rays_local, max_inference);
-		tb_finish_generator(t, t->cur, rays_local);
 	}
 	t->prefetch_valid = false;
 	ngp_testbed::RaySet& rs = t->set[t->cur];
@@ -625,10 +583,6 @@ static void tb_front(ngp_testbed* t, uint32_t batch) {
 		if (t->full_inference) {
 			// the reference's schedule: evaluate every generated sample (testbed_nerf.cu:3233-3235)
 			nerf_inference_counted(t->desc, t->stream, max_inference, &rs.counters.p->n_samples, rs.coords.p, t->params.p, t->mlp_out.p);
-		} else if (tb_lazy(t)) {
-			// march + evaluate, ray by ray, only the samples the loss kernel will read
-			nerf_march_inference_rays(t->desc, t->stream, rays_local, t->cfg, rs.counters.p, &rs.counters.p->pad, rs.numsteps.p, rs.rays.p, rs.t_resume.p, t->eager_prefix,
-				t->bitfield.p, rs.coords.p, t->params.p, t->mlp_out.p, t->inference_chunk);
 		} else {
 			// evaluate, ray by ray, only the samples the loss kernel will read (bit-identical outputs for those)
 			nerf_inference_rays(t->desc, t->stream, rays_local, rs.counters.p, &rs.counters.p->pad, rs.numsteps.p, rs.coords.p, t->params.p,
@@ -719,9 +673,7 @@ static void tb_prefetch(ngp_testbed* t) {
 	const uint32_t max_inference = tb_max_inference(t, batch);
 	// the other buffer set was last read by the loss kernel of the previous step, which precedes ev_back_done on the main stream;
 	// the bitfield and the views are not written by anything in flight
-	// gate: behind the forward/backward kernel, or only behind the loss kernel (the counting kernel of the split generator needs no
-	// shared memory and few registers: it fits beside k_nerf_train's two CTAs per SM and its ~0.4 ms are latency, not throughput)
-	NGPB_CUDA_CHECK(cudaStreamWaitEvent(t->side_stream, (t->overlap_gate || !tb_split(t)) ? t->ev_back_done : t->ev_front_done, 0));
+	NGPB_CUDA_CHECK(cudaStreamWaitEvent(t->side_stream, t->ev_back_done, 0));
 	tb_launch_generator(t, t->side_stream, next, t->rays_per_batch, max_inference);
 	NGPB_CUDA_CHECK(cudaEventRecord(t->ev_prefetch_done, t->side_stream));
 	t->prefetch_valid = true;
@@ -820,46 +772,11 @@ int ngp_optimizer_step(const ngp_nerf_desc* d, void* stream, const ngp_adam_cfg*
 int ngp_nerf_generate_training_samples(void* stream, uint32_t n_rays, uint32_t ray_offset, uint32_t n_rays_global, uint64_t rng_state, uint64_t rng_inc,
 	const ngp_nerf_train_cfg* cfg, const ngp_train_view* views, uint32_t n_views, const uint8_t* bitfield, uint32_t max_samples, ngp_nerf_counters* counters,
 	uint32_t* ray_indices, float* rays, uint32_t* numsteps, float* coords) {
-	NGPB_TRY(require_device(); NGPB_CHECK(n_rays_global >= n_rays && ray_offset <= n_rays_global - n_rays, "ray shard outside the global batch");
+	NGPB_TRY(require_device(); const uint32_t stride = cfg->ray_stride ? cfg->ray_stride : 1u;
+		NGPB_CHECK(n_rays_global >= n_rays && (n_rays == 0 || (uint64_t)ray_offset + (uint64_t)(n_rays - 1) * stride < n_rays_global), "ray shard outside the global batch");
+		NGPB_CHECK(cfg->math_mode <= NGP_MATH_REFERENCE, "ngp_nerf_train_cfg.math_mode: unknown arithmetic flavour");
 		generate_training_samples((cudaStream_t)stream, n_rays, ray_offset, n_rays_global, rng_state, rng_inc, *cfg, views, n_views, bitfield,
-		max_samples, counters, ray_indices, rays, numsteps, coords, nullptr, 0u, nullptr));
-}
-size_t ngp_nerf_ray_sort_scratch_bytes(uint32_t max_rays) { return ray_sort_scratch_bytes(max_rays); }
-int ngp_nerf_generate_training_samples_sorted(void* stream, uint32_t n_rays, uint32_t ray_offset, uint32_t n_rays_global, uint64_t rng_state, uint64_t rng_inc,
-	const ngp_nerf_train_cfg* cfg, const ngp_train_view* views, uint32_t n_views, const uint8_t* bitfield, uint32_t max_samples, ngp_nerf_counters* counters,
-	uint32_t* ray_indices, float* rays, uint32_t* numsteps, float* coords, void* sort_scratch) {
-	NGPB_TRY(require_device(); NGPB_CHECK(n_rays_global >= n_rays && ray_offset <= n_rays_global - n_rays, "ray shard outside the global batch");
-		const uint32_t* perm = sort_training_rays((cudaStream_t)stream, n_rays, ray_offset, n_rays_global, rng_state, rng_inc, *cfg, views, n_views, bitfield,
-			sort_scratch, n_rays);
-		generate_training_samples((cudaStream_t)stream, n_rays, ray_offset, n_rays_global, rng_state, rng_inc, *cfg, views, n_views, bitfield,
-		max_samples, counters, ray_indices, rays, numsteps, coords, nullptr, 0u, perm));
-}
-int ngp_nerf_generate_training_samples_prefix(void* stream, uint32_t n_rays, uint32_t ray_offset, uint32_t n_rays_global, uint64_t rng_state, uint64_t rng_inc,
-	const ngp_nerf_train_cfg* cfg, const ngp_train_view* views, uint32_t n_views, const uint8_t* bitfield, uint32_t max_samples, ngp_nerf_counters* counters,
-	uint32_t* ray_indices, float* rays, uint32_t* numsteps, float* coords, float* t_resume, uint32_t prefix) {
-	NGPB_TRY(require_device(); NGPB_CHECK(n_rays_global >= n_rays && ray_offset <= n_rays_global - n_rays, "ray shard outside the global batch");
-		NGPB_CHECK(t_resume != nullptr, "ngp_nerf_generate_training_samples_prefix: t_resume is required");
-		generate_training_samples((cudaStream_t)stream, n_rays, ray_offset, n_rays_global, rng_state, rng_inc, *cfg, views, n_views, bitfield,
-		max_samples, counters, ray_indices, rays, numsteps, coords, t_resume, prefix, nullptr));
-}
-int ngp_nerf_march_inference_rays(const ngp_nerf_desc* d, void* stream, uint32_t n_rays_max, const ngp_nerf_train_cfg* cfg, const ngp_nerf_counters* counters,
-	uint32_t* queue, const uint32_t* numsteps, const float* rays, const float* t_resume, uint32_t prefix, const uint8_t* bitfield, float* coords, const void* params,
-	void* out) {
-	NGPB_TRY(require_device(); nerf_march_inference_rays(*d, (cudaStream_t)stream, n_rays_max, *cfg, counters, queue, numsteps, rays, t_resume, prefix, bitfield,
-		coords, (const __half*)params, (__half*)out, 8));
-}
-size_t ngp_nerf_generator_scratch_floats(uint32_t max_rays) { return generator_scratch_floats(max_rays); }
-size_t ngp_nerf_generator_scratch_u32(uint32_t max_rays) { return generator_scratch_u32(max_rays); }
-int ngp_nerf_count_training_samples(void* stream, uint32_t n_rays, uint32_t ray_offset, uint32_t n_rays_global, uint64_t rng_state, uint64_t rng_inc,
-	const ngp_nerf_train_cfg* cfg, const ngp_train_view* views, uint32_t n_views, const uint8_t* bitfield, uint32_t max_samples, ngp_nerf_counters* counters,
-	uint32_t* ray_indices, float* rays, uint32_t* numsteps, float* ckpt_scratch, uint32_t* seg_scratch) {
-	NGPB_TRY(require_device(); NGPB_CHECK(n_rays_global >= n_rays && ray_offset <= n_rays_global - n_rays, "ray shard outside the global batch");
-		count_training_samples((cudaStream_t)stream, n_rays, ray_offset, n_rays_global, rng_state, rng_inc, *cfg, views, n_views, bitfield, max_samples, counters,
-		ray_indices, rays, numsteps, ckpt_scratch, seg_scratch));
-}
-int ngp_nerf_write_training_samples(void* stream, uint32_t n_rays, const ngp_nerf_train_cfg* cfg, const uint8_t* bitfield, const float* rays, const float* ckpt_scratch,
-	const uint32_t* seg_scratch, float* coords) {
-	NGPB_TRY(require_device(); write_training_samples((cudaStream_t)stream, n_rays, *cfg, bitfield, rays, ckpt_scratch, seg_scratch, coords));
+		max_samples, counters, ray_indices, rays, numsteps, coords));
 }
 int ngp_nerf_compute_loss(void* stream, uint32_t n_rays, uint32_t n_rays_global, uint64_t rng_state, uint64_t rng_inc, const ngp_nerf_train_cfg* cfg,
 	const ngp_train_view* views, uint32_t n_views, const void* network_output, uint32_t max_compacted, ngp_nerf_counters* counters,
@@ -1110,13 +1027,11 @@ int ngp_testbed_set_option(ngp_testbed* t, const char* name_c, double value) {
 		else if (n == "background_color.b") c.background_color[2] = (float)value;
 		else if (n == "background_color.a") t->background_alpha = (float)value;
 		else if (n == "exposure") t->exposure = (float)value;
+		else if (n == "nerf.training.math_mode") { NGPB_CHECK(value == 0 || value == 1, "math_mode must be 0 (deterministic) or 1 (reference)"); tb_invalidate_prefetch(t); t->cfg.math_mode = (uint32_t)value; }
+		else if (n == "nerf.training.gen_lanes_per_ray") { const uint32_t g = (uint32_t)value; NGPB_CHECK(g <= 32 && (g & (g - 1)) == 0, "gen_lanes_per_ray must be 0 or a power of two up to 32"); tb_invalidate_prefetch(t); t->cfg.gen_lanes_per_ray = g; }
+		else if (n == "render_math") { NGPB_CHECK(value == 0 || value == 1, "render_math must be 0 (deterministic) or 1 (reference)"); t->render_math = (uint32_t)value; }
 		else if (n == "nerf.training.full_inference") { tb_invalidate_prefetch(t); t->full_inference = value != 0; }
-		else if (n == "nerf.training.lazy_sample_generation") { tb_invalidate_prefetch(t); t->lazy_sample_generation = value != 0; }
 		else if (n == "nerf.training.train_mode") { NGPB_CHECK(value == 0 || value == 1 || value == 2, "train_mode must be Nerf (0), Rfl (1) or RflRelax (2)"); c.train_mode = (uint32_t)value; }
-		else if (n == "nerf.training.sort_rays") { tb_invalidate_prefetch(t); t->sort_rays = value != 0; }
-		else if (n == "nerf.training.split_generation") { tb_invalidate_prefetch(t); t->split_generation = value != 0; }
-		else if (n == "nerf.training.overlap_gate") { tb_invalidate_prefetch(t); t->overlap_gate = value != 0; }
-		else if (n == "nerf.training.eager_prefix") { NGPB_CHECK(value >= 0 && ((uint32_t)value % 8u) == 0u, "eager_prefix must be a multiple of 8"); tb_invalidate_prefetch(t); t->eager_prefix = (uint32_t)value; }
 		else if (n == "nerf.training.inference_chunk") { NGPB_CHECK(value == 4 || value == 8, "inference_chunk must be 4 or 8"); t->inference_chunk = (uint32_t)value; }
 		else if (n == "nerf.training.overlap_sample_generation") t->overlap_sample_generation = value != 0;
 		else if (n == "train_network") t->train_network = value != 0;
@@ -1139,6 +1054,9 @@ double ngp_testbed_get_option(ngp_testbed* t, const char* name_c) {
 	if (n == "nerf.training.near_distance") return c.near_distance;
 	if (n == "nerf.training.loss_type") return c.loss_type;
 	if (n == "nerf.training.train_mode") return c.train_mode;
+	if (n == "nerf.training.math_mode") return c.math_mode;
+	if (n == "nerf.training.gen_lanes_per_ray") return c.gen_lanes_per_ray;
+	if (n == "render_math") return t->render_math;
 	if (n == "nerf.training.density_grid_decay") return t->density_grid_decay;
 	if (n == "nerf.rgb_activation") return c.rgb_activation;
 	if (n == "nerf.density_activation") return c.density_activation;
@@ -1266,6 +1184,7 @@ static void tb_fill_render_cfg(ngp_testbed* t, ngp_render_cfg& rc, int32_t width
 	render_pixel_offset(t->render_snap_to_pixel_centers ? 0u : t->render_spp_index, rc.pixel_offset);
 	rc.lens_mode = t->render_with_lens_distortion ? t->render_lens_mode : (uint32_t)NGP_LENS_PERSPECTIVE;
 	for (int k = 0; k < 4; ++k) rc.lens_params[k] = t->render_with_lens_distortion ? t->render_lens_params[k] : 0.0f;
+	rc.math_mode = t->render_math;
 }
 
 int ngp_testbed_render_device(ngp_testbed* t, int32_t width, int32_t height, const float* cam, float fx, float fy, float cx, float cy, int32_t y0,

@@ -725,8 +725,20 @@ class Testbed:
         if opts.get("start_t", -1.0) >= 0 or opts.get("end_t", -1.0) >= 0:
             raise B.NgpError("render: camera paths (start_t / end_t) are not implemented")
         cam, focal, center = self._camera.render_args(width, height)
-        return self._render_explicit(width, height, cam, focal, center, spp=int(opts.get("spp", 1)), linear=bool(opts.get("linear", True)),
-                                     return_depth=bool(opts.get("return_depth", False)))
+        # Testbed::render_to_cpu hands render_frame an EMPTY lens (python_api.cu:199-213, the `{}, // lens` argument): the Python
+        # render() of the reference never applies m_render_lens, whatever render_with_lens_distortion says (only the windowed frame()
+        # path does, src/testbed.cu:3217).  Measured on the B200 (profiles/r2a): reference render() of fox's test views = 26.0 dB
+        # against the distorted photographs, 29.4 dB once the lens is applied.  The reference-shaped call reproduces the reference;
+        # the explicit-camera form below honours render_with_lens_distortion / render_lens.
+        with_lens = self.render_with_lens_distortion
+        if with_lens:
+            self.render_with_lens_distortion = False
+        try:
+            return self._render_explicit(width, height, cam, focal, center, spp=int(opts.get("spp", 1)), linear=bool(opts.get("linear", True)),
+                                         return_depth=bool(opts.get("return_depth", False)))
+        finally:
+            if with_lens:
+                self.render_with_lens_distortion = True
 
     def render_with_depth(self, width: int = 1920, height: int = 1080, spp: int = 1, linear: bool = True):
         """python_api.cu:520-532: (rgba, depth)"""

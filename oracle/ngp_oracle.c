@@ -368,8 +368,9 @@ EXPORT uint32_t orc_generate_training_samples(uint32_t n_rays_local, uint32_t ra
 	uint32_t* n_samples_out, uint32_t* per_ray_numsteps, uint32_t* ray_indices_out, float* rays_out, uint32_t* numsteps_out, float* coords_out) {
 	const aabb_t aabb = cfg_aabb(cfg);
 	uint32_t ray_counter = 0, numsteps_counter = 0;
+	const uint32_t ray_stride = cfg->ray_stride ? cfg->ray_stride : 1u;   /* data parallel: rank r of W marches ids r, r + W, ... */
 	for (uint32_t li = 0; li < n_rays_local; ++li) {
-		const uint32_t i = ray_offset + li;
+		const uint32_t i = ray_offset + li * ray_stride;
 		if (per_ray_numsteps) per_ray_numsteps[li] = 0;
 		uint32_t img = image_idx(i, n_rays_global, n_views);
 		const ngp_train_view* vw = &views[img];

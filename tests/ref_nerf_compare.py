@@ -21,7 +21,7 @@ def golden(name):
     return np.load(p)
 
 
-def compare_generation(name, want, g):
+def compare_generation(name, want, g, exact=False):
     """`want`: dict(n_samples, ray_indices, rays, numsteps, coords) from the oracle — or from this library's CUDA generator, which equals
     the oracle bit for bit (tests/test_gpu_march.py); `g`: the reference kernel's outputs"""
     k_ref, ns_ref = int(g["gen_counters"][0]), int(g["gen_counters"][1])
@@ -35,18 +35,20 @@ def compare_generation(name, want, g):
     # rays that produce samples: the same set up to rays grazing the occupied region
     both = set(rmap) & set(wmap)
     assert len(set(rmap) ^ set(wmap)) <= max(2, 0.003 * k_ref), (len(rmap), len(wmap))
-    same_count, checked = 0, 0
+    same_count, checked, rays_identical, coords_identical = 0, 0, 0, 0
     max_pos, max_dt, max_dir = 0.0, 0.0, 0.0
     for rid in sorted(both):
         rj, wj = rmap[rid], wmap[rid]
         # the unnormalised ray: identical arithmetic apart from FMA contraction in uv_to_ray / the lens undistortion
         assert np.allclose(ref_rays[rj], want["rays"][wj], rtol=0, atol=2e-6)
+        rays_identical += int(ref_rays[rj].tobytes() == want["rays"][wj].tobytes())
         rn, rb = ref_numsteps[rj]
         wn, wb = want["numsteps"][wj]
         if rn != wn:
             assert abs(int(rn) - int(wn)) <= max(2, 0.02 * int(rn))   # a sample flipped at a voxel face, not a different march
             continue
         same_count += 1
+        coords_identical += int(ref_coords[rb:rb + rn].tobytes() == want["coords"][wb:wb + wn].tobytes())
         if checked < 400:                                              # coordinates of a few hundred rays
             a, b = ref_coords[rb:rb + rn], want["coords"][wb:wb + wn]
             max_pos = max(max_pos, float(np.abs(a[:, :3] - b[:, :3]).max()))
@@ -55,7 +57,13 @@ def compare_generation(name, want, g):
             max_dir = max(max_dir, float(np.abs(a[:, 4:] - b[:, 4:]).max()))
             checked += 1
     print(f"{name}: {k_ref} rays, {ns_ref} samples (oracle {want['n_samples']}); identical step counts on {same_count}/{len(both)} rays; "
-          f"max |pos| diff {max_pos:.2e}, max |warped dt| diff {max_dt:.2e}, max |dir| diff {max_dir:.2e}")
+          f"max |pos| diff {max_pos:.2e}, max |warped dt| diff {max_dt:.2e}, max |dir| diff {max_dir:.2e}; bit-identical ray records {rays_identical}, "
+          f"bit-identical coordinate blocks {coords_identical}")
+    if exact:
+        # the reference build's arithmetic (NGP_MATH_REFERENCE): the north star's "bit-exact ray indices and sample counts"
+        assert set(rmap) == set(wmap), (len(set(rmap) ^ set(wmap)), "rays differ in whether they produce samples")
+        assert same_count == len(both), f"{len(both) - same_count} of {len(both)} rays differ in their sample count"
+        assert ns_ref == want["n_samples"]
     assert same_count >= 0.985 * len(both)
     assert abs(ns_ref - want["n_samples"]) <= 0.003 * ns_ref
     # Warped positions live in [0, 1].  The reference's t drifts by a few 1e-6 per ray against exact arithmetic: every empty-voxel

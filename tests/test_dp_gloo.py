@@ -1,7 +1,8 @@
 """CPU, world_size 2 over gloo: the data-parallel sharding rule of SURVEY.md §8(e) / DESIGN.md §6.
 
-Each rank generates the training rays of its shard with GLOBAL ray ids (the CUDA generator takes the same
-(ray_offset, n_rays_global) pair; tests/test_gpu_march.py checks it against this oracle), computes loss gradients normalised
+Each rank generates the training rays of its shard with GLOBAL ray ids — rank r of W takes ids r, r + W, r + 2W, ... (the interleaved
+partition of Testbed::train: every rank draws from every view); the CUDA generator takes the same (ray_offset, ray_stride,
+n_rays_global) triple; tests/test_gpu_march.py checks it against this oracle — computes loss gradients normalised
 by the global ray count and the network gradient of its samples; the ranks all-reduce (sum) the flat gradient.  The result
 must equal what one process computes for the whole batch."""
 import ctypes as C
@@ -39,7 +40,8 @@ def _shard_work(rank, world, n_rays_global):
     bf = util.sphere_bitfield(radius=0.3, max_cascade=0)
     rng = M.pcg32_seed(1337)
     n_local = n_rays_global // world
-    g = M.generate_training_samples(n_local, rank * n_local, n_rays_global, rng, cfg, views, len(views), bf, n_local * 256)
+    cfg.ray_stride = world
+    g = M.generate_training_samples(n_local, rank, n_rays_global, rng, cfg, views, len(views), bf, n_local * 256)
     k, ns = g["n_kept"], g["n_samples"]
     d, L = util.make_desc(n_levels=16, F=2, log2_T=12, aabb_scale=1)
     params = util.random_params(L, seed=0, trained_like=True).astype(np.float16)
@@ -73,7 +75,8 @@ def _worker(rank, world, port, n_rays_global, out_q):
     loss = torch.tensor([w["loss"]], dtype=torch.float64)
     dist.all_reduce(loss)
     if rank == 0:
-        out_q.put(dict(grad=g.numpy(), counts=cnt.numpy(), per_ray=torch.cat(per_ray).numpy(), loss=float(loss)))
+        # rank r holds global ids r, r + W, ...: interleave the per-rank lists back into id order
+        out_q.put(dict(grad=g.numpy(), counts=cnt.numpy(), per_ray=torch.stack(per_ray, dim=1).reshape(-1).numpy(), loss=float(loss)))
     dist.barrier()
     dist.destroy_process_group()
 

@@ -41,7 +41,7 @@ SCENES = [
 ]
 
 
-def run_generator(lib, scene, n_rays, max_samples, seed=1337, ray_offset=0, n_rays_global=None):
+def run_generator(lib, scene, n_rays, max_samples, seed=1337, ray_offset=0, n_rays_global=None, ray_stride=0, math_mode=0, lanes=0):
     import time
 
     import torch
@@ -50,6 +50,9 @@ def run_generator(lib, scene, n_rays, max_samples, seed=1337, ray_offset=0, n_ra
 
     imgs, cams, focal = S.make_dataset(n_images=7, width=96, height=64, radius=scene["radius"])
     cfg = util.make_train_cfg(aabb_scale=scene["aabb_scale"])
+    cfg.ray_stride = ray_stride
+    cfg.math_mode = math_mode
+    cfg.gen_lanes_per_ray = lanes   # 0: chosen from the batch size; otherwise that many lanes of a warp march one ray together
     bf = util.sphere_bitfield(radius=0.3, max_cascade=cfg.max_cascade, full=scene["full"])
     views, keep = util.make_views(imgs, cams, focal, lens=scene["lens"])
     t_views, tens = util.views_to_device(views, keep)
@@ -77,10 +80,13 @@ def run_generator(lib, scene, n_rays, max_samples, seed=1337, ray_offset=0, n_ra
 
 
 @pytest.mark.parametrize("scene", SCENES)
-@pytest.mark.parametrize("shard", [(0, None), (4096, 16384)])
+@pytest.mark.parametrize("shard", [(0, None, 0, 0), (4096, 16384, 0, 1), (3, 16384, 4, 4), (0, None, 0, 32), (0, None, 0, 8), (0, None, 0, 2)])
 def test_training_samples_bit_exact(lib, scene, shard):
+    """shard = (ray_offset, n_rays_global, ray_stride, lanes per ray): the whole batch with the automatic schedule; a contiguous shard, one
+    thread per ray; rank 3 of 4 with interleaved ids, 4 lanes per ray; the whole batch with a warp / 8 lanes / 2 lanes per ray"""
     n_rays, max_samples = 4096, 4096 * 1024
-    want, got, _ = run_generator(lib, scene, n_rays, max_samples, ray_offset=shard[0], n_rays_global=shard[1])
+    want, got, _ = run_generator(lib, scene, n_rays, max_samples, ray_offset=shard[0], n_rays_global=shard[1], ray_stride=shard[2], lanes=shard[3])
+    stride = shard[2] or 1
     assert want["n_samples"] <= max_samples, "test scene overflows: slot order would decide which rays are kept"
     assert want["n_samples"] > 1000, "degenerate scene"
     assert got["n_kept"] == want["n_kept"]
@@ -94,7 +100,7 @@ def test_training_samples_bit_exact(lib, scene, shard):
         gj = gmap[rid]
         wn, wb = want["numsteps"][wj]
         gn, gb = got["numsteps"][gj]
-        assert gn == wn == want["per_ray_numsteps"][rid - want.get("ray_offset", 0)]
+        assert gn == wn == want["per_ray_numsteps"][(rid - want.get("ray_offset", 0)) // stride]
         assert got["rays"][gj].tobytes() == want["rays"][wj].tobytes()
         assert got["coords"][gb:gb + gn].tobytes() == want["coords"][wb:wb + wn].tobytes()
     # slots tile [0, n_samples) without gaps or overlaps
@@ -314,148 +320,30 @@ def test_ray_ordered_inference_equals_full_inference_where_the_loss_reads(lib, s
     print("evaluated", n_eval, "of", ns, "consumed", int(consumed.sum()))
 
 
-@pytest.mark.parametrize("scene", SCENES[:2])
-@pytest.mark.parametrize("prefix", [16, 0, 64])
-def test_lazy_march_inference_equals_generate_all_where_the_loss_reads(lib, scene, prefix):
-    """prefix-only generator + march-inside-the-inference kernel (the default training schedule) against the reference
-    schedule generate-all -> evaluate-all: per ray id the same sample count, and bit-identical coordinates and network outputs
-    for every sample the loss kernel consumes"""
-    import torch
-
-    n_rays, max_samples = 4096, 4096 * 1024
-    want, got, ctx = run_generator(lib, scene, n_rays, max_samples)
-    cfg, dv = ctx["cfg"], ctx["dev"]
-    k, ns = got["n_kept"], got["n_samples"]
-    d, L = util.make_desc(n_levels=16, F=2, log2_T=16, aabb_scale=scene["aabb_scale"])
-    params = util.random_params(L, seed=41, trained_like=True)
-    params[64 * 32:64 * 32 + 64] = np.abs(params[64 * 32:64 * 32 + 64]) * 60.0
-    params = params.astype(np.float16)
-    t_p = dev(params)
-    full = torch.zeros(ns, 4, dtype=torch.float16, device="cuda")
-    assert lib.ngp_nerf_inference(C.byref(d), stream(), ns, dv["co"].data_ptr(), t_p.data_ptr(), full.data_ptr(), 4) == 0, lib.ngp_last_error()
-    batch = 1 << int(np.ceil(np.log2(max(ns, 2))))
-    t_coc = torch.zeros(batch, 7, dtype=torch.float32, device="cuda")
-    t_dl = torch.zeros(batch, 4, dtype=torch.float16, device="cuda")
-    t_md = dev(np.array([0.02], dtype=np.float32))
-    ns_full = dv["ns"].cpu().numpy().view(np.uint32)[:k].copy()
-    assert lib.ngp_nerf_compute_loss(stream(), n_rays, n_rays, ctx["rng"][0], ctx["rng"][1], C.byref(cfg), ctx["t_views"].data_ptr(), len(ctx["views"]), full.data_ptr(), batch,
-                                     dv["cnt"].data_ptr(), dv["ri"].data_ptr(), dv["rays"].data_ptr(), dv["ns"].data_ptr(), dv["co"].data_ptr(), t_coc.data_ptr(),
-                                     t_dl.data_ptr(), None, t_md.data_ptr()) == 0, lib.ngp_last_error()
-    torch.cuda.synchronize()
-    consumed = dv["ns"].cpu().numpy().view(np.uint32)[:k, 0]
-    full_h = full.cpu().numpy().view(np.uint16)
-    coords_full = got["coords"]
-    by_id_full = {int(r): (int(ns_full[j, 0]), int(ns_full[j, 1]), int(consumed[j])) for j, r in enumerate(got["ray_indices"][:k])}
-
-    # ---- the lazy schedule
-    l_cnt = torch.zeros(4, dtype=torch.int32, device="cuda")
-    l_ri = torch.zeros(n_rays, dtype=torch.int32, device="cuda")
-    l_rays = torch.zeros(n_rays, 6, dtype=torch.float32, device="cuda")
-    l_ns = torch.zeros(n_rays, 2, dtype=torch.int32, device="cuda")
-    l_tf = torch.zeros(n_rays, dtype=torch.float32, device="cuda")
-    l_co = torch.full((max_samples, 7), float("nan"), dtype=torch.float32, device="cuda")
-    l_out = torch.full((ns, 4), float("nan"), dtype=torch.float16, device="cuda")
-    assert lib.ngp_nerf_generate_training_samples_prefix(stream(), n_rays, 0, n_rays, ctx["rng"][0], ctx["rng"][1], C.byref(cfg), ctx["t_views"].data_ptr(),
-                                                         len(ctx["views"]), ctx["t_bf"].data_ptr(), max_samples, l_cnt.data_ptr(), l_ri.data_ptr(), l_rays.data_ptr(),
-                                                         l_ns.data_ptr(), l_co.data_ptr(), l_tf.data_ptr(), prefix) == 0, lib.ngp_last_error()
-    queue = l_cnt[3:4]
-    assert lib.ngp_nerf_march_inference_rays(C.byref(d), stream(), n_rays, C.byref(cfg), l_cnt.data_ptr(), queue.data_ptr(), l_ns.data_ptr(), l_rays.data_ptr(),
-                                             l_tf.data_ptr(), prefix, ctx["t_bf"].data_ptr(), l_co.data_ptr(), t_p.data_ptr(), l_out.data_ptr()) == 0, lib.ngp_last_error()
-    torch.cuda.synchronize()
-    cnt = l_cnt.cpu().numpy().view(np.uint32)
-    assert int(cnt[0]) == k and int(cnt[1]) == ns
-    l_ns_h, l_ri_h = l_ns.cpu().numpy().view(np.uint32), l_ri.cpu().numpy().view(np.uint32)
-    l_co_h, l_out_h = l_co.cpu().numpy(), l_out.cpu().numpy().view(np.uint16)
-    n_written = int((~np.isnan(l_co_h[:, 0])).sum())
-    for j in range(k):
-        rid = int(l_ri_h[j])
-        n_f, b_f, c_f = by_id_full[rid]
-        n_l, b_l = int(l_ns_h[j, 0]), int(l_ns_h[j, 1])
-        assert n_l == n_f
-        assert l_co_h[b_l:b_l + c_f].tobytes() == coords_full[b_f:b_f + c_f].tobytes(), f"coordinates of ray {rid}"
-        assert np.array_equal(l_out_h[b_l:b_l + c_f], full_h[b_f:b_f + c_f]), f"network outputs of ray {rid}"
-    assert n_written <= consumed.sum() + (8 + prefix) * k and n_written < ns
-    print("written", n_written, "of", ns, "coordinates; consumed", int(consumed.sum()))
-
-
 @pytest.mark.parametrize("scene", SCENES)
-def test_count_and_write_kernels_equal_the_fused_generator(lib, scene):
-    """the split generator of the training pipeline (counting kernel + warp-per-ray write kernel) against the oracle-checked
-    fused kernel: per ray id the same count, ray record and coordinates, bit for bit; slots tile [0, n_samples)"""
-    import torch
-
+def test_reference_flavour_stays_within_rounding_of_the_deterministic_one(lib, scene):
+    """NGP_MATH_REFERENCE (march_ref.cu: the reference build's fast-math arithmetic) against NGP_MATH_DETERMINISTIC on the same batch:
+    the same rays, sample counts equal on all but the rays that graze a voxel face, coordinates equal to ~1e-5.  (That the reference
+    flavour reproduces the reference KERNEL's counts exactly is tests/test_gpu_vs_reference_nerf.py.)"""
     n_rays, max_samples = 4096, 4096 * 1024
-    want, got, ctx = run_generator(lib, scene, n_rays, max_samples)
-    cfg = ctx["cfg"]
-    k, ns = got["n_kept"], got["n_samples"]
-    s_cnt = torch.zeros(4, dtype=torch.int32, device="cuda")
-    s_ri = torch.zeros(n_rays, dtype=torch.int32, device="cuda")
-    s_rays = torch.zeros(n_rays, 6, dtype=torch.float32, device="cuda")
-    s_ns = torch.zeros(n_rays, 2, dtype=torch.int32, device="cuda")
-    s_co = torch.full((max_samples, 7), float("nan"), dtype=torch.float32, device="cuda")
-    ck = torch.zeros(lib.ngp_nerf_generator_scratch_floats(n_rays), dtype=torch.float32, device="cuda")
-    sg = torch.zeros(lib.ngp_nerf_generator_scratch_u32(n_rays), dtype=torch.int32, device="cuda")
-    assert lib.ngp_nerf_count_training_samples(stream(), n_rays, 0, n_rays, ctx["rng"][0], ctx["rng"][1], C.byref(cfg), ctx["t_views"].data_ptr(), len(ctx["views"]),
-                                               ctx["t_bf"].data_ptr(), max_samples, s_cnt.data_ptr(), s_ri.data_ptr(), s_rays.data_ptr(), s_ns.data_ptr(),
-                                               ck.data_ptr(), sg.data_ptr()) == 0, lib.ngp_last_error()
-    assert lib.ngp_nerf_write_training_samples(stream(), n_rays, C.byref(cfg), ctx["t_bf"].data_ptr(), s_rays.data_ptr(), ck.data_ptr(), sg.data_ptr(),
-                                               s_co.data_ptr()) == 0, lib.ngp_last_error()
-    torch.cuda.synchronize()
-    cnt = s_cnt.cpu().numpy().view(np.uint32)
-    assert int(cnt[0]) == k and int(cnt[1]) == ns
-    ri, rays, nsb, co = s_ri.cpu().numpy().view(np.uint32), s_rays.cpu().numpy(), s_ns.cpu().numpy().view(np.uint32), s_co.cpu().numpy()
-    fmap = {int(r): j for j, r in enumerate(got["ray_indices"][:k])}
-    assert set(fmap) == {int(r) for r in ri[:k]}
-    for j in range(k):
-        fj = fmap[int(ri[j])]
-        n_f, b_f = got["numsteps"][fj]
-        n_s, b_s = nsb[j]
-        assert n_s == n_f
-        assert rays[j].tobytes() == got["rays"][fj].tobytes()
-        assert co[b_s:b_s + n_s].tobytes() == got["coords"][b_f:b_f + n_f].tobytes(), f"coordinates of ray {int(ri[j])}"
-    order = np.argsort(nsb[:k, 1])
-    ends = nsb[:k, 1][order] + nsb[:k, 0][order]
-    assert nsb[:k, 1][order][0] == 0 and np.array_equal(ends[:-1], nsb[:k, 1][order][1:]) and ends[-1] == ns
-    assert np.isnan(co[ns:, 0]).all()
-
-
-@pytest.mark.parametrize("scene", SCENES)
-def test_sorted_generator_equals_the_unsorted_one_per_ray(lib, scene):
-    """rays bucketed by expected march length before the generator: per ray id nothing changes; the order is longest first"""
-    import torch
-
-    n_rays, max_samples = 8192, 8192 * 1024
-    want, got, ctx = run_generator(lib, scene, n_rays, max_samples)
-    cfg = ctx["cfg"]
-    k, ns = got["n_kept"], got["n_samples"]
-    s_cnt = torch.zeros(4, dtype=torch.int32, device="cuda")
-    s_ri = torch.zeros(n_rays, dtype=torch.int32, device="cuda")
-    s_rays = torch.zeros(n_rays, 6, dtype=torch.float32, device="cuda")
-    s_ns = torch.zeros(n_rays, 2, dtype=torch.int32, device="cuda")
-    s_co = torch.full((max_samples, 7), float("nan"), dtype=torch.float32, device="cuda")
-    scratch = torch.zeros(lib.ngp_nerf_ray_sort_scratch_bytes(n_rays), dtype=torch.uint8, device="cuda")
-    assert lib.ngp_nerf_generate_training_samples_sorted(stream(), n_rays, 0, n_rays, ctx["rng"][0], ctx["rng"][1], C.byref(cfg), ctx["t_views"].data_ptr(),
-                                                         len(ctx["views"]), ctx["t_bf"].data_ptr(), max_samples, s_cnt.data_ptr(), s_ri.data_ptr(), s_rays.data_ptr(),
-                                                         s_ns.data_ptr(), s_co.data_ptr(), scratch.data_ptr()) == 0, lib.ngp_last_error()
-    torch.cuda.synchronize()
-    cnt = s_cnt.cpu().numpy().view(np.uint32)
-    assert int(cnt[0]) == k and int(cnt[1]) == ns
-    ri, rays, nsb, co = s_ri.cpu().numpy().view(np.uint32), s_rays.cpu().numpy(), s_ns.cpu().numpy().view(np.uint32), s_co.cpu().numpy()
-    fmap = {int(r): j for j, r in enumerate(got["ray_indices"][:k])}
-    assert set(fmap) == {int(r) for r in ri[:k]}
-    for j in range(k):
-        fj = fmap[int(ri[j])]
-        n_f, b_f = got["numsteps"][fj]
-        n_s, b_s = nsb[j]
-        assert n_s == n_f and rays[j].tobytes() == got["rays"][fj].tobytes()
-        assert co[b_s:b_s + n_s].tobytes() == got["coords"][b_f:b_f + n_f].tobytes()
-    # the permutation is a permutation, and it puts long rays together at the front: the per-warp spread of counts shrinks
-    perm = scratch[: n_rays * 4].cpu().numpy().view(np.uint32)
-    assert np.array_equal(np.sort(perm), np.arange(n_rays, dtype=np.uint32))
-    per_ray = np.zeros(n_rays, dtype=np.int64)
-    per_ray[got["ray_indices"][:k]] = got["numsteps"][:k, 0]
-    def waste(order):
-        w = per_ray[order].reshape(-1, 32)
-        return 1.0 - w.sum() / max(1, (w.max(axis=1) * 32).sum())
-    print("lane waste by sample count: batch order", waste(np.arange(n_rays)), "sorted", waste(perm))
-    assert waste(perm) < waste(np.arange(n_rays))
+    _, det, _ = run_generator(lib, scene, n_rays, max_samples)
+    _, ref, _ = run_generator(lib, scene, n_rays, max_samples, math_mode=1)
+    kd, kr = det["n_kept"], ref["n_kept"]
+    dmap = {int(r): j for j, r in enumerate(det["ray_indices"][:kd])}
+    rmap = {int(r): j for j, r in enumerate(ref["ray_indices"][:kr])}
+    assert len(set(dmap) ^ set(rmap)) <= max(2, 0.003 * kd)
+    same, worst = 0, 0.0
+    for rid in set(dmap) & set(rmap):
+        dn, db = det["numsteps"][dmap[rid]]
+        rn, rb = ref["numsteps"][rmap[rid]]
+        assert np.allclose(det["rays"][dmap[rid]], ref["rays"][rmap[rid]], rtol=0, atol=3e-6)
+        if dn == rn:
+            same += 1
+            worst = max(worst, float(np.abs(det["coords"][db:db + dn] - ref["coords"][rb:rb + rn]).max()))
+        else:
+            assert abs(int(dn) - int(rn)) <= max(2, 0.02 * int(dn))
+    assert same >= 0.985 * len(set(dmap) & set(rmap)) and worst < 3e-5
+    # slots tile [0, n_samples) in this flavour too
+    order = np.argsort(ref["numsteps"][:kr, 1])
+    ends = ref["numsteps"][:kr, 1][order] + ref["numsteps"][:kr, 0][order]
+    assert ref["numsteps"][:kr, 1][order][0] == 0 and np.array_equal(ends[:-1], ref["numsteps"][:kr, 1][order][1:]) and ends[-1] == ref["n_samples"]
