@@ -44,7 +44,16 @@ sys.path.insert(0, str(ROOT))
 
 BATCH = 1 << 18
 N_VIEWS, RES = 100, 800
-WORKLOAD = "nerf-synthetic-ball-100x800x800 L16 F2 T2^19 mlp64x(1,2) batch 2^18 aabb_scale 1"
+WORKLOADS = {
+    "fox": "nerf/fox (reference data/nerf/fox: 40 training views 1080x1920 of 50, every 5th held out; aabb_scale 4, cone stepping, OpenCV lens) "
+           "L16 F2 T2^19 mlp64x(1,2) batch 2^18",
+    "ball": "nerf-synthetic-ball-100x800x800 L16 F2 T2^19 mlp64x(1,2) batch 2^18 aabb_scale 1",
+}
+FOX_DIR = ROOT / "baseline" / "_ref" / "data" / "nerf" / "fox"
+REF_PYNGP = list((ROOT / "baseline" / "_ref").glob("pyngp*.so")) if (ROOT / "baseline" / "_ref").exists() else []
+# the unmodified reference application on a B200, same protocol (tools/ref_app.py), as recorded in profiles/r2/ — used only to label
+# the line when baseline/_ref is not on the box (then `reference_gpu.source` says "recorded")
+RECORDED_REFERENCE_GPU = {"fox": {"ms_per_step": 2.556, "samples_per_sec": 109.0e6, "psnr_mean": 26.032, "render_1080p_ms_best": 33.17, "source": "recorded: profiles/r2/refapp_fox.md"}}
 
 
 def pkg():
@@ -53,6 +62,16 @@ def pkg():
 
 def syn():
     return importlib.import_module("instant-ngp_b200.synthetic")
+
+
+def ref_app():
+    if str(ROOT / "tools") not in sys.path:
+        sys.path.insert(0, str(ROOT / "tools"))
+    return importlib.import_module("ref_app")
+
+
+def default_scene() -> str:
+    return "fox" if (FOX_DIR / "transforms.json").exists() else "ball"
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -133,22 +152,24 @@ class ClockSampler:
                 "samples": len(self.sm)}
 
 
-class DevicePtrTensor:
-    """zero-copy torch view of a device buffer owned by libngp_b200 (for the NCCL all-reduce)"""
-
-    def __init__(self, ptr: int, n: int, typestr: str):
-        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
-
-
-def build_testbed(rank: int, world: int, n_views: int = N_VIEWS, res: int = RES, device: int = 0):
+def build_testbed(scene: str, n_views: int = N_VIEWS, res: int = RES, device: int = 0):
+    """returns (testbed, host copies of the training images for the e2e leg, scene info)"""
     P, S = pkg(), syn()
     tb = P.Testbed(P.TestbedMode.Nerf, device=device)
-    imgs, cams, focal = S.make_dataset(n_images=n_views, width=res, height=res)
-    S.load_into_testbed(tb, imgs, cams, focal, aabb_scale=1)
+    if scene == "fox":
+        R = ref_app()
+        split, _ = R.fox_split()
+        tb.load_training_data(str(split["train"]))
+        NL = importlib.import_module("instant-ngp_b200.nerf_loader")
+        host = [NL.read_image_bytes_rgba(im["path"], tb.dataset["white_transparent"], tb.dataset["black_transparent"]) for im in tb.dataset["images"]]
+        info = dict(n_views=len(host), test_split=str(split["test"]))
+    else:
+        imgs, cams, focal = S.make_dataset(n_images=n_views, width=res, height=res)
+        S.load_into_testbed(tb, imgs, cams, focal, aabb_scale=1)
+        host = [imgs[i] for i in range(imgs.shape[0])]
+        info = dict(n_views=n_views, cams=cams, focal=focal, imgs=imgs)
     tb.reload_network_from_json(S.base_config(16, 2, 19))
-    if world > 1:
-        tb.set_data_parallel(rank, world)
-    return tb, imgs, cams, focal
+    return tb, host, info
 
 
 def peaks() -> dict:
@@ -208,7 +229,7 @@ def cpu_training_sample(n_rays: int = 2048, n_net: int = 16384):
     return sps, desc, os.cpu_count() or 1
 
 
-def run_reference_arm(args) -> None:
+def run_reference_arm(args, scene: str) -> None:
     """--impl reference: the CPU oracle port on the host cores (tiny-cuda-nn has no CPU path), rank 0 only.  Every step is a bounded
     sample of the workload; the sample shrinks if W + K steps of the first size would not finish within ~2.5 minutes."""
     rank = int(os.environ.get("RANK", "0"))
@@ -235,7 +256,7 @@ def run_reference_arm(args) -> None:
     line = {
         "impl": "reference", "metric": "nerf_training_samples_per_sec", "value": v, "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "note": "tiny-cuda-nn has no CPU implementation (SURVEY.md §0.2); this is the CPU oracle port of the same path on a bounded sample per step"},
+        "config": {"workload": WORKLOADS[scene], "note": "tiny-cuda-nn has no CPU implementation (SURVEY.md §0.2); this is the CPU oracle port of the same path on a bounded sample per step"},
         "cpu_baseline": {"value": v, "unit": "samples/s", "cores": os.cpu_count() or 1, "kind": "port", "sample": desc + " (last step's size; shrunk to keep W + K steps within ~2.5 min)"},
         "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -243,6 +264,35 @@ def run_reference_arm(args) -> None:
 
 
 # ---------------------------------------------------------------------------------------------------------------------
+def reference_gpu_arm(scene: str, steps: int = 1000) -> dict:
+    """the UNMODIFIED reference application (baseline/_ref/pyngp*.so, built by baseline/build_ref.sh) on this box, same scene, same
+    protocol (tools/ref_app.py: steady-state ms/step over steps 500..1000, PSNR on the held-out views, 1920x1080 render), in a
+    subprocess so that nothing of it shares a process with this library"""
+    if not REF_PYNGP:
+        rec = dict(RECORDED_REFERENCE_GPU.get(scene, {}))
+        rec.setdefault("source", "unavailable: baseline/_ref/pyngp*.so is not on this box (baseline/build_ref.sh builds it where /root/reference exists)")
+        return rec
+    out = ROOT / "gpurun_out" / f"bench_reference_gpu_{scene}.json"
+    out.parent.mkdir(parents=True, exist_ok=True)
+    cmd = [sys.executable, str(ROOT / "tools" / "ref_app.py"), "--impl", "reference", "--scene", scene, "--enc", "L16F2", "--jit", "1", "--train-mode", "Nerf",
+           "--steps", str(steps), "--out", str(out)]
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+        j = json.loads(out.read_text())
+        for ext in (".ingp", ".npz"):
+            try:
+                out.with_suffix(ext).unlink()
+            except OSError:
+                pass
+        keep = ("ms_per_step", "samples_per_sec", "rays_per_sec", "samples_per_sec_nominal", "steady_window", "counters", "psnr_mean", "n_test_views",
+                "render_1080p_ms_best", "render_1080p_mrays_per_sec", "jit", "train_mode", "enc")
+        rec = {k: j[k] for k in keep if k in j}
+        rec["source"] = "measured in this run: tools/ref_app.py --impl reference (pyngp from baseline/_ref, unmodified reference, GUI off, sm_100)"
+        return rec
+    except Exception as e:  # the reference arm never takes this arm's line down
+        return {"source": f"failed: {type(e).__name__}: {e}"[:300]}
+
+
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -251,17 +301,20 @@ def main() -> None:
     ap.add_argument("--pretrain", type=int, default=700, help="untimed set-up steps before the warm-up: the metric is STEADY-STATE training throughput "
                     "(SURVEY 8d: steps 500-1000), and the per-step workload (rays, samples per ray) only settles once the scene has formed")
     ap.add_argument("--impl", default="ngp_b200", choices=["ngp_b200", "reference"])
+    ap.add_argument("--scene", default=None, choices=["fox", "ball"], help="default: fox when baseline/_ref/data/nerf/fox is on the box, else the synthetic ball")
     ap.add_argument("--views", type=int, default=N_VIEWS)
     ap.add_argument("--res", type=int, default=RES)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-reference-gpu", action="store_true", help="skip the reference application's run on this GPU (extra key `reference_gpu`, N = 1)")
     ap.add_argument("--no-overlap", action="store_true", help="disable the side-stream prefetch of the next step's sample generation")
     ap.add_argument("--chunk", type=int, default=0, help="ray-ordered inference chunk (4 or 8)")
-    ap.add_argument("--overlap", action="store_true", help="enable the side-stream prefetch of the next step's sample generation")
     ap.add_argument("--full-inference", action="store_true", help="evaluate every generated sample like the reference schedule")
     ap.add_argument("--no-render", action="store_true", help="skip the 1920x1080 render timing (reported under the extra key `render`)")
+    ap.add_argument("--option", action="append", default=[], help="name=value passed to Testbed._set before training")
     args = ap.parse_args()
+    scene = args.scene or default_scene()
     if args.impl == "reference":
-        run_reference_arm(args)
+        run_reference_arm(args, scene)
         return
     assert args.warmup >= 3, "timing rules: at least 3 warm-up steps"
 
@@ -279,33 +332,25 @@ def main() -> None:
     __import__("__graft_entry__").build() if not (ROOT / "instant-ngp_b200" / "libngp_b200.so").exists() else None
     P = pkg()
     lib = P.load_library()
-    tb, imgs, scene_cams, scene_focal = build_testbed(rank, world, args.views, args.res, device=local_rank)
+    tb, host_images, info = build_testbed(scene, args.views, args.res, device=local_rank)
+    n_views = info["n_views"]
     if args.no_overlap:
         tb._set("nerf.training.overlap_sample_generation", 0.0)
     if args.chunk:
         tb._set("nerf.training.inference_chunk", float(args.chunk))
-    if args.overlap:
-        tb._set("nerf.training.overlap_sample_generation", 1.0)
     if args.full_inference:
         tb._set("nerf.training.full_inference", 1.0)
-    n_params = tb.n_params
-
-    grads_t = counters_t = None
+    for kv in args.option:
+        k, v = kv.split("=")
+        tb._set(k, float(v))
     if world > 1:
-        grads_t = torch.as_tensor(DevicePtrTensor(tb.grads_ptr(), n_params, "<f2"), device=torch.device("cuda", local_rank))
+        # torch.distributed is the plumbing that hands rank 0's NCCL id to the other ranks; the step's collectives are the library's own
+        ids = [tb.dp_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        tb.init_data_parallel(rank, world, ids[0])
 
     def step():
-        if world == 1:
-            tb.train(BATCH)
-        else:
-            tb.train_front(BATCH)          # generation .. loss
-            nonlocal counters_t
-            if counters_t is None:
-                counters_t = torch.as_tensor(DevicePtrTensor(tb.dp_counters_ptr(), 4, "<i4"), device=torch.device("cuda", local_rank))
-            dist.all_reduce(counters_t)    # 16 bytes: ray / sample counters for the shared rays_per_batch controller
-            tb.train_back()                # forward/backward queued; next step's generator queued behind it on a side stream
-            dist.all_reduce(grads_t)       # one NCCL all-reduce of the flat fp16 gradient buffer (hash grid + MLPs), beside that generator
-            tb.train_apply_grads()         # optimizer
+        tb.train(BATCH)   # N > 1: counters + gradient all-reduce inside (ngp_testbed_init_dp)
 
     def sync_all():
         torch.cuda.synchronize()
@@ -351,14 +396,14 @@ def main() -> None:
     tb.set_profiling(False)
 
     # ---- e2e: one training view streamed from pinned host memory per step + counters/loss read back
-    pinned = torch.from_numpy(np.ascontiguousarray(imgs)).pin_memory()   # the whole image set in pinned host memory, one view re-sent per step
-    h2d_bytes = pinned[0].numel() * 4
+    pinned = [torch.from_numpy(np.ascontiguousarray(im)).pin_memory() for im in host_images]   # the image set in pinned host memory, one view re-sent per step
+    h2d_bytes = pinned[0].numel() * pinned[0].element_size()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2e_samples = 0
     sync_all()
     f0.record()
     for i in range(args.steps):
-        tb.update_image_async(i % args.views, pinned[i % args.views].data_ptr())   # H2D of this step's training view
+        tb.update_image_async(i % n_views, pinned[i % n_views].data_ptr())   # H2D of this step's training view
         step()
         e2e_samples += tb.counters()["measured_batch_size"]        # D2H: counters (16 B) each step, loss every 16th
         _ = tb.loss
@@ -366,14 +411,55 @@ def main() -> None:
     sync_all()
     ms_e2e = f0.elapsed_time(f1)
 
+    # ---- render: 1920x1080 from training view 0's pose; N > 1: row tiles sharded over the ranks + exchange of tiles
+    render = None
+    if not args.no_render:
+        W, H = 1920, 1080
+        if scene == "fox":
+            tb.set_camera_to_training_view(0)
+            tb.render_with_lens_distortion = False     # what the reference's Python render() does (python_api.cu:212)
+            cam, focal, center = tb._camera.render_args(W, H)
+        else:
+            cam, center = syn().sphere_cameras(8, radius=1.3)[3], (0.5, 0.5)
+            focal = 0.5 * H / np.tan(0.5 * np.deg2rad(40.0))
+        rgba = torch.zeros(H, W, 4, device="cuda")
+        depth = torch.zeros(H, W, device="cuda")
+
+        def frame():
+            if world > 1:
+                tb.render_device_sharded(W, H, cam, focal, rgba.data_ptr(), depth.data_ptr(), center)
+            else:
+                tb.render_device(W, H, cam, focal, rgba.data_ptr(), depth.data_ptr(), center)
+
+        for _ in range(3):
+            frame()
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sync_all()
+        r0.record()
+        for _ in range(10):
+            frame()
+        r1.record()
+        sync_all()
+        render_ms = torch.tensor([r0.elapsed_time(r1) / 10], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(render_ms, op=dist.ReduceOp.MAX)
+        render = {"ms_per_frame": float(render_ms), "mrays_per_sec": W * H / float(render_ms) / 1e3, "resolution": [W, H],
+                  "coverage": float((rgba[..., 3] > 0.5).float().mean()), "sharding": f"{world} row tiles + ncclBroadcast of every tile" if world > 1 else "none",
+                  "min_transmittance": 0.01, "pose": "training view 0" if scene == "fox" else "orbit camera 3"}
+
     # ---- reduce over ranks: time = max, work = sum
     t = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device="cuda")
-    w = torch.tensor([samples, e2e_samples, rays], dtype=torch.float64, device="cuda")
+    w = torch.tensor([samples, e2e_samples, rays, pre], dtype=torch.float64, device="cuda")
+    ph = torch.tensor([phases[k] for k in tb.PHASES], dtype=torch.float64, device="cuda")
+    ph_all = None
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(w)
+        gathered = [torch.zeros_like(ph) for _ in range(world)]
+        dist.all_gather(gathered, ph)
+        ph_all = torch.stack(gathered).cpu().numpy()
     ms_total, ms_e2e = t.tolist()
-    samples, e2e_samples, rays = w.tolist()
+    samples, e2e_samples, rays, pre = w.tolist()
 
     if rank == 0:
         value = samples / (ms_total * 1e-3)
@@ -386,54 +472,74 @@ def main() -> None:
         fb_ms = phases["forward_backward"] / n_fb
         alg_bytes = 1572.0 * BATCH
         achieved = alg_bytes / (fb_ms * 1e-3) / 1e9 if fb_ms > 0 else None
+        sm_mhz = clocks.get("sm_mhz") or 1965.0
         roofline = {"bound": "hbm", "kernel": "k_nerf_train (+k_mlp_grads_finalize)", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
                     "frac": (achieved / pk["hbm_gbs"]) if achieved else None, "traffic": K_NERF_TRAIN_DRAM_BYTES, "peak_source": pk["source"], "ms_per_launch": fb_ms,
                     "algorithmic_bytes_per_launch": alg_bytes,
-                    "traffic_source": "profiles/r1e_end_of_round.md",
-                    # what actually bounds the kernel: the SM load/store unit takes scattered 4/8-byte accesses at ~1 lane per clock
-                    # (B300_MICROARCH.md: REDG 1.29 cyc/lane, spread addresses).  Per sample: 16 levels x 8 corners gathered + reduced, x-neighbour
-                    # pairs sharing one access when adjacent and aligned (half of them): 96 + 96 lane accesses.
-                    "lsu_floor": {"lane_accesses_per_sample": 192, "cycles_per_lane": 1.29, "sm_count": 148, "sm_mhz": clocks.get("sm_mhz") or 1965.0,
-                                  "floor_ms": 192 * 1.29 * BATCH / 148 / ((clocks.get("sm_mhz") or 1965.0) * 1e3),
-                                  "frac": (192 * 1.29 * BATCH / 148 / ((clocks.get("sm_mhz") or 1965.0) * 1e3)) / fb_ms if fb_ms > 0 else None},
-                    "note": "the 26 MB fp16 table and its gradient table are L2-resident on B200: the kernel is bound by L2 gather/reduction latency, DRAM traffic is an eighth of the algorithmic bytes"}
+                    "traffic_source": "profiles/r1e_end_of_round.md (synthetic scene; per launch)",
+                    "note": "the 26 MB fp16 table and its gradient table are L2-resident on B200: the kernel is bound by L2 gather/reduction traffic and latency, DRAM traffic is an eighth of the algorithmic bytes"}
+        # second kernel of the step by time: the sample generator.  Algorithmic bytes: the 28-byte coordinate record of every generated sample
+        # (SURVEY 8d "1 march step": the bit test itself is L1/L2 resident); it is latency bound (a serial log/exp recurrence per ray), which
+        # is what the fraction says.
+        gen_ms = phases["sample_generation"] / n_fb
+        gen_bytes = 28.0 * pre / args.steps / world
+        roofline_gen = {"bound": "hbm", "kernel": "k_generate_training_samples", "achieved": gen_bytes / (gen_ms * 1e-3) / 1e9 if gen_ms > 0 else None, "peak": pk["hbm_gbs"],
+                        "unit": "GB/s", "frac": (gen_bytes / (gen_ms * 1e-3) / 1e9 / pk["hbm_gbs"]) if gen_ms > 0 else None, "traffic": None, "ms_per_launch": gen_ms,
+                        "algorithmic_bytes_per_launch": gen_bytes, "note": "latency bound: per ray a serial recurrence t -> t + dt(t) through log/exp; see gen_kernel.cuh"}
         line = {
             "metric": "nerf_training_samples_per_sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
-            "config": {"workload": WORKLOAD if (args.views, args.res) == (N_VIEWS, RES) else f"synthetic ball {args.views}x{args.res}^2 L16F2T19 batch 2^18",
-                       "batch_per_gpu": BATCH, "l2_policy": "inputs larger than L2: 1.0 GB image set + 340 MB parameter/optimizer state per step, no explicit flush",
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",
+            "data": "reference data/nerf/fox (real photographs shipped in baseline/_ref), random-init weights" if scene == "fox" else "synthetic",
+            "config": {"workload": WORKLOADS[scene] if scene == "fox" or (args.views, args.res) == (N_VIEWS, RES) else f"synthetic ball {args.views}x{args.res}^2 L16F2T19 batch 2^18",
+                       "batch_per_gpu": BATCH,
+                       "l2_policy": "inputs larger than L2: %.2f GB image set + 340 MB parameter/optimizer state per step, no explicit flush" % (sum(x.numel() * x.element_size() for x in pinned) / 1e9),
                        "parallelism": f"dp{world}", "pretrain_steps": args.pretrain,
-                       "timed_steps": f"{args.pretrain + args.warmup}..{args.pretrain + args.warmup + args.steps} of a from-scratch training run"},
+                       "timed_steps": f"{args.pretrain + args.warmup}..{args.pretrain + args.warmup + args.steps} of a from-scratch training run",
+                       "march_arithmetic": "reference build (--use_fast_math expression trees, march_ref.cu)" if tb._get("nerf.training.math_mode") == 1 else "deterministic (ngp_detmath.h)"},
             "rays_per_sec": rays / (ms_total * 1e-3),
-            "per_step": {"rays": rays / args.steps / world, "samples_before_compaction": pre / args.steps, "samples_compacted": samples / args.steps / world},
+            "per_step": {"rays": rays / args.steps / world, "samples_before_compaction": pre / args.steps / world, "samples_compacted": samples / args.steps / world},
             "phase_ms_per_step": {k: v / n_fb for k, v in phases.items() if k != "steps"},
             "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 20, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": roofline,
+            "roofline_generator": roofline_gen,
         }
-        if not args.no_render:
-            S = syn()
-            cam = S.sphere_cameras(8, radius=1.3)[3]
-            W, H = 1920, 1080
-            focal = 0.5 * H / np.tan(0.5 * np.deg2rad(40.0))
-            rgba = torch.zeros(H, W, 4, device="cuda")
-            depth = torch.zeros(H, W, device="cuda")
-            for _ in range(3):
-                tb.render_device(W, H, cam, focal, rgba.data_ptr(), depth.data_ptr())
-            r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            torch.cuda.synchronize()
-            r0.record()
-            for _ in range(10):
-                tb.render_device(W, H, cam, focal, rgba.data_ptr(), depth.data_ptr())
-            r1.record()
-            torch.cuda.synchronize()
-            ms = r0.elapsed_time(r1) / 10
-            line["render"] = {"ms_per_frame": ms, "mrays_per_sec": W * H / ms / 1e3, "resolution": [W, H], "coverage": float((rgba[..., 3] > 0.5).float().mean())}
-            # quality of the model the timed steps produced: PSNR of training view 0 re-rendered at its own resolution
-            got = tb.render(args.res, args.res, scene_cams[0], scene_focal)
-            mse = float(np.mean((np.clip(got[..., :3], 0, 1) - imgs[0][..., :3]) ** 2))
-            line["quality"] = {"psnr_db_train_view_0": 10.0 * np.log10(1.0 / max(mse, 1e-12)), "after_steps": int(tb.training_step)}
+        if ph_all is not None:
+            line["phase_ms_per_step_by_rank"] = {k: [float(x) / n_fb for x in ph_all[:, i]] for i, k in enumerate(tb.PHASES)}
+        if render is not None:
+            line["render"] = render
+        if world == 1 and not args.no_render:
+            # quality of the model the timed steps produced
+            if scene == "fox":
+                R = ref_app()
+                tb.shall_train = False
+                tb.background_color = [0.0, 0.0, 0.0, 1.0]
+                tb.snap_to_pixel_centers = True
+                tb.nerf.render_min_transmittance = 1e-4
+                steps_done = int(tb.training_step)
+                tb.load_training_data(info["test_split"])
+                ps = []
+                for i in range(len(tb.dataset["images"])):
+                    v = tb.training_view(i)
+                    wv, hv = (int(x) for x in v["resolution"])
+                    tb.set_camera_to_training_view(i)
+                    img = tb.render(wv, hv, 1, True)       # reference-shaped call: no lens, like the reference's Python render()
+                    ps.append(R.psnr_srgb(img, R.load_gt_srgb(Path(tb.dataset["images"][i]["path"])))[0])
+                line["quality"] = {"psnr_db_held_out_views": float(np.mean(ps)), "n_views": len(ps), "after_steps": steps_done,
+                                   "protocol": "scripts/run.py:257-317 with scripts/scenes.py test_every = 5; reference-shaped render() (its Python render ignores the lens: 26.0 dB for the reference too)"}
+            else:
+                got = tb.render(args.res, args.res, info["cams"][0], info["focal"])
+                mse = float(np.mean((np.clip(got[..., :3], 0, 1) - info["imgs"][0][..., :3]) ** 2))
+                line["quality"] = {"psnr_db_train_view_0": 10.0 * np.log10(1.0 / max(mse, 1e-12)), "after_steps": int(tb.training_step)}
+        if world == 1 and not args.no_reference_gpu:
+            del tb
+            torch.cuda.empty_cache()
+            line["reference_gpu"] = reference_gpu_arm(scene)
+            rg = line["reference_gpu"]
+            if rg.get("samples_per_sec"):
+                line["vs_reference_gpu"] = {"samples_per_sec_ratio": value / rg["samples_per_sec"], "ms_per_step_ratio": rg["ms_per_step"] / (ms_total / args.steps),
+                                            "definition": "this repo / reference application, same box, same scene, same batch; > 1 = faster than the reference"}
         if world == 1 and not args.no_cpu_baseline:
             sps, desc, cores = cpu_training_sample()
             line["cpu_baseline"] = {"value": sps, "unit": "samples/s", "cores": cores, "kind": "port", "sample": desc}

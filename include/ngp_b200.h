@@ -393,7 +393,22 @@ int ngp_testbed_set_option(ngp_testbed* t, const char* name, double value); /* n
 double ngp_testbed_get_option(ngp_testbed* t, const char* name);
 /* Testbed::train(batch_size): density-grid prep on the reference's schedule, one training step, optimizer step. */
 int ngp_testbed_train(ngp_testbed* t, uint32_t batch_size);
-/* Split form for data-parallel training: grads of this rank's ray shard, then (after the caller's all-reduce over
+/* Data parallel training, one process per GPU (the reference has none).  Rank 0 calls ngp_dp_unique_id and hands the
+ * ngp_dp_unique_id_bytes() bytes to every rank by any means (a torch.distributed / MPI broadcast, a file); every rank then calls
+ * ngp_testbed_init_dp.  From then on ngp_testbed_train is the whole data-parallel step: rank r of W marches the global ray ids
+ * r, r + W, ... of a batch of W x rays_per_batch rays (every rank draws from every view; image selection and the per-ray random stream are
+ * keyed on the global id), the 16-byte counter block is summed over the ranks on a communication stream beside the forward/backward
+ * kernel (the rays_per_batch controller stays identical on all ranks), ONE ncclAllReduce sums the flat fp16 gradient buffer (hash grid +
+ * MLPs) on the training stream, and every rank runs the identical optimizer step.  NCCL is loaded at run time (libnccl.so.2). */
+size_t ngp_dp_unique_id_bytes(void);
+int ngp_dp_unique_id(uint8_t* out, size_t capacity);
+int ngp_testbed_init_dp(ngp_testbed* t, uint32_t rank, uint32_t world, const uint8_t* unique_id, size_t n_bytes);
+/* Render sharded by row tiles: rank r renders rows ngp_dp_rows(r, W, height) of the frame into its own full-size device buffers
+ * (ngp_testbed_render_device with y0, y1), then ngp_testbed_gather_rows exchanges the tiles (one ncclBroadcast per rank, in place,
+ * on the Testbed's stream): every rank ends up with the whole frame. */
+void ngp_dp_rows(uint32_t rank, uint32_t world, int32_t height, int32_t* y0, int32_t* y1);
+int ngp_testbed_gather_rows(ngp_testbed* t, int32_t width, int32_t height, float* rgba_dev, float* depth_dev);
+/* Split form for data-parallel training with the CALLER's collectives: grads of this rank's ray shard, then (after the caller's all-reduce over
  * ngp_testbed_grads()) the optimizer step.  rank/world partition the global ray batch. */
 int ngp_testbed_set_dp(ngp_testbed* t, uint32_t rank, uint32_t world);
 int ngp_testbed_train_compute_grads(ngp_testbed* t, uint32_t batch_size);
@@ -452,8 +467,9 @@ int ngp_testbed_sync(ngp_testbed* t);
 /* Per-phase device time of Testbed::train, measured with CUDA events on the Testbed stream (the reference only has host
  * wall-clock EMAs m_training_prep_ms / m_training_ms, testbed.h:1023-1027).  Phases: 0 occupancy-grid update, 1 training
  * sample generation, 2 inference over the generated samples, 3 loss + compaction + roll-over, 4 fused forward/backward,
- * 5 optimizer.  get_phase_ms returns the accumulated milliseconds and the number of steps since the last call. */
-#define NGP_N_PHASES 6
+ * 5 optimizer, 6 gradient all-reduce (data parallel through ngp_testbed_init_dp).  get_phase_ms returns the accumulated
+ * milliseconds and the number of steps since the last call. */
+#define NGP_N_PHASES 7
 int ngp_testbed_set_profiling(ngp_testbed* t, int enable);
 int ngp_testbed_get_phase_ms(ngp_testbed* t, float* ms_out, uint32_t* n_steps);
 /* Streaming data: overwrite training image `idx` (already set once with ngp_testbed_set_image / _set_image_bytes, same size and

@@ -201,6 +201,11 @@ PROTOTYPES = {
     "ngp_testbed_get_option": (C.c_double, [vp, cp]),
     "ngp_testbed_train": (C.c_int, [vp, u32]),
     "ngp_testbed_set_dp": (C.c_int, [vp, u32, u32]),
+    "ngp_dp_unique_id_bytes": (C.c_size_t, []),
+    "ngp_dp_unique_id": (C.c_int, [vp, C.c_size_t]),
+    "ngp_testbed_init_dp": (C.c_int, [vp, u32, u32, vp, C.c_size_t]),
+    "ngp_dp_rows": (None, [u32, u32, C.c_int32, P(C.c_int32), P(C.c_int32)]),
+    "ngp_testbed_gather_rows": (C.c_int, [vp, C.c_int32, C.c_int32, vp, vp]),
     "ngp_testbed_train_compute_grads": (C.c_int, [vp, u32]),
     "ngp_testbed_train_front": (C.c_int, [vp, u32]),
     "ngp_testbed_train_back": (C.c_int, [vp]),

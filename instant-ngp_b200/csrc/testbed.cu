@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "dp_nccl.h"
 #include "host_util.h"
 #include "json_mini.h"
 #include "march.cuh"
@@ -240,6 +241,10 @@ struct ngp_testbed {
 
 	// data parallel
 	uint32_t dp_rank = 0, dp_world = 1;
+	// the exchange inside the library (ngp_testbed_init_dp): gradients on the training stream, counters / loss partials on comm_stream
+	ngpb::NcclApi::comm_t comm_grads = nullptr, comm_small = nullptr;
+	cudaStream_t comm_stream = nullptr;
+	cudaEvent_t ev_counters_ready = nullptr;
 
 	// profiling (CUDA events per phase)
 	bool profiling = false;
@@ -264,7 +269,11 @@ struct ngp_testbed {
 			cudaStreamSynchronize(side_stream);
 			cudaStreamDestroy(side_stream);
 		}
-		for (cudaEvent_t e : {ev_front_done, ev_prefetch_done, ev_main_ready, ev_back_done})
+		if (comm_stream) cudaStreamSynchronize(comm_stream);
+		if (comm_grads) ngpb::NcclApi::get().CommDestroy(comm_grads);
+		if (comm_small) ngpb::NcclApi::get().CommDestroy(comm_small);
+		if (comm_stream) cudaStreamDestroy(comm_stream);
+		for (cudaEvent_t e : {ev_front_done, ev_prefetch_done, ev_main_ready, ev_back_done, ev_counters_ready})
 			if (e) cudaEventDestroy(e);
 		if (readback) cudaFreeHost(readback);
 		for (void* p : pixel_bufs)
@@ -612,11 +621,30 @@ static void tb_front(ngp_testbed* t, uint32_t batch) {
 static void tb_update_controller(ngp_testbed* t);
 static void tb_prefetch(ngp_testbed* t);
 
-// `early_controller`: read the counters and prefetch now (requires that, data parallel, the counter block has been summed)
+// The counter block (and, every 16th step, the loss partials) summed over the ranks on the communication stream, beside the
+// forward/backward kernel: the rays_per_batch controller (NerfCounters::update_after_training) sees the same numbers on every rank,
+// and nothing of it is on the training stream's critical path.
+static void tb_exchange_counters(ngp_testbed* t) {
+	const ngpb::NcclApi& nccl = ngpb::NcclApi::get();
+	NGPB_CUDA_CHECK(cudaEventRecord(t->ev_counters_ready, t->stream));
+	NGPB_CUDA_CHECK(cudaStreamWaitEvent(t->comm_stream, t->ev_counters_ready, 0));
+	nccl.check(nccl.AllReduce(t->dp_counters.p, t->dp_counters.p, 4, ngpb::NcclApi::ncclUint32, ngpb::NcclApi::ncclSum, t->comm_small, t->comm_stream), "ncclAllReduce(counters)");
+	NGPB_CUDA_CHECK(cudaMemcpyAsync(&t->readback->counters, t->dp_counters.p, sizeof(ngp_nerf_counters), cudaMemcpyDeviceToHost, t->comm_stream));
+	if (t->get_loss_pending) {
+		nccl.check(nccl.AllReduce(t->reduce_scratch.p, t->reduce_scratch.p, 1024, ngpb::NcclApi::ncclFloat32, ngpb::NcclApi::ncclSum, t->comm_small, t->comm_stream), "ncclAllReduce(loss)");
+		NGPB_CUDA_CHECK(cudaMemcpyAsync(t->readback->loss_partial, t->reduce_scratch.p, sizeof(float) * 1024, cudaMemcpyDeviceToHost, t->comm_stream));
+	}
+	NGPB_CUDA_CHECK(cudaEventRecord(t->ev_front_done, t->comm_stream));
+}
+
+// `early_controller`: read the counters and prefetch now (requires that, data parallel, the counter block has been summed — by the
+// caller, or by tb_exchange_counters when the library owns the communicators)
 static void tb_back(ngp_testbed* t, bool early_controller) {
 	NGPB_CHECK(t->front_done, "training step parts out of order: back without front");
 	ngp_testbed::RaySet& rs = t->set[t->cur];
-	if (t->dp_world == 1 || early_controller) {
+	if (t->dp_world > 1 && t->comm_small && early_controller) {
+		tb_exchange_counters(t);
+	} else if (t->dp_world == 1 || early_controller) {
 		NGPB_CUDA_CHECK(cudaMemcpyAsync(&t->readback->counters, t->dp_world == 1 ? rs.counters.p : t->dp_counters.p, sizeof(ngp_nerf_counters),
 			cudaMemcpyDeviceToHost, t->stream));
 		NGPB_CUDA_CHECK(cudaEventRecord(t->ev_front_done, t->stream));
@@ -1096,11 +1124,83 @@ int ngp_testbed_train_compute_grads(ngp_testbed* t, uint32_t batch) { NGPB_TRY(t
 int ngp_testbed_train_front(ngp_testbed* t, uint32_t batch) { NGPB_TRY(tb_front(t, batch)); }
 int ngp_testbed_train_back(ngp_testbed* t) { NGPB_TRY(tb_back(t, true)); }
 int ngp_testbed_train_apply_grads(ngp_testbed* t) { NGPB_TRY(tb_apply_grads(t)); }
+// One NCCL all-reduce (sum) of the flat fp16 gradient buffer — hash grid + MLPs, the buffer the optimizer reads (trainer.h:492-494
+// is the reference's layout of it) — on the training stream, behind the forward/backward kernel.  The next step's sample generator
+// already runs beside it on the side stream (tb_prefetch).
+static void tb_allreduce_grads(ngp_testbed* t) {
+	const ngpb::NcclApi& nccl = ngpb::NcclApi::get();
+	PhaseTimer pt(t, 6);
+	nccl.check(nccl.AllReduce(t->grads.p, t->grads.p, t->desc.n_params, ngpb::NcclApi::ncclFloat16, ngpb::NcclApi::ncclSum, t->comm_grads, t->stream), "ncclAllReduce(gradients)");
+}
+
 int ngp_testbed_train(ngp_testbed* t, uint32_t batch) {
 	NGPB_TRY({
 		if (!t->shall_train) return 0;
-		tb_compute_grads(t, batch);
+		if (t->dp_world > 1 && t->comm_grads) {
+			tb_front(t, batch);
+			tb_back(t, true);
+			tb_allreduce_grads(t);
+		} else {
+			tb_compute_grads(t, batch);
+		}
 		tb_apply_grads(t);
+	});
+}
+
+// ---- data parallel set-up: one process per GPU -------------------------------------------------------------------------------
+size_t ngp_dp_unique_id_bytes(void) { return 2 * sizeof(ngpb::NcclApi::unique_id); }
+int ngp_dp_unique_id(uint8_t* out, size_t capacity) {
+	NGPB_TRY({
+		NGPB_CHECK(out && capacity >= ngp_dp_unique_id_bytes(), "ngp_dp_unique_id: buffer too small (ngp_dp_unique_id_bytes())");
+		const ngpb::NcclApi& nccl = ngpb::NcclApi::get();
+		ngpb::NcclApi::unique_id ids[2];
+		nccl.check(nccl.GetUniqueId(&ids[0]), "ncclGetUniqueId");
+		nccl.check(nccl.GetUniqueId(&ids[1]), "ncclGetUniqueId");
+		memcpy(out, ids, sizeof(ids));
+	});
+}
+int ngp_testbed_init_dp(ngp_testbed* t, uint32_t rank, uint32_t world, const uint8_t* unique_id, size_t n_bytes) {
+	NGPB_TRY({
+		require_device();
+		NGPB_CHECK(world >= 1 && rank < world, "init_dp: rank must be < world");
+		NGPB_CHECK(unique_id && n_bytes >= ngp_dp_unique_id_bytes(), "init_dp: the unique id of ngp_dp_unique_id (rank 0) is required on every rank");
+		NGPB_CHECK(!t->comm_grads, "init_dp: already initialised");
+		tb_invalidate_prefetch(t);
+		NGPB_CUDA_CHECK(cudaSetDevice(t->device));
+		const ngpb::NcclApi& nccl = ngpb::NcclApi::get();
+		ngpb::NcclApi::unique_id ids[2];
+		memcpy(ids, unique_id, sizeof(ids));
+		if (world > 1) {
+			nccl.check(nccl.CommInitRank(&t->comm_grads, (int)world, ids[0], (int)rank), "ncclCommInitRank");
+			nccl.check(nccl.CommInitRank(&t->comm_small, (int)world, ids[1], (int)rank), "ncclCommInitRank");
+			NGPB_CUDA_CHECK(cudaStreamCreateWithFlags(&t->comm_stream, cudaStreamNonBlocking));
+			NGPB_CUDA_CHECK(cudaEventCreateWithFlags(&t->ev_counters_ready, cudaEventDisableTiming));
+		}
+		t->dp_rank = rank;
+		t->dp_world = world;
+	});
+}
+// Row-tile render sharding: after every rank has rendered its rows [y0, y1) into its own full-size frame buffers
+// (ngp_testbed_render_device), rank `root` receives the tiles of the others: one ncclBroadcast per rank of its row block, in place.
+// rgba / depth: device pointers to [height x width x 4] / [height x width] floats on every rank; rows are split evenly, ngp_dp_rows.
+void ngp_dp_rows(uint32_t rank, uint32_t world, int32_t height, int32_t* y0, int32_t* y1) {
+	const int32_t per = (height + (int32_t)world - 1) / (int32_t)world;
+	*y0 = std::min(height, (int32_t)rank * per);
+	*y1 = std::min(height, *y0 + per);
+}
+int ngp_testbed_gather_rows(ngp_testbed* t, int32_t width, int32_t height, float* rgba, float* depth) {
+	NGPB_TRY({
+		NGPB_CHECK(t->dp_world > 1 && t->comm_grads, "gather_rows: data parallel mode is not initialised (ngp_testbed_init_dp)");
+		const ngpb::NcclApi& nccl = ngpb::NcclApi::get();
+		for (uint32_t r = 0; r < t->dp_world; ++r) {
+			int32_t y0, y1;
+			ngp_dp_rows(r, t->dp_world, height, &y0, &y1);
+			if (y1 <= y0) continue;
+			float* c = rgba + (size_t)y0 * width * 4;
+			float* d = depth + (size_t)y0 * width;
+			nccl.check(nccl.Broadcast(c, c, (size_t)(y1 - y0) * width * 4, ngpb::NcclApi::ncclFloat32, (int)r, t->comm_grads, t->stream), "ncclBroadcast(rgba rows)");
+			if (depth) nccl.check(nccl.Broadcast(d, d, (size_t)(y1 - y0) * width, ngpb::NcclApi::ncclFloat32, (int)r, t->comm_grads, t->stream), "ncclBroadcast(depth rows)");
+		}
 	});
 }
 void* ngp_testbed_grads(ngp_testbed* t) { return t->grads.p; }

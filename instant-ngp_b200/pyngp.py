@@ -659,7 +659,36 @@ class Testbed:
         return True
 
     def set_data_parallel(self, rank: int, world: int) -> None:
+        """ray partition only: the caller runs the collectives (train_front / train_back / train_apply_grads)"""
         B.check(B.lib().ngp_testbed_set_dp(self._h, rank, world))
+
+    @staticmethod
+    def dp_unique_id() -> bytes:
+        """rank 0: the id every rank passes to init_data_parallel (hand it over with torch.distributed / MPI / a file)"""
+        n = B.lib().ngp_dp_unique_id_bytes()
+        buf = (C.c_uint8 * n)()
+        B.check(B.lib().ngp_dp_unique_id(buf, n))
+        return bytes(buf)
+
+    def init_data_parallel(self, rank: int, world: int, unique_id: bytes) -> None:
+        """one process per GPU: from here on train() is the whole data-parallel step (NCCL all-reduce of counters and gradients inside
+        the library, ngp_testbed_init_dp)"""
+        buf = (C.c_uint8 * len(unique_id)).from_buffer_copy(unique_id)
+        B.check(B.lib().ngp_testbed_init_dp(self._h, rank, world, buf, len(unique_id)))
+        self._dp = (rank, world)
+
+    def dp_rows(self, height: int, rank: int | None = None):
+        r, w = getattr(self, "_dp", (0, 1))
+        y0, y1 = C.c_int32(), C.c_int32()
+        B.lib().ngp_dp_rows(r if rank is None else rank, w, height, C.byref(y0), C.byref(y1))
+        return y0.value, y1.value
+
+    def render_device_sharded(self, width: int, height: int, camera_matrix, focal_length, rgba_ptr: int, depth_ptr: int, screen_center=(0.5, 0.5)) -> None:
+        """this rank's row tile of the frame, then the exchange of tiles: every rank ends up with the whole frame in its device buffers"""
+        y0, y1 = self.dp_rows(height)
+        if y1 > y0:
+            self.render_device(width, height, camera_matrix, focal_length, rgba_ptr, depth_ptr, screen_center, rows=(y0, y1))
+        B.check(B.lib().ngp_testbed_gather_rows(self._h, width, height, C.c_void_p(rgba_ptr), C.c_void_p(depth_ptr)))
 
     def train_compute_grads(self, batch_size: int | None = None) -> None:
         B.check(B.lib().ngp_testbed_train_compute_grads(self._h, int(batch_size or self.training_batch_size)))
@@ -786,13 +815,13 @@ class Testbed:
         B.check(B.lib().ngp_testbed_load_snapshot(self._h, str(Path(path)).encode()))
 
     # -- profiling / streaming data --------------------------------------------------------------------------------------
-    PHASES = ("occupancy_grid", "sample_generation", "inference", "loss_compaction", "forward_backward", "optimizer")
+    PHASES = ("occupancy_grid", "sample_generation", "inference", "loss_compaction", "forward_backward", "optimizer", "allreduce")
 
     def set_profiling(self, enable: bool) -> None:
         B.check(B.lib().ngp_testbed_set_profiling(self._h, int(enable)))
 
     def phase_ms(self) -> dict:
-        ms = (C.c_float * 6)()
+        ms = (C.c_float * len(self.PHASES))()
         n = C.c_uint32(0)
         B.check(B.lib().ngp_testbed_get_phase_ms(self._h, ms, C.byref(n)))
         return {"steps": n.value, **{k: float(ms[i]) for i, k in enumerate(self.PHASES)}}
