@@ -110,9 +110,34 @@ struct RenderFast {
 // the render camera's lens in uv_to_ray, near-plane offset, box entry and the jittered first step of advance_pos_nerf (:398-452).
 // Returns false for a ray that misses the render box.
 template <class M>
-__device__ __forceinline__ bool render_init_ray(const ngp_render_cfg& cfg, const Aabb& render_aabb, const int32_t y0, const uint32_t q, uint32_t& pix, V3& ro, V3& rd,
-	V3& idir, float& t) {
-	const uint32_t x = q % (uint32_t)cfg.width, y = (uint32_t)y0 + q / (uint32_t)cfg.width;
+__device__ __forceinline__ bool render_init_ray(const ngp_render_cfg& cfg, const Aabb& render_aabb, const int32_t y0, const uint32_t n_rows, const uint32_t q, uint32_t& pix,
+	V3& ro, V3& rd, V3& idir, float& t) {
+	// queue order: 8 x 4 pixel blocks, row-major inside a block, blocks row-major over the tile — the 32 rays a warp pulls together are
+	// neighbours in x AND y, so their samples share hash-grid cells (and 32-byte sectors) for longer than 32 pixels of one scanline do.
+	// (Widths that are not a multiple of 8 / row counts that are not a multiple of 4 fall back to scanline order for the remainder.)
+	uint32_t x, y;
+	{
+		const uint32_t w = (uint32_t)cfg.width, rows = n_rows;
+		const uint32_t wb = w / 8u, hb = rows / 4u, n_blocked = wb * hb * 32u;
+		if (q < n_blocked) {
+			const uint32_t b = q / 32u, in = q % 32u;
+			x = (b % wb) * 8u + (in % 8u);
+			y = (b / wb) * 4u + (in / 8u);
+		} else {
+			// the strip right of the last full block column, then the rows below the last full block row
+			uint32_t r = q - n_blocked;
+			const uint32_t right_w = w - wb * 8u, right_n = right_w * hb * 4u;
+			if (r < right_n) {
+				x = wb * 8u + r % right_w;
+				y = r / right_w;
+			} else {
+				r -= right_n;
+				x = r % w;
+				y = hb * 4u + r / w;
+			}
+		}
+		y += (uint32_t)y0;
+	}
 	pix = x + (uint32_t)cfg.width * y;
 	const float u = ((float)x + cfg.pixel_offset[0]) / (float)cfg.width, v = ((float)y + cfg.pixel_offset[1]) / (float)cfg.height;
 	V3 o, d;
@@ -167,7 +192,7 @@ __global__ void __launch_bounds__(128) k_render_first_hit(const __grid_constant_
 	uint32_t pix;
 	V3 ro, rd, idir, pos;
 	float t = max_depth();
-	if (render_init_ray<M>(cfg, render_aabb, y0, q, pix, ro, rd, idir, t)) render_march<M>(cfg, render_aabb, bitfield, ro, rd, idir, t, pos, 0xFFFFFFFFu);
+	if (render_init_ray<M>(cfg, render_aabb, y0, n_pixels / (uint32_t)cfg.width, q, pix, ro, rd, idir, t)) render_march<M>(cfg, render_aabb, bitfield, ro, rd, idir, t, pos, 0xFFFFFFFFu);
 	if (t >= max_depth()) {
 		// shade_kernel_nerf on an empty payload: transparent pixel, depth MAX_DEPTH
 		reinterpret_cast<float4*>(rgba_out)[pix] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -178,8 +203,10 @@ __global__ void __launch_bounds__(128) k_render_first_hit(const __grid_constant_
 
 constexpr uint32_t RENDER_SKIPS_PER_TILE = 16;   // voxel skips a slot may spend looking for its next sample before the tile goes ahead without it
 
+constexpr uint32_t RENDER_CTAS_PER_SM = 4;       // 45 KB of shared memory and 64 TMEM columns each; <= 128 registers per thread
+
 template <uint32_t F, class M>
-__global__ void __launch_bounds__(TILE, 3) k_render_nerf(
+__global__ void __launch_bounds__(TILE, RENDER_CTAS_PER_SM) k_render_nerf(
 	const __grid_constant__ NetDev net, const __grid_constant__ ngp_render_cfg cfg, const int32_t y0, const int32_t y1,
 	const __half* __restrict__ params, const uint8_t* __restrict__ bitfield, float* __restrict__ rgba_out, float* __restrict__ depth_out,
 	uint32_t* __restrict__ queue /* [0] next pixel, [1] total steps */, const float* __restrict__ t_first
@@ -252,7 +279,7 @@ __global__ void __launch_bounds__(TILE, 3) k_render_nerf(
 					const float tf = t_first[q];
 					if (tf < max_depth()) {
 						float t_unused;
-						render_init_ray<M>(cfg, render_aabb, y0, q, pix, ro, rd, idir, t_unused);
+						render_init_ray<M>(cfg, render_aabb, y0, (uint32_t)(y1 - y0), q, pix, ro, rd, idir, t_unused);
 						t = tf;
 						acc_r = acc_g = acc_b = acc_a = 0.0f;
 						max_weight = 0.0f;
@@ -544,7 +571,7 @@ static void launch_render(const NetDev& net, cudaStream_t stream, const ngp_rend
 	k_render_first_hit<M><<<div_round_up(n_pixels, 128), 128, 0, stream>>>(cfg, y0, n_pixels, bitfield, rgba, depth, t_first);
 	NGPB_LAUNCHED();
 	const uint32_t n_tiles = div_round_up(n_pixels, TILE);
-	const uint32_t max_ctas = (uint32_t)device_sm_count() * 3u;
+	const uint32_t max_ctas = (uint32_t)device_sm_count() * RENDER_CTAS_PER_SM;
 	const uint32_t grid = n_tiles < max_ctas ? n_tiles : max_ctas;
 	auto kern = k_render_nerf<F, M>;
 	static bool attr = false;

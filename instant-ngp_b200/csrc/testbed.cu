@@ -224,7 +224,7 @@ struct ngp_testbed {
 	uint32_t last_batch = 0;
 	bool grads_pending = false;
 	bool get_loss_pending = false;
-	bool overlap_sample_generation = true;   // next step's generator on the side stream, gated on this step's forward/backward kernel (see tb_prefetch)
+	uint32_t overlap_sample_generation = 2;   // next step's generator on the side stream, gated on this step's forward/backward kernel (tb_prefetch): 0 never, 1 always, 2 data parallel only
 	bool front_done = false, controller_done = false;
 	cudaStream_t side_stream = nullptr;
 	cudaEvent_t ev_front_done = nullptr, ev_prefetch_done = nullptr, ev_main_ready = nullptr, ev_back_done = nullptr;
@@ -695,7 +695,11 @@ static void tb_update_controller(ngp_testbed* t) {
 // registers and shared memory: 1.90 vs 1.68 ms, profiles/r1a).
 static void tb_prefetch(ngp_testbed* t) {
 	const uint32_t next_step = t->training_step + 1;
-	if (!(t->overlap_sample_generation && t->shall_train && !tb_prep_due(next_step) && !t->views_dirty && !t->profiling)) return;
+	// Single GPU: since the generator marches with G lanes per ray it takes 0.34 ms on nerf/fox, and running it beside the optimizer
+	// (both memory-latency bound, the optimizer streaming 340 MB) costs more than it hides: 1.50 vs 1.41 ms/step (profiles/r2).  Data
+	// parallel it runs beside the gradient all-reduce, where the SMs are idle.
+	const bool worth_it = t->overlap_sample_generation == 1 || (t->overlap_sample_generation == 2 && t->dp_world > 1);
+	if (!(worth_it && t->shall_train && !tb_prep_due(next_step) && !t->views_dirty && !t->profiling)) return;
 	const uint32_t batch = t->step_batch;
 	const uint32_t next = t->cur ^ 1u;
 	const uint32_t max_inference = tb_max_inference(t, batch);
@@ -1061,7 +1065,7 @@ int ngp_testbed_set_option(ngp_testbed* t, const char* name_c, double value) {
 		else if (n == "nerf.training.full_inference") { tb_invalidate_prefetch(t); t->full_inference = value != 0; }
 		else if (n == "nerf.training.train_mode") { NGPB_CHECK(value == 0 || value == 1 || value == 2, "train_mode must be Nerf (0), Rfl (1) or RflRelax (2)"); c.train_mode = (uint32_t)value; }
 		else if (n == "nerf.training.inference_chunk") { NGPB_CHECK(value == 4 || value == 8, "inference_chunk must be 4 or 8"); t->inference_chunk = (uint32_t)value; }
-		else if (n == "nerf.training.overlap_sample_generation") t->overlap_sample_generation = value != 0;
+		else if (n == "nerf.training.overlap_sample_generation") { NGPB_CHECK(value == 0 || value == 1 || value == 2, "overlap_sample_generation: 0 never, 1 always, 2 data parallel only"); tb_invalidate_prefetch(t); t->overlap_sample_generation = (uint32_t)value; }
 		else if (n == "train_network") t->train_network = value != 0;
 		else if (n == "train_encoding") t->train_encoding = value != 0;
 		else if (n == "shall_train") t->shall_train = value != 0;

@@ -780,8 +780,10 @@ class Testbed:
         cam = np.ascontiguousarray(np.asarray(camera_matrix, dtype=np.float32)[:3, :4])
         fx, fy = (focal_length, focal_length) if np.isscalar(focal_length) else focal_length
         y0, y1 = rows if rows is not None else (0, height)
-        rgba = np.zeros((height, width, 4), dtype=np.float32)
-        depth = np.zeros((height, width), dtype=np.float32)
+        # a full frame is written completely by the library: no need to zero 41 MB first (a 1920x1080 frame: ~8 ms of page faults)
+        alloc = np.zeros if rows is not None else np.empty
+        rgba = alloc((height, width, 4), dtype=np.float32)
+        depth = alloc((height, width), dtype=np.float32)
         if spp != 1 or not linear:
             # the accumulate + tonemap epilogue (render_buffer.cu): spp frames averaged, sRGB output for linear=False
             if rows is not None:
