@@ -83,6 +83,15 @@ inline OptimizerConfig parse_optimizer_chain(const Json& optimizer) {
 			opt.beta2 = (float)o->value("beta2", 0.999);
 			opt.epsilon = (float)o->value("epsilon", 1e-8);
 			opt.l2_reg = (float)o->value("l2_reg", 1e-8);
+			// options of the reference's Adam (adam.h:133-170, 258-300) that k_adam_ema does not implement: refuse them instead of training differently
+			auto refuse = [&](const char* key, double dflt) {
+				NGPB_CHECK(!o->contains(key) || o->value(key, dflt) == dflt, std::string("optimizer: Adam option '") + key + "' is not implemented by ngp_b200 (only its default is accepted)");
+			};
+			refuse("relative_decay", 0.0);
+			refuse("absolute_decay", 0.0);
+			refuse("adabound", 0.0);
+			refuse("clipping_magnitude", 0.0);
+			refuse("non_matrix_learning_rate_factor", 1.0);
 			break;
 		} else {
 			NGPB_CHECK(false, "optimizer.otype '" + ot + "' is not supported (Ema / ExponentialDecay / Adam)");

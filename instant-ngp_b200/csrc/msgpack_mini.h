@@ -99,7 +99,17 @@ private:
 class MsgPackReader {
 public:
 	MsgPackReader(const uint8_t* data, size_t n) : d(data), n(n) {}
+	// nesting is bounded: a crafted file must not be able to exhaust the stack (not catchable) through recursion
+	struct DepthGuard {
+		int& d;
+		explicit DepthGuard(int& depth) : d(depth) {
+			if (++d > 64) throw std::runtime_error("msgpack: nesting deeper than 64 levels");
+		}
+		~DepthGuard() { --d; }
+	};
+	int depth = 0;
 	Json read() {
+		DepthGuard guard(depth);
 		const uint8_t c = byte();
 		Json j;
 		if (c <= 0x7F) return jint(c);
@@ -174,12 +184,14 @@ private:
 	}
 	Json array(size_t len) {
 		Json j = jarr();
+		if (len > n - p) throw std::runtime_error("msgpack: truncated input (array longer than the remaining bytes)");   // every element takes at least one byte
 		j.arr.reserve(len);
 		for (size_t i = 0; i < len; ++i) j.arr.push_back(read());
 		return j;
 	}
 	Json map(size_t len) {
 		Json j = jobj();
+		if (len > (n - p) / 2) throw std::runtime_error("msgpack: truncated input (map longer than the remaining bytes)");
 		for (size_t i = 0; i < len; ++i) {
 			Json k = read();
 			if (k.type != Json::String) throw std::runtime_error("msgpack: non-string map key");

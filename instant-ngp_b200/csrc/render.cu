@@ -545,22 +545,21 @@ static void launch_forward_rays(const NetDev& net, cudaStream_t stream, uint32_t
 	NGPB_CUDA_CHECK(cudaGetLastError());
 }
 
-// chunk: samples of a ray evaluated per tensor-core tile (4 or 8; 128 / chunk ray slots per CTA)
+// chunk: consecutive samples of a ray evaluated per tensor-core tile (4, 8, 16 or 32; 128 / chunk ray slots per CTA)
 void nerf_inference_rays(const ngp_nerf_desc& d, cudaStream_t stream, uint32_t n_rays_max, const ngp_nerf_counters* counters, uint32_t* queue,
 	const uint32_t* numsteps, const float* coords, const __half* params, uint32_t density_activation, __half* out, uint32_t chunk) {
 	if (n_rays_max == 0) return;
-	NGPB_CHECK(chunk == 4 || chunk == 8, "inference chunk must be 4 or 8");
+	NGPB_CHECK(chunk == 4 || chunk == 8 || chunk == 16 || chunk == 32, "inference chunk must be 4, 8, 16 or 32");
 	const NetDev net = make_netdev(d);
+#define NGPB_FWD_RAYS(FF, CC) launch_forward_rays<FF, CC>(net, stream, n_rays_max, counters, queue, numsteps, coords, params, density_activation, out)
 	if (net.n_features == 2) {
-		if (chunk == 4) launch_forward_rays<2, 4>(net, stream, n_rays_max, counters, queue, numsteps, coords, params, density_activation, out);
-		else launch_forward_rays<2, 8>(net, stream, n_rays_max, counters, queue, numsteps, coords, params, density_activation, out);
+		if (chunk == 4) NGPB_FWD_RAYS(2, 4); else if (chunk == 8) NGPB_FWD_RAYS(2, 8); else if (chunk == 16) NGPB_FWD_RAYS(2, 16); else NGPB_FWD_RAYS(2, 32);
 	} else {
-		if (chunk == 4) launch_forward_rays<4, 4>(net, stream, n_rays_max, counters, queue, numsteps, coords, params, density_activation, out);
-		else launch_forward_rays<4, 8>(net, stream, n_rays_max, counters, queue, numsteps, coords, params, density_activation, out);
+		if (chunk == 4) NGPB_FWD_RAYS(4, 4); else if (chunk == 8) NGPB_FWD_RAYS(4, 8); else if (chunk == 16) NGPB_FWD_RAYS(4, 16); else NGPB_FWD_RAYS(4, 32);
 	}
+#undef NGPB_FWD_RAYS
 }
 
-// scratch: [0, 256) queue words | t_first[width * rows]
 size_t render_scratch_bytes(int32_t width, int32_t rows) { return 256 + sizeof(float) * (size_t)(width > 0 ? width : 0) * (size_t)(rows > 0 ? rows : 0); }
 
 template <uint32_t F, class M>

@@ -192,8 +192,8 @@ struct ngp_testbed {
 	uint32_t optimizer_step = 0;
 	uint64_t seed = 1337;
 	bool train_network = true, train_encoding = true;
-	bool full_inference = false;
-	uint32_t inference_chunk = 8;
+	uint32_t full_inference = 2;    // training-time inference schedule: 0 ray-ordered, 1 every generated sample (the reference's), 2 chosen per step (tb_full_inference)
+	uint32_t inference_chunk = 0;   // consecutive samples of a ray per tile of the ray-ordered inference pass; 0 = from the last step's samples per ray
 
 	DevBuf<float> params_fp32, m1, m2, mlp_grads_f32;
 	DevBuf<__half> params, params_ema, grads;
@@ -518,6 +518,24 @@ static uint32_t tb_max_inference(const ngp_testbed* t, uint32_t batch) {
 	if (t->measured_batch_size_before_compaction == 0) return max_samples;
 	return next_multiple(std::min(t->measured_batch_size_before_compaction, max_samples), NGP_BATCH_GRANULARITY);
 }
+// The training-time inference pass has two schedules.  Ray-ordered (k_nerf_forward_rays): a tile is 128 / chunk rays x chunk
+// consecutive samples and a ray is walked chunk by chunk until the loss kernel would stop reading it — up to chunk - 1 evaluations
+// per ray are wasted and a long ray takes many sequential tiles, but nothing behind the stopping point is evaluated.  Flat
+// (k_nerf_forward over every generated sample, the reference's schedule, testbed_nerf.cu:3233-3235): full tiles, no dependence
+// between them, but it evaluates everything.  Which one wins depends on how much of what the generator produced the loss kernel
+// reads: the synthetic unit-cube scene reads 7 % (ray-ordered: 0.25 vs 1.3 ms), nerf/fox reads 55 % (flat: 0.12 ms, ray-ordered with
+// 8 / 16 / 32-sample chunks: 0.33 / 0.21 / 0.15 ms; profiles/r2).  Both choices follow the previous step's counters; the outputs the
+// loss kernel reads are bit-identical either way (tests/test_gpu_march.py).
+static bool tb_full_inference(const ngp_testbed* t) {
+	if (t->full_inference != 2) return t->full_inference == 1;
+	if (t->measured_batch_size == 0) return false;
+	return (float)t->measured_batch_size_before_compaction < 2.5f * (float)t->measured_batch_size;
+}
+static uint32_t tb_inference_chunk(const ngp_testbed* t) {
+	if (t->inference_chunk) return t->inference_chunk;
+	const float per_ray = t->rays_per_batch ? (float)t->measured_batch_size / (float)t->rays_per_batch : 0.0f;
+	return per_ray >= 64.0f ? 32u : (per_ray >= 24.0f ? 16u : 8u);
+}
 static bool tb_prep_due(uint32_t training_step) {
 	// Testbed::train (src/testbed.cu:4596-4614): density-grid prep every clamp(step/16, 1, 16) steps
 	const uint32_t n_prep_to_skip = std::min(std::max(training_step / 16u, 1u), 16u);
@@ -589,13 +607,13 @@ static void tb_front(ngp_testbed* t, uint32_t batch) {
 	NGPB_CUDA_CHECK(cudaMemsetAsync(t->loss_per_ray.p, 0, sizeof(float) * rays_local, t->stream));
 	{
 		PhaseTimer pt(t, 2);
-		if (t->full_inference) {
+		if (tb_full_inference(t)) {
 			// the reference's schedule: evaluate every generated sample (testbed_nerf.cu:3233-3235)
 			nerf_inference_counted(t->desc, t->stream, max_inference, &rs.counters.p->n_samples, rs.coords.p, t->params.p, t->mlp_out.p);
 		} else {
 			// evaluate, ray by ray, only the samples the loss kernel will read (bit-identical outputs for those)
 			nerf_inference_rays(t->desc, t->stream, rays_local, rs.counters.p, &rs.counters.p->pad, rs.numsteps.p, rs.coords.p, t->params.p,
-				t->cfg.density_activation, t->mlp_out.p, t->inference_chunk);
+				t->cfg.density_activation, t->mlp_out.p, tb_inference_chunk(t));
 		}
 	}
 	{
@@ -1062,9 +1080,9 @@ int ngp_testbed_set_option(ngp_testbed* t, const char* name_c, double value) {
 		else if (n == "nerf.training.math_mode") { NGPB_CHECK(value == 0 || value == 1, "math_mode must be 0 (deterministic) or 1 (reference)"); tb_invalidate_prefetch(t); t->cfg.math_mode = (uint32_t)value; }
 		else if (n == "nerf.training.gen_lanes_per_ray") { const uint32_t g = (uint32_t)value; NGPB_CHECK(g <= 32 && (g & (g - 1)) == 0, "gen_lanes_per_ray must be 0 or a power of two up to 32"); tb_invalidate_prefetch(t); t->cfg.gen_lanes_per_ray = g; }
 		else if (n == "render_math") { NGPB_CHECK(value == 0 || value == 1, "render_math must be 0 (deterministic) or 1 (reference)"); t->render_math = (uint32_t)value; }
-		else if (n == "nerf.training.full_inference") { tb_invalidate_prefetch(t); t->full_inference = value != 0; }
+		else if (n == "nerf.training.full_inference") { NGPB_CHECK(value == 0 || value == 1 || value == 2, "full_inference: 0 ray-ordered, 1 every sample, 2 automatic"); tb_invalidate_prefetch(t); t->full_inference = (uint32_t)value; }
 		else if (n == "nerf.training.train_mode") { NGPB_CHECK(value == 0 || value == 1 || value == 2, "train_mode must be Nerf (0), Rfl (1) or RflRelax (2)"); c.train_mode = (uint32_t)value; }
-		else if (n == "nerf.training.inference_chunk") { NGPB_CHECK(value == 4 || value == 8, "inference_chunk must be 4 or 8"); t->inference_chunk = (uint32_t)value; }
+		else if (n == "nerf.training.inference_chunk") { NGPB_CHECK(value == 0 || value == 4 || value == 8 || value == 16 || value == 32, "inference_chunk must be 0 (automatic), 4, 8, 16 or 32"); t->inference_chunk = (uint32_t)value; }
 		else if (n == "nerf.training.overlap_sample_generation") { NGPB_CHECK(value == 0 || value == 1 || value == 2, "overlap_sample_generation: 0 never, 1 always, 2 data parallel only"); tb_invalidate_prefetch(t); t->overlap_sample_generation = (uint32_t)value; }
 		else if (n == "train_network") t->train_network = value != 0;
 		else if (n == "train_encoding") t->train_encoding = value != 0;
@@ -1555,6 +1573,10 @@ static void tb_load_snapshot_json(ngp_testbed* t, const Json& config) {
 		const uint32_t n_img = (uint32_t)ds.value("n_images", 0.0);
 		t->n_images = n_img;
 		t->aabb_scale = (uint32_t)ds.value("aabb_scale", 1.0);
+		// NerfDataset::scale / offset (json_binding.h:160-166): what set_nerf_camera_matrix converts poses with
+		t->scene_scale = (float)ds.value("scale", (double)t->scene_scale);
+		if (ds.contains("offset") && ds.at("offset").type == Json::Array && ds.at("offset").arr.size() == 3)
+			for (int k = 0; k < 3; ++k) t->scene_offset[k] = (float)ds.at("offset").arr[k].num;
 		t->views.assign(n_img, ngp_train_view{});
 		t->pixel_bufs.assign(n_img, nullptr);
 		for (uint32_t i = 0; i < n_img; ++i) {
@@ -1567,7 +1589,11 @@ static void tb_load_snapshot_json(ngp_testbed* t, const Json& config) {
 			v.principal_x = (float)m.at("principal_point").arr.at(0).num;
 			v.principal_y = (float)m.at("principal_point").arr.at(1).num;
 			const Json& lens = m.sub("lens");
-			if (lens.contains("k1") && !(lens.contains("is_fisheye") && lens.at("is_fisheye").b)) {
+			// from_json(Lens) (json_binding.h:67-99) tells the mode from the keys present; only perspective and OpenCV are built here
+			NGPB_CHECK(!(lens.contains("k1") && lens.contains("is_fisheye") && lens.at("is_fisheye").b) && !lens.contains("ftheta_p0") && !lens.contains("latlong") &&
+				!lens.contains("equirectangular") && !lens.contains("orthographic"),
+				"snapshot: view " + std::to_string(i) + " uses a lens this build does not implement (perspective and OpenCV only)");
+			if (lens.contains("k1")) {
 				v.lens_mode = NGP_LENS_OPENCV;
 				v.lens_params[0] = (float)lens.value("k1", 0.0);
 				v.lens_params[1] = (float)lens.value("k2", 0.0);
@@ -1632,11 +1658,12 @@ static void tb_load_snapshot_json(ngp_testbed* t, const Json& config) {
 		NGPB_CUDA_CHECK(cudaStreamSynchronize(t->stream));
 	}
 	const Json& rgb = nerf.sub("rgb");
-	t->rays_per_batch = (uint32_t)rgb.value("rays_per_batch", (double)t->rays_per_batch);
+	// per-step buffers are sized for at most 2^18 rays (tb_ensure_step_scratch); the controller keeps multiples of the batch granularity
+	t->rays_per_batch = std::min(std::max(next_multiple((uint32_t)rgb.value("rays_per_batch", (double)t->rays_per_batch), NGP_BATCH_GRANULARITY), NGP_BATCH_GRANULARITY), 1u << 18);
 	t->measured_batch_size = (uint32_t)rgb.value("measured_batch_size", 0.0);
 	t->measured_batch_size_before_compaction = (uint32_t)rgb.value("measured_batch_size_before_compaction", 0.0);
 	t->training_step = (uint32_t)snap.value("training_step", 0.0);
-	if (!snap.contains("optimizer")) t->optimizer_step = t->training_step;
+	if (!snap.contains("optimizer")) t->optimizer_step = 0;   // no optimizer state in the file: Adam restarts (moments zero, step 0), like Trainer::deserialize without "optimizer"
 	t->loss_scalar = (float)snap.value("loss", 0.0);
 	t->exposure = (float)snap.value("exposure", (double)t->exposure);
 	if (snap.contains("background_color") && snap.at("background_color").type == Json::Array && snap.at("background_color").arr.size() == 4) {
@@ -1673,7 +1700,7 @@ int ngp_testbed_save_snapshot(ngp_testbed* t, const char* path) {
 		NGPB_CUDA_CHECK(cudaStreamSynchronize(t->stream));
 		SnapshotHeader h{};
 		memcpy(h.magic, "NGPB200\0", 8);
-		h.version = 1;
+		h.version = 2;
 		h.n_params = t->desc.n_params;
 		h.n_grid = GRID_N_CELLS * (t->cfg.max_cascade + 1);
 		h.training_step = t->training_step;
@@ -1689,6 +1716,15 @@ int ngp_testbed_save_snapshot(ngp_testbed* t, const char* path) {
 		std::ofstream f(path, std::ios::binary);
 		NGPB_CHECK(f.good(), std::string("cannot open ") + path);
 		f.write(reinterpret_cast<const char*>(&h), sizeof(h));
+		{
+			// version 2: the network config (encoding, MLPs, loss, optimizer chain) as MessagePack, so that a fresh Testbed resumes with the
+			// optimizer and loss it was trained with instead of the defaults
+			MsgPackWriter w;
+			w.write(t->network_config);
+			const uint64_t n_cfg = w.out.size();
+			f.write(reinterpret_cast<const char*>(&n_cfg), sizeof(n_cfg));
+			f.write(reinterpret_cast<const char*>(w.out.data()), (std::streamsize)n_cfg);
+		}
 		auto dump = [&](const void* dev, size_t bytes) {
 			std::vector<char> buf(bytes);
 			NGPB_CUDA_CHECK(cudaMemcpy(buf.data(), dev, bytes, cudaMemcpyDeviceToHost));
@@ -1721,12 +1757,29 @@ int ngp_testbed_load_snapshot(ngp_testbed* t, const char* path) {
 		NGPB_CHECK(f.good(), std::string("snapshot not found: ") + path);
 		SnapshotHeader h{};
 		f.read(reinterpret_cast<char*>(&h), sizeof(h));
-		NGPB_CHECK(f.good() && memcmp(h.magic, "NGPB200\0", 8) == 0 && h.version == 1, "not an ngp_b200 snapshot");
-		t->aabb_scale = h.aabb_scale;
-		tb_update_scene(t);
-		t->desc = h.desc;
-		t->has_network = true;
-		tb_alloc_network(t);
+		NGPB_CHECK(f.good() && memcmp(h.magic, "NGPB200\0", 8) == 0 && (h.version == 1 || h.version == 2), "not an ngp_b200 snapshot");
+		NGPB_CHECK(h.aabb_scale >= 1 && h.aabb_scale <= (1u << (NGP_NERF_CASCADES - 1)) && (h.aabb_scale & (h.aabb_scale - 1)) == 0, "snapshot: bad aabb_scale");
+		if (h.version >= 2) {
+			// rebuild the network from the stored config (tb_reset_network: descriptor, loss, optimizer chain), then check it against the header
+			uint64_t n_cfg = 0;
+			f.read(reinterpret_cast<char*>(&n_cfg), sizeof(n_cfg));
+			NGPB_CHECK(f.good() && n_cfg > 0 && n_cfg < (64u << 20), "snapshot: bad network config block");
+			std::vector<uint8_t> cfg_bytes(n_cfg);
+			f.read(reinterpret_cast<char*>(cfg_bytes.data()), (std::streamsize)n_cfg);
+			NGPB_CHECK(f.good(), "snapshot truncated");
+			t->aabb_scale = h.aabb_scale;
+			tb_update_scene(t);
+			MsgPackReader r(cfg_bytes.data(), cfg_bytes.size());
+			tb_reset_network(t, r.read());
+		} else {
+			// version 1 carries no config: only into a Testbed whose network is already configured the same way
+			NGPB_CHECK(t->has_network && t->aabb_scale == h.aabb_scale, "this .ngpb (version 1) carries no network config: configure the same network and dataset first");
+		}
+		// the buffers below are sized from t->desc: the header must describe exactly that network
+		NGPB_CHECK(memcmp(&h.desc, &t->desc, sizeof(ngp_nerf_desc)) == 0, "snapshot: the network descriptor does not match the network config");
+		NGPB_CHECK(h.n_params == t->desc.n_params, "snapshot: parameter count does not match the network");
+		NGPB_CHECK(h.n_grid == GRID_N_CELLS * (t->cfg.max_cascade + 1), "snapshot: density grid size does not match aabb_scale");
+		NGPB_CHECK(h.rays_per_batch >= 1 && h.rays_per_batch <= (1u << 18), "snapshot: rays_per_batch out of range");
 		t->density_grid.ensure(GRID_N_CELLS * NGP_NERF_CASCADES);
 		t->bitfield.ensure(GRID_N_CELLS / 8 * NGP_NERF_CASCADES);
 		t->mean_density.ensure(4);

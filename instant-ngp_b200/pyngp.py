@@ -759,7 +759,7 @@ class Testbed:
         # path does, src/testbed.cu:3217).  Measured on the B200 (profiles/r2a): reference render() of fox's test views = 26.0 dB
         # against the distorted photographs, 29.4 dB once the lens is applied.  The reference-shaped call reproduces the reference;
         # the explicit-camera form below honours render_with_lens_distortion / render_lens.
-        with_lens = self.render_with_lens_distortion
+        with_lens = self._h is not None and self.render_with_lens_distortion
         if with_lens:
             self.render_with_lens_distortion = False
         try:

@@ -73,6 +73,11 @@ def test_binary_values_and_errors(lib):
     n = C.c_size_t(0)
     bad = (C.c_uint8 * 3)(0x82, 0xA1, 0x61)
     assert lib.ngp_msgpack_to_json(bad, 3, 0, out, 64, C.byref(n)) != 0 and b"truncated" in lib.ngp_last_error()
+    # a 5-byte header announcing 2^32 - 1 elements must not reserve memory for them, and nesting is bounded
+    huge = (C.c_uint8 * 5)(0xDD, 0xFF, 0xFF, 0xFF, 0xFF)
+    assert lib.ngp_msgpack_to_json(huge, 5, 0, out, 64, C.byref(n)) != 0 and b"truncated" in lib.ngp_last_error()
+    deep = (C.c_uint8 * 200)(*([0x91] * 199 + [0xC0]))
+    assert lib.ngp_msgpack_to_json(deep, 200, 0, out, 64, C.byref(n)) != 0 and b"nesting" in lib.ngp_last_error()
 
 
 # ---- pinned against the reference's own serializer stack (oracle/ref/ref_snapshot_harness.cu: nlohmann::json, zstr,
