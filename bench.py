@@ -351,6 +351,7 @@ def main() -> None:
     ap.add_argument("--views", type=int, default=N_VIEWS)
     ap.add_argument("--res", type=int, default=RES)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-fields", action="store_true", help="skip the image / SDF primitive micro-benchmark (extra key `fields`, N = 1)")
     ap.add_argument("--no-reference-gpu", action="store_true", help="skip the reference application's run on this GPU (extra key `reference_gpu`, N = 1)")
     ap.add_argument("--no-overlap", action="store_true", help="disable the side-stream prefetch of the next step's sample generation")
     ap.add_argument("--chunk", type=int, default=0, help="ray-ordered inference chunk (4 or 8)")
@@ -586,6 +587,18 @@ def main() -> None:
             if rg.get("samples_per_sec"):
                 line["vs_reference_gpu"] = {"samples_per_sec_ratio": value / rg["samples_per_sec"], "ms_per_step_ratio": rg["ms_per_step"] / (ms_total / args.steps),
                                             "definition": "this repo / reference application, same box, same scene, same batch; > 1 = faster than the reference"}
+        if world == 1 and not args.no_fields:
+            # BASELINE configs #1 (image, 64 K-sample batch) and #4 (SDF, 2^20 samples): encoding + MLP training step of the same kernels
+            # (tools/bench_fields.py, CUDA-event timed), so that they are part of the driver-visible line
+            try:
+                r = subprocess.run([sys.executable, str(ROOT / "tools" / "bench_fields.py")], capture_output=True, text=True, timeout=300)
+                rows = [json.loads(l) for l in r.stdout.splitlines() if l.startswith("{")]
+                pick = [x for x in rows if (x["case"], x["n"]) in (("image", 1 << 16), ("sdf", 1 << 20))]
+                line["fields"] = [{"config": "image 64K-sample batch (configs/image/base.json shape)" if x["case"] == "image" else "sdf 2^20-sample batch (configs/sdf/base.json shape)",
+                                   "train_step_ms": x["fwd_bwd_opt_ms"], "train_msamples_per_s": x["step_msamples_per_s"], "inference_msamples_per_s": x["fwd_msamples_per_s"],
+                                   "fwd_bwd_algorithmic_gbs": x["fwd_bwd_algorithmic_gbs"]} for x in pick]
+            except Exception as e:
+                line["fields"] = {"error": f"{type(e).__name__}: {e}"[:200]}
         if world == 1 and not args.no_cpu_baseline:
             sps, desc, cores = cpu_training_sample(scene)
             line["cpu_baseline"] = {"value": sps, "unit": "samples/s", "cores": cores, "kind": "port", "sample": desc}
