@@ -194,6 +194,12 @@ int ngp_nerf_density(const ngp_nerf_desc* d, void* stream, uint32_t n, const flo
 int ngp_nerf_forward_backward(const ngp_nerf_desc* d, void* stream, uint32_t n, const float* coords, const void* params_fp16,
 	const void* dL_dout_fp16, void* grads_fp16, void* out_fp16);
 
+/* Profiling only (tools/prof_mlp_phase.py, SURVEY §8d "tensor-pipe % for the MLP phase separately"): ngp_nerf_forward_backward's kernel with the
+ * hash-grid gather replaced by a register pattern and the scatter dropped — the 15 tcgen05 MMA groups of every 128-sample tile and their
+ * epilogues alone.  mlp_scratch_f32: n_mlp_params floats (accumulated into).  Base network only (F = 2, 1 + 2 hidden layers). */
+int ngp_profile_mlp_phase(const ngp_nerf_desc* d, void* stream, uint32_t n, const float* coords, const void* params_fp16, const void* dL_dout_fp16,
+	void* grads_fp16, float* mlp_scratch_f32);
+
 /* Hash-grid encoding alone (tests, image/SDF style use): out n x (L*F) halves, sample-contiguous. ≙ kernel_grid (grid.h:48-212). */
 int ngp_grid_encode(const ngp_grid_desc* g, void* stream, uint32_t n, const float* positions, uint32_t pos_stride,
 	const void* grid_fp16, void* out_fp16);
@@ -242,6 +248,12 @@ int ngp_nerf_update_bitfield(void* stream, uint32_t max_cascade, const float* de
 /* ≙ render_nerf (testbed_nerf.cu:1894-2150), Shade mode, pinhole or OpenCV camera, one sample per pixel.
  * camera: 4x3 column-major camera-to-world (ngp convention); rows [y0, y1) are rendered (tile sharding).
  * rgba: H x W x 4 floats (linear, premultiplied), depth: H x W floats; both full-frame pointers. */
+/* ERenderMode (common.h:68-79), values as the reference's enum.  What composite_kernel_nerf / shade_kernel_nerf put into the colour channels
+ * (testbed_nerf.cu:641-655, 1355-1372): AO the sample's alpha, Positions (pos - 0.5) / 2 + 0.5, Depth the sample's distance along the view
+ * direction x depth_scale, Cost n_steps / 128 with alpha 1, Shade the radiance (sRGB predictions accumulated in linear colour).  Normals
+ * (network input gradients), Distortion and Slice (2-D debug views) are not built: ngp_nerf_render refuses them. */
+typedef enum ngp_render_mode { NGP_RENDER_AO = 0, NGP_RENDER_SHADE = 1, NGP_RENDER_NORMALS = 2, NGP_RENDER_POSITIONS = 3, NGP_RENDER_DEPTH = 4, NGP_RENDER_DISTORTION = 5,
+	NGP_RENDER_COST = 6, NGP_RENDER_SLICE = 7 } ngp_render_mode;
 typedef struct ngp_render_cfg {
 	int32_t width, height;
 	float focal_x, focal_y;   /* pixels */
@@ -259,6 +271,8 @@ typedef struct ngp_render_cfg {
 	                             host evaluates it (ngp_render_pixel_offset): it depends on the sample index only */
 	uint32_t lens_mode;       /* ngp_lens_mode of the render camera (Testbed::m_render_lens when m_render_with_lens_distortion) */
 	float lens_params[4];
+	uint32_t render_mode;     /* ngp_render_mode */
+	float depth_scale;        /* Depth mode: 1 / dataset.scale (testbed_nerf.cu:2037) */
 	uint32_t math_mode;       /* ngp_math_mode of the march: NGP_MATH_DETERMINISTIC = ngp_detmath.h (bit-exact against the CPU oracle),
 	                             NGP_MATH_REFERENCE = the SFU log / exp / reciprocal the reference build's --use_fast_math compiles its
 	                             stepping functions to (what Testbed::render uses; ~10x cheaper per empty-voxel skip) */

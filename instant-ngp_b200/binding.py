@@ -153,6 +153,8 @@ class RenderCfg(C.Structure):
         ("pixel_offset", C.c_float * 2),
         ("lens_mode", C.c_uint32),
         ("lens_params", C.c_float * 4),
+        ("render_mode", C.c_uint32),
+        ("depth_scale", C.c_float),
         ("math_mode", C.c_uint32),
     ]
 
@@ -200,6 +202,7 @@ PROTOTYPES = {
     "ngp_testbed_set_option": (C.c_int, [vp, cp, C.c_double]),
     "ngp_testbed_get_option": (C.c_double, [vp, cp]),
     "ngp_testbed_train": (C.c_int, [vp, u32]),
+    "ngp_profile_mlp_phase": (C.c_int, [P(NerfDesc), vp, u32, vp, vp, vp, vp, vp]),
     "ngp_testbed_set_dp": (C.c_int, [vp, u32, u32]),
     "ngp_dp_unique_id_bytes": (C.c_size_t, []),
     "ngp_dp_unique_id": (C.c_int, [vp, C.c_size_t]),

@@ -184,7 +184,9 @@ __host__ __device__ inline uint32_t wgrad_col_base(uint32_t nhd, uint32_t nhr, b
 }
 __host__ __device__ inline uint32_t train_tmem_cols(uint32_t nhd, uint32_t nhr) { return wgrad_col_base(nhd, nhr, true, nhr + 1); }
 
-template <uint32_t F, uint32_t TMEM_COLS>
+// MLP_ONLY (profiling, ngp_profile_mlp_phase): the same tile loop with the hash-grid gather replaced by a register pattern and the
+// scatter dropped, i.e. the 15 tensor-core groups of a tile and their epilogues alone — the "MLP phase" SURVEY §8d asks to see separately.
+template <uint32_t F, uint32_t TMEM_COLS, bool MLP_ONLY = false>
 __global__ void __launch_bounds__(TRAIN_THREADS, 2) k_nerf_train(
 	const __grid_constant__ NetDev net, const uint32_t n, const float* __restrict__ coords, const __half* __restrict__ params,
 	const __half* __restrict__ dL_dout, __half* __restrict__ grads, float* __restrict__ mlp_grads_f32, __half* __restrict__ out
@@ -223,7 +225,12 @@ __global__ void __launch_bounds__(TRAIN_THREADS, 2) k_nerf_train(
 		const float x = c[0], y = c[1], z = c[2];
 		{
 			__half2 enc[8];
-			grid_gather_half<F>(net, grid, half, x, y, z, enc);
+			if constexpr (MLP_ONLY) {
+#pragma unroll
+				for (uint32_t j = 0; j < 8; ++j) enc[j] = __floats2half2_rn(x * (float)(j + 1), y - z * (float)j);
+			} else {
+				grid_gather_half<F>(net, grid, half, x, y, z, enc);
+			}
 			const __half2 h0[4] = {enc[0], enc[1], enc[2], enc[3]};
 			const __half2 h1[4] = {enc[4], enc[5], enc[6], enc[7]};
 			store_chunk(smem + L.a0_off, row, 2 * half + 0, h0);
@@ -289,7 +296,12 @@ __global__ void __launch_bounds__(TRAIN_THREADS, 2) k_nerf_train(
 			__half2 g[8];
 #pragma unroll
 			for (uint32_t j = 0; j < 8; ++j) g[j] = __floats2half2_rn(dx[2 * j], dx[2 * j + 1]);
-			grid_scatter_half<F>(net, grid_grad, half, x, y, z, g);
+			if constexpr (MLP_ONLY) {
+				// keep the gradient live without touching the table
+				if (__hlt(__low2half(g[0]), __float2half_rn(-60000.0f))) grid_grad[0] = __low2half(g[1]);
+			} else {
+				grid_scatter_half<F>(net, grid_grad, half, x, y, z, g);
+			}
 		}
 	}
 
@@ -455,11 +467,11 @@ void grid_encode(const ngp_grid_desc& g, cudaStream_t stream, uint32_t n, const 
 }
 
 
-template <uint32_t F, uint32_t TMEM_COLS>
+template <uint32_t F, uint32_t TMEM_COLS, bool MLP_ONLY = false>
 static void launch_train(const NetDev& net, cudaStream_t stream, uint32_t n, const float* coords, const __half* params, const __half* dL_dout,
 	__half* grads, float* mlp_grads_f32, __half* out) {
 	const TrainSmem L = train_smem_layout(net.n_hidden_density, net.n_hidden_rgb);
-	auto kern = k_nerf_train<F, TMEM_COLS>;
+	auto kern = k_nerf_train<F, TMEM_COLS, MLP_ONLY>;
 	static bool attr_set = false;
 	if (!attr_set) {
 		NGPB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -497,6 +509,15 @@ void nerf_forward_backward(const ngp_nerf_desc& d, cudaStream_t stream, uint32_t
 	k_mlp_grads_finalize<<<div_round_up(d.n_mlp_params, 256), 256, 0, stream>>>(d.n_mlp_params, mlp_grads_f32, grads);
 	NGPB_LAUNCHED();
 	NGPB_CUDA_CHECK(cudaGetLastError());
+}
+
+// profiling entry: the MLP phase of the fused training kernel alone (base network: 1 + 2 hidden layers, F = 2)
+void profile_mlp_phase(const ngp_nerf_desc& d, cudaStream_t stream, uint32_t n, const float* coords, const __half* params, const __half* dL_dout, __half* grads,
+	float* mlp_grads_f32) {
+	NGPB_CHECK(n % TILE == 0 && n > 0, "ngp_profile_mlp_phase: batch size must be a positive multiple of 128");
+	const NetDev net = make_netdev(d);
+	NGPB_CHECK(net.n_features == 2 && train_tmem_cols(net.n_hidden_density, net.n_hidden_rgb) <= 256, "ngp_profile_mlp_phase: base network (F = 2, 1 + 2 hidden layers) only");
+	launch_train<2, 256, true>(net, stream, n, coords, params, dL_dout, grads, mlp_grads_f32, nullptr);
 }
 
 }  // namespace ngpb

@@ -194,8 +194,8 @@ __global__ void __launch_bounds__(128) k_render_first_hit(const __grid_constant_
 	float t = max_depth();
 	if (render_init_ray<M>(cfg, render_aabb, y0, n_pixels / (uint32_t)cfg.width, q, pix, ro, rd, idir, t)) render_march<M>(cfg, render_aabb, bitfield, ro, rd, idir, t, pos, 0xFFFFFFFFu);
 	if (t >= max_depth()) {
-		// shade_kernel_nerf on an empty payload: transparent pixel, depth MAX_DEPTH
-		reinterpret_cast<float4*>(rgba_out)[pix] = make_float4(0.f, 0.f, 0.f, 0.f);
+		// shade_kernel_nerf on an empty payload: transparent pixel (Cost mode: 0 steps, alpha 1), depth MAX_DEPTH
+		reinterpret_cast<float4*>(rgba_out)[pix] = make_float4(0.f, 0.f, 0.f, cfg.render_mode == NGP_RENDER_COST ? 1.f : 0.f);
 		depth_out[pix] = max_depth();
 	}
 	t_first[q] = t;
@@ -252,12 +252,18 @@ __global__ void __launch_bounds__(TILE, RENDER_CTAS_PER_SM) k_render_nerf(
 	uint32_t local_steps = 0;
 
 	auto finish_ray = [&]() {
-		// shade_kernel_nerf, Shade mode, frame buffer starts at zero: rgb is predicted in sRGB (linear_colors == false)
-		float r = acc_r, g = acc_g, b = acc_b;
-		r = srgb_to_linear(r);
-		g = srgb_to_linear(g);
-		b = srgb_to_linear(b);
-		float4 o = make_float4(r, g, b, acc_a);
+		// shade_kernel_nerf (:1333-1378), frame buffer starts at zero
+		float r = acc_r, g = acc_g, b = acc_b, a = acc_a;
+		if (cfg.render_mode == NGP_RENDER_COST) {
+			r = g = b = (float)n_steps / 128.0f;
+			a = 1.0f;
+		} else if (cfg.render_mode == NGP_RENDER_SHADE) {
+			// rgb is predicted in sRGB (linear_colors == false): accumulate in linear colours
+			r = srgb_to_linear(r);
+			g = srgb_to_linear(g);
+			b = srgb_to_linear(b);
+		}
+		float4 o = make_float4(r, g, b, a);
 		reinterpret_cast<float4*>(rgba_out)[pix] = o;
 		depth_out[pix] = acc_a > 0.2f ? depth : max_depth();
 		alive = false;
@@ -349,13 +355,24 @@ __global__ void __launch_bounds__(TILE, RENDER_CTAS_PER_SM) k_render_nerf(
 			const float dtu = unwarp_dt(warp_dt(dt));
 			const float alpha = 1.0f - M::expf_(-network_to_density(o3, cfg.density_activation) * dtu);
 			const float weight = alpha * T;
-			acc_r += network_to_rgb(o0, cfg.rgb_activation) * weight;
-			acc_g += network_to_rgb(o1, cfg.rgb_activation) * weight;
-			acc_b += network_to_rgb(o2, cfg.rgb_activation) * weight;
+			// composite_kernel_nerf :641-655: what the colour channels carry depends on the render mode
+			const V3 p = unwarp_position(V3{wx, wy, wz}, train_aabb);
+			float cr, cg, cb;
+			if (cfg.render_mode == NGP_RENDER_POSITIONS) {
+				cr = (p.x - 0.5f) / 2.0f + 0.5f; cg = (p.y - 0.5f) / 2.0f + 0.5f; cb = (p.z - 0.5f) / 2.0f + 0.5f;
+			} else if (cfg.render_mode == NGP_RENDER_DEPTH) {
+				cr = cg = cb = dot3(cam_fwd, p - ro) * cfg.depth_scale;     // payload.origin = the ray origin (after the near-plane offset)
+			} else if (cfg.render_mode == NGP_RENDER_AO) {
+				cr = cg = cb = alpha;
+			} else {
+				cr = network_to_rgb(o0, cfg.rgb_activation); cg = network_to_rgb(o1, cfg.rgb_activation); cb = network_to_rgb(o2, cfg.rgb_activation);
+			}
+			acc_r += cr * weight;
+			acc_g += cg * weight;
+			acc_b += cb * weight;
 			acc_a += weight;
 			if (weight > max_weight) {
 				max_weight = weight;
-				const V3 p = unwarp_position(V3{wx, wy, wz}, train_aabb);
 				depth = dot3(cam_fwd, p - cam_o);
 			}
 			t += dt;
@@ -584,6 +601,8 @@ void render_nerf(const ngp_nerf_desc& d, cudaStream_t stream, const ngp_render_c
 	const uint8_t* bitfield, float* rgba, float* depth, void* scratch, uint32_t* n_steps_total) {
 	NGPB_CHECK(cfg.width > 0 && cfg.height > 0 && y0 >= 0 && y1 <= cfg.height && y0 < y1, "render: bad tile");
 	NGPB_CHECK(cfg.math_mode <= NGP_MATH_REFERENCE, "ngp_render_cfg.math_mode: unknown arithmetic flavour");
+	NGPB_CHECK(cfg.render_mode == NGP_RENDER_SHADE || cfg.render_mode == NGP_RENDER_AO || cfg.render_mode == NGP_RENDER_POSITIONS || cfg.render_mode == NGP_RENDER_DEPTH ||
+		cfg.render_mode == NGP_RENDER_COST, "render: this build renders the modes Shade, AO, Positions, Depth and Cost (Normals needs network input gradients; Distortion / Slice are 2-D debug views)");
 	const NetDev net = make_netdev(d);
 	uint32_t* queue = reinterpret_cast<uint32_t*>(scratch);
 	float* t_first = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(scratch) + 256);

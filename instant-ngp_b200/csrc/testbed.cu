@@ -30,6 +30,8 @@ void nerf_density(const ngp_nerf_desc& d, cudaStream_t stream, uint32_t n, const
 void grid_encode(const ngp_grid_desc& g, cudaStream_t stream, uint32_t n, const float* positions, uint32_t pos_stride, const __half* grid, __half* out);
 void nerf_forward_backward(const ngp_nerf_desc& d, cudaStream_t stream, uint32_t n, const float* coords, const __half* params, const __half* dL_dout,
 	__half* grads, float* mlp_grads_f32, __half* out);
+void profile_mlp_phase(const ngp_nerf_desc& d, cudaStream_t stream, uint32_t n, const float* coords, const __half* params, const __half* dL_dout, __half* grads,
+	float* mlp_grads_f32);
 void optimizer_step(const ngp_nerf_desc& d, cudaStream_t stream, const ngp_adam_cfg& cfg, float* params_fp32, __half* params_fp16, __half* params_ema,
 	__half* grads, float* m1, float* m2, uint32_t* steps);
 void generate_training_samples(cudaStream_t stream, uint32_t n_rays_local, uint32_t ray_offset, uint32_t n_rays_global, uint64_t rng_state, uint64_t rng_inc,
@@ -262,6 +264,7 @@ struct ngp_testbed {
 	bool render_with_lens_distortion = false;    // m_render_with_lens_distortion / m_render_lens (set by set_camera_to_training_view)
 	uint32_t render_lens_mode = NGP_LENS_PERSPECTIVE;
 	float render_lens_params[4] = {0, 0, 0, 0};
+	uint32_t render_mode = NGP_RENDER_SHADE;     // m_render_mode (ERenderMode)
 	uint32_t render_math = NGP_MATH_REFERENCE;   // arithmetic of the render march (ngp_render_cfg.math_mode); `render_math` option
 
 	~ngp_testbed() {
@@ -815,6 +818,9 @@ int ngp_nerf_forward_backward(const ngp_nerf_desc* d, void* stream, uint32_t n, 
 		NGPB_CUDA_CHECK(cudaFreeAsync(tmp, (cudaStream_t)stream));
 	});
 }
+int ngp_profile_mlp_phase(const ngp_nerf_desc* d, void* stream, uint32_t n, const float* coords, const void* params, const void* dL_dout, void* grads, float* mlp_scratch_f32) {
+	NGPB_TRY(require_device(); profile_mlp_phase(*d, (cudaStream_t)stream, n, coords, (const __half*)params, (const __half*)dL_dout, (__half*)grads, mlp_scratch_f32));
+}
 int ngp_optimizer_step(const ngp_nerf_desc* d, void* stream, const ngp_adam_cfg* cfg, float* p32, void* p16, void* ema, void* grads, float* m1, float* m2,
 	uint32_t* steps) {
 	NGPB_TRY(require_device(); optimizer_step(*d, (cudaStream_t)stream, *cfg, p32, (__half*)p16, (__half*)ema, (__half*)grads, m1, m2, steps));
@@ -1079,6 +1085,8 @@ int ngp_testbed_set_option(ngp_testbed* t, const char* name_c, double value) {
 		else if (n == "exposure") t->exposure = (float)value;
 		else if (n == "nerf.training.math_mode") { NGPB_CHECK(value == 0 || value == 1, "math_mode must be 0 (deterministic) or 1 (reference)"); tb_invalidate_prefetch(t); t->cfg.math_mode = (uint32_t)value; }
 		else if (n == "nerf.training.gen_lanes_per_ray") { const uint32_t g = (uint32_t)value; NGPB_CHECK(g <= 32 && (g & (g - 1)) == 0, "gen_lanes_per_ray must be 0 or a power of two up to 32"); tb_invalidate_prefetch(t); t->cfg.gen_lanes_per_ray = g; }
+		else if (n == "render_mode") { NGPB_CHECK(value == NGP_RENDER_SHADE || value == NGP_RENDER_AO || value == NGP_RENDER_POSITIONS || value == NGP_RENDER_DEPTH || value == NGP_RENDER_COST,
+			"render_mode: this build renders Shade, AO, Positions, Depth and Cost"); t->render_mode = (uint32_t)value; }
 		else if (n == "render_math") { NGPB_CHECK(value == 0 || value == 1, "render_math must be 0 (deterministic) or 1 (reference)"); t->render_math = (uint32_t)value; }
 		else if (n == "nerf.training.full_inference") { NGPB_CHECK(value == 0 || value == 1 || value == 2, "full_inference: 0 ray-ordered, 1 every sample, 2 automatic"); tb_invalidate_prefetch(t); t->full_inference = (uint32_t)value; }
 		else if (n == "nerf.training.train_mode") { NGPB_CHECK(value == 0 || value == 1 || value == 2, "train_mode must be Nerf (0), Rfl (1) or RflRelax (2)"); c.train_mode = (uint32_t)value; }
@@ -1107,6 +1115,7 @@ double ngp_testbed_get_option(ngp_testbed* t, const char* name_c) {
 	if (n == "nerf.training.math_mode") return c.math_mode;
 	if (n == "nerf.training.gen_lanes_per_ray") return c.gen_lanes_per_ray;
 	if (n == "render_math") return t->render_math;
+	if (n == "render_mode") return t->render_mode;
 	if (n == "nerf.training.density_grid_decay") return t->density_grid_decay;
 	if (n == "nerf.rgb_activation") return c.rgb_activation;
 	if (n == "nerf.density_activation") return c.density_activation;
@@ -1307,6 +1316,8 @@ static void tb_fill_render_cfg(ngp_testbed* t, ngp_render_cfg& rc, int32_t width
 	rc.lens_mode = t->render_with_lens_distortion ? t->render_lens_mode : (uint32_t)NGP_LENS_PERSPECTIVE;
 	for (int k = 0; k < 4; ++k) rc.lens_params[k] = t->render_with_lens_distortion ? t->render_lens_params[k] : 0.0f;
 	rc.math_mode = t->render_math;
+	rc.render_mode = t->render_mode;
+	rc.depth_scale = 1.0f / t->scene_scale;   // testbed_nerf.cu:2037
 }
 
 int ngp_testbed_render_device(ngp_testbed* t, int32_t width, int32_t height, const float* cam, float fx, float fy, float cx, float cy, int32_t y0,

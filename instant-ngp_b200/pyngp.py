@@ -51,7 +51,7 @@ class NerfActivation(enum.IntEnum):  # ENerfActivation
     Exponential = 3
 
 
-class RenderMode(enum.IntEnum):  # ERenderMode (common.h): only the shaded image is produced by this build
+class RenderMode(enum.IntEnum):  # ERenderMode (common.h:68-79); rendered here: AO, Shade, Positions, Depth, Cost
     AO = 0
     Shade = 1
     Normals = 2
@@ -463,12 +463,12 @@ class Testbed:
 
     @property
     def render_mode(self) -> RenderMode:
-        return RenderMode.Shade
+        """m_render_mode (python_api.cu:683): Shade, AO, Positions, Depth and Cost are rendered; the others are refused by the library"""
+        return RenderMode(int(self._get("render_mode")))
 
     @render_mode.setter
     def render_mode(self, v) -> None:
-        if RenderMode(int(v)) != RenderMode.Shade:
-            raise B.NgpError("render_mode: only Shade is implemented")
+        self._set("render_mode", float(int(RenderMode(int(v)))))
 
     # -- camera (src/testbed.cu:440, 486-528, 4081-4087, 4649-4657) -------------------------------------------------------
     @property

@@ -847,6 +847,14 @@ EXPORT void orc_render_composite(const ngp_render_cfg* cfg, int32_t y0, int32_t 
 	for (int32_t q = 0; q < (y1 - y0) * cfg->width; ++q) {
 		float r = 0, g = 0, b = 0, a = 0, max_weight = 0.0f, depth = MAX_DEPTH;
 		uint32_t j = 0;
+		/* the ray origin (NerfPayload::origin: after the near-plane offset), for the Depth mode */
+		v3 ray_o, ray_d;
+		{
+			const uint32_t x = (uint32_t)(q % cfg->width), y = (uint32_t)(y0 + q / cfg->width);
+			const float u = ((float)x + 0.5f) / (float)cfg->width, v = ((float)y + 0.5f) / (float)cfg->height;
+			uv_to_ray(u, v, cfg->width, cfg->height, cfg->focal_x, cfg->focal_y, cfg->screen_x, cfg->screen_y, NGP_LENS_PERSPECTIVE, 0, cfg->camera, &ray_o, &ray_d);
+			ray_o = vadd(ray_o, vscale(ray_d, cfg->near_distance));
+		}
 		for (; j < counts[q]; ++j) {
 			const float* c = coords + ((size_t)q * max_steps + j) * 7;
 			const uint16_t* o = network_output + ((size_t)q * max_steps + j) * 4;
@@ -854,22 +862,31 @@ EXPORT void orc_render_composite(const ngp_render_cfg* cfg, int32_t y0, int32_t 
 			float dt = unwarp_dt(c[3]);
 			float alpha = 1.f - ngp_expf(-network_to_density(half_to_float(o[3]), cfg->density_activation) * dt);
 			float weight = alpha * T;
-			r += network_to_rgb(half_to_float(o[0]), cfg->rgb_activation) * weight;
-			g += network_to_rgb(half_to_float(o[1]), cfg->rgb_activation) * weight;
-			b += network_to_rgb(half_to_float(o[2]), cfg->rgb_activation) * weight;
+			/* composite_kernel_nerf :641-655 */
+			v3 pos = unwarp_position(V(c[0], c[1], c[2]), &train_aabb);
+			float cr, cg, cb;
+			if (cfg->render_mode == NGP_RENDER_POSITIONS) { cr = (pos.x - 0.5f) / 2.0f + 0.5f; cg = (pos.y - 0.5f) / 2.0f + 0.5f; cb = (pos.z - 0.5f) / 2.0f + 0.5f; }
+			else if (cfg->render_mode == NGP_RENDER_DEPTH) { cr = cg = cb = vdot(cam_fwd, vsub(pos, ray_o)) * cfg->depth_scale; }
+			else if (cfg->render_mode == NGP_RENDER_AO) { cr = cg = cb = alpha; }
+			else { cr = network_to_rgb(half_to_float(o[0]), cfg->rgb_activation); cg = network_to_rgb(half_to_float(o[1]), cfg->rgb_activation); cb = network_to_rgb(half_to_float(o[2]), cfg->rgb_activation); }
+			r += cr * weight;
+			g += cg * weight;
+			b += cb * weight;
 			a += weight;
 			if (weight > max_weight) {
 				max_weight = weight;
-				v3 pos = unwarp_position(V(c[0], c[1], c[2]), &train_aabb);
 				depth = vdot(cam_fwd, vsub(pos, cam_o));
 			}
 			if (a > (1.0f - cfg->min_transmittance)) { r /= a; g /= a; b /= a; a /= a; ++j; break; }
 		}
 		if (steps_used) steps_used[q] = j;
-		/* shade_kernel_nerf: predicted colours are sRGB (linear_colors == false) -> accumulate in linear */
-		rgba_out[(size_t)q * 4 + 0] = srgb_to_linear(r);
-		rgba_out[(size_t)q * 4 + 1] = srgb_to_linear(g);
-		rgba_out[(size_t)q * 4 + 2] = srgb_to_linear(b);
+		/* shade_kernel_nerf (:1333-1378): Cost = steps / 128 with alpha 1; Shade: predicted colours are sRGB (linear_colors == false) ->
+		 * accumulate in linear; the other modes pass the composited value through */
+		if (cfg->render_mode == NGP_RENDER_COST) { r = g = b = (float)j / 128.0f; a = 1.0f; }   /* every pixel, also rays without a sample */
+		else if (cfg->render_mode == NGP_RENDER_SHADE) { r = srgb_to_linear(r); g = srgb_to_linear(g); b = srgb_to_linear(b); }
+		rgba_out[(size_t)q * 4 + 0] = r;
+		rgba_out[(size_t)q * 4 + 1] = g;
+		rgba_out[(size_t)q * 4 + 2] = b;
 		rgba_out[(size_t)q * 4 + 3] = a;
 		depth_out[q] = a > 0.2f ? depth : MAX_DEPTH;
 	}

@@ -142,7 +142,15 @@ def test_reference_shaped_camera_api(trained):
     assert lit.any() and (brighter[..., :3][lit] >= base[..., :3][lit]).all() and brighter[..., :3][lit].mean() > 1.2 * base[..., :3][lit].mean()
     assert tb.render_mode == P.RenderMode.Shade and not tb.snap_to_pixel_centers and tb.jit_fusion   # m_snap_to_pixel_centers defaults to false (testbed.h)
     with pytest.raises(P.NgpError):
-        tb.render_mode = P.RenderMode.Depth
+        tb.render_mode = P.RenderMode.Normals    # needs network input gradients: not built
+    # Depth / Cost / AO / Positions through the Testbed: alpha agrees with the shaded frame, Cost counts the frame's network evaluations
+    tb.render_mode = P.RenderMode.Depth
+    dep = tb.render(64, 64, 1, True)
+    assert np.allclose(dep[..., 3], lin[..., 3], atol=1e-5) and np.allclose(dep[..., 0], dep[..., 1]) and (dep[..., 0][lit] > 0).all()
+    tb.render_mode = P.RenderMode.Cost
+    cost = tb.render(64, 64, 1, True)
+    assert (cost[..., 3] == 1.0).all() and int(round(float(cost[..., 0].sum()) * 128)) == tb.last_render_steps
+    tb.render_mode = P.RenderMode.Shade
     with pytest.raises(P.NgpError):
         tb.render(64, 64, 1, True, 0.0, 1.0)     # camera paths
 

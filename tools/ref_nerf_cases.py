@@ -100,6 +100,8 @@ def make_render_cfg(w, h, cam, focal, aabb_scale, spp_index=0):
     rc.spp_index = spp_index
     rc.pixel_offset[0] = rc.pixel_offset[1] = 0.5   # snap_to_pixel_centers (ld_random_pixel_offset(0) == (0.5, 0.5))
     rc.near_distance = 0.0
+    rc.render_mode = 1          # ERenderMode::Shade
+    rc.depth_scale = 1.0 / 0.33
     return rc
 
 
