@@ -190,8 +190,10 @@ struct LevelCell {
 
 // gather of HALF of the levels of one sample: 16 encoded features (8 half2) = chunks {2*half, 2*half+1} of the A0 row.
 // NET is any struct with a `levels` table (NetDev, FieldDev).
-template <uint32_t F, uint32_t D, typename NET>
-__device__ __forceinline__ void grid_gather_half_nd(const NET& net, const __half* __restrict__ grid, uint32_t half, const float (&x)[D], __half2 (&enc)[8]) {
+// HALF is a template argument so that the level table is read with constant indices: with a run-time half the 5 words of every level's
+// metadata come through LDC with a register offset, 13 % of k_nerf_train's stall samples (ncu r2f); the dispatcher below is warp uniform.
+template <uint32_t F, uint32_t D, uint32_t half, typename NET>
+__device__ __forceinline__ void grid_gather_half_impl(const NET& net, const __half* __restrict__ grid, const float (&x)[D], __half2 (&enc)[8]) {
 	constexpr uint32_t H2_PER_LEVEL = F / 2;
 	constexpr uint32_t LEVELS_PER_HALF = (ENC_WIDTH / F) / 2;
 	constexpr uint32_t NC = 1u << D;
@@ -251,10 +253,16 @@ __device__ __forceinline__ void grid_gather_half_nd(const NET& net, const __half
 	}
 }
 
+template <uint32_t F, uint32_t D, typename NET>
+__device__ __forceinline__ void grid_gather_half_nd(const NET& net, const __half* __restrict__ grid, uint32_t half, const float (&x)[D], __half2 (&enc)[8]) {
+	if (half == 0) grid_gather_half_impl<F, D, 0>(net, grid, x, enc);
+	else grid_gather_half_impl<F, D, 1>(net, grid, x, enc);
+}
+
 // scatter dL/d(encoding) of HALF of the levels of one sample into the fp16 gradient table
 // (≙ kernel_grid_backward, grid.h:214-320: fp16 weight x fp16 gradient, red.global.add.f16x2 per corner).
-template <uint32_t F, uint32_t D, typename NET>
-__device__ __forceinline__ void grid_scatter_half_nd(const NET& net, __half* __restrict__ grid_grad, uint32_t half, const float (&x)[D], const __half2 (&g)[8]) {
+template <uint32_t F, uint32_t D, uint32_t half, typename NET>
+__device__ __forceinline__ void grid_scatter_half_impl(const NET& net, __half* __restrict__ grid_grad, const float (&x)[D], const __half2 (&g)[8]) {
 	constexpr uint32_t LEVELS_PER_HALF = (ENC_WIDTH / F) / 2;
 	constexpr uint32_t NC = 1u << D;
 	// fully unrolled: with a partial unroll g[ll] is indexed dynamically and the gradient array lands in local memory — the LDL
@@ -320,6 +328,12 @@ __device__ __forceinline__ void grid_scatter_half_nd(const NET& net, __half* __r
 			}
 		}
 	}
+}
+
+template <uint32_t F, uint32_t D, typename NET>
+__device__ __forceinline__ void grid_scatter_half_nd(const NET& net, __half* __restrict__ grid_grad, uint32_t half, const float (&x)[D], const __half2 (&g)[8]) {
+	if (half == 0) grid_scatter_half_impl<F, D, 0>(net, grid_grad, x, g);
+	else grid_scatter_half_impl<F, D, 1>(net, grid_grad, x, g);
 }
 
 template <uint32_t F>
