@@ -36,6 +36,7 @@ def lib() -> C.CDLL:
             "orc_cascaded_grid_idx_at": (u32, [vp, u32]),
             "orc_advance_to_next_voxel": (f32, [f32, MC, vp, vp, u32]),
             "orc_uv_to_ray": (None, [f32, f32, C.POINTER(B.TrainView), vp]),
+            "orc_detmath_n": (None, [C.c_int, vp, vp, vp, u32]),
             "orc_srgb_to_linear": (f32, [f32]),
             "orc_linear_to_srgb": (f32, [f32]),
             "orc_linear_to_srgb_n": (None, [vp, vp, u32]),

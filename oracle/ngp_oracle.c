@@ -270,6 +270,11 @@ EXPORT void orc_uv_to_ray(float u, float v, const ngp_train_view* vw, float* o6)
 /* colour (common_device.cuh:61-103) */
 static float srgb_to_linear(float s) { return s <= 0.04045f ? s / 12.92f : ngp_powf((s + 0.055f) / 1.055f, 2.4f); }
 static float linear_to_srgb(float l) { return l < 0.0031308f ? 12.92f * l : 1.055f * ngp_powf(l, 0.41666f) - 0.055f; }
+/* ngp_detmath.h itself, element-wise: the header is shared by this oracle and the CUDA product, so it is checked against libm on its own
+ * (tests/test_detmath.py) — a bug in it would be invisible to every CUDA-vs-oracle comparison.  which: 0 log, 1 exp, 2 pow(x, y) */
+EXPORT void orc_detmath_n(int which, const float* x, const float* y, float* out, uint32_t n) {
+	for (uint32_t i = 0; i < n; ++i) out[i] = which == 0 ? ngp_logf(x[i]) : (which == 1 ? ngp_expf(x[i]) : ngp_powf(x[i], y[i]));
+}
 EXPORT float orc_srgb_to_linear(float s) { return srgb_to_linear(s); }
 EXPORT float orc_linear_to_srgb(float l) { return linear_to_srgb(l); }
 EXPORT void orc_linear_to_srgb_n(const float* in, float* out, uint32_t n) {

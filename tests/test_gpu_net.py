@@ -170,6 +170,63 @@ def test_backward_accumulates_and_is_linear_in_dloss(lib):
     assert np.abs(b - 2 * a).max() <= 2e-2 * np.abs(b).max()
 
 
+def test_full_batch_gradients_match_the_fp32_cpu_port_level_by_level(lib):
+    """The training batch itself (2^18 samples): hash-grid and MLP gradients against the fp32 CPU port of the network (oracle/ngp_net_cpu.c,
+    OpenMP; checked against the fp16-exact numpy oracle in tests/test_cpu_baseline.py), LEVEL BY LEVEL.  The samples are laid out like a
+    training batch — runs of consecutive samples along rays — so the coarse levels see what they see in training: thousands of fp16
+    `red.add` operations into the same few entries at loss scale 128.  What is being checked is that the fp16 accumulation in arbitrary
+    order neither saturates nor drifts: per level, the relative L2 error of the gradient and the ratio of the sums."""
+    import torch
+
+    from oracle import net_cpu
+
+    d, L = util.make_desc(n_levels=16, F=2, log2_T=19, aabb_scale=4)
+    n = 262144
+    rng = np.random.default_rng(21)
+    params = util.random_params(L, seed=9, trained_like=True).astype(np.float16)
+    # 3584 rays x ~73 consecutive samples, step 1/256 of the unit cube, inside the central eighth of the cube (a scene's bounding box)
+    n_rays = 3584
+    o = rng.uniform(0.4, 0.6, size=(n_rays, 3))
+    dirs = rng.normal(size=(n_rays, 3))
+    dirs /= np.linalg.norm(dirs, axis=1, keepdims=True)
+    ray = rng.integers(0, n_rays, size=n)
+    ray.sort()
+    k = np.arange(n) - np.searchsorted(ray, ray)            # index of the sample along its ray
+    pos = np.clip(o[ray] + dirs[ray] * (k[:, None] * (1.0 / 1024.0)), 0.0, 1.0)
+    coords = np.zeros((n, 7), dtype=np.float32)
+    coords[:, 0:3] = pos
+    coords[:, 4:7] = (dirs[ray] + 1.0) * 0.5
+    # loss-scaled gradients of the size a training step produces (loss_scale 128 / ~3.6 K rays, activations' derivatives O(1))
+    dl = (rng.normal(0, 1, size=(n, 4)) * (128.0 / n_rays) * 0.5).astype(np.float16)
+
+    t_p, t_c, t_dl = dev(params), dev(coords), dev(dl)
+    t_g = torch.zeros(d.n_params, dtype=torch.float16, device="cuda")
+    assert lib.ngp_nerf_forward_backward(C.byref(d), stream(), n, t_c.data_ptr(), t_p.data_ptr(), t_dl.data_ptr(), t_g.data_ptr(), None) == 0, lib.ngp_last_error()
+    torch.cuda.synchronize()
+    g = t_g.cpu().numpy().astype(np.float64)
+    assert np.isfinite(g).all(), "fp16 gradient accumulation overflowed"
+    _, want = net_cpu.NetCpu(L, params).forward_backward(coords, dl)
+    want = want.astype(np.float64)
+    n_mlp = L.n_mlp_params
+    rel = np.linalg.norm(g[:n_mlp] - want[:n_mlp]) / np.linalg.norm(want[:n_mlp])
+    print(f"MLP weight gradients: relative L2 error {rel:.3e}, largest |g| {np.abs(g[:n_mlp]).max():.3e}")
+    assert rel < 2e-2
+    gg, wg = g[n_mlp:].reshape(-1, 2), want[n_mlp:].reshape(-1, 2)
+    worst = 0.0
+    for l in range(L.grid.n_levels):
+        a, b = gg[L.grid.offsets[l]:L.grid.offsets[l + 1]], wg[L.grid.offsets[l]:L.grid.offsets[l + 1]]
+        touched = int((np.abs(b).sum(axis=1) > 0).sum())
+        rel = np.linalg.norm(a - b) / (np.linalg.norm(b) + 1e-30)
+        ratio = np.abs(a).sum() / (np.abs(b).sum() + 1e-30)
+        print(f"level {l:2d}: {touched:7d} entries touched, {8 * n / max(touched, 1):9.1f} reductions per entry, relative L2 error {rel:.3e}, |sum| ratio {ratio:.4f}, "
+              f"largest |g| {np.abs(a).max():.3e}")
+        worst = max(worst, rel)
+        # fp16 (11-bit) partial sums in arbitrary order, fp16 products of fp16 weights: a few percent on the most contended levels
+        assert rel < 6e-2 and 0.97 < ratio < 1.03, f"level {l}"
+        assert (np.abs(a[np.abs(b).sum(axis=1) == 0]) == 0).all(), "gradient written to an untouched entry"
+    assert np.abs(gg).max() < 6.0e4 / 4, "within a factor 4 of fp16 saturation"
+
+
 def test_optimizer_step_matches_oracle(lib):
     """fused Adam + EMA + gradient zeroing against the oracle (which is itself pinned to the reference's adam_step / ema_step
     outputs, tests/test_oracle_vs_reference_tcnn.py)"""
