@@ -75,8 +75,10 @@ def default_scene() -> str:
 
 
 # ---------------------------------------------------------------------------------------------------------------------
-# dram__bytes_read.sum + dram__bytes_write.sum of one k_nerf_train launch at this workload (ncu --set full, profiles/r1e_end_of_round.md)
-K_NERF_TRAIN_DRAM_BYTES = 54.52e6 + 0.20e6
+# dram__bytes_read.sum + dram__bytes_write.sum of one k_nerf_train launch (ncu --set full): nerf/fox profiles/r2/r2f_train_fox_ncu.md,
+# the synthetic scene profiles/r1e_end_of_round.md
+K_NERF_TRAIN_DRAM_BYTES = {"fox": 58.57e6 + 0.29e6, "ball": 54.52e6 + 0.20e6}
+K_NERF_TRAIN_DRAM_SOURCE = {"fox": "profiles/r2/r2f_train_fox_ncu.md", "ball": "profiles/r1e_end_of_round.md"}
 
 
 class ClockSampler:
@@ -521,9 +523,9 @@ def main() -> None:
         achieved = alg_bytes / (fb_ms * 1e-3) / 1e9 if fb_ms > 0 else None
         sm_mhz = clocks.get("sm_mhz") or 1965.0
         roofline = {"bound": "hbm", "kernel": "k_nerf_train (+k_mlp_grads_finalize)", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                    "frac": (achieved / pk["hbm_gbs"]) if achieved else None, "traffic": K_NERF_TRAIN_DRAM_BYTES, "peak_source": pk["source"], "ms_per_launch": fb_ms,
+                    "frac": (achieved / pk["hbm_gbs"]) if achieved else None, "traffic": K_NERF_TRAIN_DRAM_BYTES[scene], "peak_source": pk["source"], "ms_per_launch": fb_ms,
                     "algorithmic_bytes_per_launch": alg_bytes,
-                    "traffic_source": "profiles/r1e_end_of_round.md (synthetic scene; per launch)",
+                    "traffic_source": K_NERF_TRAIN_DRAM_SOURCE[scene] + " (per launch)",
                     "note": "the 26 MB fp16 table and its gradient table are L2-resident on B200: the kernel is bound by L2 gather/reduction traffic and latency, DRAM traffic is an eighth of the algorithmic bytes"}
         # second kernel of the step by time: the sample generator.  Algorithmic bytes: the 28-byte coordinate record of every generated sample
         # (SURVEY 8d "1 march step": the bit test itself is L1/L2 resident); it is latency bound (a serial log/exp recurrence per ray), which

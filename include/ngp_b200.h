@@ -505,6 +505,11 @@ int ngp_field_testbed_set_image(ngp_field_testbed* t, const float* rgba_host, in
 /* positions [n x 3] already in the unit cube, distances [n] (what override_sdf_training_data stores after its normalisation) */
 int ngp_field_testbed_set_sdf_training_data(ngp_field_testbed* t, const float* positions_host, const float* distances_host, uint32_t n);
 int ngp_field_testbed_reload_network_from_json(ngp_field_testbed* t, const char* json_text);
+/* Testbed::save_snapshot / load_snapshot (src/testbed.cu:5288-5485) for the image / SDF modes: the reference's container (msgpack, gzip-wrapped
+ * for ".ingp") with the network config and "snapshot": {n_params, params_type "__half", params_binary = inference weights in the order
+ * MLP | encoding, version, mode "image" / "sdf", training_step, loss, aabb}.  Loading rebuilds the network from the stored config. */
+int ngp_field_testbed_save_snapshot(ngp_field_testbed* t, const char* path, int include_optimizer_state, int compress);
+int ngp_field_testbed_load_snapshot(ngp_field_testbed* t, const char* path);
 int ngp_field_testbed_set_seed(ngp_field_testbed* t, uint64_t seed);
 /* options: image.training.snap_to_pixel_centers, image.training.linear_colors, image.random_mode_stratified, train_network,
  * train_encoding, loss_scale */

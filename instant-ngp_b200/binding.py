@@ -267,6 +267,8 @@ PROTOTYPES = {
     "ngp_field_testbed_set_image": (C.c_int, [vp, vp, i32, i32]),
     "ngp_field_testbed_set_sdf_training_data": (C.c_int, [vp, vp, vp, u32]),
     "ngp_field_testbed_reload_network_from_json": (C.c_int, [vp, cp]),
+    "ngp_field_testbed_save_snapshot": (C.c_int, [vp, cp, C.c_int, C.c_int]),
+    "ngp_field_testbed_load_snapshot": (C.c_int, [vp, cp]),
     "ngp_field_testbed_set_seed": (C.c_int, [vp, u64]),
     "ngp_field_testbed_set_option": (C.c_int, [vp, cp, C.c_double]),
     "ngp_field_testbed_train": (C.c_int, [vp, u32]),

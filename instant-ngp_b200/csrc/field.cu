@@ -16,9 +16,12 @@
 #include <random>
 #include <vector>
 
+#include <fstream>
+
 #include "host_util.h"
 #include "march.cuh"
 #include "mlp_train.cuh"
+#include "msgpack_mini.h"
 
 namespace ngpb {
 
@@ -683,6 +686,7 @@ struct ngp_field_testbed {
 	Pcg32 rng{1337};
 
 	bool has_network = false;
+	Json network_config;          // as given to reload_network_from_json (m_network_config)
 	ngp_field_desc desc{};
 	OptimizerConfig opt;
 	uint32_t loss_type = NGP_LOSS_L2;
@@ -743,8 +747,10 @@ static void ftb_set_params_fp32(ngp_field_testbed* t, const float* host, size_t 
 	NGPB_CUDA_CHECK(cudaStreamSynchronize(t->stream));
 }
 
-static void ftb_reset_network(ngp_field_testbed* t, const std::string& json_text) {
-	const Json config = JsonParser(json_text).parse();
+static void ftb_reset_network_json(ngp_field_testbed* t, const Json& config_in) {
+	Json config = config_in;
+	config.obj.erase("snapshot");
+	t->network_config = config;
 	const Json& enc = config.sub("encoding");
 	const Json& net = config.sub("network");
 	const std::string enc_type = to_lower(enc.value("otype", std::string("HashGrid")));
@@ -793,6 +799,93 @@ static void ftb_reset_network(ngp_field_testbed* t, const std::string& json_text
 	std::vector<float> init(t->desc.n_params);
 	field_init_params_host(&t->desc, t->seed, init.data());
 	ftb_set_params_fp32(t, init.data(), init.size());
+}
+static void ftb_reset_network(ngp_field_testbed* t, const std::string& json_text) { ftb_reset_network_json(t, JsonParser(json_text).parse()); }
+
+// ---- snapshots of the image / SDF modes in the reference's container (Testbed::save_snapshot / load_snapshot, src/testbed.cu:5288-5485):
+// msgpack({network config..., "snapshot": {Trainer::serialize (n_params, params_type, params_binary = the INFERENCE weights, trainer.h:442-452),
+// version, mode, training_step, loss, aabb, ...}}), gzip-wrapped for ".ingp".  Parameter order MLP | encoding
+// (network_with_input_encoding.h:121-128).  No optimizer state (include_optimizer_state is refused).
+static bool ftb_has_ext(const std::string& path, const char* ext) {
+	const size_t n = strlen(ext);
+	return path.size() >= n && to_lower(path.substr(path.size() - n)) == ext;
+}
+static void ftb_save_snapshot(ngp_field_testbed* t, const std::string& path, bool include_optimizer_state, bool compress) {
+	NGPB_CHECK(t->has_network, "save_snapshot: no network");
+	NGPB_CHECK(!include_optimizer_state, "save_snapshot: optimizer state is not written for the image / SDF modes");
+	NGPB_CHECK(ftb_has_ext(path, ".ingp") || ftb_has_ext(path, ".msgpack"), "save_snapshot: the image / SDF modes write .ingp / .msgpack");
+	NGPB_CUDA_CHECK(cudaStreamSynchronize(t->stream));
+	const size_t n = t->desc.n_params;
+	std::vector<uint8_t> host(n * sizeof(__half));
+	NGPB_CUDA_CHECK(cudaMemcpy(host.data(), t->params_ema.p, host.size(), cudaMemcpyDeviceToHost));
+	Json config = t->network_config;
+	Json snap = jobj();
+	snap.obj["n_params"] = jint((int64_t)n);
+	snap.obj["params_type"] = jstr("__half");
+	snap.obj["params_binary"] = jbin(host.data(), host.size());
+	snap.obj["version"] = jint(1);
+	snap.obj["mode"] = jstr(t->mode == NGP_MODE_IMAGE ? "image" : "sdf");
+	snap.obj["training_step"] = jint(t->training_step);
+	snap.obj["loss"] = jnum(t->loss_scalar);
+	Json aabb = jobj(), mn = jarr(), mx = jarr();
+	for (int k = 0; k < 3; ++k) {
+		mn.arr.push_back(jnum(0.0));
+		mx.arr.push_back(jnum(1.0));
+	}
+	aabb.obj["min"] = mn;
+	aabb.obj["max"] = mx;
+	snap.obj["aabb"] = aabb;
+	if (t->mode == NGP_MODE_IMAGE) {
+		Json res = jarr();
+		res.arr.push_back(jint(t->img_w));
+		res.arr.push_back(jint(t->img_h));
+		snap.obj["image_resolution"] = res;   // not a reference key: lets a render-only load size its frame (the reference re-reads the image file)
+	}
+	config.obj["snapshot"] = snap;
+	MsgPackWriter w;
+	w.write(config);
+	std::vector<uint8_t> bytes = ftb_has_ext(path, ".ingp") ? gzip_compress(w.out, compress ? Z_DEFAULT_COMPRESSION : Z_NO_COMPRESSION) : w.out;
+	std::ofstream f(path, std::ios::binary);
+	NGPB_CHECK(f.good(), "cannot open " + path);
+	f.write(reinterpret_cast<const char*>(bytes.data()), (std::streamsize)bytes.size());
+	NGPB_CHECK(f.good(), "snapshot write failed");
+}
+static void ftb_load_snapshot(ngp_field_testbed* t, const std::string& path) {
+	std::ifstream f(path, std::ios::binary);
+	NGPB_CHECK(f.good(), "Network snapshot '" + path + "' does not exist.");
+	std::vector<uint8_t> bytes((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+	if (ftb_has_ext(path, ".ingp")) bytes = gzip_decompress(bytes);
+	MsgPackReader r(bytes.data(), bytes.size());
+	const Json config = r.read();
+	NGPB_CHECK(config.contains("snapshot"), "file does not contain a snapshot");
+	const Json& snap = config.at("snapshot");
+	NGPB_CHECK((uint32_t)snap.value("version", 0.0) >= 1, "Snapshot uses an old format and can not be loaded.");
+	const std::string mode = to_lower(snap.value("mode", std::string("")));
+	NGPB_CHECK(mode == (t->mode == NGP_MODE_IMAGE ? "image" : "sdf"), "snapshot mode '" + mode + "' does not match this Testbed's mode");
+	if (t->mode == NGP_MODE_IMAGE && t->img_w == 0 && snap.contains("image_resolution")) {
+		// render-only load without the training image: the per-level scale derives from the resolution (src/testbed.cu:4236-4255)
+		t->img_w = (int32_t)snap.at("image_resolution").arr.at(0).num;
+		t->img_h = (int32_t)snap.at("image_resolution").arr.at(1).num;
+	}
+	ftb_reset_network_json(t, config);
+	const size_t n = t->desc.n_params;
+	NGPB_CHECK((size_t)snap.value("n_params", 0.0) == n, "snapshot: parameter count does not match the network config");
+	const Json& pb = snap.at("params_binary");
+	NGPB_CHECK(pb.type == Json::Binary, "snapshot: params_binary is not binary");
+	const std::string ptype = snap.value("params_type", std::string("__half"));
+	std::vector<float> p32(n);
+	if (ptype == "float") {
+		NGPB_CHECK(pb.bin.size() == n * 4, "snapshot: params_binary has the wrong size");
+		memcpy(p32.data(), pb.bin.data(), n * 4);
+	} else {
+		NGPB_CHECK(ptype == "__half" && pb.bin.size() == n * 2, "snapshot: params_binary has the wrong size / type");
+		const __half* h = reinterpret_cast<const __half*>(pb.bin.data());
+		for (size_t i = 0; i < n; ++i) p32[i] = __half2float(h[i]);
+	}
+	ftb_set_params_fp32(t, p32.data(), n);   // Trainer::deserialize: all three parameter buffers from the file (trainer.h:454-478)
+	t->training_step = (uint32_t)snap.value("training_step", 0.0);
+	t->optimizer_step = 0;
+	t->loss_scalar = (float)snap.value("loss", 0.0);
 }
 
 static void ftb_train(ngp_field_testbed* t, uint32_t batch) {
@@ -984,6 +1077,10 @@ int ngp_field_testbed_set_sdf_training_data(ngp_field_testbed* t, const float* p
 	});
 }
 int ngp_field_testbed_reload_network_from_json(ngp_field_testbed* t, const char* json_text) { NGPB_TRY(ftb_reset_network(t, json_text)); }
+int ngp_field_testbed_save_snapshot(ngp_field_testbed* t, const char* path, int include_optimizer_state, int compress) {
+	NGPB_TRY(ftb_save_snapshot(t, path, include_optimizer_state != 0, compress != 0));
+}
+int ngp_field_testbed_load_snapshot(ngp_field_testbed* t, const char* path) { NGPB_TRY(ftb_load_snapshot(t, path)); }
 int ngp_field_testbed_set_seed(ngp_field_testbed* t, uint64_t seed) { NGPB_TRY(t->seed = seed; t->rng = Pcg32(seed)); }
 int ngp_field_testbed_set_option(ngp_field_testbed* t, const char* name, double v) {
 	NGPB_TRY({

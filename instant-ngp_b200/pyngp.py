@@ -263,11 +263,22 @@ class FieldTestbed:
         self.data_path = str(path)
 
     def load_file(self, path) -> None:
-        """python_api.cu:573: a network config (.json with network / encoding / loss / optimizer keys) or the training image"""
+        """python_api.cu:573: a snapshot (.ingp / .msgpack), a network config (.json with network / encoding / loss / optimizer keys) or the
+        training image"""
         p = Path(path)
+        if p.suffix.lower() in (".ingp", ".msgpack"):
+            return self.load_snapshot(p)
         if p.suffix.lower() == ".json":
             return self.reload_network_from_file(p)
         self.load_training_data(p)
+
+    def save_snapshot(self, path: str, include_optimizer_state: bool = False, compress: bool = True) -> None:
+        """python_api.cu:563-570 for the image / SDF modes: the reference's .ingp / .msgpack container (network config + inference weights)"""
+        B.check(B.lib().ngp_field_testbed_save_snapshot(self._h, str(path).encode(), int(include_optimizer_state), int(compress)))
+
+    def load_snapshot(self, path: str) -> None:
+        """python_api.cu:571: rebuilds the network from the config stored in the snapshot and takes its weights"""
+        B.check(B.lib().ngp_field_testbed_load_snapshot(self._h, str(Path(path)).encode()))
 
     def override_sdf_training_data(self, points: np.ndarray, distances: np.ndarray) -> None:
         """python_api.cu:74-113.  Points are taken as unit-cube coordinates (no mesh is loaded, so there is no raw AABB to

@@ -343,6 +343,71 @@ def test_sdf_testbed_learns_a_sphere(lib):
         tb.train(1 << 17)   # more than the available records (testbed_sdf.cu:1582 silently skips; here it is an error)
 
 
+SDF_CONFIG = {
+    "loss": {"otype": "MAPE"},
+    "optimizer": {"otype": "Ema", "decay": 0.95, "nested": {"otype": "ExponentialDecay", "decay_start": 10000, "decay_interval": 5000, "decay_base": 0.33,
+                  "nested": {"otype": "Adam", "learning_rate": 3e-3, "beta1": 0.9, "beta2": 0.99, "epsilon": 1e-15, "l2_reg": 1e-6}}},
+    "encoding": {"otype": "HashGrid", "n_levels": 16, "n_features_per_level": 2, "log2_hashmap_size": 15, "base_resolution": 16},
+    "network": {"otype": "FullyFusedMLP", "activation": "ReLU", "output_activation": "None", "n_neurons": 64, "n_hidden_layers": 2},
+}
+
+
+@pytest.mark.parametrize("ext", [".ingp", ".msgpack"])
+def test_image_and_sdf_snapshots_use_the_reference_container(lib, tmp_path, ext):
+    """Testbed::save_snapshot / load_snapshot for the image and SDF modes (src/testbed.cu:5288-5485): the file is the reference's container —
+    msgpack, gzip-wrapped for .ingp, network config + "snapshot" {Trainer::serialize keys, version, mode, training_step, loss, aabb} — read
+    back here with the independent msgpack / gzip modules; a fresh Testbed of the same mode loads it and evaluates identically."""
+    import gzip
+
+    import msgpack
+
+    ngp = util.pkg()
+    img = util.test_image(96, 64, seed=5)
+    tb = ngp.Testbed(ngp.TestbedMode.Image)
+    tb.set_image(img)
+    tb.reload_network_from_json(IMAGE_CONFIG)
+    for _ in range(20):
+        tb.train(1 << 14)
+    path = tmp_path / ("image" + ext)
+    tb.save_snapshot(str(path))
+    raw = path.read_bytes()
+    if ext == ".ingp":
+        assert raw[:2] == b"\x1f\x8b"
+        raw = gzip.decompress(raw)
+    d = msgpack.unpackb(raw, raw=False)
+    s = d["snapshot"]
+    assert s["mode"] == "image" and s["version"] == 1 and s["params_type"] == "__half" and s["n_params"] == tb.n_params and s["training_step"] == 20
+    assert d["encoding"]["otype"] == IMAGE_CONFIG["encoding"]["otype"] and "optimizer" in d and "snapshot" not in d["network"]
+    assert np.frombuffer(s["params_binary"], dtype=np.float16).tobytes() == tb.get_params(inference=True).tobytes()
+    assert s["aabb"] == {"min": [0.0, 0.0, 0.0], "max": [1.0, 1.0, 1.0]} and abs(s["loss"] - tb.loss) < 1e-12
+    pts = np.random.default_rng(2).random((512, 2), dtype=np.float32)
+    want = tb.evaluate(pts)
+    tb2 = ngp.Testbed(ngp.TestbedMode.Image)
+    tb2.load_snapshot(str(path))                       # no image set: the frame size comes from the snapshot
+    assert tb2.training_step == 20 and tb2.n_params == tb.n_params and np.array_equal(tb2.evaluate(pts), want)
+    tb2.set_image(img)
+    tb2.train(1 << 14)                                  # and training resumes (Adam restarts: no optimizer state in the file)
+    assert tb2.training_step == 21 and np.isfinite(tb2.loss)
+    with pytest.raises(ngp.NgpError):
+        ngp.Testbed(ngp.TestbedMode.Sdf).load_snapshot(str(path))     # wrong mode
+    with pytest.raises(ngp.NgpError):
+        tb.save_snapshot(str(path), include_optimizer_state=True)
+
+    rng = np.random.default_rng(3)
+    p3 = rng.random((1 << 14, 3), dtype=np.float32)
+    sdf = ngp.Testbed(ngp.TestbedMode.Sdf)
+    sdf.override_sdf_training_data(p3, (np.linalg.norm(p3 - 0.5, axis=1) - 0.3).astype(np.float32))
+    sdf.reload_network_from_json(SDF_CONFIG)
+    for _ in range(10):
+        sdf.train(1 << 14)
+    spath = tmp_path / ("sdf" + ext)
+    sdf.save_snapshot(str(spath))
+    sdf2 = ngp.Testbed(ngp.TestbedMode.Sdf)
+    sdf2.load_file(str(spath))
+    q = rng.random((256, 3), dtype=np.float32)
+    assert np.array_equal(sdf2.evaluate(q), sdf.evaluate(q)) and sdf2.training_step == 10
+
+
 def test_module_handle_inference_and_backward(lib):
     """tcnn::cpp::Module::inference / backward (cpp_api.h:100-108) through the C handle against the oracle"""
     import torch
