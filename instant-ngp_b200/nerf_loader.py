@@ -11,7 +11,7 @@ Pinned against the reference's own `ngp::load_nerf`, compiled from /root/referen
 tests/loader_scenes.py (oracle/ref/ref_loader_harness.cu -> tests/golden/ref_loader.json, tests/test_nerf_loader.py): frame order
 and culling, scale / offset / up / render_aabb, per-image focal length, principal point, lens, transform and the stored pixel bytes.
 
-Not supported (raises): EXR images, depth supervision, per-pixel ray files, dynamic masks, rolling shutter, fisheye /
+Not supported (raises): EXR images, depth supervision, per-pixel ray files, rolling shutter, fisheye /
 f-theta / lat-long lenses, environment maps.  Several transform files with different `scale` / `offset` use the final values for
 every frame (the reference converts matrices on pool threads racing the parse of the next file, nerf_loader.cu:536-706)."""
 from __future__ import annotations
@@ -174,8 +174,6 @@ def load_metadata(json_paths) -> dict:
                 raise FileNotFoundError(f"Could not find image file '{path}'.")
             if "transform_matrix_start" in f or "transform_matrix_end" in f:
                 raise ValueError("per-frame start / end transforms (motion blur) are not supported")
-            if (path.parent / f"dynamic_mask_{path.stem}.png").exists():
-                raise ValueError("dynamic masks are not supported")
             if (path.parent / f"rays_{path.stem}.dat").exists() and j.get("enable_ray_loading", True):
                 raise ValueError("per-pixel ray files are not supported")
             if "driver_parameters" in f:
@@ -222,6 +220,15 @@ def read_image_bytes_rgba(path: Path, white_transparent=False, black_transparent
         r = a[..., 0].astype(np.float32) * np.float32(1.0 / 255.0)
         lin = np.where(r <= np.float32(0.04045), r / np.float32(12.92), np.power((r + np.float32(0.055)) / np.float32(1.055), np.float32(2.4)))
         img[..., 3] = (np.float32(255.0) * lin.astype(np.float32)).astype(np.uint8)
+    # dynamic masks (nerf_loader.cu:600-619): `dynamic_mask_<stem>.png` beside the frame; every pixel where the mask is not black becomes
+    # MASK_COLOR 0x00FF00FF (R 255, G 0, B 255, A 0) — what read_rgba reports as "masked away" (negative colour): the sample generator
+    # draws no ray through it (testbed_nerf.cu:732-736)
+    mask_path = path.parent / f"dynamic_mask_{path.stem}.png"
+    if mask_path.exists():
+        m = np.asarray(Image.open(mask_path).convert("RGBA"), dtype=np.uint8)
+        if m.shape != img.shape:
+            raise ValueError(f"Dynamic mask {mask_path} has wrong resolution.")
+        img[(m[..., :3] != 0).any(axis=-1)] = (255, 0, 255, 0)
     if white_transparent:
         img[(img[..., :3] == 255).all(axis=-1), 3] = 0
     if black_transparent:

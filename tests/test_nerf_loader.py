@@ -118,8 +118,8 @@ import loader_scenes  # noqa: E402
 import util  # noqa: E402
 
 GOLDEN = json.loads((Path(__file__).resolve().parent / "golden" / "ref_loader.json").read_text())
-SUPPORTED = ["basic", "opencv", "culled", "white", "mitsuba", "alpha_file", "two_files"]
-UNSUPPORTED = {"fisheye_rs": "lenses", "masked": "dynamic masks", "depth": "not supported"}
+SUPPORTED = ["basic", "opencv", "culled", "white", "mitsuba", "alpha_file", "two_files", "masked"]
+UNSUPPORTED = {"fisheye_rs": "lenses", "depth": "not supported"}
 
 
 @pytest.fixture(scope="module")
