@@ -271,6 +271,8 @@ typedef struct ngp_render_cfg {
 	                             host evaluates it (ngp_render_pixel_offset): it depends on the sample index only */
 	uint32_t lens_mode;       /* ngp_lens_mode of the render camera (Testbed::m_render_lens when m_render_with_lens_distortion) */
 	float lens_params[4];
+	uint32_t skips_per_tile;  /* tile kernel: voxel skips a ray may spend per tile iteration looking for its next sample before the tile goes ahead
+	                             without it (0 = the default, 4).  Schedule only: a ray's samples do not depend on it */
 	uint32_t render_mode;     /* ngp_render_mode */
 	float depth_scale;        /* Depth mode: 1 / dataset.scale (testbed_nerf.cu:2037) */
 	uint32_t math_mode;       /* ngp_math_mode of the march: NGP_MATH_DETERMINISTIC = ngp_detmath.h (bit-exact against the CPU oracle),

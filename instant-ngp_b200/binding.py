@@ -153,6 +153,7 @@ class RenderCfg(C.Structure):
         ("pixel_offset", C.c_float * 2),
         ("lens_mode", C.c_uint32),
         ("lens_params", C.c_float * 4),
+        ("skips_per_tile", C.c_uint32),
         ("render_mode", C.c_uint32),
         ("depth_scale", C.c_float),
         ("math_mode", C.c_uint32),

@@ -191,17 +191,42 @@ __global__ void __launch_bounds__(128) k_render_first_hit(const __grid_constant_
 		V3{cfg.render_aabb_max[0], cfg.render_aabb_max[1], cfg.render_aabb_max[2]}};
 	uint32_t pix;
 	V3 ro, rd, idir, pos;
-	float t = max_depth();
-	if (render_init_ray<M>(cfg, render_aabb, y0, n_pixels / (uint32_t)cfg.width, q, pix, ro, rd, idir, t)) render_march<M>(cfg, render_aabb, bitfield, ro, rd, idir, t, pos, 0xFFFFFFFFu);
+	float t = max_depth(), t_end = 0.0f;
+	if (render_init_ray<M>(cfg, render_aabb, y0, n_pixels / (uint32_t)cfg.width, q, pix, ro, rd, idir, t)) {
+		render_march<M>(cfg, render_aabb, bitfield, ro, rd, idir, t, pos, 0xFFFFFFFFu);
+		if (t < max_depth()) {
+			// The other long empty stretch of a ray is the way OUT: a ray that does not saturate walks from the last surface to the far side of
+			// the box (31 % of nerf/fox's pixels), again ~100 voxel skips with a couple of lanes of a tile's warp active.  Walk in from the far
+			// side instead, here, with the same skip logic on the reversed ray: everything beyond its first occupied cell is empty, so the
+			// tile kernel may end the ray at t_end.  Conservative (margin below); a ray's samples are unchanged.
+			float tmin, tmax;
+			aabb_ray_intersect(render_aabb, ro, rd, tmin, tmax);
+			const V3 far = ro + tmax * rd, back = V3{-rd.x, -rd.y, -rd.z}, iback = V3{-idir.x, -idir.y, -idir.z};
+			float tb = 1e-6f;
+			V3 pb;
+			render_march<M>(cfg, render_aabb, bitfield, far, back, iback, tb, pb, 0xFFFFFFFFu);
+			// margin: the occupied cell found from behind extends at most one cell of the coarsest cascade further along the ray, and a
+			// forward skip lands up to one step past a cell face — two cells + two steps
+			const float t_hit = tmax - tb;
+			t_end = tb >= max_depth() ? max_depth() : t_hit + scalbnf(1.0f / 64.0f, (int)cfg.max_cascade) + 2.0f * M::calc_dt(fmaxf(t_hit, 1e-3f), cfg.march);
+			if (!(t_end > t)) t_end = max_depth();
+		}
+	}
 	if (t >= max_depth()) {
 		// shade_kernel_nerf on an empty payload: transparent pixel (Cost mode: 0 steps, alpha 1), depth MAX_DEPTH
 		reinterpret_cast<float4*>(rgba_out)[pix] = make_float4(0.f, 0.f, 0.f, cfg.render_mode == NGP_RENDER_COST ? 1.f : 0.f);
 		depth_out[pix] = max_depth();
 	}
 	t_first[q] = t;
+	t_first[n_pixels + q] = t_end;
 }
 
-constexpr uint32_t RENDER_SKIPS_PER_TILE = 16;   // voxel skips a slot may spend looking for its next sample before the tile goes ahead without it
+// Voxel skips a slot may spend per tile iteration looking for its next sample before the tile goes ahead without it.  The skips of a gap
+// are serial per ray and a warp executes them with whatever lanes are in a gap at that moment (2 of 32 on nerf/fox): the smaller the budget,
+// the more iterations a gap is spread over and the more lanes of a warp share each round of skips — at the price of the gap rays' rows
+// sitting out more tiles.  Measured on nerf/fox 1920x1080 (profiles/r2/r2k_render_fox_skips.json), min. transmittance 0.01 / 1e-4:
+// 32: 29.5 / 47.8 ms, 16: 25.4 / 41.1, 8: 22.3 / 35.8, 4: 20.7 / 33.2, 2: 20.7 / 33.1.
+constexpr uint32_t RENDER_SKIPS_PER_TILE = 4;
 
 constexpr uint32_t RENDER_CTAS_PER_SM = 4;       // 45 KB of shared memory and 64 TMEM columns each; <= 128 registers per thread
 
@@ -246,7 +271,7 @@ __global__ void __launch_bounds__(TILE, RENDER_CTAS_PER_SM) k_render_nerf(
 	bool alive = false;
 	uint32_t pix = 0, n_steps = 0;
 	V3 ro{0, 0, 0}, rd{0, 0, 1}, idir{0, 0, 0};
-	float t = 0.0f, max_weight = 0.0f, depth = 0.0f;
+	float t = 0.0f, t_end = 0.0f, max_weight = 0.0f, depth = 0.0f;
 	float acc_r = 0.0f, acc_g = 0.0f, acc_b = 0.0f, acc_a = 0.0f;
 	bool queue_empty = false;
 	uint32_t local_steps = 0;
@@ -287,6 +312,7 @@ __global__ void __launch_bounds__(TILE, RENDER_CTAS_PER_SM) k_render_nerf(
 						float t_unused;
 						render_init_ray<M>(cfg, render_aabb, y0, (uint32_t)(y1 - y0), q, pix, ro, rd, idir, t_unused);
 						t = tf;
+						t_end = t_first[n_pixels + q];
 						acc_r = acc_g = acc_b = acc_a = 0.0f;
 						max_weight = 0.0f;
 						depth = max_depth();
@@ -302,7 +328,8 @@ __global__ void __launch_bounds__(TILE, RENDER_CTAS_PER_SM) k_render_nerf(
 		V3 pos{0.5f, 0.5f, 0.5f};
 		float dt = 0.0f;
 		if (alive) {
-			const uint32_t r = render_march<M>(cfg, render_aabb, bitfield, ro, rd, idir, t, pos, RENDER_SKIPS_PER_TILE);
+			// beyond t_end every cell is empty (k_render_first_hit walked in from the far side): the ray is over without walking out
+			const uint32_t r = t > t_end ? 2u : render_march<M>(cfg, render_aabb, bitfield, ro, rd, idir, t, pos, cfg.skips_per_tile ? cfg.skips_per_tile : RENDER_SKIPS_PER_TILE);
 			has_sample = r == 1u;
 			if (r == 2u) finish_ray();
 		}
@@ -577,7 +604,7 @@ void nerf_inference_rays(const ngp_nerf_desc& d, cudaStream_t stream, uint32_t n
 #undef NGPB_FWD_RAYS
 }
 
-size_t render_scratch_bytes(int32_t width, int32_t rows) { return 256 + sizeof(float) * (size_t)(width > 0 ? width : 0) * (size_t)(rows > 0 ? rows : 0); }
+size_t render_scratch_bytes(int32_t width, int32_t rows) { return 256 + 2 * sizeof(float) * (size_t)(width > 0 ? width : 0) * (size_t)(rows > 0 ? rows : 0); }
 
 template <uint32_t F, class M>
 static void launch_render(const NetDev& net, cudaStream_t stream, const ngp_render_cfg& cfg, int32_t y0, int32_t y1, const __half* params, const uint8_t* bitfield,

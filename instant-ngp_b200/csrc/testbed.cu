@@ -265,6 +265,7 @@ struct ngp_testbed {
 	uint32_t render_lens_mode = NGP_LENS_PERSPECTIVE;
 	float render_lens_params[4] = {0, 0, 0, 0};
 	uint32_t render_mode = NGP_RENDER_SHADE;     // m_render_mode (ERenderMode)
+	uint32_t render_skips_per_tile = 0;          // ngp_render_cfg.skips_per_tile (0 = default)
 	uint32_t render_math = NGP_MATH_REFERENCE;   // arithmetic of the render march (ngp_render_cfg.math_mode); `render_math` option
 
 	~ngp_testbed() {
@@ -1087,6 +1088,7 @@ int ngp_testbed_set_option(ngp_testbed* t, const char* name_c, double value) {
 		else if (n == "nerf.training.gen_lanes_per_ray") { const uint32_t g = (uint32_t)value; NGPB_CHECK(g <= 32 && (g & (g - 1)) == 0, "gen_lanes_per_ray must be 0 or a power of two up to 32"); tb_invalidate_prefetch(t); t->cfg.gen_lanes_per_ray = g; }
 		else if (n == "render_mode") { NGPB_CHECK(value == NGP_RENDER_SHADE || value == NGP_RENDER_AO || value == NGP_RENDER_POSITIONS || value == NGP_RENDER_DEPTH || value == NGP_RENDER_COST,
 			"render_mode: this build renders Shade, AO, Positions, Depth and Cost"); t->render_mode = (uint32_t)value; }
+		else if (n == "render_skips_per_tile") { NGPB_CHECK(value >= 0 && value <= 1024, "render_skips_per_tile out of range"); t->render_skips_per_tile = (uint32_t)value; }
 		else if (n == "render_math") { NGPB_CHECK(value == 0 || value == 1, "render_math must be 0 (deterministic) or 1 (reference)"); t->render_math = (uint32_t)value; }
 		else if (n == "nerf.training.full_inference") { NGPB_CHECK(value == 0 || value == 1 || value == 2, "full_inference: 0 ray-ordered, 1 every sample, 2 automatic"); tb_invalidate_prefetch(t); t->full_inference = (uint32_t)value; }
 		else if (n == "nerf.training.train_mode") { NGPB_CHECK(value == 0 || value == 1 || value == 2, "train_mode must be Nerf (0), Rfl (1) or RflRelax (2)"); c.train_mode = (uint32_t)value; }
@@ -1317,6 +1319,7 @@ static void tb_fill_render_cfg(ngp_testbed* t, ngp_render_cfg& rc, int32_t width
 	for (int k = 0; k < 4; ++k) rc.lens_params[k] = t->render_with_lens_distortion ? t->render_lens_params[k] : 0.0f;
 	rc.math_mode = t->render_math;
 	rc.render_mode = t->render_mode;
+	rc.skips_per_tile = t->render_skips_per_tile;
 	rc.depth_scale = 1.0f / t->scene_scale;   // testbed_nerf.cu:2037
 }
 
