@@ -526,7 +526,16 @@ def main() -> None:
                     "frac": (achieved / pk["hbm_gbs"]) if achieved else None, "traffic": K_NERF_TRAIN_DRAM_BYTES[scene], "peak_source": pk["source"], "ms_per_launch": fb_ms,
                     "algorithmic_bytes_per_launch": alg_bytes,
                     "traffic_source": K_NERF_TRAIN_DRAM_SOURCE[scene] + " (per launch)",
-                    "note": "the 26 MB fp16 table and its gradient table are L2-resident on B200: the kernel is bound by L2 gather/reduction traffic and latency, DRAM traffic is an eighth of the algorithmic bytes"}
+                    # what binds the kernel: the SM's load/store path takes SCATTERED accesses (every lane another 128-byte line, L2 hits) at 1.01 cycles
+                    # per lane for gathers and 1.50 for fp16x2 reductions, whatever the width (4 or 8 bytes) and the occupancy — measured on this GPU
+                    # with tools/microbench/lsu_scatter.cu (profiles/r2/r2l_lsu_scatter.jsonl).  Per sample: 16 levels x 8 corners gathered and reduced,
+                    # x-neighbour pairs sharing one access when adjacent and aligned (about half of them): ~96 + ~96 lane accesses.
+                    "lsu_floor": {"gather_cycles_per_lane": 1.01, "red_cycles_per_lane": 1.50, "lane_accesses_per_sample": {"gather": 96, "red": 96}, "sm_count": 148,
+                                  "sm_mhz": sm_mhz, "source": "profiles/r2/r2l_lsu_scatter.jsonl",
+                                  "floor_ms": (96 * 1.01 + 96 * 1.50) * BATCH / 148 / (sm_mhz * 1e3),
+                                  "frac": ((96 * 1.01 + 96 * 1.50) * BATCH / 148 / (sm_mhz * 1e3)) / fb_ms if fb_ms > 0 else None,
+                                  "mlp_phase_ms": 0.097, "mlp_phase_source": "profiles/r2/r2h_mlp_phase.json (tensor pipe 11.5 % while it runs)"},
+                    "note": "the 26 MB fp16 table and its gradient table are L2-resident on B200: DRAM traffic is an eighth of the algorithmic bytes; the kernel runs at the SM load/store path's scattered-access rate (lsu_floor) plus the MLP phase"}
         # second kernel of the step by time: the sample generator.  Algorithmic bytes: the 28-byte coordinate record of every generated sample
         # (SURVEY 8d "1 march step": the bit test itself is L1/L2 resident); it is latency bound (a serial log/exp recurrence per ray), which
         # is what the fraction says.
