@@ -200,6 +200,11 @@ int ngp_nerf_forward_backward(const ngp_nerf_desc* d, void* stream, uint32_t n, 
 int ngp_profile_mlp_phase(const ngp_nerf_desc* d, void* stream, uint32_t n, const float* coords, const void* params_fp16, const void* dL_dout_fp16,
 	void* grads_fp16, float* mlp_scratch_f32);
 
+/* A/B switch (tests, profiling) of ngp_nerf_forward_backward's run aggregation: consecutive samples of a ray that fall into the same cell of a coarse
+ * level are summed inside the warp and issue one set of reductions.  mode 0 = off, 1 = the coarse half of the levels (default), 2 = every level.
+ * Process-wide; the result differs only by fp16 summation order. */
+void ngp_set_scatter_aggregation(int mode);
+
 /* Hash-grid encoding alone (tests, image/SDF style use): out n x (L*F) halves, sample-contiguous. ≙ kernel_grid (grid.h:48-212). */
 int ngp_grid_encode(const ngp_grid_desc* g, void* stream, uint32_t n, const float* positions, uint32_t pos_stride,
 	const void* grid_fp16, void* out_fp16);

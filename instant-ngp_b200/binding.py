@@ -203,6 +203,7 @@ PROTOTYPES = {
     "ngp_testbed_set_option": (C.c_int, [vp, cp, C.c_double]),
     "ngp_testbed_get_option": (C.c_double, [vp, cp]),
     "ngp_testbed_train": (C.c_int, [vp, u32]),
+    "ngp_set_scatter_aggregation": (None, [C.c_int]),
     "ngp_profile_mlp_phase": (C.c_int, [P(NerfDesc), vp, u32, vp, vp, vp, vp, vp]),
     "ngp_testbed_set_dp": (C.c_int, [vp, u32, u32]),
     "ngp_dp_unique_id_bytes": (C.c_size_t, []),

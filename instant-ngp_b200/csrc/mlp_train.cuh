@@ -206,8 +206,8 @@ __device__ __forceinline__ void grid_gather_half_impl(const NET& net, const __ha
 		cell.corners(lv, idx);
 		if constexpr (F == 2) {
 			__half2 v[NC];
-			// The SM's load/store unit takes scattered accesses at about one lane per clock (B300_MICROARCH.md: REDG 1.29 cyc/lane
-			// spread): 128 gathers + 128 reductions per sample are ~0.31 ms of this kernel's 0.39.  The two x-neighbours of a corner
+			// The SM's load/store unit takes scattered accesses at 1.01 cycles per lane for gathers and 1.50 for reductions (measured on the
+			// B200, tools/microbench/lsu_scatter.cu): 128 + 128 of them per sample would be 0.29 ms per 2^18 samples.  The two x-neighbours of a corner
 			// pair are adjacent entries whenever the first index is even (always on dense levels up to the wrap, and on hashed levels
 			// because the x prime is 1): one 8-byte access then serves both.
 #pragma unroll
@@ -261,10 +261,15 @@ __device__ __forceinline__ void grid_gather_half_nd(const NET& net, const __half
 
 // scatter dL/d(encoding) of HALF of the levels of one sample into the fp16 gradient table
 // (≙ kernel_grid_backward, grid.h:214-320: fp16 weight x fp16 gradient, red.global.add.f16x2 per corner).
-template <uint32_t F, uint32_t D, uint32_t half, typename NET>
+// AGG (NeRF training only): the compacted samples of one ray sit in consecutive rows, i.e. consecutive lanes, and at the coarse levels many of
+// them fall into the same cell.  Each run of equal cells in the warp is summed with a segmented shuffle scan and its first lane issues the
+// reductions: a reduction costs 1.5 load/store-unit cycles per lane (profiles/r2/r2l_lsu_scatter.jsonl), a shuffle + HADD2 a fraction of that.
+template <uint32_t F, uint32_t D, uint32_t half, bool AGG, typename NET>
 __device__ __forceinline__ void grid_scatter_half_impl(const NET& net, __half* __restrict__ grid_grad, const float (&x)[D], const __half2 (&g)[8]) {
+	static_assert(F == 2 || F == 4, "2 or 4 features per level");
 	constexpr uint32_t LEVELS_PER_HALF = (ENC_WIDTH / F) / 2;
 	constexpr uint32_t NC = 1u << D;
+	constexpr uint32_t H = F / 2;  // half2 words per table entry
 	// fully unrolled: with a partial unroll g[ll] is indexed dynamically and the gradient array lands in local memory — the LDL
 	// behind every corner's HMUL2 was 9 % of the training kernel's stall samples (ncu r1c)
 #pragma unroll
@@ -274,66 +279,76 @@ __device__ __forceinline__ void grid_scatter_half_impl(const NET& net, __half* _
 		__half2* lgrad = reinterpret_cast<__half2*>(grid_grad + (size_t)lv.offset * F);
 		uint32_t cidx[NC];
 		cell.corners(lv, cidx);
-		if constexpr (F == 2) {
-			// pairs of x-neighbours as one 8-byte vector reduction where they are adjacent and aligned (see grid_gather_half_nd)
-#pragma unroll
-			for (uint32_t c = 0; c < NC; c += 2) {
-				const __half2 v0 = __hmul2(__float2half2_rn(cell.weight(c)), g[ll]), v1 = __hmul2(__float2half2_rn(cell.weight(c + 1)), g[ll]);
-				if (((cidx[c] & 1u) == 0u) && cidx[c + 1] == cidx[c] + 1u) {
-					asm volatile("red.relaxed.gpu.global.add.noftz.v2.f16x2 [%0], {%1, %2};" ::"l"(lgrad + cidx[c]), "r"(*reinterpret_cast<const uint32_t*>(&v0)),
-								 "r"(*reinterpret_cast<const uint32_t*>(&v1))
-								 : "memory");
-				} else {
-					asm volatile("red.relaxed.gpu.global.add.noftz.f16x2 [%0], %1;" ::"l"(lgrad + cidx[c]), "r"(*reinterpret_cast<const uint32_t*>(&v0)) : "memory");
-					asm volatile("red.relaxed.gpu.global.add.noftz.f16x2 [%0], %1;" ::"l"(lgrad + cidx[c + 1]), "r"(*reinterpret_cast<const uint32_t*>(&v1)) : "memory");
-				}
-			}
-			continue;
-		}
-		if constexpr (F == 4) {
-#pragma unroll
-			for (uint32_t c = 0; c < NC; c += 2) {
-				const __half2 w0 = __float2half2_rn(cell.weight(c)), w1 = __float2half2_rn(cell.weight(c + 1));
-				const __half2 a0 = __hmul2(w0, g[ll * 2 + 0]), a1 = __hmul2(w0, g[ll * 2 + 1]), b0 = __hmul2(w1, g[ll * 2 + 0]), b1 = __hmul2(w1, g[ll * 2 + 1]);
-				if (((cidx[c] & 1u) == 0u) && cidx[c + 1] == cidx[c] + 1u) {
-					asm volatile("red.relaxed.gpu.global.add.noftz.v4.f16x2 [%0], {%1, %2, %3, %4};" ::"l"(lgrad + (size_t)cidx[c] * 2),
-								 "r"(*reinterpret_cast<const uint32_t*>(&a0)), "r"(*reinterpret_cast<const uint32_t*>(&a1)), "r"(*reinterpret_cast<const uint32_t*>(&b0)),
-								 "r"(*reinterpret_cast<const uint32_t*>(&b1))
-								 : "memory");
-				} else {
-					asm volatile("red.relaxed.gpu.global.add.noftz.v2.f16x2 [%0], {%1, %2};" ::"l"(lgrad + (size_t)cidx[c] * 2), "r"(*reinterpret_cast<const uint32_t*>(&a0)),
-								 "r"(*reinterpret_cast<const uint32_t*>(&a1))
-								 : "memory");
-					asm volatile("red.relaxed.gpu.global.add.noftz.v2.f16x2 [%0], {%1, %2};" ::"l"(lgrad + (size_t)cidx[c + 1] * 2), "r"(*reinterpret_cast<const uint32_t*>(&b0)),
-								 "r"(*reinterpret_cast<const uint32_t*>(&b1))
-								 : "memory");
-				}
-			}
-			continue;
-		}
+		__half2 v[NC][H];
 #pragma unroll
 		for (uint32_t c = 0; c < NC; ++c) {
-			const uint32_t idx = cidx[c];
 			const __half2 wh = __float2half2_rn(cell.weight(c));
-			// fire-and-forget reductions.  NOT atomicAdd(__half2*): on a generic pointer that compiles to ATOM + predicate + retry
-			// branch (a full L2 round trip per corner, serialised per thread: 59 % of all stall samples, profiles/r1_kernels.md).
-			if constexpr (F == 2) {
-				const __half2 v = __hmul2(wh, g[ll]);
-				asm volatile("red.relaxed.gpu.global.add.noftz.f16x2 [%0], %1;" ::"l"(lgrad + idx), "r"(*reinterpret_cast<const uint32_t*>(&v)) : "memory");
-			} else {
-				const __half2 v0 = __hmul2(wh, g[ll * 2 + 0]), v1 = __hmul2(wh, g[ll * 2 + 1]);
-				asm volatile("red.relaxed.gpu.global.add.noftz.v2.f16x2 [%0], {%1, %2};" ::"l"(lgrad + (size_t)idx * 2), "r"(*reinterpret_cast<const uint32_t*>(&v0)),
-							 "r"(*reinterpret_cast<const uint32_t*>(&v1))
-							 : "memory");
+#pragma unroll
+			for (uint32_t h = 0; h < H; ++h) v[c][h] = __hmul2(wh, g[ll * H + h]);
+		}
+		bool issue = true;
+		if constexpr (AGG) {
+			static_assert(D == 3, "run aggregation is written for 3-D cells");
+			const uint32_t lane = threadIdx.x & 31u;
+			const unsigned long long key = (unsigned long long)cell.g[0] | ((unsigned long long)cell.g[1] << 21) | ((unsigned long long)cell.g[2] << 42);
+			const uint32_t peers = __match_any_sync(0xFFFFFFFFu, key);
+			const uint32_t lo = (uint32_t)__ffs((int)peers) - 1u, hi = 31u - (uint32_t)__clz((int)peers);
+			// only contiguous runs are merged (lanes lo..hi all in `peers`); anything else keeps its own reductions
+			const bool run = hi > lo && peers == ((0xFFFFFFFFu >> (31u - hi)) & (0xFFFFFFFFu << lo));
+			if (__any_sync(0xFFFFFFFFu, run)) {
+				// segmented suffix sum: after step d, lane l holds the sum over lanes l .. min(l + 2d - 1, hi)
+#pragma unroll
+				for (uint32_t d = 1; d < 32u; d <<= 1) {
+					const bool take = run && lane + d <= hi;
+#pragma unroll
+					for (uint32_t c = 0; c < NC; ++c) {
+#pragma unroll
+						for (uint32_t h = 0; h < H; ++h) {
+							const __half2 o = __shfl_down_sync(0xFFFFFFFFu, v[c][h], d);
+							if (take) v[c][h] = __hadd2(v[c][h], o);
+						}
+					}
+				}
+				issue = !run || lane == lo;
+			}
+		}
+		if (!issue) continue;
+		// fire-and-forget reductions (NOT atomicAdd(__half2*): on a generic pointer that compiles to ATOM + predicate + retry branch, a full L2
+		// round trip per corner — 59 % of all stall samples in profiles/r1_kernels.md); pairs of x-neighbours as one vector reduction where
+		// they are adjacent and aligned (see grid_gather_half_impl)
+		if constexpr (D == 3 || D == 2) {
+#pragma unroll
+			for (uint32_t c = 0; c < NC; c += 2) {
+				const bool paired = ((cidx[c] & 1u) == 0u) && cidx[c + 1] == cidx[c] + 1u;
+				if constexpr (F == 2) {
+					const uint32_t v0 = *reinterpret_cast<const uint32_t*>(&v[c][0]), v1 = *reinterpret_cast<const uint32_t*>(&v[c + 1][0]);
+					if (paired) {
+						asm volatile("red.relaxed.gpu.global.add.noftz.v2.f16x2 [%0], {%1, %2};" ::"l"(lgrad + cidx[c]), "r"(v0), "r"(v1) : "memory");
+					} else {
+						asm volatile("red.relaxed.gpu.global.add.noftz.f16x2 [%0], %1;" ::"l"(lgrad + cidx[c]), "r"(v0) : "memory");
+						asm volatile("red.relaxed.gpu.global.add.noftz.f16x2 [%0], %1;" ::"l"(lgrad + cidx[c + 1]), "r"(v1) : "memory");
+					}
+				} else {
+					const uint32_t a0 = *reinterpret_cast<const uint32_t*>(&v[c][0]), a1 = *reinterpret_cast<const uint32_t*>(&v[c][1]);
+					const uint32_t b0 = *reinterpret_cast<const uint32_t*>(&v[c + 1][0]), b1 = *reinterpret_cast<const uint32_t*>(&v[c + 1][1]);
+					if (paired) {
+						asm volatile("red.relaxed.gpu.global.add.noftz.v4.f16x2 [%0], {%1, %2, %3, %4};" ::"l"(lgrad + (size_t)cidx[c] * 2), "r"(a0), "r"(a1), "r"(b0), "r"(b1) : "memory");
+					} else {
+						asm volatile("red.relaxed.gpu.global.add.noftz.v2.f16x2 [%0], {%1, %2};" ::"l"(lgrad + (size_t)cidx[c] * 2), "r"(a0), "r"(a1) : "memory");
+						asm volatile("red.relaxed.gpu.global.add.noftz.v2.f16x2 [%0], {%1, %2};" ::"l"(lgrad + (size_t)cidx[c + 1] * 2), "r"(b0), "r"(b1) : "memory");
+					}
+				}
 			}
 		}
 	}
 }
 
-template <uint32_t F, uint32_t D, typename NET>
+template <uint32_t F, uint32_t D, uint32_t AGG = 0, typename NET>
 __device__ __forceinline__ void grid_scatter_half_nd(const NET& net, __half* __restrict__ grid_grad, uint32_t half, const float (&x)[D], const __half2 (&g)[8]) {
-	if (half == 0) grid_scatter_half_impl<F, D, 0>(net, grid_grad, x, g);
-	else grid_scatter_half_impl<F, D, 1>(net, grid_grad, x, g);
+	// `half` is warp-uniform at every call site (threads 0..127 / 128..255 of the CTA), as the warp collectives of AGG require.
+	// AGG: 0 = off, 1 = the coarse half of the levels, 2 = every level
+	if (half == 0) grid_scatter_half_impl<F, D, 0, (AGG >= 1)>(net, grid_grad, x, g);
+	else grid_scatter_half_impl<F, D, 1, (AGG >= 2)>(net, grid_grad, x, g);
 }
 
 template <uint32_t F>
@@ -341,10 +356,10 @@ __device__ __forceinline__ void grid_gather_half(const NetDev& net, const __half
 	const float p[3] = {x, y, z};
 	grid_gather_half_nd<F, 3>(net, grid, half, p, enc);
 }
-template <uint32_t F>
+template <uint32_t F, uint32_t AGG = 0>
 __device__ __forceinline__ void grid_scatter_half(const NetDev& net, __half* __restrict__ grid_grad, uint32_t half, float x, float y, float z, const __half2 (&g)[8]) {
 	const float p[3] = {x, y, z};
-	grid_scatter_half_nd<F, 3>(net, grid_grad, half, p, g);
+	grid_scatter_half_nd<F, 3, AGG>(net, grid_grad, half, p, g);
 }
 
 }  // namespace ngpb

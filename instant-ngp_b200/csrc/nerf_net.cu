@@ -8,6 +8,7 @@
 //
 // One CTA = 128 threads = one 128-sample tile = one UMMA M=128 accumulator; thread t owns sample t and TMEM lane t.
 // All MLP weights stay resident in shared memory in the chunk-major operand layout for the kernel's lifetime.
+#include <atomic>
 #include "nerf_net.cuh"
 #include "mlp_train.cuh"
 
@@ -186,7 +187,7 @@ __host__ __device__ inline uint32_t train_tmem_cols(uint32_t nhd, uint32_t nhr) 
 
 // MLP_ONLY (profiling, ngp_profile_mlp_phase): the same tile loop with the hash-grid gather replaced by a register pattern and the
 // scatter dropped, i.e. the 15 tensor-core groups of a tile and their epilogues alone — the "MLP phase" SURVEY §8d asks to see separately.
-template <uint32_t F, uint32_t TMEM_COLS, bool MLP_ONLY = false>
+template <uint32_t F, uint32_t TMEM_COLS, bool MLP_ONLY = false, uint32_t AGG = 1>
 __global__ void __launch_bounds__(TRAIN_THREADS, 2) k_nerf_train(
 	const __grid_constant__ NetDev net, const uint32_t n, const float* __restrict__ coords, const __half* __restrict__ params,
 	const __half* __restrict__ dL_dout, __half* __restrict__ grads, float* __restrict__ mlp_grads_f32, __half* __restrict__ out
@@ -300,7 +301,7 @@ __global__ void __launch_bounds__(TRAIN_THREADS, 2) k_nerf_train(
 				// keep the gradient live without touching the table
 				if (__hlt(__low2half(g[0]), __float2half_rn(-60000.0f))) grid_grad[0] = __low2half(g[1]);
 			} else {
-				grid_scatter_half<F>(net, grid_grad, half, x, y, z, g);
+				grid_scatter_half<F, AGG>(net, grid_grad, half, x, y, z, g);
 			}
 		}
 	}
@@ -467,15 +468,20 @@ void grid_encode(const ngp_grid_desc& g, cudaStream_t stream, uint32_t n, const 
 }
 
 
+// A/B switch of the training kernel's run aggregation (mlp_train.cuh, grid_scatter_half_impl<AGG>); on by default
+static std::atomic<int> g_scatter_aggregation{1};
+void set_scatter_aggregation(int mode) { g_scatter_aggregation.store(mode < 0 ? 0 : mode > 2 ? 2 : mode, std::memory_order_relaxed); }
+
 template <uint32_t F, uint32_t TMEM_COLS, bool MLP_ONLY = false>
 static void launch_train(const NetDev& net, cudaStream_t stream, uint32_t n, const float* coords, const __half* params, const __half* dL_dout,
 	__half* grads, float* mlp_grads_f32, __half* out) {
 	const TrainSmem L = train_smem_layout(net.n_hidden_density, net.n_hidden_rgb);
-	auto kern = k_nerf_train<F, TMEM_COLS, MLP_ONLY>;
-	static bool attr_set = false;
-	if (!attr_set) {
+	const int agg = MLP_ONLY ? 1 : g_scatter_aggregation.load(std::memory_order_relaxed);
+	auto kern = agg == 1 ? k_nerf_train<F, TMEM_COLS, MLP_ONLY, 1> : agg == 2 ? k_nerf_train<F, TMEM_COLS, MLP_ONLY, 2> : k_nerf_train<F, TMEM_COLS, MLP_ONLY, 0>;
+	static bool attr_set[3] = {false, false, false};
+	if (!attr_set[agg]) {
 		NGPB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-		attr_set = true;
+		attr_set[agg] = true;
 	}
 	NGPB_CHECK(L.total <= 227 * 1024, "MLP too deep for the training kernel's shared memory budget");
 	const uint32_t n_tiles = n / TILE;

@@ -30,6 +30,7 @@ void nerf_density(const ngp_nerf_desc& d, cudaStream_t stream, uint32_t n, const
 void grid_encode(const ngp_grid_desc& g, cudaStream_t stream, uint32_t n, const float* positions, uint32_t pos_stride, const __half* grid, __half* out);
 void nerf_forward_backward(const ngp_nerf_desc& d, cudaStream_t stream, uint32_t n, const float* coords, const __half* params, const __half* dL_dout,
 	__half* grads, float* mlp_grads_f32, __half* out);
+void set_scatter_aggregation(int mode);
 void profile_mlp_phase(const ngp_nerf_desc& d, cudaStream_t stream, uint32_t n, const float* coords, const __half* params, const __half* dL_dout, __half* grads,
 	float* mlp_grads_f32);
 void optimizer_step(const ngp_nerf_desc& d, cudaStream_t stream, const ngp_adam_cfg& cfg, float* params_fp32, __half* params_fp16, __half* params_ema,
@@ -819,6 +820,7 @@ int ngp_nerf_forward_backward(const ngp_nerf_desc* d, void* stream, uint32_t n, 
 		NGPB_CUDA_CHECK(cudaFreeAsync(tmp, (cudaStream_t)stream));
 	});
 }
+void ngp_set_scatter_aggregation(int mode) { set_scatter_aggregation(mode); }
 int ngp_profile_mlp_phase(const ngp_nerf_desc* d, void* stream, uint32_t n, const float* coords, const void* params, const void* dL_dout, void* grads, float* mlp_scratch_f32) {
 	NGPB_TRY(require_device(); profile_mlp_phase(*d, (cudaStream_t)stream, n, coords, (const __half*)params, (const __half*)dL_dout, (__half*)grads, mlp_scratch_f32));
 }

@@ -170,8 +170,9 @@ def test_backward_accumulates_and_is_linear_in_dloss(lib):
     assert np.abs(b - 2 * a).max() <= 2e-2 * np.abs(b).max()
 
 
-def test_full_batch_gradients_match_the_fp32_cpu_port_level_by_level(lib):
-    """The training batch itself (2^18 samples): hash-grid and MLP gradients against the fp32 CPU port of the network (oracle/ngp_net_cpu.c,
+@pytest.mark.parametrize("aggregate", [1, 2, 0])
+def test_full_batch_gradients_match_the_fp32_cpu_port_level_by_level(lib, aggregate):
+    """(Both with the warp-level run aggregation of the scatter and without it: ngp_set_scatter_aggregation.)  The training batch itself (2^18 samples): hash-grid and MLP gradients against the fp32 CPU port of the network (oracle/ngp_net_cpu.c,
     OpenMP; checked against the fp16-exact numpy oracle in tests/test_cpu_baseline.py), LEVEL BY LEVEL.  The samples are laid out like a
     training batch — runs of consecutive samples along rays — so the coarse levels see what they see in training: thousands of fp16
     `red.add` operations into the same few entries at loss scale 128.  What is being checked is that the fp16 accumulation in arbitrary
@@ -201,8 +202,12 @@ def test_full_batch_gradients_match_the_fp32_cpu_port_level_by_level(lib):
 
     t_p, t_c, t_dl = dev(params), dev(coords), dev(dl)
     t_g = torch.zeros(d.n_params, dtype=torch.float16, device="cuda")
-    assert lib.ngp_nerf_forward_backward(C.byref(d), stream(), n, t_c.data_ptr(), t_p.data_ptr(), t_dl.data_ptr(), t_g.data_ptr(), None) == 0, lib.ngp_last_error()
-    torch.cuda.synchronize()
+    lib.ngp_set_scatter_aggregation(int(aggregate))
+    try:
+        assert lib.ngp_nerf_forward_backward(C.byref(d), stream(), n, t_c.data_ptr(), t_p.data_ptr(), t_dl.data_ptr(), t_g.data_ptr(), None) == 0, lib.ngp_last_error()
+        torch.cuda.synchronize()
+    finally:
+        lib.ngp_set_scatter_aggregation(1)
     g = t_g.cpu().numpy().astype(np.float64)
     assert np.isfinite(g).all(), "fp16 gradient accumulation overflowed"
     _, want = net_cpu.NetCpu(L, params).forward_backward(coords, dl)

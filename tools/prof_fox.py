@@ -28,11 +28,15 @@ def main():
     ap.add_argument("--render", type=int, default=5)
     ap.add_argument("--scene", default="fox", choices=["fox", "ball"])
     ap.add_argument("--option", action="append", default=[])
+    ap.add_argument("--scatter-aggregation", type=int, default=1)
     args = ap.parse_args()
     import ref_app as R
 
     impl = R.B200(False, "Nerf")
     tb = impl.tb
+    if args.scatter_aggregation != 1:
+        from importlib import import_module
+        import_module("instant-ngp_b200.binding").lib().ngp_set_scatter_aggregation(args.scatter_aggregation)
     if args.scene == "fox":
         split, _ = R.fox_split()
         impl.load_transforms(split["train"])
@@ -56,7 +60,8 @@ def main():
     tb.sync()
     t3 = time.perf_counter()
     rec = {"scene": args.scene, "enc": args.enc, "ms_per_step_first": (t1 - t0) / max(args.steps, 1) * 1e3, "ms_per_step_steady": (t3 - t2) / tail * 1e3,
-           "counters": tb.counters(), "options": args.option}
+           "counters": tb.counters(), "options": args.option,
+           "scatter_aggregation": args.scatter_aggregation}
     tb.set_profiling(True)
     for _ in range(args.profile_steps):
         tb.train(R.BATCH)
