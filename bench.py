@@ -77,8 +77,8 @@ def default_scene() -> str:
 # ---------------------------------------------------------------------------------------------------------------------
 # dram__bytes_read.sum + dram__bytes_write.sum of one k_nerf_train launch (ncu --set full): nerf/fox profiles/r2/r2f_train_fox_ncu.md,
 # the synthetic scene profiles/r1e_end_of_round.md
-K_NERF_TRAIN_DRAM_BYTES = {"fox": 58.57e6 + 0.29e6, "ball": 54.52e6 + 0.20e6}
-K_NERF_TRAIN_DRAM_SOURCE = {"fox": "profiles/r2/r2f_train_fox_ncu.md", "ball": "profiles/r1e_end_of_round.md"}
+K_NERF_TRAIN_DRAM_BYTES = {"fox": 61.01e6 + 0.82e6, "ball": 54.52e6 + 0.20e6}
+K_NERF_TRAIN_DRAM_SOURCE = {"fox": "profiles/r2/r2n_train_fox_ncu.md", "ball": "profiles/r1e_end_of_round.md"}
 
 
 class ClockSampler:
@@ -528,12 +528,13 @@ def main() -> None:
                     "traffic_source": K_NERF_TRAIN_DRAM_SOURCE[scene] + " (per launch)",
                     # what binds the kernel: the SM's load/store path takes SCATTERED accesses (every lane another 128-byte line, L2 hits) at 1.01 cycles
                     # per lane for gathers and 1.50 for fp16x2 reductions, whatever the width (4 or 8 bytes) and the occupancy — measured on this GPU
-                    # with tools/microbench/lsu_scatter.cu (profiles/r2/r2l_lsu_scatter.jsonl).  Per sample: 16 levels x 8 corners gathered and reduced,
-                    # x-neighbour pairs sharing one access when adjacent and aligned (about half of them): ~96 + ~96 lane accesses.
-                    "lsu_floor": {"gather_cycles_per_lane": 1.01, "red_cycles_per_lane": 1.50, "lane_accesses_per_sample": {"gather": 96, "red": 96}, "sm_count": 148,
-                                  "sm_mhz": sm_mhz, "source": "profiles/r2/r2l_lsu_scatter.jsonl",
-                                  "floor_ms": (96 * 1.01 + 96 * 1.50) * BATCH / 148 / (sm_mhz * 1e3),
-                                  "frac": ((96 * 1.01 + 96 * 1.50) * BATCH / 148 / (sm_mhz * 1e3)) / fb_ms if fb_ms > 0 else None,
+                    # with tools/microbench/lsu_scatter.cu (profiles/r2/r2l_lsu_scatter.jsonl).  Lane accesses per sample from ncu's L1 sector counts
+                    # on nerf/fox (profiles/r2/r2n_train_fox_ncu.md): 16 levels x 8 corners, x-neighbour pairs sharing one access when adjacent and
+                    # aligned, lanes of a warp reading the same sector counted once, runs of samples in one cell reduced once (mlp_train.cuh AGG).
+                    "lsu_floor": {"gather_cycles_per_lane": 1.01, "red_cycles_per_lane": 1.50, "lane_accesses_per_sample": {"gather": 77.6, "red": 79.9}, "sm_count": 148,
+                                  "sm_mhz": sm_mhz, "source": "profiles/r2/r2l_lsu_scatter.jsonl, profiles/r2/r2n_train_fox_ncu.md",
+                                  "floor_ms": (77.6 * 1.01 + 79.9 * 1.50) * BATCH / 148 / (sm_mhz * 1e3),
+                                  "frac": ((77.6 * 1.01 + 79.9 * 1.50) * BATCH / 148 / (sm_mhz * 1e3)) / fb_ms if fb_ms > 0 else None,
                                   "mlp_phase_ms": 0.097, "mlp_phase_source": "profiles/r2/r2h_mlp_phase.json (tensor pipe 11.5 % while it runs)"},
                     "note": "the 26 MB fp16 table and its gradient table are L2-resident on B200: DRAM traffic is an eighth of the algorithmic bytes; the kernel runs at the SM load/store path's scattered-access rate (lsu_floor) plus the MLP phase"}
         # second kernel of the step by time: the sample generator.  Algorithmic bytes: the 28-byte coordinate record of every generated sample
