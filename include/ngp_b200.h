@@ -126,6 +126,10 @@ typedef struct ngp_nerf_train_cfg {
 	uint32_t math_mode;  /* ngp_math_mode of the sample generator's march */
 	uint32_t gen_lanes_per_ray; /* sample generator: lanes of a warp that march one ray together (1, 2, 4, 8, 16 or 32); 0 = chosen from the
 	                               batch size.  Changes the schedule only: every ray's samples are the same for every value */
+	uint32_t gen_walk_empty;    /* sample generator: empty cells the lane that met one crosses on its own before the group's next round (>= 1);
+	                               0 = library default.  Schedule only */
+	uint32_t gen_speculation;   /* sample generator: samples a group speculates on in the first round after a skip (1 .. lanes per ray; doubles
+	                               after every fully occupied round); 0 = library default.  Schedule only */
 } ngp_nerf_train_cfg;
 
 /* Counters written by the training sample generator / loss kernel (NerfCounters, testbed.h). */

@@ -108,6 +108,8 @@ class NerfTrainCfg(C.Structure):
         ("ray_stride", C.c_uint32),
         ("math_mode", C.c_uint32),
         ("gen_lanes_per_ray", C.c_uint32),
+        ("gen_walk_empty", C.c_uint32),
+        ("gen_speculation", C.c_uint32),
     ]
 
 

@@ -42,14 +42,21 @@ __host__ __device__ constexpr uint32_t gen_smem_bytes(uint32_t G) { return (gen_
 // the warp must call this together (groups whose ray is finished pass j >= j_end).  Equivalent, value for value, to
 //     while (aabb.contains(pos = o + t d) && j < j_end) { dt = calc_dt(t); mip = mip_from_dt(dt, pos);
 //         if (occupied(pos, mip)) { emit(j, t, dt, pos); ++j; t += dt; } else t = advance_to_next_voxel(t, pos, d, idir, mip); }
+// schedule knobs of march_group (ngp_nerf_train_cfg.gen_walk_empty / gen_speculation override them; every ray's samples are the same for any value)
+// Measured on nerf/fox, 16 lanes per ray (profiles/r2/r2o_generator_knobs.jsonl): walk 1 / speculation 1: 0.361 ms, 8 / 4: 0.332, 64 / 4: 0.382,
+// 1 / 16: 0.681 (the recurrence's latency, not the round's instruction count, is what a deeper speculation pays); with one lane per ray a
+// walk only makes the warp's other rays wait (synthetic scene 0.56 -> 1.09 ms at 64).
+__host__ __device__ constexpr uint32_t gen_walk_empty_default(uint32_t G) { return G >= 8 ? 8u : 1u; }    // cells the lane that found an empty cell crosses before the group's next round
+__host__ __device__ constexpr uint32_t gen_speculation_default(uint32_t G) { return G >= 8 ? 4u : 1u; }   // samples speculated in the first round after a skip (doubles after every fully occupied round)
+
 template <class P, uint32_t G, class Emit>
 __device__ __forceinline__ uint32_t march_group(const typename P::Ctx& pc, const Aabb& aabb, const uint32_t max_cascade, const uint8_t* __restrict__ bitfield,
-	const V3 ro, const V3 rd, const V3 idir, float t, uint32_t j, const uint32_t j_end, Emit emit) {
+	const V3 ro, const V3 rd, const V3 idir, float t, uint32_t j, const uint32_t j_end, const uint32_t walk_empty, const uint32_t s_after_skip, Emit emit) {
 	const uint32_t lane = threadIdx.x & 31u;
 	const uint32_t g = lane & (G - 1u), lane0 = lane & ~(G - 1u);
 	const uint32_t gmask = G == 32 ? 0xFFFFFFFFu : ((1u << G) - 1u);
 	bool running = j < j_end;
-	uint32_t S = 1;
+	uint32_t S = s_after_skip;
 	while (__any_sync(0xFFFFFFFFu, running)) {
 		// ---- the recurrence alone: S steps as if every cell were occupied; lane g keeps step g
 		float my_t = t, my_dt = 0.0f, tc = t;
@@ -84,7 +91,21 @@ __device__ __forceinline__ uint32_t march_group(const typename P::Ctx& pc, const
 		const bool clean = n_ok == S;                              // the whole round was occupied
 		// lane n_ok of the group holds the first sample that is not occupied: outside the box -> the ray ends; empty -> skip from there
 		float t_new = 0.0f;
-		if (running && !budget_hit && !clean && g == n_ok && inside) t_new = P::advance_to_next_voxel(my_t, pc, pos, rd, idir, mip);
+		if (running && !budget_hit && !clean && g == n_ok && inside) {
+			t_new = P::advance_to_next_voxel(my_t, pc, pos, rd, idir, mip);
+			// this lane keeps walking while the cells it lands in are empty (the sequential loop's next iterations, one lane, none of the
+			// round's fixed cost): a ray crosses ~100 empty cells between the camera and the scene
+			for (uint32_t w = 0; w < walk_empty; ++w) {
+				const V3 p2 = P::ray_pos(ro, t_new, rd);
+				if (!aabb.contains(p2)) {
+					inside = false;
+					break;
+				}
+				const uint32_t mip2 = P::mip_from_dt(P::calc_dt(t_new, pc), p2, max_cascade);
+				if (density_grid_occupied_at(p2, bitfield, mip2)) break;
+				t_new = P::advance_to_next_voxel(t_new, pc, p2, rd, idir, mip2);
+			}
+		}
 		const uint32_t fail_lane = lane0 + (n_ok < G ? n_ok : G - 1u);
 		const bool fail_inside = __shfl_sync(0xFFFFFFFFu, inside ? 1 : 0, fail_lane) != 0;
 		const float t_skip = __shfl_sync(0xFFFFFFFFu, t_new, fail_lane);
@@ -97,7 +118,7 @@ __device__ __forceinline__ uint32_t march_group(const typename P::Ctx& pc, const
 			} else {
 				if (!fail_inside) running = false;
 				t = t_skip;
-				S = 1;
+				S = s_after_skip;
 			}
 		}
 	}
@@ -144,7 +165,9 @@ __global__ void __launch_bounds__(32) k_generate_training_samples(
 		}
 	}
 	// pass 1: count the occupied steps, keeping every sample's t (or the first 64 and a checkpoint every GEN_SEG samples beyond)
-	const uint32_t numsteps = march_group<P, G>(pc, aabb, cfg.max_cascade, bitfield, ro, rdn, idir, startt, 0u, live ? NGP_NERF_STEPS : 0u,
+	const uint32_t walk_empty = (cfg.gen_walk_empty ? cfg.gen_walk_empty : gen_walk_empty_default(G)) - 1u;
+	const uint32_t spec0 = cfg.gen_speculation ? (cfg.gen_speculation < G ? cfg.gen_speculation : G) : gen_speculation_default(G);
+	const uint32_t numsteps = march_group<P, G>(pc, aabb, cfg.max_cascade, bitfield, ro, rdn, idir, startt, 0u, live ? NGP_NERF_STEPS : 0u, walk_empty, spec0,
 		[&](uint32_t jj, float t, float dt, V3) {
 			if (jj < T_SLOTS) t_list[jj * NG + grp] = t;
 			if constexpr (G < 16) {
@@ -253,7 +276,7 @@ __global__ void __launch_bounds__(32) k_generate_training_samples(
 			const uint32_t j0 = T_SLOTS + m * GEN_SEG;
 			const uint32_t j_end = (j0 + GEN_SEG < o_n) ? j0 + GEN_SEG : o_n;
 			float* co = coords_out + (size_t)o_base * 7;
-			march_group<P, G>(pc, aabb, cfg.max_cascade, bitfield, o_ro, o_rdn, o_idir, t0, active ? j0 : 1u, active ? j_end : 0u, [&](uint32_t jj, float t, float dt, V3 pos) {
+			march_group<P, G>(pc, aabb, cfg.max_cascade, bitfield, o_ro, o_rdn, o_idir, t0, active ? j0 : 1u, active ? j_end : 0u, walk_empty, spec0, [&](uint32_t jj, float t, float dt, V3 pos) {
 				const V3 wp = P::warp_position(pos, aabb);
 				float* c = co + (size_t)jj * 7;
 				c[0] = wp.x; c[1] = wp.y; c[2] = wp.z; c[3] = P::warp_dt(dt); c[4] = wdir.x; c[5] = wdir.y; c[6] = wdir.z;

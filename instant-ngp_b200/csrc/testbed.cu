@@ -1087,6 +1087,8 @@ int ngp_testbed_set_option(ngp_testbed* t, const char* name_c, double value) {
 		else if (n == "background_color.a") t->background_alpha = (float)value;
 		else if (n == "exposure") t->exposure = (float)value;
 		else if (n == "nerf.training.math_mode") { NGPB_CHECK(value == 0 || value == 1, "math_mode must be 0 (deterministic) or 1 (reference)"); tb_invalidate_prefetch(t); t->cfg.math_mode = (uint32_t)value; }
+		else if (n == "nerf.training.gen_walk_empty") { NGPB_CHECK(value >= 0 && value <= 1024, "gen_walk_empty: 0 (default) .. 1024"); tb_invalidate_prefetch(t); t->cfg.gen_walk_empty = (uint32_t)value; }
+		else if (n == "nerf.training.gen_speculation") { NGPB_CHECK(value >= 0 && value <= 32, "gen_speculation: 0 (default) .. 32"); tb_invalidate_prefetch(t); t->cfg.gen_speculation = (uint32_t)value; }
 		else if (n == "nerf.training.gen_lanes_per_ray") { const uint32_t g = (uint32_t)value; NGPB_CHECK(g <= 32 && (g & (g - 1)) == 0, "gen_lanes_per_ray must be 0 or a power of two up to 32"); tb_invalidate_prefetch(t); t->cfg.gen_lanes_per_ray = g; }
 		else if (n == "render_mode") { NGPB_CHECK(value == NGP_RENDER_SHADE || value == NGP_RENDER_AO || value == NGP_RENDER_POSITIONS || value == NGP_RENDER_DEPTH || value == NGP_RENDER_COST,
 			"render_mode: this build renders Shade, AO, Positions, Depth and Cost"); t->render_mode = (uint32_t)value; }
@@ -1118,6 +1120,8 @@ double ngp_testbed_get_option(ngp_testbed* t, const char* name_c) {
 	if (n == "nerf.training.train_mode") return c.train_mode;
 	if (n == "nerf.training.math_mode") return c.math_mode;
 	if (n == "nerf.training.gen_lanes_per_ray") return c.gen_lanes_per_ray;
+	if (n == "nerf.training.gen_walk_empty") return c.gen_walk_empty;
+	if (n == "nerf.training.gen_speculation") return c.gen_speculation;
 	if (n == "render_math") return t->render_math;
 	if (n == "render_mode") return t->render_mode;
 	if (n == "nerf.training.density_grid_decay") return t->density_grid_decay;

@@ -41,7 +41,7 @@ SCENES = [
 ]
 
 
-def run_generator(lib, scene, n_rays, max_samples, seed=1337, ray_offset=0, n_rays_global=None, ray_stride=0, math_mode=0, lanes=0):
+def run_generator(lib, scene, n_rays, max_samples, seed=1337, ray_offset=0, n_rays_global=None, ray_stride=0, math_mode=0, lanes=0, walk=0, speculation=0):
     import time
 
     import torch
@@ -53,6 +53,8 @@ def run_generator(lib, scene, n_rays, max_samples, seed=1337, ray_offset=0, n_ra
     cfg.ray_stride = ray_stride
     cfg.math_mode = math_mode
     cfg.gen_lanes_per_ray = lanes   # 0: chosen from the batch size; otherwise that many lanes of a warp march one ray together
+    cfg.gen_walk_empty = walk       # 0: library default; empty cells one lane crosses on its own per round
+    cfg.gen_speculation = speculation  # 0: library default; samples speculated in the first round after a skip
     bf = util.sphere_bitfield(radius=0.3, max_cascade=cfg.max_cascade, full=scene["full"])
     views, keep = util.make_views(imgs, cams, focal, lens=scene["lens"])
     t_views, tens = util.views_to_device(views, keep)
@@ -80,12 +82,15 @@ def run_generator(lib, scene, n_rays, max_samples, seed=1337, ray_offset=0, n_ra
 
 
 @pytest.mark.parametrize("scene", SCENES)
-@pytest.mark.parametrize("shard", [(0, None, 0, 0), (4096, 16384, 0, 1), (3, 16384, 4, 4), (0, None, 0, 32), (0, None, 0, 8), (0, None, 0, 2)])
+@pytest.mark.parametrize("shard", [(0, None, 0, 0), (4096, 16384, 0, 1), (3, 16384, 4, 4), (0, None, 0, 32), (0, None, 0, 8), (0, None, 0, 2),
+                                   (0, None, 0, 16, 1, 1), (0, None, 0, 16, 64, 16), (0, None, 0, 4, 7, 3), (0, None, 0, 1, 1024, 1)])
 def test_training_samples_bit_exact(lib, scene, shard):
-    """shard = (ray_offset, n_rays_global, ray_stride, lanes per ray): the whole batch with the automatic schedule; a contiguous shard, one
-    thread per ray; rank 3 of 4 with interleaved ids, 4 lanes per ray; the whole batch with a warp / 8 lanes / 2 lanes per ray"""
+    """shard = (ray_offset, n_rays_global, ray_stride, lanes per ray[, empty cells walked per round, speculation after a skip]): the whole batch
+    with the automatic schedule; a contiguous shard, one thread per ray; rank 3 of 4 with interleaved ids, 4 lanes per ray; the whole batch with
+    a warp / 8 lanes / 2 lanes per ray; the schedule knobs at their extremes"""
     n_rays, max_samples = 4096, 4096 * 1024
-    want, got, _ = run_generator(lib, scene, n_rays, max_samples, ray_offset=shard[0], n_rays_global=shard[1], ray_stride=shard[2], lanes=shard[3])
+    walk, speculation = (shard[4], shard[5]) if len(shard) > 4 else (0, 0)
+    want, got, _ = run_generator(lib, scene, n_rays, max_samples, ray_offset=shard[0], n_rays_global=shard[1], ray_stride=shard[2], lanes=shard[3], walk=walk, speculation=speculation)
     stride = shard[2] or 1
     assert want["n_samples"] <= max_samples, "test scene overflows: slot order would decide which rays are kept"
     assert want["n_samples"] > 1000, "degenerate scene"
