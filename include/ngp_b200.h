@@ -106,6 +106,14 @@ typedef struct ngp_march_consts {
 	float log1p_c, a, b, at, bt; /* valid when cone_angle > 1e-5 */
 } ngp_march_consts;
 
+/* The reference's order is that of its atomics (testbed_nerf.cu:1010): the 32 rays of a warp (consecutive ray ids = pixels of one view)
+ * together, warps as they finish. */
+typedef enum ngp_compaction_order {
+	NGP_COMPACTION_GROUPS = 0,    /* groups of 32 consecutive rays, the groups in a per-step shuffle (two passes + a prefix sum) */
+	NGP_COMPACTION_ATOMIC = 1,    /* one atomic per ray as the rays finish: single rays, shortest first (one pass) */
+	NGP_COMPACTION_RAY_ORDER = 2  /* ascending ray id */
+} ngp_compaction_order;
+
 typedef struct ngp_nerf_train_cfg {
 	float aabb_min[3], aabb_max[3];
 	uint32_t max_cascade; /* testbed_nerf.cu:2433-2436 */
@@ -130,6 +138,8 @@ typedef struct ngp_nerf_train_cfg {
 	                               0 = library default.  Schedule only */
 	uint32_t gen_speculation;   /* sample generator: samples a group speculates on in the first round after a skip (1 .. lanes per ray; doubles
 	                               after every fully occupied round); 0 = library default.  Schedule only */
+	uint32_t compaction_order;  /* ngp_compaction_order: the order in which rays take their slots in the compacted batch, i.e. which rays are cut when
+	                               a step's samples exceed the batch and which are repeated when they fall short.  A ray's gradients do not depend on it */
 } ngp_nerf_train_cfg;
 
 /* Counters written by the training sample generator / loss kernel (NerfCounters, testbed.h). */

@@ -110,6 +110,7 @@ class NerfTrainCfg(C.Structure):
         ("gen_lanes_per_ray", C.c_uint32),
         ("gen_walk_empty", C.c_uint32),
         ("gen_speculation", C.c_uint32),
+        ("compaction_order", C.c_uint32),
     ]
 
 

@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(32) k_generate_training_samples(
 			if constexpr (G < 16) {
 				// resuming the loop at this t finds sample jn first
 				const uint32_t jn = jj + 1u;
-				if (jn >= T_SLOTS && ((jn - T_SLOTS) & (GEN_SEG - 1u)) == 0u) ckpt[((jn - T_SLOTS) / GEN_SEG) * NG + grp] = t + dt;
+				if (jn >= T_SLOTS && jn < NGP_NERF_STEPS && ((jn - T_SLOTS) & (GEN_SEG - 1u)) == 0u) ckpt[((jn - T_SLOTS) / GEN_SEG) * NG + grp] = t + dt;
 			}
 		});
 

@@ -102,12 +102,87 @@ __device__ __forceinline__ SampleTerms sample_terms(const __half* __restrict__ n
 	return s;
 }
 
+// Which rays lose their gradients when a step's compacted samples exceed the batch (`compacted_base >= max_compacted`), and which
+// are repeated when they fall short (fill_rollover), follows from the order in which rays take their compacted slots.  The reference
+// reserves with one atomic per ray after its one-thread-per-ray loop (testbed_nerf.cu:1010): the 32 rays of a warp — consecutive ray
+// ids, i.e. pixels of one training view — take consecutive slots, warps in the order they finish (early in training, when every ray
+// runs to the step budget, that is launch order).  The order matters more than it looks: the controller rounds rays_per_batch UP to a
+// multiple of 256 (NerfCounters::update_after_training), so most steps overshoot the batch by a few percent, and the first steps
+// overshoot it tenfold.  One atomic per ray in a warp-per-ray kernel cuts rays one by one in the order they finish; on nerf/fox that
+// leaves floaters in two held-out views in most runs (-0.2 dB in the mean, profiles/r2/psnr_ab.md) whatever the sample generator's
+// schedule, while the reference's grouping does not.  So the order is computed instead of raced for: pass 1
+// (k_compute_loss<LOSS_PASS1>) composites every ray and records its sample count under its local ray index, k_compaction_order hands
+// out the slots along cfg.compaction_order, pass 2 (k_compute_loss<LOSS_PASS2>) writes gradients and compacted coordinates.
+enum LossMode : uint32_t { LOSS_FUSED = 0, LOSS_PASS1 = 1, LOSS_PASS2 = 2 };
+struct LossRayScratch {   // pass 1 -> pass 2, one per ray slot
+	float rgb_ray[3];
+	float loss_bg[3];
+	uint32_t count;        // samples the ray is read for (before truncation)
+	uint32_t pad;
+};
+constexpr uint32_t COMPACTION_GROUP = 32;   // rays that stay together, in ray order: a warp of the reference's kernel
+
+// local ray index of the q-th ray in the step's compaction order
+__device__ __forceinline__ uint32_t compaction_ray(uint32_t q, uint32_t n_groups, uint32_t order, uint32_t offset) {
+	if (order == NGP_COMPACTION_RAY_ORDER) return q;
+	// groups of 32 consecutive rays in shuffled order: an affine walk through [0, n_groups) with a prime stride larger than any count
+	const uint32_t grp = (uint32_t)(((uint64_t)(q / COMPACTION_GROUP) * 2654435761ull + offset) % n_groups);
+	return grp * COMPACTION_GROUP + (q % COMPACTION_GROUP);
+}
+
+// exclusive prefix sum of the rays' sample counts along the compaction order, in place (count -> first slot); one CTA of 1024 threads,
+// a contiguous chunk of the order each
+__global__ void __launch_bounds__(1024) k_compaction_order(const uint32_t n_rays_local, ngp_nerf_counters* __restrict__ counters, uint32_t* __restrict__ by_ray,
+	const uint32_t order, const uint32_t offset) {
+	const uint32_t n_groups = (n_rays_local + COMPACTION_GROUP - 1u) / COMPACTION_GROUP;
+	const uint32_t n = n_groups * COMPACTION_GROUP;
+	const uint32_t chunk = (n + 1023u) / 1024u;
+	const uint32_t q0 = threadIdx.x * chunk < n ? threadIdx.x * chunk : n, q1 = (q0 + chunk < n) ? q0 + chunk : n;
+	uint32_t sum = 0;
+	for (uint32_t q = q0; q < q1; ++q) {
+		const uint32_t li = compaction_ray(q, n_groups, order, offset);
+		if (li < n_rays_local) sum += by_ray[li];
+	}
+	__shared__ uint32_t warp_sums[32];
+	const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+	uint32_t incl = sum;
+#pragma unroll
+	for (uint32_t o = 1; o < 32; o <<= 1) {
+		const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+		if (lane >= o) incl += t;
+	}
+	if (lane == 31) warp_sums[warp] = incl;
+	__syncthreads();
+	if (warp == 0) {
+		const uint32_t v = warp_sums[lane];
+		uint32_t w = v;
+#pragma unroll
+		for (uint32_t o = 1; o < 32; o <<= 1) {
+			const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, w, o);
+			if (lane >= o) w += t;
+		}
+		warp_sums[lane] = w - v;
+		if (lane == 31) counters->n_samples_compacted = w;   // what the reference's atomic counter ends at: not clamped
+	}
+	__syncthreads();
+	uint32_t run = warp_sums[warp] + incl - sum;
+	for (uint32_t q = q0; q < q1; ++q) {
+		const uint32_t li = compaction_ray(q, n_groups, order, offset);
+		if (li < n_rays_local) {
+			const uint32_t c = by_ray[li];
+			by_ray[li] = run;
+			run += c;
+		}
+	}
+}
+
+template <uint32_t MODE>
 __global__ void __launch_bounds__(128) k_compute_loss(
 	const uint32_t n_rays_global, Pcg32 rng_in, const ngp_nerf_train_cfg cfg, const ngp_train_view* __restrict__ views, const uint32_t n_views,
 	const __half* __restrict__ network_output, const uint32_t max_compacted, ngp_nerf_counters* __restrict__ counters,
 	const uint32_t* __restrict__ ray_indices_in, const float* __restrict__ rays_in, uint32_t* __restrict__ numsteps_in,
 	const float* __restrict__ coords_in, float* __restrict__ coords_out, __half* __restrict__ dloss_out, float* __restrict__ loss_output,
-	const float* __restrict__ mean_density_ptr
+	const float* __restrict__ mean_density_ptr, LossRayScratch* __restrict__ scratch, uint32_t* __restrict__ by_ray, const uint32_t n_rays_local
 ) {
 	const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // ray slot
 	const uint32_t lane = threadIdx.x & 31u;
@@ -159,7 +234,13 @@ __global__ void __launch_bounds__(128) k_compute_loss(
 	V3 rgb_ray{0, 0, 0}, loss_bg{0, 0, 0};
 	uint32_t compacted_numsteps = 0;
 	bool stopped = false;
-	for (uint32_t c0 = 0; c0 < numsteps && !stopped; c0 += 32) {
+	if constexpr (MODE == LOSS_PASS2) {
+		const LossRayScratch r = scratch[i];
+		rgb_ray = V3{r.rgb_ray[0], r.rgb_ray[1], r.rgb_ray[2]};
+		loss_bg = V3{r.loss_bg[0], r.loss_bg[1], r.loss_bg[2]};
+		compacted_numsteps = r.count;
+	}
+	for (uint32_t c0 = 0; MODE != LOSS_PASS2 && c0 < numsteps && !stopped; c0 += 32) {
 		const uint32_t k = c0 + lane;
 		SampleTerms st{0, 0, 0, 0};
 		float o0, o1, o2, o3, dt;
@@ -187,7 +268,7 @@ __global__ void __launch_bounds__(128) k_compute_loss(
 		}
 	}
 
-	if (compacted_numsteps == numsteps) {
+	if (MODE != LOSS_PASS2 && compacted_numsteps == numsteps) {
 		rgb_ray = rgb_ray + T * bg;
 		if (cfg.train_mode == NGP_TRAIN_RFL) {   // train_nerf.cuh:251-254
 			float l0, l1, l2, gd;
@@ -204,10 +285,26 @@ __global__ void __launch_bounds__(128) k_compute_loss(
 	loss_and_gradient1(target.z, rgb_ray.z, cfg.loss_type, lz, lg_grad.z);
 	const float mean_loss = ((lx + ly) + lz) / 3.0f;
 
+	if constexpr (MODE == LOSS_PASS1) {
+		if (lane == 0) {
+			LossRayScratch r;
+			r.rgb_ray[0] = rgb_ray.x; r.rgb_ray[1] = rgb_ray.y; r.rgb_ray[2] = rgb_ray.z;
+			r.loss_bg[0] = loss_bg.x; r.loss_bg[1] = loss_bg.y; r.loss_bg[2] = loss_bg.z;
+			r.count = compacted_numsteps;
+			r.pad = 0;
+			scratch[i] = r;
+			by_ray[(ray_idx / (cfg.ray_stride ? cfg.ray_stride : 1u)) % n_rays_local] = compacted_numsteps;
+		}
+		return;
+	}
 	// ---- compaction: one reservation per ray (testbed_nerf.cu:1010-1016)
 	uint32_t compacted_base = 0;
-	if (lane == 0) compacted_base = atomicAdd(&counters->n_samples_compacted, compacted_numsteps);
-	compacted_base = __shfl_sync(0xFFFFFFFFu, compacted_base, 0);
+	if constexpr (MODE == LOSS_PASS2) {
+		compacted_base = by_ray[(ray_idx / (cfg.ray_stride ? cfg.ray_stride : 1u)) % n_rays_local];
+	} else {
+		if (lane == 0) compacted_base = atomicAdd(&counters->n_samples_compacted, compacted_numsteps);
+		compacted_base = __shfl_sync(0xFFFFFFFFu, compacted_base, 0);
+	}
 	const uint32_t cb_clamped = compacted_base < max_compacted ? compacted_base : max_compacted;
 	const uint32_t room = max_compacted - cb_clamped;
 	compacted_numsteps = room < compacted_numsteps ? room : compacted_numsteps;
@@ -469,15 +566,54 @@ static Aabb cfg_aabb(const ngp_nerf_train_cfg& cfg) {
 	return Aabb{V3{cfg.aabb_min[0], cfg.aabb_min[1], cfg.aabb_min[2]}, V3{cfg.aabb_max[0], cfg.aabb_max[1], cfg.aabb_max[2]}};
 }
 
+// a memory pool of the current device whose freed blocks stay allocated (release threshold: never)
+static cudaMemPool_t scratch_pool() {
+	static cudaMemPool_t pools[64] = {};
+	int dev = 0;
+	NGPB_CUDA_CHECK(cudaGetDevice(&dev));
+	NGPB_CHECK(dev >= 0 && dev < 64, "device index out of range");
+	if (!pools[dev]) {
+		cudaMemPoolProps props{};
+		props.allocType = cudaMemAllocationTypePinned;
+		props.handleTypes = cudaMemHandleTypeNone;
+		props.location.type = cudaMemLocationTypeDevice;
+		props.location.id = dev;
+		NGPB_CUDA_CHECK(cudaMemPoolCreate(&pools[dev], &props));
+		uint64_t keep = UINT64_MAX;
+		NGPB_CUDA_CHECK(cudaMemPoolSetAttribute(pools[dev], cudaMemPoolAttrReleaseThreshold, &keep));
+	}
+	return pools[dev];
+}
+
 void compute_loss(cudaStream_t stream, uint32_t n_rays_local, uint32_t n_rays_global, uint64_t rng_state, uint64_t rng_inc,
 	const ngp_nerf_train_cfg& cfg, const ngp_train_view* views, uint32_t n_views, const __half* network_output, uint32_t max_compacted,
 	ngp_nerf_counters* counters, const uint32_t* ray_indices, const float* rays, uint32_t* numsteps, const float* coords, float* coords_compacted,
 	__half* dloss, float* loss_per_ray, const float* mean_density) {
 	if (n_rays_local == 0) return;
 	// one warp per ray, 4 rays per CTA
-	k_compute_loss<<<div_round_up(n_rays_local, 4), 128, 0, stream>>>(n_rays_global, Pcg32(rng_state, rng_inc, true), cfg, views, n_views,
-		network_output, max_compacted, counters, ray_indices, rays, numsteps, coords, coords_compacted, dloss, loss_per_ray, mean_density);
-	NGPB_LAUNCHED();
+	const Pcg32 rng(rng_state, rng_inc, true);
+	NGPB_CHECK(cfg.compaction_order <= NGP_COMPACTION_RAY_ORDER, "ngp_nerf_train_cfg.compaction_order: 0 (groups of 32 rays, shuffled), 1 (one atomic per ray), 2 (ray order)");
+	if (cfg.compaction_order == NGP_COMPACTION_ATOMIC) {
+		k_compute_loss<LOSS_FUSED><<<div_round_up(n_rays_local, 4), 128, 0, stream>>>(n_rays_global, rng, cfg, views, n_views,
+			network_output, max_compacted, counters, ray_indices, rays, numsteps, coords, coords_compacted, dloss, loss_per_ray, mean_density, nullptr, nullptr, n_rays_local);
+		NGPB_LAUNCHED();
+	} else {
+		// stream-ordered scratch from a pool that keeps its memory (the default pool hands it back at every synchronisation)
+		const size_t slot_bytes = sizeof(LossRayScratch) * (size_t)n_rays_local;
+		uint8_t* mem = nullptr;
+		NGPB_CUDA_CHECK(cudaMallocFromPoolAsync(reinterpret_cast<void**>(&mem), slot_bytes + sizeof(uint32_t) * (size_t)n_rays_local, scratch_pool(), stream));
+		LossRayScratch* scratch = reinterpret_cast<LossRayScratch*>(mem);
+		uint32_t* by_ray = reinterpret_cast<uint32_t*>(mem + slot_bytes);
+		NGPB_CUDA_CHECK(cudaMemsetAsync(by_ray, 0, sizeof(uint32_t) * (size_t)n_rays_local, stream));
+		k_compute_loss<LOSS_PASS1><<<div_round_up(n_rays_local, 4), 128, 0, stream>>>(n_rays_global, rng, cfg, views, n_views,
+			network_output, max_compacted, counters, ray_indices, rays, numsteps, coords, coords_compacted, dloss, loss_per_ray, mean_density, scratch, by_ray, n_rays_local);
+		// the shuffle's offset changes with the step's random stream (the multiplier is fixed)
+		k_compaction_order<<<1, 1024, 0, stream>>>(n_rays_local, counters, by_ray, cfg.compaction_order, (uint32_t)((rng_state >> 33) ^ rng_state));
+		k_compute_loss<LOSS_PASS2><<<div_round_up(n_rays_local, 4), 128, 0, stream>>>(n_rays_global, rng, cfg, views, n_views,
+			network_output, max_compacted, counters, ray_indices, rays, numsteps, coords, coords_compacted, dloss, loss_per_ray, mean_density, scratch, by_ray, n_rays_local);
+		NGPB_LAUNCHED(); NGPB_LAUNCHED(); NGPB_LAUNCHED();
+		NGPB_CUDA_CHECK(cudaFreeAsync(mem, stream));
+	}
 	NGPB_CUDA_CHECK(cudaGetLastError());
 }
 

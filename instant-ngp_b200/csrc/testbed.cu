@@ -195,6 +195,7 @@ struct ngp_testbed {
 	uint32_t optimizer_step = 0;
 	uint64_t seed = 1337;
 	bool train_network = true, train_encoding = true;
+	uint32_t drop_overflowing_rays = 0;   // sample generator capacity: 0 = the sample buffer (16 x batch), 1 = the previous step's sample count like the reference (tb_generator_capacity)
 	uint32_t full_inference = 2;    // training-time inference schedule: 0 ray-ordered, 1 every generated sample (the reference's), 2 chosen per step (tb_full_inference)
 	uint32_t inference_chunk = 0;   // consecutive samples of a ray per tile of the ray-ordered inference pass; 0 = from the last step's samples per ray
 
@@ -523,6 +524,12 @@ static uint32_t tb_max_inference(const ngp_testbed* t, uint32_t batch) {
 	if (t->measured_batch_size_before_compaction == 0) return max_samples;
 	return next_multiple(std::min(t->measured_batch_size_before_compaction, max_samples), NGP_BATCH_GRANULARITY);
 }
+// What the sample generator may fill.  The reference sizes its inference launch on the host from the PREVIOUS step's sample count
+// (max_inference, testbed_nerf.cu:3055-3061) and so drops every ray whose samples end beyond it: whenever a step generates more than
+// the last one did, the rays that reserve their slots last — the longest — are lost.  Here the inference pass reads the count from the
+// device counter and the only limit is the buffer (16 x batch, the reference's max_samples); `nerf.training.drop_overflowing_rays` = 1
+// restores the reference's rule.
+static uint32_t tb_generator_capacity(const ngp_testbed* t, uint32_t batch) { return t->drop_overflowing_rays ? tb_max_inference(t, batch) : batch * 16; }
 // The training-time inference pass has two schedules.  Ray-ordered (k_nerf_forward_rays): a tile is 128 / chunk rays x chunk
 // consecutive samples and a ray is walked chunk by chunk until the loss kernel would stop reading it — up to chunk - 1 evaluations
 // per ray are wasted and a long ray takes many sequential tiles, but nothing behind the stopping point is evaluated.  Flat
@@ -592,8 +599,8 @@ static void tb_front(ngp_testbed* t, uint32_t batch) {
 	if (t->training_step == 0) t->n_rays_total = 0;
 	const uint32_t rays_local = t->rays_per_batch;
 	const uint32_t rays_global = rays_local * t->dp_world;
-	const uint32_t max_inference = tb_max_inference(t, batch);
-	if (t->measured_batch_size_before_compaction == 0) t->measured_batch_size_before_compaction = max_inference;
+	if (t->measured_batch_size_before_compaction == 0) t->measured_batch_size_before_compaction = tb_max_inference(t, batch);
+	const uint32_t max_inference = tb_generator_capacity(t, batch);
 	t->n_rays_total += rays_global;
 
 	const bool use_prefetch = t->prefetch_valid && t->prefetch_step == t->training_step && t->prefetch_batch == batch && t->prefetch_rays == rays_local &&
@@ -725,7 +732,7 @@ static void tb_prefetch(ngp_testbed* t) {
 	if (!(worth_it && t->shall_train && !tb_prep_due(next_step) && !t->views_dirty && !t->profiling)) return;
 	const uint32_t batch = t->step_batch;
 	const uint32_t next = t->cur ^ 1u;
-	const uint32_t max_inference = tb_max_inference(t, batch);
+	const uint32_t max_inference = tb_generator_capacity(t, batch);
 	// the other buffer set was last read by the loss kernel of the previous step, which precedes ev_back_done on the main stream;
 	// the bitfield and the views are not written by anything in flight
 	NGPB_CUDA_CHECK(cudaStreamWaitEvent(t->side_stream, t->ev_back_done, 0));
@@ -1089,6 +1096,8 @@ int ngp_testbed_set_option(ngp_testbed* t, const char* name_c, double value) {
 		else if (n == "nerf.training.math_mode") { NGPB_CHECK(value == 0 || value == 1, "math_mode must be 0 (deterministic) or 1 (reference)"); tb_invalidate_prefetch(t); t->cfg.math_mode = (uint32_t)value; }
 		else if (n == "nerf.training.gen_walk_empty") { NGPB_CHECK(value >= 0 && value <= 1024, "gen_walk_empty: 0 (default) .. 1024"); tb_invalidate_prefetch(t); t->cfg.gen_walk_empty = (uint32_t)value; }
 		else if (n == "nerf.training.gen_speculation") { NGPB_CHECK(value >= 0 && value <= 32, "gen_speculation: 0 (default) .. 32"); tb_invalidate_prefetch(t); t->cfg.gen_speculation = (uint32_t)value; }
+		else if (n == "nerf.training.compaction_order") { NGPB_CHECK(value == 0 || value == 1 || value == 2, "compaction_order: 0 (groups of 32 rays, shuffled), 1 (one atomic per ray), 2 (ray order)"); t->cfg.compaction_order = (uint32_t)value; }
+		else if (n == "nerf.training.drop_overflowing_rays") { NGPB_CHECK(value == 0 || value == 1, "drop_overflowing_rays: 0 or 1"); tb_invalidate_prefetch(t); t->drop_overflowing_rays = (uint32_t)value; }
 		else if (n == "nerf.training.gen_lanes_per_ray") { const uint32_t g = (uint32_t)value; NGPB_CHECK(g <= 32 && (g & (g - 1)) == 0, "gen_lanes_per_ray must be 0 or a power of two up to 32"); tb_invalidate_prefetch(t); t->cfg.gen_lanes_per_ray = g; }
 		else if (n == "render_mode") { NGPB_CHECK(value == NGP_RENDER_SHADE || value == NGP_RENDER_AO || value == NGP_RENDER_POSITIONS || value == NGP_RENDER_DEPTH || value == NGP_RENDER_COST,
 			"render_mode: this build renders Shade, AO, Positions, Depth and Cost"); t->render_mode = (uint32_t)value; }
@@ -1122,6 +1131,8 @@ double ngp_testbed_get_option(ngp_testbed* t, const char* name_c) {
 	if (n == "nerf.training.gen_lanes_per_ray") return c.gen_lanes_per_ray;
 	if (n == "nerf.training.gen_walk_empty") return c.gen_walk_empty;
 	if (n == "nerf.training.gen_speculation") return c.gen_speculation;
+	if (n == "nerf.training.compaction_order") return c.compaction_order;
+	if (n == "nerf.training.drop_overflowing_rays") return t->drop_overflowing_rays;
 	if (n == "render_math") return t->render_math;
 	if (n == "render_mode") return t->render_mode;
 	if (n == "nerf.training.density_grid_decay") return t->density_grid_decay;

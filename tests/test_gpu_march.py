@@ -211,6 +211,83 @@ def test_loss_and_compaction_bit_exact(lib, scene, loss_type, random_bg, train_m
     assert t_dl.cpu().numpy().tobytes() == dl_pad.tobytes()
 
 
+def _run_loss(lib, ctx, got, net_out_dev, batch, order, n_rays):
+    import torch
+
+    cfg = ctx["cfg"]
+    cfg.compaction_order = order
+    d = ctx["dev"]
+    t_cnt = d["cnt"].clone()
+    t_ns = d["ns"].clone()
+    t_coc = torch.zeros(batch, 7, dtype=torch.float32, device="cuda")
+    t_dl = torch.zeros(batch, 4, dtype=torch.float16, device="cuda")
+    t_loss = torch.zeros(n_rays, dtype=torch.float32, device="cuda")
+    t_md = dev(np.array([0.02], dtype=np.float32))
+    rc = lib.ngp_nerf_compute_loss(stream(), n_rays, n_rays, ctx["rng"][0], ctx["rng"][1], C.byref(cfg), ctx["t_views"].data_ptr(), len(ctx["views"]), net_out_dev.data_ptr(),
+                                   batch, t_cnt.data_ptr(), d["ri"].data_ptr(), d["rays"].data_ptr(), t_ns.data_ptr(), d["co"].data_ptr(), t_coc.data_ptr(), t_dl.data_ptr(),
+                                   t_loss.data_ptr(), t_md.data_ptr())
+    assert rc == 0, lib.ngp_last_error()
+    torch.cuda.synchronize()
+    k = got["n_kept"]
+    return dict(total=int(t_cnt.cpu().numpy().view(np.uint32)[2]), ns=t_ns.cpu().numpy().view(np.uint32)[:k], co=t_coc.cpu().numpy(), dl=t_dl.cpu().numpy(),
+                loss=t_loss.cpu().numpy()[:k])
+
+
+def test_compaction_orders(lib):
+    """ngp_nerf_train_cfg.compaction_order decides where a ray's samples go in the compacted batch — and with it which rays an overfull
+    batch cuts — not what they are: groups of 32 consecutive rays (the default), one atomic per ray, ascending ray id."""
+    n_rays, max_samples = 4096, 4096 * 1024
+    want, got, ctx = run_generator(lib, SCENES[1], n_rays, max_samples)
+    k = got["n_kept"]
+    rng = np.random.default_rng(5)
+    net_out = np.zeros((max_samples, 4), dtype=np.float16)
+    net_out[:, 0:3] = rng.normal(0, 1.5, size=(max_samples, 3)).astype(np.float16)
+    net_out[:, 3] = rng.normal(1.0, 2.5, size=max_samples).astype(np.float16)
+    t_no = dev(net_out)
+    ray_ids = got["ray_indices"][:k].astype(np.int64)
+    big = 1 << int(np.ceil(np.log2(max(got["n_samples"], 2))))
+    runs = {order: _run_loss(lib, ctx, got, t_no, big, order, n_rays) for order in (1, 0, 2)}
+    ref = runs[1]
+    assert ref["total"] > 0
+    for order, r in runs.items():
+        assert r["total"] == ref["total"]                                  # the counter: every ray's samples, not clamped
+        assert np.array_equal(r["ns"][:, 0], ref["ns"][:, 0])              # per-ray counts
+        assert r["loss"].tobytes() == ref["loss"].tobytes()
+        cnt, base = r["ns"][:, 0].astype(np.int64), r["ns"][:, 1].astype(np.int64)
+        o = np.argsort(base, kind="stable")
+        nz = o[cnt[o] > 0]
+        assert base[nz][0] == 0 and np.array_equal(base[nz][1:], (base[nz] + cnt[nz])[:-1]) and base[nz][-1] + cnt[nz][-1] == r["total"]   # slots tile [0, total)
+        for i in np.flatnonzero(cnt)[::7]:
+            a, b, n = int(base[i]), int(ref["ns"][i, 1]), int(cnt[i])
+            assert r["co"][a:a + n].tobytes() == ref["co"][b:b + n].tobytes()
+            assert r["dl"][a:a + n].tobytes() == ref["dl"][b:b + n].tobytes()
+    # ascending ray id
+    cnt, base = runs[2]["ns"][:, 0].astype(np.int64), runs[2]["ns"][:, 1].astype(np.int64)
+    by_id = np.argsort(ray_ids)
+    assert np.array_equal(base[by_id], np.concatenate([[0], np.cumsum(cnt[by_id])[:-1]]))
+    # groups of 32 consecutive ray ids stay together, in ray order; the groups themselves are shuffled
+    cnt, base = runs[0]["ns"][:, 0].astype(np.int64), runs[0]["ns"][:, 1].astype(np.int64)
+    starts = []
+    for g in range(n_rays // 32):
+        m = by_id[(ray_ids[by_id] // 32) == g]
+        if len(m) == 0:
+            continue
+        assert np.array_equal(base[m], base[m][0] + np.concatenate([[0], np.cumsum(cnt[m])[:-1]]))
+        starts.append(base[m][0])
+    assert len(starts) > 8 and not np.array_equal(np.sort(starts), np.array(starts))
+    # an overfull batch: the rays behind the limit keep nothing, the one across it keeps its head, everything before is whole
+    small = (ref["total"] // 2) // 256 * 256
+    for order in (0, 2):
+        whole = runs[order]["ns"]
+        cut = _run_loss(lib, ctx, got, t_no, small, order, n_rays)
+        assert cut["total"] == ref["total"]
+        assert np.array_equal(cut["ns"][:, 1], whole[:, 1])
+        room = np.clip(small - whole[:, 1].astype(np.int64), 0, None)
+        assert np.array_equal(cut["ns"][:, 0], np.minimum(whole[:, 0], room))
+        assert int(cut["ns"][:, 0].sum()) == small
+        assert cut["co"][:small].tobytes() == runs[order]["co"][:small].tobytes()
+
+
 @pytest.mark.parametrize("aabb_scale", [1, 4])
 def test_density_grid_update_matches_oracle(lib, aabb_scale):
     import torch

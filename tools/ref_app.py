@@ -314,6 +314,8 @@ def main():
     ap.add_argument("--no-eval", action="store_true")
     ap.add_argument("--render-repeats", type=int, default=5)
     ap.add_argument("--ball-res", type=int, default=800)
+    ap.add_argument("--save-views", action="store_true", help="keep every held-out view (every 6th pixel, sRGB 8 bit) in the .npz")
+    ap.add_argument("--sync-every-step", action="store_true", help="wait for the device after every train() (the reference does: src/testbed.cu:4641)")
     ap.add_argument("--option", action="append", default=[], help="ngp_b200 only: name=value passed to Testbed._set before training")
     args = ap.parse_args()
     out = Path(args.out)
@@ -351,6 +353,8 @@ def main():
         stamps[0] = t_start
         for s in range(1, args.steps + 1):
             impl.train()
+            if args.sync_every_step:
+                impl.sync()
             if s in marks:
                 impl.sync()
                 stamps[s] = time.perf_counter()
@@ -402,6 +406,9 @@ def main():
                     arte["crop64_linear"] = img[cy - 32:cy + 32, cx - 32:cx + 32].astype(np.float32)
                     arte["view0_small_linear"] = img[::8, ::8].astype(np.float32)
                     arte["view0_alpha_mean"] = np.float32(img[..., 3].mean())
+                if args.save_views:
+                    arte[f"view{i}_srgb8"] = (np.clip(linear_to_srgb(img[::6, ::6, :3]), 0, 1) * 255).astype(np.uint8)
+                    arte[f"view{i}_err8"] = (np.clip(np.abs(np.clip(linear_to_srgb(img[::6, ::6, :3]), 0, 1) - np.clip(gt[::6, ::6], 0, 1)).mean(-1) * 4, 0, 1) * 255).astype(np.uint8)
         else:
             impl.load_arrays(ball["timgs"], ball["tcams"], ball["focal"])
             impl.prepare_eval()
