@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """gen_consistency.py — do all schedules of the training sample generator produce the same rays on a TRAINED scene?
 
-tests/test_gpu_march.py pins every schedule (lanes per ray, walk, speculation, slot reservation) against the CPU oracle on synthetic
+tests/test_gpu_march.py pins every schedule (lanes per ray, walk, speculation) against the CPU oracle on synthetic
 scenes whose occupancy is a sphere.  This tool repeats the comparison where training runs: nerf/fox after `--steps` training steps
 (fragmented three-cascade occupancy, OpenCV lens, cone stepping), both arithmetic flavours, every schedule against one thread per ray.
 
@@ -74,9 +74,9 @@ def main():
     t_ns = torch.zeros(n_rays, 2, dtype=torch.int32, device="cuda")
     t_co = torch.zeros(max_samples, 7, dtype=torch.float32, device="cuda")
 
-    def run(seed, math_mode, lanes, slot, walk=0, spec=0):
+    def run(seed, math_mode, lanes, walk=0, spec=0):
         cfg = util.make_train_cfg(aabb_scale=4)
-        cfg.math_mode, cfg.gen_lanes_per_ray, cfg.slot_reservation, cfg.gen_walk_empty, cfg.gen_speculation = math_mode, lanes, slot, walk, spec
+        cfg.math_mode, cfg.gen_lanes_per_ray, cfg.gen_walk_empty, cfg.gen_speculation = math_mode, lanes, walk, spec
         s, inc = pcg32_seed(seed)
         t_cnt.zero_(); t_ns.zero_(); t_ri.zero_()
         rc = lib.ngp_nerf_generate_training_samples(stream, n_rays, 0, n_rays, s, inc, C.byref(cfg), t_views.data_ptr(), n_views, t_bf.data_ptr(), max_samples,
@@ -92,13 +92,13 @@ def main():
         return {int(r): (int(ns[j, 0]), rays[j].tobytes(), co[ns[j, 1]:ns[j, 1] + ns[j, 0]].copy()) for j, r in enumerate(ri)}, int(cnt[1])
 
     out = {"steps": args.steps, "rays": n_rays, "occupancy_per_cascade": occupancy, "cases": []}
-    variants = [(16, 0, 0, 0), (16, 1, 0, 0), (32, 0, 0, 0), (8, 0, 0, 0), (4, 1, 0, 0), (2, 0, 0, 0), (16, 1, 1, 1), (16, 1, 64, 16), (1, 0, 0, 0)]
+    variants = [(16, 0, 0), (32, 0, 0), (8, 0, 0), (4, 0, 0), (2, 0, 0), (16, 1, 1), (16, 64, 16), (1, 0, 0)]
     for math_mode in (1, 0):
         for seed in range(1, args.seeds + 1):
-            base, n_base = run(seed, math_mode, 1, 1)
-            for lanes, slot, walk, spec in variants:
-                got, n_got = run(seed, math_mode, lanes, slot, walk, spec)
-                rec = {"math_mode": math_mode, "seed": seed, "lanes": lanes, "slot_reservation": slot, "walk": walk, "speculation": spec,
+            base, n_base = run(seed, math_mode, 1)
+            for lanes, walk, spec in variants:
+                got, n_got = run(seed, math_mode, lanes, walk, spec)
+                rec = {"math_mode": math_mode, "seed": seed, "lanes": lanes, "walk": walk, "speculation": spec,
                        "n_samples": n_got, "n_samples_base": n_base, "rays_base": len(base), "rays_got": len(got)}
                 diff_set = sorted(set(base) ^ set(got))
                 diff_count, diff_coord, worst = [], 0, 0.0

@@ -4,6 +4,9 @@
 nerf/fox is trained with one thread per ray to a list of checkpoints; at each, the exact state (.ngpb: fp32 weights, optimizer, occupancy
 grid, RNG streams, controller) is written out.  Every variant then reloads the checkpoint, runs `train_compute_grads` once and its fp16
 gradient buffer is compared with the one-thread-per-ray run's (twice, which gives the noise floor of the fp16 reductions' order).
+Variants: lanes per ray of the generator, compaction order (0 groups of 32 rays shuffled, 1 one atomic per ray, 2 ray id), the reference's
+generator capacity (drop), the inference schedule.  (profiles/r2/order/step_consistency.json was taken with the experiment's `slot`
+knob in place of `order`: 1 = one atomic per warp / ray, 0 = one per CTA of 32 / 16 rays.)
 
     python tools/step_consistency.py --checkpoints 0,8,32,100,300,700 > gpurun_out/step_consistency.json
 """
@@ -50,11 +53,12 @@ def main():
 
     def set_variant(v):
         tb._set("nerf.training.gen_lanes_per_ray", v["lanes"])
-        tb._set("nerf.training.slot_reservation", v["slot"])
+        tb._set("nerf.training.compaction_order", v["order"])
+        tb._set("nerf.training.drop_overflowing_rays", v.get("drop", 0))
         tb._set("nerf.training.full_inference", v.get("full_inference", 2))
 
     tb._set("nerf.training.gen_lanes_per_ray", 1)
-    tb._set("nerf.training.slot_reservation", 1)
+    tb._set("nerf.training.compaction_order", 1)
     step = 0
     for ck in cks:
         while step < ck:
@@ -78,11 +82,12 @@ def main():
         tb.sync()
         return g.astype(np.float32), before, after
 
-    variants = [dict(lanes=1, slot=1), dict(lanes=1, slot=0), dict(lanes=2, slot=1), dict(lanes=16, slot=1), dict(lanes=16, slot=0), dict(lanes=32, slot=1),
-                dict(lanes=0, slot=0), dict(lanes=1, slot=1, full_inference=1), dict(lanes=16, slot=1, full_inference=1), dict(lanes=16, slot=1, full_inference=0)]
+    variants = [dict(lanes=1, order=1), dict(lanes=1, order=0), dict(lanes=2, order=1), dict(lanes=16, order=1), dict(lanes=16, order=0), dict(lanes=16, order=2),
+                dict(lanes=0, order=0), dict(lanes=0, order=0, drop=1), dict(lanes=1, order=1, full_inference=1), dict(lanes=16, order=1, full_inference=1),
+                dict(lanes=16, order=1, full_inference=0)]
     out = {"n_params": n_params, "n_mlp": n_mlp, "checkpoints": []}
     for ck in cks:
-        base, b0, a0 = one_step(ck, dict(lanes=1, slot=1))
+        base, b0, a0 = one_step(ck, dict(lanes=1, order=1))
         nb = float(np.linalg.norm(base))
         rec = {"step": ck, "controller_before": b0, "controller_after": a0, "grad_norm": nb, "grad_norm_mlp": float(np.linalg.norm(base[:n_mlp])),
                "nonfinite": int((~np.isfinite(base)).sum()), "variants": []}
