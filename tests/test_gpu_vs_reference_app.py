@@ -83,18 +83,18 @@ def test_the_reference_renders_our_snapshot_like_we_do(runs):
 def test_trained_psnr_and_loss_track_the_reference(runs):
     """own training, same protocol.  The two runs draw the same rays only while their rays_per_batch controllers agree, the atomics order
     differs and this library accumulates the MLP in fp32 (the reference in fp16).  Measured on a B200 (profiles/r2/psnr_ab.md): the
-    reference lands on 26.03-26.11 dB over five runs, this library on 25.66-26.05 dB over ten — 0.15 dB (6e-3 relative) lower on
-    average with a larger run-to-run spread, and ~8 % higher training loss at step 1000; on identical weights the two renderers agree
-    to 3e-6 relative (the test above), so the residue is in the training trajectory, not in the evaluation.  Open item.
-    The bound here is that measured spread, not the north star's 1e-3."""
+    reference lands on 26.03-26.11 dB over six runs, this library on 25.99-26.08 dB over four since rays take their compacted slots in
+    groups of 32 consecutive rays (before: 25.1-26.1, floaters in two held-out views in most runs) — means 1.5e-3 apart, spreads alike;
+    the training loss at step ~1000 is 6-19 % above the reference's three samples.  On identical weights the two renderers agree to 3e-6
+    relative (the test above).  The bounds here are three times the measured spread, not the north star's 1e-3."""
     ref, ours = runs["ref"], runs["ours"]
     rel = abs(ours["psnr_mean"] - ref["psnr_mean"]) / ref["psnr_mean"]
     print(f"PSNR@{STEPS}: reference {ref['psnr_mean']:.4f} dB, this library {ours['psnr_mean']:.4f} dB, relative difference {rel:.2e}")
-    assert rel < 1.5e-2
+    assert rel < 8e-3
     for k in ("1", "97", "497", "993"):
         a, b = ref["loss_curve"].get(k), ours["loss_curve"].get(k)
         if a is not None and b is not None:
-            assert abs(a - b) <= 0.2 * max(a, b), (k, a, b)
+            assert abs(a - b) <= 0.25 * max(a, b), (k, a, b)
     # the controller settles on the same workload
     assert abs(ours["counters"]["rays_per_batch"] - ref["counters"]["rays_per_batch"]) <= 0.15 * ref["counters"]["rays_per_batch"]
 
