@@ -69,9 +69,12 @@ typedef struct ngp_nerf_desc {
 
 typedef enum ngp_activation { NGP_ACT_NONE = 0, NGP_ACT_RELU = 1, NGP_ACT_LOGISTIC = 2, NGP_ACT_EXPONENTIAL = 3 } ngp_activation;
 typedef enum ngp_loss_type { NGP_LOSS_L2 = 0, NGP_LOSS_L1 = 1, NGP_LOSS_MAPE = 2, NGP_LOSS_SMAPE = 3, NGP_LOSS_HUBER = 4, NGP_LOSS_LOGL1 = 5, NGP_LOSS_RELATIVE_L2 = 6 } ngp_loss_type;
-/* ETrainMode (common.h:47-51).  Rfl / RflRelax change only how the per-sample gradients are formed from the composited ray
- * (fused_kernels/train_nerf.cuh:391-410): Rfl supervises every sample's colour with the radiance-field loss, RflRelax evaluates
- * the loss gradient at the colour the ray would have if the medium behind the sample were opaque. */
+/* ETrainMode (common.h:47-51).  Rfl / RflRelax are what the reference runs through its fused train_nerf kernel: they change how the
+ * per-sample gradients are formed from the composited ray (fused_kernels/train_nerf.cuh:391-410) — Rfl supervises every sample's colour
+ * with the radiance-field loss, RflRelax evaluates the loss gradient at the colour the ray would have if the medium behind the sample
+ * were opaque — and they composite with that kernel's arithmetic: transmittance = 1 - accumulated weight (:228-230, 363-367), the
+ * background shows through unless the ray is opaque (:251), no L1 term on the density (:305).  Nerf is the non-fused kernels' arithmetic
+ * (testbed_nerf.cu:926-1140). */
 typedef enum ngp_train_mode { NGP_TRAIN_NERF = 0, NGP_TRAIN_RFL = 1, NGP_TRAIN_RFL_RELAX = 2 } ngp_train_mode;
 /* Arithmetic flavour of the training-ray march (ngp_nerf_generate_training_samples):
  *   NGP_MATH_DETERMINISTIC  IEEE add / mul / fma only, transcendentals from ngp_detmath.h, no contraction: what the CPU oracle reproduces
@@ -191,9 +194,11 @@ int ngp_nerf_inference(const ngp_nerf_desc* d, void* stream, uint32_t n, const f
  * numsteps[2*r] = (count, base) for r < counters->n_rays, their samples evaluated in order, 8 at a time, until the ray is
  * exhausted or its transmittance drops below 1e-4 (testbed_nerf.cu:926-929).  out rows that are evaluated are bit-identical
  * to ngp_nerf_inference(out_stride = 4); rows that the loss kernel never reads are left untouched.
- * queue: a zeroed device uint32 (work-queue head).  n_rays_max bounds the launch (>= counters->n_rays). */
+ * queue: a zeroed device uint32 (work-queue head).  n_rays_max bounds the launch (>= counters->n_rays).  train_mode (ngp_train_mode): whose
+ * transmittance decides where a ray stops — the running product of the loss kernel (Nerf) or one minus the accumulated weight of the fused
+ * train kernel (Rfl, RflRelax; fused_kernels/train_nerf.cuh:228-238); ngp_nerf_compute_loss follows the same rule. */
 int ngp_nerf_inference_rays(const ngp_nerf_desc* d, void* stream, uint32_t n_rays_max, const ngp_nerf_counters* counters_dev, uint32_t* queue_dev,
-	const uint32_t* numsteps, const float* coords, const void* params_fp16, uint32_t density_activation, void* out_fp16);
+	const uint32_t* numsteps, const float* coords, const void* params_fp16, uint32_t density_activation, void* out_fp16, uint32_t train_mode);
 
 /* ≙ NerfNetwork::density (nerf_network.h:270-280): hash grid + density MLP only. positions: n x pos_stride floats
  * (NerfPosition, pos_stride >= 3), out: n halves (raw density). */

@@ -177,7 +177,7 @@ PROTOTYPES = {
     "ngp_march_consts_init": (C.c_int, [P(MarchConsts), f32]),
     "ngp_nerf_init_params_host": (C.c_int, [P(NerfDesc), u64, vp]),
     "ngp_nerf_inference": (C.c_int, [P(NerfDesc), vp, u32, vp, vp, vp, u32]),
-    "ngp_nerf_inference_rays": (C.c_int, [P(NerfDesc), vp, u32, vp, vp, vp, vp, vp, u32, vp]),
+    "ngp_nerf_inference_rays": (C.c_int, [P(NerfDesc), vp, u32, vp, vp, vp, vp, vp, u32, vp, u32]),
     "ngp_nerf_density": (C.c_int, [P(NerfDesc), vp, u32, vp, u32, vp, vp]),
     "ngp_nerf_forward_backward": (C.c_int, [P(NerfDesc), vp, u32, vp, vp, vp, vp, vp]),
     "ngp_grid_encode": (C.c_int, [P(GridDesc), vp, u32, vp, u32, vp, vp]),

@@ -114,6 +114,20 @@ __device__ __forceinline__ SampleTerms sample_terms(const __half* __restrict__ n
 // (k_compute_loss<LOSS_PASS1>) composites every ray and records its sample count under its local ray index, k_compaction_order hands
 // out the slots along cfg.compaction_order, pass 2 (k_compute_loss<LOSS_PASS2>) writes gradients and compacted coordinates.
 enum LossMode : uint32_t { LOSS_FUSED = 0, LOSS_PASS1 = 1, LOSS_PASS2 = 2 };
+// One compositing step: returns the sample's weight and advances the transmittance.  The reference has two forms of the same quantity:
+// its loss kernel keeps T as a running product (testbed_nerf.cu:946, 1095), its fused train_nerf kernel — the one the Rfl / RflRelax
+// train modes run through — as one minus the accumulated weight (fused_kernels/train_nerf.cuh:228-230, 363-367).  They differ by rounding,
+// which decides where `T < 1e-4` falls, so each train mode gets its kernel's form (`accumulated` is the weight sum of the second form).
+__device__ __forceinline__ float composite_step(const bool weight_sum_form, const float alpha, float& T, float& accumulated) {
+	const float weight = alpha * T;
+	if (weight_sum_form) {
+		accumulated += weight;
+		T = 1.0f - accumulated;
+	} else {
+		T *= (1.0f - alpha);
+	}
+	return weight;
+}
 struct LossRayScratch {   // pass 1 -> pass 2, one per ray slot
 	float rgb_ray[3];
 	float loss_bg[3];
@@ -229,8 +243,9 @@ __global__ void __launch_bounds__(128) k_compute_loss(
 			target = bg;
 		}
 	}
-	// ---- pass 1: composite front to back until T < EPSILON (testbed_nerf.cu:926-948)
-	float T = 1.0f;
+	// ---- pass 1: composite front to back until T < EPSILON (testbed_nerf.cu:926-948; train_nerf.cuh:176-238 for the Rfl modes)
+	const bool rtc = cfg.train_mode != NGP_TRAIN_NERF;   // the arithmetic of the reference's fused train_nerf kernel
+	float T = 1.0f, acc = 0.0f;
 	V3 rgb_ray{0, 0, 0}, loss_bg{0, 0, 0};
 	uint32_t compacted_numsteps = 0;
 	bool stopped = false;
@@ -253,9 +268,8 @@ __global__ void __launch_bounds__(128) k_compute_loss(
 			}
 			const float a = __shfl_sync(0xFFFFFFFFu, st.alpha, j);
 			const float r = __shfl_sync(0xFFFFFFFFu, st.r, j), g = __shfl_sync(0xFFFFFFFFu, st.g, j), b = __shfl_sync(0xFFFFFFFFu, st.b, j);
-			const float weight = a * T;
+			const float weight = composite_step(rtc, a, T, acc);
 			rgb_ray = rgb_ray + weight * V3{r, g, b};
-			T *= (1.0f - a);
 			++compacted_numsteps;
 			if (cfg.train_mode == NGP_TRAIN_RFL) {
 				// train_nerf.cuh:231: the ray's accumulated per-sample radiance-field loss
@@ -268,7 +282,8 @@ __global__ void __launch_bounds__(128) k_compute_loss(
 		}
 	}
 
-	if (MODE != LOSS_PASS2 && compacted_numsteps == numsteps) {
+	// the background shows through: when every sample was read (loss kernel, :950) / when the ray is not opaque yet (train_nerf.cuh:251)
+	if (MODE != LOSS_PASS2 && (rtc ? !(T < EPSILON) : compacted_numsteps == numsteps)) {
 		rgb_ray = rgb_ray + T * bg;
 		if (cfg.train_mode == NGP_TRAIN_RFL) {   // train_nerf.cuh:251-254
 			float l0, l1, l2, gd;
@@ -317,13 +332,14 @@ __global__ void __launch_bounds__(128) k_compute_loss(
 
 	const float loss_scale = cfg.loss_scale / (float)n_rays_global;
 	const float output_l2_reg = cfg.rgb_activation == NGP_ACT_EXPONENTIAL ? 1e-4f : 0.0f;
-	const float output_l1_reg_density = *mean_density_ptr < min_optical_thickness() ? 1e-4f : 0.0f;
+	const float output_l1_reg_density = (!rtc && *mean_density_ptr < min_optical_thickness()) ? 1e-4f : 0.0f;   // train_nerf.cuh:305 has it switched off
 
 	// ---- pass 2: gradients and compaction (testbed_nerf.cu:1078-1140)
 	float* co = coords_out + (size_t)compacted_base * 7;
 	__half* dl = dloss_out + (size_t)compacted_base * 4;
 	V3 rgb_ray2{0, 0, 0}, loss_bg2{0, 0, 0};
 	T = 1.0f;
+	acc = 0.0f;
 	for (uint32_t c0 = 0; c0 < compacted_numsteps; c0 += 32) {
 		const uint32_t k = c0 + lane;
 		const bool mine = k < compacted_numsteps;
@@ -351,9 +367,8 @@ __global__ void __launch_bounds__(128) k_compute_loss(
 		for (uint32_t j = 0; j < n_here; ++j) {
 			const float a = __shfl_sync(0xFFFFFFFFu, st.alpha, j);
 			const float r = __shfl_sync(0xFFFFFFFFu, st.r, j), g = __shfl_sync(0xFFFFFFFFu, st.g, j), b = __shfl_sync(0xFFFFFFFFu, st.b, j);
-			const float weight = a * T;
+			const float weight = composite_step(rtc, a, T, acc);
 			rgb_ray2 = rgb_ray2 + weight * V3{r, g, b};
-			T *= (1.0f - a);
 			if (cfg.train_mode == NGP_TRAIN_RFL) {
 				const V3 ll{__shfl_sync(0xFFFFFFFFu, my_ll.x, j), __shfl_sync(0xFFFFFFFFu, my_ll.y, j), __shfl_sync(0xFFFFFFFFu, my_ll.z, j)};
 				loss_bg2 = loss_bg2 + weight * ll;

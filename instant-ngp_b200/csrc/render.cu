@@ -439,7 +439,7 @@ constexpr uint32_t FWD_RAYS_CTAS_PER_SM = 3;   // measured: 3 -> 0.249 ms, 4 -> 
 template <uint32_t F, uint32_t RAY_CHUNK>
 __global__ void __launch_bounds__(TILE, FWD_RAYS_CTAS_PER_SM) k_nerf_forward_rays(
 	const __grid_constant__ NetDev net, const ngp_nerf_counters* __restrict__ counters, uint32_t* __restrict__ queue, const uint32_t* __restrict__ numsteps,
-	const float* __restrict__ coords, const __half* __restrict__ params, const uint32_t density_activation, __half* __restrict__ out
+	const float* __restrict__ coords, const __half* __restrict__ params, const uint32_t density_activation, __half* __restrict__ out, const bool weight_sum_form
 ) {
 	extern __shared__ __align__(128) uint8_t smem[];
 	const FwdSmem L = fwd_smem_layout(net.n_hidden_density, net.n_hidden_rgb);
@@ -472,7 +472,7 @@ __global__ void __launch_bounds__(TILE, FWD_RAYS_CTAS_PER_SM) k_nerf_forward_ray
 	// slot state, replicated in the 8 lanes of the slot
 	bool have_ray = false, queue_empty = false;
 	uint32_t n = 0, base = 0, k0 = 0;
-	float T = 1.0f;
+	float T = 1.0f, acc = 0.0f;   // `acc`: the accumulated weight of the fused train kernel's form of T (composite_step, march.cu)
 	const float EPSILON = 1e-4f;
 
 	for (;;) {
@@ -494,6 +494,7 @@ __global__ void __launch_bounds__(TILE, FWD_RAYS_CTAS_PER_SM) k_nerf_forward_ray
 					base = numsteps[r * 2 + 1];
 					k0 = 0;
 					T = 1.0f;
+					acc = 0.0f;
 					have_ray = n > 0;
 				}
 			}
@@ -559,7 +560,12 @@ __global__ void __launch_bounds__(TILE, FWD_RAYS_CTAS_PER_SM) k_nerf_forward_ray
 				if (k0 + j >= n) { done = true; continue; }
 				// the loss kernel reads sample k0+j only if T >= EPSILON before it; it was evaluated above either way
 				if (T < EPSILON) { done = true; continue; }
-				T *= (1.0f - a);
+				if (weight_sum_form) {
+					acc += a * T;
+					T = 1.0f - acc;
+				} else {
+					T *= (1.0f - a);
+				}
 			}
 			k0 += RAY_CHUNK;
 			if (done || k0 >= n || T < EPSILON) have_ray = false;
@@ -576,7 +582,7 @@ __global__ void __launch_bounds__(TILE, FWD_RAYS_CTAS_PER_SM) k_nerf_forward_ray
 // queue: a zeroed u32 (the `pad` word of the step's counter block).  Grid sized for the worst case (n_rays_max rays).
 template <uint32_t F, uint32_t CHUNK>
 static void launch_forward_rays(const NetDev& net, cudaStream_t stream, uint32_t n_rays_max, const ngp_nerf_counters* counters, uint32_t* queue,
-	const uint32_t* numsteps, const float* coords, const __half* params, uint32_t density_activation, __half* out) {
+	const uint32_t* numsteps, const float* coords, const __half* params, uint32_t density_activation, __half* out, bool weight_sum_form) {
 	const FwdSmem L = fwd_smem_layout(net.n_hidden_density, net.n_hidden_rgb);
 	const uint32_t n_tiles = div_round_up(n_rays_max, TILE / CHUNK);
 	const uint32_t max_ctas = (uint32_t)device_sm_count() * FWD_RAYS_CTAS_PER_SM;
@@ -584,18 +590,19 @@ static void launch_forward_rays(const NetDev& net, cudaStream_t stream, uint32_t
 	auto kern = k_nerf_forward_rays<F, CHUNK>;
 	static bool attr = false;
 	if (!attr) { NGPB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); attr = true; }
-	kern<<<grid, TILE, L.total, stream>>>(net, counters, queue, numsteps, coords, params, density_activation, out);
+	kern<<<grid, TILE, L.total, stream>>>(net, counters, queue, numsteps, coords, params, density_activation, out, weight_sum_form);
 	NGPB_LAUNCHED();
 	NGPB_CUDA_CHECK(cudaGetLastError());
 }
 
 // chunk: consecutive samples of a ray evaluated per tensor-core tile (4, 8, 16 or 32; 128 / chunk ray slots per CTA)
+// train_mode: whose form of the transmittance decides where a ray stops (composite_step, march.cu): the loss kernel's or the fused train kernel's
 void nerf_inference_rays(const ngp_nerf_desc& d, cudaStream_t stream, uint32_t n_rays_max, const ngp_nerf_counters* counters, uint32_t* queue,
-	const uint32_t* numsteps, const float* coords, const __half* params, uint32_t density_activation, __half* out, uint32_t chunk) {
+	const uint32_t* numsteps, const float* coords, const __half* params, uint32_t density_activation, __half* out, uint32_t chunk, uint32_t train_mode) {
 	if (n_rays_max == 0) return;
 	NGPB_CHECK(chunk == 4 || chunk == 8 || chunk == 16 || chunk == 32, "inference chunk must be 4, 8, 16 or 32");
 	const NetDev net = make_netdev(d);
-#define NGPB_FWD_RAYS(FF, CC) launch_forward_rays<FF, CC>(net, stream, n_rays_max, counters, queue, numsteps, coords, params, density_activation, out)
+#define NGPB_FWD_RAYS(FF, CC) launch_forward_rays<FF, CC>(net, stream, n_rays_max, counters, queue, numsteps, coords, params, density_activation, out, train_mode != NGP_TRAIN_NERF)
 	if (net.n_features == 2) {
 		if (chunk == 4) NGPB_FWD_RAYS(2, 4); else if (chunk == 8) NGPB_FWD_RAYS(2, 8); else if (chunk == 16) NGPB_FWD_RAYS(2, 16); else NGPB_FWD_RAYS(2, 32);
 	} else {

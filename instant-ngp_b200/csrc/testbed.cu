@@ -25,7 +25,7 @@ void set_last_error(const std::string& msg) { g_last_error = msg; }
 void nerf_inference(const ngp_nerf_desc& d, cudaStream_t stream, uint32_t n, const float* coords, const __half* params, __half* out, uint32_t out_stride);
 void nerf_inference_counted(const ngp_nerf_desc& d, cudaStream_t stream, uint32_t n_max, const uint32_t* n_dev, const float* coords, const __half* params, __half* out);
 void nerf_inference_rays(const ngp_nerf_desc& d, cudaStream_t stream, uint32_t n_rays_max, const ngp_nerf_counters* counters, uint32_t* queue,
-	const uint32_t* numsteps, const float* coords, const __half* params, uint32_t density_activation, __half* out, uint32_t chunk);
+	const uint32_t* numsteps, const float* coords, const __half* params, uint32_t density_activation, __half* out, uint32_t chunk, uint32_t train_mode);
 void nerf_density(const ngp_nerf_desc& d, cudaStream_t stream, uint32_t n, const float* positions, uint32_t pos_stride, const __half* params, __half* out);
 void grid_encode(const ngp_grid_desc& g, cudaStream_t stream, uint32_t n, const float* positions, uint32_t pos_stride, const __half* grid, __half* out);
 void nerf_forward_backward(const ngp_nerf_desc& d, cudaStream_t stream, uint32_t n, const float* coords, const __half* params, const __half* dL_dout,
@@ -625,7 +625,7 @@ static void tb_front(ngp_testbed* t, uint32_t batch) {
 		} else {
 			// evaluate, ray by ray, only the samples the loss kernel will read (bit-identical outputs for those)
 			nerf_inference_rays(t->desc, t->stream, rays_local, rs.counters.p, &rs.counters.p->pad, rs.numsteps.p, rs.coords.p, t->params.p,
-				t->cfg.density_activation, t->mlp_out.p, tb_inference_chunk(t));
+				t->cfg.density_activation, t->mlp_out.p, tb_inference_chunk(t), t->cfg.train_mode);
 		}
 	}
 	{
@@ -805,9 +805,9 @@ int ngp_nerf_inference(const ngp_nerf_desc* d, void* stream, uint32_t n, const f
 	NGPB_TRY(require_device(); nerf_inference(*d, (cudaStream_t)stream, n, coords, (const __half*)params, (__half*)out, out_stride));
 }
 int ngp_nerf_inference_rays(const ngp_nerf_desc* d, void* stream, uint32_t n_rays_max, const ngp_nerf_counters* counters, uint32_t* queue, const uint32_t* numsteps,
-	const float* coords, const void* params, uint32_t density_activation, void* out) {
+	const float* coords, const void* params, uint32_t density_activation, void* out, uint32_t train_mode) {
 	NGPB_TRY(require_device(); nerf_inference_rays(*d, (cudaStream_t)stream, n_rays_max, counters, queue, numsteps, coords, (const __half*)params, density_activation,
-		(__half*)out, 8));
+		(__half*)out, 8, train_mode));
 }
 int ngp_nerf_density(const ngp_nerf_desc* d, void* stream, uint32_t n, const float* positions, uint32_t pos_stride, const void* params, void* out) {
 	NGPB_TRY(require_device(); nerf_density(*d, (cudaStream_t)stream, n, positions, pos_stride, (const __half*)params, (__half*)out));

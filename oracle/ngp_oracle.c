@@ -472,7 +472,8 @@ static void loss_and_gradient1(float target, float pred, uint32_t type, float* l
 }
 
 /* ------------------------------------------------------------------------------------------------------------------
- * compute_loss_kernel_train_nerf (src/testbed_nerf.cu:852-1180) — Nerf mode, no envmap / depth / exposure / error map.
+ * compute_loss_kernel_train_nerf (src/testbed_nerf.cu:852-1180) — no envmap / depth / exposure / error map; train modes Rfl / RflRelax with the
+ * gradient forms and the compositing arithmetic of the fused kernel they run through in the reference (fused_kernels/train_nerf.cuh:176-420).
  * network_output: n_samples x 4 binary16 values (rgb raw x3, density raw).  Rays are visited in slot order, compacted
  * slots are handed out in that order.  Returns the (unclamped) compacted sample count.
  * ---------------------------------------------------------------------------------------------------------------- */
@@ -488,6 +489,10 @@ EXPORT uint32_t orc_compute_loss(uint32_t n_rays_kept, uint32_t n_rays_global, u
 		const uint16_t* no = network_output + (size_t)base * 4;
 		float T = 1.f;
 		const float EPSILON = 1e-4f;
+		/* Rfl / RflRelax: the fused train_nerf kernel's compositing (fused_kernels/train_nerf.cuh:228-238, 251, 305, 363-367):
+		 * transmittance = 1 - accumulated weight, background unless opaque, no L1 term on the density */
+		const int rtc = cfg->train_mode != NGP_TRAIN_NERF;
+		float acc = 0.f;
 		v3 rgb_ray = V(0, 0, 0);
 		uint32_t compacted_numsteps = 0;
 		v3 ray_o = V(rays_in[(size_t)i * 6], rays_in[(size_t)i * 6 + 1], rays_in[(size_t)i * 6 + 2]);
@@ -501,7 +506,7 @@ EXPORT uint32_t orc_compute_loss(uint32_t n_rays_kept, uint32_t n_rays_global, u
 			float alpha = 1.f - ngp_expf(-density * dt);
 			float weight = alpha * T;
 			rgb_ray = vadd(rgb_ray, vscale(rgb, weight));
-			T *= (1.f - alpha);
+			if (rtc) { acc += weight; T = 1.f - acc; } else T *= (1.f - alpha);
 		}
 		uint32_t ray_idx = ray_indices_in[i];
 		pcg32_t rng = {rng_state, rng_inc};
@@ -530,11 +535,12 @@ EXPORT uint32_t orc_compute_loss(uint32_t n_rays_kept, uint32_t n_rays_global, u
 			} else target = bg;
 		}
 		const float T_end = T;
-		if (compacted_numsteps == numsteps) rgb_ray = vadd(rgb_ray, vscale(bg, T));
+		const int background_shows = rtc ? !(T < EPSILON) : (compacted_numsteps == numsteps);
+		if (background_shows) rgb_ray = vadd(rgb_ray, vscale(bg, T));
 		/* Rfl (train_nerf.cuh:231, 251-254): the ray's accumulated per-sample loss, background term included */
 		v3 loss_bg = V(0, 0, 0);
 		if (cfg->train_mode == NGP_TRAIN_RFL) {
-			float Tq = 1.f;
+			float Tq = 1.f, accq = 0.f;
 			for (uint32_t q = 0; q < compacted_numsteps; ++q) {
 				const uint16_t* o = no + (size_t)q * 4;
 				v3 rgb = V(network_to_rgb(half_to_float(o[0]), cfg->rgb_activation), network_to_rgb(half_to_float(o[1]), cfg->rgb_activation),
@@ -542,14 +548,15 @@ EXPORT uint32_t orc_compute_loss(uint32_t n_rays_kept, uint32_t n_rays_global, u
 				float dt = unwarp_dt(ci[(size_t)q * 7 + 3]);
 				float alpha = 1.f - ngp_expf(-network_to_density(half_to_float(o[3]), cfg->density_activation) * dt);
 				float weight = alpha * Tq;
-				Tq *= (1.f - alpha);
+				accq += weight;
+				Tq = 1.f - accq;   /* Rfl is an rtc mode */
 				float l0, l1, l2, gdummy;
 				loss_and_gradient1(target.x, rgb.x, cfg->loss_type, &l0, &gdummy);
 				loss_and_gradient1(target.y, rgb.y, cfg->loss_type, &l1, &gdummy);
 				loss_and_gradient1(target.z, rgb.z, cfg->loss_type, &l2, &gdummy);
 				loss_bg = vadd(loss_bg, vscale(V(l0, l1, l2), weight));
 			}
-			if (compacted_numsteps == numsteps) {
+			if (background_shows) {
 				float l0, l1, l2, gdummy;
 				loss_and_gradient1(target.x, bg.x, cfg->loss_type, &l0, &gdummy);
 				loss_and_gradient1(target.y, bg.y, cfg->loss_type, &l1, &gdummy);
@@ -576,12 +583,13 @@ EXPORT uint32_t orc_compute_loss(uint32_t n_rays_kept, uint32_t n_rays_global, u
 
 		float loss_scale = cfg->loss_scale / (float)n_rays_global;
 		const float output_l2_reg = cfg->rgb_activation == NGP_ACT_EXPONENTIAL ? 1e-4f : 0.0f;
-		const float output_l1_reg_density = mean_density < MIN_OPTICAL_THICKNESS ? 1e-4f : 0.0f;
+		const float output_l1_reg_density = (!rtc && mean_density < MIN_OPTICAL_THICKNESS) ? 1e-4f : 0.0f;
 		float* co = coords_out + (size_t)compacted_base * 7;
 		uint16_t* dl = dloss_out + (size_t)compacted_base * 4;
 		v3 rgb_ray2 = V(0, 0, 0);
 		v3 loss_bg2 = V(0, 0, 0);
 		T = 1.f;
+		acc = 0.f;
 		for (uint32_t j = 0; j < compacted_numsteps; ++j) {
 			const float* c = ci + (size_t)j * 7;
 			for (int k = 0; k < 7; ++k) co[(size_t)j * 7 + k] = c[k];
@@ -595,7 +603,7 @@ EXPORT uint32_t orc_compute_loss(uint32_t n_rays_kept, uint32_t n_rays_global, u
 			float alpha = 1.f - ngp_expf(-density * dt);
 			float weight = alpha * T;
 			rgb_ray2 = vadd(rgb_ray2, vscale(rgb, weight));
-			T *= (1.f - alpha);
+			if (rtc) { acc += weight; T = 1.f - acc; } else T *= (1.f - alpha);
 			v3 suffix = vsub(rgb_ray, rgb_ray2);
 			v3 dloss_by_drgb = vscale(g, weight);
 			float dmlp_inner = 0.0f;   /* the bracket that multiplies density_derivative * dt (train_nerf.cuh:391-410) */

@@ -355,8 +355,8 @@ def test_density_grid_update_matches_oracle(lib, aabb_scale):
         assert (grid_w < 0).sum() > 0  # voxels no camera sees were culled at step 0
 
 
-@pytest.mark.parametrize("scene", SCENES[:2])
-def test_ray_ordered_inference_equals_full_inference_where_the_loss_reads(lib, scene):
+@pytest.mark.parametrize("scene,train_mode", [(SCENES[0], 0), (SCENES[1], 0), (SCENES[1], 2)])
+def test_ray_ordered_inference_equals_full_inference_where_the_loss_reads(lib, scene, train_mode):
     """the early-terminating inference pass (k_nerf_forward_rays) writes, for every ray, exactly the rows the loss kernel
     consumes, bit-identical to the evaluate-everything pass of the reference schedule"""
     import torch
@@ -364,6 +364,7 @@ def test_ray_ordered_inference_equals_full_inference_where_the_loss_reads(lib, s
     n_rays, max_samples = 4096, 4096 * 1024
     want, got, ctx = run_generator(lib, scene, n_rays, max_samples)
     cfg = ctx["cfg"]
+    cfg.train_mode = train_mode   # Rfl / RflRelax stop a ray on the fused train kernel's form of the transmittance (1 - accumulated weight)
     k, ns = got["n_kept"], got["n_samples"]
     d, L = util.make_desc(n_levels=16, F=2, log2_T=16, aabb_scale=scene["aabb_scale"])
     rng = np.random.default_rng(77)
@@ -379,7 +380,7 @@ def test_ray_ordered_inference_equals_full_inference_where_the_loss_reads(lib, s
     rays_out = torch.full((ns, 4), float("nan"), dtype=torch.float16, device="cuda")
     queue = torch.zeros(1, dtype=torch.int32, device="cuda")
     assert lib.ngp_nerf_inference_rays(C.byref(d), stream(), n_rays, dv["cnt"].data_ptr(), queue.data_ptr(), dv["ns"].data_ptr(), dv["co"].data_ptr(), t_p.data_ptr(),
-                                       cfg.density_activation, rays_out.data_ptr()) == 0, lib.ngp_last_error()
+                                       cfg.density_activation, rays_out.data_ptr(), cfg.train_mode) == 0, lib.ngp_last_error()
     # run the loss kernel on the FULL outputs to learn what it consumes
     batch = 1 << int(np.ceil(np.log2(max(ns, 2))))
     t_coc = torch.zeros(batch, 7, dtype=torch.float32, device="cuda")
