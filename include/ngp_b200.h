@@ -143,6 +143,10 @@ typedef struct ngp_nerf_train_cfg {
 	                               after every fully occupied round); 0 = library default.  Schedule only */
 	uint32_t compaction_order;  /* ngp_compaction_order: the order in which rays take their slots in the compacted batch, i.e. which rays are cut when
 	                               a step's samples exceed the batch and which are repeated when they fall short.  A ray's gradients do not depend on it */
+	const float* cam_exposure;      /* per-image exposure, 3 floats per training view: the view's colour is multiplied by 2^exposure per channel before it
+	                                   becomes the ray's target (testbed_nerf.cu:979-995).  Device memory (host memory for the oracle); NULL = none */
+	float* cam_exposure_gradient;   /* 3 floats per view, accumulated by the loss kernel with atomics (testbed_nerf.cu:1142-1155: the reference's
+	                                   expression, which leaves out the pixel colour); NULL = exposure is not being optimised */
 } ngp_nerf_train_cfg;
 
 /* Counters written by the training sample generator / loss kernel (NerfCounters, testbed.h). */
@@ -430,6 +434,11 @@ int ngp_testbed_reset(ngp_testbed* t, int reset_density_grid);
 /* one training view as held by the Testbed (what set_camera_to_training_view reads, src/testbed.cu:486-505) */
 int ngp_testbed_get_view(ngp_testbed* t, uint32_t idx, ngp_train_view* out);
 int ngp_testbed_set_option(ngp_testbed* t, const char* name, double value); /* nerf.training.* knobs by name */
+/* Per-image exposure in stops per colour channel (Nerf::Training::cam_exposure, testbed.h:774): optimised while the option
+ * nerf.training.optimize_exposure is on (testbed_nerf.cu:2962-3000), applied to the view's colour by the loss kernel (:979).  Setting a value
+ * starts that image's optimizer state afresh. */
+int ngp_testbed_get_camera_exposure(ngp_testbed* t, uint32_t idx, float* rgb_out);
+int ngp_testbed_set_camera_exposure(ngp_testbed* t, uint32_t idx, const float* rgb);
 double ngp_testbed_get_option(ngp_testbed* t, const char* name);
 /* Testbed::train(batch_size): density-grid prep on the reference's schedule, one training step, optimizer step. */
 int ngp_testbed_train(ngp_testbed* t, uint32_t batch_size);

@@ -111,6 +111,8 @@ class NerfTrainCfg(C.Structure):
         ("gen_walk_empty", C.c_uint32),
         ("gen_speculation", C.c_uint32),
         ("compaction_order", C.c_uint32),
+        ("cam_exposure", C.c_void_p),
+        ("cam_exposure_gradient", C.c_void_p),
     ]
 
 
@@ -204,6 +206,8 @@ PROTOTYPES = {
     "ngp_testbed_reset": (C.c_int, [vp, C.c_int]),
     "ngp_testbed_get_view": (C.c_int, [vp, u32, P(TrainView)]),
     "ngp_testbed_set_option": (C.c_int, [vp, cp, C.c_double]),
+    "ngp_testbed_get_camera_exposure": (C.c_int, [vp, u32, vp]),
+    "ngp_testbed_set_camera_exposure": (C.c_int, [vp, u32, vp]),
     "ngp_testbed_get_option": (C.c_double, [vp, cp]),
     "ngp_testbed_train": (C.c_int, [vp, u32]),
     "ngp_set_scatter_aggregation": (None, [C.c_int]),

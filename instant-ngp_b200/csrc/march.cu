@@ -226,7 +226,16 @@ __global__ void __launch_bounds__(128) k_compute_loss(
 		bg.z = rng.next_float();
 	}
 	bg = V3{srgb_to_linear(bg.x), srgb_to_linear(bg.y), srgb_to_linear(bg.z)};
-	const Rgba tex = read_rgba_uv(u, v, vw->width, vw->height, vw->pixels, vw->image_type);
+	Rgba tex = read_rgba_uv(u, v, vw->width, vw->height, vw->pixels, vw->image_type);
+	// per-image exposure (testbed_nerf.cu:979): the view's colour times 2^exposure, channel by channel
+	V3 exposure_scale{1.0f, 1.0f, 1.0f};
+	if (cfg.cam_exposure) {
+		exposure_scale = V3{ngp_expf(0.6931471805599453f * cfg.cam_exposure[img * 3 + 0]), ngp_expf(0.6931471805599453f * cfg.cam_exposure[img * 3 + 1]),
+			ngp_expf(0.6931471805599453f * cfg.cam_exposure[img * 3 + 2])};
+		tex.r = exposure_scale.x * tex.r;
+		tex.g = exposure_scale.y * tex.g;
+		tex.b = exposure_scale.z * tex.b;
+	}
 	V3 target;
 	if (cfg.linear_colors || cfg.color_space == NGP_COLOR_LINEAR) {
 		target = V3{tex.r + (1.0f - tex.a) * bg.x, tex.g + (1.0f - tex.a) * bg.y, tex.b + (1.0f - tex.a) * bg.z};
@@ -333,6 +342,19 @@ __global__ void __launch_bounds__(128) k_compute_loss(
 	const float loss_scale = cfg.loss_scale / (float)n_rays_global;
 	const float output_l2_reg = cfg.rgb_activation == NGP_ACT_EXPONENTIAL ? 1e-4f : 0.0f;
 	const float output_l1_reg_density = (!rtc && *mean_density_ptr < min_optical_thickness()) ? 1e-4f : 0.0f;   // train_nerf.cuh:305 has it switched off
+
+	// ---- the gradient with respect to the view's exposure (testbed_nerf.cu:1142-1155), once per ray that keeps samples
+	if (cfg.cam_exposure_gradient && lane == 0) {
+		V3 dloss_by_dgt{-lg_grad.x, -lg_grad.y, -lg_grad.z};   // "assume symmetric loss"; uv_pdf == 1
+		if (!cfg.linear_colors) {
+			dloss_by_dgt = V3{dloss_by_dgt.x / srgb_to_linear_derivative(target.x), dloss_by_dgt.y / srgb_to_linear_derivative(target.y),
+				dloss_by_dgt.z / srgb_to_linear_derivative(target.z)};
+		}
+		float* eg = cfg.cam_exposure_gradient + (size_t)img * 3;
+		atomicAdd(eg + 0, ((loss_scale * dloss_by_dgt.x) * exposure_scale.x) * 0.6931471805599453f);
+		atomicAdd(eg + 1, ((loss_scale * dloss_by_dgt.y) * exposure_scale.y) * 0.6931471805599453f);
+		atomicAdd(eg + 2, ((loss_scale * dloss_by_dgt.z) * exposure_scale.z) * 0.6931471805599453f);
+	}
 
 	// ---- pass 2: gradients and compaction (testbed_nerf.cu:1078-1140)
 	float* co = coords_out + (size_t)compacted_base * 7;

@@ -185,6 +185,8 @@ __host__ __device__ inline float network_to_density_derivative(float v, uint32_t
 
 // ---- colour (common_device.cuh:61-103) -------------------------------------------------------------------------------
 __host__ __device__ inline float srgb_to_linear(float s) { return s <= 0.04045f ? s / 12.92f : ngp_powf((s + 0.055f) / 1.055f, 2.4f); }
+// common_device.cuh:71-77
+__host__ __device__ inline float srgb_to_linear_derivative(float s) { return s <= 0.04045f ? 1.0f / 12.92f : 2.4f / 1.055f * ngp_powf((s + 0.055f) / 1.055f, 1.4f); }
 __host__ __device__ inline float linear_to_srgb(float l) { return l < 0.0031308f ? 12.92f * l : 1.055f * ngp_powf(l, 0.41666f) - 0.055f; }
 
 // warp helpers (nerf_device.cuh:266-315)

@@ -213,6 +213,15 @@ struct ngp_testbed {
 	uint32_t rays_per_batch = 1u << 12, measured_batch_size = 0, measured_batch_size_before_compaction = 0, n_rays_total = 0;
 	float loss_scalar = 0.0f;
 	bool shall_train = true;
+	// per-image exposure optimisation (Nerf::Training::optimize_exposure, testbed_nerf.cu:2962-3000): one host-side Adam per image
+	// (AdamOptimizer<vec3>, adam_optimizer.h:129-152: lr 1e-3 replaced by the network optimizer's, eps 1e-8, betas 0.9 / 0.99)
+	struct ExposureAdam { float variable[3] = {0, 0, 0}, first_moment[3] = {0, 0, 0}, second_moment[3] = {0, 0, 0}; uint32_t iter = 0; };
+	bool optimize_exposure = false;
+	float exposure_l2_reg = 0.0f;
+	uint32_t n_steps_between_cam_updates = 16, n_steps_since_cam_update = 0;
+	std::vector<ExposureAdam> cam_exposure;
+	DevBuf<float> cam_exposure_dev, cam_exposure_gradient_dev;
+	bool cam_exposure_nonzero = false;
 
 	// per-step scratch.  Everything the sample generator writes exists twice: while step k trains, the generator of step
 	// k+1 already runs on a side stream into the other set (it depends only on the occupancy bitfield, the RNG and
@@ -428,6 +437,12 @@ static void tb_reset_network(ngp_testbed* t, const Json& config_in) {
 	t->n_rays_total = 0;
 	t->loss_scalar = 0.0f;
 	t->shall_train = true;
+	// reset_camera_extrinsics (src/testbed.cu:4180, testbed_nerf.cu:2215-2227): the per-image exposures start over as well
+	t->cam_exposure.clear();
+	t->cam_exposure_nonzero = false;
+	t->cam_exposure_dev.release();
+	t->cam_exposure_gradient_dev.release();
+	t->n_steps_since_cam_update = 0;
 
 	const uint32_t n_grid = GRID_N_CELLS * (t->cfg.max_cascade + 1);
 	t->density_grid.ensure(GRID_N_CELLS * NGP_NERF_CASCADES);
@@ -570,6 +585,79 @@ static void tb_launch_generator(ngp_testbed* t, cudaStream_t stream, uint32_t se
 		t->bitfield.p, max_inference, rs.counters.p, rs.ray_indices.p, rs.rays.p, rs.numsteps.p, rs.coords.p);
 }
 
+// Per-image exposure (testbed_nerf.cu:979, 1142-1155, 2962-3000).  The loss kernel multiplies a view's colour by 2^exposure and, while
+// `optimize_exposure` is on, accumulates the reference's gradient expression per view; every n_steps_between_cam_updates steps the host
+// takes one Adam step per view with the network optimizer's current learning rate and re-centres the exposures on a zero mean.
+static void tb_exposure_begin_step(ngp_testbed* t) {
+	const uint32_t n = tb_n_views(t);
+	const bool active = t->optimize_exposure || t->cam_exposure_nonzero;
+	if (!active) {
+		t->cfg.cam_exposure = nullptr;
+		t->cfg.cam_exposure_gradient = nullptr;
+		return;
+	}
+	NGPB_CHECK(t->dp_world == 1, "per-image exposure is not exchanged between ranks: optimize_exposure needs a single process");
+	if (t->cam_exposure.size() != t->n_images) {
+		t->cam_exposure.assign(t->n_images, ngp_testbed::ExposureAdam{});
+		t->cam_exposure_nonzero = false;
+		t->cam_exposure_dev.release();
+	}
+	if (t->cam_exposure_dev.n < (size_t)t->n_images * 3) {
+		t->cam_exposure_dev.release();
+		t->cam_exposure_gradient_dev.release();
+		t->cam_exposure_dev.ensure_zeroed((size_t)t->n_images * 3);
+		t->cam_exposure_gradient_dev.ensure_zeroed((size_t)t->n_images * 3);
+		std::vector<float> host((size_t)t->n_images * 3);
+		for (uint32_t i = 0; i < t->n_images; ++i)
+			for (int c = 0; c < 3; ++c) host[(size_t)i * 3 + c] = t->cam_exposure[i].variable[c];
+		NGPB_CUDA_CHECK(cudaMemcpyAsync(t->cam_exposure_dev.p, host.data(), host.size() * sizeof(float), cudaMemcpyHostToDevice, t->stream));
+		NGPB_CUDA_CHECK(cudaStreamSynchronize(t->stream));
+	}
+	t->cfg.cam_exposure = t->cam_exposure_dev.p;
+	t->cfg.cam_exposure_gradient = t->optimize_exposure ? t->cam_exposure_gradient_dev.p : nullptr;
+	// train_nerf (:2731-2735): the accumulators start from zero after every camera update
+	if (t->optimize_exposure && t->n_steps_since_cam_update == 0)
+		NGPB_CUDA_CHECK(cudaMemsetAsync(t->cam_exposure_gradient_dev.p, 0, sizeof(float) * 3 * (size_t)n, t->stream));
+}
+
+// after the optimizer step (train_nerf, :2878-3003)
+static void tb_exposure_end_step(ngp_testbed* t) {
+	t->n_steps_since_cam_update += 1;
+	if (!t->optimize_exposure || t->n_steps_since_cam_update < t->n_steps_between_cam_updates) return;
+	const uint32_t n = tb_n_views(t);
+	std::vector<float> grad((size_t)n * 3);
+	NGPB_CUDA_CHECK(cudaMemcpyAsync(grad.data(), t->cam_exposure_gradient_dev.p, grad.size() * sizeof(float), cudaMemcpyDeviceToHost, t->stream));
+	NGPB_CUDA_CHECK(cudaStreamSynchronize(t->stream));
+	const float per_camera_loss_scale = (float)n / t->cfg.loss_scale / (float)t->n_steps_between_cam_updates;
+	const float learning_rate = t->opt.learning_rate * t->lr_factor;   // m_optimizer->learning_rate(): the nested Adam's, after the decay
+	const float beta1 = 0.9f, beta2 = 0.99f, epsilon = 1e-8f;
+	float mean[3] = {0, 0, 0};
+	for (uint32_t i = 0; i < n; ++i) {
+		ngp_testbed::ExposureAdam& a = t->cam_exposure[i];
+		++a.iter;
+		const float actual_lr = learning_rate * std::sqrt(1.0f - std::pow(beta2, (float)a.iter)) / (1.0f - std::pow(beta1, (float)a.iter));
+		for (int c = 0; c < 3; ++c) {
+			const float g = grad[(size_t)i * 3 + c] * per_camera_loss_scale + a.variable[c] * t->exposure_l2_reg;
+			a.first_moment[c] = beta1 * a.first_moment[c] + (1.0f - beta1) * g;
+			a.second_moment[c] = beta2 * a.second_moment[c] + (1.0f - beta2) * g * g;
+			a.variable[c] -= actual_lr * a.first_moment[c] / (std::sqrt(a.second_moment[c]) + epsilon);
+			mean[c] += a.variable[c];
+		}
+	}
+	for (int c = 0; c < 3; ++c) mean[c] /= (float)n;
+	std::vector<float> host((size_t)t->n_images * 3, 0.0f);
+	for (uint32_t i = 0; i < t->n_images; ++i)
+		for (int c = 0; c < 3; ++c) {
+			if (i < n) t->cam_exposure[i].variable[c] -= mean[c];   // renormalise: zero mean over the training views
+			host[(size_t)i * 3 + c] = t->cam_exposure[i].variable[c];
+		}
+	NGPB_CUDA_CHECK(cudaMemcpyAsync(t->cam_exposure_dev.p, host.data(), host.size() * sizeof(float), cudaMemcpyHostToDevice, t->stream));
+	NGPB_CUDA_CHECK(cudaStreamSynchronize(t->stream));   // `host` goes out of scope
+	t->cam_exposure_nonzero = true;
+	t->n_steps_since_cam_update = 0;
+	tb_invalidate_prefetch(t);
+}
+
 // A training step (train_nerf_step, testbed_nerf.cu:3007-3382 + optimizer_step :2770) is issued in three parts so that a
 // data-parallel caller can put its collectives where they belong and so that the next step's sample generation overlaps them:
 //   front  occupancy-grid upkeep, ray generation (or the prefetched one), ray-ordered inference, loss + compaction.
@@ -590,6 +678,7 @@ static void tb_front(ngp_testbed* t, uint32_t batch) {
 	tb_ensure_step_scratch(t, batch);
 	tb_upload_views(t);
 
+	tb_exposure_begin_step(t);
 	const bool prep = tb_prep_due(t->training_step);
 	if (prep) {
 		tb_invalidate_prefetch(t);  // the bitfield is about to change (a prefetch is never issued for such a step anyway)
@@ -762,6 +851,7 @@ static void tb_apply_grads(ngp_testbed* t) {
 	if (!t->controller_done) tb_update_controller(t);
 	++t->training_step;
 	t->grads_pending = false;
+	tb_exposure_end_step(t);
 	if (t->profiling) {
 		NGPB_CUDA_CHECK(cudaStreamSynchronize(t->stream));  // phase timing wants completed events; only paid while profiling
 		tb_collect_phases(t);
@@ -1067,6 +1157,25 @@ int ngp_testbed_get_view(ngp_testbed* t, uint32_t idx, ngp_train_view* out) {
 		*out = t->views[idx];
 	});
 }
+int ngp_testbed_get_camera_exposure(ngp_testbed* t, uint32_t idx, float* rgb_out) {
+	NGPB_TRY({
+		NGPB_CHECK(idx < t->n_images, "image index out of range");
+		for (int c = 0; c < 3; ++c) rgb_out[c] = idx < t->cam_exposure.size() ? t->cam_exposure[idx].variable[c] : 0.0f;
+	});
+}
+int ngp_testbed_set_camera_exposure(ngp_testbed* t, uint32_t idx, const float* rgb) {
+	NGPB_TRY({
+		NGPB_CHECK(idx < t->n_images, "image index out of range");
+		tb_invalidate_prefetch(t);
+		if (t->cam_exposure.size() != t->n_images) t->cam_exposure.assign(t->n_images, ngp_testbed::ExposureAdam{});
+		ngp_testbed::ExposureAdam a{};   // reset_camera_extrinsics-style: a set value starts a fresh optimizer state (testbed_nerf.cu:2207)
+		for (int c = 0; c < 3; ++c) a.variable[c] = rgb[c];
+		t->cam_exposure[idx] = a;
+		t->cam_exposure_nonzero = true;
+		t->cam_exposure_dev.release();   // re-uploaded by the next training step
+		t->cam_exposure_gradient_dev.release();
+	});
+}
 int ngp_testbed_set_option(ngp_testbed* t, const char* name_c, double value) {
 	NGPB_TRY({
 		tb_invalidate_prefetch(t);
@@ -1096,6 +1205,9 @@ int ngp_testbed_set_option(ngp_testbed* t, const char* name_c, double value) {
 		else if (n == "nerf.training.math_mode") { NGPB_CHECK(value == 0 || value == 1, "math_mode must be 0 (deterministic) or 1 (reference)"); tb_invalidate_prefetch(t); t->cfg.math_mode = (uint32_t)value; }
 		else if (n == "nerf.training.gen_walk_empty") { NGPB_CHECK(value >= 0 && value <= 1024, "gen_walk_empty: 0 (default) .. 1024"); tb_invalidate_prefetch(t); t->cfg.gen_walk_empty = (uint32_t)value; }
 		else if (n == "nerf.training.gen_speculation") { NGPB_CHECK(value >= 0 && value <= 32, "gen_speculation: 0 (default) .. 32"); tb_invalidate_prefetch(t); t->cfg.gen_speculation = (uint32_t)value; }
+		else if (n == "nerf.training.optimize_exposure") { t->optimize_exposure = value != 0; }
+		else if (n == "nerf.training.exposure_l2_reg") { t->exposure_l2_reg = (float)value; }
+		else if (n == "nerf.training.n_steps_between_cam_updates") { NGPB_CHECK(value >= 1 && value <= 65536, "n_steps_between_cam_updates: 1 .. 65536"); t->n_steps_between_cam_updates = (uint32_t)value; }
 		else if (n == "nerf.training.compaction_order") { NGPB_CHECK(value == 0 || value == 1 || value == 2, "compaction_order: 0 (groups of 32 rays, shuffled), 1 (one atomic per ray), 2 (ray order)"); t->cfg.compaction_order = (uint32_t)value; }
 		else if (n == "nerf.training.drop_overflowing_rays") { NGPB_CHECK(value == 0 || value == 1, "drop_overflowing_rays: 0 or 1"); tb_invalidate_prefetch(t); t->drop_overflowing_rays = (uint32_t)value; }
 		else if (n == "nerf.training.gen_lanes_per_ray") { const uint32_t g = (uint32_t)value; NGPB_CHECK(g <= 32 && (g & (g - 1)) == 0, "gen_lanes_per_ray must be 0 or a power of two up to 32"); tb_invalidate_prefetch(t); t->cfg.gen_lanes_per_ray = g; }
@@ -1131,6 +1243,9 @@ double ngp_testbed_get_option(ngp_testbed* t, const char* name_c) {
 	if (n == "nerf.training.gen_lanes_per_ray") return c.gen_lanes_per_ray;
 	if (n == "nerf.training.gen_walk_empty") return c.gen_walk_empty;
 	if (n == "nerf.training.gen_speculation") return c.gen_speculation;
+	if (n == "nerf.training.optimize_exposure") return t->optimize_exposure ? 1.0 : 0.0;
+	if (n == "nerf.training.exposure_l2_reg") return t->exposure_l2_reg;
+	if (n == "nerf.training.n_steps_between_cam_updates") return t->n_steps_between_cam_updates;
 	if (n == "nerf.training.compaction_order") return c.compaction_order;
 	if (n == "nerf.training.drop_overflowing_rays") return t->drop_overflowing_rays;
 	if (n == "render_math") return t->render_math;

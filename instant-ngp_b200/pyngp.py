@@ -89,6 +89,19 @@ class _Training:
     snap_to_pixel_centers = _opt_property("nerf.training.snap_to_pixel_centers", bool)
     near_distance = _opt_property("nerf.training.near_distance", float)
     density_grid_decay = _opt_property("nerf.training.density_grid_decay", float)
+    optimize_exposure = _opt_property("nerf.training.optimize_exposure", bool)       # python_api.cu:791
+    exposure_l2_reg = _opt_property("nerf.training.exposure_l2_reg", float)          # python_api.cu:806
+    n_steps_between_cam_updates = _opt_property("nerf.training.n_steps_between_cam_updates", int)
+
+    def camera_exposure(self, frame_idx: int) -> np.ndarray:
+        """the image's exposure in stops per colour channel (Nerf::Training::cam_exposure[i].variable(), zero-mean over the training views)"""
+        out = np.zeros(3, dtype=np.float32)
+        B.check(B.lib().ngp_testbed_get_camera_exposure(self._tb._h, int(frame_idx), out.ctypes.data))
+        return out
+
+    def set_camera_exposure(self, frame_idx: int, rgb) -> None:
+        v = np.ascontiguousarray(np.broadcast_to(np.asarray(rgb, dtype=np.float32), (3,)))
+        B.check(B.lib().ngp_testbed_set_camera_exposure(self._tb._h, int(frame_idx), v.ctypes.data))
 
     @property
     def loss_type(self) -> LossType:

@@ -269,6 +269,7 @@ EXPORT void orc_uv_to_ray(float u, float v, const ngp_train_view* vw, float* o6)
 
 /* colour (common_device.cuh:61-103) */
 static float srgb_to_linear(float s) { return s <= 0.04045f ? s / 12.92f : ngp_powf((s + 0.055f) / 1.055f, 2.4f); }
+static float srgb_to_linear_derivative(float s) { return s <= 0.04045f ? 1.0f / 12.92f : 2.4f / 1.055f * ngp_powf((s + 0.055f) / 1.055f, 1.4f); }   /* common_device.cuh:71-77 */
 static float linear_to_srgb(float l) { return l < 0.0031308f ? 12.92f * l : 1.055f * ngp_powf(l, 0.41666f) - 0.055f; }
 /* ngp_detmath.h itself, element-wise: the header is shared by this oracle and the CUDA product, so it is checked against libm on its own
  * (tests/test_detmath.py) — a bug in it would be invisible to every CUDA-vs-oracle comparison.  which: 0 log, 1 exp, 2 pow(x, y) */
@@ -520,6 +521,15 @@ EXPORT uint32_t orc_compute_loss(uint32_t n_rays_kept, uint32_t n_rays_global, u
 		if (cfg->random_bg_color) { bg.x = pcg_next_float(&rng); bg.y = pcg_next_float(&rng); bg.z = pcg_next_float(&rng); }
 		bg = V(srgb_to_linear(bg.x), srgb_to_linear(bg.y), srgb_to_linear(bg.z));
 		rgba_t tex = read_rgba_uv(u, v, vw->width, vw->height, vw->pixels, vw->image_type);
+		/* per-image exposure (testbed_nerf.cu:979): the view's colour times 2^exposure, channel by channel */
+		v3 exposure_scale = V(1.0f, 1.0f, 1.0f);
+		if (cfg->cam_exposure) {
+			exposure_scale = V(ngp_expf(0.6931471805599453f * cfg->cam_exposure[img * 3 + 0]), ngp_expf(0.6931471805599453f * cfg->cam_exposure[img * 3 + 1]),
+				ngp_expf(0.6931471805599453f * cfg->cam_exposure[img * 3 + 2]));
+			tex.r = exposure_scale.x * tex.r;
+			tex.g = exposure_scale.y * tex.g;
+			tex.b = exposure_scale.z * tex.b;
+		}
 		v3 target;
 		if (cfg->linear_colors || cfg->color_space == NGP_COLOR_LINEAR) {
 			target = V(tex.r + (1.0f - tex.a) * bg.x, tex.g + (1.0f - tex.a) * bg.y, tex.b + (1.0f - tex.a) * bg.z);
@@ -582,6 +592,14 @@ EXPORT uint32_t orc_compute_loss(uint32_t n_rays_kept, uint32_t n_rays_global, u
 		if (loss_output) loss_output[i] = mean_loss / (float)n_rays_global;
 
 		float loss_scale = cfg->loss_scale / (float)n_rays_global;
+		if (cfg->cam_exposure_gradient) {   /* testbed_nerf.cu:1142-1155 */
+			v3 dgt = V(-g.x, -g.y, -g.z);
+			if (!cfg->linear_colors) dgt = V(dgt.x / srgb_to_linear_derivative(target.x), dgt.y / srgb_to_linear_derivative(target.y), dgt.z / srgb_to_linear_derivative(target.z));
+			float* eg = cfg->cam_exposure_gradient + (size_t)img * 3;
+			eg[0] += ((loss_scale * dgt.x) * exposure_scale.x) * 0.6931471805599453f;
+			eg[1] += ((loss_scale * dgt.y) * exposure_scale.y) * 0.6931471805599453f;
+			eg[2] += ((loss_scale * dgt.z) * exposure_scale.z) * 0.6931471805599453f;
+		}
 		const float output_l2_reg = cfg->rgb_activation == NGP_ACT_EXPONENTIAL ? 1e-4f : 0.0f;
 		const float output_l1_reg_density = (!rtc && mean_density < MIN_OPTICAL_THICKNESS) ? 1e-4f : 0.0f;
 		float* co = coords_out + (size_t)compacted_base * 7;

@@ -233,6 +233,54 @@ def _run_loss(lib, ctx, got, net_out_dev, batch, order, n_rays):
                 loss=t_loss.cpu().numpy()[:k])
 
 
+def test_per_image_exposure_matches_oracle(lib):
+    """ngp_nerf_train_cfg.cam_exposure / cam_exposure_gradient (testbed_nerf.cu:979-995, 1142-1155): targets, and with them every sample
+    gradient, bit-exact against the oracle; the per-view accumulators to float-atomics order"""
+    import torch
+
+    n_rays, max_samples = 2048, 2048 * 1024
+    want, got, ctx = run_generator(lib, SCENES[1], n_rays, max_samples)
+    k = got["n_kept"]
+    n_views = len(ctx["views"])
+    rng = np.random.default_rng(9)
+    net_out = np.zeros((max_samples, 4), dtype=np.float16)
+    net_out[:, 0:3] = rng.normal(0, 1.5, size=(max_samples, 3)).astype(np.float16)
+    net_out[:, 3] = rng.normal(1.0, 2.5, size=max_samples).astype(np.float16)
+    expo = rng.uniform(-1.0, 1.0, size=(n_views, 3)).astype(np.float32)
+    batch = 1 << int(np.ceil(np.log2(max(got["n_samples"], 2))))
+    cfg = ctx["cfg"]
+    cfg.compaction_order = 1    # one kernel; the oracle hands slots out in ray-slot order, outputs are compared ray by ray
+    for linear_colors in (0, 1):
+        cfg.linear_colors = linear_colors
+        # oracle (host pointers)
+        grad_w = np.zeros((n_views, 3), dtype=np.float32)
+        cfg.cam_exposure, cfg.cam_exposure_gradient = expo.ctypes.data, grad_w.ctypes.data
+        ns_host = got["numsteps"][:k].copy()
+        co_w = np.zeros((batch, 7), dtype=np.float32)
+        dl_w = np.zeros((batch, 4), dtype=np.float16)
+        loss_w = np.zeros(n_rays, dtype=np.float32)
+        M.lib().orc_compute_loss(k, n_rays, ctx["rng"][0], ctx["rng"][1], C.byref(cfg), C.addressof(ctx["views"]), n_views, net_out.ctypes.data, batch,
+                                 got["ray_indices"].ctypes.data, got["rays"].ctypes.data, ns_host.ctypes.data, got["coords"].ctypes.data, co_w.ctypes.data, dl_w.ctypes.data,
+                                 loss_w.ctypes.data, np.float32(0.02))
+        # library (device pointers)
+        t_expo, t_grad = dev(expo), torch.zeros(n_views, 3, dtype=torch.float32, device="cuda")
+        cfg.cam_exposure, cfg.cam_exposure_gradient = t_expo.data_ptr(), t_grad.data_ptr()
+        r = _run_loss(lib, ctx, got, dev(net_out), batch, 1, n_rays)
+        assert np.array_equal(r["ns"][:, 0], ns_host[:, 0])
+        assert r["loss"].tobytes() == loss_w[:k].tobytes()
+        for i in range(0, k, 5):
+            n_i, gb, wb = int(r["ns"][i, 0]), int(r["ns"][i, 1]), int(ns_host[i, 1])
+            assert r["dl"][gb:gb + n_i].tobytes() == dl_w[wb:wb + n_i].tobytes(), f"ray slot {i}"
+        g = t_grad.cpu().numpy()
+        assert np.abs(grad_w).max() > 0 and np.allclose(g, grad_w, rtol=2e-4, atol=1e-5 * np.abs(grad_w).max())
+        # exposure without an accumulator: same gradients, accumulator untouched
+        t_grad.zero_()
+        cfg.cam_exposure_gradient = None
+        r2 = _run_loss(lib, ctx, got, dev(net_out), batch, 1, n_rays)
+        assert r2["dl"].tobytes() == r["dl"].tobytes() and not t_grad.cpu().numpy().any()
+    cfg.cam_exposure, cfg.cam_exposure_gradient = None, None
+
+
 def test_compaction_orders(lib):
     """ngp_nerf_train_cfg.compaction_order decides where a ray's samples go in the compacted batch — and with it which rays an overfull
     batch cuts — not what they are: groups of 32 consecutive rays (the default), one atomic per ray, ascending ray id."""
