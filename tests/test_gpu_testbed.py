@@ -360,33 +360,39 @@ def test_the_reference_serializer_stack_reads_our_snapshot(trained, tmp_path):
 
 
 def test_optimize_exposure_finds_the_darkened_views():
-    """Nerf::Training::optimize_exposure (testbed_nerf.cu:2962-3000): a view's colour is multiplied by 2^exposure before it becomes the target, so
-    views whose colours were halved are pulled up towards one stop above the others; the exposures stay zero-mean, and nothing moves while the
-    option is off"""
+    """Nerf::Training::optimize_exposure (testbed_nerf.cu:2962-3000).  A view's colour is multiplied by 2^exposure before it becomes the target.
+    A model trained on the clean views is frozen, three views are then replaced by half-bright copies: their exposures must rise towards one
+    stop above the others' (with the network free to move, its view dependence simply absorbs a darker view and there is nothing left for the
+    exposure to explain).  The exposures stay zero-mean, and nothing moves while the option is off."""
     P = util.pkg()
     tb = P.Testbed()
-    imgs, cams, focal = S.make_dataset(n_images=16, width=96, height=96)
-    dark = [3, 8, 12]
-    imgs = imgs.copy()
-    for i in dark:
-        imgs[i, ..., :3] *= 0.5
+    # a narrow field of view: the ball fills the frame, every pixel carries colour
+    imgs, cams, focal = S.make_dataset(n_images=16, width=96, height=96, fov_deg=16.0)
+    assert imgs[..., 3].min() > 0.99
     S.load_into_testbed(tb, imgs, cams, focal, aabb_scale=1)
     tb.reload_network_from_json(S.base_config(16, 2, 16))
-    for _ in range(32):
+    for _ in range(300):
         tb.train(1 << 15)
     assert not any(tb.nerf.training.camera_exposure(i).any() for i in range(16))
+    dark = [3, 8, 12]
+    others = [i for i in range(16) if i not in dark]
+    for i in dark:
+        half = imgs[i].copy()
+        half[..., :3] *= 0.5
+        tb.nerf.training.set_image(i, half)
+    tb._set("train_network", 0)
+    tb._set("train_encoding", 0)
     tb.nerf.training.optimize_exposure = True
     tb.nerf.training.n_steps_between_cam_updates = 2     # one Adam step of at most ~1e-2 stops per update: 16 (the default) would need thousands of steps
     assert tb.nerf.training.optimize_exposure is True
-    for _ in range(500):
+    for _ in range(400):
         tb.train(1 << 15)
     e = np.stack([tb.nerf.training.camera_exposure(i) for i in range(16)])
     assert np.isfinite(e).all() and np.abs(e.mean(0)).max() < 1e-5
-    others = [i for i in range(16) if i not in dark]
     gap = e[dark].mean() - e[others].mean()
     print("exposures (mean over channels):", np.round(e.mean(1), 3), "gap", gap)
     assert e[dark].mean(1).min() > e[others].mean(1).max()
-    assert 0.3 < gap < 1.5          # towards one stop
+    assert 0.5 < gap < 1.3          # one stop
     # a set value restarts that view's optimizer and is applied
     tb.nerf.training.set_camera_exposure(0, [0.25, 0.25, 0.25])
     assert np.allclose(tb.nerf.training.camera_exposure(0), 0.25)
