@@ -222,6 +222,15 @@ struct ngp_testbed {
 	std::vector<ExposureAdam> cam_exposure;
 	DevBuf<float> cam_exposure_dev, cam_exposure_gradient_dev;
 	bool cam_exposure_nonzero = false;
+	// update_image_async: the host-to-device copy of a replacement frame runs on its own stream into one of two staging buffers, beside
+	// whatever the training stream is doing; the training stream picks it up (a device-to-device copy) right before the loss kernel, the
+	// first reader of the pixels of a view without masked pixels (tb_apply_pending_images)
+	struct ImageStaging { void* buf = nullptr; size_t cap = 0; cudaEvent_t copied = nullptr, consumed = nullptr; bool in_flight = false; };
+	struct PendingImage { uint32_t idx, slot; size_t bytes; };
+	cudaStream_t copy_stream = nullptr;
+	ImageStaging staging[2];
+	uint32_t staging_next = 0;
+	std::vector<PendingImage> pending_images;
 
 	// per-step scratch.  Everything the sample generator writes exists twice: while step k trains, the generator of step
 	// k+1 already runs on a side stream into the other set (it depends only on the occupancy bitfield, the RNG and
@@ -291,6 +300,15 @@ struct ngp_testbed {
 		for (cudaEvent_t e : {ev_front_done, ev_prefetch_done, ev_main_ready, ev_back_done, ev_counters_ready})
 			if (e) cudaEventDestroy(e);
 		if (readback) cudaFreeHost(readback);
+		if (copy_stream) {
+			cudaStreamSynchronize(copy_stream);
+			cudaStreamDestroy(copy_stream);
+		}
+		for (ImageStaging& st : staging) {
+			if (st.buf) cudaFree(st.buf);
+			if (st.copied) cudaEventDestroy(st.copied);
+			if (st.consumed) cudaEventDestroy(st.consumed);
+		}
 		for (void* p : pixel_bufs)
 			if (p) cudaFree(p);
 	}
@@ -585,6 +603,19 @@ static void tb_launch_generator(ngp_testbed* t, cudaStream_t stream, uint32_t se
 		t->bitfield.p, max_inference, rs.counters.p, rs.ray_indices.p, rs.rays.p, rs.numsteps.p, rs.coords.p);
 }
 
+// Replacement frames handed over by ngp_testbed_update_image_async become visible to `stream` here: wait for each frame's staging copy,
+// move it into the view's pixel buffer, release the staging buffer.
+static void tb_apply_pending_images(ngp_testbed* t, cudaStream_t stream) {
+	for (const ngp_testbed::PendingImage& pi : t->pending_images) {
+		ngp_testbed::ImageStaging& st = t->staging[pi.slot];
+		NGPB_CUDA_CHECK(cudaStreamWaitEvent(stream, st.copied, 0));
+		NGPB_CUDA_CHECK(cudaMemcpyAsync(t->pixel_bufs[pi.idx], st.buf, pi.bytes, cudaMemcpyDeviceToDevice, stream));
+		NGPB_CUDA_CHECK(cudaEventRecord(st.consumed, stream));
+		st.in_flight = false;
+	}
+	t->pending_images.clear();
+}
+
 // Per-image exposure (testbed_nerf.cu:979, 1142-1155, 2962-3000).  The loss kernel multiplies a view's colour by 2^exposure and, while
 // `optimize_exposure` is on, accumulates the reference's gradient expression per view; every n_steps_between_cam_updates steps the host
 // takes one Adam step per view with the network optimizer's current learning rate and re-centres the exposures on a zero mean.
@@ -717,6 +748,7 @@ static void tb_front(ngp_testbed* t, uint32_t batch) {
 				t->cfg.density_activation, t->mlp_out.p, tb_inference_chunk(t), t->cfg.train_mode);
 		}
 	}
+	tb_apply_pending_images(t, t->stream);   // frames streamed in by update_image_async: first read by the loss kernel
 	{
 		PhaseTimer pt(t, 3);
 		compute_loss(t->stream, rays_local, rays_global, t->rng.state, t->rng.inc, t->cfg, t->views_dev.p, tb_n_views(t), t->mlp_out.p, batch, rs.counters.p,
@@ -990,6 +1022,8 @@ void ngp_testbed_destroy(ngp_testbed* t) {
 int ngp_testbed_create_empty_nerf_dataset(ngp_testbed* t, uint32_t n_images, uint32_t aabb_scale) {
 	NGPB_TRY({
 		tb_invalidate_prefetch(t);
+		tb_apply_pending_images(t, t->stream);
+		NGPB_CUDA_CHECK(cudaStreamSynchronize(t->stream));   // the pixel buffers are freed below
 		NGPB_CHECK(n_images > 0, "create_empty_nerf_dataset: n_images must be > 0");
 		NGPB_CHECK(aabb_scale >= 1 && aabb_scale <= 128 && (aabb_scale & (aabb_scale - 1)) == 0, "aabb_scale must be a power of two in [1, 128]");
 		for (void* p : t->pixel_bufs)
@@ -1012,6 +1046,10 @@ int ngp_testbed_create_empty_nerf_dataset(ngp_testbed* t, uint32_t n_images, uin
 int ngp_testbed_set_image(ngp_testbed* t, uint32_t idx, const float* rgba_host, int32_t w, int32_t h) {
 	NGPB_TRY({
 		tb_invalidate_prefetch(t);
+		if (!t->pending_images.empty()) {   // a streamed-in frame still on its way: land it before the buffer it targets may be freed
+			tb_apply_pending_images(t, t->stream);
+			NGPB_CUDA_CHECK(cudaStreamSynchronize(t->stream));
+		}
 		NGPB_CHECK(idx < t->n_images, "Invalid frame index");
 		NGPB_CHECK(w > 0 && h > 0, "image must have positive size");
 		if (t->pixel_bufs[idx]) cudaFree(t->pixel_bufs[idx]);
@@ -1036,6 +1074,10 @@ int ngp_testbed_set_image(ngp_testbed* t, uint32_t idx, const float* rgba_host, 
 int ngp_testbed_set_image_bytes(ngp_testbed* t, uint32_t idx, const uint8_t* rgba8_host, int32_t w, int32_t h) {
 	NGPB_TRY({
 		tb_invalidate_prefetch(t);
+		if (!t->pending_images.empty()) {   // a streamed-in frame still on its way: land it before the buffer it targets may be freed
+			tb_apply_pending_images(t, t->stream);
+			NGPB_CUDA_CHECK(cudaStreamSynchronize(t->stream));
+		}
 		NGPB_CHECK(idx < t->n_images, "Invalid frame index");
 		NGPB_CHECK(w > 0 && h > 0, "image must have positive size");
 		if (t->pixel_bufs[idx]) cudaFree(t->pixel_bufs[idx]);
@@ -2020,14 +2062,47 @@ int ngp_testbed_update_image_async(ngp_testbed* t, uint32_t idx, const void* rgb
 	NGPB_TRY({
 		NGPB_CHECK(idx < t->n_images && t->pixel_bufs[idx], "update_image_async: image slot was never set");
 		const ngp_train_view& v = t->views[idx];
-		// The sample generator looks at pixels only to skip masked ones.  A view registered without masked pixels
-		// (no_mask, established by set_image) promises that replacement frames have none either, so a generator launch
-		// already in flight for the next step stays valid; otherwise it is discarded.
-		if (!v.no_mask) tb_invalidate_prefetch(t);
 		const size_t px_bytes = v.image_type == NGP_IMAGE_BYTE ? 4 : (v.image_type == NGP_IMAGE_HALF ? 8 : 16);
-		NGPB_CUDA_CHECK(cudaMemcpyAsync(t->pixel_bufs[idx], rgba_host, (size_t)v.width * v.height * px_bytes, cudaMemcpyHostToDevice, t->stream));
+		const size_t bytes = (size_t)v.width * v.height * px_bytes;
+		if (!v.no_mask) {
+			// The sample generator looks at pixels only to skip masked ones.  A view that may contain masked pixels is replaced in stream order,
+			// ahead of the generator, and a generator launch already in flight for the next step is discarded.
+			tb_invalidate_prefetch(t);
+			tb_apply_pending_images(t, t->stream);
+			NGPB_CUDA_CHECK(cudaMemcpyAsync(t->pixel_bufs[idx], rgba_host, bytes, cudaMemcpyHostToDevice, t->stream));
+			return 0;
+		}
+		// A view registered without masked pixels (no_mask, established by set_image) promises that replacement frames have none either: its
+		// pixels are first read by the loss kernel.  The upload runs on the copy stream into a staging buffer — beside the optimizer of the
+		// step before and the generator / inference of this one — and tb_front moves it into place right before the loss kernel.
+		if (!t->copy_stream) NGPB_CUDA_CHECK(cudaStreamCreateWithFlags(&t->copy_stream, cudaStreamNonBlocking));
+		const uint32_t slot = t->staging_next++ & 1u;
+		ngp_testbed::ImageStaging& st = t->staging[slot];
+		if (st.in_flight) tb_apply_pending_images(t, t->stream);   // more than two frames between training steps: land the earlier ones now
+		if (!st.copied) {
+			NGPB_CUDA_CHECK(cudaEventCreateWithFlags(&st.copied, cudaEventDisableTiming));
+			NGPB_CUDA_CHECK(cudaEventCreateWithFlags(&st.consumed, cudaEventDisableTiming));
+			NGPB_CUDA_CHECK(cudaEventRecord(st.consumed, t->stream));
+		}
+		if (st.cap < bytes) {
+			NGPB_CUDA_CHECK(cudaStreamSynchronize(t->stream));   // the staging buffer's last reader
+			if (st.buf) NGPB_CUDA_CHECK(cudaFree(st.buf));
+			st.buf = nullptr;
+			NGPB_CUDA_CHECK(cudaMalloc(&st.buf, bytes));
+			st.cap = bytes;
+		}
+		NGPB_CUDA_CHECK(cudaStreamWaitEvent(t->copy_stream, st.consumed, 0));   // the previous frame in this buffer has been moved out
+		NGPB_CUDA_CHECK(cudaMemcpyAsync(st.buf, rgba_host, bytes, cudaMemcpyHostToDevice, t->copy_stream));
+		NGPB_CUDA_CHECK(cudaEventRecord(st.copied, t->copy_stream));
+		st.in_flight = true;
+		t->pending_images.push_back(ngp_testbed::PendingImage{idx, slot, bytes});
 	});
 }
-int ngp_testbed_sync(ngp_testbed* t) { NGPB_TRY(NGPB_CUDA_CHECK(cudaStreamSynchronize(t->stream))); }
+int ngp_testbed_sync(ngp_testbed* t) {
+	NGPB_TRY({
+		tb_apply_pending_images(t, t->stream);
+		NGPB_CUDA_CHECK(cudaStreamSynchronize(t->stream));
+	});
+}
 
 }  // extern "C"

@@ -404,6 +404,58 @@ def test_optimize_exposure_finds_the_darkened_views():
     assert np.isfinite(tb.loss)
 
 
+def test_update_image_async_lands_before_the_loss_kernel():
+    """ngp_testbed_update_image_async: a replacement frame of a view without masked pixels is uploaded on a copy stream into a staging buffer
+    and moved into the view's pixel buffer right before the next step's loss kernel (or by sync()); frames land in call order, also when more
+    of them are queued than there are staging buffers"""
+    import ctypes as C
+
+    import torch
+
+    P = util.pkg()
+    B = importlib.import_module("instant-ngp_b200.binding")
+    cudart = C.CDLL("/usr/local/cuda/lib64/libcudart.so")
+    cudart.cudaMemcpy.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]
+    tb = P.Testbed()
+    imgs, cams, focal = S.make_dataset(n_images=6, width=64, height=64)
+    S.load_into_testbed(tb, imgs, cams, focal, aabb_scale=1)
+    tb.reload_network_from_json(S.base_config(16, 2, 15))
+
+    def device_pixels(i):
+        v = B.TrainView()
+        B.check(B.lib().ngp_testbed_get_view(tb._h, i, C.byref(v)))
+        out = np.empty((64, 64, 4), dtype=np.float32)
+        assert cudart.cudaMemcpy(out.ctypes.data, C.c_void_p(v.pixels), out.nbytes, 2) == 0
+        return out
+
+    for _ in range(3):
+        tb.train(1 << 14)
+    rng = np.random.default_rng(3)
+    frames = [torch.from_numpy(np.ascontiguousarray(rng.uniform(0.0, 1.0, size=(64, 64, 4)).astype(np.float32))).pin_memory() for _ in range(5)]
+    # one frame, one training step
+    tb.update_image_async(2, frames[0].data_ptr())
+    tb.train(1 << 14)
+    tb.sync()
+    assert np.array_equal(device_pixels(2), frames[0].numpy())
+    # a frame per step, views in turn
+    last = {2: 0}
+    for k in range(25):
+        f, view = k % 5, (k * 5) % 6
+        tb.update_image_async(view, frames[f].data_ptr())
+        last[view] = f
+        tb.train(1 << 14)
+    tb.sync()
+    for view, f in last.items():
+        assert np.array_equal(device_pixels(view), frames[f].numpy()), view
+    # four frames queued without a step in between (two staging buffers), the same view twice: the later frame wins
+    for k, (view, f) in enumerate([(0, 1), (1, 2), (0, 3), (4, 4)]):
+        tb.update_image_async(view, frames[f].data_ptr())
+    tb.sync()
+    assert np.array_equal(device_pixels(0), frames[3].numpy()) and np.array_equal(device_pixels(1), frames[2].numpy()) and np.array_equal(device_pixels(4), frames[4].numpy())
+    tb.train(1 << 14)
+    assert np.isfinite(tb.loss)
+
+
 def test_errors_are_reported(trained):
     P = util.pkg()
     tb = P.Testbed()
