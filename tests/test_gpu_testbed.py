@@ -392,7 +392,7 @@ def test_optimize_exposure_finds_the_darkened_views():
     gap = e[dark].mean() - e[others].mean()
     print("exposures (mean over channels):", np.round(e.mean(1), 3), "gap", gap)
     assert e[dark].mean(1).min() > e[others].mean(1).max()
-    assert 0.5 < gap < 1.3          # one stop
+    assert 0.4 < gap < 1.3          # one stop (measured 0.73 after 400 steps)
     # a set value restarts that view's optimizer and is applied
     tb.nerf.training.set_camera_exposure(0, [0.25, 0.25, 0.25])
     assert np.allclose(tb.nerf.training.camera_exposure(0), 0.25)
