@@ -14,15 +14,17 @@ generation + marching, inference, loss + compaction, fused forward/backward, opt
 
 value  : compacted samples trained per second, all ranks, dataset resident in HBM (device-timed with CUDA events).
 e2e    : the same through the public pyngp-style API while one training image per step is streamed from pinned host
-         memory (H2D inside the timed region) and the step's counters + loss are read back (D2H).
+         memory (H2D inside the timed region: update_image_async uploads on a copy stream into a staging buffer and the training
+         stream moves the frame into place before the loss kernel) and the step's counters + loss are read back (D2H).
 timing : steady state — 700 untimed set-up steps (--pretrain) + W warm-up steps come first: the per-step workload (rays per batch,
          samples per ray) only settles once the scene has formed (SURVEY §8d asks for steps 500-1000); then exactly K timed steps.
 extras : roofline (k_nerf_train), cpu_baseline (oracle port, rank 0, N = 1), clocks (NVML during the timed region), render
          (1920x1080 Mrays/s), quality (PSNR of the trained model), phase_ms_per_step (CUDA events per phase, separate pass),
          reference_gpu (the UNMODIFIED reference application, baseline/_ref/pyngp*.so, driven by tools/ref_app.py on the same
          box, same scene, same protocol, in a subprocess after this arm's timing; N = 1 only).
-N > 1  : weak scaling — every rank trains its own 2^18-sample batch on its shard of the global ray batch; one
-         torch.distributed (NCCL) all-reduce of the flat fp16 gradient buffer per step.
+N > 1  : weak scaling — every rank trains its own 2^18-sample batch on its (interleaved) shard of the global ray batch; the all-reduce of the
+         flat fp16 gradient buffer and of the counter block happen inside Testbed.train over NCCL (ngp_testbed_init_dp); torch.distributed only
+         hands the NCCL ids to the ranks and takes the max over ranks of the timings.
 """
 from __future__ import annotations
 
@@ -554,7 +556,9 @@ def main() -> None:
                        "l2_policy": "inputs larger than L2: %.2f GB image set + 340 MB parameter/optimizer state per step, no explicit flush" % (sum(x.numel() * x.element_size() for x in pinned) / 1e9),
                        "parallelism": f"dp{world}", "pretrain_steps": args.pretrain,
                        "timed_steps": f"{args.pretrain + args.warmup}..{args.pretrain + args.warmup + args.steps} of a from-scratch training run",
-                       "march_arithmetic": "reference build (--use_fast_math expression trees, march_ref.cu)" if tb._get("nerf.training.math_mode") == 1 else "deterministic (ngp_detmath.h)"},
+                       "march_arithmetic": "reference build (--use_fast_math expression trees, march_ref.cu)" if tb._get("nerf.training.math_mode") == 1 else "deterministic (ngp_detmath.h)",
+                       "compaction_order": {0: "groups of 32 consecutive rays, shuffled per step", 1: "one atomic per ray", 2: "ascending ray id"}.get(int(tb._get("nerf.training.compaction_order")), "?"),
+                       "e2e_upload": "copy stream -> staging buffer -> pixel buffer before the loss kernel (update_image_async)"},
             "rays_per_sec": rays / (ms_total * 1e-3),
             "per_step": {"rays": rays / args.steps / world, "samples_before_compaction": pre / args.steps / world, "samples_compacted": samples / args.steps / world},
             "phase_ms_per_step": {k: v / n_fb for k, v in phases.items() if k != "steps"},
