@@ -523,7 +523,7 @@ int ngp_testbed_set_profiling(ngp_testbed* t, int enable);
 int ngp_testbed_get_phase_ms(ngp_testbed* t, float* ms_out, uint32_t* n_steps);
 /* Streaming data: overwrite training image `idx` (already set once with ngp_testbed_set_image / _set_image_bytes, same size and
  * pixel type: 16 or 4 bytes per pixel) from a host buffer, asynchronously (pinned memory makes the copy truly asynchronous; the
- * buffer must stay valid until the next training step has been issued or ngp_testbed_sync has returned).  A view without masked
+ * buffer must stay valid until the next training step has finished on the device or ngp_testbed_sync has returned).  A view without masked
  * pixels is uploaded on a copy stream of the Testbed's own into a staging buffer, beside whatever the Testbed stream is doing, and
  * becomes visible right before the next training step's loss kernel — the first reader of its pixels — or at ngp_testbed_sync;
  * frames land in call order.  A view that may contain masked pixels (the sample generator reads those) is replaced in stream order. */
